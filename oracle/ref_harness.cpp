@@ -191,12 +191,16 @@ void* ref_mcts_new(void* state, int sims, float cpuct, int virtual_loss, int eva
     // useBatchedMCTS stays false) BatchQueue.  Keep it false here: plain serial path.
     cfg.useBatchInference = false; cfg.useBatchedMCTS = false;
     r->mcts.reset(new alphazero::mcts::ParallelMCTS(*(IGameState*)state, cfg, r->nn.get(), r->tt.get()));
+    // Deterministic mode AFTER construction (parallel_mcts.cpp:1263-1274): flips useBatchInference so
+    // selectAction takes its first-max / argmax branches (:1018-1021, :1037-1039) — the behaviour
+    // SelfPlayManager forces (self_play_manager.cpp:169) — without creating a BatchQueue, so search()
+    // stays on the serial runSingleSimulation path.  It also stops the dtor deleting our TT (:105-109).
+    r->mcts->setDeterministicMode(true);
     return r;
 }
 void ref_mcts_free(void* h) {
     auto* r = (RefMcts*)h;
-    // reference dtor deletes a caller-supplied TT when !useBatchInference (parallel_mcts.cpp:105-109)
-    r->tt.release();
+    r->mcts.reset();   // before the TT and evaluator it points at
     delete r;
 }
 void ref_mcts_search(void* h) { ((RefMcts*)h)->mcts->search(); }
