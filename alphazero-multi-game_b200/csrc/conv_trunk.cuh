@@ -1,0 +1,58 @@
+// conv_trunk.cuh — 3x3 convolution (+ folded BatchNorm bias, residual add, ReLU) as an implicit GEMM on
+// tcgen05 tensor cores, operands staged in shared memory by TMA bulk copies, accumulators in TMEM.
+//
+// Replaces: the cuDNN convolutions behind torch::jit forward (reference src/nn/torch_neural_network.cpp:187,273)
+// for the residual trunk of SURVEY.md §8a N1b.
+//
+// Layout ("padded position stream"): activations live in HBM as  act[C/8][p_total][8]  bf16.  A row is one
+// board cell; a board of H x W cells occupies (H+1)*(W+1) consecutive rows with row pitch W+1 — column W and
+// row H are permanent zeros — and boards follow each other back to back, with `guard` zero rows before the
+// first and after the last.  The zero column/row give every cell its 3x3 zero padding for free: tap (ky,kx) of
+// output row r reads input row r + (ky-1)*(W+1) + (kx-1).  So for one tap the A operand of the GEMM
+// (M = 128 consecutive cells, K = 16 channels) is the SAME shared-memory tile at a shifted start address:
+// no im2col, no duplicated data, one TMA load per (channel chunk, work item).
+//
+// Shared-memory operand format: K-major, SWIZZLE_NONE core matrices (8 rows x 16 bytes contiguous).  With
+// act[c/8][row][c%8] every 8 consecutive rows of one channel chunk ARE a core matrix, wherever the start row
+// is, which is what makes the shifted-address trick legal (SBO = 128 B, LBO = bytes per channel-chunk plane).
+//
+// Work item: BM = 256 consecutive rows (two UMMA M=128 tiles; for 15x15 Gomoku exactly one board).
+// Per item: 9 taps x CIN/16 K-steps x 2 M-tiles tcgen05.mma (128x128x16) into two 128-column TMEM accumulators;
+// accumulators are double-buffered (4 x 128 = 512 TMEM columns) so the epilogue of item i overlaps the MMAs
+// of item i+1.  Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
+// warp 5 MMA issuer + TMEM allocator.  Persistent: grid = #SMs, items strided by gridDim.x.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace az { namespace nn {
+
+constexpr int CONV_BM = 256;        // rows per work item
+constexpr int CONV_HALO = 24;       // max |tap shift| supported = W + 2 <= 24  (W <= 22)
+constexpr int CONV_GUARD = 32;      // zero rows before/after the board stream (>= CONV_HALO)
+constexpr int CONV_COUT = 128;
+constexpr int CONV_THREADS = 192;
+
+struct ConvParams {
+    const __nv_bfloat16* in;        // [CIN/8][p_total][8]
+    __nv_bfloat16* out;             // [COUT/8][p_total][8]
+    const __nv_bfloat16* resid;     // same layout as out, or nullptr
+    const __nv_bfloat16* w;         // weight image, see conv_weight_image()
+    const float* bias;              // [COUT] folded BatchNorm shift
+    const uint8_t* rowvalid;        // [p_total] 1 = real board cell, 0 = padding row
+    const int* n_boards_dev;        // optional: rows to process = *n_boards_dev * board_pitch
+    int n_rows;                     // rows to process when n_boards_dev == nullptr
+    int board_pitch;                // rows per board (H+1)*(W+1)
+    int p_total;                    // rows per channel-chunk plane
+    int row_pitch;                  // W + 1
+    int relu;
+};
+
+size_t conv_smem_bytes(int cin);
+// launches on `stream`; cin in {16, 128}; returns cudaError_t as int
+int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream);
+// element index of weight (tap, cin, cout) inside the image for a layer with `cin` input channels
+size_t conv_weight_index(int cin_total, int tap, int ci, int co);
+size_t conv_weight_elems(int cin_total);
+
+}}  // namespace az::nn

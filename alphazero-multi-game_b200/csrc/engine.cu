@@ -1,0 +1,639 @@
+// engine.cu — host side of the batched self-play engine + its C ABI (include/az_b200.h).
+//
+// The host owns no search logic: it allocates the pools, launches the wave kernels in order
+// (select → evaluator → expand/backup) and the per-move kernels (choose → re-root → game turnover),
+// and moves results across the ABI.  Reference counterparts: ParallelMCTS (src/mcts/parallel_mcts.cpp),
+// SelfPlayManager (src/selfplay/self_play_manager.cpp), TorchNeuralNetwork (src/nn/torch_neural_network.cpp).
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+#include <cmath>
+#include <algorithm>
+#include <unordered_set>
+
+#include "../../include/az_b200.h"
+#include "common.cuh"
+
+namespace az {
+static thread_local std::string g_error;
+void set_error(const std::string& s) { g_error = s; }
+}  // namespace az
+
+#include "gomoku.cuh"
+#include "tree_kernels.cuh"
+#include "conv_trunk.cuh"
+#include "heads.cuh"
+
+namespace az {
+
+#define AZ_CHECK(cond, msg) do { if (!(cond)) { set_error(std::string(msg)); return -1; } } while (0)
+#define AZ_LAUNCH_CHECK() AZ_CUDA_CHECK(cudaGetLastError())
+
+template <class T>
+static int dev_alloc(T** p, size_t n) { AZ_CUDA_CHECK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T))); return 0; }
+
+// ------------------------------------------------------------------------------------------------ network
+struct NetWeights {            // device images
+    std::vector<__nv_bfloat16*> conv_w;   // stem + 2*blocks
+    std::vector<float*> conv_b;
+    float *w1x1 = nullptr, *b1x1 = nullptr, *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;
+};
+
+struct Net {
+    int blocks = 0, C = 0, in_planes = 0, H = 0, W = 0, A = 0, PH = 0, PW = 0, feat = 0;
+    int row_pitch = 0, board_pitch = 0, p_total = 0, max_boards = 0;
+    bool loaded = false;
+    NetWeights w;
+    __nv_bfloat16 *in16 = nullptr, *X = nullptr, *Y = nullptr;
+    uint8_t* rowvalid = nullptr;
+    float *featbuf = nullptr, *logits = nullptr, *hidden = nullptr;
+    int n_sms = 148;
+    unsigned long long launches = 0;
+
+    int init(int H_, int W_, int A_, int max_boards_, int channels) {
+        H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
+        row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
+        AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
+        AZ_CHECK(channels == nn::CONV_COUT, "conv trunk is built for 128 channels");
+        const size_t rows = (size_t)max_boards * board_pitch;
+        p_total = (int)(nn::CONV_GUARD + (rows + nn::CONV_BM - 1) / nn::CONV_BM * nn::CONV_BM + nn::CONV_GUARD);
+        PH = std::min(8, H); PW = std::min(8, W); feat = 32 * PH * PW;
+        if (dev_alloc(&in16, (size_t)2 * p_total * 8)) return -1;
+        if (dev_alloc(&X, (size_t)(C / 8) * p_total * 8)) return -1;
+        if (dev_alloc(&Y, (size_t)(C / 8) * p_total * 8)) return -1;
+        AZ_CUDA_CHECK(cudaMemset(in16, 0, (size_t)2 * p_total * 16));
+        AZ_CUDA_CHECK(cudaMemset(X, 0, (size_t)(C / 8) * p_total * 16));
+        AZ_CUDA_CHECK(cudaMemset(Y, 0, (size_t)(C / 8) * p_total * 16));
+        std::vector<uint8_t> rv(p_total, 0);
+        for (int b = 0; b < max_boards; ++b)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) rv[nn::CONV_GUARD + (size_t)b * board_pitch + y * row_pitch + x] = 1;
+        if (dev_alloc(&rowvalid, (size_t)p_total)) return -1;
+        AZ_CUDA_CHECK(cudaMemcpy(rowvalid, rv.data(), p_total, cudaMemcpyHostToDevice));
+        if (dev_alloc(&featbuf, (size_t)max_boards * 2 * feat)) return -1;
+        if (dev_alloc(&logits, (size_t)max_boards * A)) return -1;
+        if (dev_alloc(&hidden, (size_t)max_boards * 256)) return -1;
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        return 0;
+    }
+
+    // AZW1 blob: header + fp32 tensors (net.py:export_weights).  Folds eval-mode BatchNorm
+    // (scale = gamma / sqrt(var + 1e-5), shift = beta - mean * scale) into weights / bias here.
+    int load(const void* blob, size_t bytes) {
+        struct Hdr { char magic[4]; int32_t version, blocks, channels, in_planes, H, W, actions; };
+        AZ_CHECK(bytes >= sizeof(Hdr), "weight blob too small");
+        const Hdr* h = (const Hdr*)blob;
+        AZ_CHECK(std::memcmp(h->magic, "AZW1", 4) == 0 && h->version == 1, "bad weight blob magic/version");
+        AZ_CHECK(h->channels == C && h->H == H && h->W == W && h->actions == A, "weight blob does not match engine config");
+        AZ_CHECK(h->in_planes <= 16, "at most 16 input planes");
+        blocks = h->blocks; in_planes = h->in_planes;
+        const float* f = (const float*)((const char*)blob + sizeof(Hdr));
+        const float* fend = (const float*)((const char*)blob + bytes);
+        auto take = [&](size_t n) -> const float* { const float* p = f; f += n; return (f <= fend) ? p : nullptr; };
+        auto fold = [&](const float* bn, int n, std::vector<float>& scale, std::vector<float>& shift) {
+            scale.resize(n); shift.resize(n);
+            for (int i = 0; i < n; ++i) { scale[i] = bn[i] / std::sqrt(bn[3 * n + i] + 1e-5f); shift[i] = bn[n + i] - bn[2 * n + i] * scale[i]; }
+        };
+        free_weights();
+        const int nconv = 1 + 2 * blocks;
+        for (int l = 0; l < nconv; ++l) {
+            const int cin_real = l == 0 ? in_planes : C, cin = l == 0 ? 16 : C;
+            const float* cw = take((size_t)C * cin_real * 9); const float* bn = take((size_t)4 * C);
+            AZ_CHECK(cw && bn, "weight blob truncated (trunk)");
+            std::vector<float> sc, sh; fold(bn, C, sc, sh);
+            std::vector<__nv_bfloat16> img(nn::conv_weight_elems(cin), __float2bfloat16(0.0f));
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < cin_real; ++ci)
+                    for (int t = 0; t < 9; ++t)
+                        img[nn::conv_weight_index(cin, t, ci, co)] = __float2bfloat16(cw[((size_t)co * cin_real + ci) * 9 + t] * sc[co]);
+            __nv_bfloat16* dw; float* db;
+            if (dev_alloc(&dw, img.size()) || dev_alloc(&db, (size_t)C)) return -1;
+            AZ_CUDA_CHECK(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+            AZ_CUDA_CHECK(cudaMemcpy(db, sh.data(), C * 4, cudaMemcpyHostToDevice));
+            w.conv_w.push_back(dw); w.conv_b.push_back(db);
+        }
+        std::vector<float> w1((size_t)64 * C), b1(64);
+        const float* pcw = take((size_t)32 * C); const float* pbn = take(128);
+        const float* pfw = take((size_t)A * feat); const float* pfb = take(A);
+        const float* vcw = take((size_t)32 * C); const float* vbn = take(128);
+        const float* v1w = take((size_t)256 * feat); const float* v1b = take(256);
+        const float* v2w = take(256); const float* v2b = take(1);
+        AZ_CHECK(pcw && pbn && pfw && pfb && vcw && vbn && v1w && v1b && v2w && v2b, "weight blob truncated (heads)");
+        std::vector<float> sc, sh;
+        fold(pbn, 32, sc, sh);
+        for (int o = 0; o < 32; ++o) { b1[o] = sh[o]; for (int c = 0; c < C; ++c) w1[(size_t)o * C + c] = pcw[(size_t)o * C + c] * sc[o]; }
+        fold(vbn, 32, sc, sh);
+        for (int o = 0; o < 32; ++o) { b1[32 + o] = sh[o]; for (int c = 0; c < C; ++c) w1[(size_t)(32 + o) * C + c] = vcw[(size_t)o * C + c] * sc[o]; }
+        auto up = [&](float** d, const float* src, size_t n) -> int { if (dev_alloc(d, n)) return -1; AZ_CUDA_CHECK(cudaMemcpy(*d, src, n * 4, cudaMemcpyHostToDevice)); return 0; };
+        if (up(&w.w1x1, w1.data(), w1.size()) || up(&w.b1x1, b1.data(), 64) || up(&w.pfc_w, pfw, (size_t)A * feat) || up(&w.pfc_b, pfb, A) ||
+            up(&w.vfc1_w, v1w, (size_t)256 * feat) || up(&w.vfc1_b, v1b, 256) || up(&w.vfc2_w, v2w, 256) || up(&w.vfc2_b, v2b, 1)) return -1;
+        loaded = true;
+        return 0;
+    }
+    void free_weights() {
+        for (auto p : w.conv_w) cudaFree(p);
+        for (auto p : w.conv_b) cudaFree(p);
+        w.conv_w.clear(); w.conv_b.clear();
+        for (float** p : {&w.w1x1, &w.b1x1, &w.pfc_w, &w.pfc_b, &w.vfc1_w, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b}) { cudaFree(*p); *p = nullptr; }
+        loaded = false;
+    }
+    void destroy() {
+        free_weights();
+        for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)featbuf, (void*)logits, (void*)hidden}) cudaFree(p);
+    }
+    // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
+    int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
+        AZ_CHECK(loaded, "no network weights loaded (az_engine_load_weights)");
+        nn::ConvParams cp{};
+        cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
+        cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1;
+        cp.in = in16; cp.out = X; cp.resid = nullptr; cp.w = w.conv_w[0]; cp.bias = w.conv_b[0];
+        AZ_CHECK(nn::conv3x3_launch(cp, 16, n_sms, s) == 0, "stem conv launch failed"); ++launches;
+        for (int b = 0; b < blocks; ++b) {
+            cp.in = X; cp.out = Y; cp.resid = nullptr; cp.w = w.conv_w[1 + 2 * b]; cp.bias = w.conv_b[1 + 2 * b];
+            AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
+            cp.in = Y; cp.out = X; cp.resid = X; cp.w = w.conv_w[2 + 2 * b]; cp.bias = w.conv_b[2 + 2 * b];
+            AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
+        }
+        nn::HeadParams hp{X, w.w1x1, w.b1x1, featbuf, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD};
+        AZ_CHECK(nn::head_pool_conv_launch(hp, n_sms * 2, s) == 0, "head launch failed"); ++launches;
+        nn::FcParams fp{featbuf, w.pfc_w, w.pfc_b, logits, n_dev, n_fixed, feat, A, 2 * feat, A, 0};
+        AZ_CHECK(nn::fc_launch(fp, n_sms * 2, s) == 0, "policy fc launch failed"); ++launches;
+        nn::FcParams fv{featbuf + feat, w.vfc1_w, w.vfc1_b, hidden, n_dev, n_fixed, feat, 256, 2 * feat, 256, 1};
+        AZ_CHECK(nn::fc_launch(fv, n_sms * 2, s) == 0, "value fc launch failed"); ++launches;
+        nn::OutParams op{logits, hidden, w.vfc2_w, w.vfc2_b, policy, value, n_dev, n_fixed, A, 256};
+        AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ rules replay
+template <class G>
+__global__ void k_rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal,
+                               int32_t* n_legal, int32_t* terminal, int32_t* result, int32_t* player, float* planes) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_games) return;
+    typename G::State s; G::init(s);
+    int bad = 0;
+    for (int i = 0; i < n_moves[g]; ++i) {
+        const int a = moves[(size_t)g * max_moves + i];
+        if (a < 0 || a >= G::CELLS || G::occupied(s, a)) { bad = 1; break; }   // make_move throws (gomoku_state.cpp:681-689)
+        G::apply(s, a);
+    }
+    const int res = G::result(s);
+    int n = 0;
+    for (int a = G::CELLS - 1; a >= 0; --a) if (!G::occupied(s, a)) legal[(size_t)g * G::CELLS + n++] = a;
+    n_legal[g] = bad ? -1 : n; terminal[g] = res != RES_ONGOING; result[g] = res; player[g] = s.player;
+    if (planes)
+        for (int c = 0; c < G::PLANES; ++c)
+            for (int x = 0; x < G::N; ++x)
+                for (int y = 0; y < G::N; ++y) planes[(((size_t)g * G::PLANES + c) * G::N + x) * G::N + y] = G::feature(s, c, x, y);
+}
+
+// createGameState + fresh ParallelMCTS for every slot (self_play_manager.cpp:157-175)
+template <class G>
+__global__ void k_reset_all(TreePools tp, typename G::State* root_state, const int16_t* default_order, int n_order, int16_t* root_order,
+                            int32_t* root_order_n, int noise, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const size_t base = (size_t)t * tp.cap;
+    typename G::State s; G::init(s); root_state[t] = s;
+    tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
+    tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] = 0;
+    tp.tflags[t] = (uint8_t)(TF_ACTIVE | TF_FIRST_FILL | (noise ? TF_NEED_NOISE : 0));
+    root_order_n[t] = n_order;
+    for (int i = 0; i < n_order; ++i) root_order[(size_t)t * G::CELLS + i] = default_order[i];
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct EngineBase {
+    virtual ~EngineBase() {}
+    virtual int load_weights(const void* blob, size_t bytes) = 0;
+    virtual int reset_games() = 0;
+    virtual int set_root(int slot, const int32_t* moves, int n, const int32_t* order, int n_order) = 0;
+    virtual int search(int sims) = 0;
+    virtual int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) = 0;
+    virtual int advance(const int32_t* actions, int n) = 0;
+    virtual int play(int n_moves) = 0;
+    virtual int last_actions(int32_t* out, int n) = 0;
+    virtual int slot_state(int slot, int32_t* result, int32_t* ply, int32_t* player) = 0;
+    virtual int sample_layout(az_sample_layout* out) = 0;
+    virtual int drain(void* buf, size_t cap, size_t* n, bool device) = 0;
+    virtual int get_stats(az_stats* out) = 0;
+    virtual int sync() = 0;
+    virtual int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) = 0;
+    virtual int nn_bench(int n_boards, int reps, float* ms) = 0;
+    virtual int conv_bench(int n_boards, int reps, float* ms) = 0;
+    virtual int event_record(int idx) = 0;
+    virtual int event_elapsed(int i, int j, float* ms) = 0;
+    virtual int rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal, int32_t* n_legal,
+                             int32_t* terminal, int32_t* result, int32_t* player, float* planes) = 0;
+};
+
+template <class G>
+struct EngineT : EngineBase {
+    using State = typename G::State;
+    using SampleT = Sample<G>;
+    static constexpr int A = G::CELLS;
+    az_config cfg;
+    int T = 0;
+    cudaStream_t stream = nullptr;
+    TreePools tp{};
+    WaveBuffers wb{};
+    ScratchPools sc{};
+    int scratch_trees = 0;
+    State *root_state = nullptr, *leaf_state = nullptr;
+    int16_t *root_order = nullptr, *default_order = nullptr; int32_t* root_order_n = nullptr;
+    int32_t *chosen_child = nullptr, *chosen_action = nullptr, *forced = nullptr;
+    SampleT *game_buf = nullptr, *ring = nullptr; int32_t* ring_count = nullptr; int ring_cap = 0; int max_moves = 0;
+    float* noise_scratch = nullptr;
+    Stats* dstats = nullptr;
+    Net net;
+    unsigned long long launches = 0, waves = 0;
+    std::vector<int16_t> h_default_order;
+
+    ~EngineT() override { destroy(); }
+
+    void destroy() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* p : {(void*)tp.N, (void*)tp.W, (void*)tp.P, (void*)tp.first, (void*)tp.act, (void*)tp.nchild, (void*)tp.flags, (void*)tp.root,
+                        (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id, (void*)wb.path, (void*)wb.path_len,
+                        (void*)wb.leaf_node, (void*)wb.leaf_kind, (void*)wb.leaf_value, (void*)wb.policy, (void*)wb.value, (void*)wb.eval_slot, (void*)wb.n_eval,
+                        (void*)sc.N, (void*)sc.W, (void*)sc.P, (void*)sc.first, (void*)sc.act, (void*)sc.nchild, (void*)sc.flags, (void*)sc.old_id,
+                        (void*)root_state, (void*)leaf_state, (void*)root_order, (void*)default_order, (void*)root_order_n, (void*)chosen_child,
+                        (void*)chosen_action, (void*)forced, (void*)game_buf, (void*)ring, (void*)ring_count, (void*)noise_scratch, (void*)dstats})
+            cudaFree(p);
+        net.destroy();
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
+
+    int init(const az_config& c) {
+        cfg = c; T = c.n_slots;
+        AZ_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaDeviceProp prop; AZ_CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
+        AZ_CHECK(prop.major >= 10, "az_b200 needs an sm_100-class GPU (no fallback path exists)");
+        AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        int cap = c.max_nodes_per_tree;
+        if (cap <= 0) cap = 2 * (std::max(c.num_simulations, 1) + 1) * A + 1;
+        tp.cap = cap;
+        const size_t tn = (size_t)T * cap;
+        if (dev_alloc(&tp.N, tn) || dev_alloc(&tp.W, tn) || dev_alloc(&tp.P, tn) || dev_alloc(&tp.first, tn) || dev_alloc(&tp.act, tn) ||
+            dev_alloc(&tp.nchild, tn) || dev_alloc(&tp.flags, tn) || dev_alloc(&tp.root, T) || dev_alloc(&tp.alloc, T) || dev_alloc(&tp.root_vl, T) ||
+            dev_alloc(&tp.tflags, T) || dev_alloc(&tp.move_num, T) || dev_alloc(&tp.game_id, T)) return -1;
+        if (dev_alloc(&wb.path, (size_t)T * MAX_DEPTH) || dev_alloc(&wb.path_len, T) || dev_alloc(&wb.leaf_node, T) || dev_alloc(&wb.leaf_kind, T) ||
+            dev_alloc(&wb.leaf_value, T) || dev_alloc(&wb.policy, (size_t)T * A) || dev_alloc(&wb.value, T) || dev_alloc(&wb.eval_slot, T) ||
+            dev_alloc(&wb.n_eval, 1)) return -1;
+        // scratch for re-rooting: as many trees at a time as fit in ~1/8 of the pool memory (at least 1)
+        scratch_trees = std::max(1, std::min(T, (int)(((size_t)4 << 30) / ((size_t)cap * 25))));
+        const size_t sn = (size_t)scratch_trees * cap;
+        if (dev_alloc(&sc.N, sn) || dev_alloc(&sc.W, sn) || dev_alloc(&sc.P, sn) || dev_alloc(&sc.first, sn) || dev_alloc(&sc.act, sn) ||
+            dev_alloc(&sc.nchild, sn) || dev_alloc(&sc.flags, sn) || dev_alloc(&sc.old_id, sn)) return -1;
+        if (dev_alloc(&root_state, T) || dev_alloc(&leaf_state, T) || dev_alloc(&root_order, (size_t)T * A) || dev_alloc(&default_order, A) ||
+            dev_alloc(&root_order_n, T) || dev_alloc(&chosen_child, T) || dev_alloc(&chosen_action, T) || dev_alloc(&forced, T)) return -1;
+        max_moves = A;
+        ring_cap = c.sample_ring_capacity > 0 ? c.sample_ring_capacity : std::max(4 * T, 4096);
+        if (dev_alloc(&game_buf, (size_t)T * max_moves) || dev_alloc(&ring, (size_t)ring_cap) || dev_alloc(&ring_count, 1)) return -1;
+        AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
+        if (dev_alloc(&noise_scratch, (size_t)T * A) || dev_alloc(&dstats, 1)) return -1;
+        AZ_CUDA_CHECK(cudaMemset(dstats, 0, sizeof(Stats)));
+        // QUIRK G2: legal-move order of the first-ever enumeration of a fresh state = iteration order of a
+        // libstdc++ std::unordered_set<int> filled with 0..A-1 ascending (include/alphazero/games/gomoku/
+        // gomoku_state.h:124, gomoku_state.cpp:531-566).  Computed with the real container, uploaded once.
+        {
+            std::unordered_set<int> us; for (int a = 0; a < A; ++a) us.insert(a);
+            h_default_order.assign(us.begin(), us.end());
+            AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), A * 2, cudaMemcpyHostToDevice));
+        }
+        if (c.evaluator == AZ_EVAL_RESNET) { if (net.init(G::N, G::N, A, T, c.net_channels)) return -1; }
+        return reset_games();
+    }
+
+    SearchParams sparams() const { return SearchParams{cfg.c_puct, cfg.virtual_loss, MAX_DEPTH}; }
+    int blocks_for_warps(int n) const { return (n * 32 + 127) / 128; }
+
+    int load_weights(const void* blob, size_t bytes) override {
+        AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return net.load(blob, bytes);
+    }
+
+    int write_fresh(int slot, const State& s, const int16_t* order, int n_order, bool first_fill) {
+        const size_t base = (size_t)slot * tp.cap;
+        const int res = G::result(s);
+        int32_t zero = 0, one = 1, m1 = -1; float fz = 0.0f; int16_t a16 = -1, z16 = 0;
+        uint8_t nf = res != RES_ONGOING ? (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)) : 0;
+        uint8_t tf = TF_ACTIVE | (first_fill ? TF_FIRST_FILL : 0) | (res != RES_ONGOING ? TF_GAME_OVER : 0) | (cfg.deterministic ? 0 : TF_NEED_NOISE);
+        uint32_t gid = 0;
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.N + base, &zero, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.W + base, &fz, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.P + base, &fz, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.first + base, &m1, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.act + base, &a16, 2, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.nchild + base, &z16, 2, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.flags + base, &nf, 1, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.root + slot, &zero, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.alloc + slot, &one, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.root_vl + slot, &zero, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.tflags + slot, &tf, 1, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.move_num + slot, &zero, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.game_id + slot, &gid, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(root_state + slot, &s, sizeof(State), cudaMemcpyHostToDevice, stream));
+        if (order && n_order > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(root_order + (size_t)slot * A, order, (size_t)n_order * 2, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(root_order_n + slot, &n_order, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));   // host temporaries above go out of scope
+        return 0;
+    }
+
+    int reset_games() override {
+        k_reset_all<G><<<(T + 127) / 128, 128, 0, stream>>>(tp, root_state, default_order, A, root_order, root_order_n, cfg.deterministic ? 0 : 1, T);
+        AZ_LAUNCH_CHECK(); ++launches;
+        AZ_CUDA_CHECK(cudaMemsetAsync(ring_count, 0, 4, stream));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    int set_root(int slot, const int32_t* moves, int n, const int32_t* order, int n_order) override {
+        AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
+        State s; G::init(s);
+        for (int i = 0; i < n; ++i) {
+            AZ_CHECK(moves[i] >= 0 && moves[i] < A && !G::occupied(s, moves[i]), "illegal move in az_engine_set_root");   // IllegalMove (gomoku_state.cpp:681-689)
+            G::apply(s, moves[i]);
+        }
+        std::vector<int16_t> ord;
+        if (order) { ord.resize(n_order); for (int i = 0; i < n_order; ++i) ord[i] = (int16_t)order[i]; }
+        return write_fresh(slot, s, order ? ord.data() : nullptr, order ? n_order : 0, order != nullptr);
+    }
+
+    // one wave: select → evaluator → expand/backup
+    int wave(int mode) {
+        AZ_CUDA_CHECK(cudaMemsetAsync(wb.n_eval, 0, 4, stream));
+        EncodeTarget enc{nullptr, 0, 0, 0};
+        if (cfg.evaluator == AZ_EVAL_RESNET) enc = EncodeTarget{net.in16, net.p_total, nn::CONV_GUARD, net.board_pitch};
+        k_select<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, leaf_state, wb, sparams(), enc, T, mode);
+        AZ_LAUNCH_CHECK(); ++launches;
+        if (cfg.evaluator == AZ_EVAL_HASH) {
+            k_hash_eval<G><<<blocks_for_warps(T), 128, 4 * A * sizeof(float), stream>>>(leaf_state, wb, T);
+            AZ_LAUNCH_CHECK(); ++launches;
+        } else {
+            if (net.forward(wb.n_eval, 0, wb.policy, wb.value, stream)) return -1;
+        }
+        k_expand_backup<G><<<blocks_for_warps(T), 128, 4 * A * sizeof(float), stream>>>(tp, leaf_state, wb, root_order, root_order_n, sparams(), T, dstats);
+        AZ_LAUNCH_CHECK(); ++launches; ++waves;
+        return 0;
+    }
+
+    int search(int sims) override {
+        if (sims <= 0) sims = cfg.num_simulations;
+        if (wave(1)) return -1;                      // search() preamble: expand unexpanded roots
+        if (!cfg.deterministic) {
+            k_dirichlet<<<blocks_for_warps(T), 128, 0, stream>>>(tp, T, cfg.dirichlet_alpha, cfg.dirichlet_epsilon, cfg.seed, noise_scratch, A);
+            AZ_LAUNCH_CHECK(); ++launches;
+        }
+        for (int i = 0; i < sims; ++i) if (wave(0)) return -1;
+        return 0;
+    }
+
+    int commit_moves(const int32_t* forced_dev) {
+        MoveParams mp{cfg.deterministic, cfg.init_temperature, cfg.final_temperature, cfg.temperature_drop_move, cfg.seed};
+        k_choose_move<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, mp, game_buf, max_moves, forced_dev, chosen_child, chosen_action, T, dstats);
+        AZ_LAUNCH_CHECK(); ++launches;
+        for (int t0 = 0; t0 < T; t0 += scratch_trees) {
+            const int cnt = std::min(scratch_trees, T - t0);
+            k_reroot<G><<<blocks_for_warps(cnt), 128, 0, stream>>>(tp, sc, root_state, chosen_child, t0, cnt, T);
+            AZ_LAUNCH_CHECK(); ++launches;
+        }
+        k_finish_games<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, game_buf, max_moves, ring, ring_cap, ring_count, default_order, A,
+                                                                   root_order, root_order_n, cfg.auto_restart, cfg.deterministic ? 0 : 1, T, dstats);
+        AZ_LAUNCH_CHECK(); ++launches;
+        return 0;
+    }
+
+    int advance(const int32_t* actions, int n) override {
+        AZ_CHECK(n == T, "az_engine_advance needs one action per slot");
+        AZ_CUDA_CHECK(cudaMemcpyAsync(forced, actions, 4 * T, cudaMemcpyHostToDevice, stream));
+        if (commit_moves(forced)) return -1;
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    int play(int n_moves) override {
+        for (int m = 0; m < n_moves; ++m) { if (search(cfg.num_simulations)) return -1; if (commit_moves(nullptr)) return -1; }
+        return 0;
+    }
+
+    int last_actions(int32_t* out, int n) override {
+        AZ_CHECK(n == T, "need one entry per slot");
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        AZ_CUDA_CHECK(cudaMemcpy(out, chosen_action, 4 * T, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+
+    int slot_state(int slot, int32_t* result, int32_t* ply, int32_t* player) override {
+        AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        State s; AZ_CUDA_CHECK(cudaMemcpy(&s, root_state + slot, sizeof(State), cudaMemcpyDeviceToHost));
+        if (result) *result = G::result(s);
+        if (ply) *ply = s.ply;
+        if (player) *player = s.player;
+        return 0;
+    }
+
+    int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) override {
+        AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const size_t base = (size_t)slot * tp.cap;
+        int32_t root; AZ_CUDA_CHECK(cudaMemcpy(&root, tp.root + slot, 4, cudaMemcpyDeviceToHost));
+        int32_t f; int16_t nc;
+        AZ_CUDA_CHECK(cudaMemcpy(&f, tp.first + base + root, 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(&nc, tp.nchild + base + root, 2, cudaMemcpyDeviceToHost));
+        if (rn) AZ_CUDA_CHECK(cudaMemcpy(rn, tp.N + base + root, 4, cudaMemcpyDeviceToHost));
+        if (rw) AZ_CUDA_CHECK(cudaMemcpy(rw, tp.W + base + root, 4, cudaMemcpyDeviceToHost));
+        int count = f >= 0 ? nc : 0;
+        AZ_CHECK(*n >= count, "root_stats: buffers too small");
+        *n = count;
+        if (count > 0) {
+            std::vector<int16_t> a16(count);
+            AZ_CUDA_CHECK(cudaMemcpy(a16.data(), tp.act + base + f, 2 * count, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < count; ++i) actions[i] = a16[i];
+            AZ_CUDA_CHECK(cudaMemcpy(visits, tp.N + base + f, 4 * count, cudaMemcpyDeviceToHost));
+            AZ_CUDA_CHECK(cudaMemcpy(wsum, tp.W + base + f, 4 * count, cudaMemcpyDeviceToHost));
+            AZ_CUDA_CHECK(cudaMemcpy(priors, tp.P + base + f, 4 * count, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    }
+
+    int sample_layout(az_sample_layout* o) override {
+        SampleT* z = nullptr;
+        o->record_bytes = sizeof(SampleT);
+        o->off_game_id = (int)(size_t)&z->game_id; o->off_slot = (int)(size_t)&z->slot; o->off_ply = (int)(size_t)&z->ply;
+        o->off_action = (int)(size_t)&z->action; o->off_player = (int)(size_t)&z->player; o->off_z = (int)(size_t)&z->z;
+        o->off_result = (int)(size_t)&z->result; o->off_root_value = (int)(size_t)&z->root_value; o->off_root_visits = (int)(size_t)&z->root_visits;
+        o->off_state = (int)(size_t)&z->state; o->state_bytes = sizeof(State); o->off_visits = (int)(size_t)&z->visits[0];
+        o->n_visits = (int)(sizeof(z->visits) / 2);
+        return 0;
+    }
+
+    int drain(void* buf, size_t cap, size_t* n, bool device) override {
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        int32_t cnt = 0; AZ_CUDA_CHECK(cudaMemcpy(&cnt, ring_count, 4, cudaMemcpyDeviceToHost));
+        size_t take = std::min<size_t>(std::min<size_t>(cnt, ring_cap), cap);
+        if (take) AZ_CUDA_CHECK(cudaMemcpy(buf, ring, take * sizeof(SampleT), device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
+        *n = take;
+        return 0;
+    }
+
+    int get_stats(az_stats* o) override {
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
+        o->simulations = s.simulations; o->evaluations = s.evaluations; o->terminal_leaves = s.terminal_leaves; o->nodes_created = s.nodes_created;
+        o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped;
+        o->kernel_launches = launches + net.launches; o->waves = waves;
+        return 0;
+    }
+    int sync() override { AZ_CUDA_CHECK(cudaStreamSynchronize(stream)); return 0; }
+
+    int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) override {
+        AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
+        AZ_CHECK(n >= 1 && n <= T, "n must be in [1, n_slots]");
+        float* dpl; if (dev_alloc(&dpl, (size_t)n * net.in_planes * A)) return -1;
+        AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes, (size_t)n * net.in_planes * A * 4, cudaMemcpyHostToDevice, stream));
+        AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, n, net.in_planes, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, stream) == 0, "pack launch failed");
+        ++launches;
+        if (net.forward(nullptr, n, wb.policy, wb.value, stream)) { cudaFree(dpl); return -1; }
+        AZ_CUDA_CHECK(cudaMemcpyAsync(policy, wb.policy, (size_t)n * A * 4, cudaMemcpyDeviceToHost, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(value, wb.value, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+        if (logits) AZ_CUDA_CHECK(cudaMemcpyAsync(logits, net.logits, (size_t)n * A * 4, cudaMemcpyDeviceToHost, stream));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        cudaFree(dpl);
+        return 0;
+    }
+
+    int nn_bench(int n_boards, int reps, float* ms) override {
+        AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
+        AZ_CHECK(n_boards >= 1 && n_boards <= T, "n_boards must be in [1, n_slots]");
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        if (net.forward(nullptr, n_boards, wb.policy, wb.value, stream)) return -1;   // warm-up
+        AZ_CUDA_CHECK(cudaEventRecord(e0, stream));
+        for (int i = 0; i < reps; ++i) if (net.forward(nullptr, n_boards, wb.policy, wb.value, stream)) return -1;
+        AZ_CUDA_CHECK(cudaEventRecord(e1, stream));
+        AZ_CUDA_CHECK(cudaEventSynchronize(e1));
+        float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return 0;
+    }
+
+    int conv_bench(int n_boards, int reps, float* ms) override {
+        AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET && net.loaded && net.blocks >= 1, "conv_bench needs a loaded ResNet with >= 1 block");
+        AZ_CHECK(n_boards >= 1 && n_boards <= T, "n_boards must be in [1, n_slots]");
+        nn::ConvParams cp{};
+        cp.rowvalid = net.rowvalid; cp.n_boards_dev = nullptr; cp.n_rows = n_boards * net.board_pitch; cp.board_pitch = net.board_pitch;
+        cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
+        cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[1]; cp.bias = net.w.conv_b[1];
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, stream) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e0, stream));
+        for (int i = 0; i < reps; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, stream) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e1, stream));
+        AZ_CUDA_CHECK(cudaEventSynchronize(e1));
+        float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        launches += reps + 3;
+        return 0;
+    }
+    cudaEvent_t events[8] = {};
+    int event_record(int idx) override {
+        AZ_CHECK(idx >= 0 && idx < 8, "event index out of range");
+        if (!events[idx]) AZ_CUDA_CHECK(cudaEventCreate(&events[idx]));
+        AZ_CUDA_CHECK(cudaEventRecord(events[idx], stream));
+        return 0;
+    }
+    int event_elapsed(int i, int j, float* ms) override {
+        AZ_CHECK(i >= 0 && i < 8 && j >= 0 && j < 8 && events[i] && events[j], "events not recorded");
+        AZ_CUDA_CHECK(cudaEventSynchronize(events[j]));
+        AZ_CUDA_CHECK(cudaEventElapsedTime(ms, events[i], events[j]));
+        return 0;
+    }
+
+    int rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_mv, int32_t* legal, int32_t* n_legal,
+                     int32_t* terminal, int32_t* result, int32_t* player, float* planes) override {
+        int32_t *dm, *dn, *dl, *dnl, *dt, *dr, *dp; float* dpl = nullptr;
+        if (dev_alloc(&dm, (size_t)n_games * max_mv) || dev_alloc(&dn, n_games) || dev_alloc(&dl, (size_t)n_games * A) || dev_alloc(&dnl, n_games) ||
+            dev_alloc(&dt, n_games) || dev_alloc(&dr, n_games) || dev_alloc(&dp, n_games)) return -1;
+        if (planes && dev_alloc(&dpl, (size_t)n_games * G::PLANES * A)) return -1;
+        AZ_CUDA_CHECK(cudaMemcpy(dm, moves, (size_t)n_games * max_mv * 4, cudaMemcpyHostToDevice));
+        AZ_CUDA_CHECK(cudaMemcpy(dn, n_moves, (size_t)n_games * 4, cudaMemcpyHostToDevice));
+        k_rules_replay<G><<<(n_games + 63) / 64, 64, 0, stream>>>(dm, dn, n_games, max_mv, dl, dnl, dt, dr, dp, dpl);
+        AZ_LAUNCH_CHECK(); ++launches;
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        AZ_CUDA_CHECK(cudaMemcpy(legal, dl, (size_t)n_games * A * 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(n_legal, dnl, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(terminal, dt, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(result, dr, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(player, dp, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
+        if (planes) AZ_CUDA_CHECK(cudaMemcpy(planes, dpl, (size_t)n_games * G::PLANES * A * 4, cudaMemcpyDeviceToHost));
+        for (void* p : {(void*)dm, (void*)dn, (void*)dl, (void*)dnl, (void*)dt, (void*)dr, (void*)dp, (void*)dpl}) cudaFree(p);
+        return 0;
+    }
+};
+
+}  // namespace az
+
+// ================================================================================================ C ABI
+struct az_engine { std::unique_ptr<az::EngineBase> impl; };
+
+extern "C" {
+
+AZ_API void az_config_default(az_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
+    c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
+    c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234;
+}
+
+AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }
+
+AZ_API int az_engine_create(const az_config* cfg, az_engine** out) {
+    if (!cfg || !out) { az::set_error("null argument"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { az::set_error("no CUDA device: az_b200 has no CPU path"); return -2; }
+    if (cfg->n_slots < 1) { az::set_error("n_slots must be >= 1"); return -1; }
+    std::unique_ptr<az::EngineBase> impl;
+    int rc = -1;
+    if (cfg->game == AZ_GAME_GOMOKU && cfg->board_size == 15) { auto* e = new az::EngineT<az::Gomoku<15>>(); impl.reset(e); rc = e->init(*cfg); }
+    else if (cfg->game == AZ_GAME_GOMOKU && cfg->board_size == 9) { auto* e = new az::EngineT<az::Gomoku<9>>(); impl.reset(e); rc = e->init(*cfg); }
+    else { az::set_error("unsupported game / board size (built: Gomoku 15x15, 9x9)"); return -3; }
+    if (rc != 0) return rc;
+    *out = new az_engine{std::move(impl)};
+    return 0;
+}
+AZ_API int az_engine_destroy(az_engine* e) { delete e; return 0; }
+#define AZ_FWD(call) do { if (!e) { az::set_error("null engine"); return -1; } return e->impl->call; } while (0)
+AZ_API int az_engine_load_weights(az_engine* e, const void* blob, size_t bytes) { AZ_FWD(load_weights(blob, bytes)); }
+AZ_API int az_engine_reset_games(az_engine* e) { AZ_FWD(reset_games()); }
+AZ_API int az_engine_set_root(az_engine* e, int slot, const int32_t* moves, int n, const int32_t* order, int n_order) { AZ_FWD(set_root(slot, moves, n, order, n_order)); }
+AZ_API int az_engine_search(az_engine* e, int sims) { AZ_FWD(search(sims)); }
+AZ_API int az_engine_root_stats(az_engine* e, int slot, int32_t* a, int32_t* v, float* w, float* p, int32_t* n, int32_t* rn, float* rw) { AZ_FWD(root_stats(slot, a, v, w, p, n, rn, rw)); }
+AZ_API int az_engine_advance(az_engine* e, const int32_t* actions, int n) { AZ_FWD(advance(actions, n)); }
+AZ_API int az_engine_play(az_engine* e, int n_moves) { AZ_FWD(play(n_moves)); }
+AZ_API int az_engine_last_actions(az_engine* e, int32_t* actions, int n) { AZ_FWD(last_actions(actions, n)); }
+AZ_API int az_engine_slot_state(az_engine* e, int slot, int32_t* r, int32_t* ply, int32_t* pl) { AZ_FWD(slot_state(slot, r, ply, pl)); }
+AZ_API int az_engine_sample_layout(az_engine* e, az_sample_layout* out) { AZ_FWD(sample_layout(out)); }
+AZ_API int az_engine_drain_samples(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, false)); }
+AZ_API int az_engine_drain_samples_device(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, true)); }
+AZ_API int az_engine_get_stats(az_engine* e, az_stats* out) { AZ_FWD(get_stats(out)); }
+AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
+AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits) { AZ_FWD(nn_forward(planes, n, policy, value, logits)); }
+AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(nn_bench(n_boards, reps, ms)); }
+AZ_API int az_engine_conv_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(conv_bench(n_boards, reps, ms)); }
+AZ_API int az_engine_event_record(az_engine* e, int idx) { AZ_FWD(event_record(idx)); }
+AZ_API int az_engine_event_elapsed(az_engine* e, int i, int j, float* ms) { AZ_FWD(event_elapsed(i, j, ms)); }
+AZ_API int az_rules_replay(az_engine* e, const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal, int32_t* n_legal,
+                    int32_t* terminal, int32_t* result, int32_t* player, float* planes) {
+    AZ_FWD(rules_replay(moves, n_moves, n_games, max_moves, legal, n_legal, terminal, result, player, planes));
+}
+
+}  // extern "C"

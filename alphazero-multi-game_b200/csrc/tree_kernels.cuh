@@ -1,0 +1,543 @@
+// tree_kernels.cuh — the per-wave tree kernels: warp-per-tree PUCT selection, leaf replay + terminal
+// detection + feature encoding, expansion with legal-order prior normalisation, backup; plus the
+// per-move kernels (choose / record sample, re-root with compaction, game turnover, Dirichlet noise).
+//
+// One warp owns one tree and runs ONE simulation per wave, so inside a tree the arithmetic is exactly the
+// reference's serial ParallelMCTS (numThreads = 1): every float operation below is a single correctly
+// rounded fp32 op in the reference's order (no FMA contraction) and every tie-break follows the reference
+// scan order — visit counts are bit-exact, see tests/test_engine_parity.py.
+#pragma once
+#include <cuda_bf16.h>
+#include <cfloat>
+#include "tree.cuh"
+
+namespace az {
+
+struct EncodeTarget {          // where k_select writes the NN input planes (bf16), conv_trunk.cu layout
+    __nv_bfloat16* ptr;        // [CIN/8][p_total][8]; nullptr = no encoding (hash evaluator)
+    int p_total;               // rows per channel-chunk plane
+    int guard;                 // zero rows before board 0
+    int board_pitch;           // rows per board (PITCH*PITCH)
+};
+
+AZ_D int warp_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// ------------------------------------------------------------------------------------------------
+// Selection (M3/M4) + leaf replay + terminal test (M10) + feature encoding (G5).
+// mode 0: one simulation; mode 1: root-expansion wave (search() preamble, parallel_mcts.cpp:153-174).
+template <class G>
+__global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
+                                               typename G::State* __restrict__ leaf_state, WaveBuffers wb,
+                                               SearchParams sp, EncodeTarget enc, int T, int mode) {
+    using State = typename G::State;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const size_t base = (size_t)t * tp.cap;
+    const uint8_t tf = tp.tflags[t];
+    int8_t kind = LEAF_NONE;
+    int node = tp.root[t];
+    int depth = 0;
+    float tvalue = 0.0f;
+    State s = root_state[t];
+
+    const bool live = (tf & TF_ACTIVE) && !(tf & TF_GAME_OVER);
+    if (live) {
+        const int rf = tp.first[base + node];
+        const bool rterm = tp.flags[base + node] & NF_TERMINAL;
+        if (mode == 1) {
+            if (rf < 0 && !rterm) kind = LEAF_EVAL;          // root needs its first evaluation
+        } else if (rf >= 0 && !rterm) {
+            // --- selectLeafWithPath (parallel_mcts.cpp:456-535).  The root carries one fresh virtual
+            // loss while its children are scored (:461), so parentVisits = N_root + virtualLoss (:539).
+            int* path = wb.path + (size_t)t * MAX_DEPTH;
+            if (lane == 0) path[0] = node;
+            int parentN = tp.N[base + node] + sp.virtual_loss;
+            int f = rf;
+            while (true) {
+                const int nc = tp.nchild[base + node];
+                // QUIRK M4: Q is negated only for children of depth-1 nodes (mcts_node.cpp:88-93)
+                const bool negate = (depth == 1);
+                const float sq = fsqrt((float)parentN);
+                float best = -FLT_MAX; int bi = 0x7fffffff;
+                for (int i = lane; i < nc; i += 32) {
+                    const size_t c = base + f + i;
+                    const int n = tp.N[c];
+                    float sc;
+                    if (n == 0) sc = FLT_MAX;                   // mcts_node.cpp:63-66
+                    else {
+                        float q = fdiv(tp.W[c], (float)n);      // children carry no virtual loss when scored
+                        if (negate) q = -q;
+                        const float u = fdiv(fmul(fmul(sp.c_puct, tp.P[c]), sq), fadd(1.0f, (float)n));
+                        const float d = n < 5 ? fmul(0.05f, (float)(5 - n)) : 0.0f;   // :113-116
+                        sc = fadd(fadd(q, u), d);
+                    }
+                    if (sc > best) { best = sc; bi = i; }       // strict >: first child wins ties (:556)
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (bi == 0x7fffffff) break;                    // no selectable child (bestChild == nullptr)
+                const int child = f + bi;
+                G::apply(s, (int)tp.act[base + child]);
+                ++depth;
+                if (lane == 0) path[depth] = child;
+                node = child;
+                f = tp.first[base + node];
+                if (f < 0 || (tp.flags[base + node] & NF_TERMINAL) || depth >= sp.max_depth - 1) break;
+                parentN = tp.N[base + node];
+            }
+            // --- leaf classification (parallel_mcts.cpp:300-313)
+            const uint8_t fl = tp.flags[base + node];
+            if (fl & NF_TERMINAL) { kind = LEAF_TERMINAL; tvalue = result_to_value((fl >> NF_RESULT_SHIFT) & 3, s.player); }
+            else {
+                const int res = G::result(s);
+                if (res != RES_ONGOING) {
+                    kind = LEAF_TERMINAL; tvalue = result_to_value(res, s.player);
+                    if (lane == 0) tp.flags[base + node] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT));
+                } else kind = LEAF_EVAL;
+            }
+            ++depth;   // path length
+        }
+    }
+    int slot = -1;
+    if (kind == LEAF_EVAL) {
+        if (lane == 0) slot = atomicAdd(wb.n_eval, 1);
+        slot = warp_bcast(slot, 0);
+    }
+    if (lane == 0) {
+        wb.leaf_kind[t] = kind; wb.leaf_node[t] = node; wb.path_len[t] = (mode == 1 || kind == LEAF_NONE) ? 0 : depth;
+        wb.leaf_value[t] = tvalue; wb.eval_slot[t] = slot;
+        if (kind == LEAF_EVAL) leaf_state[t] = s;
+    }
+    // --- feature planes, straight into the conv trunk's input layout (bf16, 16 channels = 11 + 5 zero)
+    if (kind == LEAF_EVAL && enc.ptr != nullptr) {
+        const size_t row0 = (size_t)enc.guard + (size_t)slot * enc.board_pitch;
+        for (int p = lane; p < G::N * G::PITCH; p += 32) {
+            const int x = p / G::PITCH, y = p % G::PITCH;
+            if (y >= G::N) continue;                             // hole column stays zero
+            __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(c < G::PLANES ? G::feature(s, c, x, y) : 0.0f);
+            uint4* d0 = reinterpret_cast<uint4*>(enc.ptr + ((size_t)0 * enc.p_total + row0 + p) * 8);
+            uint4* d1 = reinterpret_cast<uint4*>(enc.ptr + ((size_t)1 * enc.p_total + row0 + p) * 8);
+            *d0 = *reinterpret_cast<const uint4*>(&v[0]);
+            *d1 = *reinterpret_cast<const uint4*>(&v[8]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stateless HashEvaluator — the deterministic evaluator used for bit-exact parity
+// against the reference's serial search.  One warp per leaf; the policy sum is accumulated in ascending
+// action order by one lane so it is the reference's fp32 sum bit for bit.
+template <class G>
+__global__ void __launch_bounds__(128) k_hash_eval(const typename G::State* __restrict__ leaf_state, WaveBuffers wb, int T) {
+    extern __shared__ float sm[];
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (t >= T) return;
+    if (wb.leaf_kind[t] != LEAF_EVAL) return;
+    constexpr int A = G::CELLS;
+    float* raw = sm + wib * A;
+    const int slot = wb.eval_slot[t];
+    const uint64_t h = G::key(leaf_state[t]);
+    for (int i = lane; i < A; i += 32) {
+        const uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
+        raw[i] = fdiv((float)(r + 1), 16777216.0f);
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    if (lane == 0) for (int i = 0; i < A; ++i) sum = fadd(sum, raw[i]);
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    for (int i = lane; i < A; i += 32) wb.policy[(size_t)slot * A + i] = fdiv(raw[i], sum);
+    if (lane == 0) {
+        float v = fdiv((float)(mix64(h ^ 0xABCDEFULL) >> 40), 16777216.0f);
+        v = fsub(fmul(v, 2.0f), 1.0f);
+        wb.value[slot] = fmul(v, 0.5f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expansion (M5) + backup (M6/M7).
+template <class G>
+__global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typename G::State* __restrict__ leaf_state,
+                                                      WaveBuffers wb, const int16_t* __restrict__ root_order,
+                                                      const int32_t* __restrict__ root_order_n, SearchParams sp,
+                                                      int T, Stats* stats) {
+    using State = typename G::State;
+    extern __shared__ float sm[];
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (t >= T) return;
+    const int8_t kind = wb.leaf_kind[t];
+    if (kind == LEAF_NONE) return;
+    constexpr int A = G::CELLS;
+    const size_t base = (size_t)t * tp.cap;
+    float* raw = sm + wib * A;
+    float v = wb.leaf_value[t];
+    const int leaf = wb.leaf_node[t];
+
+    if (kind == LEAF_EVAL) {
+        const int slot = wb.eval_slot[t];
+        const float* pol = wb.policy + (size_t)slot * A;
+        v = wb.value[slot];
+        const State s = leaf_state[t];
+        const uint8_t tf = tp.tflags[t];
+        const bool first_fill = (tf & TF_FIRST_FILL) && leaf == tp.root[t];
+        const int alloc = tp.alloc[t];
+        // legal moves in the reference's order (QUIRK G2): std::unordered_set iteration order = strictly
+        // descending action index, except the very first enumeration of a lineage (host-computed table).
+        int n = first_fill ? root_order_n[t] : (A - G::stones(s));
+        if (alloc + n > tp.cap) {
+            if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
+        } else if (n > 0) {
+            int16_t* act = tp.act + base + alloc;
+            if (first_fill) {
+                const int16_t* ord = root_order + (size_t)t * A;
+                for (int i = lane; i < n; i += 32) { const int a = ord[i]; act[i] = (int16_t)a; raw[i] = pol[a]; }
+            } else {
+                int cnt = 0;
+                for (int k = 0; k < A; k += 32) {
+                    const int a = A - 1 - (k + lane);
+                    const bool empty = a >= 0 && !G::occupied(s, a);
+                    const unsigned m = __ballot_sync(0xffffffffu, empty);
+                    if (empty) { const int i = cnt + __popc(m & ((1u << lane) - 1)); act[i] = (int16_t)a; raw[i] = pol[a]; }
+                    cnt += __popc(m);
+                }
+            }
+            __syncwarp();
+            // policySum accumulated in child order (parallel_mcts.cpp:705-711) — serial on purpose
+            float sum = 0.0f;
+            if (lane == 0) for (int i = 0; i < n; ++i) sum = fadd(sum, raw[i]);
+            sum = __shfl_sync(0xffffffffu, sum, 0);
+            const float uniform = fdiv(1.0f, (float)n);
+            for (int i = lane; i < n; i += 32) {
+                const size_t c = base + alloc + i;
+                tp.N[c] = 0; tp.W[c] = 0.0f; tp.first[c] = -1; tp.nchild[c] = 0; tp.flags[c] = 0;
+                tp.P[c] = sum > 0.0f ? fdiv(raw[i], sum) : uniform;     // :714-724
+            }
+            if (lane == 0) {
+                tp.first[base + leaf] = alloc; tp.nchild[base + leaf] = (int16_t)n; tp.alloc[t] = alloc + n;
+                if (first_fill) tp.tflags[t] = tf & ~TF_FIRST_FILL;
+                atomicAdd(&stats->nodes_created, (unsigned long long)n);
+                atomicAdd(&stats->nodes_expanded, 1ULL);
+            }
+        }
+        if (lane == 0) atomicAdd(&stats->evaluations, 1ULL);
+    } else if (lane == 0) atomicAdd(&stats->terminal_leaves, 1ULL);
+
+    // --- virtual loss add/remove + backpropagate, folded (mcts_node.cpp:168-196, parallel_mcts.cpp:782-833).
+    // Per path node the reference does W -= 3 (added after selection), then in reverse path order
+    // W += 3, N += 1, W += v.  The root received one extra virtual loss at selection start that is never
+    // removed (QUIRK M7): N_root += 4, VL_root += 3, W_root goes through -3,-3,+3,+v.
+    const int plen = wb.path_len[t];
+    if (plen > 0 && lane == 0) {
+        const int* path = wb.path + (size_t)t * MAX_DEPTH;
+        const float vl = (float)sp.virtual_loss;
+        float cv = v;
+        for (int j = plen - 1; j >= 0; --j) {
+            const size_t c = base + path[j];
+            float w = tp.W[c];
+            if (j == 0) { w = fsub(w, vl); w = fsub(w, vl); w = fadd(w, vl); w = fadd(w, cv);
+                          tp.N[c] += sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
+            else { w = fsub(w, vl); w = fadd(w, vl); w = fadd(w, cv); tp.N[c] += 1; }
+            tp.W[c] = w;
+            cv = -cv;
+        }
+        atomicAdd(&stats->simulations, 1ULL);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based RNG; per-slot streams: key = seed, counter = (slot, game, move, draw)).
+struct Philox {
+    uint32_t k0, k1, c0, c1, c2, c3; uint32_t out[4]; int have;
+    AZ_D Philox(uint64_t seed, uint32_t a, uint32_t b, uint32_t c) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0(0), c1(a), c2(b), c3(c), have(0) {}
+    AZ_D void round4() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            x0 = hi1 ^ x1 ^ a; x1 = lo1; x2 = hi0 ^ x3 ^ b; x3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3; ++c0; have = 4;
+    }
+    AZ_D uint32_t next() { if (!have) round4(); return out[--have]; }
+    AZ_D float uniform() { return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+    AZ_D float normal() { const float u1 = uniform(), u2 = uniform(); return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2); }
+    AZ_D float gamma(float alpha) {   // Marsaglia–Tsang, with the alpha<1 boost
+        float boost = 1.0f;
+        if (alpha < 1.0f) { boost = __powf(uniform(), 1.0f / alpha); alpha += 1.0f; }
+        const float d = alpha - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
+        for (int it = 0; it < 64; ++it) {
+            const float x = normal(); float v = 1.0f + c * x;
+            if (v <= 0.0f) continue;
+            v = v * v * v; const float u = uniform();
+            if (__logf(u) < 0.5f * x * x + d - d * v + d * __logf(v)) return d * v * boost;
+        }
+        return d * boost;
+    }
+};
+
+// Dirichlet noise on the root priors (M11, parallel_mcts.cpp:1110-1171): P = (1-eps) P + eps * noise_i by
+// child index.  The reference draws from libstdc++'s gamma_distribution with a random_device seed, which is
+// unpinned; here the draws come from Philox(seed; slot, game, move).
+__global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, float alpha, float eps, uint64_t seed, float* scratch /*[T][maxA]*/, int maxA) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const uint8_t tf = tp.tflags[t];
+    if (!(tf & TF_ACTIVE) || (tf & TF_GAME_OVER) || !(tf & TF_NEED_NOISE)) return;
+    const size_t base = (size_t)t * tp.cap;
+    const int root = tp.root[t];
+    const int f = tp.first[base + root];
+    if (f < 0) return;                                   // terminal root: nothing to perturb
+    const int nc = tp.nchild[base + root];
+    float* nz = scratch + (size_t)t * maxA;
+    float part = 0.0f;
+    for (int i = lane; i < nc; i += 32) {
+        Philox rng(seed, (uint32_t)t, tp.game_id[t], ((uint32_t)tp.move_num[t] << 12) | (uint32_t)i);
+        const float g = fmaxf(1e-10f, rng.gamma(alpha));
+        nz[i] = g; part += g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float inv = part > 0.0f ? 1.0f / part : 0.0f;
+    for (int i = lane; i < nc; i += 32) {
+        const size_t c = base + f + i;
+        const float noise = part > 0.0f ? nz[i] * inv : 1.0f / (float)nc;
+        tp.P[c] = (1.0f - eps) * tp.P[c] + eps * noise;
+    }
+    if (lane == 0) tp.tflags[t] = tf & ~TF_NEED_NOISE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sample record: one per move played (the device-side equivalent of selfplay::MoveData,
+// include/alphazero/selfplay/game_record.h:18-70, with action-indexed visit counts instead of the
+// reference's child-ordered policy — SURVEY.md §8f.1).
+template <class G>
+struct alignas(16) Sample {
+    uint32_t game_id; int32_t slot;
+    int16_t ply, action; int8_t player, z, result, pad_;
+    float root_value; int32_t root_visits;
+    typename G::State state;                       // position the move was chosen from
+    uint16_t visits[(G::CELLS + 7) / 8 * 8];      // root child visit counts by action
+};
+
+struct MoveParams {
+    int deterministic;          // 1: first-max-visit child (what SelfPlayManager's forced useBatchInference does, M13)
+    float init_temperature, final_temperature; int temperature_drop_move;   // self_play_manager.cpp:236-240
+    uint64_t seed;
+};
+
+// Choose the move (M13), record the sample (S1/S2), advance the root state.  Leaves the chosen child's
+// old index in chosen_child[t] for k_reroot.  forced_action: nullptr, or per-slot action to play
+// (-2 = leave slot alone) for the manual ParallelMCTS::updateWithMove path (M14).
+template <class G>
+__global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::State* root_state, MoveParams mp,
+                                                    Sample<G>* game_buf /*[T][max_moves]*/, int max_moves,
+                                                    const int32_t* forced_action, int32_t* chosen_child,
+                                                    int32_t* chosen_action, int T, Stats* stats) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    if (lane == 0) { chosen_child[t] = -2; chosen_action[t] = -2; }
+    const uint8_t tf = tp.tflags[t];
+    if (!(tf & TF_ACTIVE) || (tf & TF_GAME_OVER)) return;
+    if (forced_action && forced_action[t] == -2) return;
+    const size_t base = (size_t)t * tp.cap;
+    const int root = tp.root[t];
+    const int f = tp.first[base + root];
+    const int nc = f >= 0 ? tp.nchild[base + root] : 0;
+    int bi = -1, action = -1;
+    if (forced_action) {
+        action = forced_action[t];
+        int found = 0x7fffffff;
+        for (int i = lane; i < nc; i += 32) if (tp.act[base + f + i] == action) found = min(found, i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+        bi = found == 0x7fffffff ? -1 : found;
+    } else {
+        if (nc == 0) return;     // unexpanded / terminal root: nothing to choose (host keeps roots expanded)
+        const int mv = tp.move_num[t];
+        const float T_ = mv >= mp.temperature_drop_move ? mp.final_temperature : mp.init_temperature;
+        if (mp.deterministic || T_ <= 0.0f) {
+            // getBestActions()[0] / max_element: first child with the maximum visit count
+            int bn = -1; bi = 0x7fffffff;
+            for (int i = lane; i < nc; i += 32) { const int n = tp.N[base + f + i]; if (n > bn) { bn = n; bi = i; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int on = __shfl_xor_sync(0xffffffffu, bn, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (on > bn || (on == bn && oi < bi)) { bn = on; bi = oi; }
+            }
+        } else {
+            // sample child ∝ N^(1/T)  (getVisitCountDistribution + discrete_distribution, M12/M13)
+            const float e = 1.0f / fmaxf(0.01f, T_);
+            float part = 0.0f;
+            for (int i = lane; i < nc; i += 32) part += powf((float)tp.N[base + f + i], e);
+            float tot = part;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (lane == 0) {
+                Philox rng(mp.seed ^ 0x5eedULL, (uint32_t)t, tp.game_id[t], (uint32_t)mv);
+                const float target = rng.uniform() * tot;
+                float acc = 0.0f; bi = nc - 1;
+                for (int i = 0; i < nc; ++i) { acc += powf((float)tp.N[base + f + i], e); if (acc > target) { bi = i; break; } }
+            }
+            bi = warp_bcast(bi, 0);
+        }
+        action = tp.act[base + f + bi];
+    }
+    // --- record the sample
+    const int mv = tp.move_num[t];
+    if (game_buf && mv < max_moves) {
+        Sample<G>* sp_ = game_buf + (size_t)t * max_moves + mv;
+        for (int i = lane; i < (int)(sizeof(sp_->visits) / 2); i += 32) sp_->visits[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < nc; i += 32) {
+            const int a = tp.act[base + f + i];
+            if (a >= 0) sp_->visits[a] = (uint16_t)min(tp.N[base + f + i], 65535);
+        }
+        if (lane == 0) {
+            const int rn = tp.N[base + root];
+            sp_->game_id = tp.game_id[t]; sp_->slot = t; sp_->ply = root_state[t].ply; sp_->action = (int16_t)action;
+            sp_->player = root_state[t].player; sp_->z = 0; sp_->result = 0; sp_->pad_ = 0;
+            sp_->root_value = (nc == 0 || rn == 0) ? 0.0f : fdiv(tp.W[base + root], (float)rn);   // getRootValue (M15)
+            sp_->root_visits = rn; sp_->state = root_state[t];
+        }
+    }
+    // --- advance the root state (updateWithMove, M14)
+    if (lane == 0) {
+        typename G::State s = root_state[t];
+        G::apply(s, action);
+        root_state[t] = s;
+        chosen_child[t] = bi >= 0 ? f + bi : -1;
+        chosen_action[t] = action;
+        tp.move_num[t] = mv + 1;
+        atomicAdd(&stats->moves, 1ULL);
+    }
+}
+
+// Re-root with compaction (M14): the chosen child's subtree is copied breadth-first into a scratch pool
+// (children stay contiguous and in order), then copied back to the front of the tree's pool.  The
+// reference frees the siblings recursively; here they are simply not copied.
+struct ScratchPools { int32_t* N; float* W; float* P; int32_t* first; int16_t* act; int16_t* nchild; uint8_t* flags; int32_t* old_id; };
+
+template <class G>
+__global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, const typename G::State* __restrict__ root_state,
+                                               const int32_t* __restrict__ chosen_child, int t0, int tcount, int T) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= tcount) return;
+    const int t = t0 + w;
+    if (t >= T) return;
+    const int cc = chosen_child[t];
+    if (cc == -2) return;                                // slot did not move
+    const size_t base = (size_t)t * tp.cap;
+    const size_t sb = (size_t)w * tp.cap;
+    int count = 1;
+    if (cc < 0) {
+        // child did not exist: fresh root (parallel_mcts.cpp:1097-1101)
+        if (lane == 0) { tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0; }
+    } else {
+        if (lane == 0) {
+            sc.N[sb] = tp.N[base + cc]; sc.W[sb] = tp.W[base + cc]; sc.P[sb] = tp.P[base + cc]; sc.act[sb] = tp.act[base + cc];
+            sc.flags[sb] = tp.flags[base + cc]; sc.first[sb] = -1; sc.nchild[sb] = 0; sc.old_id[sb] = cc;
+        }
+        __syncwarp();
+        for (int j0 = 0; j0 < count; j0 += 32) {
+            const int j = j0 + lane;
+            int fo = -1, no = 0;
+            if (j < count) { const int o = sc.old_id[sb + j]; fo = tp.first[base + o]; no = tp.nchild[base + o]; }
+            unsigned m = __ballot_sync(0xffffffffu, fo >= 0);
+            while (m) {
+                const int src = __ffs(m) - 1; m &= m - 1;
+                const int f = __shfl_sync(0xffffffffu, fo, src), n = __shfl_sync(0xffffffffu, no, src);
+                for (int i = lane; i < n; i += 32) {
+                    const size_t o = base + f + i, d = sb + count + i;
+                    sc.N[d] = tp.N[o]; sc.W[d] = tp.W[o]; sc.P[d] = tp.P[o]; sc.act[d] = tp.act[o]; sc.flags[d] = tp.flags[o];
+                    sc.first[d] = -1; sc.nchild[d] = 0; sc.old_id[d] = f + i;
+                }
+                if (lane == 0) { sc.first[sb + j0 + src] = count; sc.nchild[sb + j0 + src] = (int16_t)n; }
+                count += n;
+            }
+            __syncwarp();
+        }
+        for (int i = lane; i < count; i += 32) {
+            tp.N[base + i] = sc.N[sb + i]; tp.W[base + i] = sc.W[sb + i]; tp.P[base + i] = sc.P[sb + i]; tp.first[base + i] = sc.first[sb + i];
+            tp.act[base + i] = sc.act[sb + i]; tp.nchild[base + i] = sc.nchild[sb + i]; tp.flags[base + i] = sc.flags[sb + i];
+        }
+    }
+    if (lane == 0) {
+        // the new root's terminal status comes from the state, as in the root MCTSNode ctor (mcts_node.cpp:24-25)
+        const int res = G::result(root_state[t]);
+        uint8_t tf = tp.tflags[t];
+        if (res != RES_ONGOING) { tp.flags[base] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)); tf |= TF_GAME_OVER; }
+        tf &= ~TF_FIRST_FILL;
+        tp.tflags[t] = tf;
+        tp.root[t] = 0; tp.alloc[t] = count; tp.root_vl[t] = 0;
+    }
+}
+
+// Game turnover (S1, self_play_manager.cpp:187-234): stamp z / result into the finished game's samples,
+// append them to the output ring, then (auto_restart) start a new game in the slot.
+template <class G>
+__global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::State* root_state, Sample<G>* game_buf, int max_moves,
+                                                     Sample<G>* out, int out_cap, int* out_count, const int16_t* __restrict__ default_order,
+                                                     int default_order_n, int16_t* root_order, int32_t* root_order_n,
+                                                     int auto_restart, int noise_every_even_move, int T, Stats* stats) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    uint8_t tf = tp.tflags[t];
+    if (!(tf & TF_ACTIVE)) return;
+    if (!(tf & TF_GAME_OVER)) {
+        // addDirichletNoise after every even move (self_play_manager.cpp:209-211): move_num was already incremented
+        if (noise_every_even_move && lane == 0 && tp.move_num[t] > 0 && ((tp.move_num[t] - 1) % 2 == 0)) tp.tflags[t] = tf | TF_NEED_NOISE;
+        return;
+    }
+    const size_t base = (size_t)t * tp.cap;
+    const int res = G::result(root_state[t]);
+    const int n = min(tp.move_num[t], max_moves);
+    if (game_buf && out) {
+        int dst = -1;
+        if (lane == 0) {     // reserve n records, or nothing at all if the ring is full
+            int old = *(volatile int*)out_count;
+            while (old + n <= out_cap) {
+                const int seen = atomicCAS(out_count, old, old + n);
+                if (seen == old) { dst = old; break; }
+                old = seen;
+            }
+        }
+        dst = warp_bcast(dst, 0);
+        if (dst >= 0) {
+            for (int j = 0; j < n; ++j) {
+                Sample<G>* s = game_buf + (size_t)t * max_moves + j;
+                if (lane == 0) { s->result = (int8_t)res; s->z = (int8_t)result_to_value(res, s->player); }
+                __syncwarp();
+                const uint4* src = reinterpret_cast<const uint4*>(s);
+                uint4* d = reinterpret_cast<uint4*>(out + dst + j);
+                for (int i = lane; i < (int)(sizeof(Sample<G>) / 16); i += 32) d[i] = src[i];
+            }
+        } else if (lane == 0) atomicAdd(&stats->samples_dropped, (unsigned long long)n);
+    }
+    if (lane == 0) {
+        atomicAdd(&stats->games, 1ULL);
+        if (auto_restart) {
+            typename G::State s; G::init(s); root_state[t] = s;
+            tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
+            tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] += 1;
+            tp.tflags[t] = TF_ACTIVE | TF_FIRST_FILL | (noise_every_even_move ? TF_NEED_NOISE : 0);
+            root_order_n[t] = default_order_n;
+        } else tp.tflags[t] = tf & ~TF_ACTIVE;   // keeps TF_GAME_OVER for the host to see
+    }
+    if (auto_restart) for (int i = lane; i < default_order_n; i += 32) root_order[(size_t)t * G::CELLS + i] = default_order[i];
+}
+
+}  // namespace az

@@ -1,0 +1,146 @@
+/* az_b200.h — C ABI of the B200-native batched self-play engine (libaz_b200.so).
+ *
+ * This is the drop-in boundary #3 of SURVEY.md §8(b): plain C, pointers + sizes, no torch / STL types.
+ * Every entry point names the reference interface it stands in for (paths relative to the reference repo).
+ * The closest precedent in the reference is its plugin ABI (include/alphazero/core/plugin_api.h:19-37).
+ *
+ * Conventions: every function returns 0 on success and a negative status on failure (az_last_error() gives
+ * the message); no exception crosses the boundary; the caller owns all host buffers, the engine owns all
+ * device memory; calls on one engine must be serialised by the caller (one host thread per engine / GPU).
+ * There is NO CPU fallback: az_engine_create fails when no sm_100-class CUDA device is present.
+ */
+#ifndef AZ_B200_H
+#define AZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AZ_API __attribute__((visibility("default")))
+#else
+#define AZ_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* core::GameType, include/alphazero/core/igamestate.h:16-20 */
+enum { AZ_GAME_GOMOKU = 0, AZ_GAME_CHESS = 1, AZ_GAME_GO = 2 };
+/* core::GameResult, include/alphazero/core/igamestate.h:25-30 */
+enum { AZ_ONGOING = 0, AZ_DRAW = 1, AZ_WIN_PLAYER1 = 2, AZ_WIN_PLAYER2 = 3 };
+/* evaluator behind nn::NeuralNetwork::predict (include/alphazero/nn/neural_network.h:29) */
+enum { AZ_EVAL_HASH = 0,   /* stateless integer-mix evaluator (parity runs) */
+       AZ_EVAL_RESNET = 1  /* policy/value ResNet, bf16 on tcgen05 tensor cores */ };
+
+/* mcts::MCTSConfig (include/alphazero/mcts/parallel_mcts.h:41-74) + SelfPlayManager exploration params
+ * (src/selfplay/self_play_manager.cpp:16-37) + engine sizing. */
+typedef struct az_config {
+    int32_t game;               /* AZ_GAME_* */
+    int32_t board_size;         /* 15 (Gomoku) */
+    int32_t n_slots;            /* concurrent games = trees searched per wave */
+    int32_t num_simulations;    /* MCTSConfig::numSimulations (800) */
+    float   c_puct;             /* MCTSConfig::cPuct (1.5) */
+    int32_t virtual_loss;       /* MCTSConfig::virtualLoss (3) */
+    int32_t evaluator;          /* AZ_EVAL_* */
+    int32_t net_blocks;         /* residual blocks (10) */
+    int32_t net_channels;       /* trunk width (128) */
+    int32_t max_nodes_per_tree; /* node-pool capacity per slot; 0 = default */
+    int32_t deterministic;      /* 1 = noise off, first-max-visit move (the reference's forced useBatchInference
+                                   branch, parallel_mcts.cpp:1018-1021,1037-1039); 0 = Dirichlet noise + temperature */
+    float   dirichlet_alpha;    /* 0.03 */
+    float   dirichlet_epsilon;  /* 0.25 */
+    float   init_temperature;   /* 1.0 */
+    float   final_temperature;  /* 0.0 */
+    int32_t temperature_drop_move; /* 30 */
+    int32_t auto_restart;       /* 1 = a finished game's slot starts a new game (self-play); 0 = slot goes idle */
+    int32_t sample_ring_capacity; /* finished-game sample records held on device until drained; 0 = default */
+    int32_t device;             /* CUDA device ordinal */
+    uint64_t seed;              /* Philox key for noise / temperature sampling */
+} az_config;
+
+/* mcts::MCTSStats (include/alphazero/mcts/parallel_mcts.h:77-99) + engine counters, cumulative */
+typedef struct az_stats {
+    uint64_t simulations, evaluations, terminal_leaves, nodes_created, nodes_expanded, pool_overflows,
+             moves, games, samples_dropped;
+    uint64_t kernel_launches;   /* CUDA kernels this engine has launched */
+    uint64_t waves;
+} az_stats;
+
+typedef struct az_engine az_engine;
+
+AZ_API void az_config_default(az_config* cfg);
+AZ_API const char* az_last_error(void);
+
+/* ParallelMCTS ctor + SelfPlayManager ctor (src/mcts/parallel_mcts.cpp:44-96, src/selfplay/self_play_manager.cpp:16-37) */
+AZ_API int az_engine_create(const az_config* cfg, az_engine** out);
+AZ_API int az_engine_destroy(az_engine* e);
+
+/* TorchNeuralNetwork model load (src/nn/torch_neural_network.cpp:90): `blob` is the AZW1 fp32 weight file
+ * written by alphazero-multi-game_b200/net.py:export_weights; BatchNorm is folded and bf16 images built here. */
+AZ_API int az_engine_load_weights(az_engine* e, const void* blob, size_t bytes);
+
+/* createGameState + ParallelMCTS(rootState,...) for every slot: empty boards, fresh trees
+ * (src/selfplay/self_play_manager.cpp:157-175) */
+AZ_API int az_engine_reset_games(az_engine* e);
+/* ParallelMCTS::initialize(rootState) for one slot: root = empty board + `moves`.  `first_fill_order`
+ * (may be NULL → descending order) is the legal-move order of the root's first expansion (QUIRK G2). */
+AZ_API int az_engine_set_root(az_engine* e, int slot, const int32_t* moves, int n_moves,
+                       const int32_t* first_fill_order, int n_order);
+/* ParallelMCTS::search() on every active slot: root expansion if needed, then `sims` simulations per tree
+ * as `sims` waves (src/mcts/parallel_mcts.cpp:142-274, serial semantics per tree). sims<=0 → config value. */
+AZ_API int az_engine_search(az_engine* e, int sims);
+/* root children in child order (rootNode_->children[i]): action, visitCount, valueSum, prior;
+ * *n_children in: capacity, out: count.  root_visits/root_value_sum are the root node's own fields. */
+AZ_API int az_engine_root_stats(az_engine* e, int slot, int32_t* actions, int32_t* visits, float* value_sums,
+                         float* priors, int32_t* n_children, int32_t* root_visits, float* root_value_sum);
+/* ParallelMCTS::updateWithMove(action) per slot (src/mcts/parallel_mcts.cpp:1065-1108); actions[slot] = -2 skips a slot */
+AZ_API int az_engine_advance(az_engine* e, const int32_t* actions, int n);
+/* SelfPlayManager::playSingleGame loop body for all slots, `n_moves` times: search → getActionProbabilities /
+ * selectAction / getRootValue → record → makeMove → updateWithMove → noise (src/selfplay/self_play_manager.cpp:187-217) */
+AZ_API int az_engine_play(az_engine* e, int n_moves);
+/* action chosen by the last az_engine_play / az_engine_advance per slot (-2 = slot did not move) */
+AZ_API int az_engine_last_actions(az_engine* e, int32_t* actions, int n);
+/* per-slot state: result (AZ_*), ply, player to move */
+AZ_API int az_engine_slot_state(az_engine* e, int slot, int32_t* result, int32_t* ply, int32_t* player);
+
+/* GameRecord/MoveData stream (include/alphazero/selfplay/game_record.h:18-70): finished-game samples.
+ * Record layout: az_engine_sample_layout.  drain copies up to cap records to host and empties the ring. */
+typedef struct az_sample_layout {
+    int32_t record_bytes, off_game_id, off_slot, off_ply, off_action, off_player, off_z, off_result,
+            off_root_value, off_root_visits, off_state, state_bytes, off_visits, n_visits;
+} az_sample_layout;
+AZ_API int az_engine_sample_layout(az_engine* e, az_sample_layout* out);
+AZ_API int az_engine_drain_samples(az_engine* e, void* host_buf, size_t cap_records, size_t* n_records);
+/* device-side variant for the NCCL all-gather: packs the ring into caller-provided DEVICE memory */
+AZ_API int az_engine_drain_samples_device(az_engine* e, void* dev_buf, size_t cap_records, size_t* n_records);
+
+AZ_API int az_engine_get_stats(az_engine* e, az_stats* out);
+AZ_API int az_engine_sync(az_engine* e);
+
+/* NeuralNetwork::predictBatch (src/nn/torch_neural_network.cpp:224-363) on caller-supplied feature planes:
+ * planes fp32 [n][C][H][W] (host) → policy fp32 [n][A] (softmax over the A logits, :298-316), value fp32 [n]. */
+AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits_or_null);
+/* same forward on already-resident device inputs in the trunk's layout, `reps` times (kernel timing) */
+AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms_per_rep);
+
+/* one 128→128-channel 3x3 conv layer (the dominant kernel) alone, `reps` launches, CUDA-event timed on the
+ * engine's stream: ms per launch (roofline numerator for bench.py) */
+AZ_API int az_engine_conv_bench(az_engine* e, int n_boards, int reps, float* ms_per_launch);
+/* CUDA events on the engine's own stream (torch.cuda.Event only sees torch's stream): record slot idx (0..7),
+ * elapsed(i → j) in ms after synchronising on j */
+AZ_API int az_engine_event_record(az_engine* e, int idx);
+AZ_API int az_engine_event_elapsed(az_engine* e, int i, int j, float* ms);
+
+/* IGameState on the device rules kernels (include/alphazero/core/igamestate.h:60-223), batched: replays
+ * `n_moves[g]` moves of game g from the empty board, then reports per game: legal moves in reference order
+ * (legal[g*A .. ], n_legal[g]), isTerminal, getGameResult, getCurrentPlayer and the enhanced tensor
+ * (planes [g][C][H][W] fp32, may be NULL). */
+AZ_API int az_rules_replay(az_engine* e, const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves,
+                    int32_t* legal, int32_t* n_legal, int32_t* terminal, int32_t* result, int32_t* player,
+                    float* planes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_B200_H */

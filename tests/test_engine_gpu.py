@@ -1,0 +1,183 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against the
+oracle (CPU restatement, pinned to the reference) and the golden fixtures generated from the reference itself.
+
+Bar (BASELINE.json north_star): legal moves, terminal flags and per-root visit counts bit-exact; Q within 1e-6
+(here W and P are compared as IEEE bit patterns, which is stronger)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _orc
+from _orc import GOMOKU
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def test_rules_kernels_match_golden_and_oracle():
+    """Device rules (apply / win / draw / legal order / 11-plane encoder) on the golden playouts."""
+    from _eng import hash_engine
+    O = _orc.oracle()
+    for board in (15, 9):
+        eng = hash_engine(4, board=board, sims=8)
+        games, expect = [], []
+        for case in json.load(open(os.path.join(GOLD, "state_playouts.json"))):
+            if case["game"] != GOMOKU or case["board"] != board:
+                continue
+            s = O.new_state(GOMOKU, board)
+            for ply in range(len(case["moves"]) + 1):
+                games.append(case["moves"][:ply])
+                expect.append((np.sort(O.legal(s))[::-1].copy(), O.state_is_terminal(s), O.state_result(s),
+                               O.state_current_player(s), O.tensor(s)))
+                if ply < len(case["moves"]):
+                    O.state_make_move(s, case["moves"][ply])
+        assert len(games) > 100
+        r = eng.rules_replay(games)
+        for i, (legal, term, res, pl, planes) in enumerate(expect):
+            assert np.array_equal(r["legal"][i], legal), (board, i)
+            assert r["terminal"][i] == term and r["result"][i] == res and r["player"][i] == pl, (board, i)
+            assert np.array_equal(r["planes"][i], planes), (board, i)
+        # illegal replays are reported, not applied (reference make_move throws, gomoku_state.cpp:681-689)
+        bad = eng.rules_replay([[0, 0], [board * board]])
+        assert bad["n_legal"][0] == -1 and bad["n_legal"][1] == -1
+        eng.close()
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_search_matches_reference_golden(idx):
+    """Serial-search parity on the golden cases generated from the patched reference (Gomoku 15x15 @800 sims,
+    9x9 @200 sims): child order, visit counts, valueSum and prior bits, root leak, chosen move."""
+    from _eng import hash_engine
+    case = json.load(open(os.path.join(GOLD, "search_hash_eval.json")))[idx]
+    assert case["game"] == GOMOKU
+    eng = hash_engine(3, board=case["board"], sims=case["sims"])
+    for mv, g in enumerate(case["moves"]):
+        eng.search()
+        for slot in range(3):                      # identical games in every slot
+            st = eng.root_stats(slot)
+            assert st["actions"].tolist() == g["actions"], (mv, slot)
+            assert st["N"].tolist() == g["N"], (mv, slot)
+            assert bits(st["W"]).tolist() == g["W"], (mv, slot)
+            assert bits(st["P"]).tolist() == g["P"], (mv, slot)
+            assert st["rootN"] == g["rootN"] and int(bits([st["rootW"]])[0]) == g["rootW"]
+        eng.advance([g["action"]] * 3)
+        if eng.slot_state(0)[0] != 0:
+            break
+    st = eng.stats()
+    assert st["pool_overflows"] == 0
+    eng.close()
+
+
+def test_search_matches_oracle_random_openings():
+    """Different position in every slot, searched together wave by wave, each compared with the oracle's serial
+    search: covers enumerated roots (descending order) and never-enumerated roots (first-fill order, QUIRK G2)."""
+    from _eng import hash_engine
+    O = _orc.oracle()
+    rng = np.random.default_rng(11)
+    T, sims, board = 12, 300, 15
+    eng = hash_engine(T, board=board, sims=sims)
+    states, searches = [], []
+    for t in range(T):
+        s = O.new_state(GOMOKU, board)
+        nply = int(rng.integers(0, 40))
+        moves = rng.choice(board * board, nply, replace=False).tolist()
+        enumerated = (t % 2 == 0)
+        for a in moves:
+            if enumerated:
+                O.legal(s)
+            assert O.state_make_move(s, int(a)) == 0
+        if O.state_is_terminal(O.state_clone(s)):       # (clone: do not disturb s's cache state)
+            moves = []; s = O.new_state(GOMOKU, board); enumerated = False
+        if enumerated:
+            O.legal(s)
+            eng.set_root(t, moves)
+        else:
+            empties = [a for a in range(board * board) if a not in set(moves)]
+            eng.set_root(t, moves, first_fill_order=_orc.first_fill_order(empties))
+        states.append(s)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+    for mv in range(4):
+        eng.search()
+        acts = []
+        for t in range(T):
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            assert np.array_equal(a["actions"], b["actions"]), (mv, t)
+            assert np.array_equal(a["N"], b["N"]), (mv, t)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (mv, t)
+            assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0]
+            q_e = a["W"][a["N"] > 0] / a["N"][a["N"] > 0]
+            q_o = b["W"][b["N"] > 0] / b["N"][b["N"] > 0]
+            assert np.max(np.abs(q_e - q_o), initial=0.0) <= 1e-6          # the stated Q tolerance
+            act = O.mcts_select_action(searches[t], 1, 1.0)
+            acts.append(act)
+            O.mcts_update_with_move(searches[t], act)
+        eng.advance(acts)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
+
+
+def test_selfplay_loop_matches_oracle_full_game():
+    """az_engine_play (search → choose → record → re-root → turnover) in deterministic mode against the oracle's
+    playSingleGame restatement, a whole 9x9 game: same moves, same recorded visit counts, same result, and the
+    drained sample records carry the right z."""
+    from _eng import hash_engine
+    O = _orc.oracle()
+    board, sims = 9, 120
+    eng = hash_engine(2, board=board, sims=sims)
+    s = O.new_state(GOMOKU, board)
+    m = O.mcts_new(s, sims, 1.5, 3, 0, None, None)
+    moves, visit_rows, rvals = [], [], []
+    while not O.state_is_terminal(s):
+        O.mcts_search(m)
+        st = O.root_stats(m)
+        v = np.zeros(board * board, np.int64); v[st["actions"]] = st["N"]
+        a = O.mcts_select_action(m, 1, 1.0)
+        visit_rows.append(v); moves.append(a); rvals.append(O.mcts_root_value(m))
+        O.state_make_move(s, a); O.mcts_update_with_move(m, a)
+    result = O.state_result(s)
+    for i, a in enumerate(moves):
+        eng.play(1)
+        assert eng.last_actions().tolist() == [a, a], i
+    assert eng.slot_state(0)[0] == result
+    smp = eng.drain_samples()
+    assert len(smp) == 2 * len(moves)
+    s0 = np.sort(smp[smp["slot"] == 0], order="ply")
+    assert s0["action"].tolist() == moves
+    for i in range(len(moves)):
+        assert np.array_equal(s0["visits"][i][:board * board].astype(np.int64), visit_rows[i]), i
+        assert bits([s0["root_value"][i]])[0] == bits([rvals[i]])[0]
+        pl = 1 + (i % 2)
+        z = 0 if result == 1 else (1 if (result == 2) == (pl == 1) else -1)
+        assert s0["z"][i] == z and s0["result"][i] == result and s0["player"][i] == pl
+    st = eng.stats()
+    assert st["games"] == 2 and st["moves"] == 2 * len(moves) and st["pool_overflows"] == 0
+    eng.close()
+
+
+def test_selfplay_auto_restart_and_noise_smoke():
+    """Throughput-mode loop (Dirichlet noise + temperature sampling + auto-restart): invariants only —
+    visit counts sum to sims (+ reused subtree), games finish, slots restart, samples are well-formed."""
+    from _eng import hash_engine
+    board, sims, T = 9, 64, 64
+    eng = hash_engine(T, board=board, sims=sims, deterministic=0, auto_restart=1, seed=7)
+    total = 0
+    for _ in range(30):
+        eng.play(3)
+        smp = eng.drain_samples()
+        total += len(smp)
+        if len(smp):
+            assert np.all(smp["visits"][:, :board * board].sum(1) >= sims - 1)
+            assert np.all(np.abs(smp["z"]) <= 1) and np.all(smp["result"] >= 1)
+            played = smp["visits"][np.arange(len(smp)), smp["action"]]
+            assert np.all(played >= 1)
+    st = eng.stats()
+    assert st["games"] >= 1 and total >= 1 and st["pool_overflows"] == 0 and st["samples_dropped"] == 0
+    assert st["moves"] == 90 * T
+    eng.close()

@@ -1,0 +1,68 @@
+"""GPU parity of the bf16 tcgen05 trunk + heads against the fp32 PyTorch network (the TorchScript-equivalent
+oracle, SURVEY.md §8c "third-party arithmetic": parity unpinned by the reference's own tests, so the oracle is
+torch fp32 on CPU).  Tolerance (BASELINE.json north_star): value |Δ| <= 1e-2, policy KL(fp32 || bf16) <= 1e-3."""
+import numpy as np
+import pytest
+
+import _orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _positions(n, board=15, seed=0):
+    O = _orc.oracle()
+    rng = np.random.default_rng(seed)
+    xs = []
+    for g in range(n):
+        s = O.new_state(_orc.GOMOKU, board)
+        for _ in range(int(rng.integers(0, 70))):
+            O.state_make_move(s, int(rng.choice(O.legal(s))))
+            if O.state_is_terminal(s):
+                break
+        xs.append(O.tensor(s))
+    return np.stack(xs)
+
+
+def _check(model, n_pos, slots, tag):
+    import torch
+    import torch.nn.functional as F
+    from _eng import E, N
+    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=slots, evaluator=E.EVAL_RESNET, net_blocks=model.blocks_n,
+                   net_channels=128, num_simulations=8, max_nodes_per_tree=4096, deterministic=1)
+    eng.load_weights(N.export_weights(model))
+    x = _positions(n_pos)
+    pol, val, logits = eng.nn_forward(x, want_logits=True)
+    with torch.no_grad():
+        torch.set_num_threads(8)
+        p32, v32 = model(torch.tensor(x))
+    lp32 = F.log_softmax(p32, 1)
+    lp = torch.log(torch.tensor(pol).clamp_min(1e-30))
+    kl = (lp32.exp() * (lp32 - lp)).sum(1).numpy()
+    verr = np.abs(val - v32.numpy().reshape(-1))
+    dl = np.abs(logits - p32.numpy())
+    print(f"[{tag}] max KL {kl.max():.3e}  max |dv| {verr.max():.3e}  max |dlogit| {dl.max():.3e}  logit std {p32.std():.2f}")
+    assert np.all(np.isfinite(pol)) and np.allclose(pol.sum(1), 1.0, atol=1e-4)
+    assert kl.max() <= 1e-3, f"{tag}: policy KL {kl.max()}"
+    assert verr.max() <= 1e-2, f"{tag}: value error {verr.max()}"
+    eng.close()
+
+
+@pytest.mark.parametrize("blocks", [0, 1, 10])
+def test_trunk_matches_fp32_calibrated_heads(blocks):
+    """Non-saturated heads + randomised BatchNorm statistics so folding, residual adds and the heads are all
+    exercised with outputs in their sensitive range; blocks=0 isolates the stem conv + heads, 1 adds one
+    residual block (both 128-channel conv variants), 10 is the BASELINE network depth."""
+    import torch
+    from _eng import N
+    m = N.make_random_model(seed=1, randomize_bn=True, blocks=blocks)
+    with torch.no_grad():
+        scale = {0: 1.0, 1: 0.5, 10: 0.03}[blocks]
+        m.p_fc.weight *= scale; m.v_fc1.weight *= scale * 0.7; m.v_fc2.weight *= 0.2
+        m.p_fc.bias.uniform_(-0.5, 0.5); m.v_fc1.bias.uniform_(-0.1, 0.1); m.v_fc2.bias.uniform_(-0.2, 0.2)
+    _check(m, 37, 64, f"calibrated-{blocks}")
+
+
+def test_trunk_matches_fp32_reference_init_model():
+    """`random_model_gomoku_15x15` equivalent (reference init, seed 0, 10 blocks x 128 channels)."""
+    from _eng import N
+    _check(N.make_random_model(seed=0), 300, 512, "reference-init")
