@@ -451,10 +451,12 @@ __global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, c
             sc.flags[sb] = tp.flags[base + cc]; sc.first[sb] = -1; sc.nchild[sb] = 0; sc.old_id[sb] = cc;
         }
         __syncwarp();
-        for (int j0 = 0; j0 < count; j0 += 32) {
+        for (int j0 = 0; j0 < count;) {
+            // only nodes that exist at the start of the chunk; nodes appended meanwhile wait for a later chunk
+            const int end = min(j0 + 32, count);
             const int j = j0 + lane;
             int fo = -1, no = 0;
-            if (j < count) { const int o = sc.old_id[sb + j]; fo = tp.first[base + o]; no = tp.nchild[base + o]; }
+            if (j < end) { const int o = sc.old_id[sb + j]; fo = tp.first[base + o]; no = tp.nchild[base + o]; }
             unsigned m = __ballot_sync(0xffffffffu, fo >= 0);
             while (m) {
                 const int src = __ffs(m) - 1; m &= m - 1;
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, c
                 count += n;
             }
             __syncwarp();
+            j0 = end;
         }
         for (int i = lane; i < count; i += 32) {
             tp.N[base + i] = sc.N[sb + i]; tp.W[base + i] = sc.W[sb + i]; tp.P[base + i] = sc.P[sb + i]; tp.first[base + i] = sc.first[sb + i];
