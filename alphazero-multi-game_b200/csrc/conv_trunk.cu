@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
         uint32_t wit = 0, ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+            if ((p.dbg & 8) && ait >= 2) { if (!(p.dbg & 4)) goto weights; continue; }
             mbar_wait(&a_empty[as], aph ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&a_full[as], C::A_STAGE);
@@ -73,8 +74,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                 for (int kc = 0; kc < C::KCH; ++kc)
                     bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
             }
+        weights:
             for (int st = 0; st < 9 * C::STAGES_PER_TAP; ++st, ++wit) {
                 const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
+                if ((p.dbg & 4) && wit >= C::NWS) continue;
                 mbar_wait(&w_empty[ws], wph ^ 1);
                 if (lane == 0) {
                     mbar_arrive_expect_tx(&w_full[ws], C::W_STAGE);
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
         uint32_t wit = 0, ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-            mbar_wait(&a_full[as], ph);
+            if (!((p.dbg & 8) && ait >= 2)) mbar_wait(&a_full[as], ph);
             mbar_wait(&acc_empty[as], ph ^ 1);
             tc_fence_after();
             const uint32_t acc = tmem_base + as * 256;
@@ -98,13 +101,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                 const int shift = (tap / 3 - 1) * p.row_pitch + (tap % 3 - 1);
                 for (int h = 0; h < C::STAGES_PER_TAP; ++h, ++wit) {
                     const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
-                    mbar_wait(&w_full[ws], wph);
+                    if (!((p.dbg & 4) && wit >= C::NWS)) mbar_wait(&w_full[ws], wph);
                     tc_fence_after();
                     if (lane == 0) {
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-                            for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                        for (int it = 0; it < 2 * C::KSTEPS; ++it) {
+                            {
+                                const int mt = (p.dbg & 1) ? (it & 1) : (it / C::KSTEPS);
+                                const int kk = (p.dbg & 1) ? (it >> 1) : (it % C::KSTEPS);
                                 const int kc = h * (C::WK / 8) + 2 * kk;
                                 const uint32_t a_addr = sA_u + as * C::A_STAGE + kc * C::PLANE + (CONV_HALO + mt * 128 + shift) * 16;
                                 const uint32_t b_addr = sW_u + ws * C::W_STAGE + (2 * kk) * C::WPLANE;
@@ -112,12 +116,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                                           (tap | h | kk) != 0 ? 1u : 0u);
                             }
                         }
-                        umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
+                        if (!(p.dbg & 4)) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
                     }
                     __syncwarp();
                 }
             }
-            if (lane == 0) { umma_commit(&a_empty[as]); umma_commit(&acc_full[as]); }
+            if (lane == 0) { if (!(p.dbg & 8)) umma_commit(&a_empty[as]); umma_commit(&acc_full[as]); }
             __syncwarp();
         }
     } else {
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     uint4 res[4];
+                    if (p.dbg & 2) { tmem_ld_wait(); continue; }
                     if (p.resid != nullptr) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)

@@ -46,6 +46,7 @@ struct ConvParams {
     int p_total;                    // rows per channel-chunk plane
     int row_pitch;                  // W + 1
     int relu;
+    int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
 };
 
 size_t conv_smem_bytes(int cin);

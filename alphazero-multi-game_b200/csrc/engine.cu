@@ -5,6 +5,7 @@
 // and moves results across the ABI.  Reference counterparts: ParallelMCTS (src/mcts/parallel_mcts.cpp),
 // SelfPlayManager (src/selfplay/self_play_manager.cpp), TorchNeuralNetwork (src/nn/torch_neural_network.cpp).
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <memory>
@@ -532,6 +533,7 @@ struct EngineT : EngineBase {
         cp.rowvalid = net.rowvalid; cp.n_boards_dev = nullptr; cp.n_rows = n_boards * net.board_pitch; cp.board_pitch = net.board_pitch;
         cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[1]; cp.bias = net.w.conv_b[1];
+        if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, stream) == 0, "conv launch failed");
         AZ_CUDA_CHECK(cudaEventRecord(e0, stream));
