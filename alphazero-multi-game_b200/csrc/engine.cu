@@ -25,6 +25,7 @@ void set_error(const std::string& s) { g_error = s; }
 #include "tree_kernels.cuh"
 #include "conv_trunk.cuh"
 #include "heads.cuh"
+#include "gemm_tc.cuh"
 
 namespace az {
 
@@ -38,7 +39,8 @@ static int dev_alloc(T** p, size_t n) { AZ_CUDA_CHECK(cudaMalloc((void**)p, std:
 struct NetWeights {            // device images
     std::vector<__nv_bfloat16*> conv_w;   // stem + 2*blocks
     std::vector<float*> conv_b;
-    float *w1x1 = nullptr, *b1x1 = nullptr, *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;
+    float *b1x1 = nullptr, *pfc_b = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;   // fp32 biases / tiny last layer
+    __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
 };
 
 struct Net {
@@ -48,7 +50,9 @@ struct Net {
     NetWeights w;
     __nv_bfloat16 *in16 = nullptr, *X = nullptr, *Y = nullptr;
     uint8_t* rowvalid = nullptr;
-    float *featbuf = nullptr, *logits = nullptr, *hidden = nullptr;
+    __nv_bfloat16 *pooled = nullptr, *featP = nullptr, *featV = nullptr;   // head GEMM operands (bf16, chunk-plane layout)
+    float *logits = nullptr, *hidden = nullptr;
+    int boards_cap = 0;
     int n_sms = 148;
     unsigned long long launches = 0;
 
@@ -72,7 +76,12 @@ struct Net {
                 for (int x = 0; x < W; ++x) rv[nn::CONV_GUARD + (size_t)b * board_pitch + y * row_pitch + x] = 1;
         if (dev_alloc(&rowvalid, (size_t)p_total)) return -1;
         AZ_CUDA_CHECK(cudaMemcpy(rowvalid, rv.data(), p_total, cudaMemcpyHostToDevice));
-        if (dev_alloc(&featbuf, (size_t)max_boards * 2 * feat)) return -1;
+        AZ_CHECK(PH == 8 && PW == 8, "heads are built for an 8x8 pooled map (board >= 8)");
+        boards_cap = (max_boards + 127) / 128 * 128;
+        if (dev_alloc(&pooled, (size_t)2 * (C / 8) * 64 * boards_cap * 8) || dev_alloc(&featP, (size_t)512 * boards_cap * 8) || dev_alloc(&featV, (size_t)512 * boards_cap * 8)) return -1;
+        AZ_CUDA_CHECK(cudaMemset(pooled, 0, (size_t)2 * (C / 8) * 64 * boards_cap * 16));
+        AZ_CUDA_CHECK(cudaMemset(featP, 0, (size_t)512 * boards_cap * 16));
+        AZ_CUDA_CHECK(cudaMemset(featV, 0, (size_t)512 * boards_cap * 16));
         if (dev_alloc(&logits, (size_t)max_boards * A)) return -1;
         if (dev_alloc(&hidden, (size_t)max_boards * 256)) return -1;
         int dev = 0; cudaGetDevice(&dev);
@@ -115,21 +124,42 @@ struct Net {
             AZ_CUDA_CHECK(cudaMemcpy(db, sh.data(), C * 4, cudaMemcpyHostToDevice));
             w.conv_w.push_back(dw); w.conv_b.push_back(db);
         }
-        std::vector<float> w1((size_t)64 * C), b1(64);
+        std::vector<float> b1(64);
         const float* pcw = take((size_t)32 * C); const float* pbn = take(128);
         const float* pfw = take((size_t)A * feat); const float* pfb = take(A);
         const float* vcw = take((size_t)32 * C); const float* vbn = take(128);
         const float* v1w = take((size_t)256 * feat); const float* v1b = take(256);
         const float* v2w = take(256); const float* v2b = take(1);
         AZ_CHECK(pcw && pbn && pfw && pfb && vcw && vbn && v1w && v1b && v2w && v2b, "weight blob truncated (heads)");
+        AZ_CHECK(A <= 256, "policy FC image is built for <= 256 actions");
+        // Head GEMMs run as a three-term bf16 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (K' = 3K) so that the heads add no
+        // bf16 rounding of their own on top of the trunk's: weight images are [W_hi | W_hi | W_lo] along K.
+        auto put3 = [](std::vector<__nv_bfloat16>& img, int K, int n, int k, float v) {
+            const __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
+            img[nn::gemm_weight_index(3 * K, n, k)] = hi; img[nn::gemm_weight_index(3 * K, n, K + k)] = hi; img[nn::gemm_weight_index(3 * K, n, 2 * K + k)] = lo;
+        };
+        // GEMM 1: both 1x1 convs as one [64 x C] matrix (rows 0-31 policy, 32-63 value), BatchNorm scale folded in
         std::vector<float> sc, sh;
+        std::vector<__nv_bfloat16> g1(nn::gemm_weight_elems(64, 3 * C), __float2bfloat16(0.0f));
         fold(pbn, 32, sc, sh);
-        for (int o = 0; o < 32; ++o) { b1[o] = sh[o]; for (int c = 0; c < C; ++c) w1[(size_t)o * C + c] = pcw[(size_t)o * C + c] * sc[o]; }
+        for (int o = 0; o < 32; ++o) { b1[o] = sh[o]; for (int c = 0; c < C; ++c) put3(g1, C, o, c, pcw[(size_t)o * C + c] * sc[o]); }
         fold(vbn, 32, sc, sh);
-        for (int o = 0; o < 32; ++o) { b1[32 + o] = sh[o]; for (int c = 0; c < C; ++c) w1[(size_t)(32 + o) * C + c] = vcw[(size_t)o * C + c] * sc[o]; }
+        for (int o = 0; o < 32; ++o) { b1[32 + o] = sh[o]; for (int c = 0; c < C; ++c) put3(g1, C, 32 + o, c, vcw[(size_t)o * C + c] * sc[o]); }
+        // GEMM 2/3: FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the
+        // 1x1-conv GEMM writes (cell*32 + ch); N padded to 256 with zero rows
+        std::vector<__nv_bfloat16> pimg(nn::gemm_weight_elems(256, 3 * feat), __float2bfloat16(0.0f)), vimg(nn::gemm_weight_elems(256, 3 * feat), __float2bfloat16(0.0f));
+        for (int n = 0; n < 256; ++n)
+            for (int ch = 0; ch < 32; ++ch)
+                for (int cell = 0; cell < 64; ++cell) {
+                    const int kp = cell * 32 + ch, kt = ch * 64 + cell;
+                    if (n < A) put3(pimg, feat, n, kp, pfw[(size_t)n * feat + kt]);
+                    put3(vimg, feat, n, kp, v1w[(size_t)n * feat + kt]);
+                }
+        std::vector<float> pb(256, 0.0f); for (int n = 0; n < A; ++n) pb[n] = pfb[n];
         auto up = [&](float** d, const float* src, size_t n) -> int { if (dev_alloc(d, n)) return -1; AZ_CUDA_CHECK(cudaMemcpy(*d, src, n * 4, cudaMemcpyHostToDevice)); return 0; };
-        if (up(&w.w1x1, w1.data(), w1.size()) || up(&w.b1x1, b1.data(), 64) || up(&w.pfc_w, pfw, (size_t)A * feat) || up(&w.pfc_b, pfb, A) ||
-            up(&w.vfc1_w, v1w, (size_t)256 * feat) || up(&w.vfc1_b, v1b, 256) || up(&w.vfc2_w, v2w, 256) || up(&w.vfc2_b, v2b, 1)) return -1;
+        auto upb = [&](__nv_bfloat16** d, const std::vector<__nv_bfloat16>& v) -> int { if (dev_alloc(d, v.size())) return -1; AZ_CUDA_CHECK(cudaMemcpy(*d, v.data(), v.size() * 2, cudaMemcpyHostToDevice)); return 0; };
+        if (up(&w.b1x1, b1.data(), 64) || up(&w.pfc_b, pb.data(), 256) || up(&w.vfc1_b, v1b, 256) || up(&w.vfc2_w, v2w, 256) || up(&w.vfc2_b, v2b, 1) ||
+            upb(&w.g1_w, g1) || upb(&w.pfc_img, pimg) || upb(&w.vfc1_img, vimg)) return -1;
         loaded = true;
         return 0;
     }
@@ -137,12 +167,13 @@ struct Net {
         for (auto p : w.conv_w) cudaFree(p);
         for (auto p : w.conv_b) cudaFree(p);
         w.conv_w.clear(); w.conv_b.clear();
-        for (float** p : {&w.w1x1, &w.b1x1, &w.pfc_w, &w.pfc_b, &w.vfc1_w, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b}) { cudaFree(*p); *p = nullptr; }
+        for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b}) { cudaFree(*p); *p = nullptr; }
+        for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img}) { cudaFree(*p); *p = nullptr; }
         loaded = false;
     }
     void destroy() {
         free_weights();
-        for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)featbuf, (void*)logits, (void*)hidden}) cudaFree(p);
+        for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)pooled, (void*)featP, (void*)featV, (void*)logits, (void*)hidden}) cudaFree(p);
     }
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
     int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
@@ -158,12 +189,18 @@ struct Net {
             cp.in = Y; cp.out = X; cp.resid = X; cp.w = w.conv_w[2 + 2 * b]; cp.bias = w.conv_b[2 + 2 * b];
             AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
         }
-        nn::HeadParams hp{X, w.w1x1, w.b1x1, featbuf, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD};
-        AZ_CHECK(nn::head_pool_conv_launch(hp, n_sms * 2, s) == 0, "head launch failed"); ++launches;
-        nn::FcParams fp{featbuf, w.pfc_w, w.pfc_b, logits, n_dev, n_fixed, feat, A, 2 * feat, A, 0};
-        AZ_CHECK(nn::fc_launch(fp, n_sms * 2, s) == 0, "policy fc launch failed"); ++launches;
-        nn::FcParams fv{featbuf + feat, w.vfc1_w, w.vfc1_b, hidden, n_dev, n_fixed, feat, 256, 2 * feat, 256, 1};
-        AZ_CHECK(nn::fc_launch(fv, n_sms * 2, s) == 0, "value fc launch failed"); ++launches;
+        // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
+        nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
+        AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
+        nn::GemmParams g1{}; g1.A = pooled; g1.B = w.g1_w; g1.bias = w.b1x1; g1.a_rows = 64 * boards_cap; g1.a_plane_mod = 2 * (C / 8); g1.K = 3 * C; g1.n_tiles = 1; g1.n_valid = 64;
+        g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
+        g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
+        AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
+        nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = 3 * feat; g2.n_tiles = 4; g2.n_valid = A;
+        g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits; g2.ldo = A;
+        AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
+        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
+        AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         nn::OutParams op{logits, hidden, w.vfc2_w, w.vfc2_b, policy, value, n_dev, n_fixed, A, 256};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
         return 0;

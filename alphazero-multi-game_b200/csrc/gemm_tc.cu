@@ -1,0 +1,222 @@
+// gemm_tc.cu — small K-pipelined GEMM on tcgen05 for the network heads (1x1 convs and the FC layers):
+//   D[m][n] = act( sum_k A[m][k] * B[n][k] + bias[n] ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Operand format is the conv trunk's (conv_trunk.cuh): A lives in HBM as A[k/8][rows][8] bf16, so a 128-row x
+// 64-channel stage is 8 TMA bulk copies of 2 KB and already IS the K-major SWIZZLE_NONE shared-memory image
+// (core matrix = 8 rows x 16 bytes; LBO = 2048 B between K chunks, SBO = 128 B between 8-row groups).  B (weights) is
+// pre-arranged on the host as one contiguous 8 KB image per (n-tile of 64, K stage of 64).
+// Work item = (M tile of 128 rows, N tile of 64 columns); 4-stage TMA ring; 64-column accumulators, double-buffered.
+// Warp roles as in the conv kernel: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer / TMEM allocator.
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace az { namespace nn {
+
+using namespace az::ptx;
+
+namespace {
+
+constexpr int G_BM = 128, G_BN = 64, G_BK = 64;
+constexpr int G_A_STAGE = (G_BK / 8) * G_BM * 16;   // 16 KB
+constexpr int G_B_STAGE = (G_BK / 8) * G_BN * 16;   // 8 KB
+constexpr int G_STAGE = G_A_STAGE + G_B_STAGE;
+constexpr int G_NST = 4;
+constexpr int G_OFF_BARS = G_NST * G_STAGE;
+constexpr int G_OFF_TSLOT = G_OFF_BARS + 16 * 8;
+constexpr int G_SMEM = G_OFF_TSLOT + 16;
+constexpr int G_THREADS = 192;
+
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + G_OFF_TSLOT);
+    uint64_t* full = bars;            // [4] TMA → MMA
+    uint64_t* empty = bars + 4;       // [4] MMA → TMA
+    uint64_t* acc_full = bars + 8;    // [2]
+    uint64_t* acc_empty = bars + 10;  // [2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work decomposition: `units` row groups (GEMM1: the 64 pooled cells; FC: 1), each with m_tiles tiles of 128 rows
+    const int m_valid = p.m_valid_dev ? *p.m_valid_dev : p.m_valid;            // valid rows inside one unit
+    const int m_tiles = (m_valid + G_BM - 1) / G_BM;
+    const int n_items = p.units * m_tiles * p.n_tiles;
+    const int k_stages = p.K / G_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tslot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    if (warp == 4) {
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int nt = item % p.n_tiles, mi = item / p.n_tiles;
+            const int unit = mi / m_tiles, mt = mi % m_tiles;
+            const size_t row0 = (size_t)unit * p.unit_rows + (size_t)mt * G_BM;
+            for (int ks = 0; ks < k_stages; ++ks, ++it) {
+                const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], G_STAGE);
+                    uint8_t* dst = smem + s * G_STAGE;
+                    for (int j = 0; j < G_BK / 8; ++j)
+                        bulk_g2s(dst + j * (G_BM * 16), p.A + ((size_t)((ks * (G_BK / 8) + j) % p.a_plane_mod) * p.a_rows + row0) * 8, G_BM * 16, &full[s]);
+                    bulk_g2s(dst + G_A_STAGE, reinterpret_cast<const uint8_t*>(p.B) + ((size_t)nt * k_stages + ks) * G_B_STAGE, G_B_STAGE, &full[s]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        constexpr uint32_t IDESC = idesc_bf16(G_BM, G_BN);
+        const uint32_t s_u = smem_u32(smem);
+        uint32_t it = 0, ait = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
+            const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+            mbar_wait(&acc_empty[as], aph ^ 1);
+            tc_fence_after();
+            for (int ks = 0; ks < k_stages; ++ks, ++it) {
+                const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < G_BK / 16; ++kk) {
+                        const uint32_t a_addr = s_u + s * G_STAGE + (2 * kk) * (G_BM * 16);
+                        const uint32_t b_addr = s_u + s * G_STAGE + G_A_STAGE + (2 * kk) * (G_BN * 16);
+                        umma_bf16(tmem_base + as * G_BN, smem_desc(a_addr, G_BM * 16, 128), smem_desc(b_addr, G_BN * 16, 128), IDESC,
+                                  (ks | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&acc_full[as]);
+            __syncwarp();
+        }
+    } else {
+        uint32_t ait = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
+            const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+            const int nt = item % p.n_tiles, mi = item / p.n_tiles;
+            const int unit = mi / m_tiles, mt = mi % m_tiles;
+            const int r = mt * G_BM + warp * 32 + lane;          // row inside the unit
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * G_BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < G_BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                if (r < m_valid) {
+                    if (p.mode == GEMM_OUT_FEAT) {
+                        // 1x1-conv output → the FC layers' A layout: feature k' = unit*32 + channel, plane = k'/8, row = board.
+                        // columns 0-31 = policy head, 32-63 = value head.
+                        __nv_bfloat16* dst = (c0 == 0) ? p.out_feat0 : p.out_feat1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o, ol;
+                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+                            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&ol);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float a = __uint_as_float(v[q * 8 + 2 * e]) + p.bias[c0 + q * 8 + 2 * e];
+                                float b = __uint_as_float(v[q * 8 + 2 * e + 1]) + p.bias[c0 + q * 8 + 2 * e + 1];
+                                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                                ob[e] = __floats2bfloat162_rn(a, b);
+                                const float2 hi = __bfloat1622float2(ob[e]);
+                                lb[e] = __floats2bfloat162_rn(a - hi.x, b - hi.y);          // low half of the hi/lo split
+                            }
+                            *reinterpret_cast<uint4*>(dst + ((size_t)(unit * 4 + q) * p.feat_rows + r) * 8) = o;
+                            *reinterpret_cast<uint4*>(dst + ((size_t)(p.feat_lo_plane + unit * 4 + q) * p.feat_rows + r) * 8) = ol;
+                        }
+                    } else {
+                        float* dst = p.out_rows + (size_t)r * p.ldo;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nt * G_BN + c0 + j;
+                            if (n < p.n_valid) {
+                                float a = __uint_as_float(v[j]) + p.bias[n];
+                                if (p.relu) a = fmaxf(a, 0.0f);
+                                dst[n] = a;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
+// adaptive_avg_pool2d (H x W → PH x PW, windows [floor(i*H/PH), ceil((i+1)*H/PH))) of the trunk output, written as the
+// 1x1-conv GEMM's A operand: pooled[c/8][cell * boards_cap + board][8] as a bf16 hi/lo pair (planes [0,C/8) hi,
+// [C/8, 2C/8) lo) so the heads see the fp32 average.  One thread per (board, channel chunk, pooled cell), cell fastest:
+// a warp re-reads neighbouring board rows out of L1, DRAM traffic = the trunk output once.
+__global__ void __launch_bounds__(256) k_pool(PoolParams p) {
+    const int KCH = p.channels / 8;
+    const int PH = p.H < 8 ? p.H : 8, PW = p.W < 8 ? p.W : 8, cells = PH * PW;
+    const int n = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
+    const long long total = (long long)n * KCH * cells;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cell = (int)(i % cells), kc = (int)((i / cells) % KCH), b = (int)(i / ((long long)cells * KCH));
+        const int oy = cell / PW, ox = cell % PW;
+        const int y0 = (oy * p.H) / PH, y1 = ((oy + 1) * p.H + PH - 1) / PH;
+        const int x0 = (ox * p.W) / PW, x1 = ((ox + 1) * p.W + PW - 1) / PW;
+        const __nv_bfloat16* src = p.act + ((size_t)kc * p.p_total + (size_t)p.guard + (size_t)b * p.board_pitch) * 8;
+        float s[8] = {};
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(y * p.row_pitch + x) * 8));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
+            }
+        const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+        uint4 o, ol;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+        __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&ol);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = s[2 * e] * inv, c = s[2 * e + 1] * inv;
+            ob[e] = __floats2bfloat162_rn(a, c);
+            const float2 hi = __bfloat1622float2(ob[e]);
+            lb[e] = __floats2bfloat162_rn(a - hi.x, c - hi.y);
+        }
+        const size_t row = (size_t)cell * p.boards_cap + b;
+        *reinterpret_cast<uint4*>(p.pooled + ((size_t)kc * p.pooled_rows + row) * 8) = o;
+        *reinterpret_cast<uint4*>(p.pooled + ((size_t)(KCH + kc) * p.pooled_rows + row) * 8) = ol;
+    }
+}
+
+}  // namespace
+
+size_t gemm_weight_elems(int n_total, int k_total) { return (size_t)((n_total + 63) / 64) * 64 * k_total; }
+// image[ntile][k stage][k chunk j][n in tile][e]
+size_t gemm_weight_index(int k_total, int n, int k) {
+    const int nt = n / 64, ni = n % 64, ks = k / 64, j = (k % 64) / 8, e = k % 8;
+    return ((((size_t)nt * (k_total / 64) + ks) * 8 + j) * 64 + ni) * 8 + e;
+}
+
+int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
+    static bool done = false;
+    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM); if (e) return (int)e; done = true; }
+    k_gemm_tc<<<grid, G_THREADS, G_SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
+int pool_launch(const PoolParams& p, int grid, cudaStream_t s) {
+    k_pool<<<grid, 256, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}}  // namespace az::nn

@@ -40,7 +40,13 @@ def _check(model, n_pos, slots, tag, saturated=False):
     kl = (lp32.exp() * (lp32 - lp)).sum(1).numpy()
     verr = np.abs(val - v32.numpy().reshape(-1))
     dl = np.abs(logits - p32.numpy())
-    print(f"[{tag}] max KL {kl.max():.3e}  max |dv| {verr.max():.3e}  max |dlogit| {dl.max():.3e}  logit std {p32.std():.2f}")
+    line = (f"[{tag}] max KL {kl.max():.3e}  q99 KL {np.quantile(kl, 0.99):.3e}  max |dv| {verr.max():.3e}  "
+            f"max |dlogit| {dl.max():.3e}  logit std {p32.std():.2f}")
+    print(line)
+    import os
+    log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(log_dir):
+        open(os.path.join(log_dir, "nn_parity.txt"), "a").write(line + "\n")
     assert np.all(np.isfinite(pol)) and np.allclose(pol.sum(1), 1.0, atol=1e-4)
     assert verr.max() <= 1e-2, f"{tag}: value error {verr.max()}"
     if not saturated:
