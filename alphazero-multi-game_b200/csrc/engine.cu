@@ -43,11 +43,13 @@ struct NetWeights {            // device images
     __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
 };
 
+// Net = one set of activation buffers (one per stream group) + a pointer to the shared weights.
 struct Net {
     int blocks = 0, C = 0, in_planes = 0, H = 0, W = 0, A = 0, PH = 0, PW = 0, feat = 0;
     int row_pitch = 0, board_pitch = 0, p_total = 0, max_boards = 0;
     bool loaded = false;
-    NetWeights w;
+    NetWeights w;              // owned by group 0's Net; other groups hold a shallow copy (share())
+    bool owns_weights = true;
     __nv_bfloat16 *in16 = nullptr, *X = nullptr, *Y = nullptr;
     uint8_t* rowvalid = nullptr;
     __nv_bfloat16 *pooled = nullptr, *featP = nullptr, *featV = nullptr;   // head GEMM operands (bf16, chunk-plane layout)
@@ -163,7 +165,9 @@ struct Net {
         loaded = true;
         return 0;
     }
+    void share(const Net& o) { w = o.w; blocks = o.blocks; in_planes = o.in_planes; loaded = o.loaded; owns_weights = false; }
     void free_weights() {
+        if (!owns_weights) { w = NetWeights(); loaded = false; return; }
         for (auto p : w.conv_w) cudaFree(p);
         for (auto p : w.conv_b) cudaFree(p);
         w.conv_w.clear(); w.conv_b.clear();
@@ -275,11 +279,16 @@ struct EngineT : EngineBase {
     using State = typename G::State;
     using SampleT = Sample<G>;
     static constexpr int A = G::CELLS;
+    // Slots are split into `NG` stream groups; each group runs its own wave sequence (select → network → expand) on
+    // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
+    // pass of the other.  Move-commit kernels run once for all slots on the main stream.
+    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; Net net; };
     az_config cfg;
-    int T = 0;
+    int T = 0, NG = 1;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_main = nullptr;
+    std::vector<Group> groups;
     TreePools tp{};
-    WaveBuffers wb{};
     ScratchPools sc{};
     int scratch_trees = 0;
     State *root_state = nullptr, *leaf_state = nullptr;
@@ -288,22 +297,28 @@ struct EngineT : EngineBase {
     SampleT *game_buf = nullptr, *ring = nullptr; int32_t* ring_count = nullptr; int ring_cap = 0; int max_moves = 0;
     float* noise_scratch = nullptr;
     Stats* dstats = nullptr;
-    Net net;
     unsigned long long launches = 0, waves = 0;
     std::vector<int16_t> h_default_order;
 
     ~EngineT() override { destroy(); }
 
     void destroy() {
-        if (stream) cudaStreamSynchronize(stream);
+        cudaDeviceSynchronize();
+        for (auto& g : groups) {
+            for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
+                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval}) cudaFree(p);
+            g.net.destroy();
+            if (g.ev) cudaEventDestroy(g.ev);
+            if (g.stream) cudaStreamDestroy(g.stream);
+        }
+        groups.clear();
+        if (ev_main) { cudaEventDestroy(ev_main); ev_main = nullptr; }
         for (void* p : {(void*)tp.N, (void*)tp.W, (void*)tp.P, (void*)tp.first, (void*)tp.act, (void*)tp.nchild, (void*)tp.flags, (void*)tp.root,
-                        (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id, (void*)wb.path, (void*)wb.path_len,
-                        (void*)wb.leaf_node, (void*)wb.leaf_kind, (void*)wb.leaf_value, (void*)wb.policy, (void*)wb.value, (void*)wb.eval_slot, (void*)wb.n_eval,
+                        (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id,
                         (void*)sc.N, (void*)sc.W, (void*)sc.P, (void*)sc.first, (void*)sc.act, (void*)sc.nchild, (void*)sc.flags, (void*)sc.old_id,
                         (void*)root_state, (void*)leaf_state, (void*)root_order, (void*)default_order, (void*)root_order_n, (void*)chosen_child,
                         (void*)chosen_action, (void*)forced, (void*)game_buf, (void*)ring, (void*)ring_count, (void*)noise_scratch, (void*)dstats})
             cudaFree(p);
-        net.destroy();
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 
@@ -320,9 +335,6 @@ struct EngineT : EngineBase {
         if (dev_alloc(&tp.N, tn) || dev_alloc(&tp.W, tn) || dev_alloc(&tp.P, tn) || dev_alloc(&tp.first, tn) || dev_alloc(&tp.act, tn) ||
             dev_alloc(&tp.nchild, tn) || dev_alloc(&tp.flags, tn) || dev_alloc(&tp.root, T) || dev_alloc(&tp.alloc, T) || dev_alloc(&tp.root_vl, T) ||
             dev_alloc(&tp.tflags, T) || dev_alloc(&tp.move_num, T) || dev_alloc(&tp.game_id, T)) return -1;
-        if (dev_alloc(&wb.path, (size_t)T * MAX_DEPTH) || dev_alloc(&wb.path_len, T) || dev_alloc(&wb.leaf_node, T) || dev_alloc(&wb.leaf_kind, T) ||
-            dev_alloc(&wb.leaf_value, T) || dev_alloc(&wb.policy, (size_t)T * A) || dev_alloc(&wb.value, T) || dev_alloc(&wb.eval_slot, T) ||
-            dev_alloc(&wb.n_eval, 1)) return -1;
         // scratch for re-rooting: as many trees at a time as fit in ~1/8 of the pool memory (at least 1)
         scratch_trees = std::max(1, std::min(T, (int)(((size_t)4 << 30) / ((size_t)cap * 25))));
         const size_t sn = (size_t)scratch_trees * cap;
@@ -344,17 +356,56 @@ struct EngineT : EngineBase {
             h_default_order.assign(us.begin(), us.end());
             AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), A * 2, cudaMemcpyHostToDevice));
         }
-        if (c.evaluator == AZ_EVAL_RESNET) { if (net.init(G::N, G::N, A, T, c.net_channels)) return -1; }
+        AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 2, T));
+        const int per = (T + NG - 1) / NG;
+        groups.resize(NG);
+        for (int gi = 0; gi < NG; ++gi) {
+            Group& g = groups[gi];
+            g.t0 = gi * per; g.n = std::min(per, T - g.t0);
+            AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+            AZ_CUDA_CHECK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
+            const int n = g.n;
+            if (dev_alloc(&g.wb.path, (size_t)n * MAX_DEPTH) || dev_alloc(&g.wb.path_len, n) || dev_alloc(&g.wb.leaf_node, n) || dev_alloc(&g.wb.leaf_kind, n) ||
+                dev_alloc(&g.wb.leaf_value, n) || dev_alloc(&g.wb.policy, (size_t)n * A) || dev_alloc(&g.wb.value, n) || dev_alloc(&g.wb.eval_slot, n) ||
+                dev_alloc(&g.wb.n_eval, 1)) return -1;
+            // view of the pools for this group's slots
+            g.tp = tp;
+            const size_t off = (size_t)g.t0 * cap;
+            g.tp.N += off; g.tp.W += off; g.tp.P += off; g.tp.first += off; g.tp.act += off; g.tp.nchild += off; g.tp.flags += off;
+            g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
+            if (c.evaluator == AZ_EVAL_RESNET) { if (g.net.init(G::N, G::N, A, per, c.net_channels)) return -1; }
+        }
         return reset_games();
     }
 
     SearchParams sparams() const { return SearchParams{cfg.c_puct, cfg.virtual_loss, MAX_DEPTH}; }
     int blocks_for_warps(int n) const { return (n * 32 + 127) / 128; }
 
+    // main stream waits for every group stream (and vice versa): brackets the per-move kernels and host reads
+    int join_groups() {
+        for (auto& g : groups) { AZ_CUDA_CHECK(cudaEventRecord(g.ev, g.stream)); AZ_CUDA_CHECK(cudaStreamWaitEvent(stream, g.ev, 0)); }
+        return 0;
+    }
+    int fork_groups() {
+        AZ_CUDA_CHECK(cudaEventRecord(ev_main, stream));
+        for (auto& g : groups) AZ_CUDA_CHECK(cudaStreamWaitEvent(g.stream, ev_main, 0));
+        return 0;
+    }
+    int sync_all() {
+        for (auto& g : groups) AZ_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    unsigned long long net_launches() const { unsigned long long n = 0; for (auto& g : groups) n += g.net.launches; return n; }
+
     int load_weights(const void* blob, size_t bytes) override {
         AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
-        return net.load(blob, bytes);
+        if (sync_all()) return -1;
+        for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.free_weights();
+        if (groups[0].net.load(blob, bytes)) return -1;
+        for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.share(groups[0].net);
+        return 0;
     }
 
     int write_fresh(int slot, const State& s, const int16_t* order, int n_order, bool first_fill) {
@@ -380,7 +431,7 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_state + slot, &s, sizeof(State), cudaMemcpyHostToDevice, stream));
         if (order && n_order > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(root_order + (size_t)slot * A, order, (size_t)n_order * 2, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_order_n + slot, &n_order, 4, cudaMemcpyHostToDevice, stream));
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));   // host temporaries above go out of scope
+        if (sync_all()) return -1;   // host temporaries above go out of scope
         return 0;
     }
 
@@ -388,7 +439,7 @@ struct EngineT : EngineBase {
         k_reset_all<G><<<(T + 127) / 128, 128, 0, stream>>>(tp, root_state, default_order, A, root_order, root_order_n, cfg.deterministic ? 0 : 1, T);
         AZ_LAUNCH_CHECK(); ++launches;
         AZ_CUDA_CHECK(cudaMemsetAsync(ring_count, 0, 4, stream));
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         return 0;
     }
 
@@ -404,33 +455,41 @@ struct EngineT : EngineBase {
         return write_fresh(slot, s, order ? ord.data() : nullptr, order ? n_order : 0, order != nullptr);
     }
 
-    // one wave: select → evaluator → expand/backup
-    int wave(int mode) {
-        AZ_CUDA_CHECK(cudaMemsetAsync(wb.n_eval, 0, 4, stream));
+    // one wave of one group: select → evaluator → expand/backup, on the group's stream
+    int wave(Group& g, int mode) {
+        cudaStream_t st = g.stream;
+        AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
         EncodeTarget enc{nullptr, 0, 0, 0};
-        if (cfg.evaluator == AZ_EVAL_RESNET) enc = EncodeTarget{net.in16, net.p_total, nn::CONV_GUARD, net.board_pitch};
-        k_select<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, leaf_state, wb, sparams(), enc, T, mode);
+        if (cfg.evaluator == AZ_EVAL_RESNET) enc = EncodeTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch};
+        k_select<G><<<blocks_for_warps(g.n), 128, 0, st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
         if (cfg.evaluator == AZ_EVAL_HASH) {
-            k_hash_eval<G><<<blocks_for_warps(T), 128, 4 * A * sizeof(float), stream>>>(leaf_state, wb, T);
+            k_hash_eval<G><<<blocks_for_warps(g.n), 128, 4 * A * sizeof(float), st>>>(leaf_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
-            if (net.forward(wb.n_eval, 0, wb.policy, wb.value, stream)) return -1;
+            if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
         }
-        k_expand_backup<G><<<blocks_for_warps(T), 128, 4 * A * sizeof(float), stream>>>(tp, leaf_state, wb, root_order, root_order_n, sparams(), T, dstats);
-        AZ_LAUNCH_CHECK(); ++launches; ++waves;
+        k_expand_backup<G><<<blocks_for_warps(g.n), 128, 4 * A * sizeof(float), st>>>(g.tp, leaf_state + g.t0, g.wb, root_order + (size_t)g.t0 * A,
+                                                                                    root_order_n + g.t0, sparams(), g.n, dstats);
+        AZ_LAUNCH_CHECK(); ++launches;
         return 0;
     }
 
     int search(int sims) override {
         if (sims <= 0) sims = cfg.num_simulations;
-        if (wave(1)) return -1;                      // search() preamble: expand unexpanded roots
-        if (!cfg.deterministic) {
-            k_dirichlet<<<blocks_for_warps(T), 128, 0, stream>>>(tp, T, cfg.dirichlet_alpha, cfg.dirichlet_epsilon, cfg.seed, noise_scratch, A);
-            AZ_LAUNCH_CHECK(); ++launches;
+        if (fork_groups()) return -1;
+        for (auto& g : groups) {
+            if (wave(g, 1)) return -1;                  // search() preamble: expand unexpanded roots
+            if (!cfg.deterministic) {
+                k_dirichlet<<<blocks_for_warps(g.n), 128, 0, g.stream>>>(g.tp, g.n, g.t0, cfg.dirichlet_alpha, cfg.dirichlet_epsilon, cfg.seed,
+                                                                        noise_scratch + (size_t)g.t0 * A, A);
+                AZ_LAUNCH_CHECK(); ++launches;
+            }
         }
-        for (int i = 0; i < sims; ++i) if (wave(0)) return -1;
-        return 0;
+        for (int i = 0; i < sims; ++i)
+            for (auto& g : groups) if (wave(g, 0)) return -1;
+        waves += sims + 1;
+        return join_groups();
     }
 
     int commit_moves(const int32_t* forced_dev) {
@@ -452,7 +511,7 @@ struct EngineT : EngineBase {
         AZ_CHECK(n == T, "az_engine_advance needs one action per slot");
         AZ_CUDA_CHECK(cudaMemcpyAsync(forced, actions, 4 * T, cudaMemcpyHostToDevice, stream));
         if (commit_moves(forced)) return -1;
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         return 0;
     }
 
@@ -463,14 +522,14 @@ struct EngineT : EngineBase {
 
     int last_actions(int32_t* out, int n) override {
         AZ_CHECK(n == T, "need one entry per slot");
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         AZ_CUDA_CHECK(cudaMemcpy(out, chosen_action, 4 * T, cudaMemcpyDeviceToHost));
         return 0;
     }
 
     int slot_state(int slot, int32_t* result, int32_t* ply, int32_t* player) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         State s; AZ_CUDA_CHECK(cudaMemcpy(&s, root_state + slot, sizeof(State), cudaMemcpyDeviceToHost));
         if (result) *result = G::result(s);
         if (ply) *ply = s.ply;
@@ -480,7 +539,7 @@ struct EngineT : EngineBase {
 
     int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         const size_t base = (size_t)slot * tp.cap;
         int32_t root; AZ_CUDA_CHECK(cudaMemcpy(&root, tp.root + slot, 4, cudaMemcpyDeviceToHost));
         int32_t f; int16_t nc;
@@ -514,7 +573,7 @@ struct EngineT : EngineBase {
     }
 
     int drain(void* buf, size_t cap, size_t* n, bool device) override {
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         int32_t cnt = 0; AZ_CUDA_CHECK(cudaMemcpy(&cnt, ring_count, 4, cudaMemcpyDeviceToHost));
         size_t take = std::min<size_t>(std::min<size_t>(cnt, ring_cap), cap);
         if (take) AZ_CUDA_CHECK(cudaMemcpy(buf, ring, take * sizeof(SampleT), device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
@@ -524,58 +583,78 @@ struct EngineT : EngineBase {
     }
 
     int get_stats(az_stats* o) override {
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (sync_all()) return -1;
         Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
         o->simulations = s.simulations; o->evaluations = s.evaluations; o->terminal_leaves = s.terminal_leaves; o->nodes_created = s.nodes_created;
         o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped;
-        o->kernel_launches = launches + net.launches; o->waves = waves;
+        o->kernel_launches = launches + net_launches(); o->waves = waves;
         return 0;
     }
-    int sync() override { AZ_CUDA_CHECK(cudaStreamSynchronize(stream)); return 0; }
+    int sync() override { return sync_all(); }
 
     int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) override {
         AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
-        AZ_CHECK(n >= 1 && n <= T, "n must be in [1, n_slots]");
-        float* dpl; if (dev_alloc(&dpl, (size_t)n * net.in_planes * A)) return -1;
-        AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes, (size_t)n * net.in_planes * A * 4, cudaMemcpyHostToDevice, stream));
-        AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, n, net.in_planes, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, stream) == 0, "pack launch failed");
-        ++launches;
-        if (net.forward(nullptr, n, wb.policy, wb.value, stream)) { cudaFree(dpl); return -1; }
-        AZ_CUDA_CHECK(cudaMemcpyAsync(policy, wb.policy, (size_t)n * A * 4, cudaMemcpyDeviceToHost, stream));
-        AZ_CUDA_CHECK(cudaMemcpyAsync(value, wb.value, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-        if (logits) AZ_CUDA_CHECK(cudaMemcpyAsync(logits, net.logits, (size_t)n * A * 4, cudaMemcpyDeviceToHost, stream));
-        AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        AZ_CHECK(n >= 1, "n must be >= 1");
+        if (sync_all()) return -1;
+        Group& g = groups[0];
+        Net& net = g.net;
+        AZ_CHECK(net.loaded, "no network weights loaded (az_engine_load_weights)");
+        const int cap = net.max_boards;
+        float* dpl; if (dev_alloc(&dpl, (size_t)cap * net.in_planes * A)) return -1;
+        for (int o = 0; o < n; o += cap) {               // group 0's buffers, `cap` boards at a time
+            const int c = std::min(cap, n - o);
+            AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes + (size_t)o * net.in_planes * A, (size_t)c * net.in_planes * A * 4, cudaMemcpyHostToDevice, g.stream));
+            AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, g.stream) == 0, "pack launch failed");
+            ++launches;
+            if (net.forward(nullptr, c, g.wb.policy, g.wb.value, g.stream)) { cudaFree(dpl); return -1; }
+            AZ_CUDA_CHECK(cudaMemcpyAsync(policy + (size_t)o * A, g.wb.policy, (size_t)c * A * 4, cudaMemcpyDeviceToHost, g.stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(value + o, g.wb.value, (size_t)c * 4, cudaMemcpyDeviceToHost, g.stream));
+            if (logits) AZ_CUDA_CHECK(cudaMemcpyAsync(logits + (size_t)o * A, net.logits, (size_t)c * A * 4, cudaMemcpyDeviceToHost, g.stream));
+            AZ_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+        }
         cudaFree(dpl);
         return 0;
     }
 
+    // whole-network forward over n_boards (in group-capacity chunks on group 0's buffers), `reps` times
     int nn_bench(int n_boards, int reps, float* ms) override {
         AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
-        AZ_CHECK(n_boards >= 1 && n_boards <= T, "n_boards must be in [1, n_slots]");
+        AZ_CHECK(n_boards >= 1, "n_boards must be >= 1");
+        if (sync_all()) return -1;
+        Group& g = groups[0];
+        const int cap = g.net.max_boards;
+        auto pass = [&]() -> int {
+            for (int o = 0; o < n_boards; o += cap) if (g.net.forward(nullptr, std::min(cap, n_boards - o), g.wb.policy, g.wb.value, g.stream)) return -1;
+            return 0;
+        };
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        if (net.forward(nullptr, n_boards, wb.policy, wb.value, stream)) return -1;   // warm-up
-        AZ_CUDA_CHECK(cudaEventRecord(e0, stream));
-        for (int i = 0; i < reps; ++i) if (net.forward(nullptr, n_boards, wb.policy, wb.value, stream)) return -1;
-        AZ_CUDA_CHECK(cudaEventRecord(e1, stream));
+        if (pass()) return -1;   // warm-up
+        AZ_CUDA_CHECK(cudaEventRecord(e0, g.stream));
+        for (int i = 0; i < reps; ++i) if (pass()) return -1;
+        AZ_CUDA_CHECK(cudaEventRecord(e1, g.stream));
         AZ_CUDA_CHECK(cudaEventSynchronize(e1));
         float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return 0;
     }
 
+    // one production-shaped launch of the 128->128 conv (n_boards <= one group's capacity), timed alone
     int conv_bench(int n_boards, int reps, float* ms) override {
+        if (sync_all()) return -1;
+        Group& g = groups[0];
+        Net& net = g.net;
         AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET && net.loaded && net.blocks >= 1, "conv_bench needs a loaded ResNet with >= 1 block");
-        AZ_CHECK(n_boards >= 1 && n_boards <= T, "n_boards must be in [1, n_slots]");
+        AZ_CHECK(n_boards >= 1 && n_boards <= net.max_boards, "n_boards must be in [1, slots per stream group]");
         nn::ConvParams cp{};
         cp.rowvalid = net.rowvalid; cp.n_boards_dev = nullptr; cp.n_rows = n_boards * net.board_pitch; cp.board_pitch = net.board_pitch;
         cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[1]; cp.bias = net.w.conv_b[1];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, stream) == 0, "conv launch failed");
-        AZ_CUDA_CHECK(cudaEventRecord(e0, stream));
-        for (int i = 0; i < reps; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, stream) == 0, "conv launch failed");
-        AZ_CUDA_CHECK(cudaEventRecord(e1, stream));
+        for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, g.stream) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e0, g.stream));
+        for (int i = 0; i < reps; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, g.stream) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e1, g.stream));
         AZ_CUDA_CHECK(cudaEventSynchronize(e1));
         float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -586,6 +665,7 @@ struct EngineT : EngineBase {
     int event_record(int idx) override {
         AZ_CHECK(idx >= 0 && idx < 8, "event index out of range");
         if (!events[idx]) AZ_CUDA_CHECK(cudaEventCreate(&events[idx]));
+        if (join_groups()) return -1;                    // the main stream is ordered after all group streams
         AZ_CUDA_CHECK(cudaEventRecord(events[idx], stream));
         return 0;
     }
@@ -630,7 +710,7 @@ AZ_API void az_config_default(az_config* c) {
     c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
     c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
     c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
-    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 2;
 }
 
 AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }

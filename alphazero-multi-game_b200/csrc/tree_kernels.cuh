@@ -288,7 +288,7 @@ struct Philox {
 // Dirichlet noise on the root priors (M11, parallel_mcts.cpp:1110-1171): P = (1-eps) P + eps * noise_i by
 // child index.  The reference draws from libstdc++'s gamma_distribution with a random_device seed, which is
 // unpinned; here the draws come from Philox(seed; slot, game, move).
-__global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, float alpha, float eps, uint64_t seed, float* scratch /*[T][maxA]*/, int maxA) {
+__global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, int slot_base, float alpha, float eps, uint64_t seed, float* scratch /*[T][maxA]*/, int maxA) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, float al
     float* nz = scratch + (size_t)t * maxA;
     float part = 0.0f;
     for (int i = lane; i < nc; i += 32) {
-        Philox rng(seed, (uint32_t)t, tp.game_id[t], ((uint32_t)tp.move_num[t] << 12) | (uint32_t)i);
+        Philox rng(seed, (uint32_t)(slot_base + t), tp.game_id[t], ((uint32_t)tp.move_num[t] << 12) | (uint32_t)i);
         const float g = fmaxf(1e-10f, rng.gamma(alpha));
         nz[i] = g; part += g;
     }

@@ -29,7 +29,8 @@ class EngineConfig(C.Structure):
                 ("dirichlet_alpha", C.c_float), ("dirichlet_epsilon", C.c_float),
                 ("init_temperature", C.c_float), ("final_temperature", C.c_float),
                 ("temperature_drop_move", C.c_int32), ("auto_restart", C.c_int32),
-                ("sample_ring_capacity", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64)]
+                ("sample_ring_capacity", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+                ("n_streams", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Stats(C.Structure):

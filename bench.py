@@ -156,7 +156,7 @@ def workload_config(args, world):
     return {"workload": f"Gomoku 15x15 batched self-play, {args.slots} concurrent games per GPU, {args.sims} sims/move, "
                         f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[1])",
             "slots_per_gpu": args.slots, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s)",
-            "step": "one self-play move on every slot (root expansion + sims waves + move commit)",
+            "step": "one self-play move on every slot (root expansion + sims waves + move commit)", "stream_groups": args.streams,
             "l2": "working set (node pools, 3 x 268 MB activations) >> 126 MB L2; no explicit flush"}
 
 
@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slots", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--streams", type=int, default=2, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
     ap.add_argument("--ref-sims-per-step", type=int, default=200)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -192,7 +193,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     eng = E.Engine(game=E.GOMOKU, board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
-                   net_blocks=BLOCKS, net_channels=CHANNELS, deterministic=0, auto_restart=1, device=local, seed=1234 + rank)
+                   net_blocks=BLOCKS, net_channels=CHANNELS, deterministic=0, auto_restart=1, device=local, seed=1234 + rank,
+                   n_streams=args.streams)
     model = N.make_random_model(seed=0, in_planes=PLANES, board=BOARD, actions=ACTIONS, blocks=BLOCKS, channels=CHANNELS)
     blob = N.export_weights(model)
     eng.load_weights(blob)
@@ -274,15 +276,16 @@ def main():
 
     # ---- roofline of the dominant kernel (3x3 conv 128->128 on tcgen05), timed alone with CUDA events ------
     pk = peaks()
-    conv_ms = eng.conv_bench(args.slots, 20)
-    conv_flop = CONV_FLOP_PER_BOARD * args.slots
+    boards_per_launch = (args.slots + args.streams - 1) // args.streams      # the production launch shape: one stream group
+    conv_ms = eng.conv_bench(boards_per_launch, 20)
+    conv_flop = CONV_FLOP_PER_BOARD * boards_per_launch
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     nn_ms = eng.nn_bench(args.slots, 5)
-    roofline = {"bound": "tensor", "kernel": "k_conv3x3<128> (one 128->128 3x3 conv layer over all slots)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": f"k_conv3x3<128> (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group)", "achieved": achieved,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16",
                 "traffic": None, "launch_ms": conv_ms, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": NET_FLOP_PER_EVAL * args.slots / (nn_ms / 1e3) / 1e12,
-                "step_share_note": "20 of these launches per wave; see profiles/ for the ncu launch list"}
+                "step_share_note": f"{20 * args.streams} of these launches per wave (20 per stream group); see profiles/ for the ncu launch list"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own serial search on the host cores --
     cpu = None

@@ -57,6 +57,9 @@ typedef struct az_config {
     int32_t sample_ring_capacity; /* finished-game sample records held on device until drained; 0 = default */
     int32_t device;             /* CUDA device ordinal */
     uint64_t seed;              /* Philox key for noise / temperature sampling */
+    int32_t n_streams;          /* stream groups the slots are split into (tree kernels of one group overlap the
+                                   network pass of another); 0 = default (2) */
+    int32_t reserved_;
 } az_config;
 
 /* mcts::MCTSStats (include/alphazero/mcts/parallel_mcts.h:77-99) + engine counters, cumulative */
