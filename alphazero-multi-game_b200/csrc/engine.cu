@@ -259,6 +259,7 @@ struct EngineBase {
     virtual int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) = 0;
     virtual int advance(const int32_t* actions, int n) = 0;
     virtual int play(int n_moves) = 0;
+    virtual int add_noise(float alpha, float eps) = 0;
     virtual int last_actions(int32_t* out, int n) = 0;
     virtual int slot_state(int slot, int32_t* result, int32_t* ply, int32_t* player) = 0;
     virtual int sample_layout(az_sample_layout* out) = 0;
@@ -357,7 +358,7 @@ struct EngineT : EngineBase {
             AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), A * 2, cudaMemcpyHostToDevice));
         }
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
-        NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 2, T));
+        NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
         const int per = (T + NG - 1) / NG;
         groups.resize(NG);
         for (int gi = 0; gi < NG; ++gi) {
@@ -514,6 +515,20 @@ struct EngineT : EngineBase {
         if (sync_all()) return -1;
         return 0;
     }
+
+    int add_noise(float alpha, float eps) override {
+        if (fork_groups()) return -1;
+        for (auto& g : groups) {
+            k_flag_noise<<<(g.n + 127) / 128, 128, 0, g.stream>>>(g.tp, g.n);
+            AZ_LAUNCH_CHECK(); ++launches;
+            if (wave(g, 1)) return -1;
+            k_dirichlet<<<blocks_for_warps(g.n), 128, 0, g.stream>>>(g.tp, g.n, g.t0, alpha, eps, cfg.seed ^ (0x9E37ULL * ++noise_calls), noise_scratch + (size_t)g.t0 * A, A);
+            AZ_LAUNCH_CHECK(); ++launches;
+        }
+        if (join_groups()) return -1;
+        return sync_all();
+    }
+    unsigned long long noise_calls = 0;
 
     int play(int n_moves) override {
         for (int m = 0; m < n_moves; ++m) { if (search(cfg.num_simulations)) return -1; if (commit_moves(nullptr)) return -1; }
@@ -710,7 +725,7 @@ AZ_API void az_config_default(az_config* c) {
     c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
     c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
     c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
-    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 2;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1;
 }
 
 AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }
@@ -738,6 +753,7 @@ AZ_API int az_engine_search(az_engine* e, int sims) { AZ_FWD(search(sims)); }
 AZ_API int az_engine_root_stats(az_engine* e, int slot, int32_t* a, int32_t* v, float* w, float* p, int32_t* n, int32_t* rn, float* rw) { AZ_FWD(root_stats(slot, a, v, w, p, n, rn, rw)); }
 AZ_API int az_engine_advance(az_engine* e, const int32_t* actions, int n) { AZ_FWD(advance(actions, n)); }
 AZ_API int az_engine_play(az_engine* e, int n_moves) { AZ_FWD(play(n_moves)); }
+AZ_API int az_engine_add_dirichlet_noise(az_engine* e, float alpha, float eps) { AZ_FWD(add_noise(alpha, eps)); }
 AZ_API int az_engine_last_actions(az_engine* e, int32_t* actions, int n) { AZ_FWD(last_actions(actions, n)); }
 AZ_API int az_engine_slot_state(az_engine* e, int slot, int32_t* r, int32_t* ply, int32_t* pl) { AZ_FWD(slot_state(slot, r, ply, pl)); }
 AZ_API int az_engine_sample_layout(az_engine* e, az_sample_layout* out) { AZ_FWD(sample_layout(out)); }

@@ -317,6 +317,11 @@ __global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, int slot
     if (lane == 0) tp.tflags[t] = tf & ~TF_NEED_NOISE;
 }
 
+__global__ void k_flag_noise(TreePools tp, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && (tp.tflags[t] & TF_ACTIVE) && !(tp.tflags[t] & TF_GAME_OVER)) tp.tflags[t] |= TF_NEED_NOISE;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sample record: one per move played (the device-side equivalent of selfplay::MoveData,
 // include/alphazero/selfplay/game_record.h:18-70, with action-indexed visit counts instead of the

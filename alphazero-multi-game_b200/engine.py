@@ -47,7 +47,7 @@ class SampleLayout(C.Structure):
 
 EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_destroy",
            "az_engine_load_weights", "az_engine_reset_games", "az_engine_set_root", "az_engine_search",
-           "az_engine_root_stats", "az_engine_advance", "az_engine_play", "az_engine_last_actions",
+           "az_engine_root_stats", "az_engine_advance", "az_engine_play", "az_engine_add_dirichlet_noise", "az_engine_last_actions",
            "az_engine_slot_state", "az_engine_sample_layout", "az_engine_drain_samples",
            "az_engine_drain_samples_device", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_event_record", "az_engine_event_elapsed",
@@ -92,6 +92,7 @@ def load_library():
         "az_engine_root_stats": [vp, C.c_int, i32p, i32p, f32p, f32p, i32p, i32p, f32p],
         "az_engine_advance": [vp, i32p, C.c_int],
         "az_engine_play": [vp, C.c_int],
+        "az_engine_add_dirichlet_noise": [vp, C.c_float, C.c_float],
         "az_engine_last_actions": [vp, i32p, C.c_int],
         "az_engine_slot_state": [vp, C.c_int, i32p, i32p, i32p],
         "az_engine_sample_layout": [vp, C.POINTER(SampleLayout)],
@@ -192,6 +193,9 @@ class Engine:
 
     def play(self, n_moves=1):
         self._check(self.lib.az_engine_play(self.h, n_moves))
+
+    def add_dirichlet_noise(self, alpha=0.03, epsilon=0.25):
+        self._check(self.lib.az_engine_add_dirichlet_noise(self.h, alpha, epsilon))
 
     def last_actions(self):
         a = np.zeros(self.n_slots, np.int32)

@@ -1,0 +1,454 @@
+// alphazero_host.cpp — see alphazero_host.hpp.  Host logic only; every search / network call goes through the C ABI.
+#include "alphazero_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+
+#include <nlohmann/json.hpp>
+
+#include "../csrc/gomoku.cuh"   // host+device rules header (hash-evaluator key for B200NeuralNetwork("hash").predict)
+
+namespace az { void set_error(const std::string&) {} }   // common.cuh declares it; unused on the host side
+
+namespace alphazero {
+
+static void check(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + az_last_error());
+}
+
+// ================================================================================================ core
+namespace core {
+std::unique_ptr<IGameState> createGameState(GameType type, int boardSize, bool variantRules) {
+    // reference: src/core/igamestate.cpp:10-69 (registry based); only what the engine can search is constructible
+    if (type == GameType::GOMOKU) {
+        if (variantRules) throw GameStateException("Failed to create game state: Renju rules are out of scope of the B200 engine");
+        return std::make_unique<gomoku::GomokuState>(boardSize > 0 ? boardSize : 15, false, false, 0, false);
+    }
+    throw GameStateException("Failed to create game state: game type not built into the B200 engine yet");
+}
+}  // namespace core
+
+// ================================================================================================ gomoku
+namespace gomoku {
+
+GomokuState::GomokuState(int bs, bool use_renju, bool use_omok, int, bool use_pro_long)
+    : IGameState(core::GameType::GOMOKU), board_size(bs), current_player(BLACK), cells_((size_t)bs * bs, 0) {
+    if (use_renju || use_omok || use_pro_long) throw core::GameStateException("Renju / Omok / pro-long variants are out of scope of the B200 engine");
+    if (bs < 5 || bs > 19) throw core::GameStateException("unsupported board size");
+}
+bool GomokuState::is_occupied(int a) const { return a < 0 || a >= (int)cells_.size() || cells_[a] != 0; }
+
+std::vector<int> GomokuState::getLegalMoves() const {       // gomoku_state.cpp:518-566 (QUIRK G2: set iteration order)
+    if (valid_moves_dirty_) {
+        cached_valid_moves_.clear();
+        for (int a = 0; a < (int)cells_.size(); ++a) if (!cells_[a]) cached_valid_moves_.insert(a);
+        valid_moves_dirty_ = false; never_filled_ = false;
+    }
+    return std::vector<int>(cached_valid_moves_.begin(), cached_valid_moves_.end());
+}
+bool GomokuState::isLegalMove(int a) const { return a >= 0 && a < (int)cells_.size() && cells_[a] == 0; }
+void GomokuState::makeMove(int a) {                          // gomoku_state.cpp:681-722
+    if (a < 0 || a >= (int)cells_.size()) throw std::runtime_error("Move " + std::to_string(a) + " out of range.");
+    if (cells_[a]) throw std::runtime_error("Cell " + std::to_string(a) + " is already occupied.");
+    cells_[a] = (int8_t)current_player; current_player = 3 - current_player; move_history.push_back(a); valid_moves_dirty_ = true;
+}
+bool GomokuState::undoMove() {
+    if (move_history.empty()) return false;
+    int a = move_history.back(); move_history.pop_back();
+    cells_[a] = 0; current_player = 3 - current_player; valid_moves_dirty_ = true;
+    return true;
+}
+int GomokuState::winner() const {                            // gomoku_rules.cpp:39-115, BLACK first, black exactly five (QUIRK G3)
+    static const int D[4][2] = {{0, 1}, {1, 0}, {1, 1}, {1, -1}};
+    const int N = board_size;
+    for (int p = 1; p <= 2; ++p)
+        for (int a = 0; a < N * N; ++a) {
+            if (cells_[a] != p) continue;
+            const int x = a / N, y = a % N;
+            for (auto& d : D) {
+                int len = 1;
+                for (int s = -1; s <= 1; s += 2) {
+                    int cx = x + s * d[0], cy = y + s * d[1];
+                    while (cx >= 0 && cx < N && cy >= 0 && cy < N && cells_[cx * N + cy] == p) { ++len; cx += s * d[0]; cy += s * d[1]; }
+                }
+                if (p == 1 ? len == 5 : len >= 5) return p;
+            }
+        }
+    return 0;
+}
+bool GomokuState::isTerminal() const {                       // gomoku_state.cpp:491-521
+    if (winner() != 0) return true;
+    if (!valid_moves_dirty_) return cached_valid_moves_.empty();
+    if ((int)move_history.size() >= board_size * board_size) return true;
+    return getLegalMoves().empty();
+}
+core::GameResult GomokuState::getGameResult() const {
+    const int w = winner();
+    if (w == 1) return core::GameResult::WIN_PLAYER1;
+    if (w == 2) return core::GameResult::WIN_PLAYER2;
+    return (int)move_history.size() >= board_size * board_size ? core::GameResult::DRAW : core::GameResult::ONGOING;
+}
+std::vector<std::vector<std::vector<float>>> GomokuState::getTensorRepresentation() const {   // to_tensor :811-840
+    const int N = board_size;
+    std::vector<std::vector<std::vector<float>>> t(3, std::vector<std::vector<float>>(N, std::vector<float>(N, 0.0f)));
+    for (int a = 0; a < N * N; ++a) {
+        if (cells_[a] == current_player) t[0][a / N][a % N] = 1.0f; else if (cells_[a]) t[1][a / N][a % N] = 1.0f;
+        if (current_player == BLACK) t[2][a / N][a % N] = 1.0f;
+    }
+    return t;
+}
+std::vector<std::vector<std::vector<float>>> GomokuState::getEnhancedTensorRepresentation() const {   // :207-258 (QUIRK G5)
+    const int N = board_size;
+    auto t = getTensorRepresentation();
+    t.resize(11, std::vector<std::vector<float>>(N, std::vector<float>(N, 0.0f)));
+    const int n = (int)move_history.size();
+    for (int k = 0; k < 3; ++k) {
+        // moves attributed to the side to move: last, last-2, last-4; to the other side: last-1, last-3, last-5
+        const int mine = n - 1 - 2 * k, theirs = n - 2 - 2 * k;
+        const int b = current_player == BLACK ? mine : theirs, w = current_player == BLACK ? theirs : mine;
+        if (b >= 0) t[3 + k][move_history[b] / N][move_history[b] % N] = 1.0f;
+        if (w >= 0) t[6 + k][move_history[w] / N][move_history[w] % N] = 1.0f;
+    }
+    for (int x = 0; x < N; ++x) for (int y = 0; y < N; ++y) { t[9][x][y] = (float)x / (N - 1); t[10][x][y] = (float)y / (N - 1); }
+    return t;
+}
+uint64_t GomokuState::getHash() const {   // only equality within a process matters (reference keys are time-seeded)
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t a = 0; a < cells_.size(); ++a) if (cells_[a]) h ^= az::mix64(0x9E37ULL + a * 2 + (cells_[a] - 1));
+    return h ^ az::mix64(0xABCDULL + current_player);
+}
+std::string GomokuState::actionToString(int a) const {       // gomoku_state.cpp:270-283
+    if (a < 0 || a >= board_size * board_size) return "invalid";
+    char col = (char)('A' + a % board_size); if (col >= 'I') col++;
+    return std::string(1, col) + std::to_string(board_size - a / board_size);
+}
+std::optional<int> GomokuState::stringToAction(const std::string& s) const {
+    if (s.size() < 2 || s.size() > 3) return std::nullopt;
+    char col = s[0]; if (col >= 'a' && col <= 'z') col = (char)(col - 'a' + 'A');
+    if (col < 'A' || col > 'Z') return std::nullopt;
+    if (col >= 'I') col--;
+    int y = col - 'A', row;
+    try { row = std::stoi(s.substr(1)); } catch (...) { return std::nullopt; }
+    int x = board_size - row;
+    if (x < 0 || x >= board_size || y < 0 || y >= board_size) return std::nullopt;
+    return x * board_size + y;
+}
+std::string GomokuState::toString() const {
+    std::ostringstream ss;
+    for (int x = 0; x < board_size; ++x) { for (int y = 0; y < board_size; ++y) ss << ".XO"[cells_[x * board_size + y]] << ' '; ss << '\n'; }
+    return ss.str();
+}
+bool GomokuState::equals(const core::IGameState& o) const {
+    auto* g = dynamic_cast<const GomokuState*>(&o);
+    return g && g->board_size == board_size && g->current_player == current_player && g->cells_ == cells_;
+}
+bool GomokuState::validate() const { return true; }
+std::vector<std::vector<int>> GomokuState::get_board() const {
+    std::vector<std::vector<int>> b(board_size, std::vector<int>(board_size, 0));
+    for (int a = 0; a < board_size * board_size; ++a) b[a / board_size][a % board_size] = cells_[a];
+    return b;
+}
+}  // namespace gomoku
+
+// ================================================================================================ nn
+namespace nn {
+
+std::unique_ptr<NeuralNetwork> NeuralNetwork::create(const std::string& modelPath, core::GameType gameType, int boardSize, bool) {
+    return std::make_unique<B200NeuralNetwork>(modelPath, gameType, boardSize);
+}
+
+B200NeuralNetwork::B200NeuralNetwork(const std::string& modelPath, core::GameType gameType, int boardSize)
+    : gameType_(gameType), boardSize_(boardSize > 0 ? boardSize : 15) {
+    if (modelPath.empty() || modelPath == "hash") { hash_ = true; return; }
+    std::ifstream f(modelPath, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open weight blob " + modelPath);
+    blob_.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    if (blob_.size() < 32 || std::memcmp(blob_.data(), "AZW1", 4) != 0) throw std::runtime_error(modelPath + " is not an AZW1 weight blob (net.py:export_weights)");
+    int32_t hdr[7]; std::memcpy(hdr, blob_.data() + 4, sizeof(hdr));
+    blocks_ = hdr[1]; channels_ = hdr[2];
+}
+B200NeuralNetwork::~B200NeuralNetwork() { if (eng_) az_engine_destroy(eng_); }
+
+void B200NeuralNetwork::ensureEngine() {
+    if (eng_ || hash_) return;
+    az_config c; az_config_default(&c);
+    c.game = (int)gameType_; c.board_size = boardSize_; c.n_slots = batch_; c.evaluator = AZ_EVAL_RESNET; c.net_blocks = blocks_; c.net_channels = channels_;
+    c.num_simulations = 1; c.max_nodes_per_tree = 1024;
+    check(az_engine_create(&c, &eng_), "az_engine_create");
+    check(az_engine_load_weights(eng_, blob_.data(), blob_.size()), "az_engine_load_weights");
+}
+std::pair<std::vector<float>, float> B200NeuralNetwork::predict(const core::IGameState& state) {
+    std::vector<std::vector<float>> p; std::vector<float> v;
+    predictBatch({std::cref(state)}, p, v);
+    return {p[0], v[0]};
+}
+void B200NeuralNetwork::predictBatch(const std::vector<std::reference_wrapper<const core::IGameState>>& states,
+                                     std::vector<std::vector<float>>& policies, std::vector<float>& values) {
+    const int n = (int)states.size();
+    policies.assign(n, {}); values.assign(n, 0.0f);
+    if (n == 0) return;
+    const int A = states[0].get().getActionSpaceSize();
+    if (hash_) {   // stateless HashEvaluator on the canonical bitboards
+        for (int i = 0; i < n; ++i) {
+            const auto& s = states[i].get();
+            if (s.getGameType() != core::GameType::GOMOKU || s.getBoardSize() != 15) throw std::runtime_error("hash evaluator: Gomoku 15x15 only on the host side");
+            az::Gomoku<15>::State gs; az::Gomoku<15>::init(gs);
+            for (int a : s.getMoveHistory()) az::Gomoku<15>::apply(gs, a);
+            const uint64_t h = az::Gomoku<15>::key(gs);
+            std::vector<float> pol(A); float sum = 0.0f;
+            for (int a = 0; a < A; ++a) { pol[a] = az::fdiv((float)((az::mix64(h + (uint64_t)a * 0x9E3779B97F4A7C15ULL) >> 40) + 1), 16777216.0f); sum = az::fadd(sum, pol[a]); }
+            for (int a = 0; a < A; ++a) pol[a] = az::fdiv(pol[a], sum);
+            float v = az::fdiv((float)(az::mix64(h ^ 0xABCDEFULL) >> 40), 16777216.0f);
+            policies[i] = pol; values[i] = az::fmul(az::fsub(az::fmul(v, 2.0f), 1.0f), 0.5f);
+        }
+        return;
+    }
+    ensureEngine();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int o = 0; o < n; o += batch_) {
+        const int c = std::min(batch_, n - o);
+        std::vector<float> planes;
+        int C = 0;
+        for (int i = 0; i < c; ++i) {
+            auto t = states[o + i].get().getEnhancedTensorRepresentation();
+            C = (int)t.size();
+            for (auto& pl : t) for (auto& row : pl) planes.insert(planes.end(), row.begin(), row.end());
+        }
+        (void)C;
+        std::vector<float> pol((size_t)c * A), val(c);
+        check(az_engine_nn_forward(eng_, planes.data(), c, pol.data(), val.data(), nullptr), "az_engine_nn_forward");
+        for (int i = 0; i < c; ++i) { policies[o + i].assign(pol.begin() + (size_t)i * A, pol.begin() + (size_t)(i + 1) * A); values[o + i] = val[i]; }
+    }
+    lastMs_ = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+std::string B200NeuralNetwork::getDeviceInfo() const { return "NVIDIA B200 (sm_100a) via libaz_b200"; }
+std::string B200NeuralNetwork::getModelInfo() const {
+    return hash_ ? std::string("HashEvaluator (stateless, parity runs)") : ("ResNet " + std::to_string(blocks_) + "x" + std::to_string(channels_) + " bf16/tcgen05");
+}
+void B200NeuralNetwork::benchmark(int numIterations, int batchSize) {
+    if (hash_) return;
+    ensureEngine();
+    float ms = 0; check(az_engine_nn_bench(eng_, std::min(batchSize, batch_), numIterations, &ms), "az_engine_nn_bench");
+    lastMs_ = ms;
+}
+void B200NeuralNetwork::printModelSummary() const { std::cout << getModelInfo() << std::endl; }
+
+}  // namespace nn
+
+// ================================================================================================ mcts
+namespace mcts {
+
+ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, nn::NeuralNetwork* nn, TranspositionTable*, int numThreads, int numSimulations,
+                           float cPuct, float fpuReduction, int virtualLoss) : nn_(nn) {
+    config_.numThreads = numThreads; config_.numSimulations = numSimulations; config_.cPuct = cPuct; config_.fpuReduction = fpuReduction; config_.virtualLoss = virtualLoss;
+    build(rootState);
+}
+ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, const MCTSConfig& config, nn::NeuralNetwork* nn, TranspositionTable*) : config_(config), nn_(nn) { build(rootState); }
+ParallelMCTS::~ParallelMCTS() { if (eng_) az_engine_destroy(eng_); }
+
+void ParallelMCTS::build(const core::IGameState& rootState) {
+    auto* b = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
+    if (!b) throw std::runtime_error("ParallelMCTS on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork); arbitrary host evaluators cannot run inside the device waves");
+    rootState_ = rootState.clone();                                   // parallel_mcts.cpp:65
+    az_config c; az_config_default(&c);
+    c.game = (int)rootState.getGameType(); c.board_size = rootState.getBoardSize(); c.n_slots = 1;
+    c.num_simulations = config_.numSimulations; c.c_puct = config_.cPuct; c.virtual_loss = config_.virtualLoss;
+    c.evaluator = b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET; c.net_blocks = b->blocks(); c.net_channels = b->channels();
+    c.deterministic = config_.useDirichletNoise ? 0 : 1; c.dirichlet_alpha = config_.dirichletAlpha; c.dirichlet_epsilon = config_.dirichletEpsilon;
+    c.auto_restart = 0; c.n_streams = 1;
+    check(az_engine_create(&c, &eng_), "az_engine_create");
+    if (!b->isHash()) check(az_engine_load_weights(eng_, b->blob().data(), b->blob().size()), "az_engine_load_weights");
+    // The root MCTSNode ctor calls state->isTerminal() (mcts_node.cpp:24), which is what first enumerates the legal moves
+    // of a fresh lineage; the order that enumeration produces is the root's child order (QUIRK G2).
+    rootState_->isTerminal();
+    std::vector<int> order = rootState_->getLegalMoves();
+    const std::vector<int> hist = rootState_->getMoveHistory();
+    std::vector<int32_t> moves(hist.begin(), hist.end());
+    std::vector<int32_t> ord(order.begin(), order.end());
+    check(az_engine_set_root(eng_, 0, moves.data(), (int)moves.size(), ord.data(), (int)ord.size()), "az_engine_set_root");
+}
+void ParallelMCTS::setCPuct(float c) { config_.cPuct = c; }
+void ParallelMCTS::setVirtualLoss(int v) { config_.virtualLoss = v; }
+
+void ParallelMCTS::search() { check(az_engine_search(eng_, config_.numSimulations), "az_engine_search"); check(az_engine_sync(eng_), "az_engine_sync"); searched_ = true; }
+
+ParallelMCTS::RootStats ParallelMCTS::rootStats() const {
+    RootStats r; const int cap = rootState_->getActionSpaceSize() + 1;
+    std::vector<int32_t> a(cap), n(cap); r.valueSums.resize(cap); r.priors.resize(cap);
+    int32_t cnt = cap, rn = 0; float rw = 0;
+    check(az_engine_root_stats(eng_, 0, a.data(), n.data(), r.valueSums.data(), r.priors.data(), &cnt, &rn, &rw), "az_engine_root_stats");
+    r.actions.assign(a.begin(), a.begin() + cnt); r.visits.assign(n.begin(), n.begin() + cnt); r.valueSums.resize(cnt); r.priors.resize(cnt);
+    r.rootVisits = rn; r.rootValueSum = rw;
+    return r;
+}
+std::vector<float> ParallelMCTS::getActionProbabilities(float temperature) const {   // mcts_node.cpp:289-322, child order
+    RootStats r = rootStats();
+    std::vector<float> d(r.visits.size(), 0.0f);
+    if (d.empty()) return d;
+    float total = 0.0f; std::vector<float> c(d.size());
+    for (size_t i = 0; i < d.size(); ++i) { c[i] = std::pow((float)r.visits[i], 1.0f / std::max(0.01f, temperature)); total += c[i]; }
+    if (total > 0.0f) for (size_t i = 0; i < d.size(); ++i) d[i] = c[i] / total; else for (auto& x : d) x = 1.0f / (float)d.size();
+    return d;
+}
+int ParallelMCTS::selectAction(bool isTraining, float temperature) {   // parallel_mcts.cpp:987-1047
+    if (!searched_) search();
+    RootStats r = rootStats();
+    static thread_local std::mt19937 rng{std::random_device{}()};
+    if (r.actions.empty()) {
+        auto legal = rootState_->getLegalMoves();
+        if (legal.empty()) return -1;
+        if (config_.useBatchInference) return legal[0];
+        return legal[std::uniform_int_distribution<size_t>(0, legal.size() - 1)(rng)];
+    }
+    if (isTraining && temperature > 0.0f) {
+        auto d = getActionProbabilities(temperature);
+        if (config_.useBatchInference) return r.actions[std::max_element(d.begin(), d.end()) - d.begin()];
+        return r.actions[std::discrete_distribution<int>(d.begin(), d.end())(rng)];
+    }
+    int mx = 0; for (int v : r.visits) mx = std::max(mx, v);
+    std::vector<int> best; for (size_t i = 0; i < r.visits.size(); ++i) if (r.visits[i] == mx) best.push_back(r.actions[i]);
+    if (best.size() == 1 || config_.useBatchInference) return best[0];
+    return best[std::uniform_int_distribution<size_t>(0, best.size() - 1)(rng)];
+}
+float ParallelMCTS::getRootValue() const { RootStats r = rootStats(); return (r.actions.empty() || r.rootVisits == 0) ? 0.0f : r.rootValueSum / r.rootVisits; }
+void ParallelMCTS::updateWithMove(int action) {                        // parallel_mcts.cpp:1065-1108
+    try { rootState_->makeMove(action); } catch (const std::exception&) { return; }   // invalid move: keep current state
+    int32_t a = action; check(az_engine_advance(eng_, &a, 1), "az_engine_advance");
+}
+void ParallelMCTS::addDirichletNoise(float alpha, float epsilon) { check(az_engine_add_dirichlet_noise(eng_, alpha, epsilon), "az_engine_add_dirichlet_noise"); }
+MCTSStats ParallelMCTS::getStats() const {
+    az_stats s; check(az_engine_get_stats(eng_, &s), "az_engine_get_stats");
+    MCTSStats m; m.nodesCreated = s.nodes_created; m.nodesExpanded = s.nodes_expanded; m.simulationCount = s.simulations; m.evaluationCalls = s.evaluations;
+    return m;
+}
+std::string ParallelMCTS::getSearchInfo() const {                       // parallel_mcts.cpp:1319-1388 (same fields)
+    RootStats r = rootStats(); MCTSStats m = getStats();
+    std::ostringstream ss;
+    if (r.actions.empty()) { ss << "Root node not expanded"; return ss.str(); }
+    ss << "Search stats:\n  Total visits: " << r.rootVisits << "\n  Root value: " << std::fixed << std::setprecision(3) << getRootValue()
+       << "\n  Nodes created: " << m.nodesCreated << "\n  Nodes expanded: " << m.nodesExpanded << "\n  Evaluations: " << m.evaluationCalls << "\n  Child visits:\n";
+    std::vector<size_t> idx(r.actions.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return r.visits[a] > r.visits[b]; });
+    for (size_t k = 0; k < std::min<size_t>(10, idx.size()); ++k) {
+        const size_t i = idx[k];
+        ss << "    Action " << r.actions[i] << ": visits=" << r.visits[i] << ", value=" << (r.visits[i] ? r.valueSums[i] / r.visits[i] : 0.0f) << ", prior=" << r.priors[i] << "\n";
+    }
+    return ss.str();
+}
+void ParallelMCTS::printSearchStats() const { std::cout << getSearchInfo() << std::endl; }
+size_t ParallelMCTS::getMemoryUsage() const { az_stats s; az_engine_get_stats(eng_, &s); return (size_t)s.nodes_created * 21; }
+
+}  // namespace mcts
+
+// ================================================================================================ selfplay
+namespace selfplay {
+using json = nlohmann::json;
+
+std::string MoveData::toJson() const { json j; j["action"] = action; j["policy"] = policy; j["value"] = value; j["thinking_time_ms"] = thinking_time_ms; return j.dump(); }
+MoveData MoveData::fromJson(const std::string& s) {
+    json j = json::parse(s); MoveData d; d.action = j["action"]; d.policy = j["policy"].get<std::vector<float>>(); d.value = j["value"]; d.thinking_time_ms = j["thinking_time_ms"]; return d;
+}
+GameRecord::GameRecord(core::GameType t, int bs, bool v) : gameType_(t), boardSize_(bs), useVariantRules_(v), result_(core::GameResult::ONGOING), timestamp_(std::chrono::system_clock::now()) {}
+void GameRecord::addMove(int action, const std::vector<float>& policy, float value, int64_t ms) { MoveData m; m.action = action; m.policy = policy; m.value = value; m.thinking_time_ms = ms; moves_.push_back(std::move(m)); }
+std::string GameRecord::toJson() const {       // src/selfplay/game_record.cpp:64-90
+    json j; j["game_type"] = (int)gameType_; j["board_size"] = boardSize_; j["use_variant_rules"] = useVariantRules_; j["result"] = (int)result_;
+    auto tt = std::chrono::system_clock::to_time_t(timestamp_); std::stringstream ss; ss << std::put_time(std::gmtime(&tt), "%FT%TZ"); j["timestamp"] = ss.str();
+    json mv = json::array();
+    for (const auto& m : moves_) { json x; x["action"] = m.action; x["policy"] = m.policy; x["value"] = m.value; x["thinking_time_ms"] = m.thinking_time_ms; mv.push_back(x); }
+    j["moves"] = mv;
+    return j.dump(4);
+}
+GameRecord GameRecord::fromJson(const std::string& s) {
+    try {
+        json j = json::parse(s);
+        GameRecord r((core::GameType)j["game_type"].get<int>(), j["board_size"], j["use_variant_rules"]);
+        r.result_ = (core::GameResult)j["result"].get<int>();
+        for (const auto& x : j["moves"]) { MoveData m; m.action = x["action"]; m.policy = x["policy"].get<std::vector<float>>(); m.value = x["value"]; m.thinking_time_ms = x["thinking_time_ms"]; r.moves_.push_back(m); }
+        return r;
+    } catch (const json::exception& e) { throw std::runtime_error("Failed to parse JSON: " + std::string(e.what())); }
+}
+bool GameRecord::saveToFile(const std::string& fn) const { try { std::ofstream f(fn); if (!f.is_open()) return false; f << toJson(); return true; } catch (...) { return false; } }
+GameRecord GameRecord::loadFromFile(const std::string& fn) {
+    std::ifstream f(fn); if (!f.is_open()) throw std::runtime_error("Failed to load game record: Could not open file: " + fn);
+    std::stringstream b; b << f.rdbuf(); return fromJson(b.str());
+}
+
+SelfPlayManager::SelfPlayManager(nn::NeuralNetwork* nn, int numGames, int numSimulations, int numThreads)
+    : nn_(nn), numGames_(numGames), numSimulations_(numSimulations), numThreads_(numThreads) {}
+SelfPlayManager::~SelfPlayManager() { abort_ = true; }
+void SelfPlayManager::setExplorationParams(float a, float e, float t0, int drop, float t1) { dirichletAlpha_ = a; dirichletEpsilon_ = e; initialTemperature_ = t0; temperatureDropMove_ = drop; finalTemperature_ = t1; }
+
+// The reference runs numGames games on a CPU thread pool, one ParallelMCTS each (self_play_manager.cpp:47-113, 151-234).
+// Here the games are slots of one engine: every az_engine_play(1) plays one move in every slot; finished games come
+// back through the sample ring and are re-assembled into GameRecords.
+std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, int boardSize, bool useVariantRules) {
+    auto* b = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
+    if (!b) throw std::runtime_error("SelfPlayManager on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork)");
+    if (useVariantRules) throw std::runtime_error("variant rules are out of scope of the B200 engine");
+    running_ = true; abort_ = false; completedGames_ = 0; totalMoves_ = 0;
+    const int bs = boardSize > 0 ? boardSize : 15;
+    az_config c; az_config_default(&c);
+    c.game = (int)gameType; c.board_size = bs; c.n_slots = concurrentGames_ > 0 ? concurrentGames_ : std::max(1, std::min(numGames_, 4096));
+    c.num_simulations = numSimulations_; c.c_puct = mctsConfig_.cPuct > 0 ? mctsConfig_.cPuct : 1.5f; c.virtual_loss = mctsConfig_.virtualLoss;
+    c.evaluator = b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET; c.net_blocks = b->blocks(); c.net_channels = b->channels();
+    c.deterministic = deterministic_ ? 1 : 0; c.dirichlet_alpha = dirichletAlpha_; c.dirichlet_epsilon = dirichletEpsilon_;
+    c.init_temperature = initialTemperature_; c.final_temperature = finalTemperature_; c.temperature_drop_move = temperatureDropMove_; c.auto_restart = 1;
+    c.sample_ring_capacity = c.n_slots * bs * bs;
+    az_engine* e = nullptr;
+    check(az_engine_create(&c, &e), "az_engine_create");
+    std::vector<GameRecord> done;
+    if (saveGames_) std::filesystem::create_directories(outputDir_);
+    try {
+        if (!b->isHash()) check(az_engine_load_weights(e, b->blob().data(), b->blob().size()), "az_engine_load_weights");
+        az_sample_layout L; check(az_engine_sample_layout(e, &L), "az_engine_sample_layout");
+        std::vector<uint8_t> buf((size_t)c.sample_ring_capacity * L.record_bytes);
+        const int A = bs * bs;
+        while ((int)done.size() < numGames_ && !abort_) {
+            const auto t0 = std::chrono::steady_clock::now();
+            check(az_engine_play(e, 1), "az_engine_play");
+            size_t n = 0; check(az_engine_drain_samples(e, buf.data(), (size_t)c.sample_ring_capacity, &n), "az_engine_drain_samples");
+            const int64_t ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+            totalMoves_ += c.n_slots;
+            // samples of one finished game are contiguous and in ply order (k_finish_games)
+            size_t i = 0;
+            while (i < n && (int)done.size() < numGames_) {
+                const uint8_t* r0 = buf.data() + i * L.record_bytes;
+                uint32_t gid; int32_t slot; std::memcpy(&gid, r0 + L.off_game_id, 4); std::memcpy(&slot, r0 + L.off_slot, 4);
+                GameRecord rec(gameType, bs, false);
+                int8_t result = 0;
+                for (; i < n; ++i) {
+                    const uint8_t* r = buf.data() + i * L.record_bytes;
+                    uint32_t g2; int32_t s2; std::memcpy(&g2, r + L.off_game_id, 4); std::memcpy(&s2, r + L.off_slot, 4);
+                    if (g2 != gid || s2 != slot) break;
+                    int16_t action; float rv; std::memcpy(&action, r + L.off_action, 2); std::memcpy(&rv, r + L.off_root_value, 4); std::memcpy(&result, r + L.off_result, 1);
+                    std::vector<float> pol(A, 0.0f); float tot = 0.0f;
+                    for (int a = 0; a < A; ++a) { uint16_t v; std::memcpy(&v, r + L.off_visits + 2 * a, 2); pol[a] = (float)v; tot += pol[a]; }
+                    if (tot > 0) for (auto& x : pol) x /= tot;            // action-indexed visit distribution
+                    rec.addMove(action, pol, rv, ms);
+                }
+                rec.setResult((core::GameResult)result);
+                if (saveGames_) {
+                    std::ostringstream fn; fn << outputDir_ << "/" << std::setfill('0') << std::setw(3) << done.size() << "_slot" << slot << "_" << gid << ".json";
+                    rec.saveToFile(fn.str());
+                }
+                done.push_back(std::move(rec));
+                completedGames_ = (int)done.size();
+                if (progressCallback_) progressCallback_((int)done.size() - 1, (int)done.back().getMoves().size(), numGames_, totalMoves_.load());
+            }
+        }
+    } catch (...) { az_engine_destroy(e); running_ = false; throw; }
+    az_engine_destroy(e);
+    running_ = false;
+    return done;
+}
+
+}  // namespace selfplay
+}  // namespace alphazero

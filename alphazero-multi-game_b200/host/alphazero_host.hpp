@@ -1,0 +1,340 @@
+// alphazero_host.hpp — C++ host side above the C ABI: the reference's class names, signatures and error behaviour
+// for the self-play path, implemented on top of libaz_b200.so (include/az_b200.h).  No search or network arithmetic
+// happens here: these classes hold moves / configuration and forward to the engine.
+//
+// Mirrors (reference file:line):
+//   core::IGameState                 include/alphazero/core/igamestate.h:60-223
+//   gomoku::GomokuState              include/alphazero/games/gomoku/gomoku_state.h:21-171 (standard rules)
+//   nn::NeuralNetwork                include/alphazero/nn/neural_network.h:19-131
+//   mcts::MCTSConfig / ParallelMCTS  include/alphazero/mcts/parallel_mcts.h:41-74, 131-282
+//   selfplay::MoveData / GameRecord  include/alphazero/selfplay/game_record.h:18-126
+//   selfplay::SelfPlayManager        include/alphazero/selfplay/self_play_manager.h:28-196
+#pragma once
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#include "../../include/az_b200.h"
+
+namespace alphazero {
+
+namespace core {
+
+enum class GameType { GOMOKU, CHESS, GO };
+enum class GameResult { ONGOING, DRAW, WIN_PLAYER1, WIN_PLAYER2 };
+
+class GameStateException : public std::runtime_error {
+public:
+    explicit GameStateException(const std::string& m) : std::runtime_error(m) {}
+};
+class IllegalMoveException : public GameStateException {
+public:
+    IllegalMoveException(const std::string& m, int action) : GameStateException(m), action_(action) {}
+    int getAction() const { return action_; }
+private:
+    int action_;
+};
+
+class IGameState {
+public:
+    explicit IGameState(GameType t) : gameType_(t) {}
+    virtual ~IGameState() = default;
+    virtual std::vector<int> getLegalMoves() const = 0;
+    virtual bool isLegalMove(int action) const = 0;
+    virtual void makeMove(int action) = 0;
+    virtual bool undoMove() = 0;
+    virtual bool isTerminal() const = 0;
+    virtual GameResult getGameResult() const = 0;
+    virtual int getCurrentPlayer() const = 0;
+    virtual int getBoardSize() const = 0;
+    virtual int getActionSpaceSize() const = 0;
+    virtual std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const = 0;
+    virtual std::vector<std::vector<std::vector<float>>> getEnhancedTensorRepresentation() const = 0;
+    virtual uint64_t getHash() const = 0;
+    virtual std::unique_ptr<IGameState> clone() const = 0;
+    virtual std::string actionToString(int action) const = 0;
+    virtual std::optional<int> stringToAction(const std::string& s) const = 0;
+    virtual std::string toString() const = 0;
+    virtual bool equals(const IGameState& other) const = 0;
+    virtual std::vector<int> getMoveHistory() const = 0;
+    virtual bool validate() const = 0;
+    GameType getGameType() const { return gameType_; }
+protected:
+    GameType gameType_;
+};
+
+std::unique_ptr<IGameState> createGameState(GameType type, int boardSize = 0, bool variantRules = false);
+
+}  // namespace core
+
+namespace gomoku {
+
+constexpr int BLACK = 1, WHITE = 2;
+
+// Host-side state container: bitboards + history, standard rules.  Rules arithmetic is the SAME header the kernels
+// compile (csrc/gomoku.cuh, host+device) for 15x15 and 9x9; other sizes use the generic loop below it.
+class GomokuState : public core::IGameState {
+public:
+    GomokuState(int board_size = 15, bool use_renju = false, bool use_omok = false, int seed = 0, bool use_pro_long_opening = false);
+    std::vector<int> getLegalMoves() const override;
+    bool isLegalMove(int action) const override;
+    void makeMove(int action) override;
+    bool undoMove() override;
+    bool isTerminal() const override;
+    core::GameResult getGameResult() const override;
+    int getCurrentPlayer() const override { return current_player; }
+    int getBoardSize() const override { return board_size; }
+    int getActionSpaceSize() const override { return board_size * board_size; }
+    std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const override;
+    std::vector<std::vector<std::vector<float>>> getEnhancedTensorRepresentation() const override;
+    uint64_t getHash() const override;
+    std::unique_ptr<core::IGameState> clone() const override { return std::make_unique<GomokuState>(*this); }
+    std::string actionToString(int action) const override;
+    std::optional<int> stringToAction(const std::string& s) const override;
+    std::string toString() const override;
+    bool equals(const core::IGameState& other) const override;
+    std::vector<int> getMoveHistory() const override { return move_history; }
+    bool validate() const override;
+    bool is_occupied(int action) const;
+    std::vector<std::vector<int>> get_board() const;
+    // true until the legal moves of this lineage were enumerated once (QUIRK G2: first-fill order)
+    bool neverEnumerated() const { return never_filled_; }
+
+    int board_size;
+    int current_player;
+private:
+    int winner() const;
+    std::vector<int8_t> cells_;                 // 0 empty, 1 black, 2 white; index a = x*N + y
+    std::vector<int> move_history;
+    // legal-move cache with the reference's container, so its iteration order is the reference's
+    mutable std::unordered_set<int> cached_valid_moves_;
+    mutable bool valid_moves_dirty_ = true;
+    mutable bool never_filled_ = true;
+};
+
+}  // namespace gomoku
+
+namespace nn {
+
+class NeuralNetwork {
+public:
+    virtual ~NeuralNetwork() = default;
+    virtual std::pair<std::vector<float>, float> predict(const core::IGameState& state) = 0;
+    virtual void predictBatch(const std::vector<std::reference_wrapper<const core::IGameState>>& states,
+                              std::vector<std::vector<float>>& policies, std::vector<float>& values) = 0;
+    virtual bool isGpuAvailable() const = 0;
+    virtual std::string getDeviceInfo() const = 0;
+    virtual float getInferenceTimeMs() const = 0;
+    virtual int getBatchSize() const = 0;
+    virtual std::string getModelInfo() const = 0;
+    virtual size_t getModelSizeBytes() const = 0;
+    virtual void benchmark(int numIterations = 100, int batchSize = 16) = 0;
+    virtual void enableDebugMode(bool enable) = 0;
+    virtual void printModelSummary() const = 0;
+    // modelPath: an AZW1 weight blob (net.py:export_weights); "" or "hash" → the stateless HashEvaluator (parity runs)
+    static std::unique_ptr<NeuralNetwork> create(const std::string& modelPath, core::GameType gameType, int boardSize = 0, bool useGpu = true);
+};
+
+// The evaluator the engine runs on the device: either the bf16 ResNet (weights from an AZW1 blob) or the hash evaluator.
+class B200NeuralNetwork : public NeuralNetwork {
+public:
+    B200NeuralNetwork(const std::string& modelPath, core::GameType gameType, int boardSize);
+    ~B200NeuralNetwork() override;
+    std::pair<std::vector<float>, float> predict(const core::IGameState& state) override;
+    void predictBatch(const std::vector<std::reference_wrapper<const core::IGameState>>& states,
+                      std::vector<std::vector<float>>& policies, std::vector<float>& values) override;
+    bool isGpuAvailable() const override { return true; }
+    std::string getDeviceInfo() const override;
+    float getInferenceTimeMs() const override { return lastMs_; }
+    int getBatchSize() const override { return batch_; }
+    std::string getModelInfo() const override;
+    size_t getModelSizeBytes() const override { return blob_.size(); }
+    void benchmark(int numIterations = 100, int batchSize = 16) override;
+    void enableDebugMode(bool) override {}
+    void printModelSummary() const override;
+    bool isHash() const { return hash_; }
+    const std::vector<uint8_t>& blob() const { return blob_; }
+    core::GameType gameType() const { return gameType_; }
+    int boardSize() const { return boardSize_; }
+    int blocks() const { return blocks_; }
+    int channels() const { return channels_; }
+private:
+    void ensureEngine();
+    std::vector<uint8_t> blob_;
+    bool hash_ = false;
+    core::GameType gameType_;
+    int boardSize_, blocks_ = 0, channels_ = 128, batch_ = 64;
+    az_engine* eng_ = nullptr;
+    float lastMs_ = 0.0f;
+};
+
+}  // namespace nn
+
+namespace mcts {
+
+enum class MCTSNodeSelection { UCB, PUCT, PROGRESSIVE_BIAS, RAVE };
+enum class MCTSSearchMode { SERIAL, PARALLEL, BATCHED };
+
+struct MCTSConfig {   // include/alphazero/mcts/parallel_mcts.h:41-74 (same names, same defaults)
+    int numThreads = 1;
+    int numSimulations = 800;
+    float cPuct = 1.5f;
+    float fpuReduction = 0.0f;
+    int virtualLoss = 3;
+    int maxSearchDepth = 1000;
+    bool useDirichletNoise = false;
+    float dirichletAlpha = 0.03f;
+    float dirichletEpsilon = 0.25f;
+    bool useBatchInference = false;
+    bool useTemporalDifference = false;
+    float tdLambda = 0.8f;
+    bool useProgressiveWidening = false;
+    int minVisitsForWidening = 10;
+    float progressiveWideningBase = 2.0f;
+    float progressiveWideningExponent = 0.5f;
+    MCTSNodeSelection selectionStrategy = MCTSNodeSelection::PUCT;
+    int maxRetries = 3;
+    int transpositionTableSize = 1048576;
+    uint64_t cacheEntryMaxAge = 60000;
+    bool useFmapCache = false;
+    int batchSize = 16;
+    bool useBatchedMCTS = false;
+    int batchTimeoutMs = 5;
+    MCTSSearchMode searchMode = MCTSSearchMode::PARALLEL;
+    bool pinThreads = false;
+    bool deterministic = false;
+    int cacheSize = 2097152;
+};
+
+struct MCTSStats {
+    size_t nodesCreated = 0, nodesExpanded = 0, nodesTotalVisits = 0, simulationCount = 0, evaluationCalls = 0,
+           cacheHits = 0, cacheMisses = 0, batchedEvaluations = 0, totalBatches = 0;
+};
+
+// The reference's TT is an evaluation cache that is result-transparent with a deterministic evaluator;
+// the engine has no use for it.  Kept so existing call sites construct and pass one.
+class TranspositionTable {
+public:
+    explicit TranspositionTable(size_t size = 1048576, size_t numShards = 1024) : size_(size) { (void)numShards; }
+    size_t getSize() const { return size_; }
+    float getHitRate() const { return 0.0f; }
+    size_t getLookups() const { return 0; }
+    size_t getHits() const { return 0; }
+    size_t getEntryCount() const { return 0; }
+    size_t getMemoryUsageBytes() const { return 0; }
+    void clear() {}
+    void resize(size_t s) { size_ = s; }
+private:
+    size_t size_;
+};
+
+class ParallelMCTS {
+public:
+    ParallelMCTS(const core::IGameState& rootState, nn::NeuralNetwork* nn = nullptr, TranspositionTable* tt = nullptr,
+                 int numThreads = 1, int numSimulations = 800, float cPuct = 1.5f, float fpuReduction = 0.0f, int virtualLoss = 3);
+    ParallelMCTS(const core::IGameState& rootState, const MCTSConfig& config, nn::NeuralNetwork* nn = nullptr, TranspositionTable* tt = nullptr);
+    ~ParallelMCTS();
+    void search();
+    int selectAction(bool isTraining = false, float temperature = 1.0f);
+    std::vector<float> getActionProbabilities(float temperature = 1.0f) const;
+    float getRootValue() const;
+    void updateWithMove(int action);
+    void addDirichletNoise(float alpha = 0.03f, float epsilon = 0.25f);
+    void setNumThreads(int n) { config_.numThreads = n; }
+    void setNumSimulations(int n) { config_.numSimulations = n; }
+    void setCPuct(float c);
+    void setFpuReduction(float f) { config_.fpuReduction = f; }
+    void setVirtualLoss(int v);
+    void setDeterministicMode(bool enable) { config_.useBatchInference = enable; }
+    void setDebugMode(bool) {}
+    std::string getSearchInfo() const;
+    void printSearchStats() const;
+    size_t getMemoryUsage() const;
+    MCTSStats getStats() const;
+    // root children in the reference's child order
+    struct RootStats { std::vector<int> actions, visits; std::vector<float> valueSums, priors; int rootVisits = 0; float rootValueSum = 0; };
+    RootStats rootStats() const;
+private:
+    void build(const core::IGameState& rootState);
+    MCTSConfig config_;
+    nn::NeuralNetwork* nn_;
+    az_engine* eng_ = nullptr;
+    std::unique_ptr<core::IGameState> rootState_;
+    bool searched_ = false;
+};
+
+}  // namespace mcts
+
+namespace selfplay {
+
+struct MoveData {
+    int action = -1;
+    std::vector<float> policy;
+    float value = 0.0f;
+    int64_t thinking_time_ms = 0;
+    std::string toJson() const;
+    static MoveData fromJson(const std::string& jsonStr);
+};
+
+class GameRecord {
+public:
+    GameRecord(core::GameType gameType, int boardSize, bool useVariantRules = false);
+    void addMove(int action, const std::vector<float>& policy, float value, int64_t thinkingTimeMs);
+    void setResult(core::GameResult r) { result_ = r; }
+    std::tuple<core::GameType, int, bool> getMetadata() const { return {gameType_, boardSize_, useVariantRules_}; }
+    const std::vector<MoveData>& getMoves() const { return moves_; }
+    core::GameResult getResult() const { return result_; }
+    std::string toJson() const;                                  // src/selfplay/game_record.cpp:64-90 format
+    static GameRecord fromJson(const std::string& jsonStr);
+    bool saveToFile(const std::string& filename) const;
+    static GameRecord loadFromFile(const std::string& filename);
+private:
+    core::GameType gameType_; int boardSize_; bool useVariantRules_;
+    core::GameResult result_;
+    std::vector<MoveData> moves_;
+    std::chrono::system_clock::time_point timestamp_;
+};
+
+class SelfPlayManager {
+public:
+    SelfPlayManager(nn::NeuralNetwork* neuralNetwork, int numGames = 100, int numSimulations = 800, int numThreads = 4);
+    ~SelfPlayManager();
+    std::vector<GameRecord> generateGames(core::GameType gameType, int boardSize = 0, bool useVariantRules = false);
+    void setExplorationParams(float dirichletAlpha = 0.03f, float dirichletEpsilon = 0.25f, float initialTemperature = 1.0f,
+                              int temperatureDropMove = 30, float finalTemperature = 0.0f);
+    void setProgressCallback(std::function<void(int, int, int, int)> cb) { progressCallback_ = std::move(cb); }
+    void setBatchConfig(int batchSize, int batchTimeoutMs) { batchSize_ = batchSize; batchTimeoutMs_ = batchTimeoutMs; }
+    void setSaveGames(bool saveGames, const std::string& outputDir = "games") { saveGames_ = saveGames; outputDir_ = outputDir; }
+    void setAbort(bool abort) { abort_ = abort; }
+    bool isRunning() const { return running_; }
+    void setMctsConfig(const mcts::MCTSConfig& c) { mctsConfig_ = c; }
+    int getCompletedGamesCount() const { return completedGames_; }
+    int getTotalMovesCount() const { return totalMoves_; }
+    // engine knobs without a reference counterpart
+    void setConcurrentGames(int n) { concurrentGames_ = n; }     // game slots on the GPU (default min(numGames, 4096))
+    void setDeterministic(bool d) { deterministic_ = d; }        // noise off + first-max-visit move (parity runs)
+private:
+    nn::NeuralNetwork* nn_;
+    int numGames_, numSimulations_, numThreads_;
+    float dirichletAlpha_ = 0.03f, dirichletEpsilon_ = 0.25f, initialTemperature_ = 1.0f, finalTemperature_ = 0.0f;
+    int temperatureDropMove_ = 30;
+    bool saveGames_ = false; std::string outputDir_ = "games";
+    std::function<void(int, int, int, int)> progressCallback_;
+    std::atomic<bool> abort_{false}, running_{false};
+    std::atomic<int> completedGames_{0}, totalMoves_{0};
+    int batchSize_ = 64, batchTimeoutMs_ = 10, concurrentGames_ = 0;
+    bool deterministic_ = false;
+    mcts::MCTSConfig mctsConfig_;
+};
+
+}  // namespace selfplay
+}  // namespace alphazero

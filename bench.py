@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slots", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=800)
-    ap.add_argument("--streams", type=int, default=2, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
+    ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
     ap.add_argument("--ref-sims-per-step", type=int, default=200)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -58,7 +58,7 @@ typedef struct az_config {
     int32_t device;             /* CUDA device ordinal */
     uint64_t seed;              /* Philox key for noise / temperature sampling */
     int32_t n_streams;          /* stream groups the slots are split into (tree kernels of one group overlap the
-                                   network pass of another); 0 = default (2) */
+                                   network pass of another); 0 = default (1: measured no gain under the 1 kW power cap) */
     int32_t reserved_;
 } az_config;
 
@@ -99,6 +99,9 @@ AZ_API int az_engine_root_stats(az_engine* e, int slot, int32_t* actions, int32_
                          float* priors, int32_t* n_children, int32_t* root_visits, float* root_value_sum);
 /* ParallelMCTS::updateWithMove(action) per slot (src/mcts/parallel_mcts.cpp:1065-1108); actions[slot] = -2 skips a slot */
 AZ_API int az_engine_advance(az_engine* e, const int32_t* actions, int n);
+/* ParallelMCTS::addDirichletNoise(alpha, epsilon) on every active slot's root (expanding it first if needed),
+ * src/mcts/parallel_mcts.cpp:1110-1171 */
+AZ_API int az_engine_add_dirichlet_noise(az_engine* e, float alpha, float epsilon);
 /* SelfPlayManager::playSingleGame loop body for all slots, `n_moves` times: search → getActionProbabilities /
  * selectAction / getRootValue → record → makeMove → updateWithMove → noise (src/selfplay/self_play_manager.cpp:187-217) */
 AZ_API int az_engine_play(az_engine* e, int n_moves);

@@ -13,6 +13,6 @@ from alphazero_multi_game_b200 import net as N  # noqa: E402
 
 def hash_engine(n_slots, board=15, sims=800, **kw):
     cfg = dict(game=E.GOMOKU, board_size=board, n_slots=n_slots, num_simulations=sims, evaluator=E.EVAL_HASH,
-               deterministic=1, auto_restart=0, max_nodes_per_tree=2 * (sims + 1) * board * board + 1)
+               deterministic=1, auto_restart=0, max_nodes_per_tree=2 * (sims + 1) * board * board + 1, n_streams=2)
     cfg.update(kw)
     return E.Engine(**cfg)

@@ -1,0 +1,109 @@
+"""CPU suite, part 3: the reference-shaped pybind module `_alphazero_cpp` (host side above the C ABI): same names,
+argument meaning and error behaviour as src/pybind/python_bindings.cpp for the self-play path."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import _orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "alphazero-multi-game_b200")
+
+
+def _mod():
+    sys.path.insert(0, PKG)
+    try:
+        import _alphazero_cpp as az
+    except ImportError:
+        import subprocess
+        subprocess.check_call(["bash", os.path.join(PKG, "host", "build.sh")])
+        import _alphazero_cpp as az
+    return az
+
+
+def test_module_surface_matches_reference_names():
+    az = _mod()
+    for name in ["GameType", "GameResult", "MCTSNodeSelection", "MCTSSearchMode", "IGameState", "GomokuState", "createGameState",
+                 "NeuralNetwork", "createNeuralNetwork", "MCTSConfig", "MCTSStats", "TranspositionTable", "ParallelMCTS", "MoveData",
+                 "GameRecord", "SelfPlayManager"]:
+        assert hasattr(az, name), name
+    for meth in ["search", "selectAction", "getActionProbabilities", "getRootValue", "updateWithMove", "addDirichletNoise", "setNumSimulations",
+                 "setDeterministicMode", "getSearchInfo", "getMemoryUsage"]:
+        assert hasattr(az.ParallelMCTS, meth), meth
+    for meth in ["generateGames", "setExplorationParams", "setProgressCallback", "setBatchConfig", "setSaveGames", "setAbort", "isRunning",
+                 "setMctsConfig", "getCompletedGamesCount", "getTotalMovesCount"]:
+        assert hasattr(az.SelfPlayManager, meth), meth
+    c = az.MCTSConfig()
+    assert (c.numSimulations, c.virtualLoss) == (800, 3) and abs(c.cPuct - 1.5) < 1e-7 and c.fpuReduction == 0.0
+    assert int(az.GameType.GO) == 2 and int(az.GameResult.WIN_PLAYER2) == 3
+
+
+def test_gomoku_state_matches_oracle_including_legal_order():
+    az = _mod()
+    O = _orc.oracle()
+    rng = np.random.default_rng(5)
+    for n in (15, 9):
+        for g in range(6):
+            s = az.GomokuState(n); o = O.new_state(_orc.GOMOKU, n)
+            enumerate_always = g % 2 == 0
+            for ply in range(n * n + 1):
+                if enumerate_always or ply % 7 == 3:
+                    assert s.getLegalMoves() == O.legal(o).tolist(), (n, g, ply)    # incl. first-fill order (QUIRK G2)
+                assert s.isTerminal() == bool(O.state_is_terminal(o))
+                assert int(s.getGameResult()) == O.state_result(o)
+                assert s.getCurrentPlayer() == O.state_current_player(o)
+                if ply % 5 == 0:
+                    assert np.array_equal(np.array(s.getEnhancedTensorRepresentation(), np.float32), O.tensor(o))
+                if s.isTerminal():
+                    break
+                a = int(rng.choice(O.legal(o)))
+                if not enumerate_always:
+                    pass
+                s.makeMove(a); O.state_make_move(o, a)
+    s = az.GomokuState(15)
+    with pytest.raises(RuntimeError):
+        s.makeMove(225)
+    s.makeMove(112)
+    with pytest.raises(RuntimeError):
+        s.makeMove(112)
+    assert s.is_occupied(112) and not s.is_occupied(0) and s.get_board()[7][7] == 1
+    assert s.actionToString(112) == "H8" and s.stringToAction("H8") == 112
+    with pytest.raises(RuntimeError):
+        az.createGameState(az.GameType.CHESS)
+    assert az.createGameState(az.GameType.GOMOKU).getBoardSize() == 15
+
+
+def test_game_record_json_roundtrip_reference_format():
+    az = _mod()
+    r = az.GameRecord(az.GameType.GOMOKU, 15, False)
+    r.addMove(112, [0.25, 0.75], 0.5, 12)
+    r.addMove(113, [1.0], -0.25, 7)
+    r.setResult(az.GameResult.WIN_PLAYER1)
+    j = json.loads(r.toJson())
+    assert set(j) == {"game_type", "board_size", "use_variant_rules", "result", "timestamp", "moves"}      # game_record.cpp:64-90
+    assert j["game_type"] == 0 and j["board_size"] == 15 and j["result"] == 2 and len(j["moves"]) == 2
+    assert set(j["moves"][0]) == {"action", "policy", "value", "thinking_time_ms"}
+    r2 = az.GameRecord.fromJson(r.toJson())
+    assert [m.action for m in r2.getMoves()] == [112, 113] and r2.getResult() == az.GameResult.WIN_PLAYER1
+    with pytest.raises(RuntimeError):
+        az.GameRecord.fromJson("{not json")
+
+
+def test_search_classes_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    az = _mod()
+    nn = az.createNeuralNetwork("hash", az.GameType.GOMOKU, 15)
+    assert "Hash" in nn.getModelInfo()
+    pol, v = nn.predict(az.GomokuState(15))        # the hash evaluator is host arithmetic (test evaluator), no engine needed
+    O = _orc.oracle()
+    po, vo = O.hash_policy_value(O.new_state(_orc.GOMOKU, 15))
+    assert np.array_equal(np.array(pol, np.float32), po) and np.float32(v) == vo
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        az.ParallelMCTS(az.GomokuState(15), nn)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        az.SelfPlayManager(nn, 2, 10, 1).generateGames(az.GameType.GOMOKU, 15, False)
