@@ -88,42 +88,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
+        // One thread issues every tcgen05.mma of the CTA, so the issue loop itself is on the critical path: a 128x128x16
+        // MMA occupies the tensor pipe for 64 cycles and the loop must spend fewer instructions than that per MMA.
+        // Descriptors are therefore built once; inside the loop a descriptor is `base + constant` (the start-address
+        // field is the low 14 bits in 16-byte units and never carries into the LBO field for addresses < 256 KB).
         constexpr uint32_t IDESC = idesc_bf16(128, C::COUT);
-        const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
-        uint32_t wit = 0, ait = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
-            const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-            if (!((p.dbg & 8) && ait >= 2)) mbar_wait(&a_full[as], ph);
-            mbar_wait(&acc_empty[as], ph ^ 1);
-            tc_fence_after();
-            const uint32_t acc = tmem_base + as * 256;
-            for (int tap = 0; tap < 9; ++tap) {
-                const int shift = (tap / 3 - 1) * p.row_pitch + (tap % 3 - 1);
-                for (int h = 0; h < C::STAGES_PER_TAP; ++h, ++wit) {
-                    const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
-                    if (!((p.dbg & 4) && wit >= C::NWS)) mbar_wait(&w_full[ws], wph);
-                    tc_fence_after();
-                    if (lane == 0) {
+        if (lane == 0) {
+            const bool skip_a = (p.dbg & 8) != 0, skip_w = (p.dbg & 4) != 0;
+            const uint64_t a_desc0 = smem_desc(smem_u32(sA) + CONV_HALO * 16, C::PLANE, 128);
+            const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
+            const int row_pitch = p.row_pitch;
+            uint32_t wit = 0, ait = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
+                const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                if (!(skip_a && ait >= 2)) mbar_wait(&a_full[as], ph);
+                mbar_wait(&acc_empty[as], ph ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + as * 256;
+                const uint64_t a_item = a_desc0 + (uint64_t)(as * (C::A_STAGE >> 4));
+                uint32_t accumulate = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int shift = (tap / 3 - 1) * row_pitch + (tap % 3 - 1);      // rows == 16-byte units
+                    const uint64_t a_tap = a_item + (uint64_t)(int64_t)shift;
 #pragma unroll
-                        for (int it = 0; it < 2 * C::KSTEPS; ++it) {
-                            {
-                                const int mt = (p.dbg & 1) ? (it & 1) : (it / C::KSTEPS);
-                                const int kk = (p.dbg & 1) ? (it >> 1) : (it % C::KSTEPS);
-                                const int kc = h * (C::WK / 8) + 2 * kk;
-                                const uint32_t a_addr = sA_u + as * C::A_STAGE + kc * C::PLANE + (CONV_HALO + mt * 128 + shift) * 16;
-                                const uint32_t b_addr = sW_u + ws * C::W_STAGE + (2 * kk) * C::WPLANE;
-                                umma_bf16(acc + mt * 128, smem_desc(a_addr, C::PLANE, 128), smem_desc(b_addr, C::WPLANE, 128), IDESC,
-                                          (tap | h | kk) != 0 ? 1u : 0u);
+                    for (int h = 0; h < C::STAGES_PER_TAP; ++h, ++wit) {
+                        const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
+                        if (!(skip_w && wit >= C::NWS)) mbar_wait(&w_full[ws], wph);
+                        tc_fence_after();
+                        const uint64_t b_st = b_desc0 + (uint64_t)(ws * (C::W_STAGE >> 4));
+                        const uint64_t a_h = a_tap + (uint64_t)(h * (C::WK / 8) * (C::PLANE >> 4));
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+                            for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                                umma_bf16(acc + mt * 128, a_h + (uint64_t)(2 * kk * (C::PLANE >> 4) + mt * 128),
+                                          b_st + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, kk == 0 ? accumulate : 1u);
                             }
                         }
-                        if (!(p.dbg & 4)) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
+                        accumulate = 1;
+                        if (!skip_w) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
                     }
-                    __syncwarp();
                 }
+                if (!skip_a) umma_commit(&a_empty[as]);
+                umma_commit(&acc_full[as]);
             }
-            if (lane == 0) { if (!(p.dbg & 8)) umma_commit(&a_empty[as]); umma_commit(&acc_full[as]); }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // ===================== epilogue (warps 0-3) =====================
         uint32_t ait = 0;
@@ -181,15 +192,242 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_conv3x3_pair — the 128 -> 128 layer as a WEIGHT-STATIONARY CTA-PAIR kernel (cta_group::2).
+//
+// Why: with one CTA per tile the single-CTA kernel re-streams the whole 295 KB weight image from L2 into shared memory
+// for every 256 rows (1.5 GB per launch) and each 128x128x16 MMA reads 8 KB of operands from shared memory in 64 cycles
+// — exactly the shared-memory bandwidth, with the TMA fills on top.  A CTA pair splits B by N: each CTA holds HALF the
+// weights (64 output channels x 1152 K = 147 KB), which fits in shared memory next to two activation stages, so the
+// weights are loaded ONCE per launch and an MMA (M = 256: one 128-row tile per CTA, N = 128, K = 16) reads 4 KB of A and
+// 2 KB of B per CTA per 64 cycles.  L2 -> SM traffic drops from 1.8 GB to the activations alone.
+//
+// Work item = 256 consecutive rows of the padded position stream, 128 per CTA (rank r takes rows 256 i + 128 r).
+// Roles per CTA (192 threads): warps 0-3 epilogue, warp 4 TMA producer, warp 5 = MMA issuer in the leader (rank 0) /
+// relay in the peer (forwards "my stage is full" to the leader's barriers with a remote mbarrier arrive; bulk copies can
+// only signal a barrier of the CTA they write to).  tcgen05.commit is multicast to both CTAs' barriers.
+constexpr int PAIR_HALO = 17;                                   // max |tap shift| = row_pitch + 1 <= 17  (W <= 15)
+struct PairCfg {
+    static constexpr int ROWS = 128 + 2 * PAIR_HALO;            // 162 rows per A tile incl. halo
+    static constexpr int PLANE = ROWS * 16;                     // 2592 B per 8-channel chunk
+    static constexpr int A_STAGE = 16 * PLANE;                  // 41,472 B
+    static constexpr int WPLANE = 64 * 16;                      // 1 KB: 64 output channels x 8 input channels
+    static constexpr int WTAP = 16 * WPLANE;                    // 16 KB per tap
+    static constexpr int W_BYTES = 9 * WTAP;                    // 147,456 B: this CTA's half of the layer
+    static constexpr int OFF_A = W_BYTES;
+    static constexpr int OFF_BIAS = OFF_A + 2 * A_STAGE;
+    static constexpr int OFF_BARS = OFF_BIAS + CONV_COUT * 4;
+    static constexpr int OFF_TSLOT = OFF_BARS + 16 * 8;
+    static constexpr int SMEM = OFF_TSLOT + 16;                 // 231,056 B
+};
+
+// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 → four 16-byte stores
+__device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
+                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8), b1 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bb[e];
+        if (has_res) {
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+        }
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x = v[2 * e], y = v[2 * e + 1];
+            if (relu) { x = fmaxf(x, 0.0f); y = fmaxf(y, 0.0f); }
+            if (!valid) { x = 0.0f; y = 0.0f; }
+            ob[e] = __floats2bfloat162_rn(x, y);
+        }
+        if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
+        *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
+    }
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvParams p) {
+    using C = PairCfg;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + C::OFF_A;
+    float* sBias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::OFF_TSLOT);
+    uint64_t* a_full = bars;            // [2] own TMA (+ in the leader: the peer's relay) → leader: MMA issuer | peer: relay
+    uint64_t* a_empty = bars + 2;       // [2] MMA commit (multicast) → own TMA producer
+    uint64_t* acc_full = bars + 4;      // [2] MMA commit (multicast) → own epilogue
+    uint64_t* acc_empty = bars + 6;     // [2] leader only: 4 local + 4 remote epilogue warps → MMA issuer
+    uint64_t* w_full = bars + 8;        // [1] own weight half loaded (+ in the leader: the peer's)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_rows = p.n_boards_dev ? (*p.n_boards_dev) * p.board_pitch : p.n_rows;
+    const int n_items = (n_rows + 255) / 256;
+    const int first_item = (int)cluster_id_x(), item_step = (int)n_clusters_x();
+
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = rank == 0 ? 2 : 1;      // the leader's "full" barriers also take the peer relay's arrival
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        mbar_init(w_full, full_count);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < CONV_COUT; i += CONV_THREADS) sBias[i] = p.bias[i];
+    if (warp == 5) tmem_alloc2(tslot, 256);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    if (first_item < n_items) {
+        if (warp == 4) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                mbar_arrive_expect_tx(w_full, C::W_BYTES);
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * C::W_BYTES;
+                for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
+                uint32_t ait = 0;
+                for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                    const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+                    if ((p.dbg & 8) && ait >= 2) continue;
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    mbar_arrive_expect_tx(&a_full[as], C::A_STAGE);
+                    const size_t row0 = (size_t)CONV_GUARD + (size_t)item * 256 + rank * 128 - PAIR_HALO;
+                    for (int kc = 0; kc < 16; ++kc)
+                        bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5 && rank != 0) {
+            // ===================== relay (peer CTA): my stage is full → second arrival on the leader's barrier =====================
+            if (lane == 0) {
+                mbar_wait(w_full, 0);
+                mbar_arrive_cluster(w_full, 0);
+                uint32_t ait = 0;
+                for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                    const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                    if ((p.dbg & 8) && ait >= 2) continue;
+                    mbar_wait(&a_full[as], ph);
+                    mbar_arrive_cluster(&a_full[as], 0);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5) {
+            // ===================== MMA issuer (leader CTA, one thread) =====================
+            // The tensor pipe accepts only ~2 MMAs ahead of execution (measured: the commit fires ~90 cycles after the last
+            // issue), so this thread runs in lock-step with the pipe: every instruction between two MMAs beyond a handful, and
+            // every barrier wait at an item boundary, is pipe idle time.  Hence: all 72 MMAs of an item unrolled with
+            // descriptors that are `register + constant`, per-tap bases computed once per launch, one fused wait per item.
+            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            {
+                // the whole warp runs the loop converged; the tcgen05 instructions sit under elect_one()
+                const bool skip_a = (p.dbg & 8) != 0;
+                const uint64_t a_desc0 = smem_desc(smem_u32(sA) + PAIR_HALO * 16, C::PLANE, 128);
+                const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
+                uint64_t a_tap0[9];
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap)
+                    a_tap0[tap] = a_desc0 + (uint64_t)(int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));     // tap shift in rows == 16-byte units
+                const long long t_begin = p.trace ? clock64() : 0;
+                long long wait_all = 0;
+                mbar_wait_cluster(w_full, 0);
+                if (p.trace && lane == 0) p.trace[1024 + 2 * first_item] = clock64() - t_begin;      // cycles until both weight halves are resident
+                uint32_t ait = 0;
+                for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                    const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                    const bool tr = p.trace != nullptr && first_item == 0 && ait < 64 && lane == 0;
+                    const long long tw0 = p.trace ? clock64() : 0;
+                    if (tr) p.trace[ait * 8 + 0] = tw0;
+                    if (skip_a && ait >= 2) mbar_wait_cluster(&acc_empty[as], ph ^ 1);
+                    else mbar_wait2_cluster(&a_full[as], ph, &acc_empty[as], ph ^ 1);
+                    if (p.trace) wait_all += clock64() - tw0;
+                    if (tr) p.trace[ait * 8 + 3] = clock64();
+                    tc_fence_after();
+                    const uint32_t acc = tmem_base + as * 128;
+                    const uint64_t a_off = (uint64_t)(as * (C::A_STAGE >> 4));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t a_tap = a_tap0[tap] + a_off;
+                            const uint64_t b_tap = b_desc0 + (uint64_t)(tap * (C::WTAP >> 4));
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                umma2_bf16(acc, a_tap + (uint64_t)(2 * kk * (C::PLANE >> 4)), b_tap + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC,
+                                           (kk == 0 && tap == 0) ? 0u : 1u);
+                        }
+                        if (!skip_a) umma2_commit_both(&a_empty[as]);
+                        umma2_commit_both(&acc_full[as]);
+                    }
+                    __syncwarp();
+                    if (tr) p.trace[ait * 8 + 4] = clock64();
+                }
+                if (p.trace && lane == 0) { p.trace[1024 + 2 * first_item + 1] = clock64() - t_begin; p.trace[1280 + 2 * first_item + 1] = wait_all; }
+            }
+        } else {
+            // ===================== epilogue (warps 0-3): TMEM lanes 32w..32w+31 = rows of this CTA's tile =====================
+            const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+            const size_t p_total = (size_t)p.p_total;
+            uint32_t ait = 0;
+            for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                const int row = item * 256 + (int)rank * 128 + warp * 32 + lane;
+                const size_t grow = (size_t)CONV_GUARD + row;
+                const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
+                // the residual does not depend on the MMAs: fetch all of it before waiting for the accumulator
+                uint4 res[16];
+                if (has_res && !(p.dbg & 2)) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.resid + ((size_t)q * p_total + grow) * 8);
+                }
+                mbar_wait(&acc_full[as], ph);
+                tc_fence_after();
+                const bool tr = p.trace != nullptr && first_item == 0 && ait < 64 && warp == 0 && lane == 0;
+                if (tr) p.trace[ait * 8 + 5 + rank * 512] = clock64();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128;
+                // TMEM → registers, software-pipelined: chunk c+1 is in flight while chunk c is converted and stored
+                uint32_t ra[32], rb[32];
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, rb);
+                if (!(p.dbg & 2)) pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, ra);
+                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, rb);
+                if (!(p.dbg & 2)) pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);      // accumulator drained: the leader's barrier (also from the leader itself)
+                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                if (tr) p.trace[ait * 8 + 6 + rank * 512] = clock64();
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                 // the peer's shared memory / TMEM / barriers stay alive until both CTAs are done
+    if (warp == 5) tmem_dealloc2(tmem_base, 256);
+}
+
 }  // namespace
 
 size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : Cfg<128>::SMEM; }
 
+bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= PAIR_HALO; }
+
 size_t conv_weight_elems(int cin_total) { return (size_t)9 * cin_total * CONV_COUT; }
 
-// Weight image = the exact shared-memory picture of each weight stage, stages in the order the kernel
-// consumes them: [tap][K stage h][8-channel chunk j][cout n][8 channels e].
-size_t conv_weight_index(int cin_total, int tap, int ci, int co) {
+// Weight image = the exact shared-memory picture the kernel consumes.
+//   single-CTA kernel: [tap][K stage h][8-channel chunk j][cout n][8 channels e], stages in consumption order;
+//   pair kernel:       [CTA rank r = cout / 64][tap][8-channel chunk j (16)][cout % 64][8 channels e].
+size_t conv_weight_index(int cin_total, bool pair, int tap, int ci, int co) {
+    if (pair) return ((((size_t)(co / 64) * 9 + tap) * 16 + ci / 8) * 64 + co % 64) * 8 + ci % 8;
     const int wk = cin_total < 64 ? cin_total : 64;
     const int spt = cin_total / wk;
     const int h = ci / wk, j = (ci % wk) / 8, e = ci % 8;
@@ -197,11 +435,20 @@ size_t conv_weight_index(int cin_total, int tap, int ci, int co) {
 }
 
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) {
-    static bool attr_done[2] = {false, false};
+    static bool attr_done[3] = {false, false, false};
     cudaError_t err;
     if (cin == 16) {
         if (!attr_done[0]) { err = cudaFuncSetAttribute(k_conv3x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::SMEM); if (err) return (int)err; attr_done[0] = true; }
         k_conv3x3<16><<<grid, CONV_THREADS, Cfg<16>::SMEM, stream>>>(p);
+    } else if (conv_uses_pair(cin, p.row_pitch)) {
+        if (!attr_done[2]) { err = cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM); if (err) return (int)err; attr_done[2] = true; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair, p);
+        if (err) return (int)err;
     } else if (cin == 128) {
         if (!attr_done[1]) { err = cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM); if (err) return (int)err; attr_done[1] = true; }
         k_conv3x3<128><<<grid, CONV_THREADS, Cfg<128>::SMEM, stream>>>(p);

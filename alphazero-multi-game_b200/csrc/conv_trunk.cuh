@@ -46,6 +46,7 @@ struct ConvParams {
     int p_total;                    // rows per channel-chunk plane
     int row_pitch;                  // W + 1
     int relu;
+    long long* trace;               // profiling only: per-item clock64 stamps of cluster 0 (conv_bench, AZ_CONV_TRACE), else nullptr
     int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
 };
 
@@ -53,7 +54,9 @@ size_t conv_smem_bytes(int cin);
 // launches on `stream`; cin in {16, 128}; returns cudaError_t as int
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream);
 // element index of weight (tap, cin, cout) inside the image for a layer with `cin` input channels
-size_t conv_weight_index(int cin_total, int tap, int ci, int co);
+size_t conv_weight_index(int cin_total, bool pair, int tap, int ci, int co);
+// true when the launch for (cin, row_pitch) goes to the weight-stationary CTA-pair kernel (its own weight image layout)
+bool conv_uses_pair(int cin, int row_pitch);
 size_t conv_weight_elems(int cin_total);
 
 }}  // namespace az::nn

@@ -119,7 +119,7 @@ struct Net {
             for (int co = 0; co < C; ++co)
                 for (int ci = 0; ci < cin_real; ++ci)
                     for (int t = 0; t < 9; ++t)
-                        img[nn::conv_weight_index(cin, t, ci, co)] = __float2bfloat16(cw[((size_t)co * cin_real + ci) * 9 + t] * sc[co]);
+                        img[nn::conv_weight_index(cin, nn::conv_uses_pair(cin, row_pitch), t, ci, co)] = __float2bfloat16(cw[((size_t)co * cin_real + ci) * 9 + t] * sc[co]);
             __nv_bfloat16* dw; float* db;
             if (dev_alloc(&dw, img.size()) || dev_alloc(&db, (size_t)C)) return -1;
             AZ_CUDA_CHECK(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
@@ -460,17 +460,18 @@ struct EngineT : EngineBase {
     int wave(Group& g, int mode) {
         cudaStream_t st = g.stream;
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
-        EncodeTarget enc{nullptr, 0, 0, 0};
-        if (cfg.evaluator == AZ_EVAL_RESNET) enc = EncodeTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch};
-        k_select<G><<<blocks_for_warps(g.n), 128, 0, st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
+        typename G::EncTarget enc{nullptr, 0, 0, 0};
+        if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch};
+        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
         if (cfg.evaluator == AZ_EVAL_HASH) {
-            k_hash_eval<G><<<blocks_for_warps(g.n), 128, 4 * A * sizeof(float), st>>>(leaf_state + g.t0, g.wb, g.n);
+            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(A * 4), st>>>(leaf_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
         }
-        k_expand_backup<G><<<blocks_for_warps(g.n), 128, 4 * A * sizeof(float), st>>>(g.tp, leaf_state + g.t0, g.wb, root_order + (size_t)g.t0 * A,
+        constexpr int MC = G::MAX_CHILDREN;
+        k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
                                                                                     root_order_n + g.t0, sparams(), g.n, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
         return 0;
@@ -665,6 +666,8 @@ struct EngineT : EngineBase {
         cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[1]; cp.bias = net.w.conv_b[1];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
+        long long* trace = nullptr;
+        if (getenv("AZ_CONV_TRACE")) { if (dev_alloc(&trace, 2048)) return -1; AZ_CUDA_CHECK(cudaMemset(trace, 0, 2048 * 8)); cp.trace = trace; }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, g.stream) == 0, "conv launch failed");
         AZ_CUDA_CHECK(cudaEventRecord(e0, g.stream));
@@ -673,6 +676,17 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaEventSynchronize(e1));
         float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (trace) {   // stamps of the last launch: cluster 0's issuer (top, waits done, issued) + epilogue (start, end) per item; totals per cluster
+            std::vector<long long> h(2048); AZ_CUDA_CHECK(cudaMemcpy(h.data(), trace, 2048 * 8, cudaMemcpyDeviceToHost)); cudaFree(trace);
+            const long long t0 = h[0];
+            for (int i = 0; i < 56; i += (i < 8 ? 1 : 8))
+                fprintf(stderr, "item %2d: top %7lld ready %7lld issued %7lld | epi0 %7lld..%7lld | epi1 (own clock) %7lld..%7lld\n", i, h[i * 8] - t0, h[i * 8 + 3] - t0,
+                        h[i * 8 + 4] - t0, h[i * 8 + 5] - t0, h[i * 8 + 6] - t0, h[i * 8 + 5 + 512] - h[5 + 512], h[i * 8 + 6 + 512] - h[5 + 512]);
+            long long mn = 1LL << 60, mx = 0, sum = 0, wmx = 0; int n = 0;
+            for (int c = 0; c < 74; ++c) { const long long v = h[1024 + 2 * c + 1]; if (v > 0) { mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++n; wmx = std::max(wmx, h[1024 + 2 * c]); } }
+            for (int c = 0; c < 74; c += 6) fprintf(stderr, "cluster %2d: total %lld  wait a_full %lld  wait all %lld\n", c, h[1024 + 2 * c + 1], h[1280 + 2 * c], h[1280 + 2 * c + 1]);
+            if (n) fprintf(stderr, "issuer cycles per cluster: min %lld avg %lld max %lld (%d clusters); weights resident after <= %lld cycles; %.1f us/launch => %.0f MHz\n", mn, sum / n, mx, n, wmx, *ms * 1e3, mx / (*ms * 1e3));
+        }
         launches += reps + 3;
         return 0;
     }

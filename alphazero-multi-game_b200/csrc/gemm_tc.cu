@@ -74,31 +74,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
         }
     } else if (warp == 5) {
         constexpr uint32_t IDESC = idesc_bf16(G_BM, G_BN);
-        const uint32_t s_u = smem_u32(smem);
-        uint32_t it = 0, ait = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
-            const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
-            mbar_wait(&acc_empty[as], aph ^ 1);
-            tc_fence_after();
-            for (int ks = 0; ks < k_stages; ++ks, ++it) {
-                const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
-                mbar_wait(&full[s], ph);
+        // single-thread issue loop: descriptors are `base + constant` (see conv_trunk.cu)
+        if (lane == 0) {
+            const uint64_t a_desc0 = smem_desc(smem_u32(smem), G_BM * 16, 128);
+            const uint64_t b_desc0 = smem_desc(smem_u32(smem) + G_A_STAGE, G_BN * 16, 128);
+            uint32_t it = 0, ait = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
+                const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t acc = tmem_base + as * G_BN;
+                uint32_t accumulate = 0;
+                for (int ks = 0; ks < k_stages; ++ks, ++it) {
+                    const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t so = (uint64_t)(s * (G_STAGE >> 4));
 #pragma unroll
-                    for (int kk = 0; kk < G_BK / 16; ++kk) {
-                        const uint32_t a_addr = s_u + s * G_STAGE + (2 * kk) * (G_BM * 16);
-                        const uint32_t b_addr = s_u + s * G_STAGE + G_A_STAGE + (2 * kk) * (G_BN * 16);
-                        umma_bf16(tmem_base + as * G_BN, smem_desc(a_addr, G_BM * 16, 128), smem_desc(b_addr, G_BN * 16, 128), IDESC,
-                                  (ks | kk) != 0 ? 1u : 0u);
-                    }
+                    for (int kk = 0; kk < G_BK / 16; ++kk)
+                        umma_bf16(acc, a_desc0 + so + (uint64_t)(2 * kk * G_BM), b_desc0 + so + (uint64_t)(2 * kk * G_BN), IDESC, kk == 0 ? accumulate : 1u);
+                    accumulate = 1;
                     umma_commit(&empty[s]);
                 }
-                __syncwarp();
+                umma_commit(&acc_full[as]);
             }
-            if (lane == 0) umma_commit(&acc_full[as]);
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         uint32_t ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {

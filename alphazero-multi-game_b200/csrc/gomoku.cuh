@@ -8,6 +8,9 @@
 // activation layout (conv_trunk.cu), so encode needs no index translation.
 #pragma once
 #include "common.cuh"
+#if defined(__CUDACC__)
+#include <cuda_bf16.h>
+#endif
 
 namespace az {
 
@@ -166,6 +169,91 @@ struct Gomoku {
             }
         }
     }
+
+#if defined(__CUDACC__)
+    // ---------------------------------------------------------------------------------------------
+    // Warp API used by the tree kernels (tree_kernels.cuh): the game state of the tree a warp owns lives in that
+    // warp's shared-memory workspace; mutating calls are made by the whole warp (lane 0 writes, __syncwarp after).
+    static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
+    static constexpr int MAX_CHILDREN = CELLS;
+    struct Warp { State s; };
+    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch; };
+
+    __device__ static void w_load(Warp& w, const State* g, int lane) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&w.s);
+        for (int i = lane; i < (int)(sizeof(State) / 4); i += 32) dst[i] = src[i];
+        __syncwarp();
+    }
+    __device__ static void w_store(const Warp& w, State* g, int lane) {
+        __syncwarp();
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&w.s);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(g);
+        for (int i = lane; i < (int)(sizeof(State) / 4); i += 32) dst[i] = src[i];
+    }
+    __device__ static void w_init(Warp& w, int lane) { if (lane == 0) init(w.s); __syncwarp(); }
+    // returns false if the reference's makeMove would throw (gomoku_state.cpp:681-689)
+    __device__ static bool w_apply(Warp& w, int a, int lane) {
+        const bool ok = a >= 0 && a < CELLS && !occupied(w.s, a);
+        __syncwarp();
+        if (ok && lane == 0) apply(w.s, a);
+        __syncwarp();
+        return ok;
+    }
+    __device__ static int w_result(Warp& w, int) { return result(w.s); }
+    __device__ static int w_player(const Warp& w) { return w.s.player; }
+    __device__ static int w_ply(const Warp& w) { return w.s.ply; }
+    __device__ static int visit_index(int action) { return action; }
+    // Legal moves in the reference's order (QUIRK G2): descending action index — std::unordered_set iteration order
+    // after any refill — except the first enumeration of a lineage (`root_order`, computed on the host with the real
+    // container).  Writes acts[i] and raw[i] = policy[action] (expandNodeWithPolicy, parallel_mcts.cpp:705-711).
+    __device__ static int w_enumerate(Warp& w, int lane, const int16_t* root_order, int root_order_n, int16_t* acts, float* raw, const float* pol) {
+        if (root_order != nullptr) {
+            for (int i = lane; i < root_order_n; i += 32) { const int a = root_order[i]; acts[i] = (int16_t)a; raw[i] = pol[a]; }
+            __syncwarp();
+            return root_order_n;
+        }
+        int cnt = 0;
+        for (int k = 0; k < CELLS; k += 32) {
+            const int a = CELLS - 1 - (k + lane);
+            const bool empty = a >= 0 && !occupied(w.s, a);
+            const unsigned m = __ballot_sync(0xffffffffu, empty);
+            if (empty) { const int i = cnt + __popc(m & ((1u << lane) - 1)); acts[i] = (int16_t)a; raw[i] = pol[a]; }
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        return cnt;
+    }
+    // legal moves for the state API (az_rules_replay): the order of every enumeration after the first
+    __device__ static int w_legal(Warp& w, int lane, int32_t* out) {
+        int cnt = 0;
+        for (int k = 0; k < CELLS; k += 32) {
+            const int a = CELLS - 1 - (k + lane);
+            const bool empty = a >= 0 && !occupied(w.s, a);
+            const unsigned m = __ballot_sync(0xffffffffu, empty);
+            if (empty) out[cnt + __popc(m & ((1u << lane) - 1))] = a;
+            cnt += __popc(m);
+        }
+        return cnt;
+    }
+    // feature planes straight into the conv trunk's input layout (bf16, 16 channels = 11 + 5 zero)
+    __device__ static void w_encode(Warp& w, int lane, const EncTarget& enc, int slot) {
+        const size_t row0 = (size_t)enc.guard + (size_t)slot * enc.board_pitch;
+        for (int p = lane; p < N * PITCH; p += 32) {
+            const int x = p / PITCH, y = p % PITCH;
+            if (y >= N) continue;                             // hole column stays zero
+            __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(c < PLANES ? feature(w.s, c, x, y) : 0.0f);
+            *reinterpret_cast<uint4*>(enc.ptr + ((size_t)0 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[0]);
+            *reinterpret_cast<uint4*>(enc.ptr + ((size_t)1 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[8]);
+        }
+    }
+    __device__ static void w_planes(Warp& w, int lane, float* out) {      // fp32 [PLANES][N][N] (state API)
+        for (int i = lane; i < PLANES * CELLS; i += 32) { const int c = i / CELLS, a = i % CELLS; out[i] = feature(w.s, c, a / N, a % N); }
+    }
+    __device__ static uint64_t w_key(Warp& w, int) { return key(w.s); }
+#endif
 };
 
 }  // namespace az

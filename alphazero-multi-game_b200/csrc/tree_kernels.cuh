@@ -13,41 +13,45 @@
 
 namespace az {
 
-struct EncodeTarget {          // where k_select writes the NN input planes (bf16), conv_trunk.cu layout
-    __nv_bfloat16* ptr;        // [CIN/8][p_total][8]; nullptr = no encoding (hash evaluator)
-    int p_total;               // rows per channel-chunk plane
-    int guard;                 // zero rows before board 0
-    int board_pitch;           // rows per board (PITCH*PITCH)
-};
-
 AZ_D int warp_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// Each warp owns one tree; its game state lives in the warp's slice of dynamic shared memory (G::Warp, see the
+// "Warp API" of gomoku.cuh / go.cuh).  Blocks are 128 threads = 4 warps.
+template <class G>
+AZ_D typename G::Warp& warp_ws(unsigned char* smem, int extra_bytes_per_warp = 0) {
+    constexpr int WS = (int)((sizeof(typename G::Warp) + 15) / 16 * 16);
+    return *reinterpret_cast<typename G::Warp*>(smem + (size_t)(threadIdx.x >> 5) * (WS + (extra_bytes_per_warp + 15) / 16 * 16));
+}
+template <class G>
+constexpr size_t warp_ws_bytes(int extra_bytes_per_warp = 0) { return 4 * ((sizeof(typename G::Warp) + 15) / 16 * 16 + (size_t)(extra_bytes_per_warp + 15) / 16 * 16); }
+
 // ------------------------------------------------------------------------------------------------
-// Selection (M3/M4) + leaf replay + terminal test (M10) + feature encoding (G5).
+// Selection (M3/M4) + leaf replay + terminal test (M10) + feature encoding (G5 / Go7).
 // mode 0: one simulation; mode 1: root-expansion wave (search() preamble, parallel_mcts.cpp:153-174).
 template <class G>
 __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
                                                typename G::State* __restrict__ leaf_state, WaveBuffers wb,
-                                               SearchParams sp, EncodeTarget enc, int T, int mode) {
-    using State = typename G::State;
+                                               SearchParams sp, typename G::EncTarget enc, int T, int mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    typename G::Warp& w = warp_ws<G>(smem);
     const size_t base = (size_t)t * tp.cap;
     const uint8_t tf = tp.tflags[t];
     int8_t kind = LEAF_NONE;
     int node = tp.root[t];
     int depth = 0;
     float tvalue = 0.0f;
-    State s = root_state[t];
 
     const bool live = (tf & TF_ACTIVE) && !(tf & TF_GAME_OVER);
     if (live) {
         const int rf = tp.first[base + node];
         const bool rterm = tp.flags[base + node] & NF_TERMINAL;
         if (mode == 1) {
-            if (rf < 0 && !rterm) kind = LEAF_EVAL;          // root needs its first evaluation
+            if (rf < 0 && !rterm) { kind = LEAF_EVAL; G::w_load(w, root_state + t, lane); }   // root needs its first evaluation
         } else if (rf >= 0 && !rterm) {
+            G::w_load(w, root_state + t, lane);
             // --- selectLeafWithPath (parallel_mcts.cpp:456-535).  The root carries one fresh virtual
             // loss while its children are scored (:461), so parentVisits = N_root + virtualLoss (:539).
             int* path = wb.path + (size_t)t * MAX_DEPTH;
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                 }
                 if (bi == 0x7fffffff) break;                    // no selectable child (bestChild == nullptr)
                 const int child = f + bi;
-                G::apply(s, (int)tp.act[base + child]);
+                G::w_apply(w, (int)tp.act[base + child], lane);
                 ++depth;
                 if (lane == 0) path[depth] = child;
                 node = child;
@@ -92,11 +96,11 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
             }
             // --- leaf classification (parallel_mcts.cpp:300-313)
             const uint8_t fl = tp.flags[base + node];
-            if (fl & NF_TERMINAL) { kind = LEAF_TERMINAL; tvalue = result_to_value((fl >> NF_RESULT_SHIFT) & 3, s.player); }
+            if (fl & NF_TERMINAL) { kind = LEAF_TERMINAL; tvalue = result_to_value((fl >> NF_RESULT_SHIFT) & 3, G::w_player(w)); }
             else {
-                const int res = G::result(s);
+                const int res = G::w_result(w, lane);
                 if (res != RES_ONGOING) {
-                    kind = LEAF_TERMINAL; tvalue = result_to_value(res, s.player);
+                    kind = LEAF_TERMINAL; tvalue = result_to_value(res, G::w_player(w));
                     if (lane == 0) tp.flags[base + node] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT));
                 } else kind = LEAF_EVAL;
             }
@@ -111,22 +115,10 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
     if (lane == 0) {
         wb.leaf_kind[t] = kind; wb.leaf_node[t] = node; wb.path_len[t] = (mode == 1 || kind == LEAF_NONE) ? 0 : depth;
         wb.leaf_value[t] = tvalue; wb.eval_slot[t] = slot;
-        if (kind == LEAF_EVAL) leaf_state[t] = s;
     }
-    // --- feature planes, straight into the conv trunk's input layout (bf16, 16 channels = 11 + 5 zero)
-    if (kind == LEAF_EVAL && enc.ptr != nullptr) {
-        const size_t row0 = (size_t)enc.guard + (size_t)slot * enc.board_pitch;
-        for (int p = lane; p < G::N * G::PITCH; p += 32) {
-            const int x = p / G::PITCH, y = p % G::PITCH;
-            if (y >= G::N) continue;                             // hole column stays zero
-            __align__(16) __nv_bfloat16 v[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(c < G::PLANES ? G::feature(s, c, x, y) : 0.0f);
-            uint4* d0 = reinterpret_cast<uint4*>(enc.ptr + ((size_t)0 * enc.p_total + row0 + p) * 8);
-            uint4* d1 = reinterpret_cast<uint4*>(enc.ptr + ((size_t)1 * enc.p_total + row0 + p) * 8);
-            *d0 = *reinterpret_cast<const uint4*>(&v[0]);
-            *d1 = *reinterpret_cast<const uint4*>(&v[8]);
-        }
+    if (kind == LEAF_EVAL) {
+        G::w_store(w, leaf_state + t, lane);
+        if (enc.ptr != nullptr) G::w_encode(w, lane, enc, slot);
     }
 }
 
@@ -136,15 +128,17 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
 // action order by one lane so it is the reference's fp32 sum bit for bit.
 template <class G>
 __global__ void __launch_bounds__(128) k_hash_eval(const typename G::State* __restrict__ leaf_state, WaveBuffers wb, int T) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= T) return;
     if (wb.leaf_kind[t] != LEAF_EVAL) return;
-    constexpr int A = G::CELLS;
-    float* raw = sm + wib * A;
+    constexpr int A = G::ACTIONS;
+    typename G::Warp& w = warp_ws<G>(smem, A * 4);
+    float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     const int slot = wb.eval_slot[t];
-    const uint64_t h = G::key(leaf_state[t]);
+    G::w_load(w, leaf_state + t, lane);
+    const uint64_t h = G::w_key(w, lane);
     for (int i = lane; i < A; i += 32) {
         const uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
         raw[i] = fdiv((float)(r + 1), 16777216.0f);
@@ -168,16 +162,18 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
                                                       WaveBuffers wb, const int16_t* __restrict__ root_order,
                                                       const int32_t* __restrict__ root_order_n, SearchParams sp,
                                                       int T, Stats* stats) {
-    using State = typename G::State;
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= T) return;
     const int8_t kind = wb.leaf_kind[t];
     if (kind == LEAF_NONE) return;
-    constexpr int A = G::CELLS;
+    constexpr int A = G::ACTIONS, MC = G::MAX_CHILDREN;
+    constexpr int EXTRA = MC * 4 + (MC * 2 + 15) / 16 * 16;
+    typename G::Warp& w = warp_ws<G>(smem, EXTRA);
+    float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
+    int16_t* acts = reinterpret_cast<int16_t*>(raw + MC);
     const size_t base = (size_t)t * tp.cap;
-    float* raw = sm + wib * A;
     float v = wb.leaf_value[t];
     const int leaf = wb.leaf_node[t];
 
@@ -185,39 +181,24 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         const int slot = wb.eval_slot[t];
         const float* pol = wb.policy + (size_t)slot * A;
         v = wb.value[slot];
-        const State s = leaf_state[t];
+        G::w_load(w, leaf_state + t, lane);
         const uint8_t tf = tp.tflags[t];
         const bool first_fill = (tf & TF_FIRST_FILL) && leaf == tp.root[t];
         const int alloc = tp.alloc[t];
-        // legal moves in the reference's order (QUIRK G2): std::unordered_set iteration order = strictly
-        // descending action index, except the very first enumeration of a lineage (host-computed table).
-        int n = first_fill ? root_order_n[t] : (A - G::stones(s));
+        // children = the legal moves in the reference's order, priors = policy[action] (0 for out-of-range actions, i.e.
+        // Go's pass at -1), expandNodeWithPolicy parallel_mcts.cpp:690-711
+        const int n = G::w_enumerate(w, lane, first_fill ? root_order + (size_t)t * MC : nullptr, first_fill ? root_order_n[t] : 0, acts, raw, pol);
         if (alloc + n > tp.cap) {
             if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         } else if (n > 0) {
-            int16_t* act = tp.act + base + alloc;
-            if (first_fill) {
-                const int16_t* ord = root_order + (size_t)t * A;
-                for (int i = lane; i < n; i += 32) { const int a = ord[i]; act[i] = (int16_t)a; raw[i] = pol[a]; }
-            } else {
-                int cnt = 0;
-                for (int k = 0; k < A; k += 32) {
-                    const int a = A - 1 - (k + lane);
-                    const bool empty = a >= 0 && !G::occupied(s, a);
-                    const unsigned m = __ballot_sync(0xffffffffu, empty);
-                    if (empty) { const int i = cnt + __popc(m & ((1u << lane) - 1)); act[i] = (int16_t)a; raw[i] = pol[a]; }
-                    cnt += __popc(m);
-                }
-            }
-            __syncwarp();
             // policySum accumulated in child order (parallel_mcts.cpp:705-711) — serial on purpose
             float sum = 0.0f;
-            if (lane == 0) for (int i = 0; i < n; ++i) sum = fadd(sum, raw[i]);
+            if (lane == 0) for (int i = 0; i < n; ++i) if (acts[i] >= 0 && acts[i] < A) sum = fadd(sum, raw[i]);
             sum = __shfl_sync(0xffffffffu, sum, 0);
             const float uniform = fdiv(1.0f, (float)n);
             for (int i = lane; i < n; i += 32) {
                 const size_t c = base + alloc + i;
-                tp.N[c] = 0; tp.W[c] = 0.0f; tp.first[c] = -1; tp.nchild[c] = 0; tp.flags[c] = 0;
+                tp.N[c] = 0; tp.W[c] = 0.0f; tp.first[c] = -1; tp.nchild[c] = 0; tp.flags[c] = 0; tp.act[c] = acts[i];
                 tp.P[c] = sum > 0.0f ? fdiv(raw[i], sum) : uniform;     // :714-724
             }
             if (lane == 0) {
@@ -241,11 +222,11 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         float cv = v;
         for (int j = plen - 1; j >= 0; --j) {
             const size_t c = base + path[j];
-            float w = tp.W[c];
-            if (j == 0) { w = fsub(w, vl); w = fsub(w, vl); w = fadd(w, vl); w = fadd(w, cv);
+            float wv = tp.W[c];
+            if (j == 0) { wv = fsub(wv, vl); wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv);
                           tp.N[c] += sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
-            else { w = fsub(w, vl); w = fadd(w, vl); w = fadd(w, cv); tp.N[c] += 1; }
-            tp.W[c] = w;
+            else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] += 1; }
+            tp.W[c] = wv;
             cv = -cv;
         }
         atomicAdd(&stats->simulations, 1ULL);

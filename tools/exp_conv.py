@@ -11,7 +11,7 @@ eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=slots, evaluator=E.EVAL_RES
                max_nodes_per_tree=2048, deterministic=1)
 eng.load_weights(N.export_weights(N.make_random_model(seed=0, blocks=1)))
 flop = 225 * 9 * 128 * 128 * 2 * slots
-for dbg in [0, 1, 2, 4, 8, 6, 12, 14, 15, 0]:
+for dbg in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 2, 8, 10, 0]):
     os.environ["AZ_CONV_DBG"] = str(dbg)
     ms = min(eng.conv_bench(slots, 20) for _ in range(3))
     print(f"dbg={dbg:2d}  {ms*1e3:8.1f} us  {flop/ms/1e9:8.1f} TFLOP/s", flush=True)
