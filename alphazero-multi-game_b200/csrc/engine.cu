@@ -22,6 +22,7 @@ void set_error(const std::string& s) { g_error = s; }
 }  // namespace az
 
 #include "gomoku.cuh"
+#include "go.cuh"
 #include "tree_kernels.cuh"
 #include "conv_trunk.cuh"
 #include "heads.cuh"
@@ -212,41 +213,48 @@ struct Net {
 };
 
 // ------------------------------------------------------------------------------------------------ rules replay
+// State API on the device (one warp per game): replay a move list, then report what the reference's IGameState would:
+// getLegalMoves (in order), isTerminal, getGameResult, getCurrentPlayer, getEnhancedTensorRepresentation.
 template <class G>
-__global__ void k_rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal,
-                               int32_t* n_legal, int32_t* terminal, int32_t* result, int32_t* player, float* planes) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal,
+                                                     int32_t* n_legal, int32_t* terminal, int32_t* result, int32_t* player, float* planes,
+                                                     uint64_t* hist_scratch /*[n_games][max_moves]*/) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (g >= n_games) return;
-    typename G::State s; G::init(s);
+    typename G::Warp& w = warp_ws<G>(smem);
+    G::w_init(w, lane);
+    G::w_attach_history(w, hist_scratch + (size_t)g * max_moves, lane);
     int bad = 0;
     for (int i = 0; i < n_moves[g]; ++i) {
-        const int a = moves[(size_t)g * max_moves + i];
-        if (a < 0 || a >= G::CELLS || G::occupied(s, a)) { bad = 1; break; }   // make_move throws (gomoku_state.cpp:681-689)
-        G::apply(s, a);
+        if (!G::w_apply(w, moves[(size_t)g * max_moves + i], lane, true)) { bad = 1; break; }   // makeMove throws
     }
-    const int res = G::result(s);
-    int n = 0;
-    for (int a = G::CELLS - 1; a >= 0; --a) if (!G::occupied(s, a)) legal[(size_t)g * G::CELLS + n++] = a;
-    n_legal[g] = bad ? -1 : n; terminal[g] = res != RES_ONGOING; result[g] = res; player[g] = s.player;
-    if (planes)
-        for (int c = 0; c < G::PLANES; ++c)
-            for (int x = 0; x < G::N; ++x)
-                for (int y = 0; y < G::N; ++y) planes[(((size_t)g * G::PLANES + c) * G::N + x) * G::N + y] = G::feature(s, c, x, y);
+    const int res = G::w_result(w, lane);
+    const int n = G::w_legal(w, lane, legal + (size_t)g * G::MAX_CHILDREN);
+    if (lane == 0) { n_legal[g] = bad ? -1 : n; terminal[g] = res != RES_ONGOING; result[g] = res; player[g] = G::w_player(w); }
+    if (planes) G::w_planes(w, lane, planes + (size_t)g * G::PLANES * G::CELLS);
 }
 
 // createGameState + fresh ParallelMCTS for every slot (self_play_manager.cpp:157-175)
 template <class G>
-__global__ void k_reset_all(TreePools tp, typename G::State* root_state, const int16_t* default_order, int n_order, int16_t* root_order,
-                            int32_t* root_order_n, int noise, int T) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_reset_all(TreePools tp, typename G::State* root_state, const int16_t* default_order, int n_order, int16_t* root_order,
+                                                  int32_t* root_order_n, int noise, int T) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    typename G::Warp& w = warp_ws<G>(smem);
     const size_t base = (size_t)t * tp.cap;
-    typename G::State s; G::init(s); root_state[t] = s;
-    tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
-    tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] = 0;
-    tp.tflags[t] = (uint8_t)(TF_ACTIVE | TF_FIRST_FILL | (noise ? TF_NEED_NOISE : 0));
-    root_order_n[t] = n_order;
-    for (int i = 0; i < n_order; ++i) root_order[(size_t)t * G::CELLS + i] = default_order[i];
+    G::w_init(w, lane);
+    G::w_store_root(w, root_state + t, lane);
+    if (lane == 0) {
+        tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
+        tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] = 0;
+        tp.tflags[t] = (uint8_t)(TF_ACTIVE | (G::FIRST_FILL ? TF_FIRST_FILL : 0) | (noise ? TF_NEED_NOISE : 0));
+        root_order_n[t] = n_order;
+    }
+    for (int i = lane; i < n_order; i += 32) root_order[(size_t)t * G::MAX_CHILDREN + i] = default_order[i];
 }
 
 // ------------------------------------------------------------------------------------------------ engine
@@ -278,8 +286,10 @@ struct EngineBase {
 template <class G>
 struct EngineT : EngineBase {
     using State = typename G::State;
+    using Leaf = typename G::Leaf;
     using SampleT = Sample<G>;
-    static constexpr int A = G::CELLS;
+    static constexpr int A = G::ACTIONS;          // policy length
+    static constexpr int MC = G::MAX_CHILDREN;
     // Slots are split into `NG` stream groups; each group runs its own wave sequence (select → network → expand) on
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
@@ -292,7 +302,7 @@ struct EngineT : EngineBase {
     TreePools tp{};
     ScratchPools sc{};
     int scratch_trees = 0;
-    State *root_state = nullptr, *leaf_state = nullptr;
+    State* root_state = nullptr; Leaf* leaf_state = nullptr;
     int16_t *root_order = nullptr, *default_order = nullptr; int32_t* root_order_n = nullptr;
     int32_t *chosen_child = nullptr, *chosen_action = nullptr, *forced = nullptr;
     SampleT *game_buf = nullptr, *ring = nullptr; int32_t* ring_count = nullptr; int ring_cap = 0; int max_moves = 0;
@@ -341,9 +351,9 @@ struct EngineT : EngineBase {
         const size_t sn = (size_t)scratch_trees * cap;
         if (dev_alloc(&sc.N, sn) || dev_alloc(&sc.W, sn) || dev_alloc(&sc.P, sn) || dev_alloc(&sc.first, sn) || dev_alloc(&sc.act, sn) ||
             dev_alloc(&sc.nchild, sn) || dev_alloc(&sc.flags, sn) || dev_alloc(&sc.old_id, sn)) return -1;
-        if (dev_alloc(&root_state, T) || dev_alloc(&leaf_state, T) || dev_alloc(&root_order, (size_t)T * A) || dev_alloc(&default_order, A) ||
+        if (dev_alloc(&root_state, T) || dev_alloc(&leaf_state, T) || dev_alloc(&root_order, (size_t)T * MC) || dev_alloc(&default_order, MC) ||
             dev_alloc(&root_order_n, T) || dev_alloc(&chosen_child, T) || dev_alloc(&chosen_action, T) || dev_alloc(&forced, T)) return -1;
-        max_moves = A;
+        max_moves = G::MAX_GAME_MOVES;
         ring_cap = c.sample_ring_capacity > 0 ? c.sample_ring_capacity : std::max(4 * T, 4096);
         if (dev_alloc(&game_buf, (size_t)T * max_moves) || dev_alloc(&ring, (size_t)ring_cap) || dev_alloc(&ring_count, 1)) return -1;
         AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
@@ -352,10 +362,10 @@ struct EngineT : EngineBase {
         // QUIRK G2: legal-move order of the first-ever enumeration of a fresh state = iteration order of a
         // libstdc++ std::unordered_set<int> filled with 0..A-1 ascending (include/alphazero/games/gomoku/
         // gomoku_state.h:124, gomoku_state.cpp:531-566).  Computed with the real container, uploaded once.
-        {
-            std::unordered_set<int> us; for (int a = 0; a < A; ++a) us.insert(a);
+        if (G::FIRST_FILL) {
+            std::unordered_set<int> us; for (int a = 0; a < G::CELLS; ++a) us.insert(a);
             h_default_order.assign(us.begin(), us.end());
-            AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), A * 2, cudaMemcpyHostToDevice));
+            AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), h_default_order.size() * 2, cudaMemcpyHostToDevice));
         }
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
@@ -411,7 +421,7 @@ struct EngineT : EngineBase {
 
     int write_fresh(int slot, const State& s, const int16_t* order, int n_order, bool first_fill) {
         const size_t base = (size_t)slot * tp.cap;
-        const int res = G::result(s);
+        const int res = G::host_root_result(s);
         int32_t zero = 0, one = 1, m1 = -1; float fz = 0.0f; int16_t a16 = -1, z16 = 0;
         uint8_t nf = res != RES_ONGOING ? (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)) : 0;
         uint8_t tf = TF_ACTIVE | (first_fill ? TF_FIRST_FILL : 0) | (res != RES_ONGOING ? TF_GAME_OVER : 0) | (cfg.deterministic ? 0 : TF_NEED_NOISE);
@@ -430,14 +440,15 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.move_num + slot, &zero, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.game_id + slot, &gid, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_state + slot, &s, sizeof(State), cudaMemcpyHostToDevice, stream));
-        if (order && n_order > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(root_order + (size_t)slot * A, order, (size_t)n_order * 2, cudaMemcpyHostToDevice, stream));
+        if (order && n_order > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(root_order + (size_t)slot * MC, order, (size_t)n_order * 2, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_order_n + slot, &n_order, 4, cudaMemcpyHostToDevice, stream));
         if (sync_all()) return -1;   // host temporaries above go out of scope
         return 0;
     }
 
     int reset_games() override {
-        k_reset_all<G><<<(T + 127) / 128, 128, 0, stream>>>(tp, root_state, default_order, A, root_order, root_order_n, cfg.deterministic ? 0 : 1, T);
+        k_reset_all<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, default_order, G::FIRST_FILL ? G::CELLS : 0, root_order, root_order_n,
+                                                                                 cfg.deterministic ? 0 : 1, T);
         AZ_LAUNCH_CHECK(); ++launches;
         AZ_CUDA_CHECK(cudaMemsetAsync(ring_count, 0, 4, stream));
         if (sync_all()) return -1;
@@ -446,11 +457,9 @@ struct EngineT : EngineBase {
 
     int set_root(int slot, const int32_t* moves, int n, const int32_t* order, int n_order) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
-        State s; G::init(s);
-        for (int i = 0; i < n; ++i) {
-            AZ_CHECK(moves[i] >= 0 && moves[i] < A && !G::occupied(s, moves[i]), "illegal move in az_engine_set_root");   // IllegalMove (gomoku_state.cpp:681-689)
-            G::apply(s, moves[i]);
-        }
+        std::unique_ptr<State> sp(new State()); State& s = *sp; G::init(s);
+        for (int i = 0; i < n; ++i) AZ_CHECK(G::host_apply(s, moves[i]), "illegal move in az_engine_set_root");   // IllegalMove (igamestate.h:36-52)
+        AZ_CHECK(!order || G::FIRST_FILL, "a root child order can only be given for Gomoku (QUIRK G2)");
         std::vector<int16_t> ord;
         if (order) { ord.resize(n_order); for (int i = 0; i < n_order; ++i) ord[i] = (int16_t)order[i]; }
         return write_fresh(slot, s, order ? ord.data() : nullptr, order ? n_order : 0, order != nullptr);
@@ -465,13 +474,12 @@ struct EngineT : EngineBase {
         k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
         if (cfg.evaluator == AZ_EVAL_HASH) {
-            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(A * 4), st>>>(leaf_state + g.t0, g.wb, g.n);
+            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(A * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
         }
-        constexpr int MC = G::MAX_CHILDREN;
-        k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
+        k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, root_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
                                                                                     root_order_n + g.t0, sparams(), g.n, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
         return 0;
@@ -496,14 +504,14 @@ struct EngineT : EngineBase {
 
     int commit_moves(const int32_t* forced_dev) {
         MoveParams mp{cfg.deterministic, cfg.init_temperature, cfg.final_temperature, cfg.temperature_drop_move, cfg.seed};
-        k_choose_move<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, mp, game_buf, max_moves, forced_dev, chosen_child, chosen_action, T, dstats);
+        k_choose_move<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, mp, game_buf, max_moves, forced_dev, chosen_child, chosen_action, T, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
         for (int t0 = 0; t0 < T; t0 += scratch_trees) {
             const int cnt = std::min(scratch_trees, T - t0);
-            k_reroot<G><<<blocks_for_warps(cnt), 128, 0, stream>>>(tp, sc, root_state, chosen_child, t0, cnt, T);
+            k_reroot<G><<<blocks_for_warps(cnt), 128, warp_ws_bytes<G>(), stream>>>(tp, sc, root_state, chosen_child, t0, cnt, T);
             AZ_LAUNCH_CHECK(); ++launches;
         }
-        k_finish_games<G><<<blocks_for_warps(T), 128, 0, stream>>>(tp, root_state, game_buf, max_moves, ring, ring_cap, ring_count, default_order, A,
+        k_finish_games<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, game_buf, max_moves, ring, ring_cap, ring_count, default_order, G::FIRST_FILL ? G::CELLS : 0,
                                                                    root_order, root_order_n, cfg.auto_restart, cfg.deterministic ? 0 : 1, T, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
         return 0;
@@ -546,10 +554,11 @@ struct EngineT : EngineBase {
     int slot_state(int slot, int32_t* result, int32_t* ply, int32_t* player) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
         if (sync_all()) return -1;
-        State s; AZ_CUDA_CHECK(cudaMemcpy(&s, root_state + slot, sizeof(State), cudaMemcpyDeviceToHost));
-        if (result) *result = G::result(s);
-        if (ply) *ply = s.ply;
-        if (player) *player = s.player;
+        std::unique_ptr<State> sp(new State());
+        AZ_CUDA_CHECK(cudaMemcpy(sp.get(), root_state + slot, sizeof(State), cudaMemcpyDeviceToHost));
+        if (result) *result = G::host_root_result(*sp);
+        if (ply) *ply = G::host_ply(*sp);
+        if (player) *player = G::host_player(*sp);
         return 0;
     }
 
@@ -583,7 +592,7 @@ struct EngineT : EngineBase {
         o->off_game_id = (int)(size_t)&z->game_id; o->off_slot = (int)(size_t)&z->slot; o->off_ply = (int)(size_t)&z->ply;
         o->off_action = (int)(size_t)&z->action; o->off_player = (int)(size_t)&z->player; o->off_z = (int)(size_t)&z->z;
         o->off_result = (int)(size_t)&z->result; o->off_root_value = (int)(size_t)&z->root_value; o->off_root_visits = (int)(size_t)&z->root_visits;
-        o->off_state = (int)(size_t)&z->state; o->state_bytes = sizeof(State); o->off_visits = (int)(size_t)&z->visits[0];
+        o->off_state = (int)(size_t)&z->state; o->state_bytes = sizeof(typename G::Snapshot); o->off_visits = (int)(size_t)&z->visits[0];
         o->n_visits = (int)(sizeof(z->visits) / 2);
         return 0;
     }
@@ -616,10 +625,10 @@ struct EngineT : EngineBase {
         Net& net = g.net;
         AZ_CHECK(net.loaded, "no network weights loaded (az_engine_load_weights)");
         const int cap = net.max_boards;
-        float* dpl; if (dev_alloc(&dpl, (size_t)cap * net.in_planes * A)) return -1;
+        float* dpl; if (dev_alloc(&dpl, (size_t)cap * net.in_planes * G::CELLS)) return -1;
         for (int o = 0; o < n; o += cap) {               // group 0's buffers, `cap` boards at a time
             const int c = std::min(cap, n - o);
-            AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes + (size_t)o * net.in_planes * A, (size_t)c * net.in_planes * A * 4, cudaMemcpyHostToDevice, g.stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes + (size_t)o * net.in_planes * G::CELLS, (size_t)c * net.in_planes * G::CELLS * 4, cudaMemcpyHostToDevice, g.stream));
             AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, g.stream) == 0, "pack launch failed");
             ++launches;
             if (net.forward(nullptr, c, g.wb.policy, g.wb.value, g.stream)) { cudaFree(dpl); return -1; }
@@ -707,22 +716,23 @@ struct EngineT : EngineBase {
 
     int rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_mv, int32_t* legal, int32_t* n_legal,
                      int32_t* terminal, int32_t* result, int32_t* player, float* planes) override {
-        int32_t *dm, *dn, *dl, *dnl, *dt, *dr, *dp; float* dpl = nullptr;
-        if (dev_alloc(&dm, (size_t)n_games * max_mv) || dev_alloc(&dn, n_games) || dev_alloc(&dl, (size_t)n_games * A) || dev_alloc(&dnl, n_games) ||
+        int32_t *dm, *dn, *dl, *dnl, *dt, *dr, *dp; float* dpl = nullptr; uint64_t* dh;
+        if (dev_alloc(&dh, (size_t)n_games * max_mv)) return -1;
+        if (dev_alloc(&dm, (size_t)n_games * max_mv) || dev_alloc(&dn, n_games) || dev_alloc(&dl, (size_t)n_games * MC) || dev_alloc(&dnl, n_games) ||
             dev_alloc(&dt, n_games) || dev_alloc(&dr, n_games) || dev_alloc(&dp, n_games)) return -1;
-        if (planes && dev_alloc(&dpl, (size_t)n_games * G::PLANES * A)) return -1;
+        if (planes && dev_alloc(&dpl, (size_t)n_games * G::PLANES * G::CELLS)) return -1;
         AZ_CUDA_CHECK(cudaMemcpy(dm, moves, (size_t)n_games * max_mv * 4, cudaMemcpyHostToDevice));
         AZ_CUDA_CHECK(cudaMemcpy(dn, n_moves, (size_t)n_games * 4, cudaMemcpyHostToDevice));
-        k_rules_replay<G><<<(n_games + 63) / 64, 64, 0, stream>>>(dm, dn, n_games, max_mv, dl, dnl, dt, dr, dp, dpl);
+        k_rules_replay<G><<<blocks_for_warps(n_games), 128, warp_ws_bytes<G>(), stream>>>(dm, dn, n_games, max_mv, dl, dnl, dt, dr, dp, dpl, dh);
         AZ_LAUNCH_CHECK(); ++launches;
         AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
-        AZ_CUDA_CHECK(cudaMemcpy(legal, dl, (size_t)n_games * A * 4, cudaMemcpyDeviceToHost));
+        AZ_CUDA_CHECK(cudaMemcpy(legal, dl, (size_t)n_games * MC * 4, cudaMemcpyDeviceToHost));
         AZ_CUDA_CHECK(cudaMemcpy(n_legal, dnl, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
         AZ_CUDA_CHECK(cudaMemcpy(terminal, dt, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
         AZ_CUDA_CHECK(cudaMemcpy(result, dr, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
         AZ_CUDA_CHECK(cudaMemcpy(player, dp, (size_t)n_games * 4, cudaMemcpyDeviceToHost));
-        if (planes) AZ_CUDA_CHECK(cudaMemcpy(planes, dpl, (size_t)n_games * G::PLANES * A * 4, cudaMemcpyDeviceToHost));
-        for (void* p : {(void*)dm, (void*)dn, (void*)dl, (void*)dnl, (void*)dt, (void*)dr, (void*)dp, (void*)dpl}) cudaFree(p);
+        if (planes) AZ_CUDA_CHECK(cudaMemcpy(planes, dpl, (size_t)n_games * G::PLANES * G::CELLS * 4, cudaMemcpyDeviceToHost));
+        for (void* p : {(void*)dm, (void*)dn, (void*)dl, (void*)dnl, (void*)dt, (void*)dr, (void*)dp, (void*)dpl, (void*)dh}) cudaFree(p);
         return 0;
     }
 };
@@ -753,7 +763,10 @@ AZ_API int az_engine_create(const az_config* cfg, az_engine** out) {
     int rc = -1;
     if (cfg->game == AZ_GAME_GOMOKU && cfg->board_size == 15) { auto* e = new az::EngineT<az::Gomoku<15>>(); impl.reset(e); rc = e->init(*cfg); }
     else if (cfg->game == AZ_GAME_GOMOKU && cfg->board_size == 9) { auto* e = new az::EngineT<az::Gomoku<9>>(); impl.reset(e); rc = e->init(*cfg); }
-    else { az::set_error("unsupported game / board size (built: Gomoku 15x15, 9x9)"); return -3; }
+    else if (cfg->game == AZ_GAME_GO && cfg->board_size == 9) { auto* e = new az::EngineT<az::Go<9>>(); impl.reset(e); rc = e->init(*cfg); }
+    else if (cfg->game == AZ_GAME_GO && cfg->board_size == 13) { auto* e = new az::EngineT<az::Go<13>>(); impl.reset(e); rc = e->init(*cfg); }
+    else if (cfg->game == AZ_GAME_GO && cfg->board_size == 19) { auto* e = new az::EngineT<az::Go<19>>(); impl.reset(e); rc = e->init(*cfg); }
+    else { az::set_error("unsupported game / board size (built: Gomoku 15x15, 9x9; Go 9x9, 13x13, 19x19)"); return -3; }
     if (rc != 0) return rc;
     *out = new az_engine{std::move(impl)};
     return 0;

@@ -23,6 +23,10 @@ struct Gomoku {
     static constexpr int NW = (PBITS + 63) / 64;   // words per colour
     static constexpr int PLANES = 11;              // getEnhancedTensorRepresentation (QUIRK G5)
     static constexpr int PACKED_NW = (CELLS + 63) / 64;
+    static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
+    static constexpr int MAX_CHILDREN = CELLS;
+    static constexpr bool FIRST_FILL = true;       // QUIRK G2: the first enumeration of a lineage has its own order
+    static constexpr int MAX_GAME_MOVES = CELLS;
 
     struct BB { uint64_t w[NW]; };
 
@@ -33,6 +37,9 @@ struct Gomoku {
         int8_t player;         // 1 = BLACK to move, 2 = WHITE
         int8_t pad_;
     };
+
+    using Leaf = State;
+    using Snapshot = State;
 
     AZ_HD static int a2p(int a) { return (a / N) * PITCH + (a % N); }
     AZ_HD static int p2a(int p) { return (p / PITCH) * N + (p % PITCH); }
@@ -170,12 +177,16 @@ struct Gomoku {
         }
     }
 
+    // host-side helpers used by az_engine_set_root / slot_state (single thread)
+    static bool host_apply(State& s, int a) { if (a < 0 || a >= CELLS || occupied(s, a)) return false; apply(s, a); return true; }   // IllegalMove, gomoku_state.cpp:681-689
+    static int host_root_result(const State& s) { return result(s); }
+    static int host_ply(const State& s) { return s.ply; }
+    static int host_player(const State& s) { return s.player; }
+
 #if defined(__CUDACC__)
     // ---------------------------------------------------------------------------------------------
     // Warp API used by the tree kernels (tree_kernels.cuh): the game state of the tree a warp owns lives in that
     // warp's shared-memory workspace; mutating calls are made by the whole warp (lane 0 writes, __syncwarp after).
-    static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
-    static constexpr int MAX_CHILDREN = CELLS;
     struct Warp { State s; };
     struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch; };
 
@@ -191,9 +202,17 @@ struct Gomoku {
         uint32_t* dst = reinterpret_cast<uint32_t*>(g);
         for (int i = lane; i < (int)(sizeof(State) / 4); i += 32) dst[i] = src[i];
     }
+    // root / leaf states are the same 88-byte record for Gomoku (Go keeps its superko history out of the leaf, go.cuh)
+    __device__ static void w_load_root(Warp& w, const State* g, int lane) { w_load(w, g, lane); }
+    __device__ static void w_store_root(Warp& w, State* g, int lane) { w_store(w, g, lane); }
+    __device__ static void w_store_leaf(Warp& w, Leaf* g, int lane) { w_store(w, g, lane); }
+    __device__ static void w_load_leaf(Warp& w, const Leaf* g, const State*, int lane) { w_load(w, g, lane); }
+    __device__ static void w_snapshot(const Warp& w, Snapshot* out, int lane) { w_store(w, out, lane); }
+    __device__ static int w_root_result(Warp& w, int) { return result(w.s); }
     __device__ static void w_init(Warp& w, int lane) { if (lane == 0) init(w.s); __syncwarp(); }
+    __device__ static void w_attach_history(Warp&, uint64_t*, int) {}
     // returns false if the reference's makeMove would throw (gomoku_state.cpp:681-689)
-    __device__ static bool w_apply(Warp& w, int a, int lane) {
+    __device__ static bool w_apply(Warp& w, int a, int lane, bool = false) {
         const bool ok = a >= 0 && a < CELLS && !occupied(w.s, a);
         __syncwarp();
         if (ok && lane == 0) apply(w.s, a);

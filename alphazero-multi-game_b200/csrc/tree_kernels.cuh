@@ -30,7 +30,7 @@ constexpr size_t warp_ws_bytes(int extra_bytes_per_warp = 0) { return 4 * ((size
 // mode 0: one simulation; mode 1: root-expansion wave (search() preamble, parallel_mcts.cpp:153-174).
 template <class G>
 __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
-                                               typename G::State* __restrict__ leaf_state, WaveBuffers wb,
+                                               typename G::Leaf* __restrict__ leaf_state, WaveBuffers wb,
                                                SearchParams sp, typename G::EncTarget enc, int T, int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -49,9 +49,9 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
         const int rf = tp.first[base + node];
         const bool rterm = tp.flags[base + node] & NF_TERMINAL;
         if (mode == 1) {
-            if (rf < 0 && !rterm) { kind = LEAF_EVAL; G::w_load(w, root_state + t, lane); }   // root needs its first evaluation
+            if (rf < 0 && !rterm) { kind = LEAF_EVAL; G::w_load_root(w, root_state + t, lane); }   // root needs its first evaluation
         } else if (rf >= 0 && !rterm) {
-            G::w_load(w, root_state + t, lane);
+            G::w_load_root(w, root_state + t, lane);
             // --- selectLeafWithPath (parallel_mcts.cpp:456-535).  The root carries one fresh virtual
             // loss while its children are scored (:461), so parentVisits = N_root + virtualLoss (:539).
             int* path = wb.path + (size_t)t * MAX_DEPTH;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
         wb.leaf_value[t] = tvalue; wb.eval_slot[t] = slot;
     }
     if (kind == LEAF_EVAL) {
-        G::w_store(w, leaf_state + t, lane);
+        G::w_store_leaf(w, leaf_state + t, lane);
         if (enc.ptr != nullptr) G::w_encode(w, lane, enc, slot);
     }
 }
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
 // against the reference's serial search.  One warp per leaf; the policy sum is accumulated in ascending
 // action order by one lane so it is the reference's fp32 sum bit for bit.
 template <class G>
-__global__ void __launch_bounds__(128) k_hash_eval(const typename G::State* __restrict__ leaf_state, WaveBuffers wb, int T) {
+__global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __restrict__ leaf_state, const typename G::State* __restrict__ root_state,
+                                                  WaveBuffers wb, int T) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::State* __re
     typename G::Warp& w = warp_ws<G>(smem, A * 4);
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     const int slot = wb.eval_slot[t];
-    G::w_load(w, leaf_state + t, lane);
+    G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
     const uint64_t h = G::w_key(w, lane);
     for (int i = lane; i < A; i += 32) {
         const uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::State* __re
 // ------------------------------------------------------------------------------------------------
 // Expansion (M5) + backup (M6/M7).
 template <class G>
-__global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typename G::State* __restrict__ leaf_state,
-                                                      WaveBuffers wb, const int16_t* __restrict__ root_order,
+__global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typename G::Leaf* __restrict__ leaf_state,
+                                                      const typename G::State* __restrict__ root_state, WaveBuffers wb, const int16_t* __restrict__ root_order,
                                                       const int32_t* __restrict__ root_order_n, SearchParams sp,
                                                       int T, Stats* stats) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         const int slot = wb.eval_slot[t];
         const float* pol = wb.policy + (size_t)slot * A;
         v = wb.value[slot];
-        G::w_load(w, leaf_state + t, lane);
+        G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
         const uint8_t tf = tp.tflags[t];
         const bool first_fill = (tf & TF_FIRST_FILL) && leaf == tp.root[t];
         const int alloc = tp.alloc[t];
@@ -312,8 +313,8 @@ struct alignas(16) Sample {
     uint32_t game_id; int32_t slot;
     int16_t ply, action; int8_t player, z, result, pad_;
     float root_value; int32_t root_visits;
-    typename G::State state;                       // position the move was chosen from
-    uint16_t visits[(G::CELLS + 7) / 8 * 8];      // root child visit counts by action
+    typename G::Snapshot state;                    // position the move was chosen from
+    uint16_t visits[(G::ACTIONS + 7) / 8 * 8];    // root child visit counts by action (G::visit_index: Go's pass is the last entry)
 };
 
 struct MoveParams {
@@ -330,9 +331,11 @@ __global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::S
                                                     Sample<G>* game_buf /*[T][max_moves]*/, int max_moves,
                                                     const int32_t* forced_action, int32_t* chosen_child,
                                                     int32_t* chosen_action, int T, Stats* stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    typename G::Warp& w = warp_ws<G>(smem);
     if (lane == 0) { chosen_child[t] = -2; chosen_action[t] = -2; }
     const uint8_t tf = tp.tflags[t];
     if (!(tf & TF_ACTIVE) || (tf & TF_GAME_OVER)) return;
@@ -380,29 +383,29 @@ __global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::S
         }
         action = tp.act[base + f + bi];
     }
+    G::w_load_root(w, root_state + t, lane);
     // --- record the sample
     const int mv = tp.move_num[t];
     if (game_buf && mv < max_moves) {
         Sample<G>* sp_ = game_buf + (size_t)t * max_moves + mv;
         for (int i = lane; i < (int)(sizeof(sp_->visits) / 2); i += 32) sp_->visits[i] = 0;
         __syncwarp();
-        for (int i = lane; i < nc; i += 32) {
-            const int a = tp.act[base + f + i];
-            if (a >= 0) sp_->visits[a] = (uint16_t)min(tp.N[base + f + i], 65535);
-        }
+        for (int i = lane; i < nc; i += 32) sp_->visits[G::visit_index(tp.act[base + f + i])] = (uint16_t)min(tp.N[base + f + i], 65535);
         if (lane == 0) {
             const int rn = tp.N[base + root];
-            sp_->game_id = tp.game_id[t]; sp_->slot = t; sp_->ply = root_state[t].ply; sp_->action = (int16_t)action;
-            sp_->player = root_state[t].player; sp_->z = 0; sp_->result = 0; sp_->pad_ = 0;
+            sp_->game_id = tp.game_id[t]; sp_->slot = t; sp_->ply = (int16_t)G::w_ply(w); sp_->action = (int16_t)action;
+            sp_->player = (int8_t)G::w_player(w); sp_->z = 0; sp_->result = 0; sp_->pad_ = 0;
             sp_->root_value = (nc == 0 || rn == 0) ? 0.0f : fdiv(tp.W[base + root], (float)rn);   // getRootValue (M15)
-            sp_->root_visits = rn; sp_->state = root_state[t];
+            sp_->root_visits = rn;
         }
+        G::w_snapshot(w, &sp_->state, lane);
     }
-    // --- advance the root state (updateWithMove, M14)
+    // --- advance the root state (updateWithMove, M14).  A forced action the rules reject leaves the slot untouched
+    // (the reference's makeMove throws): chosen_action = -3 tells the host.
+    const bool ok = G::w_apply(w, action, lane, forced_action != nullptr);
+    if (!ok) { if (lane == 0) chosen_action[t] = -3; return; }
+    G::w_store_root(w, root_state + t, lane);
     if (lane == 0) {
-        typename G::State s = root_state[t];
-        G::apply(s, action);
-        root_state[t] = s;
         chosen_child[t] = bi >= 0 ? f + bi : -1;
         chosen_action[t] = action;
         tp.move_num[t] = mv + 1;
@@ -418,15 +421,17 @@ struct ScratchPools { int32_t* N; float* W; float* P; int32_t* first; int16_t* a
 template <class G>
 __global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, const typename G::State* __restrict__ root_state,
                                                const int32_t* __restrict__ chosen_child, int t0, int tcount, int T) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= tcount) return;
-    const int t = t0 + w;
+    if (wi >= tcount) return;
+    const int t = t0 + wi;
     if (t >= T) return;
     const int cc = chosen_child[t];
     if (cc == -2) return;                                // slot did not move
+    typename G::Warp& w = warp_ws<G>(smem);
     const size_t base = (size_t)t * tp.cap;
-    const size_t sb = (size_t)w * tp.cap;
+    const size_t sb = (size_t)wi * tp.cap;
     int count = 1;
     if (cc < 0) {
         // child did not exist: fresh root (parallel_mcts.cpp:1097-1101)
@@ -463,9 +468,10 @@ __global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, c
             tp.act[base + i] = sc.act[sb + i]; tp.nchild[base + i] = sc.nchild[sb + i]; tp.flags[base + i] = sc.flags[sb + i];
         }
     }
+    // the new root's terminal status comes from the state, as in the root MCTSNode ctor (mcts_node.cpp:24-25)
+    G::w_load_root(w, root_state + t, lane);
+    const int res = G::w_root_result(w, lane);
     if (lane == 0) {
-        // the new root's terminal status comes from the state, as in the root MCTSNode ctor (mcts_node.cpp:24-25)
-        const int res = G::result(root_state[t]);
         uint8_t tf = tp.tflags[t];
         if (res != RES_ONGOING) { tp.flags[base] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)); tf |= TF_GAME_OVER; }
         tf &= ~TF_FIRST_FILL;
@@ -481,9 +487,11 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
                                                      Sample<G>* out, int out_cap, int* out_count, const int16_t* __restrict__ default_order,
                                                      int default_order_n, int16_t* root_order, int32_t* root_order_n,
                                                      int auto_restart, int noise_every_even_move, int T, Stats* stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    typename G::Warp& w = warp_ws<G>(smem);
     uint8_t tf = tp.tflags[t];
     if (!(tf & TF_ACTIVE)) return;
     if (!(tf & TF_GAME_OVER)) {
@@ -492,7 +500,8 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
         return;
     }
     const size_t base = (size_t)t * tp.cap;
-    const int res = G::result(root_state[t]);
+    G::w_load_root(w, root_state + t, lane);
+    const int res = G::w_root_result(w, lane);
     const int n = min(tp.move_num[t], max_moves);
     if (game_buf && out) {
         int dst = -1;
@@ -516,17 +525,17 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
             }
         } else if (lane == 0) atomicAdd(&stats->samples_dropped, (unsigned long long)n);
     }
+    if (auto_restart) { G::w_init(w, lane); G::w_store_root(w, root_state + t, lane); }
     if (lane == 0) {
         atomicAdd(&stats->games, 1ULL);
         if (auto_restart) {
-            typename G::State s; G::init(s); root_state[t] = s;
             tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
             tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] += 1;
-            tp.tflags[t] = TF_ACTIVE | TF_FIRST_FILL | (noise_every_even_move ? TF_NEED_NOISE : 0);
+            tp.tflags[t] = TF_ACTIVE | (G::FIRST_FILL ? TF_FIRST_FILL : 0) | (noise_every_even_move ? TF_NEED_NOISE : 0);
             root_order_n[t] = default_order_n;
         } else tp.tflags[t] = tf & ~TF_ACTIVE;   // keeps TF_GAME_OVER for the host to see
     }
-    if (auto_restart) for (int i = lane; i < default_order_n; i += 32) root_order[(size_t)t * G::CELLS + i] = default_order[i];
+    if (auto_restart) for (int i = lane; i < default_order_n; i += 32) root_order[(size_t)t * G::MAX_CHILDREN + i] = default_order[i];
 }
 
 }  // namespace az

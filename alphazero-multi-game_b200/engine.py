@@ -142,7 +142,12 @@ class Engine:
         self.h = h
         self.n_slots = self.cfg.n_slots
         self.board = self.cfg.board_size
-        self.actions = self.board * self.board
+        self.cells = self.board * self.board
+        # policy length / getActionSpaceSize: N*N for Gomoku, N*N + 1 for Go (go_state.cpp:345-347); a node has at most
+        # `max_children` children (Go: pass + every cell)
+        self.actions = self.cells + (1 if self.cfg.game == GO else 0)
+        self.max_children = self.actions
+        self.planes = 8 if self.cfg.game == GO else 11
 
     def _check(self, rc):
         if rc != 0:
@@ -272,7 +277,7 @@ class Engine:
         self._check(self.lib.az_engine_event_elapsed(self.h, i, j, C.byref(ms)))
         return ms.value
 
-    def rules_replay(self, games, want_planes=True, planes_c=11):
+    def rules_replay(self, games, want_planes=True, planes_c=None):
         """games: list of move lists.  Returns per game: legal (reference order for non-first fills), terminal,
         result, player, planes."""
         ng = len(games)
@@ -280,7 +285,8 @@ class Engine:
         mv = np.zeros((ng, mx), np.int32); nm = np.zeros(ng, np.int32)
         for i, g in enumerate(games):
             mv[i, :len(g)] = g; nm[i] = len(g)
-        A = self.actions
+        A = self.max_children
+        planes_c = planes_c or self.planes
         legal = np.zeros((ng, A), np.int32); nl = np.zeros(ng, np.int32)
         term = np.zeros(ng, np.int32); res = np.zeros(ng, np.int32); pl = np.zeros(ng, np.int32)
         planes = np.zeros((ng, planes_c, self.board, self.board), np.float32) if want_planes else None

@@ -1,0 +1,195 @@
+"""GPU parity tests for Go (BASELINE.json configs[2]): device rules (capture, ko, positional
+superko, suicide, area score, legal-move order with pass first, 8-plane encoder) and the batched search, called through the
+C ABI, against the oracle (CPU restatement pinned to the patched reference) and the golden fixtures generated from the
+reference itself.  Bar: legal moves, terminal flags, results, planes and per-root visit counts bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _orc
+from _orc import GO
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def go_engine(n_slots, board=9, sims=400, **kw):
+    from _eng import E
+    cfg = dict(game=E.GO, board_size=board, n_slots=n_slots, num_simulations=sims, evaluator=E.EVAL_HASH, deterministic=1,
+               auto_restart=0, max_nodes_per_tree=2 * (sims + 1) * (board * board + 1) + 1, n_streams=2)
+    cfg.update(kw)
+    return E.Engine(**cfg)
+
+
+@pytest.mark.parametrize("board", [9, 19])
+def test_go_rules_kernels_match_golden_and_oracle(board):
+    """Every prefix of the golden playouts (generated from the patched reference: captures, ko, superko, passes):
+    getLegalMoves in order, isTerminal, getGameResult, getCurrentPlayer, the 8 feature planes."""
+    O = _orc.oracle()
+    eng = go_engine(2, board=board, sims=4)
+    games, expect = [], []
+    for case in json.load(open(os.path.join(GOLD, "state_playouts.json"))):
+        if case["game"] != GO or case["board"] != board:
+            continue
+        s = O.new_state(GO, board)
+        step = 1 if board == 9 else 3
+        for ply in range(len(case["moves"]) + 1):
+            if ply % step == 0 or ply == len(case["moves"]):
+                games.append(case["moves"][:ply])
+                expect.append((O.legal(s), O.state_is_terminal(s), O.state_result(s), O.state_current_player(s), O.tensor(s)))
+            if ply < len(case["moves"]):
+                assert O.state_make_move(s, case["moves"][ply]) == 0
+    assert len(games) > 80
+    r = eng.rules_replay(games)
+    for i, (legal, term, res, pl, planes) in enumerate(expect):
+        assert r["n_legal"][i] >= 0, (board, i)
+        assert np.array_equal(r["legal"][i], legal), (board, i, len(games[i]))
+        assert r["terminal"][i] == term and r["result"][i] == res and r["player"][i] == pl, (board, i)
+        assert np.array_equal(r["planes"][i], planes), (board, i)
+    eng.close()
+
+
+def test_go_rules_edge_cases():
+    """Occupied cell, suicide, simple ko and out-of-range moves are rejected like the reference's makeMove (it throws);
+    two passes end the game and the empty board scores for White (komi 7.5)."""
+    O = _orc.oracle()
+    eng = go_engine(2, board=9, sims=4)
+    # a ko: black 1,9+? build the classic shape around (x=1,y=1)
+    #   . B W .        black: (1,0) (0,1) (1,2)   white: (2,0) (3,1) (2,2), then white plays (1,1)?? no:
+    # black stones at 1, 9, 19; white stones at 2, 12, 20; black plays 11 (x=2,y=1); white captures at 10 (x=1,y=1)
+    ko = [1, 2, 9, 12, 19, 20, 11, 10]
+    cases = [[0, 0], [81], [-2], ko + [11], ko, [-1, -1], [-1, -1, 5]]
+    r = eng.rules_replay(cases)
+    exp_bad = []
+    for c in cases:
+        s = O.new_state(GO, 9)
+        bad = False
+        for a in c:
+            if O.state_make_move(s, a) != 0:
+                bad = True
+                break
+        exp_bad.append(bad)
+        if not bad:
+            i = len(exp_bad) - 1
+            assert np.array_equal(r["legal"][i], O.legal(s)), c
+            assert r["terminal"][i] == O.state_is_terminal(s) and r["result"][i] == O.state_result(s), c
+    assert [int(n) == -1 for n in r["n_legal"]] == exp_bad
+    assert exp_bad[3] is True and exp_bad[4] is False          # immediate ko recapture is illegal, the ko itself is fine
+    assert r["terminal"][5] == 1 and r["result"][5] == _orc.WIN_P2
+    # suicide: white fills its own last liberty in the corner surrounded by black
+    su = [1, 40, 9, 0]
+    s = O.new_state(GO, 9)
+    ok = [O.state_make_move(s, a) for a in su]
+    rr = eng.rules_replay([su])
+    assert (rr["n_legal"][0] == -1) == (ok[-1] != 0)
+    eng.close()
+
+
+def test_go_search_matches_reference_golden():
+    """Serial-search parity on the golden case generated from the patched reference (Go 9x9 @400 sims):
+    child order (pass first), visit counts, valueSum and prior bits, root leak, chosen move."""
+    cases = [c for c in json.load(open(os.path.join(GOLD, "search_hash_eval.json"))) if c["game"] == GO]
+    assert cases
+    case = cases[0]
+    eng = go_engine(3, board=case["board"], sims=case["sims"])
+    for mv, g in enumerate(case["moves"]):
+        eng.search()
+        for slot in range(3):
+            st = eng.root_stats(slot)
+            assert st["actions"].tolist() == g["actions"], (mv, slot)
+            assert st["N"].tolist() == g["N"], (mv, slot)
+            assert bits(st["W"]).tolist() == g["W"], (mv, slot)
+            assert bits(st["P"]).tolist() == g["P"], (mv, slot)
+            assert st["rootN"] == g["rootN"] and int(bits([st["rootW"]])[0]) == g["rootW"]
+        eng.advance([g["action"]] * 3)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
+
+
+def test_go_search_matches_oracle_random_positions():
+    """A different mid-game position (random legal playouts with captures) in every slot, searched together wave by wave,
+    each compared with the oracle's serial search for several consecutive moves (subtree reuse included)."""
+    O = _orc.oracle()
+    rng = np.random.default_rng(5)
+    T, sims, board = 10, 200, 9
+    eng = go_engine(T, board=board, sims=sims)
+    searches = []
+    for t in range(T):
+        s = O.new_state(GO, board)
+        moves = []
+        for _ in range(int(rng.integers(0, 70))):
+            lg = O.legal(s)
+            cand = lg[lg >= 0] if (len(lg) > 1 and rng.random() < 0.97) else lg
+            a = int(rng.choice(cand))
+            assert O.state_make_move(s, a) == 0
+            moves.append(a)
+            if O.state_is_terminal(s):
+                break
+        if O.state_is_terminal(s):
+            s = O.new_state(GO, board); moves = []
+        eng.set_root(t, moves)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+    for mv in range(3):
+        eng.search()
+        acts = []
+        for t in range(T):
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            assert np.array_equal(a["actions"], b["actions"]), (mv, t)
+            assert np.array_equal(a["N"], b["N"]), (mv, t)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (mv, t)
+            assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0]
+            act = O.mcts_select_action(searches[t], 1, 1.0)
+            acts.append(act)
+            O.mcts_update_with_move(searches[t], act)
+        eng.advance(acts)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
+
+
+def test_go_selfplay_loop_matches_oracle():
+    """az_engine_play in deterministic mode against the oracle's playSingleGame restatement for the first 30 moves of a
+    9x9 game: same moves, same recorded visit counts (pass = last entry of the visit vector)."""
+    O = _orc.oracle()
+    board, sims = 9, 100
+    eng = go_engine(2, board=board, sims=sims)
+    s = O.new_state(GO, board)
+    m = O.mcts_new(s, sims, 1.5, 3, 0, None, None)
+    for i in range(30):
+        if O.state_is_terminal(s):
+            break
+        O.mcts_search(m)
+        a = O.mcts_select_action(m, 1, 1.0)
+        O.state_make_move(s, a); O.mcts_update_with_move(m, a)
+        eng.play(1)
+        assert eng.last_actions().tolist() == [a, a], i
+        r, ply, pl = eng.slot_state(0)
+        assert ply == i + 1 and pl == O.state_current_player(s) and r == O.state_result(s)
+    eng.close()
+
+
+def test_go_selfplay_auto_restart_and_noise_smoke():
+    """Throughput-mode loop on Go 9x9 (Dirichlet noise, temperature sampling, auto-restart, move cap): invariants only."""
+    board, sims, T = 9, 32, 64
+    eng = go_engine(T, board=board, sims=sims, deterministic=0, auto_restart=1, seed=3)
+    total = 0
+    for _ in range(60):
+        eng.play(3)
+        smp = eng.drain_samples()
+        total += len(smp)
+        if len(smp):
+            assert np.all(smp["visits"].sum(1) >= sims - 1)
+            assert np.all(np.abs(smp["z"]) <= 1) and np.all(smp["result"] >= 1)
+            idx = np.where(smp["action"] < 0, board * board, smp["action"])
+            assert np.all(smp["visits"][np.arange(len(smp)), idx] >= 1)
+            assert np.all(smp["ply"] < 2 * board * board)
+    st = eng.stats()
+    assert st["games"] >= 1 and total >= 1 and st["pool_overflows"] == 0 and st["samples_dropped"] == 0
+    assert st["moves"] == 180 * T
+    eng.close()
