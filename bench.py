@@ -153,8 +153,9 @@ def run_reference_arm(args, rank):
 
 
 def workload_config(args, world):
-    return {"workload": f"Gomoku 15x15 batched self-play, {args.slots} concurrent games per GPU, {args.sims} sims/move, "
-                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[1])",
+    name = "Go 9x9 (capture/ko/superko)" if args.game == "go9" else "Gomoku 15x15"
+    return {"workload": f"{name} batched self-play, {args.slots} concurrent games per GPU, {args.sims} sims/move, "
+                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[{2 if args.game == 'go9' else 1}])",
             "slots_per_gpu": args.slots, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s)",
             "step": "one self-play move on every slot (root expansion + sims waves + move commit)", "stream_groups": args.streams,
             "l2": "working set (node pools, 3 x 268 MB activations) >> 126 MB L2; no explicit flush"}
@@ -167,13 +168,22 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--slots", type=int, default=4096)
-    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--game", default="gomoku15", choices=["gomoku15", "go9"],
+                    help="gomoku15 = BASELINE.json configs[1] (the headline metric); go9 = configs[2] (Go 9x9, 2048 games, 400 sims) as an extra line")
+    ap.add_argument("--slots", type=int, default=None)
+    ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
     ap.add_argument("--ref-sims-per-step", type=int, default=200)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global BOARD, ACTIONS, PLANES, CONV_FLOP_PER_BOARD, NET_FLOP_PER_EVAL
+    if args.game == "go9":
+        BOARD, ACTIONS, PLANES = 9, 82, 8
+        CONV_FLOP_PER_BOARD = 81 * 9 * 128 * 128 * 2
+        NET_FLOP_PER_EVAL = 81 * 9 * 8 * 128 * 2 + 20 * CONV_FLOP_PER_BOARD + 2 * (64 * 128 * 32 * 2) + 2048 * 82 * 2 + 2048 * 256 * 2 + 512
+    args.slots = args.slots or (2048 if args.game == "go9" else 4096)
+    args.sims = args.sims or (400 if args.game == "go9" else 800)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
@@ -192,7 +202,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    eng = E.Engine(game=E.GOMOKU, board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
+    eng = E.Engine(game=E.GO if args.game == "go9" else E.GOMOKU, board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
                    net_blocks=BLOCKS, net_channels=CHANNELS, deterministic=0, auto_restart=1, device=local, seed=1234 + rank,
                    n_streams=args.streams)
     model = N.make_random_model(seed=0, in_planes=PLANES, board=BOARD, actions=ACTIONS, blocks=BLOCKS, channels=CHANNELS)
@@ -281,7 +291,7 @@ def main():
     conv_flop = CONV_FLOP_PER_BOARD * boards_per_launch
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     nn_ms = eng.nn_bench(args.slots, 5)
-    roofline = {"bound": "tensor", "kernel": f"k_conv3x3<128> (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)", "achieved": achieved,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16",
                 "traffic": None, "launch_ms": conv_ms, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": NET_FLOP_PER_EVAL * args.slots / (nn_ms / 1e3) / 1e12,
@@ -289,7 +299,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own serial search on the host cores --
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.game == "gomoku15":
         try:
             threads = os.cpu_count() or 1
             run, kind = reference_searcher(threads)

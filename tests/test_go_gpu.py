@@ -193,3 +193,33 @@ def test_go_selfplay_auto_restart_and_noise_smoke():
     assert st["games"] >= 1 and total >= 1 and st["pool_overflows"] == 0 and st["samples_dropped"] == 0
     assert st["moves"] == 180 * T
     eng.close()
+
+
+def test_go_selfplay_with_resnet_evaluator():
+    """Go 9x9 self-play with the tcgen05 ResNet evaluator in the loop (random-init 2-block net): the wave pipeline
+    (select -> 8-plane encode -> trunk + heads -> expand/backup) runs, every simulation is accounted for, root visit
+    counts add up, and the evaluator's policy for the root position matches the fp32 network."""
+    import torch
+    from _eng import E, N
+    O = _orc.oracle()
+    board, sims, T = 9, 24, 48
+    model = N.make_random_model(seed=4, blocks=2, in_planes=8, board=board, actions=board * board + 1)
+    with torch.no_grad():
+        model.p_fc.weight *= 0.2; model.v_fc1.weight *= 0.2
+    eng = E.Engine(game=E.GO, board_size=board, n_slots=T, evaluator=E.EVAL_RESNET, net_blocks=2, num_simulations=sims,
+                   deterministic=1, auto_restart=1)
+    eng.load_weights(N.export_weights(model))
+    eng.search()
+    st = eng.root_stats(5)
+    assert st["actions"].tolist() == [-1] + list(range(board * board))
+    assert int(st["N"].sum()) == sims
+    x = O.tensor(O.new_state(GO, board))[None]
+    with torch.no_grad():
+        p32 = torch.softmax(model(torch.tensor(x))[0], 1).numpy()[0]
+    prior = st["P"][1:]                                      # children 1.. are the cells in ascending order
+    ref = p32[:board * board] / p32[:board * board].sum()   # expandNodeWithPolicy renormalises over the legal moves
+    assert st["P"][0] == 0.0 and np.abs(prior - ref).max() <= 2e-3
+    eng.play(3)
+    s = eng.stats()
+    assert s["moves"] == 3 * T and s["simulations"] == 4 * sims * T and s["pool_overflows"] == 0
+    eng.close()

@@ -9,12 +9,12 @@ import _orc
 pytestmark = pytest.mark.gpu
 
 
-def _positions(n, board=15, seed=0):
+def _positions(n, board=15, seed=0, game=_orc.GOMOKU):
     O = _orc.oracle()
     rng = np.random.default_rng(seed)
     xs = []
     for g in range(n):
-        s = O.new_state(_orc.GOMOKU, board)
+        s = O.new_state(game, board)
         for _ in range(int(rng.integers(0, 70))):
             O.state_make_move(s, int(rng.choice(O.legal(s))))
             if O.state_is_terminal(s):
@@ -23,14 +23,14 @@ def _positions(n, board=15, seed=0):
     return np.stack(xs)
 
 
-def _check(model, n_pos, slots, tag, saturated=False):
+def _check(model, n_pos, slots, tag, saturated=False, game=_orc.GOMOKU, board=15):
     import torch
     import torch.nn.functional as F
     from _eng import E, N
-    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=slots, evaluator=E.EVAL_RESNET, net_blocks=model.blocks_n,
+    eng = E.Engine(game=game, board_size=board, n_slots=slots, evaluator=E.EVAL_RESNET, net_blocks=model.blocks_n,
                    net_channels=128, num_simulations=8, max_nodes_per_tree=4096, deterministic=1)
     eng.load_weights(N.export_weights(model))
-    x = _positions(n_pos)
+    x = _positions(n_pos, board=board, game=game)
     pol, val, logits = eng.nn_forward(x, want_logits=True)
     with torch.no_grad():
         torch.set_num_threads(8)
@@ -81,3 +81,17 @@ def test_trunk_matches_fp32_reference_init_model():
     """`random_model_gomoku_15x15` equivalent (reference init, seed 0, 10 blocks x 128 channels)."""
     from _eng import N
     _check(N.make_random_model(seed=0), 300, 512, "reference-init", saturated=True)
+
+
+@pytest.mark.parametrize("game,board,planes", [(_orc.GO, 9, 8), (_orc.GO, 13, 8), (_orc.GOMOKU, 9, 11)])
+def test_trunk_matches_fp32_other_boards(game, board, planes):
+    """Go 9x9 / 13x13 (8 planes, A = N*N + 1, boards that do not fill whole 128-row MMA tiles) and Gomoku 9x9: same
+    kernels, same tolerance."""
+    import torch
+    from _eng import N
+    actions = board * board + (1 if game == _orc.GO else 0)
+    m = N.make_random_model(seed=2, randomize_bn=True, blocks=3, in_planes=planes, board=board, actions=actions)
+    with torch.no_grad():
+        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.15; m.v_fc2.weight *= 0.2
+        m.p_fc.bias.uniform_(-0.5, 0.5); m.v_fc2.bias.uniform_(-0.2, 0.2)
+    _check(m, 41, 64, f"game{game}-{board}x{board}", game=game, board=board)
