@@ -421,19 +421,6 @@ size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : Cfg<128>::S
 
 bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= PAIR_HALO; }
 
-size_t conv_weight_elems(int cin_total) { return (size_t)9 * cin_total * CONV_COUT; }
-
-// Weight image = the exact shared-memory picture the kernel consumes.
-//   single-CTA kernel: [tap][K stage h][8-channel chunk j][cout n][8 channels e], stages in consumption order;
-//   pair kernel:       [CTA rank r = cout / 64][tap][8-channel chunk j (16)][cout % 64][8 channels e].
-size_t conv_weight_index(int cin_total, bool pair, int tap, int ci, int co) {
-    if (pair) return ((((size_t)(co / 64) * 9 + tap) * 16 + ci / 8) * 64 + co % 64) * 8 + ci % 8;
-    const int wk = cin_total < 64 ? cin_total : 64;
-    const int spt = cin_total / wk;
-    const int h = ci / wk, j = (ci % wk) / 8, e = ci % 8;
-    return ((((size_t)tap * spt + h) * (wk / 8) + j) * CONV_COUT + co) * 8 + e;
-}
-
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) {
     static bool attr_done[3] = {false, false, false};
     cudaError_t err;

@@ -54,9 +54,21 @@ size_t conv_smem_bytes(int cin);
 // launches on `stream`; cin in {16, 128}; returns cudaError_t as int
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream);
 // element index of weight (tap, cin, cout) inside the image for a layer with `cin` input channels
-size_t conv_weight_index(int cin_total, bool pair, int tap, int ci, int co);
+// Weight image = the exact shared-memory picture the kernel consumes.
+//   single-CTA kernel: [tap][K stage h][8-channel chunk j][cout n][8 channels e], stages in consumption order;
+//   pair kernel:       [CTA rank r = cout / 64][tap][8-channel chunk j (16)][cout % 64][8 channels e].
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t conv_weight_index(int cin_total, bool pair, int tap, int ci, int co) {
+    if (pair) return ((((size_t)(co / 64) * 9 + tap) * 16 + ci / 8) * 64 + co % 64) * 8 + ci % 8;
+    const int wk = cin_total < 64 ? cin_total : 64;
+    const int spt = cin_total / wk;
+    const int h = ci / wk, j = (ci % wk) / 8, e = ci % 8;
+    return ((((size_t)tap * spt + h) * (wk / 8) + j) * CONV_COUT + co) * 8 + e;
+}
 // true when the launch for (cin, row_pitch) goes to the weight-stationary CTA-pair kernel (its own weight image layout)
 bool conv_uses_pair(int cin, int row_pitch);
-size_t conv_weight_elems(int cin_total);
+inline size_t conv_weight_elems(int cin_total) { return (size_t)9 * cin_total * CONV_COUT; }
 
 }}  // namespace az::nn

@@ -36,12 +36,54 @@ namespace az {
 template <class T>
 static int dev_alloc(T** p, size_t n) { AZ_CUDA_CHECK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T))); return 0; }
 
+// ------------------------------------------------------------------------------------------------ weight preparation
+// az_engine_load_weights hands over the trainer's fp32 tensors (AZW1 blob).  Folding eval-mode BatchNorm into the conv
+// weights, converting to bf16 and laying the weights out as the kernels' shared-memory images runs on the device: the
+// host only uploads the blob.  scale = gamma / sqrt(var + 1e-5), shift = beta - mean * scale (bn = [gamma|beta|mean|var]).
+AZ_D float bn_scale(const float* bn, int n, int i) { return bn[i] / sqrtf(bn[3 * n + i] + 1e-5f); }
+
+__global__ void k_prep_conv(const float* __restrict__ w /*[C][cin_real][9]*/, const float* __restrict__ bn, __nv_bfloat16* img, float* bias,
+                            int C, int cin_real, int cin, int pair) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < C) bias[idx] = bn[C + idx] - bn[2 * C + idx] * bn_scale(bn, C, idx);
+    if (idx >= C * cin * 9) return;
+    const int t = idx % 9, ci = (idx / 9) % cin, co = idx / (9 * cin);
+    const float v = ci < cin_real ? w[((size_t)co * cin_real + ci) * 9 + t] * bn_scale(bn, C, co) : 0.0f;
+    img[nn::conv_weight_index(cin, pair != 0, t, ci, co)] = __float2bfloat16(v);
+}
+// Head GEMM weight images: three-term bf16 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (K' = 3K), image = [W_hi | W_hi | W_lo]
+AZ_D void put3(__nv_bfloat16* img, int K, int n, int k, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
+    img[nn::gemm_weight_index(3 * K, n, k)] = hi; img[nn::gemm_weight_index(3 * K, n, K + k)] = hi; img[nn::gemm_weight_index(3 * K, n, 2 * K + k)] = lo;
+}
+// both 1x1 convs as one [64 x C] matrix (rows 0-31 policy, 32-63 value), BatchNorm scale folded in; b1 = BN shifts
+__global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restrict__ pbn, const float* __restrict__ vcw, const float* __restrict__ vbn,
+                           __nv_bfloat16* g1, float* b1, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 64) { const float* bn = idx < 32 ? pbn : vbn; const int o = idx & 31; b1[idx] = bn[32 + o] - bn[64 + o] * bn_scale(bn, 32, o); }
+    if (idx >= 64 * C) return;
+    const int c = idx % C, n = idx / C, o = n & 31;
+    const float* cw = n < 32 ? pcw : vcw; const float* bn = n < 32 ? pbn : vbn;
+    put3(g1, C, n, c, cw[(size_t)o * C + c] * bn_scale(bn, 32, o));
+}
+// FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the 1x1-conv GEMM writes
+// (cell*32 + ch); rows >= n_rows stay zero (N padded to 256)
+__global__ void k_prep_fc(const float* __restrict__ w /*[n_rows][feat]*/, __nv_bfloat16* img, int n_rows, int feat) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_rows * feat) return;
+    const int kt = (int)(idx % feat), n = (int)(idx / feat);
+    const int ch = kt / 64, cell = kt % 64;
+    put3(img, feat, n, cell * 32 + ch, w[idx]);
+}
+
 // ------------------------------------------------------------------------------------------------ network
 struct NetWeights {            // device images
     std::vector<__nv_bfloat16*> conv_w;   // stem + 2*blocks
     std::vector<float*> conv_b;
     float *b1x1 = nullptr, *pfc_b = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;   // fp32 biases / tiny last layer
     __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
+    float* blob = nullptr; size_t blob_bytes = 0;                                                        // device copy of the last AZW1 blob
+    int blocks = -1, in_planes = -1;                                                                     // shape the images above were allocated for
 };
 
 // Net = one set of activation buffers (one per stream group) + a pointer to the shared weights.
@@ -92,77 +134,59 @@ struct Net {
         return 0;
     }
 
-    // AZW1 blob: header + fp32 tensors (net.py:export_weights).  Folds eval-mode BatchNorm
-    // (scale = gamma / sqrt(var + 1e-5), shift = beta - mean * scale) into weights / bias here.
-    int load(const void* blob, size_t bytes) {
+    // AZW1 blob: header + fp32 tensors (net.py:export_weights).  The blob is uploaded as is; BatchNorm folding, bf16
+    // conversion and the shared-memory image layouts are produced by the k_prep_* kernels above.  Device buffers are
+    // allocated on the first load and reused while the network shape stays the same.
+    int load(const void* blob, size_t bytes, cudaStream_t st) {
         struct Hdr { char magic[4]; int32_t version, blocks, channels, in_planes, H, W, actions; };
         AZ_CHECK(bytes >= sizeof(Hdr), "weight blob too small");
         const Hdr* h = (const Hdr*)blob;
         AZ_CHECK(std::memcmp(h->magic, "AZW1", 4) == 0 && h->version == 1, "bad weight blob magic/version");
         AZ_CHECK(h->channels == C && h->H == H && h->W == W && h->actions == A, "weight blob does not match engine config");
-        AZ_CHECK(h->in_planes <= 16, "at most 16 input planes");
-        blocks = h->blocks; in_planes = h->in_planes;
-        const float* f = (const float*)((const char*)blob + sizeof(Hdr));
-        const float* fend = (const float*)((const char*)blob + bytes);
-        auto take = [&](size_t n) -> const float* { const float* p = f; f += n; return (f <= fend) ? p : nullptr; };
-        auto fold = [&](const float* bn, int n, std::vector<float>& scale, std::vector<float>& shift) {
-            scale.resize(n); shift.resize(n);
-            for (int i = 0; i < n; ++i) { scale[i] = bn[i] / std::sqrt(bn[3 * n + i] + 1e-5f); shift[i] = bn[n + i] - bn[2 * n + i] * scale[i]; }
-        };
-        free_weights();
-        const int nconv = 1 + 2 * blocks;
-        for (int l = 0; l < nconv; ++l) {
-            const int cin_real = l == 0 ? in_planes : C, cin = l == 0 ? 16 : C;
-            const float* cw = take((size_t)C * cin_real * 9); const float* bn = take((size_t)4 * C);
-            AZ_CHECK(cw && bn, "weight blob truncated (trunk)");
-            std::vector<float> sc, sh; fold(bn, C, sc, sh);
-            std::vector<__nv_bfloat16> img(nn::conv_weight_elems(cin), __float2bfloat16(0.0f));
-            for (int co = 0; co < C; ++co)
-                for (int ci = 0; ci < cin_real; ++ci)
-                    for (int t = 0; t < 9; ++t)
-                        img[nn::conv_weight_index(cin, nn::conv_uses_pair(cin, row_pitch), t, ci, co)] = __float2bfloat16(cw[((size_t)co * cin_real + ci) * 9 + t] * sc[co]);
-            __nv_bfloat16* dw; float* db;
-            if (dev_alloc(&dw, img.size()) || dev_alloc(&db, (size_t)C)) return -1;
-            AZ_CUDA_CHECK(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-            AZ_CUDA_CHECK(cudaMemcpy(db, sh.data(), C * 4, cudaMemcpyHostToDevice));
-            w.conv_w.push_back(dw); w.conv_b.push_back(db);
-        }
-        std::vector<float> b1(64);
-        const float* pcw = take((size_t)32 * C); const float* pbn = take(128);
-        const float* pfw = take((size_t)A * feat); const float* pfb = take(A);
-        const float* vcw = take((size_t)32 * C); const float* vbn = take(128);
-        const float* v1w = take((size_t)256 * feat); const float* v1b = take(256);
-        const float* v2w = take(256); const float* v2b = take(1);
-        AZ_CHECK(pcw && pbn && pfw && pfb && vcw && vbn && v1w && v1b && v2w && v2b, "weight blob truncated (heads)");
+        AZ_CHECK(h->in_planes <= 16 && h->in_planes >= 1 && h->blocks >= 0, "at most 16 input planes");
         AZ_CHECK(A <= 256, "policy FC image is built for <= 256 actions");
-        // Head GEMMs run as a three-term bf16 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (K' = 3K) so that the heads add no
-        // bf16 rounding of their own on top of the trunk's: weight images are [W_hi | W_hi | W_lo] along K.
-        auto put3 = [](std::vector<__nv_bfloat16>& img, int K, int n, int k, float v) {
-            const __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
-            img[nn::gemm_weight_index(3 * K, n, k)] = hi; img[nn::gemm_weight_index(3 * K, n, K + k)] = hi; img[nn::gemm_weight_index(3 * K, n, 2 * K + k)] = lo;
-        };
-        // GEMM 1: both 1x1 convs as one [64 x C] matrix (rows 0-31 policy, 32-63 value), BatchNorm scale folded in
-        std::vector<float> sc, sh;
-        std::vector<__nv_bfloat16> g1(nn::gemm_weight_elems(64, 3 * C), __float2bfloat16(0.0f));
-        fold(pbn, 32, sc, sh);
-        for (int o = 0; o < 32; ++o) { b1[o] = sh[o]; for (int c = 0; c < C; ++c) put3(g1, C, o, c, pcw[(size_t)o * C + c] * sc[o]); }
-        fold(vbn, 32, sc, sh);
-        for (int o = 0; o < 32; ++o) { b1[32 + o] = sh[o]; for (int c = 0; c < C; ++c) put3(g1, C, 32 + o, c, vcw[(size_t)o * C + c] * sc[o]); }
-        // GEMM 2/3: FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the
-        // 1x1-conv GEMM writes (cell*32 + ch); N padded to 256 with zero rows
-        std::vector<__nv_bfloat16> pimg(nn::gemm_weight_elems(256, 3 * feat), __float2bfloat16(0.0f)), vimg(nn::gemm_weight_elems(256, 3 * feat), __float2bfloat16(0.0f));
-        for (int n = 0; n < 256; ++n)
-            for (int ch = 0; ch < 32; ++ch)
-                for (int cell = 0; cell < 64; ++cell) {
-                    const int kp = cell * 32 + ch, kt = ch * 64 + cell;
-                    if (n < A) put3(pimg, feat, n, kp, pfw[(size_t)n * feat + kt]);
-                    put3(vimg, feat, n, kp, v1w[(size_t)n * feat + kt]);
-                }
-        std::vector<float> pb(256, 0.0f); for (int n = 0; n < A; ++n) pb[n] = pfb[n];
-        auto up = [&](float** d, const float* src, size_t n) -> int { if (dev_alloc(d, n)) return -1; AZ_CUDA_CHECK(cudaMemcpy(*d, src, n * 4, cudaMemcpyHostToDevice)); return 0; };
-        auto upb = [&](__nv_bfloat16** d, const std::vector<__nv_bfloat16>& v) -> int { if (dev_alloc(d, v.size())) return -1; AZ_CUDA_CHECK(cudaMemcpy(*d, v.data(), v.size() * 2, cudaMemcpyHostToDevice)); return 0; };
-        if (up(&w.b1x1, b1.data(), 64) || up(&w.pfc_b, pb.data(), 256) || up(&w.vfc1_b, v1b, 256) || up(&w.vfc2_w, v2w, 256) || up(&w.vfc2_b, v2b, 1) ||
-            upb(&w.g1_w, g1) || upb(&w.pfc_img, pimg) || upb(&w.vfc1_img, vimg)) return -1;
+        const int nb = h->blocks, ip = h->in_planes, nconv = 1 + 2 * nb;
+        // tensor offsets (in floats) inside the blob
+        size_t off = 0;
+        auto take = [&](size_t n) { const size_t o = off; off += n; return o; };
+        std::vector<size_t> cw(nconv), cbn(nconv);
+        for (int l = 0; l < nconv; ++l) { cw[l] = take((size_t)C * (l == 0 ? ip : C) * 9); cbn[l] = take((size_t)4 * C); }
+        const size_t pcw = take((size_t)32 * C), pbn = take(128), pfw = take((size_t)A * feat), pfb = take(A);
+        const size_t vcw = take((size_t)32 * C), vbn = take(128), v1w = take((size_t)256 * feat), v1b = take(256), v2w = take(256), v2b = take(1);
+        AZ_CHECK(sizeof(Hdr) + off * 4 <= bytes, "weight blob truncated");
+        if (w.blocks != nb || w.in_planes != ip) {          // (re)allocate the images for this shape
+            free_weights();
+            for (int l = 0; l < nconv; ++l) {
+                __nv_bfloat16* dw; float* db;
+                if (dev_alloc(&dw, nn::conv_weight_elems(l == 0 ? 16 : C)) || dev_alloc(&db, (size_t)C)) return -1;
+                w.conv_w.push_back(dw); w.conv_b.push_back(db);
+            }
+            if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, 256) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
+                dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(256, 3 * feat)) ||
+                dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat))) return -1;
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(256, 3 * feat) * 2, st));      // rows >= A stay zero
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, 256 * 4, st));
+            w.blocks = nb; w.in_planes = ip;
+        }
+        if (w.blob_bytes < off * 4) { cudaFree(w.blob); w.blob = nullptr; if (dev_alloc(&w.blob, off)) return -1; w.blob_bytes = off * 4; }
+        AZ_CUDA_CHECK(cudaMemcpyAsync(w.blob, (const char*)blob + sizeof(Hdr), off * 4, cudaMemcpyHostToDevice, st));
+        const float* d = w.blob;
+        for (int l = 0; l < nconv; ++l) {
+            const int cin_real = l == 0 ? ip : C, cin = l == 0 ? 16 : C;
+            const int n = C * cin * 9;
+            k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[l], w.conv_b[l], C, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
+        }
+        k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C);
+        k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat);
+        k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat);
+        AZ_CUDA_CHECK(cudaGetLastError());
+        AZ_CUDA_CHECK(cudaMemcpyAsync(w.pfc_b, d + pfb, (size_t)A * 4, cudaMemcpyDeviceToDevice, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc1_b, d + v1b, 256 * 4, cudaMemcpyDeviceToDevice, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc2_w, d + v2w, 256 * 4, cudaMemcpyDeviceToDevice, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc2_b, d + v2b, 4, cudaMemcpyDeviceToDevice, st));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(st));            // the caller's blob may go away after this call returns
+        launches += nconv + 3;
+        blocks = nb; in_planes = ip;
         loaded = true;
         return 0;
     }
@@ -172,7 +196,8 @@ struct Net {
         for (auto p : w.conv_w) cudaFree(p);
         for (auto p : w.conv_b) cudaFree(p);
         w.conv_w.clear(); w.conv_b.clear();
-        for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b}) { cudaFree(*p); *p = nullptr; }
+        for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b, &w.blob}) { cudaFree(*p); *p = nullptr; }
+        w.blob_bytes = 0; w.blocks = -1; w.in_planes = -1;
         for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img}) { cudaFree(*p); *p = nullptr; }
         loaded = false;
     }
@@ -413,8 +438,7 @@ struct EngineT : EngineBase {
     int load_weights(const void* blob, size_t bytes) override {
         AZ_CHECK(cfg.evaluator == AZ_EVAL_RESNET, "engine was created with the hash evaluator");
         if (sync_all()) return -1;
-        for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.free_weights();
-        if (groups[0].net.load(blob, bytes)) return -1;
+        if (groups[0].net.load(blob, bytes, stream)) return -1;
         for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.share(groups[0].net);
         return 0;
     }

@@ -202,13 +202,6 @@ __global__ void __launch_bounds__(256) k_pool(PoolParams p) {
 
 }  // namespace
 
-size_t gemm_weight_elems(int n_total, int k_total) { return (size_t)((n_total + 63) / 64) * 64 * k_total; }
-// image[ntile][k stage][k chunk j][n in tile][e]
-size_t gemm_weight_index(int k_total, int n, int k) {
-    const int nt = n / 64, ni = n % 64, ks = k / 64, j = (k % 64) / 8, e = k % 8;
-    return ((((size_t)nt * (k_total / 64) + ks) * 8 + j) * 64 + ni) * 8 + e;
-}
-
 int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
     static bool done = false;
     if (!done) { cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM); if (e) return (int)e; done = true; }

@@ -36,8 +36,15 @@ struct PoolParams {
     int channels, H, W, row_pitch, board_pitch, p_total, guard, boards_cap, pooled_rows;
 };
 
-size_t gemm_weight_elems(int n_total, int k_total);
-size_t gemm_weight_index(int k_total, int n, int k);
+inline size_t gemm_weight_elems(int n_total, int k_total) { return (size_t)((n_total + 63) / 64) * 64 * k_total; }
+// image[ntile][k stage][k chunk j][n in tile][e]
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t gemm_weight_index(int k_total, int n, int k) {
+    const int nt = n / 64, ni = n % 64, ks = k / 64, j = (k % 64) / 8, e = k % 8;
+    return ((((size_t)nt * (k_total / 64) + ks) * 8 + j) * 64 + ni) * 8 + e;
+}
 int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s);
 int pool_launch(const PoolParams& p, int grid, cudaStream_t s);
 
