@@ -5,7 +5,7 @@
 // 64-channel stage is 8 TMA bulk copies of 2 KB and already IS the K-major SWIZZLE_NONE shared-memory image
 // (core matrix = 8 rows x 16 bytes; LBO = 2048 B between K chunks, SBO = 128 B between 8-row groups).  B (weights) is
 // pre-arranged on the host as one contiguous 8 KB image per (n-tile of 64, K stage of 64).
-// Work item = (M tile of 128 rows, N tile of 64 columns); 4-stage TMA ring; 64-column accumulators, double-buffered.
+// Work item = (M tile of 128 rows, N tile of 64 columns); 8-stage TMA ring; 64-column accumulators, double-buffered.
 // Warp roles as in the conv kernel: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer / TMEM allocator.
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
@@ -20,9 +20,9 @@ constexpr int G_BM = 128, G_BN = 64, G_BK = 64;
 constexpr int G_A_STAGE = (G_BK / 8) * G_BM * 16;   // 16 KB
 constexpr int G_B_STAGE = (G_BK / 8) * G_BN * 16;   // 8 KB
 constexpr int G_STAGE = G_A_STAGE + G_B_STAGE;
-constexpr int G_NST = 4;
+constexpr int G_NST = 8;          // 8 x 24 KB in flight per SM: the head GEMMs are L2-latency bound (K = 384 ... 6144, tiny tiles)
 constexpr int G_OFF_BARS = G_NST * G_STAGE;
-constexpr int G_OFF_TSLOT = G_OFF_BARS + 16 * 8;
+constexpr int G_OFF_TSLOT = G_OFF_BARS + (2 * G_NST + 4) * 8;
 constexpr int G_SMEM = G_OFF_TSLOT + 16;
 constexpr int G_THREADS = 192;
 
@@ -30,10 +30,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BARS);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + G_OFF_TSLOT);
-    uint64_t* full = bars;            // [4] TMA → MMA
-    uint64_t* empty = bars + 4;       // [4] MMA → TMA
-    uint64_t* acc_full = bars + 8;    // [2]
-    uint64_t* acc_empty = bars + 10;  // [2]
+    uint64_t* full = bars;                        // [G_NST] TMA → MMA
+    uint64_t* empty = bars + G_NST;               // [G_NST] MMA → TMA
+    uint64_t* acc_full = bars + 2 * G_NST;        // [2]
+    uint64_t* acc_empty = bars + 2 * G_NST + 2;   // [2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // work decomposition: `units` row groups (GEMM1: the 64 pooled cells; FC: 1), each with m_tiles tiles of 128 rows
@@ -162,41 +162,54 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
 
 // adaptive_avg_pool2d (H x W → PH x PW, windows [floor(i*H/PH), ceil((i+1)*H/PH))) of the trunk output, written as the
 // 1x1-conv GEMM's A operand: pooled[c/8][cell * boards_cap + board][8] as a bf16 hi/lo pair (planes [0,C/8) hi,
-// [C/8, 2C/8) lo) so the heads see the fp32 average.  One thread per (board, channel chunk, pooled cell), cell fastest:
-// a warp re-reads neighbouring board rows out of L1, DRAM traffic = the trunk output once.
+// [C/8, 2C/8) lo) so the heads see the fp32 average.
+// One block = POOL_NB consecutive boards x one 8-channel chunk: the boards' rows of that chunk are one contiguous run of the
+// position stream (coalesced 16-byte loads into shared memory, every trunk byte read exactly once); the outputs of one
+// pooled cell for the POOL_NB boards are contiguous in `pooled` (full 128-byte lines).
+constexpr int POOL_NB = 8;
 __global__ void __launch_bounds__(256) k_pool(PoolParams p) {
+    extern __shared__ __align__(16) uint4 srows[];                    // [POOL_NB][board_pitch + 1]: +1 row so the boards start in different banks
     const int KCH = p.channels / 8;
     const int PH = p.H < 8 ? p.H : 8, PW = p.W < 8 ? p.W : 8, cells = PH * PW;
     const int n = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
-    const long long total = (long long)n * KCH * cells;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cell = (int)(i % cells), kc = (int)((i / cells) % KCH), b = (int)(i / ((long long)cells * KCH));
-        const int oy = cell / PW, ox = cell % PW;
-        const int y0 = (oy * p.H) / PH, y1 = ((oy + 1) * p.H + PH - 1) / PH;
-        const int x0 = (ox * p.W) / PW, x1 = ((ox + 1) * p.W + PW - 1) / PW;
-        const __nv_bfloat16* src = p.act + ((size_t)kc * p.p_total + (size_t)p.guard + (size_t)b * p.board_pitch) * 8;
-        float s[8] = {};
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(y * p.row_pitch + x) * 8));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const int groups = (n + POOL_NB - 1) / POOL_NB;
+    for (int item = blockIdx.x; item < groups * KCH; item += gridDim.x) {
+        const int kc = item % KCH, b0 = (item / KCH) * POOL_NB;
+        const int nb = min(POOL_NB, n - b0);
+        const uint4* src = reinterpret_cast<const uint4*>(p.act) + (size_t)kc * p.p_total + (size_t)p.guard + (size_t)b0 * p.board_pitch;
+        __syncthreads();                                              // previous item's readers are done
+        for (int i = threadIdx.x; i < nb * p.board_pitch; i += blockDim.x) srows[i + i / p.board_pitch] = __ldg(src + i);
+        __syncthreads();
+        for (int o = threadIdx.x; o < POOL_NB * cells; o += blockDim.x) {
+            const int bl = o % POOL_NB, cell = o / POOL_NB;
+            if (bl >= nb) continue;
+            const int oy = cell / PW, ox = cell % PW;
+            const int y0 = (oy * p.H) / PH, y1 = ((oy + 1) * p.H + PH - 1) / PH;
+            const int x0 = (ox * p.W) / PW, x1 = ((ox + 1) * p.W + PW - 1) / PW;
+            const uint4* brow = srows + bl * (p.board_pitch + 1);
+            float s[8] = {};
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) {
+                    const uint4 u = brow[y * p.row_pitch + x];
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
+                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
+                }
+            const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+            uint4 ov, ol;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&ol);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = s[2 * e] * inv, c = s[2 * e + 1] * inv;
+                ob[e] = __floats2bfloat162_rn(a, c);
+                const float2 hi = __bfloat1622float2(ob[e]);
+                lb[e] = __floats2bfloat162_rn(a - hi.x, c - hi.y);
             }
-        const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
-        uint4 o, ol;
-        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-        __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&ol);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float a = s[2 * e] * inv, c = s[2 * e + 1] * inv;
-            ob[e] = __floats2bfloat162_rn(a, c);
-            const float2 hi = __bfloat1622float2(ob[e]);
-            lb[e] = __floats2bfloat162_rn(a - hi.x, c - hi.y);
+            const size_t row = (size_t)cell * p.boards_cap + b0 + bl;
+            *reinterpret_cast<uint4*>(p.pooled + ((size_t)kc * p.pooled_rows + row) * 8) = ov;
+            *reinterpret_cast<uint4*>(p.pooled + ((size_t)(KCH + kc) * p.pooled_rows + row) * 8) = ol;
         }
-        const size_t row = (size_t)cell * p.boards_cap + b;
-        *reinterpret_cast<uint4*>(p.pooled + ((size_t)kc * p.pooled_rows + row) * 8) = o;
-        *reinterpret_cast<uint4*>(p.pooled + ((size_t)(KCH + kc) * p.pooled_rows + row) * 8) = ol;
     }
 }
 
@@ -209,7 +222,11 @@ int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 int pool_launch(const PoolParams& p, int grid, cudaStream_t s) {
-    k_pool<<<grid, 256, 0, s>>>(p);
+    const size_t smem = (size_t)POOL_NB * (p.board_pitch + 1) * 16;
+    static bool done = false;
+    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); if (e) return (int)e; done = true; }
+    if (smem > 96 * 1024) return (int)cudaErrorInvalidValue;
+    k_pool<<<grid, 256, smem, s>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -72,8 +72,11 @@ def test_trunk_matches_fp32_calibrated_heads(blocks):
     m = N.make_random_model(seed=1, randomize_bn=True, blocks=blocks)
     with torch.no_grad():
         scale = {0: 1.0, 1: 0.5, 10: 0.03}[blocks]
+        gen = torch.Generator().manual_seed(11 + blocks)   # fixed: the heads' calibration must not depend on the global RNG
         m.p_fc.weight *= scale; m.v_fc1.weight *= scale * 0.7; m.v_fc2.weight *= 0.2
-        m.p_fc.bias.uniform_(-0.5, 0.5); m.v_fc1.bias.uniform_(-0.1, 0.1); m.v_fc2.bias.uniform_(-0.2, 0.2)
+        m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
+        m.v_fc1.bias.copy_(0.2 * torch.rand(m.v_fc1.bias.shape, generator=gen) - 0.1)
+        m.v_fc2.bias.copy_(0.4 * torch.rand(m.v_fc2.bias.shape, generator=gen) - 0.2)
     _check(m, 37, 64, f"calibrated-{blocks}")
 
 
@@ -91,7 +94,9 @@ def test_trunk_matches_fp32_other_boards(game, board, planes):
     from _eng import N
     actions = board * board + (1 if game == _orc.GO else 0)
     m = N.make_random_model(seed=2, randomize_bn=True, blocks=3, in_planes=planes, board=board, actions=actions)
+    gen = torch.Generator().manual_seed(7)                 # fixed: the heads' calibration must not depend on the global RNG
     with torch.no_grad():
-        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.15; m.v_fc2.weight *= 0.2
-        m.p_fc.bias.uniform_(-0.5, 0.5); m.v_fc2.bias.uniform_(-0.2, 0.2)
+        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.1; m.v_fc2.weight *= 0.2
+        m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
+        m.v_fc2.bias.copy_(0.4 * torch.rand(m.v_fc2.bias.shape, generator=gen) - 0.2)
     _check(m, 41, 64, f"game{game}-{board}x{board}", game=game, board=board)
