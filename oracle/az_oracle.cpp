@@ -21,6 +21,8 @@
 #include <unordered_set>
 #include <algorithm>
 #include <memory>
+#include <cstdlib>
+#include <utility>
 
 namespace orc {
 
@@ -288,6 +290,243 @@ struct Go : State {
     }
 };
 
+// -------------------------------------------------------------------------------------------- Chess
+// The reference's chess is NOT runnable (makeMove → isLegalMove → moveExposesKing → cloneWithMove → makeMove … recurses
+// without end), so this restatement cannot be pinned against oracle/_ref; it is pinned on the known answers
+// the reference's own tests state (tests/games/chess/chess_state_test.cpp:27-65: 20 legal moves at the start, player
+// alternation; :92-180 FEN positions) and on perft from the start position.  The recursion is cut where SURVEY says:
+// moveExposesKing applies the move without a legality check.
+struct Chess : State {
+    enum { NONE = 0, PAWN = 1, KNIGHT = 2, BISHOP = 3, ROOK = 4, QUEEN = 5, KING = 6 };   // chess_state.h:20-36
+    enum { WHITE = 1, BLACK = 2 };
+    struct Pc { int8_t t = 0, c = 0; };
+    struct Mv { int from, to, promo; };
+    Pc b[64];                                   // square 0 = a8, rank = sq/8 counted from black's back rank (chess_rules.h:24-32)
+    int cur = WHITE, ep = -1, half = 0;
+    bool wk = true, wq = true, bk = true, bq = true;
+    uint64_t h = 0;                             // QUIRK: hash_ is only ever updated by setPiece (chess_state.cpp:233-245); makeMove never
+                                                // marks it dirty, so side to move / castling / en passant changes do not enter the
+                                                // repetition key — it is the piece placement (plus constants that cancel)
+    std::vector<std::pair<uint64_t, int>> pos_hist;   // position_history_ (hash → count)
+    std::vector<int> hist;
+    static bool& fide() { static bool f = false; return f; }   // false = literal isSquareAttacked pawn direction (QUIRK C5)
+
+    Chess() { start(); }
+    static uint64_t zk(const Pc& p, int sq) { return mix64(0xC0FFEEULL + (uint64_t)((p.t - 1) + (p.c == BLACK ? 6 : 0)) * 64 + sq); }
+    void put(int sq, int t, int c) { if (b[sq].t) h ^= zk(b[sq], sq); b[sq].t = (int8_t)t; b[sq].c = (int8_t)(t ? c : 0); if (t) h ^= zk(b[sq], sq); }
+    int& count(uint64_t k) { for (auto& e : pos_hist) if (e.first == k) return e.second; pos_hist.push_back({k, 0}); return pos_hist.back().second; }
+    int seen(uint64_t k) const { for (auto& e : pos_hist) if (e.first == k) return e.second; return 0; }
+    void clear() { for (auto& p : b) p = Pc(); h = 0; cur = WHITE; wk = wq = bk = bq = true; ep = -1; half = 0; pos_hist.clear(); hist.clear(); }
+    void start() {                              // initializeStartingPosition chess_state.cpp:152-200
+        clear();
+        static const int back[8] = {ROOK, KNIGHT, BISHOP, QUEEN, KING, BISHOP, KNIGHT, ROOK};
+        for (int f = 0; f < 8; ++f) { put(0 * 8 + f, back[f], BLACK); put(1 * 8 + f, PAWN, BLACK); put(6 * 8 + f, PAWN, WHITE); put(7 * 8 + f, back[f], WHITE); }
+        count(h)++;                             // ctor: recordPosition() :66-67
+    }
+    bool set_fen(const char* fen) {             // test helper (setFromFEN): board / side / castling / ep / halfmove
+        clear(); int r = 0, f = 0; const char* p = fen;
+        for (; *p && *p != ' '; ++p) {
+            if (*p == '/') { ++r; f = 0; continue; }
+            if (*p >= '1' && *p <= '8') { f += *p - '0'; continue; }
+            const char* names = "pnbrqk"; const char lc = (char)(*p | 32); const char* q = strchr(names, lc);
+            if (!q || r > 7 || f > 7) return false;
+            put(r * 8 + f, (int)(q - names) + 1, (*p & 32) ? BLACK : WHITE); ++f;
+        }
+        if (*p) ++p; cur = (*p == 'b') ? BLACK : WHITE; while (*p && *p != ' ') ++p; if (*p) ++p;
+        wk = wq = bk = bq = false;
+        for (; *p && *p != ' '; ++p) { if (*p == 'K') wk = true; if (*p == 'Q') wq = true; if (*p == 'k') bk = true; if (*p == 'q') bq = true; }
+        if (*p) ++p;
+        if (*p && *p != '-') { const int file = p[0] - 'a', rk = p[1] - '0'; if (file >= 0 && file < 8 && rk >= 1 && rk <= 8) ep = (8 - rk) * 8 + file; }
+        while (*p && *p != ' ') ++p; if (*p) ++p;
+        half = atoi(p);
+        count(h)++;
+        return true;
+    }
+    State* clone() const override { return new Chess(*this); }
+    int player() const override { return cur; }
+    int action_space() const override { return 64 * 64 * 5; }        // chess_state.h:117
+    int board_size() const override { return 8; }
+    int game_type() const override { return 1; }
+    int planes() const override { return 18; }
+
+    static bool on(int r, int f) { return r >= 0 && r < 8 && f >= 0 && f < 8; }
+    bool attacked(int sq, int by) const {       // isSquareAttacked chess_rules.cpp:130-229: pawn, knight, king, diagonals, straights
+        const int r = sq / 8, f = sq % 8;
+        // QUIRK C5: the reference looks for `by`'s pawns at rank + pawnDir with pawnDir = (by == WHITE) ? -1 : +1, i.e. in the
+        // direction those pawns MOVE — a white pawn really attacking (r, f) from (r+1, f±1) is not seen.  fide() flips it.
+        const int pd = ((by == WHITE) ? -1 : 1) * (fide() ? -1 : 1);
+        for (int df = -1; df <= 1; df += 2) if (on(r + pd, f + df)) { const Pc& a = b[(r + pd) * 8 + f + df]; if (a.t == PAWN && a.c == by) return true; }
+        static const int KN[8][2] = {{-2, -1}, {-2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}, {2, -1}, {2, 1}};
+        static const int KG[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+        for (auto& d : KN) if (on(r + d[0], f + d[1])) { const Pc& a = b[(r + d[0]) * 8 + f + d[1]]; if (a.t == KNIGHT && a.c == by) return true; }
+        for (auto& d : KG) if (on(r + d[0], f + d[1])) { const Pc& a = b[(r + d[0]) * 8 + f + d[1]]; if (a.t == KING && a.c == by) return true; }
+        static const int BD[4][2] = {{-1, -1}, {-1, 1}, {1, -1}, {1, 1}}, RD[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+        for (auto& d : BD) for (int k = 1; on(r + d[0] * k, f + d[1] * k); ++k) { const Pc& a = b[(r + d[0] * k) * 8 + f + d[1] * k]; if (a.t) { if (a.c == by && (a.t == BISHOP || a.t == QUEEN)) return true; break; } }
+        for (auto& d : RD) for (int k = 1; on(r + d[0] * k, f + d[1] * k); ++k) { const Pc& a = b[(r + d[0] * k) * 8 + f + d[1] * k]; if (a.t) { if (a.c == by && (a.t == ROOK || a.t == QUEEN)) return true; break; } }
+        return false;
+    }
+    int king_sq(int c) const { for (int s = 0; s < 64; ++s) if (b[s].t == KING && b[s].c == c) return s; return -1; }   // :1139-1147
+    bool in_check(int c) const { const int k = king_sq(c); return k >= 0 && attacked(k, 3 - c); }                    // chess_rules.cpp:119-128
+    void slide(std::vector<Mv>& m, int sq, const int (*dirs)[2], int nd) const {   // addSlidingMoves :559-590
+        const int r = sq / 8, f = sq % 8;
+        for (int i = 0; i < nd; ++i)
+            for (int k = 1; on(r + dirs[i][0] * k, f + dirs[i][1] * k); ++k) {
+                const int t = (r + dirs[i][0] * k) * 8 + f + dirs[i][1] * k;
+                if (!b[t].t) m.push_back({sq, t, 0});
+                else { if (b[t].c != cur) m.push_back({sq, t, 0}); break; }
+            }
+    }
+    bool castle_ok(int from, int to) const {     // isValidCastle chess_rules.cpp:675-727 (standard chess: rook files 7 / 0)
+        const int r = from / 8, ff = from % 8, tf = to % 8; const bool ks = tf > ff; const int rf = ks ? 7 : 0, rs = r * 8 + rf;
+        if (b[rs].t != ROOK || b[rs].c != cur) return false;
+        for (int f = std::min(ff, rf) + 1; f < std::max(ff, rf); ++f) if (b[r * 8 + f].t) return false;
+        const int step = ks ? 1 : -1;
+        for (int f = ff; f != tf + step; f += step) {
+            const int s = r * 8 + f;
+            if (s == from) continue;
+            if (attacked(s, 3 - cur)) return false;
+            if (s != rs && b[s].t) return false;
+        }
+        return true;
+    }
+    std::vector<Mv> pseudo() const {             // generatePseudoLegalMoves chess_rules.cpp:57-98: squares ascending, castling last
+        std::vector<Mv> m;
+        static const int KN[8][2] = {{-2, -1}, {-2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}, {2, -1}, {2, 1}};
+        static const int KG[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+        static const int BD[4][2] = {{-1, -1}, {-1, 1}, {1, -1}, {1, 1}}, RD[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+        for (int sq = 0; sq < 64; ++sq) {
+            if (b[sq].c != cur) continue;
+            const int r = sq / 8, f = sq % 8;
+            switch (b[sq].t) {
+                case PAWN: {                     // addPawnMoves :470-528: push (promotions Q,R,B,N), double push, captures file-1 then +1, e.p.
+                    const int d = cur == WHITE ? -1 : 1, nr = r + d;
+                    if (nr >= 0 && nr < 8 && !b[nr * 8 + f].t) {
+                        if (nr == 0 || nr == 7) for (int pr : {QUEEN, ROOK, BISHOP, KNIGHT}) m.push_back({sq, nr * 8 + f, pr});
+                        else m.push_back({sq, nr * 8 + f, 0});
+                        if ((cur == WHITE && r == 6) || (cur == BLACK && r == 1)) { const int t2 = (nr + d) * 8 + f; if (!b[t2].t) m.push_back({sq, t2, 0}); }
+                    }
+                    for (int df = -1; df <= 1; df += 2) {
+                        const int nf = f + df;
+                        if (!on(nr, nf)) continue;
+                        const int t = nr * 8 + nf;
+                        if (b[t].t && b[t].c != cur) {
+                            if (nr == 0 || nr == 7) for (int pr : {QUEEN, ROOK, BISHOP, KNIGHT}) m.push_back({sq, t, pr});
+                            else m.push_back({sq, t, 0});
+                        }
+                        if (ep == t) m.push_back({sq, t, 0});
+                    }
+                    break;
+                }
+                case KNIGHT: for (auto& dd : KN) if (on(r + dd[0], f + dd[1])) { const int t = (r + dd[0]) * 8 + f + dd[1]; if (!b[t].t || b[t].c != cur) m.push_back({sq, t, 0}); } break;
+                case BISHOP: slide(m, sq, BD, 4); break;
+                case ROOK: slide(m, sq, RD, 4); break;
+                case QUEEN: slide(m, sq, KG, 8); break;       // QUEEN_DIRECTIONS == KING_MOVES order (chess_rules.cpp:15-30)
+                case KING: for (auto& dd : KG) if (on(r + dd[0], f + dd[1])) { const int t = (r + dd[0]) * 8 + f + dd[1]; if (!b[t].t || b[t].c != cur) m.push_back({sq, t, 0}); } break;
+                default: break;
+            }
+        }
+        // addCastlingMoves :613-673: not in check, right still set, king target = file 4 +- 2 on the home rank
+        if (!in_check(cur)) {
+            const bool ck = cur == WHITE ? wk : bk, cq = cur == WHITE ? wq : bq;
+            const int ks = king_sq(cur);
+            if ((ck || cq) && ks >= 0) {
+                const int home = cur == WHITE ? 7 : 0;
+                if (ck && castle_ok(ks, home * 8 + 6)) m.push_back({ks, home * 8 + 6, 0});
+                if (cq && castle_ok(ks, home * 8 + 2)) m.push_back({ks, home * 8 + 2, 0});
+            }
+        }
+        return m;
+    }
+    void apply(const Mv& mv) {                   // makeMove(ChessMove) chess_state.cpp:976-1095 without the legality check
+        Pc pc = b[mv.from]; const Pc cap = b[mv.to];
+        half = (pc.t == PAWN || cap.t) ? 0 : half + 1;
+        const int old_ep = ep; ep = -1;
+        if (pc.t == PAWN) {
+            const int fr = mv.from / 8, tr = mv.to / 8;
+            if (std::abs(fr - tr) == 2) ep = ((fr + tr) / 2) * 8 + mv.from % 8;
+            if (mv.to == old_ep) put((mv.from / 8) * 8 + mv.to % 8, 0, 0);
+            if (mv.promo) pc.t = (int8_t)mv.promo;
+        }
+        if (pc.t == KING && std::abs(mv.from % 8 - mv.to % 8) == 2) {
+            const int r = mv.from / 8; const bool ks = mv.to % 8 > mv.from % 8;
+            const int rf = r * 8 + (ks ? 7 : 0), rt = r * 8 + (ks ? 5 : 3);
+            const Pc rook = b[rf]; put(rf, 0, 0); put(rt, rook.t, rook.c);
+        }
+        // getUpdatedCastlingRights chess_rules.cpp:395-468
+        if (pc.t == KING) { if (pc.c == WHITE) wk = wq = false; else bk = bq = false; }
+        if (pc.t == ROOK) {
+            const int f = mv.from % 8, r = mv.from / 8;
+            if (pc.c == WHITE) { if (f == 7 && r == 7) wk = false; else if (f == 0 && r == 7) wq = false; }
+            else { if (f == 7 && r == 0) bk = false; else if (f == 0 && r == 0) bq = false; }
+        }
+        if (cap.t == ROOK) {
+            const int f = mv.to % 8, r = mv.to / 8;
+            if (cap.c == WHITE) { if (f == 7 && r == 7) wk = false; else if (f == 0 && r == 7) wq = false; }
+            else { if (f == 7 && r == 0) bk = false; else if (f == 0 && r == 0) bq = false; }
+        }
+        put(mv.from, 0, 0); put(mv.to, pc.t, pc.c);
+        cur = 3 - cur;
+        count(h)++;                              // recordPosition :1092-1095
+    }
+    std::vector<Mv> legal_moves() const {         // generateLegalMoves chess_rules.cpp:38-55 (+ the recursion cut in moveExposesKing)
+        std::vector<Mv> out;
+        for (const Mv& mv : pseudo()) { Chess t(*this); t.apply(mv); if (!t.in_check(cur)) out.push_back(mv); }
+        return out;
+    }
+    static int code(const Mv& m) {                // chessMoveToAction chess_state.cpp:1214-1230 (C1)
+        const int pc = m.promo == QUEEN ? 1 : m.promo == ROOK ? 2 : m.promo == BISHOP ? 3 : m.promo == KNIGHT ? 4 : 0;
+        return (pc << 12) | (m.from << 6) | m.to;
+    }
+    static Mv decode(int a) { static const int P[5] = {0, QUEEN, ROOK, BISHOP, KNIGHT}; const int pc = (a >> 12) & 7; return {(a >> 6) & 63, a & 63, pc <= 4 ? P[pc] : 0}; }
+    std::vector<int> legal() const override { std::vector<int> r; for (const Mv& m : legal_moves()) r.push_back(code(m)); return r; }
+    bool make_move(int a) override {
+        if (a < 0 || a >= action_space()) return false;
+        const Mv want = decode(a);
+        for (const Mv& m : legal_moves()) if (m.from == want.from && m.to == want.to && m.promo == want.promo) { apply(m); hist.push_back(a); return true; }
+        return false;                              // "Illegal move attempted" (chess_state.cpp:977-979)
+    }
+    bool insufficient() const {                   // hasInsufficientMaterial chess_rules.cpp:231-389
+        int n = 0, P[3] = {0, 0, 0}, N[3] = {0, 0, 0}, B[3] = {0, 0, 0}, R[3] = {0, 0, 0}, Q[3] = {0, 0, 0}; bool light[3] = {false, false, false}, dark[3] = {false, false, false};
+        for (int s = 0; s < 64; ++s) {
+            if (!b[s].t) continue; ++n; const int c = b[s].c; const bool lt = ((s / 8 + s % 8) % 2 == 0);
+            switch (b[s].t) { case PAWN: ++P[c]; break; case KNIGHT: ++N[c]; break; case BISHOP: ++B[c]; (lt ? light[c] : dark[c]) = true; break; case ROOK: ++R[c]; break; case QUEEN: ++Q[c]; break; default: break; }
+        }
+        const int W = WHITE, K = BLACK;
+        const bool noP = !P[W] && !P[K], noN = !N[W] && !N[K], noB = !B[W] && !B[K], noR = !R[W] && !R[K], noQ = !Q[W] && !Q[K];
+        if (n == 2) return true;
+        if (((N[W] == 1 && N[K] == 0) || (N[W] == 0 && N[K] == 1)) && noP && noB && noR && noQ) return true;
+        if (((B[W] == 1 && B[K] == 0) || (B[W] == 0 && B[K] == 1)) && noP && noN && noR && noQ) return true;
+        if (noP && noN && B[W] == 1 && B[K] == 1 && noR && noQ && ((light[W] && light[K]) || (dark[W] && dark[K]))) return true;
+        if (N[W] == 2 && N[K] == 0 && noP && noB && noR && noQ) return true;
+        if (N[W] == 0 && N[K] == 2 && noP && noB && noR && noQ) return true;
+        if (N[W] == 1 && N[K] == 1 && noP && noB && noR && noQ) return true;
+        if (((N[W] == 1 && B[K] == 1 && N[K] == 0 && B[W] == 0) || (N[K] == 1 && B[W] == 1 && N[W] == 0 && B[K] == 0)) && noP && noR && noQ) return true;
+        return false;
+    }
+    int result() const override {                 // isTerminal chess_state.cpp:599-652: no moves, material, 50-move, threefold
+        if (legal_moves().empty()) return in_check(cur) ? (cur == WHITE ? WIN_P2 : WIN_P1) : DRAW;
+        if (insufficient() || half >= 100 || seen(h) >= 3) return DRAW;
+        return ONGOING;
+    }
+    bool terminal() const override { return result() != ONGOING; }
+    uint64_t key() const override {               // HashEvaluator key for chess (this repo's definition; the survey probe had none)
+        uint64_t k = 1469598103934665603ULL;
+        for (int s = 0; s < 64; ++s) k = mix64(k ^ (uint64_t)(b[s].t + 8 * b[s].c));
+        k = mix64(k ^ (uint64_t)cur);
+        k = mix64(k ^ (uint64_t)((wk ? 1 : 0) | (wq ? 2 : 0) | (bk ? 4 : 0) | (bq ? 8 : 0)));
+        return mix64(k ^ (uint64_t)(int64_t)(ep + 1));
+    }
+    void tensor(float* t) const override {        // getEnhancedTensorRepresentation chess_state.cpp:665-769 (C4), [plane][rank][file]
+        std::fill(t, t + 18 * 64, 0.0f);
+        for (int s = 0; s < 64; ++s) if (b[s].t) t[((b[s].t - 1) + (b[s].c == BLACK ? 6 : 0)) * 64 + s] = 1.0f;
+        const float cast = (wk ? 0.25f : 0.0f) + (wq ? 0.25f : 0.0f) + (bk ? 0.25f : 0.0f) + (bq ? 0.25f : 0.0f);
+        const float hm = std::min(1.0f, (float)half / 100.0f), rep = (float)seen(h) / 3.0f;
+        for (int s = 0; s < 64; ++s) { t[12 * 64 + s] = cur == WHITE ? 1.0f : 0.0f; t[13 * 64 + s] = cast; t[15 * 64 + s] = hm; t[17 * 64 + s] = rep; }
+        if (ep >= 0 && ep < 64) t[14 * 64 + ep] = 1.0f;
+    }
+    long perft(int d) const { if (d == 0) return 1; long n = 0; for (const Mv& m : legal_moves()) { Chess t(*this); t.apply(m); n += t.perft(d - 1); } return n; }
+};
+
 // ------------------------------------------------------------------------------------ HashEvaluator
 static void hash_eval(uint64_t h, int A, float* policy, float* value) {
     float sum = 0.0f;
@@ -409,6 +648,7 @@ extern "C" {
 void* orc_state_new(int game_type, int board_size) {
     if (game_type == 0) return new Gomoku(board_size);
     if (game_type == 2) return new Go(board_size);
+    if (game_type == 1) return new Chess();
     return nullptr;
 }
 void orc_state_free(void* h) { delete (State*)h; }
@@ -423,6 +663,11 @@ int orc_state_board_size(void* h) { return ((State*)h)->board_size(); }
 int orc_state_tensor(void* h, float* out) { State* s = (State*)h; if (out) s->tensor(out); return s->planes(); }
 uint64_t orc_state_key(void* h) { return ((State*)h)->key(); }
 void orc_hash_eval(void* h, float* policy, float* value) { State* s = (State*)h; hash_eval(s->key(), s->action_space(), policy, value); }
+int orc_chess_set_fen(void* h, const char* fen) { return ((Chess*)h)->set_fen(fen) ? 0 : -1; }
+void orc_chess_set_fide(int on) { Chess::fide() = on != 0; }
+long orc_chess_perft(void* h, int depth) { return ((Chess*)h)->perft(depth); }
+int orc_chess_piece(void* h, int sq) { const Chess* c = (Chess*)h; return c->b[sq].t + 8 * c->b[sq].c; }
+int orc_chess_in_check(void* h) { const Chess* c = (Chess*)h; return c->in_check(c->cur) ? 1 : 0; }
 int orc_go_stone(void* h, int pos) { return ((Go*)h)->board[pos]; }
 int orc_go_ko(void* h) { return ((Go*)h)->ko; }
 int orc_go_captured(void* h, int pl) { return ((Go*)h)->captured[pl]; }

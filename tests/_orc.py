@@ -37,6 +37,12 @@ class Checker:
         f("state_tensor", C.c_int, [C.c_void_p, C.c_void_p])
         f("state_key", C.c_uint64, [C.c_void_p])
         f("hash_eval", None, [C.c_void_p, C.c_void_p, C.c_void_p])
+        if prefix == "orc_":     # chess exists only in the restatement (the reference's chess is not runnable)
+            f("chess_set_fen", C.c_int, [C.c_void_p, C.c_char_p])
+            f("chess_set_fide", None, [C.c_int])
+            f("chess_perft", C.c_long, [C.c_void_p, C.c_int])
+            f("chess_piece", C.c_int, [C.c_void_p, C.c_int])
+            f("chess_in_check", C.c_int, [C.c_void_p])
         f("go_stone", C.c_int, [C.c_void_p, C.c_int])
         f("go_ko", C.c_int, [C.c_void_p])
         f("go_captured", C.c_int, [C.c_void_p, C.c_int])
@@ -66,7 +72,13 @@ class Checker:
     def legal(self, s):
         buf = np.zeros(512, np.int32)
         n = self.state_legal_moves(s, buf.ctypes.data, 512)
+        assert n <= 512
         return buf[:n].copy()
+
+    def chess_from_fen(self, fen):
+        s = self.new_state(CHESS, 8)
+        assert self.chess_set_fen(s, fen.encode()) == 0
+        return s
 
     def tensor(self, s):
         c = self.state_tensor(s, None)
