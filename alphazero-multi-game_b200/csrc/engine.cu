@@ -23,6 +23,7 @@ void set_error(const std::string& s) { g_error = s; }
 
 #include "gomoku.cuh"
 #include "go.cuh"
+#include "chess.cuh"
 #include "tree_kernels.cuh"
 #include "conv_trunk.cuh"
 #include "heads.cuh"
@@ -365,7 +366,7 @@ struct EngineT : EngineBase {
         AZ_CHECK(prop.major >= 10, "az_b200 needs an sm_100-class GPU (no fallback path exists)");
         AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         int cap = c.max_nodes_per_tree;
-        if (cap <= 0) cap = 2 * (std::max(c.num_simulations, 1) + 1) * A + 1;
+        if (cap <= 0) cap = 2 * (std::max(c.num_simulations, 1) + 1) * MC + 1;
         tp.cap = cap;
         const size_t tn = (size_t)T * cap;
         if (dev_alloc(&tp.N, tn) || dev_alloc(&tp.W, tn) || dev_alloc(&tp.P, tn) || dev_alloc(&tp.first, tn) || dev_alloc(&tp.act, tn) ||
@@ -382,7 +383,7 @@ struct EngineT : EngineBase {
         ring_cap = c.sample_ring_capacity > 0 ? c.sample_ring_capacity : std::max(4 * T, 4096);
         if (dev_alloc(&game_buf, (size_t)T * max_moves) || dev_alloc(&ring, (size_t)ring_cap) || dev_alloc(&ring_count, 1)) return -1;
         AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
-        if (dev_alloc(&noise_scratch, (size_t)T * A) || dev_alloc(&dstats, 1)) return -1;
+        if (dev_alloc(&noise_scratch, (size_t)T * MC) || dev_alloc(&dstats, 1)) return -1;
         AZ_CUDA_CHECK(cudaMemset(dstats, 0, sizeof(Stats)));
         // QUIRK G2: legal-move order of the first-ever enumeration of a fresh state = iteration order of a
         // libstdc++ std::unordered_set<int> filled with 0..A-1 ascending (include/alphazero/games/gomoku/
@@ -410,7 +411,10 @@ struct EngineT : EngineBase {
             const size_t off = (size_t)g.t0 * cap;
             g.tp.N += off; g.tp.W += off; g.tp.P += off; g.tp.first += off; g.tp.act += off; g.tp.nchild += off; g.tp.flags += off;
             g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
-            if (c.evaluator == AZ_EVAL_RESNET) { if (g.net.init(G::N, G::N, A, per, c.net_channels)) return -1; }
+            if (c.evaluator == AZ_EVAL_RESNET) {
+                AZ_CHECK(G::PLANES <= 16 && A <= 256, "the bf16 ResNet evaluator is built for <= 16 input planes and <= 256 actions (chess, Go 19x19: hash evaluator only)");
+                if (g.net.init(G::N, G::N, A, per, c.net_channels)) return -1;
+            }
         }
         return reset_games();
     }
@@ -498,7 +502,7 @@ struct EngineT : EngineBase {
         k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
         if (cfg.evaluator == AZ_EVAL_HASH) {
-            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(A * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
+            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
@@ -516,7 +520,7 @@ struct EngineT : EngineBase {
             if (wave(g, 1)) return -1;                  // search() preamble: expand unexpanded roots
             if (!cfg.deterministic) {
                 k_dirichlet<<<blocks_for_warps(g.n), 128, 0, g.stream>>>(g.tp, g.n, g.t0, cfg.dirichlet_alpha, cfg.dirichlet_epsilon, cfg.seed,
-                                                                        noise_scratch + (size_t)g.t0 * A, A);
+                                                                        noise_scratch + (size_t)g.t0 * MC, MC);
                 AZ_LAUNCH_CHECK(); ++launches;
             }
         }
@@ -555,7 +559,7 @@ struct EngineT : EngineBase {
             k_flag_noise<<<(g.n + 127) / 128, 128, 0, g.stream>>>(g.tp, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
             if (wave(g, 1)) return -1;
-            k_dirichlet<<<blocks_for_warps(g.n), 128, 0, g.stream>>>(g.tp, g.n, g.t0, alpha, eps, cfg.seed ^ (0x9E37ULL * ++noise_calls), noise_scratch + (size_t)g.t0 * A, A);
+            k_dirichlet<<<blocks_for_warps(g.n), 128, 0, g.stream>>>(g.tp, g.n, g.t0, alpha, eps, cfg.seed ^ (0x9E37ULL * ++noise_calls), noise_scratch + (size_t)g.t0 * MC, MC);
             AZ_LAUNCH_CHECK(); ++launches;
         }
         if (join_groups()) return -1;
@@ -790,7 +794,8 @@ AZ_API int az_engine_create(const az_config* cfg, az_engine** out) {
     else if (cfg->game == AZ_GAME_GO && cfg->board_size == 9) { auto* e = new az::EngineT<az::Go<9>>(); impl.reset(e); rc = e->init(*cfg); }
     else if (cfg->game == AZ_GAME_GO && cfg->board_size == 13) { auto* e = new az::EngineT<az::Go<13>>(); impl.reset(e); rc = e->init(*cfg); }
     else if (cfg->game == AZ_GAME_GO && cfg->board_size == 19) { auto* e = new az::EngineT<az::Go<19>>(); impl.reset(e); rc = e->init(*cfg); }
-    else { az::set_error("unsupported game / board size (built: Gomoku 15x15, 9x9; Go 9x9, 13x13, 19x19)"); return -3; }
+    else if (cfg->game == AZ_GAME_CHESS && (cfg->board_size == 8 || cfg->board_size == 0)) { auto* e = new az::EngineT<az::Chess>(); impl.reset(e); rc = e->init(*cfg); }
+    else { az::set_error("unsupported game / board size (built: Gomoku 15x15, 9x9; Go 9x9, 13x13, 19x19; chess)"); return -3; }
     if (rc != 0) return rc;
     *out = new az_engine{std::move(impl)};
     return 0;

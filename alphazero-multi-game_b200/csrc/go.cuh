@@ -27,6 +27,7 @@ struct Go {
     static constexpr int NW = (PBITS + 63) / 64;
     static constexpr int ACTIONS = CELLS + 1;          // getActionSpaceSize (go_state.cpp:345-347); index N*N is never used
     static constexpr int MAX_CHILDREN = CELLS + 1;     // pass + every cell
+    static constexpr int SAMPLE_VISITS = CELLS + 1;    // visit counts by action, pass last
     static constexpr int PLANES = 8;
     static constexpr bool FIRST_FILL = false;          // legal-move order is the same for every enumeration (QUIRK Go2)
     static constexpr int MAX_GAME_MOVES = 2 * CELLS;   // engine cap (the reference has none): the game is scored at this ply
@@ -368,6 +369,7 @@ struct Go {
     __device__ static int w_player(const Warp& w) { return w.s.c.player; }
     __device__ static int w_ply(const Warp& w) { return w.s.c.ply; }
     __device__ static int visit_index(int action) { return action < 0 ? CELLS : action; }
+    __device__ static void record_visit(uint16_t* visits, int, int action, int n) { visits[visit_index(action)] = (uint16_t)min(n, 65535); }
     // legal moves in the reference's order (QUIRK Go2): pass (-1) first, then cells ascending.  `emit(i, a)` per move.
     template <class F>
     __device__ static int w_for_legal(Warp& w, int lane, F emit) {

@@ -25,6 +25,7 @@ struct Gomoku {
     static constexpr int PACKED_NW = (CELLS + 63) / 64;
     static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
     static constexpr int MAX_CHILDREN = CELLS;
+    static constexpr int SAMPLE_VISITS = CELLS;
     static constexpr bool FIRST_FILL = true;       // QUIRK G2: the first enumeration of a lineage has its own order
     static constexpr int MAX_GAME_MOVES = CELLS;
 
@@ -223,6 +224,7 @@ struct Gomoku {
     __device__ static int w_player(const Warp& w) { return w.s.player; }
     __device__ static int w_ply(const Warp& w) { return w.s.ply; }
     __device__ static int visit_index(int action) { return action; }
+    __device__ static void record_visit(uint16_t* visits, int, int action, int n) { visits[visit_index(action)] = (uint16_t)min(n, 65535); }
     // Legal moves in the reference's order (QUIRK G2): descending action index — std::unordered_set iteration order
     // after any refill — except the first enumeration of a lineage (`root_order`, computed on the host with the real
     // container).  Writes acts[i] and raw[i] = policy[action] (expandNodeWithPolicy, parallel_mcts.cpp:705-711).

@@ -13,6 +13,8 @@
 
 namespace az {
 
+constexpr int HASH_EVAL_CHUNK = 1024;
+
 AZ_D int warp_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // Each warp owns one tree; its game state lives in the warp's slice of dynamic shared memory (G::Warp, see the
@@ -135,20 +137,27 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __res
     if (t >= T) return;
     if (wb.leaf_kind[t] != LEAF_EVAL) return;
     constexpr int A = G::ACTIONS;
-    typename G::Warp& w = warp_ws<G>(smem, A * 4);
+    constexpr int CH = A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK;      // raw values staged per chunk (chess: A = 20480)
+    typename G::Warp& w = warp_ws<G>(smem, CH * 4);
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     const int slot = wb.eval_slot[t];
     G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
     const uint64_t h = G::w_key(w, lane);
+    float sum = 0.0f;
+    for (int c0 = 0; c0 < A; c0 += CH) {
+        __syncwarp();
+        for (int i = lane; i < CH && c0 + i < A; i += 32) {
+            const uint64_t r = mix64(h + (uint64_t)(c0 + i) * 0x9E3779B97F4A7C15ULL) >> 40;
+            raw[i] = fdiv((float)(r + 1), 16777216.0f);
+        }
+        __syncwarp();
+        if (lane == 0) for (int i = 0; i < CH && c0 + i < A; ++i) sum = fadd(sum, raw[i]);      // ascending action order, one lane
+    }
+    sum = __shfl_sync(0xffffffffu, sum, 0);
     for (int i = lane; i < A; i += 32) {
         const uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
-        raw[i] = fdiv((float)(r + 1), 16777216.0f);
+        wb.policy[(size_t)slot * A + i] = fdiv(fdiv((float)(r + 1), 16777216.0f), sum);
     }
-    __syncwarp();
-    float sum = 0.0f;
-    if (lane == 0) for (int i = 0; i < A; ++i) sum = fadd(sum, raw[i]);
-    sum = __shfl_sync(0xffffffffu, sum, 0);
-    for (int i = lane; i < A; i += 32) wb.policy[(size_t)slot * A + i] = fdiv(raw[i], sum);
     if (lane == 0) {
         float v = fdiv((float)(mix64(h ^ 0xABCDEFULL) >> 40), 16777216.0f);
         v = fsub(fmul(v, 2.0f), 1.0f);
@@ -314,7 +323,7 @@ struct alignas(16) Sample {
     int16_t ply, action; int8_t player, z, result, pad_;
     float root_value; int32_t root_visits;
     typename G::Snapshot state;                    // position the move was chosen from
-    uint16_t visits[(G::ACTIONS + 7) / 8 * 8];    // root child visit counts by action (G::visit_index: Go's pass is the last entry)
+    uint16_t visits[(G::SAMPLE_VISITS + 7) / 8 * 8];   // root child visit counts: by action for Gomoku / Go (pass last), (action, count) pairs for chess
 };
 
 struct MoveParams {
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::S
         Sample<G>* sp_ = game_buf + (size_t)t * max_moves + mv;
         for (int i = lane; i < (int)(sizeof(sp_->visits) / 2); i += 32) sp_->visits[i] = 0;
         __syncwarp();
-        for (int i = lane; i < nc; i += 32) sp_->visits[G::visit_index(tp.act[base + f + i])] = (uint16_t)min(tp.N[base + f + i], 65535);
+        for (int i = lane; i < nc; i += 32) G::record_visit(sp_->visits, i, tp.act[base + f + i], tp.N[base + f + i]);
         if (lane == 0) {
             const int rn = tp.N[base + root];
             sp_->game_id = tp.game_id[t]; sp_->slot = t; sp_->ply = (int16_t)G::w_ply(w); sp_->action = (int16_t)action;

@@ -141,13 +141,15 @@ class Engine:
         self._check(self.lib.az_engine_create(C.byref(self.cfg), C.byref(h)))
         self.h = h
         self.n_slots = self.cfg.n_slots
-        self.board = self.cfg.board_size
+        self.board = self.cfg.board_size if self.cfg.game != CHESS else 8
         self.cells = self.board * self.board
         # policy length / getActionSpaceSize: N*N for Gomoku, N*N + 1 for Go (go_state.cpp:345-347); a node has at most
         # `max_children` children (Go: pass + every cell)
         self.actions = self.cells + (1 if self.cfg.game == GO else 0)
         self.max_children = self.actions
         self.planes = 8 if self.cfg.game == GO else 11
+        if self.cfg.game == CHESS:      # action = promo << 12 | from << 6 | to (chess_state.h:117); at most 218 legal moves
+            self.actions, self.max_children, self.planes = 20480, 256, 18
 
     def _check(self, rc):
         if rc != 0:

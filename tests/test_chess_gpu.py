@@ -1,0 +1,140 @@
+"""GPU parity tests for chess (BASELINE.json configs[4]): device move generation in the reference's
+order, legality (incl. the literal isSquareAttacked quirk C5), castling / en passant / promotion, terminal rules (mate,
+stalemate, material, fifty-move, placement-only threefold), the 18 feature planes, and the batched search with the hash
+evaluator — against the oracle's chess restatement (pinned in tests/test_chess_oracle.py; the reference's own chess cannot
+run).  Bar: bit-exact."""
+import numpy as np
+import pytest
+
+import _orc
+from _orc import CHESS
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def code(frm, to, promo=0):
+    return (promo << 12) | (frm << 6) | to
+
+
+def chess_engine(n_slots, sims=100, **kw):
+    from _eng import E
+    cfg = dict(game=E.CHESS, board_size=8, n_slots=n_slots, num_simulations=sims, evaluator=E.EVAL_HASH, deterministic=1,
+               auto_restart=0, max_nodes_per_tree=(sims + 2) * 256 + 1, n_streams=1)
+    cfg.update(kw)
+    return E.Engine(**cfg)
+
+
+def _random_games(O, n_games, max_plies, seed):
+    rng = np.random.default_rng(seed)
+    games = []
+    for g in range(n_games):
+        s = O.new_state(CHESS, 8)
+        mv = []
+        for _ in range(max_plies):
+            lg = O.legal(s)
+            if len(lg) == 0 or O.state_is_terminal(s):
+                break
+            caps = [a for a in lg if O.chess_piece(s, int(a) & 63) != 0]          # prefer captures now and then: shorter, sharper games
+            a = int(rng.choice(caps)) if (caps and rng.random() < 0.3) else int(rng.choice(lg))
+            assert O.state_make_move(s, a) == 0
+            mv.append(a)
+        games.append(mv)
+    return games
+
+
+SCRIPTED = [
+    [code(53, 45), code(12, 28), code(54, 38), code(3, 39)],                                             # fool's mate
+    [code(52, 36), code(12, 28), code(62, 45), code(1, 18), code(61, 34), code(5, 26), code(60, 62), code(6, 21), code(59, 52), code(4, 6)],   # both sides castle short
+    [code(52, 36), code(8, 16), code(36, 28), code(11, 27), code(28, 19)],                               # e4 a6 e5 d5 exd6 e.p.
+    [code(62, 45), code(6, 21), code(45, 62), code(21, 6)] * 2,                                          # threefold by placement
+    [code(48, 32), code(9, 25), code(32, 25), code(8, 16), code(25, 16), code(1, 18), code(16, 8), code(0, 1), code(8, 0, 1)],     # the a-pawn walks to a8 and promotes to a queen
+]
+
+
+def test_chess_rules_kernels_match_oracle():
+    O = _orc.oracle()
+    eng = chess_engine(2, sims=4)
+    games, expect = [], []
+    for mv in _random_games(O, 10, 160, seed=3) + SCRIPTED:
+        s = O.new_state(CHESS, 8)
+        for ply in range(len(mv) + 1):
+            games.append(mv[:ply])
+            expect.append((O.legal(s), O.state_is_terminal(s), O.state_result(s), O.state_current_player(s), O.tensor(s)))
+            if ply < len(mv):
+                assert O.state_make_move(s, mv[ply]) == 0, (mv, ply)
+    assert len(games) > 500
+    r = eng.rules_replay(games)
+    n_term = 0
+    for i, (legal, term, res, pl, planes) in enumerate(expect):
+        assert r["n_legal"][i] >= 0, (i, games[i])
+        assert np.array_equal(r["legal"][i], legal), (i, len(games[i]))
+        assert r["terminal"][i] == term and r["result"][i] == res and r["player"][i] == pl, (i, len(games[i]))
+        assert np.array_equal(r["planes"][i], planes), (i, len(games[i]))
+        n_term += int(term)
+    assert n_term >= 2
+    # illegal moves are reported, not applied (the reference's makeMove throws): pawn moving backwards, moving into check, out of range
+    bad = eng.rules_replay([[code(48, 56)], [code(52, 36), code(12, 28), code(60, 52), code(3, 39), code(53, 45)], [20480], [-1]])
+    exp = []
+    for c in ([code(48, 56)], [code(52, 36), code(12, 28), code(60, 52), code(3, 39), code(53, 45)], [20480], [-1]):
+        s = O.new_state(CHESS, 8)
+        exp.append(any(O.state_make_move(s, a) != 0 for a in c))
+    assert [int(n) == -1 for n in bad["n_legal"]] == exp and exp[0] and exp[2] and exp[3]
+    eng.close()
+
+
+def test_chess_search_matches_oracle():
+    """Batched search on chess positions (start position, an open middlegame, a position with castling / e.p. rights) against
+    the oracle's serial search with the same hash evaluator over the 20480-entry action space: child order, visit counts,
+    valueSum / prior bits, then play on for a few moves (subtree reuse)."""
+    O = _orc.oracle()
+    sims = 120
+    roots = [[], SCRIPTED[1][:6], SCRIPTED[2][:4], _random_games(O, 1, 40, seed=9)[0]]
+    eng = chess_engine(len(roots), sims=sims)
+    searches = []
+    for t, mv in enumerate(roots):
+        s = O.new_state(CHESS, 8)
+        for a in mv:
+            assert O.state_make_move(s, a) == 0
+        if O.state_is_terminal(s):
+            s = O.new_state(CHESS, 8); mv = []
+        eng.set_root(t, mv)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+    for move in range(3):
+        eng.search()
+        acts = []
+        for t in range(len(roots)):
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            assert np.array_equal(a["actions"], b["actions"]), (move, t)
+            assert np.array_equal(a["N"], b["N"]), (move, t)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, t)
+            assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0]
+            act = O.mcts_select_action(searches[t], 1, 1.0)
+            acts.append(act)
+            O.mcts_update_with_move(searches[t], act)
+        eng.advance(acts)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
+
+
+def test_chess_selfplay_auto_restart_and_noise_smoke():
+    """Throughput-mode loop on chess (Dirichlet noise, temperature sampling, auto-restart): invariants only.  Samples carry
+    (action, count) pairs in child order."""
+    sims, T = 24, 32
+    eng = chess_engine(T, sims=sims, deterministic=0, auto_restart=1, seed=5, sample_ring_capacity=T * 600)
+    for _ in range(40):
+        eng.play(4)
+    smp = eng.drain_samples(cap=T * 600)
+    st = eng.stats()
+    assert st["moves"] == 160 * T and st["pool_overflows"] == 0 and st["samples_dropped"] == 0
+    if len(smp):
+        pairs = smp["visits"].reshape(len(smp), -1, 2)
+        assert np.all(pairs[:, :, 1].sum(1) >= sims - 1)
+        assert np.all(np.abs(smp["z"]) <= 1) and np.all(smp["result"] >= 1)
+        played = [(pairs[i, :, 0] == smp["action"][i]) & (pairs[i, :, 1] >= 1) for i in range(len(smp))]
+        assert all(p.any() for p in played)
+    eng.close()
