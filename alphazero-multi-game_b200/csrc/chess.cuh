@@ -377,7 +377,21 @@ struct Chess {
         for (int i = lane; i < n; i += 32) out[i] = w.legal[i];
         return n;
     }
-    __device__ static void w_encode(Warp&, int, const EncTarget&, int) {}      // 18 planes: the bf16 trunk takes at most 16 input planes (not built)
+    // feature planes straight into the conv trunk's input layout (bf16, 32 channels = 18 + 14 zero); row = rank * 9 + file
+    __device__ static void w_encode(Warp& w, int lane, const EncTarget& enc, int slot) {
+        const int reps = w_reps(w);
+        const size_t row0 = (size_t)enc.guard + (size_t)slot * enc.board_pitch;
+        for (int sq = lane; sq < 64; sq += 32) {
+            const size_t row = row0 + (size_t)(sq >> 3) * (N + 1) + (sq & 7);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const int pl = q * 8 + e; v[e] = __float2bfloat16_rn(pl < PLANES ? feature(w.s.c, pl, sq, reps) : 0.0f); }
+                *reinterpret_cast<uint4*>(enc.ptr + ((size_t)q * enc.p_total + row) * 8) = *reinterpret_cast<const uint4*>(v);
+            }
+        }
+    }
     __device__ static void w_planes(Warp& w, int lane, float* out) {           // fp32 [18][rank][file]
         const int reps = w_reps(w);
         for (int i = lane; i < PLANES * 64; i += 32) out[i] = feature(w.s.c, i / 64, i % 64, reps);

@@ -417,14 +417,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
 
 }  // namespace
 
-size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : Cfg<128>::SMEM; }
+size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : (cin == 32 ? Cfg<32>::SMEM : Cfg<128>::SMEM); }
 
 bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= PAIR_HALO; }
 
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) {
-    static bool attr_done[3] = {false, false, false};
+    static bool attr_done[4] = {false, false, false, false};
     cudaError_t err;
-    if (cin == 16) {
+    if (cin == 32) {     // chess stem: 18 planes padded to 32 channels
+        if (!attr_done[3]) { err = cudaFuncSetAttribute(k_conv3x3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::SMEM); if (err) return (int)err; attr_done[3] = true; }
+        k_conv3x3<32><<<grid, CONV_THREADS, Cfg<32>::SMEM, stream>>>(p);
+    } else if (cin == 16) {
         if (!attr_done[0]) { err = cudaFuncSetAttribute(k_conv3x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::SMEM); if (err) return (int)err; attr_done[0] = true; }
         k_conv3x3<16><<<grid, CONV_THREADS, Cfg<16>::SMEM, stream>>>(p);
     } else if (conv_uses_pair(cin, p.row_pitch)) {

@@ -90,6 +90,8 @@ struct NetWeights {            // device images
 // Net = one set of activation buffers (one per stream group) + a pointer to the shared weights.
 struct Net {
     int blocks = 0, C = 0, in_planes = 0, H = 0, W = 0, A = 0, PH = 0, PW = 0, feat = 0;
+    int cin_pad = 16;          // stem input channels after zero padding: 16, or 32 for chess' 18 planes
+    int p_tiles = 4;           // policy FC N tiles of 64: ceil(A / 64)
     int row_pitch = 0, board_pitch = 0, p_total = 0, max_boards = 0;
     bool loaded = false;
     NetWeights w;              // owned by group 0's Net; other groups hold a shallow copy (share())
@@ -102,18 +104,20 @@ struct Net {
     int n_sms = 148;
     unsigned long long launches = 0;
 
-    int init(int H_, int W_, int A_, int max_boards_, int channels) {
+    int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
+        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64;
+        AZ_CHECK(planes <= 32, "at most 32 input planes");
         row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
         AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
         AZ_CHECK(channels == nn::CONV_COUT, "conv trunk is built for 128 channels");
         const size_t rows = (size_t)max_boards * board_pitch;
         p_total = (int)(nn::CONV_GUARD + (rows + nn::CONV_BM - 1) / nn::CONV_BM * nn::CONV_BM + nn::CONV_GUARD);
         PH = std::min(8, H); PW = std::min(8, W); feat = 32 * PH * PW;
-        if (dev_alloc(&in16, (size_t)2 * p_total * 8)) return -1;
+        if (dev_alloc(&in16, (size_t)(cin_pad / 8) * p_total * 8)) return -1;
         if (dev_alloc(&X, (size_t)(C / 8) * p_total * 8)) return -1;
         if (dev_alloc(&Y, (size_t)(C / 8) * p_total * 8)) return -1;
-        AZ_CUDA_CHECK(cudaMemset(in16, 0, (size_t)2 * p_total * 16));
+        AZ_CUDA_CHECK(cudaMemset(in16, 0, (size_t)(cin_pad / 8) * p_total * 16));
         AZ_CUDA_CHECK(cudaMemset(X, 0, (size_t)(C / 8) * p_total * 16));
         AZ_CUDA_CHECK(cudaMemset(Y, 0, (size_t)(C / 8) * p_total * 16));
         std::vector<uint8_t> rv(p_total, 0);
@@ -144,8 +148,7 @@ struct Net {
         const Hdr* h = (const Hdr*)blob;
         AZ_CHECK(std::memcmp(h->magic, "AZW1", 4) == 0 && h->version == 1, "bad weight blob magic/version");
         AZ_CHECK(h->channels == C && h->H == H && h->W == W && h->actions == A, "weight blob does not match engine config");
-        AZ_CHECK(h->in_planes <= 16 && h->in_planes >= 1 && h->blocks >= 0, "at most 16 input planes");
-        AZ_CHECK(A <= 256, "policy FC image is built for <= 256 actions");
+        AZ_CHECK(h->in_planes <= cin_pad && h->in_planes >= 1 && h->blocks >= 0, "weight blob has more input planes than the engine's game");
         const int nb = h->blocks, ip = h->in_planes, nconv = 1 + 2 * nb;
         // tensor offsets (in floats) inside the blob
         size_t off = 0;
@@ -159,21 +162,21 @@ struct Net {
             free_weights();
             for (int l = 0; l < nconv; ++l) {
                 __nv_bfloat16* dw; float* db;
-                if (dev_alloc(&dw, nn::conv_weight_elems(l == 0 ? 16 : C)) || dev_alloc(&db, (size_t)C)) return -1;
+                if (dev_alloc(&dw, nn::conv_weight_elems(l == 0 ? cin_pad : C)) || dev_alloc(&db, (size_t)C)) return -1;
                 w.conv_w.push_back(dw); w.conv_b.push_back(db);
             }
-            if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, 256) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
-                dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(256, 3 * feat)) ||
+            if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, (size_t)p_tiles * 64) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
+                dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, 3 * feat)) ||
                 dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat))) return -1;
-            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(256, 3 * feat) * 2, st));      // rows >= A stay zero
-            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, 256 * 4, st));
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(p_tiles * 64, 3 * feat) * 2, st));      // rows >= A stay zero
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, (size_t)p_tiles * 64 * 4, st));
             w.blocks = nb; w.in_planes = ip;
         }
         if (w.blob_bytes < off * 4) { cudaFree(w.blob); w.blob = nullptr; if (dev_alloc(&w.blob, off)) return -1; w.blob_bytes = off * 4; }
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.blob, (const char*)blob + sizeof(Hdr), off * 4, cudaMemcpyHostToDevice, st));
         const float* d = w.blob;
         for (int l = 0; l < nconv; ++l) {
-            const int cin_real = l == 0 ? ip : C, cin = l == 0 ? 16 : C;
+            const int cin_real = l == 0 ? ip : C, cin = l == 0 ? cin_pad : C;
             const int n = C * cin * 9;
             k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[l], w.conv_b[l], C, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
         }
@@ -213,7 +216,7 @@ struct Net {
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
         cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1;
         cp.in = in16; cp.out = X; cp.resid = nullptr; cp.w = w.conv_w[0]; cp.bias = w.conv_b[0];
-        AZ_CHECK(nn::conv3x3_launch(cp, 16, n_sms, s) == 0, "stem conv launch failed"); ++launches;
+        AZ_CHECK(nn::conv3x3_launch(cp, cin_pad, n_sms, s) == 0, "stem conv launch failed"); ++launches;
         for (int b = 0; b < blocks; ++b) {
             cp.in = X; cp.out = Y; cp.resid = nullptr; cp.w = w.conv_w[1 + 2 * b]; cp.bias = w.conv_b[1 + 2 * b];
             AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
@@ -227,10 +230,10 @@ struct Net {
         g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
         g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
         AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
-        nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = 3 * feat; g2.n_tiles = 4; g2.n_valid = A;
+        nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = 3 * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
         g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits; g2.ldo = A;
         AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
-        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
+        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         nn::OutParams op{logits, hidden, w.vfc2_w, w.vfc2_b, policy, value, n_dev, n_fixed, A, 256};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
@@ -412,8 +415,7 @@ struct EngineT : EngineBase {
             g.tp.N += off; g.tp.W += off; g.tp.P += off; g.tp.first += off; g.tp.act += off; g.tp.nchild += off; g.tp.flags += off;
             g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
             if (c.evaluator == AZ_EVAL_RESNET) {
-                AZ_CHECK(G::PLANES <= 16 && A <= 256, "the bf16 ResNet evaluator is built for <= 16 input planes and <= 256 actions (chess, Go 19x19: hash evaluator only)");
-                if (g.net.init(G::N, G::N, A, per, c.net_channels)) return -1;
+                if (g.net.init(G::N, G::N, A, per, c.net_channels, G::PLANES)) return -1;
             }
         }
         return reset_games();
@@ -657,7 +659,7 @@ struct EngineT : EngineBase {
         for (int o = 0; o < n; o += cap) {               // group 0's buffers, `cap` boards at a time
             const int c = std::min(cap, n - o);
             AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes + (size_t)o * net.in_planes * G::CELLS, (size_t)c * net.in_planes * G::CELLS * 4, cudaMemcpyHostToDevice, g.stream));
-            AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, g.stream) == 0, "pack launch failed");
+            AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, net.cin_pad, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, g.stream) == 0, "pack launch failed");
             ++launches;
             if (net.forward(nullptr, c, g.wb.policy, g.wb.value, g.stream)) { cudaFree(dpl); return -1; }
             AZ_CUDA_CHECK(cudaMemcpyAsync(policy + (size_t)o * A, g.wb.policy, (size_t)c * A * 4, cudaMemcpyDeviceToHost, g.stream));

@@ -31,13 +31,13 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
 }
 
 // fp32 NCHW planes (host-supplied, az_engine_nn_forward) → the trunk's bf16 input layout
-__global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int Cp, int H, int W, int row_pitch, int board_pitch, int p_total, int guard) {
+__global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int cells = H * W;
     if (idx >= n * cells) return;
     const int b = idx / cells, cell = idx % cells, y = cell / W, x = cell % W;
     const size_t row = (size_t)guard + (size_t)b * board_pitch + y * row_pitch + x;
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < cin_pad; ++c) {
         const float v = c < Cp ? planes[((size_t)b * Cp + c) * cells + cell] : 0.0f;
         in[((size_t)(c >> 3) * p_total + row) * 8 + (c & 7)] = __float2bfloat16_rn(v);
     }
@@ -49,9 +49,9 @@ int policy_value_launch(const OutParams& p, int max_boards, cudaStream_t s) {
     k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
-int pack_planes_launch(const float* planes, __nv_bfloat16* in, int n, int Cp, int H, int W, int row_pitch, int board_pitch, int p_total, int guard, cudaStream_t s) {
+int pack_planes_launch(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard, cudaStream_t s) {
     const int total = n * H * W;
-    k_pack_planes<<<(total + 255) / 256, 256, 0, s>>>(planes, in, n, Cp, H, W, row_pitch, board_pitch, p_total, guard);
+    k_pack_planes<<<(total + 255) / 256, 256, 0, s>>>(planes, in, n, Cp, cin_pad, H, W, row_pitch, board_pitch, p_total, guard);
     return (int)cudaGetLastError();
 }
 

@@ -153,9 +153,9 @@ def run_reference_arm(args, rank):
 
 
 def workload_config(args, world):
-    name = "Go 9x9 (capture/ko/superko)" if args.game == "go9" else "Gomoku 15x15"
+    name = {"go9": "Go 9x9 (capture/ko/superko)", "chess": "Chess (20480-action head)"}.get(args.game, "Gomoku 15x15")
     return {"workload": f"{name} batched self-play, {args.slots} concurrent games per GPU, {args.sims} sims/move, "
-                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[{2 if args.game == 'go9' else 1}])",
+                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[{dict(go9=2, chess=4).get(args.game, 1)}])",
             "slots_per_gpu": args.slots, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s)",
             "step": "one self-play move on every slot (root expansion + sims waves + move commit)", "stream_groups": args.streams,
             "l2": "working set (node pools, 3 x 268 MB activations) >> 126 MB L2; no explicit flush"}
@@ -168,8 +168,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--game", default="gomoku15", choices=["gomoku15", "go9"],
-                    help="gomoku15 = BASELINE.json configs[1] (the headline metric); go9 = configs[2] (Go 9x9, 2048 games, 400 sims) as an extra line")
+    ap.add_argument("--game", default="gomoku15", choices=["gomoku15", "go9", "chess"],
+                    help="gomoku15 = BASELINE.json configs[1] (the headline metric); extra lines: go9 = configs[2] (Go 9x9, 2048 games, "
+                         "400 sims), chess = configs[4] (1024 games, 800 sims, 20480-action policy head)")
     ap.add_argument("--slots", type=int, default=None)
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
@@ -182,7 +183,11 @@ def main():
         BOARD, ACTIONS, PLANES = 9, 82, 8
         CONV_FLOP_PER_BOARD = 81 * 9 * 128 * 128 * 2
         NET_FLOP_PER_EVAL = 81 * 9 * 8 * 128 * 2 + 20 * CONV_FLOP_PER_BOARD + 2 * (64 * 128 * 32 * 2) + 2048 * 82 * 2 + 2048 * 256 * 2 + 512
-    args.slots = args.slots or (2048 if args.game == "go9" else 4096)
+    if args.game == "chess":
+        BOARD, ACTIONS, PLANES = 8, 20480, 18
+        CONV_FLOP_PER_BOARD = 64 * 9 * 128 * 128 * 2
+        NET_FLOP_PER_EVAL = 64 * 9 * 18 * 128 * 2 + 20 * CONV_FLOP_PER_BOARD + 2 * (64 * 128 * 32 * 2) + 2048 * 20480 * 2 + 2048 * 256 * 2 + 512
+    args.slots = args.slots or {"go9": 2048, "chess": 1024}.get(args.game, 4096)
     args.sims = args.sims or (400 if args.game == "go9" else 800)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -202,7 +207,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    eng = E.Engine(game=E.GO if args.game == "go9" else E.GOMOKU, board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
+    eng = E.Engine(game={"go9": E.GO, "chess": E.CHESS}.get(args.game, E.GOMOKU), board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
                    net_blocks=BLOCKS, net_channels=CHANNELS, deterministic=0, auto_restart=1, device=local, seed=1234 + rank,
                    n_streams=args.streams)
     model = N.make_random_model(seed=0, in_planes=PLANES, board=BOARD, actions=ACTIONS, blocks=BLOCKS, channels=CHANNELS)

@@ -138,3 +138,31 @@ def test_chess_selfplay_auto_restart_and_noise_smoke():
         played = [(pairs[i, :, 0] == smp["action"][i]) & (pairs[i, :, 1] >= 1) for i in range(len(smp))]
         assert all(p.any() for p in played)
     eng.close()
+
+
+def test_chess_selfplay_with_resnet_evaluator():
+    """Chess self-play with the tcgen05 ResNet evaluator in the loop (18 planes -> 32-channel stem, 20480-wide policy head,
+    random-init 1-block net): the wave pipeline runs, simulations are accounted for, the root priors match the fp32 network."""
+    import torch
+    from _eng import E, N
+    O = _orc.oracle()
+    sims, T = 16, 16
+    model = N.make_random_model(seed=6, blocks=1, in_planes=18, board=8, actions=20480)
+    with torch.no_grad():
+        model.p_fc.weight *= 0.2; model.v_fc1.weight *= 0.2
+    eng = E.Engine(game=E.CHESS, board_size=8, n_slots=T, evaluator=E.EVAL_RESNET, net_blocks=1, num_simulations=sims, deterministic=1,
+                   auto_restart=1, max_nodes_per_tree=(sims + 2) * 256 + 1)
+    eng.load_weights(N.export_weights(model))
+    eng.search()
+    st = eng.root_stats(3)
+    s0 = O.new_state(CHESS, 8)
+    legal = O.legal(s0)
+    assert st["actions"].tolist() == legal.tolist() and int(st["N"].sum()) == sims
+    with torch.no_grad():
+        p32 = torch.softmax(model(torch.tensor(O.tensor(s0)[None]))[0], 1).numpy()[0]
+    ref = p32[legal] / p32[legal].sum()
+    assert np.abs(st["P"] - ref).max() <= 2e-3
+    eng.play(2)
+    s = eng.stats()
+    assert s["moves"] == 2 * T and s["simulations"] == 3 * sims * T and s["pool_overflows"] == 0
+    eng.close()

@@ -86,17 +86,19 @@ def test_trunk_matches_fp32_reference_init_model():
     _check(N.make_random_model(seed=0), 300, 512, "reference-init", saturated=True)
 
 
-@pytest.mark.parametrize("game,board,planes", [(_orc.GO, 9, 8), (_orc.GO, 13, 8), (_orc.GOMOKU, 9, 11)])
+@pytest.mark.parametrize("game,board,planes", [(_orc.GO, 9, 8), (_orc.GO, 13, 8), (_orc.GOMOKU, 9, 11), (_orc.GO, 19, 8), (_orc.CHESS, 8, 18)])
 def test_trunk_matches_fp32_other_boards(game, board, planes):
-    """Go 9x9 / 13x13 (8 planes, A = N*N + 1, boards that do not fill whole 128-row MMA tiles) and Gomoku 9x9: same
-    kernels, same tolerance."""
+    """Go 9x9 / 13x13 (8 planes, A = N*N + 1, boards that do not fill whole 128-row MMA tiles), Gomoku 9x9, Go 19x19 (row
+    pitch 20: the single-CTA conv kernel, 6 policy tiles) and chess (18 planes -> 32-channel stem, 20480-wide policy head):
+    same kernels, same tolerance."""
     import torch
     from _eng import N
-    actions = board * board + (1 if game == _orc.GO else 0)
+    actions = 20480 if game == _orc.CHESS else board * board + (1 if game == _orc.GO else 0)
     m = N.make_random_model(seed=2, randomize_bn=True, blocks=3, in_planes=planes, board=board, actions=actions)
     gen = torch.Generator().manual_seed(7)                 # fixed: the heads' calibration must not depend on the global RNG
     with torch.no_grad():
-        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.1; m.v_fc2.weight *= 0.2
+        # chess: 8x8 is not pooled, so the value FC sees 4x the feature energy of a pooled 15x15 board
+        m.p_fc.weight *= 0.2; m.v_fc1.weight *= (0.05 if game == _orc.CHESS else 0.1); m.v_fc2.weight *= 0.2
         m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
         m.v_fc2.bias.copy_(0.4 * torch.rand(m.v_fc2.bias.shape, generator=gen) - 0.2)
     _check(m, 41, 64, f"game{game}-{board}x{board}", game=game, board=board)
