@@ -16,6 +16,7 @@
 
 #include "../csrc/gomoku.cuh"   // host+device rules header (hash-evaluator key for B200NeuralNetwork("hash").predict)
 #include "../csrc/go.cuh"       // host+device Go rules
+#include "../csrc/chess.cuh"    // host+device chess rules
 
 namespace az { void set_error(const std::string&) {} }   // common.cuh declares it; unused on the host side
 
@@ -37,7 +38,11 @@ std::unique_ptr<IGameState> createGameState(GameType type, int boardSize, bool v
         if (variantRules) throw GameStateException("Failed to create game state: Japanese rules are out of scope of the B200 engine");
         return std::make_unique<go::GoState>(boardSize > 0 ? boardSize : 19);       // igamestate.cpp:50-55 default 19
     }
-    throw GameStateException("Failed to create game state: game type not built into the B200 engine yet");
+    if (type == GameType::CHESS) {
+        if (variantRules) throw GameStateException("Failed to create game state: Chess960 is out of scope of the B200 engine");
+        return std::make_unique<chess::ChessState>();
+    }
+    throw GameStateException("Failed to create game state: unknown game type");
 }
 }  // namespace core
 
@@ -288,6 +293,82 @@ bool GoState::equals(const core::IGameState& o) const {
 
 }  // namespace go
 
+// ================================================================================================ chess
+namespace chess {
+
+struct ChessState::Impl { az::Chess::State s; };
+
+ChessState::ChessState(bool chess960, const std::string& fen, int) : IGameState(core::GameType::CHESS), impl_(new Impl()) {
+    if (chess960 || !fen.empty()) throw core::GameStateException("Chess960 / FEN set-up are out of scope of the B200 engine (standard initial position only)");
+    az::Chess::init(impl_->s);
+}
+ChessState::ChessState(const ChessState& o) : IGameState(core::GameType::CHESS), impl_(new Impl(*o.impl_)), move_history_(o.move_history_) {}
+ChessState::~ChessState() = default;
+std::vector<int> ChessState::getLegalMoves() const {           // chess_state.cpp:498-510 over generateLegalMoves
+    int16_t lg[az::Chess::MAX_CHILDREN]; const int n = az::Chess::host_legal(impl_->s, lg);
+    return std::vector<int>(lg, lg + n);
+}
+bool ChessState::isLegalMove(int a) const { for (int m : getLegalMoves()) if (m == a) return true; return false; }
+void ChessState::makeMove(int a) {                              // chess_state.cpp:976-979: "Illegal move attempted"
+    if (!az::Chess::host_apply(impl_->s, a)) throw core::IllegalMoveException("Illegal move attempted", a);
+    move_history_.push_back(a);
+}
+bool ChessState::undoMove() {
+    if (move_history_.empty()) return false;
+    std::vector<int> h(move_history_.begin(), move_history_.end() - 1);
+    az::Chess::init(impl_->s); move_history_.clear();
+    for (int a : h) makeMove(a);
+    return true;
+}
+static int chessResult(const az::Chess::State& s) {
+    int16_t lg[az::Chess::MAX_CHILDREN]; const int n = az::Chess::host_legal(s, lg);
+    return az::Chess::result_core(s.c, n, az::Chess::repetitions(s.c, s.hist, nullptr));
+}
+bool ChessState::isTerminal() const { return chessResult(impl_->s) != az::RES_ONGOING; }
+core::GameResult ChessState::getGameResult() const { return static_cast<core::GameResult>(chessResult(impl_->s)); }
+int ChessState::getCurrentPlayer() const { return impl_->s.c.player; }
+static std::vector<std::vector<std::vector<float>>> chessPlanes(const az::Chess::State& s, int n) {
+    std::vector<std::vector<std::vector<float>>> t(n, std::vector<std::vector<float>>(8, std::vector<float>(8, 0.0f)));
+    const int reps = az::Chess::repetitions(s.c, s.hist, nullptr);
+    for (int pl = 0; pl < n; ++pl) for (int sq = 0; sq < 64; ++sq) t[pl][sq >> 3][sq & 7] = az::Chess::feature(s.c, pl, sq, reps);
+    return t;
+}
+std::vector<std::vector<std::vector<float>>> ChessState::getTensorRepresentation() const { return chessPlanes(impl_->s, 12); }
+std::vector<std::vector<std::vector<float>>> ChessState::getEnhancedTensorRepresentation() const { return chessPlanes(impl_->s, 18); }
+uint64_t ChessState::getHash() const { return impl_->s.c.key; }
+uint64_t ChessState::hashEvaluatorKey() const { return az::Chess::key_core(impl_->s.c); }
+int ChessState::getPieceCode(int sq) const { return (sq >= 0 && sq < 64) ? impl_->s.c.b[sq] : 0; }
+bool ChessState::isInCheck() const { return az::Chess::in_check(impl_->s.c, impl_->s.c.player); }
+static std::string sqName(int sq) { return std::string(1, (char)('a' + (sq & 7))) + std::string(1, (char)('8' - (sq >> 3))); }
+std::string ChessState::actionToString(int a) const {           // chess_state.cpp:1239-1290: from + to + promotion letter
+    if (a < 0 || a >= getActionSpaceSize()) return "invalid";
+    std::string s = sqName((a >> 6) & 63) + sqName(a & 63);
+    const int pc = (a >> 12) & 7; if (pc >= 1 && pc <= 4) s += "qrbn"[pc - 1];
+    return s;
+}
+std::optional<int> ChessState::stringToAction(const std::string& s) const {
+    if (s.size() < 4) return std::nullopt;
+    auto sq = [](char f, char r) -> int { return (f < 'a' || f > 'h' || r < '1' || r > '8') ? -1 : ('8' - r) * 8 + (f - 'a'); };
+    const int from = sq(s[0], s[1]), to = sq(s[2], s[3]);
+    if (from < 0 || to < 0) return std::nullopt;
+    int pc = 0;
+    if (s.size() >= 5) { const char c = (char)std::tolower((unsigned char)s[4]); pc = c == 'q' ? 1 : c == 'r' ? 2 : c == 'b' ? 3 : c == 'n' ? 4 : 0; }
+    return (pc << 12) | (from << 6) | to;
+}
+std::string ChessState::toString() const {
+    std::ostringstream o; const char* names = ".pnbrqk";
+    for (int r = 0; r < 8; ++r) { for (int f = 0; f < 8; ++f) { const int p = impl_->s.c.b[r * 8 + f]; char c = names[p & 7]; if ((p >> 3) == 1) c = (char)std::toupper((unsigned char)c); o << c; } o << "\n"; }
+    return o.str();
+}
+bool ChessState::equals(const core::IGameState& o) const {
+    auto* c = dynamic_cast<const ChessState*>(&o);
+    if (!c) return false;
+    const auto &a = impl_->s.c, &b = c->impl_->s.c;
+    return std::memcmp(a.b, b.b, 64) == 0 && a.player == b.player && a.rights == b.rights && a.ep == b.ep;
+}
+
+}  // namespace chess
+
 // ================================================================================================ nn
 namespace nn {
 
@@ -331,6 +412,7 @@ void B200NeuralNetwork::predictBatch(const std::vector<std::reference_wrapper<co
             const auto& s = states[i].get();
             uint64_t h = 0;
             if (auto* gs_go = dynamic_cast<const go::GoState*>(&s)) h = gs_go->hashEvaluatorKey();
+            else if (auto* gs_ch = dynamic_cast<const chess::ChessState*>(&s)) h = gs_ch->hashEvaluatorKey();
             else if (s.getGameType() == core::GameType::GOMOKU && s.getBoardSize() == 15) {
                 az::Gomoku<15>::State gs; az::Gomoku<15>::init(gs);
                 for (int a : s.getMoveHistory()) az::Gomoku<15>::apply(gs, a);
@@ -532,14 +614,14 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
     if (!b) throw std::runtime_error("SelfPlayManager on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork)");
     if (useVariantRules) throw std::runtime_error("variant rules are out of scope of the B200 engine");
     running_ = true; abort_ = false; completedGames_ = 0; totalMoves_ = 0;
-    const int bs = boardSize > 0 ? boardSize : (gameType == core::GameType::GO ? 19 : 15);
+    const int bs = gameType == core::GameType::CHESS ? 8 : (boardSize > 0 ? boardSize : (gameType == core::GameType::GO ? 19 : 15));
     az_config c; az_config_default(&c);
     c.game = (int)gameType; c.board_size = bs; c.n_slots = concurrentGames_ > 0 ? concurrentGames_ : std::max(1, std::min(numGames_, 4096));
     c.num_simulations = numSimulations_; c.c_puct = mctsConfig_.cPuct > 0 ? mctsConfig_.cPuct : 1.5f; c.virtual_loss = mctsConfig_.virtualLoss;
     c.evaluator = b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET; c.net_blocks = b->blocks(); c.net_channels = b->channels();
     c.deterministic = deterministic_ ? 1 : 0; c.dirichlet_alpha = dirichletAlpha_; c.dirichlet_epsilon = dirichletEpsilon_;
     c.init_temperature = initialTemperature_; c.final_temperature = finalTemperature_; c.temperature_drop_move = temperatureDropMove_; c.auto_restart = 1;
-    c.sample_ring_capacity = c.n_slots * bs * bs * (gameType == core::GameType::GO ? 2 : 1);     // a Go game is capped at 2 N^2 moves
+    c.sample_ring_capacity = gameType == core::GameType::CHESS ? c.n_slots * 512 : c.n_slots * bs * bs * (gameType == core::GameType::GO ? 2 : 1);   // move caps: 512 / 2 N^2 / N^2
     az_engine* e = nullptr;
     check(az_engine_create(&c, &e), "az_engine_create");
     std::vector<GameRecord> done;
@@ -567,8 +649,17 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
                     uint32_t g2; int32_t s2; std::memcpy(&g2, r + L.off_game_id, 4); std::memcpy(&s2, r + L.off_slot, 4);
                     if (g2 != gid || s2 != slot) break;
                     int16_t action; float rv; std::memcpy(&action, r + L.off_action, 2); std::memcpy(&rv, r + L.off_root_value, 4); std::memcpy(&result, r + L.off_result, 1);
-                    std::vector<float> pol(A, 0.0f); float tot = 0.0f;
-                    for (int a = 0; a < A; ++a) { uint16_t v; std::memcpy(&v, r + L.off_visits + 2 * a, 2); pol[a] = (float)v; tot += pol[a]; }
+                    std::vector<float> pol; float tot = 0.0f;
+                    if (gameType == core::GameType::CHESS) {              // (action, count) pairs in child order → child-ordered distribution (the reference's own format)
+                        for (int i = 0; 2 * i + 1 < L.n_visits; ++i) {
+                            uint16_t act, v; std::memcpy(&act, r + L.off_visits + 4 * i, 2); std::memcpy(&v, r + L.off_visits + 4 * i + 2, 2);
+                            if (act == 0 && v == 0) break;
+                            pol.push_back((float)v); tot += (float)v;
+                        }
+                    } else {
+                        pol.assign(A, 0.0f);
+                        for (int a = 0; a < A; ++a) { uint16_t v; std::memcpy(&v, r + L.off_visits + 2 * a, 2); pol[a] = (float)v; tot += pol[a]; }
+                    }
                     if (tot > 0) for (auto& x : pol) x /= tot;            // action-indexed visit distribution
                     rec.addMove(action, pol, rv, ms);
                 }

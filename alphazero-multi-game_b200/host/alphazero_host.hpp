@@ -164,6 +164,46 @@ private:
 
 }  // namespace go
 
+namespace chess {
+
+// Host-side chess state (reference chess::ChessState, include/alphazero/games/chess/chess_state.h:84-406; standard chess
+// from the initial position).  Rules arithmetic is the SAME header the kernels compile (csrc/chess.cuh, host+device),
+// including the reference's literal attack test (QUIRK C5) and placement-only repetition key.
+class ChessState : public core::IGameState {
+public:
+    explicit ChessState(bool chess960 = false, const std::string& fen = "", int position_number = -1);
+    ChessState(const ChessState& o);
+    ~ChessState() override;
+    std::vector<int> getLegalMoves() const override;
+    bool isLegalMove(int action) const override;
+    void makeMove(int action) override;
+    bool undoMove() override;
+    bool isTerminal() const override;
+    core::GameResult getGameResult() const override;
+    int getCurrentPlayer() const override;
+    int getBoardSize() const override { return 8; }
+    int getActionSpaceSize() const override { return 64 * 64 * 5; }                    // chess_state.h:117
+    std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const override;        // 12 piece planes
+    std::vector<std::vector<std::vector<float>>> getEnhancedTensorRepresentation() const override;   // 18 planes
+    uint64_t getHash() const override;
+    std::unique_ptr<core::IGameState> clone() const override { return std::make_unique<ChessState>(*this); }
+    std::string actionToString(int action) const override;                             // "e2e4", "e7e8q"
+    std::optional<int> stringToAction(const std::string& s) const override;
+    std::string toString() const override;
+    bool equals(const core::IGameState& other) const override;
+    std::vector<int> getMoveHistory() const override { return move_history_; }
+    bool validate() const override { return true; }
+    int getPieceCode(int square) const;          // type | colour << 3 (0 = empty)
+    bool isInCheck() const;
+    uint64_t hashEvaluatorKey() const;
+    struct Impl;
+private:
+    std::unique_ptr<Impl> impl_;
+    std::vector<int> move_history_;
+};
+
+}  // namespace chess
+
 namespace nn {
 
 class NeuralNetwork {

@@ -71,9 +71,36 @@ def test_gomoku_state_matches_oracle_including_legal_order():
         s.makeMove(112)
     assert s.is_occupied(112) and not s.is_occupied(0) and s.get_board()[7][7] == 1
     assert s.actionToString(112) == "H8" and s.stringToAction("H8") == 112
-    with pytest.raises(RuntimeError):
-        az.createGameState(az.GameType.CHESS)
     assert az.createGameState(az.GameType.GOMOKU).getBoardSize() == 15
+
+
+def test_chess_state_matches_oracle():
+    """createGameState(CHESS): the host-side ChessState (csrc/chess.cuh compiled for the host) against the oracle's chess
+    restatement on random games: legal moves in order, terminal, result, player, 18 planes; illegal moves raise."""
+    az = _mod()
+    O = _orc.oracle()
+    rng = np.random.default_rng(21)
+    for g in range(4):
+        s = az.createGameState(az.GameType.CHESS); o = O.new_state(_orc.CHESS, 8)
+        assert s.getBoardSize() == 8 and s.getActionSpaceSize() == 20480
+        for ply in range(140):
+            lg = O.legal(o)
+            assert s.getLegalMoves() == lg.tolist(), (g, ply)
+            assert s.isTerminal() == bool(O.state_is_terminal(o)) and int(s.getGameResult()) == O.state_result(o)
+            assert s.getCurrentPlayer() == O.state_current_player(o)
+            if ply % 9 == 0:
+                assert np.array_equal(np.array(s.getEnhancedTensorRepresentation(), np.float32), O.tensor(o))
+            if s.isTerminal() or len(lg) == 0:
+                break
+            a = int(rng.choice(lg))
+            s.makeMove(a); assert O.state_make_move(o, a) == 0
+    s = az.createGameState(az.GameType.CHESS)
+    assert len(s.getLegalMoves()) == 20 and s.actionToString(s.getLegalMoves()[1]) == "a2a4" and s.stringToAction("e2e4") == (52 << 6) | 36
+    with pytest.raises(RuntimeError):
+        s.makeMove((48 << 6) | 56)                 # a pawn moving backwards
+    for mv in ("f2f3", "e7e5", "g2g4", "d8h4"):
+        s.makeMove(s.stringToAction(mv))
+    assert s.isTerminal() and int(s.getGameResult()) == 3 and s.getMoveHistory()[-1] == s.stringToAction("d8h4")      # Fool's mate: WIN_PLAYER2
 
 
 def test_go_state_matches_oracle():

@@ -98,3 +98,35 @@ def test_selfplay_manager_generate_go_games():
         assert 2 <= len(mv) <= 162 and int(g.getResult()) in (1, 2, 3)
         assert len(mv[0].policy) == 82 and abs(sum(mv[0].policy) - 1.0) < 1e-5
         assert all(-1 <= m.action < 81 for m in mv)
+
+
+def test_parallel_mcts_and_selfplay_on_chess():
+    """The reference-shaped API on chess: createGameState(CHESS) -> host ChessState, ParallelMCTS against the oracle's serial
+    search (hash evaluator), SelfPlayManager.generateGames returning child-ordered policies."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    nn = az.createNeuralNetwork("hash", az.GameType.CHESS, 8)
+    state = az.createGameState(az.GameType.CHESS, 0, False)
+    o_state = O.new_state(_orc.CHESS, 8)
+    for mv in ("e2e4", "e7e5", "g1f3"):
+        a = state.stringToAction(mv); state.makeMove(a); assert O.state_make_move(o_state, a) == 0
+    mcts = az.ParallelMCTS(state, nn, None, 1, 100, 1.5, 0.0, 3)
+    mcts.setDeterministicMode(True)
+    om = O.mcts_new(o_state, 100, 1.5, 3, 0, None, None)
+    for mv in range(2):
+        mcts.search(); O.mcts_search(om)
+        actions, visits, wsum, priors, root_n, root_w = mcts.getRootChildren()
+        b = O.root_stats(om)
+        assert actions == b["actions"].tolist() and visits == b["N"].tolist()
+        assert np.array_equal(np.array(wsum, np.float32).view(np.uint32), b["W"].view(np.uint32))
+        a = mcts.selectAction(True, 1.0)
+        assert a == O.mcts_select_action(om, 1, 1.0)
+        state.makeMove(a); mcts.updateWithMove(a); O.mcts_update_with_move(om, a)
+    mgr = az.SelfPlayManager(nn, 2, 16, 1)
+    mgr.setConcurrentGames(8)
+    games = mgr.generateGames(az.GameType.CHESS, 0, False)
+    assert len(games) == 2
+    for g in games:
+        mv = g.getMoves()
+        assert 2 <= len(mv) <= 512 and int(g.getResult()) in (1, 2, 3)
+        assert 1 <= len(mv[0].policy) <= 218 and abs(sum(mv[0].policy) - 1.0) < 1e-5
