@@ -257,12 +257,11 @@ def main():
     # one self-play move; (D2H) finished-game samples into pinned host memory + the chosen actions + the counters;
     # for N > 1 the finished-game samples are also all-gathered over NCCL (the path's only exchange step).
     h2d = len(blob)
-    gather_buf = None
     if dist is not None:
+        from alphazero_multi_game_b200 import gather as GA
         cap = 2 * args.slots
-        dev_samples = torch.zeros(cap * eng.sample_layout().record_bytes, dtype=torch.uint8, device="cuda")
-        gather_buf = torch.zeros(world * dev_samples.numel(), dtype=torch.uint8, device="cuda")
-        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        rec_bytes = eng.sample_layout().record_bytes
+        dev_samples = torch.zeros(cap * rec_bytes, dtype=torch.uint8, device="cuda")
     barrier()
     e0 = eng.stats()
     t0 = time.perf_counter()
@@ -275,9 +274,8 @@ def main():
             d2h += smp.nbytes
         else:
             n = eng.drain_samples_device(dev_samples.data_ptr(), cap)
-            dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device="cuda"))
-            dist.all_gather_into_tensor(gather_buf, dev_samples)
-            d2h += int(counts.sum().item()) * 0 + 8 * world
+            all_samples, per_rank = GA.all_gather_samples(dist, dev_samples, n, rec_bytes)     # NCCL; the path's only exchange step
+            d2h += 8 * world
         acts = eng.last_actions(); d2h += acts.nbytes
         eng.stats(); d2h += 88
     barrier()
