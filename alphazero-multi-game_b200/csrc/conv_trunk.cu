@@ -29,6 +29,35 @@ struct Cfg {
     static constexpr int SMEM = OFF_TSLOT + 16;
 };
 
+// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 → four 16-byte stores
+__device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
+                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8), b1 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bb[e];
+        if (has_res) {
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+        }
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x = v[2 * e], y = v[2 * e + 1];
+            if (relu) { x = fmaxf(x, 0.0f); y = fmaxf(y, 0.0f); }
+            if (!valid) { x = 0.0f; y = 0.0f; }
+            ob[e] = __floats2bfloat162_rn(x, y);
+        }
+        if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
+        *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
+    }
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p) {
     using C = Cfg<CIN>;
@@ -93,7 +122,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
         // Descriptors are therefore built once; inside the loop a descriptor is `base + constant` (the start-address
         // field is the low 14 bits in 16-byte units and never carries into the LBO field for addresses < 256 KB).
         constexpr uint32_t IDESC = idesc_bf16(128, C::COUT);
-        if (lane == 0) {
+        {
             const bool skip_a = (p.dbg & 8) != 0, skip_w = (p.dbg & 4) != 0;
             const uint64_t a_desc0 = smem_desc(smem_u32(sA) + CONV_HALO * 16, C::PLANE, 128);
             const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
@@ -118,73 +147,60 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                         tc_fence_after();
                         const uint64_t b_st = b_desc0 + (uint64_t)(ws * (C::W_STAGE >> 4));
                         const uint64_t a_h = a_tap + (uint64_t)(h * (C::WK / 8) * (C::PLANE >> 4));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
+                            for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-                            for (int kk = 0; kk < C::KSTEPS; ++kk) {
-                                umma_bf16(acc + mt * 128, a_h + (uint64_t)(2 * kk * (C::PLANE >> 4) + mt * 128),
-                                          b_st + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, kk == 0 ? accumulate : 1u);
+                                for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                                    umma_bf16(acc + mt * 128, a_h + (uint64_t)(2 * kk * (C::PLANE >> 4) + mt * 128),
+                                              b_st + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, kk == 0 ? accumulate : 1u);
+                                }
                             }
+                            if (!skip_w) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
+                            if (tap == 8 && h == C::STAGES_PER_TAP - 1) { if (!skip_a) umma_commit(&a_empty[as]); umma_commit(&acc_full[as]); }
                         }
+                        __syncwarp();
                         accumulate = 1;
-                        if (!skip_w) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
                     }
                 }
-                if (!skip_a) umma_commit(&a_empty[as]);
-                umma_commit(&acc_full[as]);
             }
         }
         __syncwarp();
     } else {
         // ===================== epilogue (warps 0-3) =====================
+        const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+        const size_t p_total = (size_t)p.p_total;
         uint32_t ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-            mbar_wait(&acc_full[as], ph);
-            tc_fence_after();
+            bool waited = false;
 #pragma unroll 1
             for (int mt = 0; mt < 2; ++mt) {
                 const int row = item * CONV_BM + mt * 128 + warp * 32 + lane;
                 const size_t grow = (size_t)CONV_GUARD + row;
                 const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256 + mt * 128;
-#pragma unroll 1
-                for (int c0 = 0; c0 < C::COUT; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    uint4 res[4];
-                    if (p.dbg & 2) { tmem_ld_wait(); continue; }
-                    if (p.resid != nullptr) {
+                uint4 res[16];                                    // the residual does not depend on the MMAs: fetch it first
+                if (has_res && !(p.dbg & 2)) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            res[q] = *reinterpret_cast<const uint4*>(p.resid + ((size_t)(c0 / 8 + q) * p.p_total + grow) * 8);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + sBias[c0 + q * 8 + e];
-                        if (p.resid != nullptr) {
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[q]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
-                        }
-                        uint4 o;
-                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float a = v[2 * e], b = v[2 * e + 1];
-                            if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                            if (!valid) { a = 0.0f; b = 0.0f; }
-                            ob[e] = __floats2bfloat162_rn(a, b);
-                        }
-                        *reinterpret_cast<uint4*>(p.out + ((size_t)(c0 / 8 + q) * p.p_total + grow) * 8) = o;
-                    }
+                    for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.resid + ((size_t)q * p_total + grow) * 8);
                 }
+                if (!waited) { mbar_wait(&acc_full[as], ph); tc_fence_after(); waited = true; }
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256 + mt * 128;
+                uint32_t ra[32], rb[32];                          // TMEM → registers, software-pipelined
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, rb);
+                if (!(p.dbg & 2)) pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, ra);
+                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, rb);
+                if (!(p.dbg & 2)) pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                if (mt == 1) { tc_fence_before(); mbar_arrive(&acc_empty[as]); }      // both accumulators of this stage drained
+                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
         }
     }
     tc_fence_before();
@@ -221,35 +237,6 @@ struct PairCfg {
     static constexpr int OFF_TSLOT = OFF_BARS + 16 * 8;
     static constexpr int SMEM = OFF_TSLOT + 16;                 // 231,056 B
 };
-
-// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 → four 16-byte stores
-__device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
-                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float v[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8), b1 = *reinterpret_cast<const float4*>(sBias + c0 + q * 8 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bb[e];
-        if (has_res) {
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[q]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
-        }
-        uint4 o;
-        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float x = v[2 * e], y = v[2 * e + 1];
-            if (relu) { x = fmaxf(x, 0.0f); y = fmaxf(y, 0.0f); }
-            if (!valid) { x = 0.0f; y = 0.0f; }
-            ob[e] = __floats2bfloat162_rn(x, y);
-        }
-        if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
-        *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
-    }
-}
 
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvParams p) {
     using C = PairCfg;

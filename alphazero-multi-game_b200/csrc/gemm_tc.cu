@@ -54,28 +54,36 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
     const uint32_t tmem_base = *tslot;
 
     if (warp == 4) {
-        uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int nt = item % p.n_tiles, mi = item / p.n_tiles;
-            const int unit = mi / m_tiles, mt = mi % m_tiles;
-            const size_t row0 = (size_t)unit * p.unit_rows + (size_t)mt * G_BM;
-            for (int ks = 0; ks < k_stages; ++ks, ++it) {
-                const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (lane == 0) {
+        // TMA producer (one thread).  No integer division inside the stage loop: the A plane index advances by 8 per stage and
+        // wraps at a_plane_mod (a multiple of 8), addresses are running pointers.
+        if (lane == 0) {
+            uint32_t it = 0;
+            const size_t plane_stride = (size_t)p.a_rows * 8;                 // elements between two 8-channel K planes of A
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int nt = item % p.n_tiles, mi = item / p.n_tiles;
+                const int unit = mi / m_tiles, mt = mi % m_tiles;
+                const size_t row0 = (size_t)unit * p.unit_rows + (size_t)mt * G_BM;
+                const __nv_bfloat16* a_base = p.A + row0 * 8;
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(p.B) + (size_t)nt * k_stages * G_B_STAGE;
+                int plane = 0;
+                for (int ks = 0; ks < k_stages; ++ks, ++it, b_src += G_B_STAGE) {
+                    const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], G_STAGE);
                     uint8_t* dst = smem + s * G_STAGE;
-                    for (int j = 0; j < G_BK / 8; ++j)
-                        bulk_g2s(dst + j * (G_BM * 16), p.A + ((size_t)((ks * (G_BK / 8) + j) % p.a_plane_mod) * p.a_rows + row0) * 8, G_BM * 16, &full[s]);
-                    bulk_g2s(dst + G_A_STAGE, reinterpret_cast<const uint8_t*>(p.B) + ((size_t)nt * k_stages + ks) * G_B_STAGE, G_B_STAGE, &full[s]);
+                    const __nv_bfloat16* a_src = a_base + (size_t)plane * plane_stride;
+#pragma unroll
+                    for (int j = 0; j < G_BK / 8; ++j) bulk_g2s(dst + j * (G_BM * 16), a_src + (size_t)j * plane_stride, G_BM * 16, &full[s]);
+                    bulk_g2s(dst + G_A_STAGE, b_src, G_B_STAGE, &full[s]);
+                    plane += G_BK / 8; if (plane >= p.a_plane_mod) plane -= p.a_plane_mod;
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp == 5) {
         constexpr uint32_t IDESC = idesc_bf16(G_BM, G_BN);
-        // single-thread issue loop: descriptors are `base + constant` (see conv_trunk.cu)
-        if (lane == 0) {
+        // converged warp, tcgen05 under elect.sync, descriptors `base + constant` (see conv_trunk.cu)
+        {
             const uint64_t a_desc0 = smem_desc(smem_u32(smem), G_BM * 16, 128);
             const uint64_t b_desc0 = smem_desc(smem_u32(smem) + G_A_STAGE, G_BN * 16, 128);
             uint32_t it = 0, ait = 0;
@@ -90,16 +98,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint64_t so = (uint64_t)(s * (G_STAGE >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < G_BK / 16; ++kk)
-                        umma_bf16(acc, a_desc0 + so + (uint64_t)(2 * kk * G_BM), b_desc0 + so + (uint64_t)(2 * kk * G_BN), IDESC, kk == 0 ? accumulate : 1u);
+                        for (int kk = 0; kk < G_BK / 16; ++kk)
+                            umma_bf16(acc, a_desc0 + so + (uint64_t)(2 * kk * G_BM), b_desc0 + so + (uint64_t)(2 * kk * G_BN), IDESC, kk == 0 ? accumulate : 1u);
+                        umma_commit(&empty[s]);
+                        if (ks == k_stages - 1) umma_commit(&acc_full[as]);
+                    }
+                    __syncwarp();
                     accumulate = 1;
-                    umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[as]);
             }
         }
-        __syncwarp();
     } else {
         uint32_t ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
