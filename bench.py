@@ -296,7 +296,10 @@ def main():
     nn_ms = eng.nn_bench(args.slots, 5)
     roofline = {"bound": "tensor", "kernel": f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)", "achieved": achieved,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16",
-                "traffic": None, "launch_ms": conv_ms, "flop_per_launch": conv_flop,
+                # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
+                # layer without residual): dram__bytes_read.sum 269.9 MB + dram__bytes_write.sum 224.3 MB; algorithmic 268 + 268 MB
+                "traffic": 494.2e6 if (args.game == "gomoku15" and boards_per_launch == 4096) else None,
+                "launch_ms": conv_ms, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": NET_FLOP_PER_EVAL * args.slots / (nn_ms / 1e3) / 1e12,
                 "step_share_note": f"{20 * args.streams} of these launches per wave (20 per stream group); see profiles/ for the ncu launch list"}
 
