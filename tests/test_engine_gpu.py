@@ -181,3 +181,54 @@ def test_selfplay_auto_restart_and_noise_smoke():
     assert st["games"] >= 1 and total >= 1 and st["pool_overflows"] == 0 and st["samples_dropped"] == 0
     assert st["moves"] == 90 * T
     eng.close()
+
+
+def test_full_size_4096_slots_identical_and_golden():
+    """BASELINE.json configs[1] at full size (4096 slots, 800 simulations) with the hash evaluator in deterministic mode:
+    size-independent property — every slot plays the same game, so all 4096 trees must be bit-identical to each other and
+    slot 0 must equal the golden search generated from the reference (Gomoku 15x15 @800)."""
+    from _eng import hash_engine
+    case = json.load(open(os.path.join(GOLD, "search_hash_eval.json")))[0]
+    assert case["game"] == GOMOKU and case["board"] == 15 and case["sims"] == 800
+    T = 4096
+    eng = hash_engine(T, board=15, sims=800, n_streams=1)
+    for mv, g in enumerate(case["moves"][:3]):
+        eng.search()
+        for slot in (0, 1, 17, 2047, 2048, 4095):
+            st = eng.root_stats(slot)
+            assert st["actions"].tolist() == g["actions"] and st["N"].tolist() == g["N"], (mv, slot)
+            assert bits(st["W"]).tolist() == g["W"] and bits(st["P"]).tolist() == g["P"], (mv, slot)
+            assert st["rootN"] == g["rootN"] and int(bits([st["rootW"]])[0]) == g["rootW"]
+        eng.play(0)
+        eng.advance([g["action"]] * T)
+    st = eng.stats()
+    assert st["simulations"] == 3 * 800 * T and st["pool_overflows"] == 0 and st["moves"] == 3 * T
+    eng.close()
+
+
+def test_full_size_resnet_batch_position_independence():
+    """4096 slots with the bf16 ResNet evaluator in deterministic mode: every slot holds the same position, so the network
+    must give every board of the batch the same bits wherever it sits in the 4096-board launch (tile position, CTA pair,
+    accumulator stage), and the searches built on it must be identical across slots — at the BASELINE batch size."""
+    import torch
+    from _eng import E, N
+    T, sims = 4096, 24
+    model = N.make_random_model(seed=3, blocks=10)
+    with torch.no_grad():
+        model.p_fc.weight *= 0.03; model.v_fc1.weight *= 0.02
+    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=T, evaluator=E.EVAL_RESNET, net_blocks=10, num_simulations=sims,
+                   deterministic=1, auto_restart=0, max_nodes_per_tree=2 * (sims + 2) * 225 + 1)
+    eng.load_weights(N.export_weights(model))
+    for mv in range(2):
+        eng.search()
+        ref = eng.root_stats(0)
+        assert int(ref["N"].sum()) == sims * (mv + 1) or int(ref["N"].sum()) >= sims
+        for slot in (1, 255, 256, 1000, 2049, 4094, 4095):
+            st = eng.root_stats(slot)
+            assert np.array_equal(st["actions"], ref["actions"]) and np.array_equal(st["N"], ref["N"]), (mv, slot)
+            assert np.array_equal(bits(st["W"]), bits(ref["W"])) and np.array_equal(bits(st["P"]), bits(ref["P"])), (mv, slot)
+        eng.play(0)
+        a = int(ref["actions"][int(np.argmax(ref["N"]))])
+        eng.advance([a] * T)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
