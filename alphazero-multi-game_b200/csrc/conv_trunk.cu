@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                     if ((p.dbg & 8) && ait >= 2) continue;
                     mbar_wait(&a_empty[as], aph ^ 1);
                     mbar_arrive_expect_tx(&a_full[as], C::A_STAGE);
-                    const size_t row0 = (size_t)CONV_GUARD + (size_t)item * 256 + rank * 128 - PAIR_HALO;
+                    const int item_eff = p.reverse ? n_items - 1 - item : item;
+                    const size_t row0 = (size_t)CONV_GUARD + (size_t)item_eff * 256 + rank * 128 - PAIR_HALO;
                     for (int kc = 0; kc < 16; ++kc)
                         bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
                 }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
             uint32_t ait = 0;
             for (int item = first_item; item < n_items; item += item_step, ++ait) {
                 const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-                const int row = item * 256 + (int)rank * 128 + warp * 32 + lane;
+                const int row = (p.reverse ? n_items - 1 - item : item) * 256 + (int)rank * 128 + warp * 32 + lane;
                 const size_t grow = (size_t)CONV_GUARD + row;
                 const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
                 // the residual does not depend on the MMAs: fetch all of it before waiting for the accumulator

@@ -46,6 +46,8 @@ struct ConvParams {
     int p_total;                    // rows per channel-chunk plane
     int row_pitch;                  // W + 1
     int relu;
+    int reverse;                    // pair kernel: walk the work items from the last to the first (alternated layer by layer so a layer starts on the
+                                    // rows its predecessor wrote last, which are still in L2)
     long long* trace;               // profiling only: per-item clock64 stamps of cluster 0 (conv_bench, AZ_CONV_TRACE), else nullptr
     int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
 };

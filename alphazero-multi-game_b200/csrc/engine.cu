@@ -211,6 +211,7 @@ struct Net {
     }
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
     int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
+        static const bool alt_order = getenv("AZ_CONV_NO_ALT") == nullptr;      // profiling switch for the alternating item order
         AZ_CHECK(loaded, "no network weights loaded (az_engine_load_weights)");
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
@@ -218,9 +219,9 @@ struct Net {
         cp.in = in16; cp.out = X; cp.resid = nullptr; cp.w = w.conv_w[0]; cp.bias = w.conv_b[0];
         AZ_CHECK(nn::conv3x3_launch(cp, cin_pad, n_sms, s) == 0, "stem conv launch failed"); ++launches;
         for (int b = 0; b < blocks; ++b) {
-            cp.in = X; cp.out = Y; cp.resid = nullptr; cp.w = w.conv_w[1 + 2 * b]; cp.bias = w.conv_b[1 + 2 * b];
+            cp.in = X; cp.out = Y; cp.resid = nullptr; cp.w = w.conv_w[1 + 2 * b]; cp.bias = w.conv_b[1 + 2 * b]; cp.reverse = alt_order ? 1 : 0;
             AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
-            cp.in = Y; cp.out = X; cp.resid = X; cp.w = w.conv_w[2 + 2 * b]; cp.bias = w.conv_b[2 + 2 * b];
+            cp.in = Y; cp.out = X; cp.resid = X; cp.w = w.conv_w[2 + 2 * b]; cp.bias = w.conv_b[2 + 2 * b]; cp.reverse = 0;
             AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
         }
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
@@ -344,6 +345,7 @@ struct EngineT : EngineBase {
 
     void destroy() {
         cudaDeviceSynchronize();
+        if (wave_timing && wt_n) fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
                             (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval}) cudaFree(p);
@@ -496,22 +498,34 @@ struct EngineT : EngineBase {
     }
 
     // one wave of one group: select → evaluator → expand/backup, on the group's stream
+    // AZ_WAVE_TIMING=1 (profiling): CUDA events around select / evaluator / expand of every 64th wave, printed at destroy
+    bool wave_timing = getenv("AZ_WAVE_TIMING") != nullptr;
+    cudaEvent_t wt_ev[4] = {}; double wt_ms[3] = {0, 0, 0}; long wt_n = 0, wt_seen = 0;
     int wave(Group& g, int mode) {
         cudaStream_t st = g.stream;
+        const bool timed = wave_timing && (wt_seen++ % 64) == 63;
+        if (timed) { for (auto& e : wt_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(wt_ev[0], st); }
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
         typename G::EncTarget enc{nullptr, 0, 0, 0};
         if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch};
         k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
+        if (timed) cudaEventRecord(wt_ev[1], st);
         if (cfg.evaluator == AZ_EVAL_HASH) {
             k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
         }
+        if (timed) cudaEventRecord(wt_ev[2], st);
         k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, root_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
                                                                                     root_order_n + g.t0, sparams(), g.n, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
+        if (timed) {
+            cudaEventRecord(wt_ev[3], st); cudaEventSynchronize(wt_ev[3]);
+            for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, wt_ev[i], wt_ev[i + 1]); wt_ms[i] += ms; }
+            ++wt_n;
+        }
         return 0;
     }
 
