@@ -43,13 +43,16 @@ static int dev_alloc(T** p, size_t n) { AZ_CUDA_CHECK(cudaMalloc((void**)p, std:
 // host only uploads the blob.  scale = gamma / sqrt(var + 1e-5), shift = beta - mean * scale (bn = [gamma|beta|mean|var]).
 AZ_D float bn_scale(const float* bn, int n, int i) { return bn[i] / sqrtf(bn[3 * n + i] + 1e-5f); }
 
-__global__ void k_prep_conv(const float* __restrict__ w /*[C][cin_real][9]*/, const float* __restrict__ bn, __nv_bfloat16* img, float* bias,
-                            int C, int cin_real, int cin, int pair) {
+// One 128-output-channel x `cin`-input-channel sub-block (co0.., ci0..) of a layer whose full weight tensor is
+// w[C][cin_total][9]: the conv kernels are built for 128 output channels, wider trunks run as channel slices (Net::forward).
+__global__ void k_prep_conv(const float* __restrict__ w, const float* __restrict__ bn, __nv_bfloat16* img, float* bias,
+                            int C, int cin_total, int co0, int ci0, int cin_real, int cin, int pair) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < C) bias[idx] = bn[C + idx] - bn[2 * C + idx] * bn_scale(bn, C, idx);
-    if (idx >= C * cin * 9) return;
+    constexpr int CO = nn::CONV_COUT;
+    if (idx < CO && bias) bias[idx] = bn[C + co0 + idx] - bn[2 * C + co0 + idx] * bn_scale(bn, C, co0 + idx);
+    if (idx >= CO * cin * 9) return;
     const int t = idx % 9, ci = (idx / 9) % cin, co = idx / (9 * cin);
-    const float v = ci < cin_real ? w[((size_t)co * cin_real + ci) * 9 + t] * bn_scale(bn, C, co) : 0.0f;
+    const float v = ci < cin_real ? w[((size_t)(co0 + co) * cin_total + ci0 + ci) * 9 + t] * bn_scale(bn, C, co0 + co) : 0.0f;
     img[nn::conv_weight_index(cin, pair != 0, t, ci, co)] = __float2bfloat16(v);
 }
 // Head GEMM weight images: three-term bf16 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (K' = 3K), image = [W_hi | W_hi | W_lo]
@@ -82,6 +85,7 @@ struct NetWeights {            // device images
     std::vector<__nv_bfloat16*> conv_w;   // stem + 2*blocks
     std::vector<float*> conv_b;
     float *b1x1 = nullptr, *pfc_b = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;   // fp32 biases / tiny last layer
+    float* zero_bias = nullptr;                                                                          // [128] for the accumulating channel-slice launches
     __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
     float* blob = nullptr; size_t blob_bytes = 0;                                                        // device copy of the last AZW1 blob
     int blocks = -1, in_planes = -1;                                                                     // shape the images above were allocated for
@@ -92,6 +96,9 @@ struct Net {
     int blocks = 0, C = 0, in_planes = 0, H = 0, W = 0, A = 0, PH = 0, PW = 0, feat = 0;
     int cin_pad = 16;          // stem input channels after zero padding: 16, or 32 for chess' 18 planes
     int p_tiles = 4;           // policy FC N tiles of 64: ceil(A / 64)
+    int NS = 1;                // channel slices of 128: a C-channel layer runs as NS x NS launches of the 128 -> 128 kernel
+    int wi(int l, int co, int ci) const { return l == 0 ? co : NS + (l - 1) * NS * NS + co * NS + ci; }   // weight image index
+    int bi(int l, int co) const { return l * NS + co; }
     int row_pitch = 0, board_pitch = 0, p_total = 0, max_boards = 0;
     bool loaded = false;
     NetWeights w;              // owned by group 0's Net; other groups hold a shallow copy (share())
@@ -110,7 +117,8 @@ struct Net {
         AZ_CHECK(planes <= 32, "at most 32 input planes");
         row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
         AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
-        AZ_CHECK(channels == nn::CONV_COUT, "conv trunk is built for 128 channels");
+        AZ_CHECK(channels == 128 || channels == 256, "conv trunk is built for 128 or 256 channels");
+        NS = channels / nn::CONV_COUT;
         const size_t rows = (size_t)max_boards * board_pitch;
         p_total = (int)(nn::CONV_GUARD + (rows + nn::CONV_BM - 1) / nn::CONV_BM * nn::CONV_BM + nn::CONV_GUARD);
         PH = std::min(8, H); PW = std::min(8, W); feat = 32 * PH * PW;
@@ -161,10 +169,11 @@ struct Net {
         if (w.blocks != nb || w.in_planes != ip) {          // (re)allocate the images for this shape
             free_weights();
             for (int l = 0; l < nconv; ++l) {
-                __nv_bfloat16* dw; float* db;
-                if (dev_alloc(&dw, nn::conv_weight_elems(l == 0 ? cin_pad : C)) || dev_alloc(&db, (size_t)C)) return -1;
-                w.conv_w.push_back(dw); w.conv_b.push_back(db);
+                for (int k = 0; k < (l == 0 ? NS : NS * NS); ++k) { __nv_bfloat16* dw; if (dev_alloc(&dw, nn::conv_weight_elems(l == 0 ? cin_pad : nn::CONV_COUT))) return -1; w.conv_w.push_back(dw); }
+                for (int k = 0; k < NS; ++k) { float* db; if (dev_alloc(&db, (size_t)nn::CONV_COUT)) return -1; w.conv_b.push_back(db); }
             }
+            if (dev_alloc(&w.zero_bias, (size_t)nn::CONV_COUT)) return -1;
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.zero_bias, 0, nn::CONV_COUT * 4, st));
             if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, (size_t)p_tiles * 64) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
                 dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, 3 * feat)) ||
                 dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat))) return -1;
@@ -176,9 +185,12 @@ struct Net {
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.blob, (const char*)blob + sizeof(Hdr), off * 4, cudaMemcpyHostToDevice, st));
         const float* d = w.blob;
         for (int l = 0; l < nconv; ++l) {
-            const int cin_real = l == 0 ? ip : C, cin = l == 0 ? cin_pad : C;
-            const int n = C * cin * 9;
-            k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[l], w.conv_b[l], C, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
+            const int cin_total = l == 0 ? ip : C, cin = l == 0 ? cin_pad : nn::CONV_COUT, cin_real = l == 0 ? ip : nn::CONV_COUT;
+            const int n = nn::CONV_COUT * cin * 9;
+            for (int co = 0; co < NS; ++co)
+                for (int ci = 0; ci < (l == 0 ? 1 : NS); ++ci)
+                    k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[wi(l, co, ci)], ci == 0 ? w.conv_b[bi(l, co)] : nullptr, C, cin_total,
+                                                                 co * nn::CONV_COUT, ci * nn::CONV_COUT, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
         }
         k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C);
         k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat);
@@ -189,7 +201,7 @@ struct Net {
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc2_w, d + v2w, 256 * 4, cudaMemcpyDeviceToDevice, st));
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc2_b, d + v2b, 4, cudaMemcpyDeviceToDevice, st));
         AZ_CUDA_CHECK(cudaStreamSynchronize(st));            // the caller's blob may go away after this call returns
-        launches += nconv + 3;
+        launches += (size_t)NS + (size_t)(nconv - 1) * NS * NS + 3;
         blocks = nb; in_planes = ip;
         loaded = true;
         return 0;
@@ -200,7 +212,7 @@ struct Net {
         for (auto p : w.conv_w) cudaFree(p);
         for (auto p : w.conv_b) cudaFree(p);
         w.conv_w.clear(); w.conv_b.clear();
-        for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b, &w.blob}) { cudaFree(*p); *p = nullptr; }
+        for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b, &w.blob, &w.zero_bias}) { cudaFree(*p); *p = nullptr; }
         w.blob_bytes = 0; w.blocks = -1; w.in_planes = -1;
         for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img}) { cudaFree(*p); *p = nullptr; }
         loaded = false;
@@ -216,14 +228,30 @@ struct Net {
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
         cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1;
-        cp.in = in16; cp.out = X; cp.resid = nullptr; cp.w = w.conv_w[0]; cp.bias = w.conv_b[0];
-        AZ_CHECK(nn::conv3x3_launch(cp, cin_pad, n_sms, s) == 0, "stem conv launch failed"); ++launches;
-        for (int b = 0; b < blocks; ++b) {
-            cp.in = X; cp.out = Y; cp.resid = nullptr; cp.w = w.conv_w[1 + 2 * b]; cp.bias = w.conv_b[1 + 2 * b]; cp.reverse = alt_order ? 1 : 0;
-            AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
-            cp.in = Y; cp.out = X; cp.resid = X; cp.w = w.conv_w[2 + 2 * b]; cp.bias = w.conv_b[2 + 2 * b]; cp.reverse = 0;
-            AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
+        const size_t slice = (size_t)(nn::CONV_COUT / 8) * p_total * 8;          // elements per 128-channel slice of an activation buffer
+        for (int co = 0; co < NS; ++co) {                                         // stem: one launch per 128 output channels
+            cp.in = in16; cp.out = X + co * slice; cp.resid = nullptr; cp.w = w.conv_w[wi(0, co, 0)]; cp.bias = w.conv_b[bi(0, co)];
+            AZ_CHECK(nn::conv3x3_launch(cp, cin_pad, n_sms, s) == 0, "stem conv launch failed"); ++launches;
         }
+        // A C -> C layer = NS x NS launches of the 128 -> 128 kernel: output slice co accumulates over the input slices, the first
+        // launch adds bias (+ the block's skip connection), the following ones add the partial sum through the residual path (in
+        // place: a thread re-reads only the rows it writes), ReLU on the last.  NS = 1 is the plain single launch.
+        auto layer = [&](const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* skip, int l, int reverse) -> int {
+            for (int co = 0; co < NS; ++co)
+                for (int ci = 0; ci < NS; ++ci) {
+                    cp.in = in + ci * slice; cp.out = out + co * slice;
+                    cp.w = w.conv_w[wi(l, co, ci)]; cp.bias = ci == 0 ? w.conv_b[bi(l, co)] : w.zero_bias;
+                    cp.resid = ci == 0 ? (skip ? skip + co * slice : nullptr) : cp.out;
+                    cp.relu = ci == NS - 1 ? 1 : 0; cp.reverse = NS == 1 ? reverse : 0;
+                    AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
+                }
+            return 0;
+        };
+        for (int b = 0; b < blocks; ++b) {
+            if (layer(X, Y, nullptr, 1 + 2 * b, alt_order ? 1 : 0)) return -1;
+            if (layer(Y, X, X, 2 + 2 * b, 0)) return -1;
+        }
+        cp.relu = 1; cp.reverse = 0;
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
         nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
         AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
@@ -717,7 +745,7 @@ struct EngineT : EngineBase {
         nn::ConvParams cp{};
         cp.rowvalid = net.rowvalid; cp.n_boards_dev = nullptr; cp.n_rows = n_boards * net.board_pitch; cp.board_pitch = net.board_pitch;
         cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
-        cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[1]; cp.bias = net.w.conv_b[1];
+        cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[net.wi(1, 0, 0)]; cp.bias = net.w.conv_b[net.bi(1, 0)];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
         long long* trace = nullptr;
         if (getenv("AZ_CONV_TRACE")) { if (dev_alloc(&trace, 2048)) return -1; AZ_CUDA_CHECK(cudaMemset(trace, 0, 2048 * 8)); cp.trace = trace; }

@@ -153,9 +153,9 @@ def run_reference_arm(args, rank):
 
 
 def workload_config(args, world):
-    name = {"go9": "Go 9x9 (capture/ko/superko)", "chess": "Chess (20480-action head)"}.get(args.game, "Gomoku 15x15")
+    name = {"go9": "Go 9x9 (capture/ko/superko)", "go19": "Go 19x19", "chess": "Chess (20480-action head)"}.get(args.game, "Gomoku 15x15")
     return {"workload": f"{name} batched self-play, {args.slots} concurrent games per GPU, {args.sims} sims/move, "
-                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[{dict(go9=2, chess=4).get(args.game, 1)}])",
+                        f"{BLOCKS}-block {CHANNELS}-ch random-init ResNet (BASELINE.json configs[{dict(go9=2, go19=3, chess=4).get(args.game, 1)}])",
             "slots_per_gpu": args.slots, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s)",
             "step": "one self-play move on every slot (root expansion + sims waves + move commit)", "stream_groups": args.streams,
             "l2": "working set (node pools, 3 x 268 MB activations) >> 126 MB L2; no explicit flush"}
@@ -168,9 +168,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--game", default="gomoku15", choices=["gomoku15", "go9", "chess"],
+    ap.add_argument("--game", default="gomoku15", choices=["gomoku15", "go9", "go19", "chess"],
                     help="gomoku15 = BASELINE.json configs[1] (the headline metric); extra lines: go9 = configs[2] (Go 9x9, 2048 games, "
-                         "400 sims), chess = configs[4] (1024 games, 800 sims, 20480-action policy head)")
+                         "400 sims), go19 = configs[3] per GPU (Go 19x19, 20-block 256-ch, 1024 games), chess = configs[4] (1024 games, 800 sims, 20480-action policy head)")
     ap.add_argument("--slots", type=int, default=None)
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
@@ -178,17 +178,21 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global BOARD, ACTIONS, PLANES, CONV_FLOP_PER_BOARD, NET_FLOP_PER_EVAL
+    global BOARD, ACTIONS, PLANES, BLOCKS, CHANNELS, CONV_FLOP_PER_BOARD, NET_FLOP_PER_EVAL
     if args.game == "go9":
         BOARD, ACTIONS, PLANES = 9, 82, 8
         CONV_FLOP_PER_BOARD = 81 * 9 * 128 * 128 * 2
         NET_FLOP_PER_EVAL = 81 * 9 * 8 * 128 * 2 + 20 * CONV_FLOP_PER_BOARD + 2 * (64 * 128 * 32 * 2) + 2048 * 82 * 2 + 2048 * 256 * 2 + 512
+    if args.game == "go19":
+        BOARD, ACTIONS, PLANES, BLOCKS, CHANNELS = 19, 362, 8, 20, 256
+        CONV_FLOP_PER_BOARD = 361 * 9 * 128 * 128 * 2                      # one 128 -> 128 slice launch; a 256 -> 256 layer is 4 of them
+        NET_FLOP_PER_EVAL = 361 * 9 * 8 * 256 * 2 + 40 * 4 * CONV_FLOP_PER_BOARD + 2 * (64 * 256 * 32 * 2) + 2048 * 362 * 2 + 2048 * 256 * 2 + 512
     if args.game == "chess":
         BOARD, ACTIONS, PLANES = 8, 20480, 18
         CONV_FLOP_PER_BOARD = 64 * 9 * 128 * 128 * 2
         NET_FLOP_PER_EVAL = 64 * 9 * 18 * 128 * 2 + 20 * CONV_FLOP_PER_BOARD + 2 * (64 * 128 * 32 * 2) + 2048 * 20480 * 2 + 2048 * 256 * 2 + 512
-    args.slots = args.slots or {"go9": 2048, "chess": 1024}.get(args.game, 4096)
-    args.sims = args.sims or (400 if args.game == "go9" else 800)
+    args.slots = args.slots or {"go9": 2048, "chess": 1024, "go19": 1024}.get(args.game, 4096)
+    args.sims = args.sims or {"go9": 400, "go19": 400}.get(args.game, 800)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
@@ -207,7 +211,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    eng = E.Engine(game={"go9": E.GO, "chess": E.CHESS}.get(args.game, E.GOMOKU), board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
+    eng = E.Engine(game={"go9": E.GO, "go19": E.GO, "chess": E.CHESS}.get(args.game, E.GOMOKU), board_size=BOARD, n_slots=args.slots, num_simulations=args.sims, evaluator=E.EVAL_RESNET,
                    net_blocks=BLOCKS, net_channels=CHANNELS, deterministic=0, auto_restart=1, device=local, seed=1234 + rank,
                    n_streams=args.streams)
     model = N.make_random_model(seed=0, in_planes=PLANES, board=BOARD, actions=ACTIONS, blocks=BLOCKS, channels=CHANNELS)
@@ -294,7 +298,8 @@ def main():
     conv_flop = CONV_FLOP_PER_BOARD * boards_per_launch
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     nn_ms = eng.nn_bench(args.slots, 5)
-    roofline = {"bound": "tensor", "kernel": f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": (f"k_conv3x3<128> (one 128->128 slice launch over {boards_per_launch} boards, single-CTA kernel: row pitch 20 exceeds the pair kernel's halo)" if args.game == "go19" else
+                           f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)"), "achieved": achieved,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16",
                 # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
                 # layer without residual): dram__bytes_read.sum 269.9 MB + dram__bytes_write.sum 224.3 MB; algorithmic 268 + 268 MB

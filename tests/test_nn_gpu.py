@@ -28,7 +28,7 @@ def _check(model, n_pos, slots, tag, saturated=False, game=_orc.GOMOKU, board=15
     import torch.nn.functional as F
     from _eng import E, N
     eng = E.Engine(game=game, board_size=board, n_slots=slots, evaluator=E.EVAL_RESNET, net_blocks=model.blocks_n,
-                   net_channels=128, num_simulations=8, max_nodes_per_tree=4096, deterministic=1)
+                   net_channels=model.channels, num_simulations=8, max_nodes_per_tree=4096, deterministic=1)
     eng.load_weights(N.export_weights(model))
     x = _positions(n_pos, board=board, game=game)
     pol, val, logits = eng.nn_forward(x, want_logits=True)
@@ -102,3 +102,19 @@ def test_trunk_matches_fp32_other_boards(game, board, planes):
         m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
         m.v_fc2.bias.copy_(0.4 * torch.rand(m.v_fc2.bias.shape, generator=gen) - 0.2)
     _check(m, 41, 64, f"game{game}-{board}x{board}", game=game, board=board)
+
+
+@pytest.mark.parametrize("game,board,planes", [(_orc.GOMOKU, 15, 11), (_orc.GO, 19, 8)])
+def test_trunk_256_channels_matches_fp32(game, board, planes):
+    """256-channel trunk (BASELINE.json configs[3]: Go 19x19, 256 channels): every 256 -> 256 layer runs as 2 x 2 launches of
+    the 128 -> 128 kernels over channel slices, partial sums accumulated through the residual path — weight-stationary CTA
+    pairs at 15x15, the single-CTA kernel at 19x19."""
+    import torch
+    from _eng import N
+    actions = board * board + (1 if game == _orc.GO else 0)
+    m = N.make_random_model(seed=5, randomize_bn=True, blocks=2, channels=256, in_planes=planes, board=board, actions=actions)
+    gen = torch.Generator().manual_seed(13)
+    with torch.no_grad():
+        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.1; m.v_fc2.weight *= 0.2
+        m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
+    _check(m, 23, 32, f"256ch-game{game}-{board}x{board}", game=game, board=board)
