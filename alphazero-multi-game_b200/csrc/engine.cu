@@ -413,7 +413,7 @@ struct EngineT : EngineBase {
         if (dev_alloc(&root_state, T) || dev_alloc(&leaf_state, T) || dev_alloc(&root_order, (size_t)T * MC) || dev_alloc(&default_order, MC) ||
             dev_alloc(&root_order_n, T) || dev_alloc(&chosen_child, T) || dev_alloc(&chosen_action, T) || dev_alloc(&forced, T)) return -1;
         max_moves = G::MAX_GAME_MOVES;
-        ring_cap = c.sample_ring_capacity > 0 ? c.sample_ring_capacity : std::max(4 * T, 4096);
+        ring_cap = c.sample_ring_capacity > 0 ? c.sample_ring_capacity : std::max(32 * T, 4096);    // a finished game appends up to MAX_GAME_MOVES records at once
         if (dev_alloc(&game_buf, (size_t)T * max_moves) || dev_alloc(&ring, (size_t)ring_cap) || dev_alloc(&ring_count, 1)) return -1;
         AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
         if (dev_alloc(&noise_scratch, (size_t)T * MC) || dev_alloc(&dstats, 1)) return -1;

@@ -217,7 +217,7 @@ def main():
     model = N.make_random_model(seed=0, in_planes=PLANES, board=BOARD, actions=ACTIONS, blocks=BLOCKS, channels=CHANNELS)
     blob = N.export_weights(model)
     eng.load_weights(blob)
-    pinned = torch.empty(max(4 * args.slots, 4096) * eng.sample_layout().record_bytes, dtype=torch.uint8).pin_memory()
+    pinned = torch.empty(max(32 * args.slots, 4096) * eng.sample_layout().record_bytes, dtype=torch.uint8).pin_memory()   # = the engine's default sample ring
     samples_np = pinned.numpy().view(eng.sample_dtype())
 
     def barrier():
@@ -263,7 +263,7 @@ def main():
     h2d = len(blob)
     if dist is not None:
         from alphazero_multi_game_b200 import gather as GA
-        cap = 2 * args.slots
+        cap = 32 * args.slots
         rec_bytes = eng.sample_layout().record_bytes
         dev_samples = torch.zeros(cap * rec_bytes, dtype=torch.uint8, device="cuda")
     barrier()
@@ -329,7 +329,8 @@ def main():
                           "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
                           "moves_per_sec": moves / (ms_max / 1e3), "nn_evals_per_sec_rank0": evals / (ms / 1e3),
                           "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * NET_FLOP_PER_EVAL / 1e12 / pk["bf16_sustained"],
-                          "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}))
+                          "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+                          "games_finished": int(e1["games"]), "samples_dropped": int(e1["samples_dropped"]), "pool_overflows": int(e1["pool_overflows"])}))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
