@@ -46,7 +46,7 @@ struct Chess {
     };
     struct State { Core c; uint64_t hist[MAXH]; };
     struct Leaf { Core c; uint64_t extra[EXTRA]; };
-    struct Snapshot { uint8_t b[64]; int16_t ep, half, ply; int8_t player, rights; };
+    struct Snapshot { uint8_t b[64]; int16_t ep, half, ply; int8_t player, rights, reps, pad_; };   // reps: repetition count of the position (plane 17)
 
     AZ_HD static int T(uint8_t p) { return p & 7; }
     AZ_HD static int Cc(uint8_t p) { return p >> 3; }
@@ -322,7 +322,7 @@ struct Chess {
     }
     __device__ static void w_snapshot(const Warp& w, Snapshot* out, int lane) {
         for (int i = lane; i < 16; i += 32) reinterpret_cast<uint32_t*>(out->b)[i] = reinterpret_cast<const uint32_t*>(w.s.c.b)[i];
-        if (lane == 0) { out->ep = w.s.c.ep; out->half = w.s.c.half; out->ply = w.s.c.ply; out->player = w.s.c.player; out->rights = w.s.c.rights; }
+        if (lane == 0) { out->ep = w.s.c.ep; out->half = w.s.c.half; out->ply = w.s.c.ply; out->player = w.s.c.player; out->rights = w.s.c.rights; out->reps = (int8_t)repetitions(w.s.c, w.hist, w.s.extra); out->pad_ = 0; }
     }
     // legal moves of the warp's state into w.legal (reference order); pseudo-legal by lane 0, legality one move per lane
     __device__ static int w_gen_legal(Warp& w, int lane) {
@@ -397,6 +397,21 @@ struct Chess {
         for (int i = lane; i < PLANES * 64; i += 32) out[i] = feature(w.s.c, i / 64, i % 64, reps);
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
+    // training examples (az_engine_make_examples); the repetition count travels in the snapshot (w.n_legal doubles as its holder)
+    __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {
+        for (int i = lane; i < 16; i += 32) reinterpret_cast<uint32_t*>(w.s.c.b)[i] = reinterpret_cast<const uint32_t*>(g->b)[i];
+        if (lane == 0) { w.s.c.key = 0; w.s.c.ep = g->ep; w.s.c.half = g->half; w.s.c.ply = g->ply; w.s.c.hist_n = 0; w.s.c.player = g->player; w.s.c.rights = g->rights; w.s.c.n_extra = 0; w.hist = nullptr; w.hist_rw = nullptr; w.n_legal = g->reps; }
+        __syncwarp();
+    }
+    __device__ static float tensor_value(Warp& w, int c, int i, int j) { return feature(w.s.c, c, i * 8 + j, w.n_legal); }
+    __device__ static int policy_total(const uint16_t* visits, int lane) {
+        int t = 0; for (int k = lane; k < MAX_CHILDREN; k += 32) t += visits[2 * k + 1];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        return t;
+    }
+    template <class F> __device__ static void policy_for_each(const uint16_t* visits, int lane, F f) {
+        for (int k = lane; k < MAX_CHILDREN; k += 32) if (visits[2 * k] != 0 || visits[2 * k + 1] != 0) f((int)visits[2 * k], (int)visits[2 * k + 1]);
+    }
 #endif
 };
 

@@ -331,6 +331,7 @@ struct EngineBase {
     virtual int sample_layout(az_sample_layout* out) = 0;
     virtual int drain(void* buf, size_t cap, size_t* n, bool device) = 0;
     virtual int get_stats(az_stats* out) = 0;
+    virtual int make_examples(const void* samples, size_t n, int augment, float* planes, float* policy, float* value) = 0;
     virtual int sync() = 0;
     virtual int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) = 0;
     virtual int nn_bench(int n_boards, int reps, float* ms) = 0;
@@ -679,6 +680,28 @@ struct EngineT : EngineBase {
         return 0;
     }
 
+    int make_examples(const void* samples, size_t n, int augment, float* planes, float* policy, float* value) override {
+        if (n == 0) return 0;
+        AZ_CHECK(samples && planes && policy && value, "null buffer");
+        const int k = (augment && cfg.game != AZ_GAME_CHESS) ? 8 : 1;              // dataset.cpp:250-253: no augmentation for chess
+        const size_t chunk = 4096;                                                 // records per launch (bounds the staging buffers)
+        SampleT* ds; float *dp, *dq, *dv;
+        const size_t pe = (size_t)G::PLANES * G::CELLS;
+        if (dev_alloc(&ds, chunk) || dev_alloc(&dp, chunk * k * pe) || dev_alloc(&dq, chunk * k * A) || dev_alloc(&dv, chunk * k)) return -1;
+        for (size_t o = 0; o < n; o += chunk) {
+            const size_t c = std::min(chunk, n - o);
+            AZ_CUDA_CHECK(cudaMemcpyAsync(ds, (const SampleT*)samples + o, c * sizeof(SampleT), cudaMemcpyHostToDevice, stream));
+            k_make_examples<G><<<blocks_for_warps((int)(c * k)), 128, warp_ws_bytes<G>(), stream>>>(ds, (int)c, k, dp, dq, dv);
+            AZ_LAUNCH_CHECK(); ++launches;
+            AZ_CUDA_CHECK(cudaMemcpyAsync(planes + o * k * pe, dp, c * k * pe * 4, cudaMemcpyDeviceToHost, stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(policy + o * k * A, dq, c * k * A * 4, cudaMemcpyDeviceToHost, stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(value + o * k, dv, c * k * 4, cudaMemcpyDeviceToHost, stream));
+            AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+        for (void* p : {(void*)ds, (void*)dp, (void*)dq, (void*)dv}) cudaFree(p);
+        return 0;
+    }
+
     int get_stats(az_stats* o) override {
         if (sync_all()) return -1;
         Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
@@ -860,6 +883,7 @@ AZ_API int az_engine_sample_layout(az_engine* e, az_sample_layout* out) { AZ_FWD
 AZ_API int az_engine_drain_samples(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, false)); }
 AZ_API int az_engine_drain_samples_device(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, true)); }
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out) { AZ_FWD(get_stats(out)); }
+AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n, int augment, float* planes, float* policy, float* value) { AZ_FWD(make_examples(samples, n, augment, planes, policy, value)); }
 AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
 AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits) { AZ_FWD(nn_forward(planes, n, policy, value, logits)); }
 AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(nn_bench(n_boards, reps, ms)); }

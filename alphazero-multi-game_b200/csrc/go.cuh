@@ -426,6 +426,23 @@ struct Go {
         for (int i = lane; i < PLANES * CELLS; i += 32) { const int c = i / CELLS, a = i % CELLS; out[i] = feature(w.s.c, c, a % N, a / N, w.libs[a]); }
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
+    // training examples (az_engine_make_examples)
+    __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {
+        if (lane == 0) {
+            init_core(w.s.c); w.hist = nullptr; w.hist_rw = nullptr;
+            w.s.c.bb[0] = g->bb[0]; w.s.c.bb[1] = g->bb[1]; w.s.c.ko = g->ko; w.s.c.passes = g->passes; w.s.c.ply = g->ply; w.s.c.player = g->player;
+        }
+        __syncwarp();
+        w_group_libs(w, lane);
+    }
+    __device__ static float tensor_value(Warp& w, int c, int i, int j) { return feature(w.s.c, c, j, i, w.libs[i * N + j]); }     // planes are [c][y][x]
+    __device__ static int policy_total(const uint16_t* visits, int lane) {
+        int t = 0; for (int a = lane; a <= CELLS; a += 32) t += visits[a];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        return t;
+    }
+    // dense policy index: cell a, pass at N*N (the reference's action -1 has no slot in a [0, A) vector; A = N*N + 1 leaves the last free)
+    template <class F> __device__ static void policy_for_each(const uint16_t* visits, int lane, F f) { for (int a = lane; a <= CELLS; a += 32) f(a, (int)visits[a]); }
 #endif
 };
 

@@ -274,6 +274,15 @@ struct Gomoku {
         for (int i = lane; i < PLANES * CELLS; i += 32) { const int c = i / CELLS, a = i % CELLS; out[i] = feature(w.s, c, a / N, a % N); }
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key(w.s); }
+    // training examples (az_engine_make_examples): state from a sample's snapshot, plane value at tensor index [c][i][j], dense policy
+    __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) { w_load(w, g, lane); }
+    __device__ static float tensor_value(Warp& w, int c, int i, int j) { return feature(w.s, c, i, j); }
+    __device__ static int policy_total(const uint16_t* visits, int lane) {
+        int t = 0; for (int a = lane; a < CELLS; a += 32) t += visits[a];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        return t;
+    }
+    template <class F> __device__ static void policy_for_each(const uint16_t* visits, int lane, F f) { for (int a = lane; a < CELLS; a += 32) f(a, (int)visits[a]); }
 #endif
 };
 

@@ -547,4 +547,51 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
     if (auto_restart) for (int i = lane; i < default_order_n; i += 32) root_order[(size_t)t * G::MAX_CHILDREN + i] = default_order[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Training examples from sample records: Dataset::extractExamples + augmentExample (src/selfplay/dataset.cpp:64-114, 245-436).
+// One warp per (record, augmentation).  The 8 maps, in the reference's order, on tensor index (i, j) of an N x N plane:
+// identity; rot90 (j, N-1-i); rot180 (N-1-i, N-1-j); rot270 (N-1-j, i); flipH (i, N-1-j); flipH after rot90 (j, i);
+// flipH after rot180 (N-1-i, j); flipH after rot270 (N-1-j, N-1-i).  Every plane — the coordinate planes included — and the
+// first N*N policy entries move by the same map.
+AZ_D void dihedral(int aug, int n, int i, int j, int& i2, int& j2) {
+    switch (aug) {
+        case 1: i2 = j; j2 = n - 1 - i; break;
+        case 2: i2 = n - 1 - i; j2 = n - 1 - j; break;
+        case 3: i2 = n - 1 - j; j2 = i; break;
+        case 4: i2 = i; j2 = n - 1 - j; break;
+        case 5: i2 = j; j2 = i; break;
+        case 6: i2 = n - 1 - i; j2 = j; break;
+        case 7: i2 = n - 1 - j; j2 = n - 1 - i; break;
+        default: i2 = i; j2 = j;
+    }
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_make_examples(const Sample<G>* __restrict__ samples, int n, int k_aug, float* planes, float* policy, float* value) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= n * k_aug) return;
+    const int rec = wid / k_aug, aug = wid % k_aug;
+    typename G::Warp& w = warp_ws<G>(smem);
+    const Sample<G>* sm = samples + rec;
+    G::w_from_snapshot(w, &sm->state, lane);
+    constexpr int N = G::N, CELLS = N * N, A = G::ACTIONS;
+    float* pl = planes + (size_t)wid * G::PLANES * CELLS;
+    for (int idx = lane; idx < G::PLANES * CELLS; idx += 32) {
+        const int c = idx / CELLS, cell = idx % CELLS, i = cell / N, j = cell % N;
+        int i2, j2; dihedral(aug, N, i, j, i2, j2);
+        pl[(c * N + i2) * N + j2] = G::tensor_value(w, c, i, j);
+    }
+    float* po = policy + (size_t)wid * A;
+    for (int a = lane; a < A; a += 32) po[a] = 0.0f;
+    __syncwarp();
+    const int total = G::policy_total(sm->visits, lane);
+    G::policy_for_each(sm->visits, lane, [&](int a, int cnt) {
+        int a2 = a;
+        if (a < CELLS) { int i2, j2; dihedral(aug, N, a / N, a % N, i2, j2); a2 = i2 * N + j2; }
+        if (a2 < A) po[a2] = total > 0 ? fdiv((float)cnt, (float)total) : 0.0f;
+    });
+    if (lane == 0) value[wid] = (float)sm->z;
+}
+
 }  // namespace az

@@ -49,7 +49,7 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_load_weights", "az_engine_reset_games", "az_engine_set_root", "az_engine_search",
            "az_engine_root_stats", "az_engine_advance", "az_engine_play", "az_engine_add_dirichlet_noise", "az_engine_last_actions",
            "az_engine_slot_state", "az_engine_sample_layout", "az_engine_drain_samples",
-           "az_engine_drain_samples_device", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
+           "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_event_record", "az_engine_event_elapsed",
            "az_rules_replay"]
 
@@ -98,6 +98,7 @@ def load_library():
         "az_engine_sample_layout": [vp, C.POINTER(SampleLayout)],
         "az_engine_drain_samples": [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)],
         "az_engine_drain_samples_device": [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)],
+        "az_engine_make_examples": [vp, vp, C.c_size_t, C.c_int, f32p, f32p, f32p],
         "az_engine_get_stats": [vp, C.POINTER(Stats)],
         "az_engine_sync": [vp],
         "az_engine_nn_forward": [vp, f32p, C.c_int, f32p, f32p, f32p],
@@ -243,6 +244,26 @@ class Engine:
         n = C.c_size_t()
         self._check(self.lib.az_engine_drain_samples_device(self.h, C.c_void_p(dev_ptr), cap_records, C.byref(n)))
         return n.value
+
+    def make_examples(self, samples, augment=True):
+        """Dataset.extractExamples(includeAugmentations) on the device: sample records -> (planes [n*k, C, N, N], policy [n*k, A],
+        value [n*k]), k = 8 with augmentation (1 for chess)."""
+        dt = self.sample_dtype()
+        smp = np.ascontiguousarray(samples)
+        if smp.dtype != dt:          # e.g. np.concatenate re-packs a padded structured dtype: restore the engine's record layout
+            fixed = np.zeros(len(smp), dt)
+            for name in dt.names:
+                fixed[name] = smp[name]
+            smp = fixed
+        n = len(smp)
+        k = 8 if (augment and self.cfg.game != CHESS) else 1
+        planes = np.zeros((n * k, self.planes, self.board, self.board), np.float32)
+        policy = np.zeros((n * k, self.actions), np.float32)
+        value = np.zeros(n * k, np.float32)
+        if n:
+            self._check(self.lib.az_engine_make_examples(self.h, smp.ctypes.data, n, 1 if augment else 0, planes.ctypes.data,
+                                                         policy.ctypes.data, value.ctypes.data))
+        return planes, policy, value
 
     def stats(self):
         s = Stats()

@@ -121,6 +121,14 @@ AZ_API int az_engine_drain_samples(az_engine* e, void* host_buf, size_t cap_reco
 /* device-side variant for the NCCL all-gather: packs the ring into caller-provided DEVICE memory */
 AZ_API int az_engine_drain_samples_device(az_engine* e, void* dev_buf, size_t cap_records, size_t* n_records);
 
+/* Dataset::extractExamples + Dataset::augmentExample (src/selfplay/dataset.cpp:64-114, 245-436) on the device: turns drained
+ * sample records into training tensors.  Per record k = (augment && game != chess) ? 8 : 1 examples in the reference's order
+ * (original, rot90, rot180, rot270, flipH, flipH(rot90), flipH(rot180), flipH(rot270)); all planes and the first N*N policy
+ * entries are moved by the same map, entries past N*N (Go's pass) stay.  planes fp32 [n*k][C][N][N], policy fp32 [n*k][A]
+ * = visit counts / their sum by ACTION (getVisitCountDistribution at temperature 1, mcts_node.cpp:289-322; the reference
+ * stores it by child index), value fp32 [n*k] = game result seen from the player to move.  Host buffers. */
+AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n_records, int augment, float* planes, float* policy, float* value);
+
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out);
 AZ_API int az_engine_sync(az_engine* e);
 

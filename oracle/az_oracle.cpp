@@ -692,6 +692,30 @@ int orc_mcts_action_probs(void* h, float T, float* out, int cap) { auto p = ((Se
 float orc_mcts_root_value(void* h) { return ((Search*)h)->root_value(); }
 void orc_mcts_update_with_move(void* h, int a) { ((Search*)h)->update_with_move(a); }
 
+// Dataset::augmentExample (src/selfplay/dataset.cpp:245-436): the 7 extra examples in the reference's order — rot90, rot180,
+// rot270, flipH of the original, then flipH of rot90 / rot180 / rot270 — every plane and the first N*N policy entries moved
+// by the same index map, policy entries past N*N copied unchanged.  planes [C][N][N], policy [A] → out [7][...].
+static void orc_move(const float* pl, const float* po, int C, int N, int A, float* opl, float* opo, int kind) {
+    for (int a = 0; a < A; ++a) opo[a] = po[a];                               // `TrainingExample t = example;` then overwrite
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            int i2, j2;
+            if (kind == 0) { i2 = j; j2 = N - 1 - i; }                         // rot90   :264-283
+            else if (kind == 1) { i2 = N - 1 - i; j2 = N - 1 - j; }            // rot180  :286-305
+            else if (kind == 2) { i2 = N - 1 - j; j2 = i; }                    // rot270  :308-327
+            else { i2 = i; j2 = N - 1 - j; }                                   // flipH   :330-349
+            for (int p = 0; p < C; ++p) opl[(p * N + i2) * N + j2] = pl[(p * N + i) * N + j];
+            const int oi = i * N + j, ni = i2 * N + j2;
+            if (oi < A && ni < A) opo[ni] = po[oi];
+        }
+}
+void orc_augment_example(const float* planes, int C, int N, const float* policy, int A, float* out_planes, float* out_policy) {
+    const size_t ps = (size_t)C * N * N;
+    for (int k = 0; k < 3; ++k) orc_move(planes, policy, C, N, A, out_planes + k * ps, out_policy + (size_t)k * A, k);
+    orc_move(planes, policy, C, N, A, out_planes + 3 * ps, out_policy + (size_t)3 * A, 3);
+    for (int k = 0; k < 3; ++k) orc_move(out_planes + k * ps, out_policy + (size_t)k * A, C, N, A, out_planes + (4 + k) * ps, out_policy + (size_t)(4 + k) * A, 3);   // :352-433
+}
+
 // First-fill legal order of a fresh Gomoku N×N state (QUIRK G2): literally std::unordered_set<int>
 // with ascending inserts of the given empty cells.
 int orc_first_fill_order(const int* empties, int n, int* out) {

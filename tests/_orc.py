@@ -121,6 +121,9 @@ def oracle():
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libaz_oracle.so"],
                                   stdout=subprocess.DEVNULL)
         _cache["orc"] = Checker(so, "orc_")
+        ag = _cache["orc"].lib.orc_augment_example
+        ag.restype = None
+        ag.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         fn = _cache["orc"].lib.orc_first_fill_order
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -140,6 +143,15 @@ def reference():
     if "ref" not in _cache:
         _cache["ref"] = Checker(ref_path(), "ref_") if have_ref() else None
     return _cache["ref"]
+
+
+def augment_example(planes, policy):
+    """Dataset::augmentExample restatement: (planes [C,N,N], policy [A]) -> (planes [7,C,N,N], policy [7,A])."""
+    pl = np.ascontiguousarray(planes, np.float32); po = np.ascontiguousarray(policy, np.float32)
+    c, n, _ = pl.shape
+    opl = np.zeros((7, c, n, n), np.float32); opo = np.zeros((7, len(po)), np.float32)
+    oracle().lib.orc_augment_example(pl.ctypes.data, c, n, po.ctypes.data, len(po), opl.ctypes.data, opo.ctypes.data)
+    return opl, opo
 
 
 def first_fill_order(empties):

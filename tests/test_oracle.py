@@ -196,3 +196,23 @@ def test_go_known_answers():
             assert K.state_make_move(s, a) == 0
         assert K.go_stone(s, P(0, 0)) == 0 and K.go_captured(s, 1) == 1
         assert K.go_ko(s) == P(0, 0)                    # Go4: one group of one stone ⇒ ko point
+
+
+def test_augment_example_restatement_is_the_dihedral_group():
+    """Dataset::augmentExample restatement (dataset.cpp:245-436): 7 distinct images of an asymmetric plane, each a bijection of the
+    cells, policy entries moved with their cells, the entry past N*N (Go's pass) untouched, rot90 applied 4 times = identity."""
+    rng = np.random.default_rng(0)
+    n, c, a = 5, 3, 26
+    pl = rng.random((c, n, n)).astype(np.float32); po = rng.random(a).astype(np.float32)
+    opl, opo = _orc.augment_example(pl, po)
+    imgs = [pl] + [opl[k] for k in range(7)]
+    assert len({im.tobytes() for im in imgs}) == 8
+    for k in range(7):
+        assert np.array_equal(np.sort(opl[k].ravel()), np.sort(pl.ravel())) and opo[k][25] == po[25]
+        src = {float(pl[0].ravel()[i]): float(po[i]) for i in range(25)}          # the policy entry follows its cell
+        assert all(src[float(opl[k][0].ravel()[i])] == float(opo[k][i]) for i in range(25))
+    assert np.array_equal(opl[0][0], np.rot90(pl[0], -1)) and np.array_equal(opl[1][0], np.rot90(pl[0], 2)) and np.array_equal(opl[3][0], pl[0][:, ::-1])
+    r = pl
+    for _ in range(4):
+        r = _orc.augment_example(r, po)[0][0]
+    assert np.array_equal(r, pl)
