@@ -403,11 +403,192 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
     if (warp == 5) tmem_dealloc2(tmem_base, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_conv3x3_pair_wide — the same weight-stationary CTA-pair kernel for boards up to 19 wide (tap shift <= 21 rows).
+// With a 21-row halo two full activation stages no longer fit next to the resident half-layer of weights (147 KB + 2 x
+// 43.5 KB > 227 KB), so a stage is split by K: channel planes 0-7 are double-buffered (P0[2]), planes 8-15 single-buffered
+// (P1).  An item runs its 36 MMAs over planes 0-7 first (all taps), then the 36 over planes 8-15; P1 of the NEXT item is
+// loaded while that item's first half computes, P0 of the next item while the current item computes.  Same roles, barriers
+// and epilogue as k_conv3x3_pair.
+constexpr int WIDE_HALO = 21;                                   // row_pitch + 1 <= 21  (W <= 19)
+struct WideCfg {
+    static constexpr int ROWS = 128 + 2 * WIDE_HALO;            // 170
+    static constexpr int PLANE = ROWS * 16;                     // 2720 B
+    static constexpr int HALF = 8 * PLANE;                      // 21,760 B: 8 channel planes
+    static constexpr int WPLANE = 64 * 16, WTAP = 16 * WPLANE, W_BYTES = 9 * WTAP;
+    static constexpr int OFF_P0 = W_BYTES;                      // [2][HALF]
+    static constexpr int OFF_P1 = OFF_P0 + 2 * HALF;            // [HALF]
+    static constexpr int OFF_BIAS = OFF_P1 + HALF;
+    static constexpr int OFF_BARS = OFF_BIAS + CONV_COUT * 4;
+    static constexpr int OFF_TSLOT = OFF_BARS + 16 * 8;
+    static constexpr int SMEM = OFF_TSLOT + 16;                 // 213,392 B
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const ConvParams p) {
+    using C = WideCfg;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sW = smem;
+    uint8_t* sP0 = smem + C::OFF_P0;
+    uint8_t* sP1 = smem + C::OFF_P1;
+    float* sBias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::OFF_TSLOT);
+    uint64_t* p0_full = bars;           // [2]
+    uint64_t* p0_empty = bars + 2;      // [2]
+    uint64_t* acc_full = bars + 4;      // [2]
+    uint64_t* acc_empty = bars + 6;     // [2] leader only
+    uint64_t* w_full = bars + 8;        // [1]
+    uint64_t* p1_full = bars + 9;       // [1]
+    uint64_t* p1_empty = bars + 10;     // [1]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_rows = p.n_boards_dev ? (*p.n_boards_dev) * p.board_pitch : p.n_rows;
+    const int n_items = (n_rows + 255) / 256;
+    const int first_item = (int)cluster_id_x(), item_step = (int)n_clusters_x();
+
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = rank == 0 ? 2 : 1;
+        for (int i = 0; i < 2; ++i) { mbar_init(&p0_full[i], full_count); mbar_init(&p0_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        mbar_init(w_full, full_count); mbar_init(p1_full, full_count); mbar_init(p1_empty, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < CONV_COUT; i += CONV_THREADS) sBias[i] = p.bias[i];
+    if (warp == 5) tmem_alloc2(tslot, 256);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    if (first_item < n_items) {
+        if (warp == 4) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                mbar_arrive_expect_tx(w_full, C::W_BYTES);
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * C::W_BYTES;
+                for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
+                uint32_t ait = 0;
+                for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                    const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+                    const int item_eff = p.reverse ? n_items - 1 - item : item;
+                    const size_t row0 = (size_t)CONV_GUARD + (size_t)item_eff * 256 + rank * 128 - WIDE_HALO;
+                    mbar_wait(&p0_empty[as], aph ^ 1);
+                    mbar_arrive_expect_tx(&p0_full[as], C::HALF);
+                    for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP0 + as * C::HALF + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &p0_full[as]);
+                    mbar_wait(p1_empty, (ait & 1) ^ 1);
+                    mbar_arrive_expect_tx(p1_full, C::HALF);
+                    for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP1 + kc * C::PLANE, p.in + ((size_t)(8 + kc) * p.p_total + row0) * 8, C::PLANE, p1_full);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5 && rank != 0) {
+            // ===================== relay (peer CTA) =====================
+            if (lane == 0) {
+                mbar_wait(w_full, 0);
+                mbar_arrive_cluster(w_full, 0);
+                uint32_t ait = 0;
+                for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                    const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                    mbar_wait(&p0_full[as], ph);
+                    mbar_arrive_cluster(&p0_full[as], 0);
+                    mbar_wait(p1_full, ait & 1);
+                    mbar_arrive_cluster(p1_full, 0);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5) {
+            // ===================== MMA issuer (leader CTA) =====================
+            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            const uint64_t p0_desc0 = smem_desc(smem_u32(sP0) + WIDE_HALO * 16, C::PLANE, 128);
+            const uint64_t p1_desc0 = smem_desc(smem_u32(sP1) + WIDE_HALO * 16, C::PLANE, 128);
+            const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
+            int64_t shift[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) shift[tap] = (int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));
+            mbar_wait_cluster(w_full, 0);
+            uint32_t ait = 0;
+            for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                mbar_wait2_cluster(&p0_full[as], ph, &acc_empty[as], ph ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + as * 128;
+                const uint64_t a0 = p0_desc0 + (uint64_t)(as * (C::HALF >> 4));
+                if (elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint64_t a_tap = a0 + (uint64_t)shift[tap];
+                        const uint64_t b_tap = b_desc0 + (uint64_t)(tap * (C::WTAP >> 4));
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma2_bf16(acc, a_tap + (uint64_t)(2 * kk * (C::PLANE >> 4)), b_tap + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, (kk == 0 && tap == 0) ? 0u : 1u);
+                    }
+                    umma2_commit_both(&p0_empty[as]);
+                }
+                __syncwarp();
+                mbar_wait_cluster(p1_full, ait & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint64_t a_tap = p1_desc0 + (uint64_t)shift[tap];
+                        const uint64_t b_tap = b_desc0 + (uint64_t)(tap * (C::WTAP >> 4) + 8 * (C::WPLANE >> 4));
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma2_bf16(acc, a_tap + (uint64_t)(2 * kk * (C::PLANE >> 4)), b_tap + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, 1u);
+                    }
+                    umma2_commit_both(p1_empty);
+                    umma2_commit_both(&acc_full[as]);
+                }
+                __syncwarp();
+            }
+        } else {
+            // ===================== epilogue (warps 0-3) =====================
+            const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+            const size_t p_total = (size_t)p.p_total;
+            uint32_t ait = 0;
+            for (int item = first_item; item < n_items; item += item_step, ++ait) {
+                const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                const int row = (p.reverse ? n_items - 1 - item : item) * 256 + (int)rank * 128 + warp * 32 + lane;
+                const size_t grow = (size_t)CONV_GUARD + row;
+                const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
+                uint4 res[16];
+                if (has_res) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.resid + ((size_t)q * p_total + grow) * 8);
+                }
+                mbar_wait(&acc_full[as], ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128;
+                uint32_t ra[32], rb[32];
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, rb);
+                pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, ra);
+                pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, rb);
+                pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+                pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 5) tmem_dealloc2(tmem_base, 256);
+}
+
 }  // namespace
 
 size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : (cin == 32 ? Cfg<32>::SMEM : Cfg<128>::SMEM); }
 
-bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= PAIR_HALO; }
+bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= WIDE_HALO; }     // same weight image for both pair kernels
 
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) {
     static bool attr_done[4] = {false, false, false, false};
@@ -418,6 +599,16 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
     } else if (cin == 16) {
         if (!attr_done[0]) { err = cudaFuncSetAttribute(k_conv3x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::SMEM); if (err) return (int)err; attr_done[0] = true; }
         k_conv3x3<16><<<grid, CONV_THREADS, Cfg<16>::SMEM, stream>>>(p);
+    } else if (conv_uses_pair(cin, p.row_pitch) && p.row_pitch + 1 > PAIR_HALO) {          // boards 16..19 wide: K-split stages
+        static bool wide_done = false;
+        if (!wide_done) { err = cudaFuncSetAttribute(k_conv3x3_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg::SMEM); if (err) return (int)err; wide_done = true; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = WideCfg::SMEM; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair_wide, p);
+        if (err) return (int)err;
     } else if (conv_uses_pair(cin, p.row_pitch)) {
         if (!attr_done[2]) { err = cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM); if (err) return (int)err; attr_done[2] = true; }
         cudaLaunchConfig_t cfg{};

@@ -298,7 +298,7 @@ def main():
     conv_flop = CONV_FLOP_PER_BOARD * boards_per_launch
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     nn_ms = eng.nn_bench(args.slots, 5)
-    roofline = {"bound": "tensor", "kernel": (f"k_conv3x3<128> (one 128->128 slice launch over {boards_per_launch} boards, single-CTA kernel: row pitch 20 exceeds the pair kernel's halo)" if args.game == "go19" else
+    roofline = {"bound": "tensor", "kernel": (f"k_conv3x3_pair_wide (one 128->128 slice launch over {boards_per_launch} boards; weight-stationary CTA pair with K-split activation stages for the 21-row halo)" if args.game == "go19" else
                            f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)"), "achieved": achieved,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16",
                 # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
