@@ -110,6 +110,8 @@ struct Net {
     int boards_cap = 0;
     int n_sms = 148;
     unsigned long long launches = 0;
+    // live timing of the trunk's 128 -> 128 conv launches inside production waves (every 64th forward): CUDA events on the launching stream
+    cudaEvent_t tev[2] = {nullptr, nullptr}; unsigned long long fwd_count = 0, conv_sampled = 0; double conv_ms = 0.0;
 
     int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
@@ -247,9 +249,16 @@ struct Net {
                 }
             return 0;
         };
+        const bool sample = n_dev != nullptr && blocks > 0 && (fwd_count++ % 64) == 63;
+        if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], s); }
         for (int b = 0; b < blocks; ++b) {
             if (layer(X, Y, nullptr, 1 + 2 * b, alt_order ? 1 : 0)) return -1;
             if (layer(Y, X, X, 2 + 2 * b, 0)) return -1;
+        }
+        if (sample) {
+            cudaEventRecord(tev[1], s); cudaEventSynchronize(tev[1]);
+            float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
+            conv_ms += ms; conv_sampled += (unsigned long long)(2 * blocks * NS * NS);
         }
         cp.relu = 1; cp.reverse = 0;
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
@@ -336,6 +345,7 @@ struct EngineBase {
     virtual int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) = 0;
     virtual int nn_bench(int n_boards, int reps, float* ms) = 0;
     virtual int conv_bench(int n_boards, int reps, float* ms) = 0;
+    virtual int conv_sampled(double* ms_sum, unsigned long long* launches_n) = 0;
     virtual int event_record(int idx) = 0;
     virtual int event_elapsed(int i, int j, float* ms) = 0;
     virtual int rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal, int32_t* n_legal,
@@ -794,6 +804,12 @@ struct EngineT : EngineBase {
         launches += reps + 3;
         return 0;
     }
+    int conv_sampled(double* ms_sum, unsigned long long* launches_n) override {
+        double m = 0; unsigned long long n = 0;
+        for (auto& g : groups) { m += g.net.conv_ms; n += g.net.conv_sampled; }
+        if (ms_sum) *ms_sum = m; if (launches_n) *launches_n = n;
+        return 0;
+    }
     cudaEvent_t events[8] = {};
     int event_record(int idx) override {
         AZ_CHECK(idx >= 0 && idx < 8, "event index out of range");
@@ -888,6 +904,7 @@ AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
 AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits) { AZ_FWD(nn_forward(planes, n, policy, value, logits)); }
 AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(nn_bench(n_boards, reps, ms)); }
 AZ_API int az_engine_conv_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(conv_bench(n_boards, reps, ms)); }
+AZ_API int az_engine_conv_sampled(az_engine* e, double* ms_sum, unsigned long long* launches_n) { AZ_FWD(conv_sampled(ms_sum, launches_n)); }
 AZ_API int az_engine_event_record(az_engine* e, int idx) { AZ_FWD(event_record(idx)); }
 AZ_API int az_engine_event_elapsed(az_engine* e, int i, int j, float* ms) { AZ_FWD(event_elapsed(i, j, ms)); }
 AZ_API int az_rules_replay(az_engine* e, const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal, int32_t* n_legal,

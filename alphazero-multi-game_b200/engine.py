@@ -50,7 +50,7 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_root_stats", "az_engine_advance", "az_engine_play", "az_engine_add_dirichlet_noise", "az_engine_last_actions",
            "az_engine_slot_state", "az_engine_sample_layout", "az_engine_drain_samples",
            "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
-           "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_event_record", "az_engine_event_elapsed",
+           "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_conv_sampled", "az_engine_event_record", "az_engine_event_elapsed",
            "az_rules_replay"]
 
 
@@ -104,6 +104,7 @@ def load_library():
         "az_engine_nn_forward": [vp, f32p, C.c_int, f32p, f32p, f32p],
         "az_engine_nn_bench": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "az_engine_conv_bench": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
+        "az_engine_conv_sampled": [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)],
         "az_engine_event_record": [vp, C.c_int],
         "az_engine_event_elapsed": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "az_rules_replay": [vp, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, f32p],
@@ -291,6 +292,12 @@ class Engine:
         ms = C.c_float()
         self._check(self.lib.az_engine_conv_bench(self.h, n_boards, reps, C.byref(ms)))
         return ms.value
+
+    def conv_sampled(self):
+        """(accumulated ms, launches) of the 128->128 conv launches timed live inside the waves (every 64th network pass)."""
+        ms = C.c_double(); n = C.c_ulonglong()
+        self._check(self.lib.az_engine_conv_sampled(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def event_record(self, idx):
         self._check(self.lib.az_engine_event_record(self.h, idx))

@@ -141,6 +141,9 @@ AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms_pe
 /* one 128→128-channel 3x3 conv layer (the dominant kernel) alone, `reps` launches, CUDA-event timed on the
  * engine's stream: ms per launch (roofline numerator for bench.py) */
 AZ_API int az_engine_conv_bench(az_engine* e, int n_boards, int reps, float* ms_per_launch);
+/* the same kernel timed LIVE inside production waves: every 64th network pass of az_engine_search / az_engine_play brackets its
+ * 128->128 conv launches with CUDA events on the launching stream; returns the accumulated ms and the number of launches covered */
+AZ_API int az_engine_conv_sampled(az_engine* e, double* ms_sum, unsigned long long* n_launches);
 /* CUDA events on the engine's own stream (torch.cuda.Event only sees torch's stream): record slot idx (0..7),
  * elapsed(i → j) in ms after synchronising on j */
 AZ_API int az_engine_event_record(az_engine* e, int idx);
