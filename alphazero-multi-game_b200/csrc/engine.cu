@@ -72,12 +72,15 @@ __global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restric
 }
 // FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the 1x1-conv GEMM writes
 // (cell*32 + ch); rows >= n_rows stay zero (N padded to 256)
-__global__ void k_prep_fc(const float* __restrict__ w /*[n_rows][feat]*/, __nv_bfloat16* img, int n_rows, int feat) {
+// split = 0: plain bf16 image (K' = K) for very wide heads (chess' 20480 actions: the three-term image would be 252 MB and its
+// GEMM 3x the L2 traffic; the A operand then uses only the hi planes)
+__global__ void k_prep_fc(const float* __restrict__ w /*[n_rows][feat]*/, __nv_bfloat16* img, int n_rows, int feat, int split) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n_rows * feat) return;
     const int kt = (int)(idx % feat), n = (int)(idx / feat);
     const int ch = kt / 64, cell = kt % 64;
-    put3(img, feat, n, cell * 32 + ch, w[idx]);
+    if (split) put3(img, feat, n, cell * 32 + ch, w[idx]);
+    else img[nn::gemm_weight_index(feat, n, cell * 32 + ch)] = __float2bfloat16(w[idx]);
 }
 
 // ------------------------------------------------------------------------------------------------ network
@@ -96,6 +99,7 @@ struct Net {
     int blocks = 0, C = 0, in_planes = 0, H = 0, W = 0, A = 0, PH = 0, PW = 0, feat = 0;
     int cin_pad = 16;          // stem input channels after zero padding: 16, or 32 for chess' 18 planes
     int p_tiles = 4;           // policy FC N tiles of 64: ceil(A / 64)
+    int p_split = 1;           // policy FC as the three-term hi/lo bf16 split (1) or plain bf16 (0: heads wider than 1024 actions)
     int NS = 1;                // channel slices of 128: a C-channel layer runs as NS x NS launches of the 128 -> 128 kernel
     int wi(int l, int co, int ci) const { return l == 0 ? co : NS + (l - 1) * NS * NS + co * NS + ci; }   // weight image index
     int bi(int l, int co) const { return l * NS + co; }
@@ -115,7 +119,7 @@ struct Net {
 
     int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
-        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64;
+        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64; p_split = A <= 1024 ? 1 : 0;
         AZ_CHECK(planes <= 32, "at most 32 input planes");
         row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
         AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
@@ -177,9 +181,9 @@ struct Net {
             if (dev_alloc(&w.zero_bias, (size_t)nn::CONV_COUT)) return -1;
             AZ_CUDA_CHECK(cudaMemsetAsync(w.zero_bias, 0, nn::CONV_COUT * 4, st));
             if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, (size_t)p_tiles * 64) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
-                dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, 3 * feat)) ||
+                dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat)) ||
                 dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat))) return -1;
-            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(p_tiles * 64, 3 * feat) * 2, st));      // rows >= A stay zero
+            AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat) * 2, st));      // rows >= A stay zero
             AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, (size_t)p_tiles * 64 * 4, st));
             w.blocks = nb; w.in_planes = ip;
         }
@@ -195,8 +199,8 @@ struct Net {
                                                                  co * nn::CONV_COUT, ci * nn::CONV_COUT, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
         }
         k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C);
-        k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat);
-        k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat);
+        k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat, p_split);
+        k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat, 1);
         AZ_CUDA_CHECK(cudaGetLastError());
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.pfc_b, d + pfb, (size_t)A * 4, cudaMemcpyDeviceToDevice, st));
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc1_b, d + v1b, 256 * 4, cudaMemcpyDeviceToDevice, st));
@@ -268,10 +272,10 @@ struct Net {
         g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
         g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
         AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
-        nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = 3 * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
+        nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
         g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits; g2.ldo = A;
         AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
-        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
+        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         nn::OutParams op{logits, hidden, w.vfc2_w, w.vfc2_b, policy, value, n_dev, n_fixed, A, 256};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
@@ -780,6 +784,7 @@ struct EngineT : EngineBase {
         cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[net.wi(1, 0, 0)]; cp.bias = net.w.conv_b[net.bi(1, 0)];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
+        if (getenv("AZ_CONV_RESID")) cp.resid = net.X;                    // time the residual variant (second conv of a block)
         long long* trace = nullptr;
         if (getenv("AZ_CONV_TRACE")) { if (dev_alloc(&trace, 2048)) return -1; AZ_CUDA_CHECK(cudaMemset(trace, 0, 2048 * 8)); cp.trace = trace; }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
