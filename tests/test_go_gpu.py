@@ -223,3 +223,23 @@ def test_go_selfplay_with_resnet_evaluator():
     s = eng.stats()
     assert s["moves"] == 3 * T and s["simulations"] == 4 * sims * T and s["pool_overflows"] == 0
     eng.close()
+
+
+def test_go_full_size_2048_slots_identical_and_golden():
+    """BASELINE.json configs[2] at full size (Go 9x9, 2048 slots, 400 simulations), hash evaluator, deterministic mode:
+    every slot must hold the same tree, bit-identical to the golden search generated from the reference."""
+    cases = [c for c in json.load(open(os.path.join(GOLD, "search_hash_eval.json"))) if c["game"] == GO]
+    case = cases[0]
+    assert case["board"] == 9 and case["sims"] == 400
+    T = 2048
+    eng = go_engine(T, board=9, sims=400, n_streams=1)
+    for mv, g in enumerate(case["moves"][:3]):
+        eng.search()
+        for slot in (0, 3, 1023, 1024, 2047):
+            st = eng.root_stats(slot)
+            assert st["actions"].tolist() == g["actions"] and st["N"].tolist() == g["N"], (mv, slot)
+            assert bits(st["W"]).tolist() == g["W"] and bits(st["P"]).tolist() == g["P"], (mv, slot)
+        eng.advance([g["action"]] * T)
+    st = eng.stats()
+    assert st["simulations"] == 3 * 400 * T and st["pool_overflows"] == 0
+    eng.close()
