@@ -110,7 +110,10 @@ struct Net {
     __nv_bfloat16 *in16 = nullptr, *X = nullptr, *Y = nullptr;
     uint8_t* rowvalid = nullptr;
     __nv_bfloat16 *pooled = nullptr, *featP = nullptr, *featV = nullptr;   // head GEMM operands (bf16, chunk-plane layout)
-    float *logits = nullptr, *hidden = nullptr;
+    float *logits = nullptr, *hidden = nullptr;                            // final logits [n][A]; `hidden` unused since split-K (kept for the destroy list)
+    float *logits_part = nullptr, *hidden_part = nullptr;                  // split-K partial sums of the two FC GEMMs: [FC_SPLITS][max_boards][A | 256]
+    static constexpr int FC_SPLITS = 4;
+    int p_splits = 4;                                                      // policy FC splits: 1 for very wide heads (the partial slabs would cost more than they save)
     int boards_cap = 0;
     int n_sms = 148;
     unsigned long long launches = 0;
@@ -119,7 +122,7 @@ struct Net {
 
     int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
-        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64; p_split = A <= 1024 ? 1 : 0;
+        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64; p_split = A <= 1024 ? 1 : 0; p_splits = A <= 1024 ? FC_SPLITS : 1;
         AZ_CHECK(planes <= 32, "at most 32 input planes");
         row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
         AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
@@ -147,6 +150,7 @@ struct Net {
         AZ_CUDA_CHECK(cudaMemset(featP, 0, (size_t)512 * boards_cap * 16));
         AZ_CUDA_CHECK(cudaMemset(featV, 0, (size_t)512 * boards_cap * 16));
         if (dev_alloc(&logits, (size_t)max_boards * A)) return -1;
+        if (dev_alloc(&logits_part, (size_t)p_splits * max_boards * A) || dev_alloc(&hidden_part, (size_t)FC_SPLITS * max_boards * 256)) return -1;
         if (dev_alloc(&hidden, (size_t)max_boards * 256)) return -1;
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -225,7 +229,7 @@ struct Net {
     }
     void destroy() {
         free_weights();
-        for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)pooled, (void*)featP, (void*)featV, (void*)logits, (void*)hidden}) cudaFree(p);
+        for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)pooled, (void*)featP, (void*)featV, (void*)logits, (void*)hidden, (void*)logits_part, (void*)hidden_part}) cudaFree(p);
     }
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
     int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
@@ -272,12 +276,16 @@ struct Net {
         g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
         g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
         AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
+        // the two FC GEMMs run split-K (FC_SPLITS x more work items: a 4096 x 256 x 6144 GEMM is only 128 tiles); the raw partial
+        // sums are added, with bias / ReLU, by k_policy_value
         nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
-        g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits; g2.ldo = A;
+        g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits_part; g2.ldo = A;
+        g2.k_splits = p_splits; g2.split_stride = (size_t)max_boards * A;
         AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
-        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden; g3.ldo = 256;
+        nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden_part; g3.ldo = 256;
+        g3.k_splits = FC_SPLITS; g3.split_stride = (size_t)max_boards * 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
-        nn::OutParams op{logits, hidden, w.vfc2_w, w.vfc2_b, policy, value, n_dev, n_fixed, A, 256};
+        nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * A, (size_t)max_boards * 256, p_splits, FC_SPLITS, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
         return 0;
     }

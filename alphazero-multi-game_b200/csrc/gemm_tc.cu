@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
     // work decomposition: `units` row groups (GEMM1: the 64 pooled cells; FC: 1), each with m_tiles tiles of 128 rows
     const int m_valid = p.m_valid_dev ? *p.m_valid_dev : p.m_valid;            // valid rows inside one unit
     const int m_tiles = (m_valid + G_BM - 1) / G_BM;
-    const int n_items = p.units * m_tiles * p.n_tiles;
-    const int k_stages = p.K / G_BK;
+    const int KS = p.k_splits > 1 ? p.k_splits : 1;          // split-K: an item covers k_stages consecutive K stages of one output tile
+    const int n_items = p.units * m_tiles * p.n_tiles * KS;
+    const int k_stages_total = p.K / G_BK, k_stages = k_stages_total / KS;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < G_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -60,12 +61,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
             uint32_t it = 0;
             const size_t plane_stride = (size_t)p.a_rows * 8;                 // elements between two 8-channel K planes of A
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int nt = item % p.n_tiles, mi = item / p.n_tiles;
+                const int split = item % KS, tile = item / KS;
+                const int nt = tile % p.n_tiles, mi = tile / p.n_tiles;
                 const int unit = mi / m_tiles, mt = mi % m_tiles;
                 const size_t row0 = (size_t)unit * p.unit_rows + (size_t)mt * G_BM;
                 const __nv_bfloat16* a_base = p.A + row0 * 8;
-                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(p.B) + (size_t)nt * k_stages * G_B_STAGE;
-                int plane = 0;
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(p.B) + ((size_t)nt * k_stages_total + (size_t)split * k_stages) * G_B_STAGE;
+                int plane = (split * k_stages * (G_BK / 8)) % p.a_plane_mod;
                 for (int ks = 0; ks < k_stages; ++ks, ++it, b_src += G_B_STAGE) {
                     const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
         uint32_t ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
-            const int nt = item % p.n_tiles, mi = item / p.n_tiles;
+            const int split = item % KS, tile = item / KS;
+            const int nt = tile % p.n_tiles, mi = tile / p.n_tiles;
             const int unit = mi / m_tiles, mt = mi % m_tiles;
             const int r = mt * G_BM + warp * 32 + lane;          // row inside the unit
             mbar_wait(&acc_full[as], aph);
@@ -148,13 +151,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
                             *reinterpret_cast<uint4*>(dst + ((size_t)(p.feat_lo_plane + unit * 4 + q) * p.feat_rows + r) * 8) = ol;
                         }
                     } else {
-                        float* dst = p.out_rows + (size_t)r * p.ldo;
+                        // split-K: raw partial sums into slab `split` (bias / ReLU are applied by the consumer, k_policy_value)
+                        float* dst = p.out_rows + (size_t)split * p.split_stride + (size_t)r * p.ldo;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n = nt * G_BN + c0 + j;
                             if (n < p.n_valid) {
-                                float a = __uint_as_float(v[j]) + p.bias[n];
-                                if (p.relu) a = fmaxf(a, 0.0f);
+                                float a = __uint_as_float(v[j]);
+                                if (p.k_splits < 1) { a += p.bias[n]; if (p.relu) a = fmaxf(a, 0.0f); }      // k_splits >= 1: raw sums, the consumer adds bias / ReLU
                                 dst[n] = a;
                             }
                         }

@@ -27,6 +27,9 @@ struct GemmParams {
     __nv_bfloat16* out_feat0; __nv_bfloat16* out_feat1; int feat_rows; int feat_lo_plane;
     // GEMM_OUT_ROWS: fp32 row-major out[row][ldo]
     float* out_rows; int ldo;
+    // split-K (GEMM_OUT_ROWS only): k_splits >= 1 → item = (tile, split), RAW partial sums (no bias / ReLU) go to out_rows + split * split_stride;
+    // 0 = classic epilogue
+    int k_splits; size_t split_stride;
 };
 
 struct PoolParams {

@@ -15,9 +15,14 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
     const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= nb) return;
-    const float* lg = p.logits + (size_t)b * p.A;
+    // logits = bias + the split-K partial sums, added in slab order (deterministic)
+    float* lg = p.logits + (size_t)b * p.A;
     float mx = -3.4e38f;
-    for (int i = lane; i < p.A; i += 32) mx = fmaxf(mx, lg[i]);
+    for (int i = lane; i < p.A; i += 32) {
+        float v = p.bias_p[i];
+        for (int sidx = 0; sidx < p.n_split_p; ++sidx) v += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.A + i];
+        lg[i] = v; mx = fmaxf(mx, v);
+    }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float s = 0.0f;
     for (int i = lane; i < p.A; i += 32) s += expf(lg[i] - mx);
@@ -25,9 +30,66 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
     const float inv = 1.0f / s;
     for (int i = lane; i < p.A; i += 32) p.policy[(size_t)b * p.A + i] = expf(lg[i] - mx) * inv;
     float d = 0.0f;
-    for (int i = lane; i < p.hidden_n; i += 32) d = fmaf(p.hidden[(size_t)b * p.hidden_n + i], p.w2[i], d);
+    for (int i = lane; i < p.hidden_n; i += 32) {
+        float h = p.bias_h[i];
+        for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
+        d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
+    }
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
+}
+
+// Wide heads (chess: A = 20480): one block of 1024 threads per board, the board's logits stay in registers between the max /
+// sum / write passes (one read of the partial sums, one write of logits and policy).
+constexpr int PV_WIDE_THREADS = 1024, PV_WIDE_MAX_PER_THREAD = 24;     // covers A <= 24576; many threads with few elements each: the passes are latency-bound
+__global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams p) {
+    __shared__ float red[PV_WIDE_THREADS / 32];
+    __shared__ float bcast;
+    const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b >= nb) return;
+    float v[PV_WIDE_MAX_PER_THREAD];
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
+        const int i = tid + k * PV_WIDE_THREADS;
+        if (i < p.A) {
+            float x = p.bias_p[i];
+            for (int sidx = 0; sidx < p.n_split_p; ++sidx) x += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.A + i];
+            v[k] = x; mx = fmaxf(mx, x);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int w = 1; w < PV_WIDE_THREADS / 32; ++w) m = fmaxf(m, red[w]); bcast = m; }
+    __syncthreads();
+    mx = bcast;
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) { const int i = tid + k * PV_WIDE_THREADS; if (i < p.A) sum += expf(v[k] - mx); }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) { float t = 0.0f; for (int w = 0; w < PV_WIDE_THREADS / 32; ++w) t += red[w]; bcast = t; }
+    __syncthreads();
+    const float inv = 1.0f / bcast;
+#pragma unroll
+    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
+        const int i = tid + k * PV_WIDE_THREADS;
+        if (i < p.A) { p.logits[(size_t)b * p.A + i] = v[k]; p.policy[(size_t)b * p.A + i] = expf(v[k] - mx) * inv; }
+    }
+    if (warp == 0) {      // value head: tanh(relu(hidden) . w2 + b2)
+        float d = 0.0f;
+        for (int i = lane; i < p.hidden_n; i += 32) {
+            float h = p.bias_h[i];
+            for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
+            d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
+        }
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
+    }
 }
 
 // fp32 NCHW planes (host-supplied, az_engine_nn_forward) → the trunk's bf16 input layout
@@ -46,6 +108,11 @@ __global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int
 }  // namespace
 
 int policy_value_launch(const OutParams& p, int max_boards, cudaStream_t s) {
+    if (p.A > 1024) {
+        if (p.A > PV_WIDE_THREADS * PV_WIDE_MAX_PER_THREAD) return (int)cudaErrorInvalidValue;
+        k_policy_value_wide<<<max_boards, PV_WIDE_THREADS, 0, s>>>(p);
+        return (int)cudaGetLastError();
+    }
     k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
     return (int)cudaGetLastError();
 }

@@ -7,7 +7,11 @@
 namespace az { namespace nn {
 
 struct OutParams {
-    const float* logits; const float* hidden; const float* w2; const float* b2;
+    const float* logits_part; const float* hidden_part;     // split-K partial sums [n_split][stride]: raw GEMM outputs
+    size_t logits_stride, hidden_stride; int n_split_p, n_split_h;
+    const float* bias_p; const float* bias_h;              // policy FC bias [A], value FC1 bias [hidden_n] (ReLU after it)
+    const float* w2; const float* b2;
+    float* logits;                                           // final logits [n][A] (kept for az_engine_nn_forward)
     float* policy; float* value;
     const int* n_boards_dev; int n_boards;
     int A, hidden_n;
