@@ -232,3 +232,49 @@ def test_full_size_resnet_batch_position_independence():
         eng.advance([a] * T)
     assert eng.stats()["pool_overflows"] == 0
     eng.close()
+
+
+def test_c_abi_error_behaviour():
+    """Status codes + az_last_error where the reference throws (igamestate.h:36-52, std::runtime_error): unsupported game /
+    board, evaluator mismatch, bad weight blobs, illegal roots, out-of-range slots; the engine stays usable afterwards."""
+    import struct
+    from _eng import E, N, hash_engine
+    with pytest.raises(E.EngineError, match="unsupported game"):
+        E.Engine(game=E.GOMOKU, board_size=7, n_slots=2, evaluator=E.EVAL_HASH)
+    with pytest.raises(E.EngineError, match="n_slots"):
+        E.Engine(game=E.GOMOKU, board_size=9, n_slots=0, evaluator=E.EVAL_HASH)
+    eng = hash_engine(2, board=9, sims=8)
+    with pytest.raises(E.EngineError, match="hash evaluator"):
+        eng.load_weights(b"AZW1" + b"\0" * 64)
+    with pytest.raises(E.EngineError, match="illegal move"):
+        eng.set_root(0, [40, 40])
+    with pytest.raises(E.EngineError, match="illegal move"):
+        eng.set_root(0, [81])
+    with pytest.raises(E.EngineError, match="slot out of range"):
+        eng.set_root(2, [])
+    with pytest.raises(E.EngineError, match="slot out of range"):
+        eng.root_stats(-1)
+    with pytest.raises(E.EngineError, match="one action per slot"):
+        eng.advance([0])
+    eng.set_root(0, [40]); eng.set_root(1, [40])
+    eng.search()
+    st = eng.root_stats(0)
+    assert int(st["N"].sum()) == 8 and 40 not in st["actions"].tolist()
+    eng.advance([-2, int(st["actions"][0])])                        # -2 = leave the slot alone
+    assert eng.slot_state(0)[1] == 1 and eng.slot_state(1)[1] == 2
+    eng.close()
+    net = E.Engine(game=E.GOMOKU, board_size=9, n_slots=4, evaluator=E.EVAL_RESNET, net_blocks=1, num_simulations=4, max_nodes_per_tree=2048)
+    with pytest.raises(E.EngineError, match="no network weights"):
+        net.search()
+    with pytest.raises(E.EngineError, match="magic"):
+        net.load_weights(b"XXXX" + b"\0" * 64)
+    good = N.export_weights(N.make_random_model(seed=0, blocks=1, board=9, actions=81))
+    with pytest.raises(E.EngineError, match="truncated"):
+        net.load_weights(good[:len(good) // 2])
+    wrong = N.export_weights(N.make_random_model(seed=0, blocks=1, board=15, actions=225))
+    with pytest.raises(E.EngineError, match="does not match"):
+        net.load_weights(wrong)
+    net.load_weights(good)
+    net.play(1)
+    assert net.stats()["moves"] == 4
+    net.close()
