@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                 mbar_arrive_expect_tx(w_full, C::W_BYTES);
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * C::W_BYTES;
                 for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
+                grid_dep_wait();            // PDL: everything above ran under the previous layer's tail; its activations are needed from here on
+                grid_dep_launch();          // (after the wait, so a dependent grid can only start once this grid's own prerequisites are complete)
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
                     const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
             const bool has_res = p.resid != nullptr, relu = p.relu != 0;
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
+            grid_dep_wait();                // PDL: the residual is read, and the output written, only after the previous layer has completed
             for (int item = first_item; item < n_items; item += item_step, ++ait) {
                 const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
                 const int row = (p.reverse ? n_items - 1 - item : item) * 256 + (int)rank * 128 + warp * 32 + lane;
@@ -468,6 +471,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
                 mbar_arrive_expect_tx(w_full, C::W_BYTES);
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * C::W_BYTES;
                 for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
+                grid_dep_wait();            // PDL: everything above ran under the previous layer's tail; its activations are needed from here on
+                grid_dep_launch();          // (after the wait, so a dependent grid can only start once this grid's own prerequisites are complete)
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
                     const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
@@ -547,6 +552,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
             const bool has_res = p.resid != nullptr, relu = p.relu != 0;
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
+            grid_dep_wait();                // PDL: the residual is read, and the output written, only after the previous layer has completed
             for (int item = first_item; item < n_items; item += item_step, ++ait) {
                 const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
                 const int row = (p.reverse ? n_items - 1 - item : item) * 256 + (int)rank * 128 + warp * 32 + lane;
@@ -604,18 +610,20 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
         if (!wide_done) { err = cudaFuncSetAttribute(k_conv3x3_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg::SMEM); if (err) return (int)err; wide_done = true; }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = WideCfg::SMEM; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = p.pdl ? 2 : 1;
         err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair_wide, p);
         if (err) return (int)err;
     } else if (conv_uses_pair(cin, p.row_pitch)) {
         if (!attr_done[2]) { err = cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM); if (err) return (int)err; attr_done[2] = true; }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = p.pdl ? 2 : 1;
         err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair, p);
         if (err) return (int)err;
     } else if (cin == 128) {

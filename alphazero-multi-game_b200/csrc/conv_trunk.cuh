@@ -50,6 +50,8 @@ struct ConvParams {
                                     // rows its predecessor wrote last, which are still in L2)
     long long* trace;               // profiling only: per-item clock64 stamps of cluster 0 (conv_bench, AZ_CONV_TRACE), else nullptr
     int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
+    int pdl;                        // pair kernels: launch with programmatic stream serialization (the prologue — barriers, TMEM, the resident
+                                    // weight half — runs while the previous kernel of the stream drains; activations are touched after griddepcontrol.wait)
 };
 
 size_t conv_smem_bytes(int cin);

@@ -234,6 +234,7 @@ struct Net {
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
     int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
         static const bool alt_order = getenv("AZ_CONV_NO_ALT") == nullptr;      // profiling switch for the alternating item order
+        static const bool pdl = getenv("AZ_CONV_NO_PDL") == nullptr;            // profiling switch for programmatic dependent launch of the trunk layers
         AZ_CHECK(loaded, "no network weights loaded (az_engine_load_weights)");
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
@@ -252,7 +253,7 @@ struct Net {
                     cp.in = in + ci * slice; cp.out = out + co * slice;
                     cp.w = w.conv_w[wi(l, co, ci)]; cp.bias = ci == 0 ? w.conv_b[bi(l, co)] : w.zero_bias;
                     cp.resid = ci == 0 ? (skip ? skip + co * slice : nullptr) : cp.out;
-                    cp.relu = ci == NS - 1 ? 1 : 0; cp.reverse = NS == 1 ? reverse : 0;
+                    cp.relu = ci == NS - 1 ? 1 : 0; cp.reverse = NS == 1 ? reverse : 0; cp.pdl = pdl ? 1 : 0;
                     AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
                 }
             return 0;
@@ -268,7 +269,7 @@ struct Net {
             float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
             conv_ms += ms; conv_sampled += (unsigned long long)(2 * blocks * NS * NS);
         }
-        cp.relu = 1; cp.reverse = 0;
+        cp.relu = 1; cp.reverse = 0; cp.pdl = 0;
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
         nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
         AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
@@ -793,6 +794,7 @@ struct EngineT : EngineBase {
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[net.wi(1, 0, 0)]; cp.bias = net.w.conv_b[net.bi(1, 0)];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
         if (getenv("AZ_CONV_RESID")) cp.resid = net.X;                    // time the residual variant (second conv of a block)
+        cp.pdl = getenv("AZ_CONV_NO_PDL") ? 0 : 1;
         long long* trace = nullptr;
         if (getenv("AZ_CONV_TRACE")) { if (dev_alloc(&trace, 2048)) return -1; AZ_CUDA_CHECK(cudaMemset(trace, 0, 2048 * 8)); cp.trace = trace; }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);

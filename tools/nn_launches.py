@@ -7,4 +7,5 @@ from alphazero_multi_game_b200 import engine as E, net as N
 eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=4096, evaluator=E.EVAL_RESNET, net_blocks=10, num_simulations=8,
                max_nodes_per_tree=2048, deterministic=1)
 eng.load_weights(N.export_weights(N.make_random_model(seed=0)))
-print("forward ms", eng.nn_bench(4096, 3))
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+print("forward ms", min(eng.nn_bench(4096, reps) for _ in range(3 if reps > 3 else 1)), "PDL off" if os.environ.get("AZ_CONV_NO_PDL") else "PDL on")
