@@ -12,6 +12,7 @@
 #include <cmath>
 #include <algorithm>
 #include <unordered_set>
+#include <cuda.h>
 
 #include "../../include/az_b200.h"
 #include "common.cuh"
@@ -84,6 +85,57 @@ __global__ void k_prep_fc(const float* __restrict__ w /*[n_rows][feat]*/, __nv_b
 }
 
 // ------------------------------------------------------------------------------------------------ network
+// ------------------------------------------------------------------------------------------------ SM partitions
+// Green contexts (CUDA 12.4+ driver API, resolved at run time — the library does not link libcuda): the device's SMs are
+// split into a large partition that runs nothing but the trunk's 128 -> 128 conv launches and a small one for everything
+// else (tree kernels, stem, heads).  The small kernels are latency- / HBM-bound and cost far fewer SM-seconds on a dozen SMs
+// than on 148, and with two stream groups they run in the shadow of the other group's tensor-core pass.
+struct SmPartitions {
+    CUgreenCtx conv_ctx = nullptr, small_ctx = nullptr;
+    int conv_sms = 0, small_sms = 0;
+    CUresult (*p_stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    CUresult (*p_ctx_destroy)(CUgreenCtx) = nullptr;
+    template <class F> static bool sym(const char* name, F& f) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion(name, &fn, 12090, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            set_error(std::string("driver entry point not available: ") + name + " (SM partitioning needs a CUDA 12.5+ driver)"); return false;
+        }
+        f = reinterpret_cast<F>(fn); return true;
+    }
+    // conv partition >= want_conv SMs (rounded up by the driver to its granularity), the remainder is the small partition
+    int create(int device, int want_conv) {
+        CUresult (*p_dev_get)(CUdevice*, int) = nullptr;
+        CUresult (*p_get_res)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+        CUresult (*p_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+        CUresult (*p_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+        CUresult (*p_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+        if (!(sym("cuDeviceGet", p_dev_get) && sym("cuDeviceGetDevResource", p_get_res) && sym("cuDevSmResourceSplitByCount", p_split) &&
+              sym("cuDevResourceGenerateDesc", p_desc) && sym("cuGreenCtxCreate", p_create) && sym("cuGreenCtxStreamCreate", p_stream_create) &&
+              sym("cuGreenCtxDestroy", p_ctx_destroy))) return -1;
+        CUdevice dev; AZ_CHECK(p_dev_get(&dev, device) == CUDA_SUCCESS, "cuDeviceGet failed");
+        CUdevResource all{}, big{}, rest{};
+        AZ_CHECK(p_get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS, "cuDeviceGetDevResource failed");
+        unsigned int nb = 1;
+        AZ_CHECK(p_split(&big, &nb, &all, &rest, 0, (unsigned)want_conv) == CUDA_SUCCESS && nb == 1, "cuDevSmResourceSplitByCount failed");
+        AZ_CHECK(rest.type == CU_DEV_RESOURCE_TYPE_SM && rest.sm.smCount >= 2, "SM split left no SMs for the small partition");
+        CUdevResourceDesc d_big = nullptr, d_rest = nullptr;
+        AZ_CHECK(p_desc(&d_big, &big, 1) == CUDA_SUCCESS && p_desc(&d_rest, &rest, 1) == CUDA_SUCCESS, "cuDevResourceGenerateDesc failed");
+        AZ_CHECK(p_create(&conv_ctx, d_big, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS, "cuGreenCtxCreate (conv partition) failed");
+        AZ_CHECK(p_create(&small_ctx, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS, "cuGreenCtxCreate (small partition) failed");
+        conv_sms = (int)big.sm.smCount; small_sms = (int)rest.sm.smCount;
+        return 0;
+    }
+    int stream(bool conv, cudaStream_t* out) {
+        CUstream st = nullptr;
+        AZ_CHECK(p_stream_create(&st, conv ? conv_ctx : small_ctx, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS, "cuGreenCtxStreamCreate failed");
+        *out = (cudaStream_t)st; return 0;
+    }
+    void destroy() {
+        if (p_ctx_destroy) { if (conv_ctx) p_ctx_destroy(conv_ctx); if (small_ctx) p_ctx_destroy(small_ctx); }
+        conv_ctx = small_ctx = nullptr;
+    }
+};
+
 struct NetWeights {            // device images
     std::vector<__nv_bfloat16*> conv_w;   // stem + 2*blocks
     std::vector<float*> conv_b;
@@ -116,9 +168,15 @@ struct Net {
     int p_splits = 4;                                                      // policy FC splits: 1 for very wide heads (the partial slabs would cost more than they save)
     int boards_cap = 0;
     int n_sms = 148;
+    // SM partitions (SmPartitions): the trunk's 128 -> 128 layers go to `conv_stream` (conv partition, n_sms_conv SMs), everything else stays on
+    // the caller's stream (small partition, n_sms SMs); ev_in / ev_out order the two.  conv_stream == nullptr: one stream, all SMs.
+    cudaStream_t conv_stream = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr; int n_sms_conv = 0;
     unsigned long long launches = 0;
     // live timing of the trunk's 128 -> 128 conv launches inside production waves (every 64th forward): CUDA events on the launching stream
     cudaEvent_t tev[2] = {nullptr, nullptr}; unsigned long long fwd_count = 0, conv_sampled = 0; double conv_ms = 0.0;
+    // AZ_WAVE_TIMING (profiling): when fe_on is set for a forward, events after stem / trunk / pool / 1x1 GEMM / policy FC / value FC / softmax
+    cudaEvent_t fe[7] = {}; bool fe_on = false;
+    void fe_rec(int i, cudaStream_t s) { if (fe_on) { if (!fe[i]) cudaEventCreate(&fe[i]); cudaEventRecord(fe[i], s); } }
 
     int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
@@ -229,6 +287,10 @@ struct Net {
     }
     void destroy() {
         free_weights();
+        for (auto e : {ev_in, ev_out, tev[0], tev[1]}) if (e) cudaEventDestroy(e);
+        for (auto& e : fe) if (e) { cudaEventDestroy(e); e = nullptr; }
+        ev_in = ev_out = tev[0] = tev[1] = nullptr;
+        if (conv_stream) { cudaStreamDestroy(conv_stream); conv_stream = nullptr; }
         for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)pooled, (void*)featP, (void*)featV, (void*)logits, (void*)hidden, (void*)logits_part, (void*)hidden_part}) cudaFree(p);
     }
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
@@ -236,6 +298,8 @@ struct Net {
         static const bool alt_order = getenv("AZ_CONV_NO_ALT") == nullptr;      // profiling switch for the alternating item order
         static const bool pdl = getenv("AZ_CONV_NO_PDL") == nullptr;            // profiling switch for programmatic dependent launch of the trunk layers
         AZ_CHECK(loaded, "no network weights loaded (az_engine_load_weights)");
+        cudaStream_t cs = conv_stream ? conv_stream : s;                          // stream / SM count of the trunk layers
+        const int cs_sms = conv_stream ? n_sms_conv : n_sms;
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
         cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1;
@@ -254,40 +318,49 @@ struct Net {
                     cp.w = w.conv_w[wi(l, co, ci)]; cp.bias = ci == 0 ? w.conv_b[bi(l, co)] : w.zero_bias;
                     cp.resid = ci == 0 ? (skip ? skip + co * slice : nullptr) : cp.out;
                     cp.relu = ci == NS - 1 ? 1 : 0; cp.reverse = NS == 1 ? reverse : 0; cp.pdl = pdl ? 1 : 0;
-                    AZ_CHECK(nn::conv3x3_launch(cp, 128, n_sms, s) == 0, "conv launch failed"); ++launches;
+                    AZ_CHECK(nn::conv3x3_launch(cp, 128, cs_sms, cs) == 0, "conv launch failed"); ++launches;
                 }
             return 0;
         };
-        const bool sample = n_dev != nullptr && blocks > 0 && (fwd_count++ % 64) == 63;
-        if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], s); }
+        fe_rec(0, s);
+        const bool sample = !fe_on && n_dev != nullptr && blocks > 0 && (fwd_count++ % 64) == 63;
+        if (conv_stream && blocks > 0) { AZ_CUDA_CHECK(cudaEventRecord(ev_in, s)); AZ_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_in, 0)); }
+        if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], cs); }
         for (int b = 0; b < blocks; ++b) {
             if (layer(X, Y, nullptr, 1 + 2 * b, alt_order ? 1 : 0)) return -1;
             if (layer(Y, X, X, 2 + 2 * b, 0)) return -1;
         }
+        if (conv_stream && blocks > 0) { AZ_CUDA_CHECK(cudaEventRecord(ev_out, cs)); AZ_CUDA_CHECK(cudaStreamWaitEvent(s, ev_out, 0)); }
         if (sample) {
-            cudaEventRecord(tev[1], s); cudaEventSynchronize(tev[1]);
+            cudaEventRecord(tev[1], cs); cudaEventSynchronize(tev[1]);
             float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
             conv_ms += ms; conv_sampled += (unsigned long long)(2 * blocks * NS * NS);
         }
         cp.relu = 1; cp.reverse = 0; cp.pdl = 0;
+        fe_rec(1, s);
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
         nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
         AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
+        fe_rec(2, s);
         nn::GemmParams g1{}; g1.A = pooled; g1.B = w.g1_w; g1.bias = w.b1x1; g1.a_rows = 64 * boards_cap; g1.a_plane_mod = 2 * (C / 8); g1.K = 3 * C; g1.n_tiles = 1; g1.n_valid = 64;
         g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
         g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
         AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
+        fe_rec(3, s);
         // the two FC GEMMs run split-K (FC_SPLITS x more work items: a 4096 x 256 x 6144 GEMM is only 128 tiles); the raw partial
         // sums are added, with bias / ReLU, by k_policy_value
         nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
         g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits_part; g2.ldo = A;
         g2.k_splits = p_splits; g2.split_stride = (size_t)max_boards * A;
         AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
+        fe_rec(4, s);
         nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden_part; g3.ldo = 256;
         g3.k_splits = FC_SPLITS; g3.split_stride = (size_t)max_boards * 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
+        fe_rec(5, s);
         nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * A, (size_t)max_boards * 256, p_splits, FC_SPLITS, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
+        fe_rec(6, s);
         return 0;
     }
 };
@@ -381,6 +454,7 @@ struct EngineT : EngineBase {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_main = nullptr;
     std::vector<Group> groups;
+    SmPartitions parts; bool partitioned = false;
     TreePools tp{};
     ScratchPools sc{};
     int scratch_trees = 0;
@@ -397,7 +471,11 @@ struct EngineT : EngineBase {
 
     void destroy() {
         cudaDeviceSynchronize();
-        if (wave_timing && wt_n) fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
+        if (wave_timing && wt_n) {
+            fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
+            fprintf(stderr, "  evaluator: stem %.3f, trunk %.3f, pool %.3f, 1x1 gemm %.3f, policy fc %.3f, value fc %.3f, softmax/tanh %.3f ms\n", wt_fwd[0] / wt_n, wt_fwd[1] / wt_n,
+                    wt_fwd[2] / wt_n, wt_fwd[3] / wt_n, wt_fwd[4] / wt_n, wt_fwd[5] / wt_n, wt_fwd[6] / wt_n);
+        }
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
                             (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval}) cudaFree(p);
@@ -406,6 +484,7 @@ struct EngineT : EngineBase {
             if (g.stream) cudaStreamDestroy(g.stream);
         }
         groups.clear();
+        parts.destroy(); partitioned = false;
         if (ev_main) { cudaEventDestroy(ev_main); ev_main = nullptr; }
         for (void* p : {(void*)tp.N, (void*)tp.W, (void*)tp.P, (void*)tp.first, (void*)tp.act, (void*)tp.nchild, (void*)tp.flags, (void*)tp.root,
                         (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id,
@@ -454,10 +533,16 @@ struct EngineT : EngineBase {
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
         const int per = (T + NG - 1) / NG;
         groups.resize(NG);
+        // SM partitions: AZ_SM_SPLIT=<SMs of the conv partition> (0 / unset: off); only useful with >= 2 stream groups and the network evaluator
+        if (const char* sp = getenv("AZ_SM_SPLIT")) {
+            const int want = atoi(sp);
+            if (want > 0 && c.evaluator == AZ_EVAL_RESNET) { if (parts.create(c.device, want)) return -1; partitioned = true; }
+        }
         for (int gi = 0; gi < NG; ++gi) {
             Group& g = groups[gi];
             g.t0 = gi * per; g.n = std::min(per, T - g.t0);
-            AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+            if (partitioned) { if (parts.stream(false, &g.stream)) return -1; }
+            else AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
             AZ_CUDA_CHECK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
             const int n = g.n;
             if (dev_alloc(&g.wb.path, (size_t)n * MAX_DEPTH) || dev_alloc(&g.wb.path_len, n) || dev_alloc(&g.wb.leaf_node, n) || dev_alloc(&g.wb.leaf_kind, n) ||
@@ -470,6 +555,12 @@ struct EngineT : EngineBase {
             g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
             if (c.evaluator == AZ_EVAL_RESNET) {
                 if (g.net.init(G::N, G::N, A, per, c.net_channels, G::PLANES)) return -1;
+                if (partitioned) {
+                    if (parts.stream(true, &g.net.conv_stream)) return -1;
+                    AZ_CUDA_CHECK(cudaEventCreateWithFlags(&g.net.ev_in, cudaEventDisableTiming));
+                    AZ_CUDA_CHECK(cudaEventCreateWithFlags(&g.net.ev_out, cudaEventDisableTiming));
+                    g.net.n_sms = parts.small_sms; g.net.n_sms_conv = parts.conv_sms;
+                }
             }
         }
         return reset_games();
@@ -552,7 +643,7 @@ struct EngineT : EngineBase {
     // one wave of one group: select → evaluator → expand/backup, on the group's stream
     // AZ_WAVE_TIMING=1 (profiling): CUDA events around select / evaluator / expand of every 64th wave, printed at destroy
     bool wave_timing = getenv("AZ_WAVE_TIMING") != nullptr;
-    cudaEvent_t wt_ev[4] = {}; double wt_ms[3] = {0, 0, 0}; long wt_n = 0, wt_seen = 0;
+    cudaEvent_t wt_ev[4] = {}; double wt_ms[3] = {0, 0, 0}, wt_fwd[7] = {0, 0, 0, 0, 0, 0, 0}; long wt_n = 0, wt_seen = 0;
     int wave(Group& g, int mode) {
         cudaStream_t st = g.stream;
         const bool timed = wave_timing && (wt_seen++ % 64) == 63;
@@ -567,7 +658,9 @@ struct EngineT : EngineBase {
             k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
+            g.net.fe_on = timed;
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
+            g.net.fe_on = false;
         }
         if (timed) cudaEventRecord(wt_ev[2], st);
         k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, root_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
@@ -576,6 +669,10 @@ struct EngineT : EngineBase {
         if (timed) {
             cudaEventRecord(wt_ev[3], st); cudaEventSynchronize(wt_ev[3]);
             for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, wt_ev[i], wt_ev[i + 1]); wt_ms[i] += ms; }
+            if (cfg.evaluator == AZ_EVAL_RESNET && g.net.fe[6]) {       // select end → stem → trunk → pool → 1x1 → policy FC → value FC → softmax
+                cudaEvent_t seq[8] = {wt_ev[1], g.net.fe[0], g.net.fe[1], g.net.fe[2], g.net.fe[3], g.net.fe[4], g.net.fe[5], g.net.fe[6]};
+                for (int i = 0; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, seq[i], seq[i + 1]); wt_fwd[i] += ms; }
+            }
             ++wt_n;
         }
         return 0;
@@ -798,10 +895,12 @@ struct EngineT : EngineBase {
         long long* trace = nullptr;
         if (getenv("AZ_CONV_TRACE")) { if (dev_alloc(&trace, 2048)) return -1; AZ_CUDA_CHECK(cudaMemset(trace, 0, 2048 * 8)); cp.trace = trace; }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, g.stream) == 0, "conv launch failed");
-        AZ_CUDA_CHECK(cudaEventRecord(e0, g.stream));
-        for (int i = 0; i < reps; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, net.n_sms, g.stream) == 0, "conv launch failed");
-        AZ_CUDA_CHECK(cudaEventRecord(e1, g.stream));
+        cudaStream_t cs = net.conv_stream ? net.conv_stream : g.stream;
+        const int cs_sms = net.conv_stream ? net.n_sms_conv : net.n_sms;
+        for (int i = 0; i < 3; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, cs_sms, cs) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e0, cs));
+        for (int i = 0; i < reps; ++i) AZ_CHECK(nn::conv3x3_launch(cp, 128, cs_sms, cs) == 0, "conv launch failed");
+        AZ_CUDA_CHECK(cudaEventRecord(e1, cs));
         AZ_CUDA_CHECK(cudaEventSynchronize(e1));
         float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
