@@ -427,6 +427,8 @@ struct EngineBase {
     virtual int drain(void* buf, size_t cap, size_t* n, bool device) = 0;
     virtual int get_stats(az_stats* out) = 0;
     virtual int make_examples(const void* samples, size_t n, int augment, float* planes, float* policy, float* value) = 0;
+    virtual int examples_from_games(const int32_t* moves, const int32_t* n_moves, const int8_t* results, int n_games, int max_moves, const float* policy_in, int P,
+                                    int augment, float* planes, float* policy, float* value) = 0;
     virtual int sync() = 0;
     virtual int nn_forward(const float* planes, int n, float* policy, float* value, float* logits) = 0;
     virtual int nn_bench(int n_boards, int reps, float* ms) = 0;
@@ -822,6 +824,48 @@ struct EngineT : EngineBase {
         return 0;
     }
 
+    // Dataset::extractExamples on game records (move lists): one example per recorded move, k images each; chunked over positions
+    int examples_from_games(const int32_t* moves, const int32_t* n_moves, const int8_t* results, int n_games, int max_mv, const float* policy_in, int P,
+                            int augment, float* planes, float* policy, float* value) override {
+        AZ_CHECK(n_games >= 0 && max_mv >= 1 && P >= 0, "bad sizes");
+        if (n_games == 0) return 0;
+        AZ_CHECK(moves && n_moves && results && planes && value && (P == 0 || (policy_in && policy)), "null buffer");
+        const int k = (augment && cfg.game != AZ_GAME_CHESS) ? 8 : 1;              // dataset.cpp:250-253: no augmentation for chess
+        std::vector<int32_t> pg, pp;
+        for (int g = 0; g < n_games; ++g) {
+            AZ_CHECK(n_moves[g] >= 0 && n_moves[g] <= max_mv, "n_moves out of range");
+            AZ_CHECK(results[g] >= RES_ONGOING && results[g] <= RES_WIN_P2, "bad game result code");
+            for (int i = 0; i < n_moves[g]; ++i) { pg.push_back(g); pp.push_back(i); }
+        }
+        const size_t n_pos = pg.size();
+        if (n_pos == 0) return 0;
+        const size_t chunk = 2048, pe = (size_t)G::PLANES * G::CELLS, Pz = (size_t)std::max(P, 1);
+        int32_t *dm, *dg, *dpl, *derr; int8_t* dr; float *dpi, *dp, *dq, *dv; uint64_t* dh;
+        if (dev_alloc(&dm, (size_t)n_games * max_mv) || dev_alloc(&dg, chunk) || dev_alloc(&dpl, chunk) || dev_alloc(&derr, 1) || dev_alloc(&dr, n_games) ||
+            dev_alloc(&dpi, chunk * Pz) || dev_alloc(&dp, chunk * k * pe) || dev_alloc(&dq, chunk * k * Pz) || dev_alloc(&dv, chunk * k) ||
+            dev_alloc(&dh, chunk * (size_t)(max_mv + 1))) return -1;
+        AZ_CUDA_CHECK(cudaMemcpyAsync(dm, moves, (size_t)n_games * max_mv * 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(dr, results, (size_t)n_games, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemsetAsync(derr, 0, 4, stream));
+        int rc = 0;
+        for (size_t o = 0; o < n_pos && rc == 0; o += chunk) {
+            const size_t c = std::min(chunk, n_pos - o);
+            AZ_CUDA_CHECK(cudaMemcpyAsync(dg, pg.data() + o, c * 4, cudaMemcpyHostToDevice, stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, pp.data() + o, c * 4, cudaMemcpyHostToDevice, stream));
+            if (P > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(dpi, policy_in + o * P, c * P * 4, cudaMemcpyHostToDevice, stream));
+            k_examples_from_games<G><<<blocks_for_warps((int)c), 128, warp_ws_bytes<G>(), stream>>>(dm, dg, dpl, (int)c, max_mv, dr, dpi, P, k, dp, dq, dv, dh, derr);
+            AZ_LAUNCH_CHECK(); ++launches;
+            AZ_CUDA_CHECK(cudaMemcpyAsync(planes + o * k * pe, dp, c * k * pe * 4, cudaMemcpyDeviceToHost, stream));
+            if (P > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(policy + o * k * P, dq, c * k * P * 4, cudaMemcpyDeviceToHost, stream));
+            AZ_CUDA_CHECK(cudaMemcpyAsync(value + o * k, dv, c * k * 4, cudaMemcpyDeviceToHost, stream));
+            int32_t err = 0; AZ_CUDA_CHECK(cudaMemcpyAsync(&err, derr, 4, cudaMemcpyDeviceToHost, stream));
+            AZ_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (err) { set_error("illegal move in game record " + std::to_string(err - 1) + " (IGameState::makeMove throws, dataset.cpp:76)"); rc = -1; }
+        }
+        for (void* p : {(void*)dm, (void*)dg, (void*)dpl, (void*)derr, (void*)dr, (void*)dpi, (void*)dp, (void*)dq, (void*)dv, (void*)dh}) cudaFree(p);
+        return rc;
+    }
+
     int get_stats(az_stats* o) override {
         if (sync_all()) return -1;
         Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
@@ -1013,6 +1057,10 @@ AZ_API int az_engine_sample_layout(az_engine* e, az_sample_layout* out) { AZ_FWD
 AZ_API int az_engine_drain_samples(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, false)); }
 AZ_API int az_engine_drain_samples_device(az_engine* e, void* buf, size_t cap, size_t* n) { AZ_FWD(drain(buf, cap, n, true)); }
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out) { AZ_FWD(get_stats(out)); }
+AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, const int32_t* n_moves, const int8_t* results, int n_games, int max_moves, const float* policy_in,
+                                         int policy_len, int augment, float* planes, float* policy, float* value) {
+    AZ_FWD(examples_from_games(moves, n_moves, results, n_games, max_moves, policy_in, policy_len, augment, planes, policy, value));
+}
 AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n, int augment, float* planes, float* policy, float* value) { AZ_FWD(make_examples(samples, n, augment, planes, policy, value)); }
 AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
 AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits) { AZ_FWD(nn_forward(planes, n, policy, value, logits)); }

@@ -594,4 +594,62 @@ __global__ void __launch_bounds__(128) k_make_examples(const Sample<G>* __restri
     if (lane == 0) value[wid] = (float)sm->z;
 }
 
+// Dataset::extractExamples (src/selfplay/dataset.cpp:64-114) + augmentExample (:245-436) from GAME RECORDS (move lists), one warp per
+// position: position (g, i) = the state after moves[g][0..i) → getEnhancedTensorRepresentation, the caller's policy vector for that
+// position (any length P: the reference never looks at its meaning), value = the game's result seen from the player to move
+// (:84-96).  The 7 extra images are produced the way the reference produces them: rot90 / rot180 / rot270 / flipH from the original,
+// then flipH of the three rotations; a policy entry moves only when both its old and its new index are < P.
+// kind: 0 rot90, 1 rot180, 2 rot270, 3 flipH (the oracle's orc_move)
+__device__ __forceinline__ void example_move(int kind, int n, int i, int j, int& i2, int& j2) {
+    if (kind == 0) { i2 = j; j2 = n - 1 - i; }
+    else if (kind == 1) { i2 = n - 1 - i; j2 = n - 1 - j; }
+    else if (kind == 2) { i2 = n - 1 - j; j2 = i; }
+    else { i2 = i; j2 = n - 1 - j; }
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_examples_from_games(const int32_t* __restrict__ moves, const int32_t* __restrict__ pos_game, const int32_t* __restrict__ pos_ply,
+                                                            int n_pos, int max_moves, const int8_t* __restrict__ results, const float* __restrict__ policy_in, int P, int k_aug,
+                                                            float* planes, float* policy, float* value, uint64_t* hist_scratch, int32_t* error_flag) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= n_pos) return;
+    typename G::Warp& w = warp_ws<G>(smem);
+    const int g = pos_game[wid], ply = pos_ply[wid];
+    G::w_init(w, lane);
+    G::w_attach_history(w, hist_scratch + (size_t)wid * (max_moves + 1), lane);
+    for (int i = 0; i < ply; ++i)
+        if (!G::w_apply(w, moves[(size_t)g * max_moves + i], lane, true)) { if (lane == 0) atomicExch(error_flag, 1 + g); return; }     // makeMove throws (dataset.cpp:76)
+    constexpr int N = G::N, CELLS = N * N;
+    const size_t pe = (size_t)G::PLANES * CELLS;
+    float* pl0 = planes + (size_t)wid * k_aug * pe;
+    float* po0 = policy + (size_t)wid * k_aug * P;
+    G::w_planes(w, lane, pl0);
+    const float* pin = policy_in + (size_t)wid * P;
+    for (int a = lane; a < P; a += 32) po0[a] = pin[a];
+    const int res = results[g], player = G::w_player(w);
+    float gv = res == RES_WIN_P1 ? 1.0f : (res == RES_WIN_P2 ? -1.0f : 0.0f);
+    if (player == 2) gv = -gv;
+    if (lane == 0) for (int k = 0; k < k_aug; ++k) value[(size_t)wid * k_aug + k] = gv;
+    __syncwarp();
+    for (int k = 1; k < k_aug; ++k) {
+        const int src = k <= 4 ? 0 : k - 4, kind = k <= 3 ? k - 1 : 3;
+        const float* spl = pl0 + (size_t)src * pe; const float* spo = po0 + (size_t)src * P;
+        float* dpl = pl0 + (size_t)k * pe; float* dpo = po0 + (size_t)k * P;
+        for (int a = lane; a < P; a += 32) dpo[a] = spo[a];
+        __syncwarp();
+        for (int idx = lane; idx < (int)pe; idx += 32) {
+            const int c = idx / CELLS, cell = idx % CELLS;
+            int i2, j2; example_move(kind, N, cell / N, cell % N, i2, j2);
+            dpl[(c * N + i2) * N + j2] = spl[idx];
+        }
+        for (int oi = lane; oi < CELLS; oi += 32) {
+            int i2, j2; example_move(kind, N, oi / N, oi % N, i2, j2);
+            const int ni = i2 * N + j2;
+            if (oi < P && ni < P) dpo[ni] = spo[oi];
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace az

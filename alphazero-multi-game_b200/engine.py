@@ -49,7 +49,7 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_load_weights", "az_engine_reset_games", "az_engine_set_root", "az_engine_search",
            "az_engine_root_stats", "az_engine_advance", "az_engine_play", "az_engine_add_dirichlet_noise", "az_engine_last_actions",
            "az_engine_slot_state", "az_engine_sample_layout", "az_engine_drain_samples",
-           "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
+           "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_examples_from_games", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_conv_sampled", "az_engine_event_record", "az_engine_event_elapsed",
            "az_rules_replay"]
 
@@ -99,6 +99,7 @@ def load_library():
         "az_engine_drain_samples": [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)],
         "az_engine_drain_samples_device": [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)],
         "az_engine_make_examples": [vp, vp, C.c_size_t, C.c_int, f32p, f32p, f32p],
+        "az_engine_examples_from_games": [vp, i32p, i32p, vp, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, f32p, f32p],
         "az_engine_get_stats": [vp, C.POINTER(Stats)],
         "az_engine_sync": [vp],
         "az_engine_nn_forward": [vp, f32p, C.c_int, f32p, f32p, f32p],
@@ -264,6 +265,30 @@ class Engine:
         if n:
             self._check(self.lib.az_engine_make_examples(self.h, smp.ctypes.data, n, 1 if augment else 0, planes.ctypes.data,
                                                          policy.ctypes.data, value.ctypes.data))
+        return planes, policy, value
+
+    def examples_from_games(self, games, results, policies, augment=True):
+        """Dataset.addGameRecord + extractExamples on the device for game records given as move lists: games = list of action lists,
+        results = GameResult code per game (0 ONGOING, 1 DRAW, 2 WIN_PLAYER1, 3 WIN_PLAYER2), policies = [sum(len(g)), P] (one vector
+        per recorded move, game order).  Returns (planes [n*k, C, N, N], policy [n*k, P], value [n*k])."""
+        n_games = len(games)
+        max_moves = max(1, max((len(g) for g in games), default=1))
+        mv = np.zeros((n_games, max_moves), np.int32)
+        nm = np.zeros(n_games, np.int32)
+        for i, g in enumerate(games):
+            mv[i, :len(g)] = g
+            nm[i] = len(g)
+        res = np.ascontiguousarray(results, np.int8)
+        pol = np.ascontiguousarray(policies, np.float32)
+        n = int(nm.sum())
+        assert pol.ndim == 2 and pol.shape[0] == n and len(res) == n_games
+        P = pol.shape[1]
+        k = 8 if (augment and self.cfg.game != CHESS) else 1
+        planes = np.zeros((n * k, self.planes, self.board, self.board), np.float32)
+        policy = np.zeros((n * k, P), np.float32)
+        value = np.zeros(n * k, np.float32)
+        self._check(self.lib.az_engine_examples_from_games(self.h, mv.ctypes.data, nm.ctypes.data, res.ctypes.data, n_games, max_moves, pol.ctypes.data, P,
+                                                           1 if augment else 0, planes.ctypes.data, policy.ctypes.data, value.ctypes.data))
         return planes, policy, value
 
     def stats(self):

@@ -601,6 +601,146 @@ GameRecord GameRecord::loadFromFile(const std::string& fn) {
     std::stringstream b; b << f.rdbuf(); return fromJson(b.str());
 }
 
+// ---- TrainingExample / Dataset (src/selfplay/dataset.cpp) ----
+static json example_json(const TrainingExample& e) {
+    json j; json st = json::array();
+    for (const auto& plane : e.state) { json pj = json::array(); for (const auto& row : plane) pj.push_back(row); st.push_back(pj); }
+    j["state"] = st; j["policy"] = e.policy; j["value"] = e.value;
+    return j;
+}
+static TrainingExample example_from(const json& j) {
+    TrainingExample e;
+    const auto& st = j["state"];
+    e.state.resize(st.size());
+    for (size_t i = 0; i < st.size(); ++i) { e.state[i].resize(st[i].size()); for (size_t r = 0; r < st[i].size(); ++r) e.state[i][r] = st[i][r].get<std::vector<float>>(); }
+    e.policy = j["policy"].get<std::vector<float>>(); e.value = j["value"];
+    return e;
+}
+std::string TrainingExample::toJson() const { return example_json(*this).dump(); }
+TrainingExample TrainingExample::fromJson(const std::string& s) { return example_from(json::parse(s)); }
+
+Dataset::Dataset() : rng_(std::random_device{}()) {}
+void Dataset::addGameRecord(const GameRecord& record, bool) { gameRecords_.push_back(record); }
+
+// dataset.cpp:64-114.  Records are grouped by (game, board) — one small engine per group provides the device rules / encoder — and, inside
+// a group, by policy-vector length (the reference copies whatever vector a move carries; az_engine_examples_from_games takes one length per call).
+void Dataset::extractExamples(bool includeAugmentations) {
+    examples_.clear();
+    std::vector<std::vector<TrainingExample>> per_record(gameRecords_.size());
+    std::vector<bool> done(gameRecords_.size(), false);
+    for (size_t r0 = 0; r0 < gameRecords_.size(); ++r0) {
+        if (done[r0]) continue;
+        auto [gt, bsz, variant] = gameRecords_[r0].getMetadata();
+        if (variant) throw std::runtime_error("variant rules are out of scope of the B200 engine");
+        const int bs = gt == core::GameType::CHESS ? 8 : (bsz > 0 ? bsz : (gt == core::GameType::GO ? 19 : 15));
+        std::vector<size_t> grp;
+        for (size_t r = r0; r < gameRecords_.size(); ++r) {
+            auto [g2, b2, v2] = gameRecords_[r].getMetadata();
+            const int bs2 = g2 == core::GameType::CHESS ? 8 : (b2 > 0 ? b2 : (g2 == core::GameType::GO ? 19 : 15));
+            if (!done[r] && g2 == gt && bs2 == bs && !v2) { grp.push_back(r); done[r] = true; }
+        }
+        az_config c; az_config_default(&c);
+        c.game = (int)gt; c.board_size = bs; c.n_slots = 1; c.num_simulations = 1; c.evaluator = AZ_EVAL_HASH; c.max_nodes_per_tree = 4096; c.sample_ring_capacity = 16;
+        az_engine* e = nullptr;
+        check(az_engine_create(&c, &e), "az_engine_create");
+        try {
+            int max_moves = 1; size_t n_pos = 0;
+            for (size_t r : grp) { max_moves = std::max<int>(max_moves, (int)gameRecords_[r].getMoves().size()); n_pos += gameRecords_[r].getMoves().size(); }
+            std::vector<int32_t> moves(grp.size() * (size_t)max_moves, 0), n_moves(grp.size());
+            std::vector<int8_t> results(grp.size());
+            std::vector<int> lengths;                                  // distinct policy lengths, first-seen order
+            for (size_t k = 0; k < grp.size(); ++k) {
+                const auto& mv = gameRecords_[grp[k]].getMoves();
+                n_moves[k] = (int)mv.size(); results[k] = (int8_t)gameRecords_[grp[k]].getResult();
+                for (size_t i = 0; i < mv.size(); ++i) {
+                    moves[k * max_moves + i] = mv[i].action;
+                    const int L = (int)mv[i].policy.size();
+                    if (std::find(lengths.begin(), lengths.end(), L) == lengths.end()) lengths.push_back(L);
+                }
+            }
+            if (n_pos == 0) { az_engine_destroy(e); continue; }
+            const bool aug = includeAugmentations && gt != core::GameType::CHESS;
+            const int K = aug ? 8 : 1;
+            const int planes_n = gt == core::GameType::CHESS ? 18 : (gt == core::GameType::GO ? 8 : 11);
+            const size_t pe = (size_t)planes_n * bs * bs;
+            std::vector<float> planes(n_pos * K * pe), value(n_pos * K);
+            std::vector<std::vector<float>> pol_out(n_pos * K);
+            bool first = true;
+            for (int L : lengths) {
+                std::vector<float> pin(n_pos * (size_t)std::max(L, 1), 0.0f), pout(n_pos * K * (size_t)std::max(L, 1), 0.0f);
+                size_t pos = 0;
+                for (size_t k = 0; k < grp.size(); ++k)
+                    for (const auto& m : gameRecords_[grp[k]].getMoves()) { if ((int)m.policy.size() == L) std::copy(m.policy.begin(), m.policy.end(), pin.begin() + pos * L); ++pos; }
+                std::vector<float> pl_tmp, va_tmp;
+                if (!first) { pl_tmp.resize(planes.size()); va_tmp.resize(value.size()); }
+                check(az_engine_examples_from_games(e, moves.data(), n_moves.data(), results.data(), (int)grp.size(), max_moves, pin.data(), L, aug ? 1 : 0,
+                                                    first ? planes.data() : pl_tmp.data(), pout.data(), first ? value.data() : va_tmp.data()), "az_engine_examples_from_games");
+                first = false;
+                pos = 0;
+                for (size_t k = 0; k < grp.size(); ++k)
+                    for (const auto& m : gameRecords_[grp[k]].getMoves()) {
+                        if ((int)m.policy.size() == L) for (int a = 0; a < K; ++a) pol_out[pos * K + a].assign(pout.begin() + (pos * K + a) * L, pout.begin() + (pos * K + a + 1) * L);
+                        ++pos;
+                    }
+            }
+            size_t pos = 0;
+            for (size_t k = 0; k < grp.size(); ++k) {
+                auto& out = per_record[grp[k]];
+                for (size_t i = 0; i < gameRecords_[grp[k]].getMoves().size(); ++i, ++pos)
+                    for (int a = 0; a < K; ++a) {
+                        TrainingExample ex;
+                        const float* src = planes.data() + (pos * K + a) * pe;
+                        ex.state.assign(planes_n, std::vector<std::vector<float>>(bs, std::vector<float>(bs)));
+                        for (int p = 0; p < planes_n; ++p) for (int y = 0; y < bs; ++y) std::copy(src + (p * bs + y) * bs, src + (p * bs + y + 1) * bs, ex.state[p][y].begin());
+                        ex.policy = std::move(pol_out[pos * K + a]); ex.value = value[pos * K + a];
+                        out.push_back(std::move(ex));
+                    }
+            }
+        } catch (...) { az_engine_destroy(e); throw; }
+        az_engine_destroy(e);
+    }
+    for (auto& v : per_record) for (auto& ex : v) examples_.push_back(std::move(ex));      // record order, original then its images (:98-106)
+    if (shuffleOnExtract_) shuffle();                                                        // :112
+}
+
+std::tuple<std::vector<std::vector<std::vector<std::vector<float>>>>, std::vector<std::vector<float>>, std::vector<float>> Dataset::getBatch(size_t batchSize) const {
+    batchSize = std::min(batchSize, examples_.size());
+    std::vector<std::vector<std::vector<std::vector<float>>>> states(batchSize);
+    std::vector<std::vector<float>> policies(batchSize);
+    std::vector<float> values(batchSize);
+    std::vector<size_t> idx(examples_.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::shuffle(idx.begin(), idx.end(), rng_);
+    for (size_t i = 0; i < batchSize; ++i) { states[i] = examples_[idx[i]].state; policies[i] = examples_[idx[i]].policy; values[i] = examples_[idx[i]].value; }
+    return {states, policies, values};
+}
+void Dataset::shuffle() { std::shuffle(examples_.begin(), examples_.end(), rng_); }
+bool Dataset::saveToFile(const std::string& fn) const {          // {"examples": [{state, policy, value}, ...]}  (:144-181)
+    try {
+        json j; json arr = json::array();
+        for (const auto& e : examples_) arr.push_back(example_json(e));
+        j["examples"] = arr;
+        std::ofstream f(fn); if (!f.is_open()) return false;
+        f << j.dump(); return true;
+    } catch (...) { return false; }
+}
+bool Dataset::loadFromFile(const std::string& fn) {
+    try {
+        std::ifstream f(fn); if (!f.is_open()) return false;
+        json j; f >> j;
+        examples_.clear();
+        for (const auto& x : j["examples"]) examples_.push_back(example_from(x));
+        return true;
+    } catch (...) { return false; }
+}
+std::vector<TrainingExample> Dataset::getRandomSubset(size_t count) const {
+    count = std::min(count, examples_.size());
+    std::vector<size_t> idx(examples_.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::shuffle(idx.begin(), idx.end(), rng_);
+    std::vector<TrainingExample> out; out.reserve(count);
+    for (size_t i = 0; i < count; ++i) out.push_back(examples_[idx[i]]);
+    return out;
+}
+
 SelfPlayManager::SelfPlayManager(nn::NeuralNetwork* nn, int numGames, int numSimulations, int numThreads)
     : nn_(nn), numGames_(numGames), numSimulations_(numSimulations), numThreads_(numThreads) {}
 SelfPlayManager::~SelfPlayManager() { abort_ = true; }

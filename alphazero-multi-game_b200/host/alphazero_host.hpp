@@ -18,6 +18,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <random>
 #include <tuple>
 #include <unordered_set>
 #include <utility>
@@ -383,6 +384,38 @@ private:
     core::GameResult result_;
     std::vector<MoveData> moves_;
     std::chrono::system_clock::time_point timestamp_;
+};
+
+// include/alphazero/selfplay/dataset.h:21-128
+struct TrainingExample {
+    std::vector<std::vector<std::vector<float>>> state;   // [plane][row][col]
+    std::vector<float> policy;
+    float value = 0.0f;
+    std::string toJson() const;
+    static TrainingExample fromJson(const std::string& json);
+};
+
+// Dataset (src/selfplay/dataset.cpp): same methods and file format.  extractExamples replays the records, evaluates the feature
+// planes and builds the dihedral images on the GPU (az_engine_examples_from_games); everything else is host bookkeeping.
+class Dataset {
+public:
+    Dataset();
+    void addGameRecord(const GameRecord& record, bool useEnhancedFeatures = true);
+    void extractExamples(bool includeAugmentations = true);
+    size_t size() const { return examples_.size(); }
+    std::tuple<std::vector<std::vector<std::vector<std::vector<float>>>>, std::vector<std::vector<float>>, std::vector<float>> getBatch(size_t batchSize) const;
+    void shuffle();
+    bool saveToFile(const std::string& filename) const;
+    bool loadFromFile(const std::string& filename);
+    std::vector<TrainingExample> getRandomSubset(size_t count) const;
+    // engine knobs without a reference counterpart
+    void setShuffleOnExtract(bool s) { shuffleOnExtract_ = s; }  // false: examples stay in record order (parity tests)
+    const std::vector<TrainingExample>& examples() const { return examples_; }
+private:
+    std::vector<GameRecord> gameRecords_;
+    std::vector<TrainingExample> examples_;
+    mutable std::mt19937 rng_;
+    bool shuffleOnExtract_ = true;
 };
 
 class SelfPlayManager {

@@ -112,6 +112,18 @@ PYBIND11_MODULE(_alphazero_cpp, m) {
         .def("saveToFile", &selfplay::GameRecord::saveToFile).def_static("fromJson", &selfplay::GameRecord::fromJson)
         .def_static("loadFromFile", &selfplay::GameRecord::loadFromFile);
 
+    py::class_<selfplay::TrainingExample>(m, "TrainingExample").def(py::init<>())
+        .def_readwrite("state", &selfplay::TrainingExample::state).def_readwrite("policy", &selfplay::TrainingExample::policy)
+        .def_readwrite("value", &selfplay::TrainingExample::value).def("toJson", &selfplay::TrainingExample::toJson)
+        .def_static("fromJson", &selfplay::TrainingExample::fromJson);
+    py::class_<selfplay::Dataset>(m, "Dataset").def(py::init<>())
+        .def("addGameRecord", &selfplay::Dataset::addGameRecord, py::arg("record"), py::arg("useEnhancedFeatures") = true)
+        .def("extractExamples", [](selfplay::Dataset& self, bool aug) { py::gil_scoped_release r; self.extractExamples(aug); }, py::arg("includeAugmentations") = true)
+        .def("size", &selfplay::Dataset::size).def("getBatch", &selfplay::Dataset::getBatch).def("shuffle", &selfplay::Dataset::shuffle)
+        .def("saveToFile", &selfplay::Dataset::saveToFile).def("loadFromFile", &selfplay::Dataset::loadFromFile)
+        .def("getRandomSubset", &selfplay::Dataset::getRandomSubset)
+        .def("setShuffleOnExtract", &selfplay::Dataset::setShuffleOnExtract).def("examples", &selfplay::Dataset::examples);
+
     py::class_<selfplay::SelfPlayManager>(m, "SelfPlayManager")
         .def(py::init<nn::NeuralNetwork*, int, int, int>(), py::arg("neuralNetwork"), py::arg("numGames") = 100, py::arg("numSimulations") = 800,
              py::arg("numThreads") = 4, py::keep_alive<1, 2>())

@@ -129,6 +129,18 @@ AZ_API int az_engine_drain_samples_device(az_engine* e, void* dev_buf, size_t ca
  * stores it by child index), value fp32 [n*k] = game result seen from the player to move.  Host buffers. */
 AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n_records, int augment, float* planes, float* policy, float* value);
 
+/* Dataset::extractExamples (src/selfplay/dataset.cpp:64-114) + augmentExample (:245-436) for GameRecords that come through the host
+ * API as move lists (GameRecord::getMoves, include/alphazero/selfplay/game_record.h): moves [n_games][max_moves] (reference action
+ * codes; Go pass = -1), n_moves[g], results[g] = GameResult code (0 ONGOING, 1 DRAW, 2 WIN_PLAYER1, 3 WIN_PLAYER2).  One example per
+ * recorded move i of game g, in game order: planes of the state after moves[g][0..i) (getEnhancedTensorRepresentation), the
+ * caller's policy vector for that move (policy_in [sum n_moves][policy_len], copied / permuted exactly as the reference does: an
+ * entry moves only when its old and new index are both < policy_len), value = result seen from the player to move (:84-96).
+ * augment != 0 and the game is not chess: the 8 images per example (original, rot90, rot180, rot270, flipH, flipH of the rotations).
+ * Outputs (host): planes fp32 [n*k][C][N][N], policy fp32 [n*k][policy_len], value fp32 [n*k].  An illegal recorded move is an error
+ * (the reference's makeMove throws). */
+AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, const int32_t* n_moves, const int8_t* results, int n_games, int max_moves,
+                                         const float* policy_in, int policy_len, int augment, float* planes, float* policy, float* value);
+
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out);
 AZ_API int az_engine_sync(az_engine* e);
 

@@ -93,3 +93,44 @@ def test_chess_examples_match_oracle_replay():
             checked += 1
     assert checked >= 10
     eng.close()
+
+
+@pytest.mark.parametrize("game,board", [(_orc.GOMOKU, 9), (_orc.GO, 9), (_orc.CHESS, 8)])
+def test_examples_from_game_records_match_sample_path_and_oracle(game, board):
+    """az_engine_examples_from_games (Dataset::addGameRecord + extractExamples for records that arrive as move lists) against
+    (1) az_engine_make_examples on the sample records of the same games — bit-identical planes / policy / value — and (2) the oracle's
+    augmentExample restatement for a policy SHORTER than N*N (child-ordered policies: an entry moves only when old and new index fit)."""
+    from _eng import E
+    kw = dict(sample_ring_capacity=48 * 600) if game == _orc.CHESS else {}
+    eng, smp = _play_and_collect(game, board, sims=12 if game == _orc.CHESS else 20, slots=48 if game == _orc.CHESS else 24,
+                                 steps=140 if game == _orc.CHESS else 60, **kw)
+    if smp is None:
+        pytest.skip("no game finished within the step budget")
+    games = _games(smp)[:8]
+    recs = np.concatenate([np.array(g, dtype=smp.dtype) for g in games])
+    planes, policy, value = eng.make_examples(recs, augment=True)
+    moves = [[int(r["action"]) for r in g] for g in games]
+    results = [int(g[0]["result"]) for g in games]
+    k = 1 if game == _orc.CHESS else 8
+    dense = policy[::k].copy()                                       # the action-indexed targets of the original images
+    pl2, po2, va2 = eng.examples_from_games(moves, results, dense, augment=True)
+    assert pl2.shape == planes.shape and np.array_equal(pl2, planes)
+    assert np.array_equal(po2, policy)
+    assert np.array_equal(va2, value)
+    if game != _orc.CHESS:
+        short = np.ascontiguousarray(dense[:, :board * 4 + 3])       # P < N*N
+        pl3, po3, _ = eng.examples_from_games(moves, results, short, augment=True)
+        assert np.array_equal(pl3, planes)
+        for i in range(0, len(short), 7):
+            apl, apo = _orc.augment_example(planes[8 * i], short[i])
+            assert np.array_equal(po3[8 * i], short[i])
+            for j in range(7):
+                assert np.array_equal(po3[8 * i + 1 + j], apo[j]), (i, j)
+                assert np.array_equal(pl3[8 * i + 1 + j], apl[j]), (i, j)
+    # an illegal recorded move is an error, as the reference's makeMove throws (dataset.cpp:76)
+    bad = [list(moves[0])]
+    if len(bad[0]) >= 2:
+        bad[0][1] = bad[0][0] if game != _orc.CHESS else 0           # occupied point / a1a1
+        with pytest.raises(E.EngineError):
+            eng.examples_from_games(bad, results[:1], dense[:len(bad[0])], augment=False)
+    eng.close()

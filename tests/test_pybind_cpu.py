@@ -28,7 +28,7 @@ def test_module_surface_matches_reference_names():
     az = _mod()
     for name in ["GameType", "GameResult", "MCTSNodeSelection", "MCTSSearchMode", "IGameState", "GomokuState", "createGameState",
                  "NeuralNetwork", "createNeuralNetwork", "MCTSConfig", "MCTSStats", "TranspositionTable", "ParallelMCTS", "MoveData",
-                 "GameRecord", "SelfPlayManager"]:
+                 "GameRecord", "TrainingExample", "Dataset", "SelfPlayManager"]:
         assert hasattr(az, name), name
     for meth in ["search", "selectAction", "getActionProbabilities", "getRootValue", "updateWithMove", "addDirichletNoise", "setNumSimulations",
                  "setDeterministicMode", "getSearchInfo", "getMemoryUsage"]:
@@ -36,6 +36,8 @@ def test_module_surface_matches_reference_names():
     for meth in ["generateGames", "setExplorationParams", "setProgressCallback", "setBatchConfig", "setSaveGames", "setAbort", "isRunning",
                  "setMctsConfig", "getCompletedGamesCount", "getTotalMovesCount"]:
         assert hasattr(az.SelfPlayManager, meth), meth
+    for meth in ["addGameRecord", "extractExamples", "size", "getBatch", "shuffle", "saveToFile", "loadFromFile", "getRandomSubset"]:
+        assert hasattr(az.Dataset, meth), meth
     c = az.MCTSConfig()
     assert (c.numSimulations, c.virtualLoss) == (800, 3) and abs(c.cPuct - 1.5) < 1e-7 and c.fpuReduction == 0.0
     assert int(az.GameType.GO) == 2 and int(az.GameResult.WIN_PLAYER2) == 3
@@ -159,6 +161,29 @@ def test_game_record_json_roundtrip_reference_format():
         az.GameRecord.fromJson("{not json")
 
 
+def test_training_example_and_dataset_file_format(tmp_path):
+    """TrainingExample JSON (dataset.cpp:14-54) and the Dataset file format {"examples": [{state, policy, value}]} (:144-216)."""
+    az = _mod()
+    e = az.TrainingExample()
+    e.state = [[[0.0, 1.0], [0.5, 0.25]], [[1.0, 1.0], [0.0, 0.0]]]
+    e.policy = [0.125, 0.875]
+    e.value = -1.0
+    j = json.loads(e.toJson())
+    assert set(j) == {"state", "policy", "value"} and j["state"][0][1] == [0.5, 0.25] and j["value"] == -1.0
+    e2 = az.TrainingExample.fromJson(e.toJson())
+    assert e2.state == e.state and e2.policy == e.policy and e2.value == e.value
+    fn = tmp_path / "ds.json"
+    fn.write_text(json.dumps({"examples": [j, j, j]}))
+    d = az.Dataset()
+    assert d.size() == 0 and d.loadFromFile(str(fn)) and d.size() == 3
+    st, po, va = d.getBatch(2)
+    assert len(st) == 2 and po[0] == e.policy and va == [-1.0, -1.0]
+    assert len(d.getRandomSubset(10)) == 3
+    out = tmp_path / "out.json"
+    assert d.saveToFile(str(out)) and json.loads(out.read_text()) == {"examples": [j, j, j]}
+    assert not d.loadFromFile(str(tmp_path / "missing.json"))
+
+
 def test_search_classes_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
@@ -174,3 +199,8 @@ def test_search_classes_fail_loudly_without_gpu():
         az.ParallelMCTS(az.GomokuState(15), nn)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         az.SelfPlayManager(nn, 2, 10, 1).generateGames(az.GameType.GOMOKU, 15, False)
+    d = az.Dataset()
+    r = az.GameRecord(az.GameType.GOMOKU, 9, False); r.addMove(40, [1.0], 0.0, 1); r.setResult(az.GameResult.DRAW)
+    d.addGameRecord(r)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        d.extractExamples(True)

@@ -130,3 +130,67 @@ def test_parallel_mcts_and_selfplay_on_chess():
         mv = g.getMoves()
         assert 2 <= len(mv) <= 512 and int(g.getResult()) in (1, 2, 3)
         assert 1 <= len(mv[0].policy) <= 218 and abs(sum(mv[0].policy) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("game,board", [("GOMOKU", 9), ("GO", 9)])
+def test_dataset_extract_examples_matches_oracle(game, board):
+    """Dataset.addGameRecord + extractExamples (dataset.cpp:60-114, 245-436) on records produced by SelfPlayManager: planes = the oracle's
+    tensor of the replayed state, the 7 images = the augmentExample restatement, value = result seen from the player to move."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    gt = getattr(az.GameType, game)
+    og = {"GOMOKU": _orc.GOMOKU, "GO": _orc.GO}[game]
+    nn = az.createNeuralNetwork("hash", gt, board)
+    mgr = az.SelfPlayManager(nn, 3, 24, 1)
+    mgr.setConcurrentGames(6)
+    games = mgr.generateGames(gt, board, False)
+    assert len(games) == 3
+    d = az.Dataset()
+    d.setShuffleOnExtract(False)
+    for g in games:
+        d.addGameRecord(g)
+    d.extractExamples(True)
+    n_moves = sum(len(g.getMoves()) for g in games)
+    assert d.size() == 8 * n_moves
+    ex = d.examples()
+    i = 0
+    for g in games:
+        s = O.new_state(og, board)
+        res = int(g.getResult())
+        for mv in g.getMoves():
+            t = O.tensor(s)
+            pol = np.array(mv.policy, np.float32)
+            z = 0.0 if res in (0, 1) else (1.0 if (res == 2) == (O.state_current_player(s) == 1) else -1.0)
+            apl, apo = _orc.augment_example(t, pol)
+            assert np.array_equal(np.array(ex[i].state, np.float32), t) and np.array_equal(np.array(ex[i].policy, np.float32), pol) and ex[i].value == z
+            for k in range(7):
+                assert np.array_equal(np.array(ex[i + 1 + k].state, np.float32), apl[k]), (i, k)
+                assert np.array_equal(np.array(ex[i + 1 + k].policy, np.float32), apo[k]), (i, k)
+                assert ex[i + 1 + k].value == z
+            i += 8
+            assert O.state_make_move(s, mv.action) == 0
+    d.extractExamples(False)
+    assert d.size() == n_moves
+    d.setShuffleOnExtract(True); d.extractExamples(True)
+    st, po, va = d.getBatch(5)
+    assert len(st) == 5 and len(st[0]) == (11 if game == "GOMOKU" else 8) and len(po[0]) == len(games[0].getMoves()[0].policy)
+
+
+def test_dataset_chess_no_augmentation_and_mixed_policy_lengths():
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    r = az.GameRecord(az.GameType.CHESS, 8, False)
+    s = O.new_state(_orc.CHESS, 8)
+    tensors = []
+    for ply in range(6):
+        legal = O.legal(s)
+        tensors.append(O.tensor(s))
+        a = int(legal[(7 * ply + 3) % len(legal)])
+        r.addMove(a, [1.0 / (ply + 1)] * (ply + 1), 0.0, 1)           # child-ordered vectors of different lengths
+        assert O.state_make_move(s, a) == 0
+    r.setResult(az.GameResult.WIN_PLAYER2)
+    d = az.Dataset(); d.setShuffleOnExtract(False); d.addGameRecord(r); d.extractExamples(True)
+    assert d.size() == 6                                             # dataset.cpp:250-253
+    for ply, e in enumerate(d.examples()):
+        assert np.array_equal(np.array(e.state, np.float32), tensors[ply])
+        assert len(e.policy) == ply + 1 and e.value == (-1.0 if ply % 2 == 0 else 1.0)
