@@ -13,3 +13,7 @@ $CXX -std=c++17 -O2 -fPIC -shared -ffp-contract=off -fvisibility=hidden -I"$PYIN
     "$HERE/alphazero_host.cpp" "$HERE/python_module.cpp" -o "$PKG/_alphazero_cpp$SUFFIX" \
     -L"$PKG" -laz_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $PKG/_alphazero_cpp$SUFFIX"
+# the reference's `self_play` command over the same host classes
+$CXX -std=c++17 -O2 -ffp-contract=off -I"$JSONINC" -I/usr/local/cuda/include "$HERE/alphazero_host.cpp" "$HERE/selfplay_main.cpp" -o "$PKG/self_play" \
+    -L"$PKG" -laz_b200 -Wl,-rpath,'$ORIGIN'
+echo "built $PKG/self_play"

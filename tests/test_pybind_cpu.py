@@ -204,3 +204,20 @@ def test_search_classes_fail_loudly_without_gpu():
     d.addGameRecord(r)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         d.extractExamples(True)
+
+
+def test_self_play_command_help_and_loud_failure_without_gpu():
+    import subprocess, torch
+    _mod()
+    exe = os.path.join(PKG, "self_play")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(PKG, "host", "build.sh")])
+    h = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert h.returncode == 0
+    for flag in ["--model", "--game", "--size", "--num-games", "--simulations", "--output-dir", "--temperature", "--temp-drop", "--final-temp",
+                 "--dirichlet-alpha", "--dirichlet-epsilon", "--c-puct", "--virtual-loss", "--threads", "--batch-size"]:      # selfplay_main.cpp:87-117
+        assert flag in h.stdout, flag
+    assert subprocess.run([exe], capture_output=True, text=True).returncode == 1           # --model is required
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--model", "hash", "--num-games", "1", "--output-dir", "/tmp/az_sp_none"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr

@@ -194,3 +194,29 @@ def test_dataset_chess_no_augmentation_and_mixed_policy_lengths():
     for ply, e in enumerate(d.examples()):
         assert np.array_equal(np.array(e.state, np.float32), tensors[ply])
         assert len(e.policy) == ply + 1 and e.value == (-1.0 if ply % 2 == 0 else 1.0)
+
+
+def test_self_play_command_reference_flags_and_outputs(tmp_path):
+    """The `self_play` command (src/selfplay/selfplay_main.cpp:87-117 flags, :352-388 metadata): GameRecord JSON per game + metadata JSON."""
+    import json, subprocess
+    exe = os.path.join(ROOT, "alphazero-multi-game_b200", "self_play")
+    out = tmp_path / "games"
+    r = subprocess.run([exe, "--model", "hash", "--game", "gomoku", "--size", "9", "--num-games", "3", "--simulations", "30", "--slots", "3", "--output-dir", str(out),
+                        "--temperature", "1.0", "--temp-drop", "10", "--c-puct", "1.5", "--virtual-loss", "3", "--threads", "2", "--batch-size", "16"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Self-play completed!" in r.stdout and "Average moves per second" in r.stdout
+    files = sorted(os.listdir(out))
+    games = [f for f in files if not f.startswith("metadata_")]
+    meta = [f for f in files if f.startswith("metadata_")]
+    assert len(games) == 3 and len(meta) == 1
+    g = json.loads((out / games[0]).read_text())
+    assert g["game_type"] == 0 and g["board_size"] == 9 and g["result"] in (1, 2, 3) and len(g["moves"]) >= 9
+    m = json.loads((out / meta[0]).read_text())
+    assert list(m) == ["game", "board_size", "num_games_requested", "num_games_completed", "simulations", "threads", "temperature", "temp_drop", "final_temp",
+                       "dirichlet_alpha", "dirichlet_epsilon", "variant", "model_path", "total_moves", "avg_moves_per_game", "total_time_seconds",
+                       "avg_moves_per_second", "use_gpu", "batch_size", "batch_timeout", "fp16_used", "c_puct", "fpu_reduction", "virtual_loss",
+                       "use_transposition_table", "progressive_widening"]
+    assert m["num_games_completed"] == 3 and m["simulations"] == 30 and m["threads"] == 2 and m["use_gpu"] is True
+    bad = subprocess.run([exe, "--model", "hash", "--variant"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "variant" in bad.stderr
