@@ -163,8 +163,9 @@ struct Net {
     uint8_t* rowvalid = nullptr;
     __nv_bfloat16 *pooled = nullptr, *featP = nullptr, *featV = nullptr;   // head GEMM operands (bf16, chunk-plane layout)
     float *logits = nullptr, *hidden = nullptr;                            // final logits [n][A]; `hidden` unused since split-K (kept for the destroy list)
-    float *logits_part = nullptr, *hidden_part = nullptr;                  // split-K partial sums of the two FC GEMMs: [FC_SPLITS][max_boards][A | 256]
-    static constexpr int FC_SPLITS = 4;
+    float *logits_part = nullptr, *hidden_part = nullptr;                  // split-K partial sums of the two FC GEMMs: [fc_splits][max_boards][A | 256]
+    int fc_splits = 4;                                                     // split-K of the FC GEMMs: 4, 8 or 16 (divisors of the 96 K stages), enough for ~one item per SM
+    int ld_part = 0;                                                       // row pitch of the policy partial-sum slabs: p_tiles * 64 (16-byte stores in the GEMM epilogue)
     int p_splits = 4;                                                      // policy FC splits: 1 for very wide heads (the partial slabs would cost more than they save)
     int boards_cap = 0;
     int n_sms = 148;
@@ -180,7 +181,14 @@ struct Net {
 
     int init(int H_, int W_, int A_, int max_boards_, int channels, int planes) {
         H = H_; W = W_; A = A_; max_boards = max_boards_; C = channels;
-        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64; p_split = A <= 1024 ? 1 : 0; p_splits = A <= 1024 ? FC_SPLITS : 1;
+        cin_pad = planes <= 16 ? 16 : 32; p_tiles = (A + 63) / 64; p_split = A <= 1024 ? 1 : 0; 
+        {   // work items of an FC GEMM = 128-row tiles x groups of up to 4 weight tiles (gemm_tc.cu NSUB) x K splits
+            const int m_tiles = (max_boards_ + 127) / 128;
+            fc_splits = 4; while (fc_splits < 16 && m_tiles * fc_splits < 120) fc_splits *= 2;
+            if (const char* f = getenv("AZ_FC_SPLITS")) { const int v = atoi(f); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) fc_splits = v; }
+        }
+        p_splits = A <= 1024 ? fc_splits : 1;
+        ld_part = p_tiles * 64;
         AZ_CHECK(planes <= 32, "at most 32 input planes");
         row_pitch = W + 1; board_pitch = (H + 1) * (W + 1);
         AZ_CHECK(W + 2 <= nn::CONV_HALO, "board too wide for the conv halo");
@@ -208,7 +216,7 @@ struct Net {
         AZ_CUDA_CHECK(cudaMemset(featP, 0, (size_t)512 * boards_cap * 16));
         AZ_CUDA_CHECK(cudaMemset(featV, 0, (size_t)512 * boards_cap * 16));
         if (dev_alloc(&logits, (size_t)max_boards * A)) return -1;
-        if (dev_alloc(&logits_part, (size_t)p_splits * max_boards * A) || dev_alloc(&hidden_part, (size_t)FC_SPLITS * max_boards * 256)) return -1;
+        if (dev_alloc(&logits_part, (size_t)p_splits * max_boards * ld_part) || dev_alloc(&hidden_part, (size_t)fc_splits * max_boards * 256)) return -1;
         if (dev_alloc(&hidden, (size_t)max_boards * 256)) return -1;
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -347,18 +355,18 @@ struct Net {
         g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
         AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
         fe_rec(3, s);
-        // the two FC GEMMs run split-K (FC_SPLITS x more work items: a 4096 x 256 x 6144 GEMM is only 128 tiles); the raw partial
+        // the two FC GEMMs run split-K (fc_splits x more work items: a 4096 x 256 x 6144 GEMM is only 128 tiles); the raw partial
         // sums are added, with bias / ReLU, by k_policy_value
         nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
-        g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits_part; g2.ldo = A;
-        g2.k_splits = p_splits; g2.split_stride = (size_t)max_boards * A;
+        g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits_part; g2.ldo = ld_part;
+        g2.k_splits = p_splits; g2.split_stride = (size_t)max_boards * ld_part;
         AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
         fe_rec(4, s);
         nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden_part; g3.ldo = 256;
-        g3.k_splits = FC_SPLITS; g3.split_stride = (size_t)max_boards * 256;
+        g3.k_splits = fc_splits; g3.split_stride = (size_t)max_boards * 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         fe_rec(5, s);
-        nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * A, (size_t)max_boards * 256, p_splits, FC_SPLITS, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256};
+        nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * ld_part, (size_t)max_boards * 256, p_splits, fc_splits, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256, ld_part};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
         fe_rec(6, s);
         return 0;

@@ -9,6 +9,8 @@
 // Warp roles as in the conv kernel: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer / TMEM allocator.
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace az { namespace nn {
 
@@ -18,37 +20,48 @@ namespace {
 
 constexpr int G_BM = 128, G_BN = 64, G_BK = 64;
 constexpr int G_A_STAGE = (G_BK / 8) * G_BM * 16;   // 16 KB
-constexpr int G_B_STAGE = (G_BK / 8) * G_BN * 16;   // 8 KB
-constexpr int G_STAGE = G_A_STAGE + G_B_STAGE;
-constexpr int G_NST = 8;          // 8 x 24 KB in flight per SM: the head GEMMs are L2-latency bound (K = 384 ... 6144, tiny tiles)
-constexpr int G_OFF_BARS = G_NST * G_STAGE;
-constexpr int G_OFF_TSLOT = G_OFF_BARS + (2 * G_NST + 4) * 8;
-constexpr int G_SMEM = G_OFF_TSLOT + 16;
+constexpr int G_B_STAGE = (G_BK / 8) * G_BN * 16;   // 8 KB per 64-column weight sub-tile
 constexpr int G_THREADS = 192;
+// NSUB = 64-column weight sub-tiles per work item (1, 2 or 4): the 128-row A stage is loaded once and multiplied with NSUB weight
+// sub-tiles (NSUB MMAs of N = 64 per K step into adjacent TMEM columns) — the head GEMMs are bound by L2 -> SM traffic (ncu: 5.8 TB/s of
+// the ~9 TB/s LTS cap with NSUB = 1), and a wider item divides the A re-reads by NSUB.  The weight image keeps its per-64-column
+// layout, so a stage's B part is NSUB separate 8 KB bulk copies.
+template <int NSUB> struct GCfg {
+    static constexpr int STAGE = G_A_STAGE + NSUB * G_B_STAGE;                 // 24 / 32 / 48 KB
+    static constexpr int NST = NSUB == 1 ? 8 : (NSUB == 2 ? 6 : 4);           // ~192 KB in flight per SM
+    static constexpr int OFF_BARS = NST * STAGE;
+    static constexpr int OFF_TSLOT = OFF_BARS + (2 * NST + 4) * 8;
+    static constexpr int SMEM = OFF_TSLOT + 16;
+    static constexpr int ACC_COLS = NSUB * G_BN;                               // accumulator columns per buffer (double-buffered)
+};
 
+template <int NSUB>
 __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
+    using C = GCfg<NSUB>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BARS);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + G_OFF_TSLOT);
-    uint64_t* full = bars;                        // [G_NST] TMA → MMA
-    uint64_t* empty = bars + G_NST;               // [G_NST] MMA → TMA
-    uint64_t* acc_full = bars + 2 * G_NST;        // [2]
-    uint64_t* acc_empty = bars + 2 * G_NST + 2;   // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::OFF_TSLOT);
+    uint64_t* full = bars;                         // [NST] TMA → MMA
+    uint64_t* empty = bars + C::NST;               // [NST] MMA → TMA
+    uint64_t* acc_full = bars + 2 * C::NST;        // [2]
+    uint64_t* acc_empty = bars + 2 * C::NST + 2;   // [2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // work decomposition: `units` row groups (GEMM1: the 64 pooled cells; FC: 1), each with m_tiles tiles of 128 rows
+    // work decomposition: `units` row groups (GEMM1: the 64 pooled cells; FC: 1), each with m_tiles tiles of 128 rows; the n_tiles
+    // weight tiles of 64 columns are taken NSUB at a time
     const int m_valid = p.m_valid_dev ? *p.m_valid_dev : p.m_valid;            // valid rows inside one unit
     const int m_tiles = (m_valid + G_BM - 1) / G_BM;
     const int KS = p.k_splits > 1 ? p.k_splits : 1;          // split-K: an item covers k_stages consecutive K stages of one output tile
-    const int n_items = p.units * m_tiles * p.n_tiles * KS;
+    const int n_groups = (p.n_tiles + NSUB - 1) / NSUB;
+    const int n_items = p.units * m_tiles * n_groups * KS;
     const int k_stages_total = p.K / G_BK, k_stages = k_stages_total / KS;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < G_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < C::NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tslot, 128);
+    if (warp == 5) tmem_alloc(tslot, 2 * C::ACC_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -62,21 +75,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
             const size_t plane_stride = (size_t)p.a_rows * 8;                 // elements between two 8-channel K planes of A
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int split = item % KS, tile = item / KS;
-                const int nt = tile % p.n_tiles, mi = tile / p.n_tiles;
+                const int ng = tile % n_groups, mi = tile / n_groups;
                 const int unit = mi / m_tiles, mt = mi % m_tiles;
+                const int nsub = min(NSUB, p.n_tiles - ng * NSUB);
                 const size_t row0 = (size_t)unit * p.unit_rows + (size_t)mt * G_BM;
                 const __nv_bfloat16* a_base = p.A + row0 * 8;
-                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(p.B) + ((size_t)nt * k_stages_total + (size_t)split * k_stages) * G_B_STAGE;
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(p.B) + ((size_t)(ng * NSUB) * k_stages_total + (size_t)split * k_stages) * G_B_STAGE;
+                const size_t b_tile_stride = (size_t)k_stages_total * G_B_STAGE;      // bytes between two 64-column weight tiles
                 int plane = (split * k_stages * (G_BK / 8)) % p.a_plane_mod;
                 for (int ks = 0; ks < k_stages; ++ks, ++it, b_src += G_B_STAGE) {
-                    const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                    const uint32_t s = it % C::NST, ph = (it / C::NST) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], G_STAGE);
-                    uint8_t* dst = smem + s * G_STAGE;
+                    mbar_arrive_expect_tx(&full[s], G_A_STAGE + nsub * G_B_STAGE);
+                    uint8_t* dst = smem + s * C::STAGE;
                     const __nv_bfloat16* a_src = a_base + (size_t)plane * plane_stride;
 #pragma unroll
                     for (int j = 0; j < G_BK / 8; ++j) bulk_g2s(dst + j * (G_BM * 16), a_src + (size_t)j * plane_stride, G_BM * 16, &full[s]);
-                    bulk_g2s(dst + G_A_STAGE, b_src, G_B_STAGE, &full[s]);
+#pragma unroll
+                    for (int t = 0; t < NSUB; ++t) if (t < nsub) bulk_g2s(dst + G_A_STAGE + t * G_B_STAGE, b_src + (size_t)t * b_tile_stride, G_B_STAGE, &full[s]);
                     plane += G_BK / 8; if (plane >= p.a_plane_mod) plane -= p.a_plane_mod;
                 }
             }
@@ -91,19 +107,25 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
             uint32_t it = 0, ait = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
                 const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+                const int ng = (item / KS) % n_groups;
+                const int nsub = min(NSUB, p.n_tiles - ng * NSUB);
                 mbar_wait(&acc_empty[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + as * G_BN;
+                const uint32_t acc = tmem_base + as * C::ACC_COLS;
                 uint32_t accumulate = 0;
                 for (int ks = 0; ks < k_stages; ++ks, ++it) {
-                    const uint32_t s = it % G_NST, ph = (it / G_NST) & 1;
+                    const uint32_t s = it % C::NST, ph = (it / C::NST) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint64_t so = (uint64_t)(s * (G_STAGE >> 4));
+                    const uint64_t so = (uint64_t)(s * (C::STAGE >> 4));
                     if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < G_BK / 16; ++kk)
-                            umma_bf16(acc, a_desc0 + so + (uint64_t)(2 * kk * G_BM), b_desc0 + so + (uint64_t)(2 * kk * G_BN), IDESC, kk == 0 ? accumulate : 1u);
+#pragma unroll
+                            for (int t = 0; t < NSUB; ++t)
+                                if (t < nsub)
+                                    umma_bf16(acc + t * G_BN, a_desc0 + so + (uint64_t)(2 * kk * G_BM), b_desc0 + so + (uint64_t)(t * (G_B_STAGE >> 4) + 2 * kk * G_BN), IDESC,
+                                              kk == 0 ? accumulate : 1u);
                         umma_commit(&empty[s]);
                         if (ks == k_stages - 1) umma_commit(&acc_full[as]);
                     }
@@ -117,21 +139,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
             const int split = item % KS, tile = item / KS;
-            const int nt = tile % p.n_tiles, mi = tile / p.n_tiles;
+            const int ng = tile % n_groups, mi = tile / n_groups;
             const int unit = mi / m_tiles, mt = mi % m_tiles;
+            const int nsub = min(NSUB, p.n_tiles - ng * NSUB);
             const int r = mt * G_BM + warp * 32 + lane;          // row inside the unit
             mbar_wait(&acc_full[as], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * G_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * C::ACC_COLS;
 #pragma unroll 1
-            for (int c0 = 0; c0 < G_BN; c0 += 32) {
+            for (int c0 = 0; c0 < nsub * G_BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
                 if (r < m_valid) {
                     if (p.mode == GEMM_OUT_FEAT) {
                         // 1x1-conv output → the FC layers' A layout: feature k' = unit*32 + channel, plane = k'/8, row = board.
-                        // columns 0-31 = policy head, 32-63 = value head.
+                        // columns 0-31 = policy head, 32-63 = value head.  (NSUB = 1 only.)
                         __nv_bfloat16* dst = (c0 == 0) ? p.out_feat0 : p.out_feat1;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -153,13 +176,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
                     } else {
                         // split-K: raw partial sums into slab `split` (bias / ReLU are applied by the consumer, k_policy_value)
                         float* dst = p.out_rows + (size_t)split * p.split_stride + (size_t)r * p.ldo;
+                        const int n0 = ng * NSUB * G_BN + c0;
+                        if (p.k_splits >= 1 && (p.ldo & 3) == 0 && n0 + 32 <= p.ldo) {
+                            // raw partial sums, 16-byte stores (a thread owns 32 consecutive columns of its row; the row pitch is a multiple of 4 floats):
+                            // 4x fewer store instructions than scalar stores — with one row per lane every store instruction is 32 separate sectors
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = nt * G_BN + c0 + j;
-                            if (n < p.n_valid) {
-                                float a = __uint_as_float(v[j]);
-                                if (p.k_splits < 1) { a += p.bias[n]; if (p.relu) a = fmaxf(a, 0.0f); }      // k_splits >= 1: raw sums, the consumer adds bias / ReLU
-                                dst[n] = a;
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<uint4*>(dst + n0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int n = n0 + j;
+                                if (n < p.n_valid) {
+                                    float a = __uint_as_float(v[j]);
+                                    if (p.k_splits < 1) { a += p.bias[n]; if (p.relu) a = fmaxf(a, 0.0f); }      // k_splits >= 1: raw sums, the consumer adds bias / ReLU
+                                    dst[n] = a;
+                                }
                             }
                         }
                     }
@@ -171,7 +203,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(const GemmParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 128);
+    if (warp == 5) tmem_dealloc(tmem_base, 2 * C::ACC_COLS);
 }
 
 // adaptive_avg_pool2d (H x W → PH x PW, windows [floor(i*H/PH), ceil((i+1)*H/PH))) of the trunk output, written as the
@@ -229,11 +261,19 @@ __global__ void __launch_bounds__(256) k_pool(PoolParams p) {
 
 }  // namespace
 
-int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
+template <int NSUB> static int gemm_tc_launch_n(const GemmParams& p, int grid, cudaStream_t s) {
     static bool done = false;
-    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM); if (e) return (int)e; done = true; }
-    k_gemm_tc<<<grid, G_THREADS, G_SMEM, s>>>(p);
+    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GCfg<NSUB>::SMEM); if (e) return (int)e; done = true; }
+    k_gemm_tc<NSUB><<<grid, G_THREADS, GCfg<NSUB>::SMEM, s>>>(p);
     return (int)cudaGetLastError();
+}
+int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
+    static const int force = getenv("AZ_GEMM_NSUB") ? atoi(getenv("AZ_GEMM_NSUB")) : 0;      // profiling switch (1 = the narrow item everywhere)
+    int nsub = p.mode == GEMM_OUT_FEAT ? 1 : (p.n_tiles >= 4 ? 4 : (p.n_tiles >= 2 ? 2 : 1));
+    if (force == 1 || force == 2 || force == 4) nsub = p.mode == GEMM_OUT_FEAT ? 1 : std::min(force, nsub);
+    if (nsub == 4) return gemm_tc_launch_n<4>(p, grid, s);
+    if (nsub == 2) return gemm_tc_launch_n<2>(p, grid, s);
+    return gemm_tc_launch_n<1>(p, grid, s);
 }
 int pool_launch(const PoolParams& p, int grid, cudaStream_t s) {
     const size_t smem = (size_t)POOL_NB * (p.board_pitch + 1) * 16;

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
     float mx = -3.4e38f;
     for (int i = lane; i < p.A; i += 32) {
         float v = p.bias_p[i];
-        for (int sidx = 0; sidx < p.n_split_p; ++sidx) v += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.A + i];
+        for (int sidx = 0; sidx < p.n_split_p; ++sidx) v += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.ld_part + i];
         lg[i] = v; mx = fmaxf(mx, v);
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams
         const int i = tid + k * PV_WIDE_THREADS;
         if (i < p.A) {
             float x = p.bias_p[i];
-            for (int sidx = 0; sidx < p.n_split_p; ++sidx) x += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.A + i];
+            for (int sidx = 0; sidx < p.n_split_p; ++sidx) x += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.ld_part + i];
             v[k] = x; mx = fmaxf(mx, x);
         }
     }
