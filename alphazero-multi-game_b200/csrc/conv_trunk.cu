@@ -58,8 +58,12 @@ __device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* r
     }
 }
 
+// 8 epilogue warps (warps 0-3: rows 0-127 of the item, warps 4-7: rows 128-255; a warp reads TMEM lanes 32 (w % 4) ...), warp 8 = TMA
+// producer, warp 9 = MMA issuer.  With 4 epilogue warps the stem (K = 16 per tap: 18 MMAs per item) was bound by the epilogue
+// draining 256 x 128 outputs per item.
+constexpr int CONV1_THREADS = 320;
 template <int CIN>
-__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p) {
+__global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p) {
     using C = Cfg<CIN>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
@@ -79,18 +83,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
     const int n_items = (n_rows + CONV_BM - 1) / CONV_BM;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
         for (int i = 0; i < C::NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < C::COUT; i += CONV_THREADS) sBias[i] = p.bias[i];
-    if (warp == 5) tmem_alloc(tslot, 512);
+    for (int i = threadIdx.x; i < C::COUT; i += CONV1_THREADS) sBias[i] = p.bias[i];
+    if (warp == 9) tmem_alloc(tslot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tslot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
         uint32_t wit = 0, ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
             }
             __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         // One thread issues every tcgen05.mma of the CTA, so the issue loop itself is on the critical path: a 128x128x16
         // MMA occupies the tensor pipe for 64 cycles and the loop must spend fewer instructions than that per MMA.
@@ -167,16 +171,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 0-3) =====================
+        // ===================== epilogue (warps 0-7) =====================
         const bool has_res = p.resid != nullptr, relu = p.relu != 0;
         const size_t p_total = (size_t)p.p_total;
+        const int mt = warp >> 2, wq = warp & 3;             // M tile of the item, TMEM lane quarter
         uint32_t ait = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ait) {
             const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
             bool waited = false;
-#pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                const int row = item * CONV_BM + mt * 128 + warp * 32 + lane;
+            {
+                const int row = item * CONV_BM + mt * 128 + wq * 32 + lane;
                 const size_t grow = (size_t)CONV_GUARD + row;
                 const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
                 uint4 res[16];                                    // the residual does not depend on the MMAs: fetch it first
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                     for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.resid + ((size_t)q * p_total + grow) * 8);
                 }
                 if (!waited) { mbar_wait(&acc_full[as], ph); tc_fence_after(); waited = true; }
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256 + mt * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256 + mt * 128;
                 uint32_t ra[32], rb[32];                          // TMEM → registers, software-pipelined
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait();
@@ -198,14 +202,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3(const ConvParams p)
                 tmem_ld32(taddr + 96, rb);
                 if (!(p.dbg & 2)) pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
-                if (mt == 1) { tc_fence_before(); mbar_arrive(&acc_empty[as]); }      // both accumulators of this stage drained
+                tc_fence_before(); mbar_arrive(&acc_empty[as]);                        // this thread's part of the stage's two accumulators is drained (256 arrivals)
                 if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 
@@ -601,10 +605,10 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
     cudaError_t err;
     if (cin == 32) {     // chess stem: 18 planes padded to 32 channels
         if (!attr_done[3]) { err = cudaFuncSetAttribute(k_conv3x3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::SMEM); if (err) return (int)err; attr_done[3] = true; }
-        k_conv3x3<32><<<grid, CONV_THREADS, Cfg<32>::SMEM, stream>>>(p);
+        k_conv3x3<32><<<grid, CONV1_THREADS, Cfg<32>::SMEM, stream>>>(p);
     } else if (cin == 16) {
         if (!attr_done[0]) { err = cudaFuncSetAttribute(k_conv3x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::SMEM); if (err) return (int)err; attr_done[0] = true; }
-        k_conv3x3<16><<<grid, CONV_THREADS, Cfg<16>::SMEM, stream>>>(p);
+        k_conv3x3<16><<<grid, CONV1_THREADS, Cfg<16>::SMEM, stream>>>(p);
     } else if (conv_uses_pair(cin, p.row_pitch) && p.row_pitch + 1 > PAIR_HALO) {          // boards 16..19 wide: K-split stages
         static bool wide_done = false;
         if (!wide_done) { err = cudaFuncSetAttribute(k_conv3x3_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg::SMEM); if (err) return (int)err; wide_done = true; }
@@ -628,7 +632,7 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
         if (err) return (int)err;
     } else if (cin == 128) {
         if (!attr_done[1]) { err = cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM); if (err) return (int)err; attr_done[1] = true; }
-        k_conv3x3<128><<<grid, CONV_THREADS, Cfg<128>::SMEM, stream>>>(p);
+        k_conv3x3<128><<<grid, CONV1_THREADS, Cfg<128>::SMEM, stream>>>(p);
     } else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
 }

@@ -366,7 +366,7 @@ struct Net {
         g3.k_splits = fc_splits; g3.split_stride = (size_t)max_boards * 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         fe_rec(5, s);
-        nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * ld_part, (size_t)max_boards * 256, p_splits, fc_splits, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256, ld_part};
+        nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * ld_part, (size_t)max_boards * 256, p_splits, fc_splits, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256, n_dev == nullptr ? 1 : 0, ld_part};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
         fe_rec(6, s);
         return 0;

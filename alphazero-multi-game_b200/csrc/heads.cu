@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams
 #pragma unroll
     for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
         const int i = tid + k * PV_WIDE_THREADS;
-        if (i < p.A) { p.logits[(size_t)b * p.A + i] = v[k]; p.policy[(size_t)b * p.A + i] = expf(v[k] - mx) * inv; }
+        if (i < p.A) { if (p.want_logits) p.logits[(size_t)b * p.A + i] = v[k]; p.policy[(size_t)b * p.A + i] = expf(v[k] - mx) * inv; }      // logits: API path only (az_engine_nn_forward)
     }
     if (warp == 0) {      // value head: tanh(relu(hidden) . w2 + b2)
         float d = 0.0f;

@@ -15,6 +15,7 @@ struct OutParams {
     float* policy; float* value;
     const int* n_boards_dev; int n_boards;
     int A, hidden_n;
+    int want_logits;                                         // wide heads: also store the final logits (az_engine_nn_forward); the search needs the policy only
     int ld_part;                                             // row pitch (floats) of the policy partial-sum slabs (>= A, a multiple of 4: the GEMM epilogue stores float4)
 };
 
