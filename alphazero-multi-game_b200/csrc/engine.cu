@@ -29,6 +29,7 @@ void set_error(const std::string& s) { g_error = s; }
 #include "conv_trunk.cuh"
 #include "heads.cuh"
 #include "gemm_tc.cuh"
+#include "head_conv.cuh"
 
 namespace az {
 
@@ -63,13 +64,19 @@ AZ_D void put3(__nv_bfloat16* img, int K, int n, int k, float v) {
 }
 // both 1x1 convs as one [64 x C] matrix (rows 0-31 policy, 32-63 value), BatchNorm scale folded in; b1 = BN shifts
 __global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restrict__ pbn, const float* __restrict__ vcw, const float* __restrict__ vbn,
-                           __nv_bfloat16* g1, float* b1, int C) {
+                           __nv_bfloat16* g1, float* b1, int C, __nv_bfloat16* h1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 64) { const float* bn = idx < 32 ? pbn : vbn; const int o = idx & 31; b1[idx] = bn[32 + o] - bn[64 + o] * bn_scale(bn, 32, o); }
     if (idx >= 64 * C) return;
     const int c = idx % C, n = idx / C, o = n & 31;
     const float* cw = n < 32 ? pcw : vcw; const float* bn = n < 32 ? pbn : vbn;
-    put3(g1, C, n, c, cw[(size_t)o * C + c] * bn_scale(bn, 32, o));
+    const float wf = cw[(size_t)o * C + c] * bn_scale(bn, 32, o);
+    put3(g1, C, n, c, wf);
+    if (h1 && C == 128) {       // the fused heads kernel's image (head_conv.cuh): bf16 hi / lo pair of the same folded weight
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wf);
+        h1[nn::head_conv_weight_index(0, n, c)] = hi;
+        h1[nn::head_conv_weight_index(1, n, c)] = __float2bfloat16_rn(wf - __bfloat162float(hi));
+    }
 }
 // FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the 1x1-conv GEMM writes
 // (cell*32 + ch); rows >= n_rows stay zero (N padded to 256)
@@ -142,6 +149,7 @@ struct NetWeights {            // device images
     float *b1x1 = nullptr, *pfc_b = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;   // fp32 biases / tiny last layer
     float* zero_bias = nullptr;                                                                          // [128] for the accumulating channel-slice launches
     __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
+    __nv_bfloat16* h1_w = nullptr;                                                                        // fused heads kernel: hi / lo image of the folded 1x1 weights (head_conv.cuh)
     float* blob = nullptr; size_t blob_bytes = 0;                                                        // device copy of the last AZW1 blob
     int blocks = -1, in_planes = -1;                                                                     // shape the images above were allocated for
 };
@@ -252,7 +260,7 @@ struct Net {
             AZ_CUDA_CHECK(cudaMemsetAsync(w.zero_bias, 0, nn::CONV_COUT * 4, st));
             if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, (size_t)p_tiles * 64) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
                 dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat)) ||
-                dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat))) return -1;
+                dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat)) || dev_alloc(&w.h1_w, nn::head_conv_weight_elems())) return -1;
             AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat) * 2, st));      // rows >= A stay zero
             AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, (size_t)p_tiles * 64 * 4, st));
             w.blocks = nb; w.in_planes = ip;
@@ -268,7 +276,7 @@ struct Net {
                     k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[wi(l, co, ci)], ci == 0 ? w.conv_b[bi(l, co)] : nullptr, C, cin_total,
                                                                  co * nn::CONV_COUT, ci * nn::CONV_COUT, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
         }
-        k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C);
+        k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C, w.h1_w);
         k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat, p_split);
         k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat, 1);
         AZ_CUDA_CHECK(cudaGetLastError());
@@ -290,7 +298,7 @@ struct Net {
         w.conv_w.clear(); w.conv_b.clear();
         for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b, &w.blob, &w.zero_bias}) { cudaFree(*p); *p = nullptr; }
         w.blob_bytes = 0; w.blocks = -1; w.in_planes = -1;
-        for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img}) { cudaFree(*p); *p = nullptr; }
+        for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img, &w.h1_w}) { cudaFree(*p); *p = nullptr; }
         loaded = false;
     }
     void destroy() {
@@ -347,14 +355,22 @@ struct Net {
         cp.relu = 1; cp.reverse = 0; cp.pdl = 0;
         fe_rec(1, s);
         // heads: pool → 1x1 convs (GEMM, bf16 features in the FC operand layout) → policy FC / value FC1 (GEMMs, fp32 out)
-        nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
-        AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
-        fe_rec(2, s);
-        nn::GemmParams g1{}; g1.A = pooled; g1.B = w.g1_w; g1.bias = w.b1x1; g1.a_rows = 64 * boards_cap; g1.a_plane_mod = 2 * (C / 8); g1.K = 3 * C; g1.n_tiles = 1; g1.n_valid = 64;
-        g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
-        g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
-        AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
-        fe_rec(3, s);
+        static const bool fuse_heads = getenv("AZ_NO_HEAD_FUSION") == nullptr;      // profiling / parity switch: the two-kernel path
+        if (fuse_heads && nn::head_conv_supported(C, board_pitch, H, W)) {
+            // 1x1 convs on the full-resolution trunk output, pooling in the epilogue (head_conv.cu): one pass over X, no pooled intermediate
+            nn::HeadConvParams hp{X, w.h1_w, w.b1x1, n_dev, n_fixed, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, featP, featV, boards_cap, 256, alt_order ? 1 : 0};
+            AZ_CHECK(nn::head_conv_launch(hp, n_sms, s) == 0, "fused heads launch failed"); ++launches;
+            fe_rec(2, s); fe_rec(3, s);
+        } else {
+            nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
+            AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
+            fe_rec(2, s);
+            nn::GemmParams g1{}; g1.A = pooled; g1.B = w.g1_w; g1.bias = w.b1x1; g1.a_rows = 64 * boards_cap; g1.a_plane_mod = 2 * (C / 8); g1.K = 3 * C; g1.n_tiles = 1; g1.n_valid = 64;
+            g1.units = 64; g1.unit_rows = boards_cap; g1.m_valid_dev = n_dev; g1.m_valid = n_fixed; g1.relu = 1; g1.mode = nn::GEMM_OUT_FEAT;
+            g1.out_feat0 = featP; g1.out_feat1 = featV; g1.feat_rows = boards_cap; g1.feat_lo_plane = 256;
+            AZ_CHECK(nn::gemm_tc_launch(g1, n_sms, s) == 0, "1x1 conv gemm launch failed"); ++launches;
+            fe_rec(3, s);
+        }
         // the two FC GEMMs run split-K (fc_splits x more work items: a 4096 x 256 x 6144 GEMM is only 128 tiles); the raw partial
         // sums are added, with bias / ReLU, by k_policy_value
         nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
@@ -483,7 +499,7 @@ struct EngineT : EngineBase {
         cudaDeviceSynchronize();
         if (wave_timing && wt_n) {
             fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
-            fprintf(stderr, "  evaluator: stem %.3f, trunk %.3f, pool %.3f, 1x1 gemm %.3f, policy fc %.3f, value fc %.3f, softmax/tanh %.3f ms\n", wt_fwd[0] / wt_n, wt_fwd[1] / wt_n,
+            fprintf(stderr, "  evaluator: stem %.3f, trunk %.3f, pool (or fused 1x1 conv + pool) %.3f, 1x1 gemm %.3f, policy fc %.3f, value fc %.3f, softmax/tanh %.3f ms\n", wt_fwd[0] / wt_n, wt_fwd[1] / wt_n,
                     wt_fwd[2] / wt_n, wt_fwd[3] / wt_n, wt_fwd[4] / wt_n, wt_fwd[5] / wt_n, wt_fwd[6] / wt_n);
         }
         for (auto& g : groups) {
