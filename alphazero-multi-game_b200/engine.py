@@ -169,8 +169,12 @@ class Engine:
         except Exception:
             pass
 
-    def load_weights(self, blob: bytes):
-        self._check(self.lib.az_engine_load_weights(self.h, blob, len(blob)))
+    def load_weights(self, blob, nbytes=None):
+        """blob: bytes, or the address (int) of `nbytes` bytes of host memory (e.g. a pinned buffer)."""
+        if isinstance(blob, int):
+            self._check(self.lib.az_engine_load_weights(self.h, C.c_void_p(blob), nbytes))
+        else:
+            self._check(self.lib.az_engine_load_weights(self.h, blob, len(blob)))
 
     def reset_games(self):
         self._check(self.lib.az_engine_reset_games(self.h))

@@ -15,18 +15,22 @@ def shard_slots(total_slots: int, world: int, rank: int):
 def all_gather_samples(dist, records: torch.Tensor, n_local: int, record_bytes: int):
     """records: uint8 tensor holding `capacity` fixed-size records of which the first n_local are valid (the engine's
     az_engine_drain_samples_device output).  Every rank gets all valid records of all ranks, rank order preserved:
-    returns (uint8 tensor [total, record_bytes], list of per-rank counts).  Fixed-capacity buffers + a count vector, no
-    all-to-all: < 1 MB/s/GPU at the tensor-bound move rate."""
+    returns (uint8 tensor [total, record_bytes], list of per-rank counts).  A count vector first, then equal chunks of max(count)
+    records (not the whole fixed-capacity buffer), no all-to-all: < 1 MB/s/GPU at the tensor-bound move rate."""
     world = dist.get_world_size()
     cap = records.numel() // record_bytes
     assert 0 <= n_local <= cap
     counts = torch.zeros(world, dtype=torch.int64, device=records.device)
     dist.all_gather_into_tensor(counts, torch.tensor([n_local], dtype=torch.int64, device=records.device))
-    gathered = torch.empty(world * records.numel(), dtype=torch.uint8, device=records.device)
-    dist.all_gather_into_tensor(gathered, records.contiguous().view(-1))
     cl = [int(c) for c in counts.tolist()]
-    g = gathered.view(world, cap, record_bytes)
-    out = torch.cat([g[r, :cl[r]] for r in range(world)], 0) if sum(cl) else g[0, :0]
+    m = max(cl)                                     # every rank sends max(count) records: equal-size chunks, but only as many as are needed
+    rec = records.view(cap, record_bytes)
+    if m == 0:
+        return rec[:0], cl
+    gathered = torch.empty(world * m * record_bytes, dtype=torch.uint8, device=records.device)
+    dist.all_gather_into_tensor(gathered, rec[:m].contiguous().view(-1))
+    g = gathered.view(world, m, record_bytes)
+    out = torch.cat([g[r, :cl[r]] for r in range(world)], 0)
     return out, cl
 
 

@@ -263,17 +263,19 @@ def main():
     # one self-play move; (D2H) finished-game samples into pinned host memory + the chosen actions + the counters;
     # for N > 1 the finished-game samples are also all-gathered over NCCL (the path's only exchange step).
     h2d = len(blob)
+    blob_pinned = torch.frombuffer(bytearray(blob), dtype=torch.uint8).pin_memory()      # the step's input lives in pinned host memory
     if dist is not None:
         from alphazero_multi_game_b200 import gather as GA
         cap = 32 * args.slots
         rec_bytes = eng.sample_layout().record_bytes
         dev_samples = torch.zeros(cap * rec_bytes, dtype=torch.uint8, device="cuda")
+        GA.all_gather_samples(dist, dev_samples, 1, rec_bytes)      # untimed warm-up of the collective (NCCL sets up its channels on first use)
     barrier()
     e0 = eng.stats()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        eng.load_weights(blob)
+        eng.load_weights(blob_pinned.data_ptr(), h2d)
         eng.play(1)
         if dist is None:
             smp = eng.drain_samples(out=samples_np)
@@ -290,7 +292,7 @@ def main():
     t_e2e = allreduce(t_e2e, dist.ReduceOp.MAX) if dist else t_e2e
     sims_e2e = allreduce(float(e1["simulations"] - e0["simulations"]), dist.ReduceOp.SUM) if dist else float(e1["simulations"] - e0["simulations"])
     e2e = {"value": sims_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // max(args.steps, 1),
-           "what": "load_weights(host blob) + play(1) + drain_samples(pinned host) + last_actions + stats per step"
+           "what": "load_weights(pinned host blob) + play(1) + drain_samples(pinned host) + last_actions + stats per step"
                    + ("; + NCCL all-gather of finished-game samples" if dist else "")}
 
     # ---- roofline of the dominant kernel (3x3 conv 128->128 on tcgen05), timed alone with CUDA events ------
