@@ -238,8 +238,8 @@ struct PairCfg {
     static constexpr int OFF_A = W_BYTES;
     static constexpr int OFF_BIAS = OFF_A + 2 * A_STAGE;
     static constexpr int OFF_BARS = OFF_BIAS + CONV_COUT * 4;
-    static constexpr int OFF_TSLOT = OFF_BARS + 16 * 8;
-    static constexpr int SMEM = OFF_TSLOT + 16;                 // 231,056 B
+    static constexpr int OFF_TSLOT = OFF_BARS + 24 * 8;
+    static constexpr int SMEM = OFF_TSLOT + 16;                 // 231,120 B
 };
 
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvParams p) {
@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
     uint64_t* a_empty = bars + 2;       // [2] MMA commit (multicast) → own TMA producer
     uint64_t* acc_full = bars + 4;      // [2] MMA commit (multicast) → own epilogue
     uint64_t* acc_empty = bars + 6;     // [2] leader only: 4 local + 4 remote epilogue warps → MMA issuer
-    uint64_t* w_full = bars + 8;        // [1] own weight half loaded (+ in the leader: the peer's)
+    uint64_t* w_full = bars + 8;        // [9] own weight half loaded (+ in the leader: the peer's), one barrier per tap: the first item's MMAs start
+                                        //     behind tap 0's 16 KB instead of behind all 147 KB — the rest streams in under them
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
     if (threadIdx.x == 0) {
         const uint32_t full_count = rank == 0 ? 2 : 1;      // the leader's "full" barriers also take the peer relay's arrival
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-        mbar_init(w_full, full_count);
+        for (int i = 0; i < 9; ++i) mbar_init(&w_full[i], full_count);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < CONV_COUT; i += CONV_THREADS) sBias[i] = p.bias[i];
@@ -279,10 +280,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
         if (warp == 4) {
             // ===================== TMA producer =====================
             if (lane == 0) {
-                mbar_arrive_expect_tx(w_full, C::W_BYTES);
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * C::W_BYTES;
-                for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
-                grid_dep_wait();            // PDL: everything above ran under the previous layer's tail; its activations are needed from here on
+                auto load_tap = [&](int tap) {
+                    mbar_arrive_expect_tx(&w_full[tap], C::WTAP);
+                    bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, &w_full[tap]);
+                };
+                // issue order = consumption order: tap 0, the first item's activations, taps 1-8, then the steady-state stage loop.
+                // PDL: the weights do not depend on the previous layer and go out before griddepcontrol.wait; activations after it.
+                load_tap(0);
+                if (p.dbg & 64) for (int tap = 1; tap < 9; ++tap) load_tap(tap);        // profiling experiment: all weights ahead of the first stage
+                grid_dep_wait();
                 grid_dep_launch();          // (after the wait, so a dependent grid can only start once this grid's own prerequisites are complete)
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
@@ -294,20 +301,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                     const size_t row0 = (size_t)CONV_GUARD + (size_t)item_eff * 256 + rank * 128 - PAIR_HALO;
                     for (int kc = 0; kc < 16; ++kc)
                         bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
+                    if (ait == 0 && !(p.dbg & 64)) for (int tap = 1; tap < 9; ++tap) load_tap(tap);
                 }
             }
             __syncwarp();
         } else if (warp == 5 && rank != 0) {
             // ===================== relay (peer CTA): my stage is full → second arrival on the leader's barrier =====================
             if (lane == 0) {
-                mbar_wait(w_full, 0);
-                mbar_arrive_cluster(w_full, 0);
+                // forward "landed" to the leader in the order the leader consumes: tap 0, first stage, taps 1-8, then the stages
+                mbar_wait(&w_full[0], 0);
+                mbar_arrive_cluster(&w_full[0], 0);
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
                     const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
                     if ((p.dbg & 8) && ait >= 2) continue;
                     mbar_wait(&a_full[as], ph);
                     mbar_arrive_cluster(&a_full[as], 0);
+                    if (ait == 0) for (int tap = 1; tap < 9; ++tap) { mbar_wait(&w_full[tap], 0); mbar_arrive_cluster(&w_full[tap], 0); }
                 }
             }
             __syncwarp();
@@ -329,8 +339,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                     a_tap0[tap] = a_desc0 + (uint64_t)(int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));     // tap shift in rows == 16-byte units
                 const long long t_begin = p.trace ? clock64() : 0;
                 long long wait_all = 0;
-                mbar_wait_cluster(w_full, 0);
-                if (p.trace && lane == 0) p.trace[1024 + 2 * first_item] = clock64() - t_begin;      // cycles until both weight halves are resident
+                mbar_wait_cluster(&w_full[0], 0);
+                if (p.trace && lane == 0) p.trace[1024 + 2 * first_item] = clock64() - t_begin;      // cycles until tap 0 of both weight halves is resident
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
                     const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                     if (elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (ait == 0 && tap > 0) mbar_wait_cluster(&w_full[tap], 0);      // first item only: the weights stream in tap by tap behind it
                             const uint64_t a_tap = a_tap0[tap] + a_off;
                             const uint64_t b_tap = b_desc0 + (uint64_t)(tap * (C::WTAP >> 4));
 #pragma unroll

@@ -313,12 +313,13 @@ struct Net {
     int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
         static const bool alt_order = getenv("AZ_CONV_NO_ALT") == nullptr;      // profiling switch for the alternating item order
         static const bool pdl = getenv("AZ_CONV_NO_PDL") == nullptr;            // profiling switch for programmatic dependent launch of the trunk layers
+        static const int conv_dbg = getenv("AZ_CONV_WEIGHTS_FIRST") ? 64 : 0;   // profiling switch: all nine weight taps ahead of the first activation stage
         AZ_CHECK(loaded, "no network weights loaded (az_engine_load_weights)");
         cudaStream_t cs = conv_stream ? conv_stream : s;                          // stream / SM count of the trunk layers
         const int cs_sms = conv_stream ? n_sms_conv : n_sms;
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
-        cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1;
+        cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1; cp.dbg = conv_dbg;
         const size_t slice = (size_t)(nn::CONV_COUT / 8) * p_total * 8;          // elements per 128-channel slice of an activation buffer
         for (int co = 0; co < NS; ++co) {                                         // stem: one launch per 128 output channels
             cp.in = in16; cp.out = X + co * slice; cp.resid = nullptr; cp.w = w.conv_w[wi(0, co, 0)]; cp.bias = w.conv_b[bi(0, co)];
