@@ -118,3 +118,15 @@ def test_trunk_256_channels_matches_fp32(game, board, planes):
         m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.1; m.v_fc2.weight *= 0.2
         m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
     _check(m, 23, 32, f"256ch-game{game}-{board}x{board}", game=game, board=board)
+
+
+def test_two_kernel_heads_path_still_matches_fp32():
+    """The fused heads kernel (head_conv.cu) is the default on 128-channel trunks; the k_pool + 1x1-GEMM path it replaced stays in use for
+    256-channel trunks and Go 19x19.  AZ_NO_HEAD_FUSION=1 forces it on the Gomoku network too (the switch is read once per process, so this
+    runs the calibrated 0 / 1 / 10-block checks in a child process)."""
+    import os, subprocess, sys
+    env = dict(os.environ, AZ_NO_HEAD_FUSION="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_nn_gpu.py") + "::test_trunk_matches_fp32_calibrated_heads", "-x", "-q",
+                        "-m", "gpu"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
