@@ -605,6 +605,250 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
     if (warp == 5) tmem_dealloc2(tmem_base, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_trunk_pair — ALL residual-block layers of the trunk in ONE persistent launch of the weight-stationary CTA-pair kernel, for
+// 256-row boards (Gomoku 15x15: work item = exactly one board).
+//
+// Boards are independent: a conv layer of board b reads only board b's 256 rows (its halo rows above are the structural zero rows
+// of the position stream, the ones below only feed masked padding outputs).  So a CTA pair can carry ITS OWN boards — groups of
+// TRUNK_GROUP = 7 work items — through every layer with no grid-wide synchronisation: layer l+1 of item j needs layer l of item j,
+// which the same pair produced.  What changes against k_conv3x3_pair:
+//   * the pair walks (group, layer, item); activations ping-pong between X and Y in global memory, but a group is small enough
+//     (74 pairs x 7 boards x 2 x 64 KB = 68 MB) to stay in the 126 MB L2 for all 20 layers: the trunk stops touching HBM
+//     (per-layer launches: 670 MB per layer, the residual layers run 10 % slower because of it);
+//   * weights: a ROLLING per-tap reload — the issuer commits w_empty[tap] behind the last item of a layer, the producer refills
+//     that tap with the next layer's weights while the remaining taps of the old layer are still being multiplied;
+//   * the epilogue publishes "item j of this layer is in memory" on out_ready[j] in both CTAs (proxy fence + cluster-scope
+//     release: the next layer's TMA loads of either CTA read rows written by both), the producer waits for it before loading.
+constexpr int TRUNK_GROUP = 7;
+// taps [T0, T1) of one item: 8 MMAs per tap, straight-line; COMMIT_W: a tcgen05.commit on w_empty[tap] behind each tap
+template <int T0, int T1, bool COMMIT_W>
+__device__ __forceinline__ void trunk_issue_taps(uint32_t acc, const uint64_t* a_tap0, uint64_t a_off, uint64_t b_desc0, uint32_t idesc, uint64_t* w_empty) {
+#pragma unroll
+    for (int tap = T0; tap < T1; ++tap) {
+        const uint64_t a_tap = a_tap0[tap] + a_off;
+        const uint64_t b_tap = b_desc0 + (uint64_t)(tap * (PairCfg::WTAP >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+            umma2_bf16(acc, a_tap + (uint64_t)(2 * kk * (PairCfg::PLANE >> 4)), b_tap + (uint64_t)(2 * kk * (PairCfg::WPLANE >> 4)), idesc, (kk == 0 && tap == 0) ? 0u : 1u);
+        if (COMMIT_W) umma2_commit_both(&w_empty[tap]);
+    }
+}
+struct TrunkCfg : PairCfg {
+    static constexpr int OFF_TBIAS = PairCfg::OFF_BIAS;         // [2][128] fp32: the current layer's folded BatchNorm shifts, double-buffered by layer parity
+    static constexpr int OFF_TBARS = OFF_TBIAS + 2 * CONV_COUT * 4;
+    static constexpr int OFF_TTSLOT = OFF_TBARS + 40 * 8;
+    static constexpr int SMEM = OFF_TTSLOT + 16;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParams p) {
+    using C = TrunkCfg;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + C::OFF_A;
+    float* sBias2 = reinterpret_cast<float*>(smem + C::OFF_TBIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_TBARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::OFF_TTSLOT);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* acc_full = bars + 4;      // [2]
+    uint64_t* acc_empty = bars + 6;     // [2] leader only
+    uint64_t* w_full = bars + 8;        // [9] tap landed (leader: + the peer's relay)
+    uint64_t* w_empty = bars + 17;      // [9] the layer's last MMAs on this tap have completed (multicast commit): the tap may be refilled
+    uint64_t* out_ready = bars + 26;    // [TRUNK_GROUP] item j of the current layer is in memory: 4 local + 4 remote epilogue warps
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_rows = p.n_boards_dev ? (*p.n_boards_dev) * 256 : p.n_rows;
+    const int n_items = (n_rows + 255) / 256;
+    const int first_item = (int)cluster_id_x(), item_step = (int)n_clusters_x();
+    const int my_items = first_item < n_items ? (n_items - first_item + item_step - 1) / item_step : 0;
+    const int n_groups = (my_items + TRUNK_GROUP - 1) / TRUNK_GROUP;
+    const int L = p.n_layers;                                    // even: 2 per residual block
+
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = rank == 0 ? 2 : 1;
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < 9; ++i) { mbar_init(&w_full[i], full_count); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], 8);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc2(tslot, 256);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    if (my_items > 0) {
+        if (warp == 4) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                uint32_t ait = 0, wl = 0;                                 // activation stage counter, layer-instance counter
+                for (int g = 0; g < n_groups; ++g) {
+                    const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                    for (int l = 0; l < L; ++l, ++wl) {
+                        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w[l]) + (size_t)rank * C::W_BYTES;
+                        const __nv_bfloat16* in = (l & 1) ? p.Y : p.X;
+                        auto load_tap = [&](int tap) {
+                            mbar_wait(&w_empty[tap], (wl & 1) ^ 1);       // the previous layer is done with this tap (first layer: passes at once)
+                            mbar_arrive_expect_tx(&w_full[tap], C::WTAP);
+                            bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, &w_full[tap]);
+                        };
+                        load_tap(0);
+                        for (int j = 0; j < nj; ++j, ++ait) {
+                            const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
+                            const int item = first_item + (g * TRUNK_GROUP + j) * item_step;
+                            if (l > 0) {
+                                mbar_wait_cluster(&out_ready[j], (uint32_t)((l - 1) & 1));      // both CTAs have written layer l-1 of this board
+                                if (!(p.dbg & 2)) asm volatile("fence.proxy.async.global;" ::: "memory");   // their generic-proxy stores → this thread's TMA loads
+                            }
+                            mbar_wait(&a_empty[as], aph ^ 1);
+                            mbar_arrive_expect_tx(&a_full[as], C::A_STAGE);
+                            const size_t row0 = (size_t)CONV_GUARD + (size_t)item * 256 + rank * 128 - PAIR_HALO;
+                            for (int kc = 0; kc < 16; ++kc)
+                                bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
+                            if (j == 0) for (int tap = 1; tap < 9; ++tap) load_tap(tap);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5 && rank != 0) {
+            // ===================== relay (peer CTA) =====================
+            if (lane == 0) {
+                uint32_t ait = 0, wl = 0;
+                for (int g = 0; g < n_groups; ++g) {
+                    const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                    for (int l = 0; l < L; ++l, ++wl) {
+                        mbar_wait(&w_full[0], wl & 1);
+                        mbar_arrive_cluster(&w_full[0], 0);
+                        for (int j = 0; j < nj; ++j, ++ait) {
+                            const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                            mbar_wait(&a_full[as], ph);
+                            mbar_arrive_cluster(&a_full[as], 0);
+                            if (j == 0) for (int tap = 1; tap < 9; ++tap) { mbar_wait(&w_full[tap], wl & 1); mbar_arrive_cluster(&w_full[tap], 0); }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5) {
+            // ===================== MMA issuer (leader CTA; converged warp, tcgen05 under elect.sync) =====================
+            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            const uint64_t a_desc0 = smem_desc(smem_u32(sA) + PAIR_HALO * 16, C::PLANE, 128);
+            const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
+            uint64_t a_tap0[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) a_tap0[tap] = a_desc0 + (uint64_t)(int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));
+            uint32_t ait = 0, wl = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                for (int l = 0; l < L; ++l, ++wl) {
+                    for (int j = 0; j < nj; ++j, ++ait) {
+                        const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                        const bool first = j == 0, last = j == nj - 1;
+                        mbar_wait2_cluster(&a_full[as], ph, &acc_empty[as], ph ^ 1);
+                        tc_fence_after();
+                        const uint32_t acc = tmem_base + as * 128;
+                        const uint64_t a_off = (uint64_t)(as * (C::A_STAGE >> 4));
+                        // The issue loop must stay a handful of instructions per MMA (see k_conv3x3_pair), so the layer-boundary work is kept out
+                        // of it: three straight-line variants of the same 72 MMAs.
+                        if (!first && !last) {
+                            if (elect_one()) { trunk_issue_taps<0, 9, false>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); umma2_commit_both(&a_empty[as]); umma2_commit_both(&acc_full[as]); }
+                            __syncwarp();
+                        } else if (!first) {         // last item of the layer: hand each tap back to the producer as soon as its MMAs are issued
+                            if (elect_one()) { trunk_issue_taps<0, 9, true>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); umma2_commit_both(&a_empty[as]); umma2_commit_both(&acc_full[as]); }
+                            __syncwarp();
+                        } else {                     // first item: the layer's weights stream in behind it; wait for them three taps at a time (converged warp)
+                            for (int t = 0; t < 3; ++t) mbar_wait_cluster(&w_full[t], wl & 1);
+                            if (elect_one()) { if (last) trunk_issue_taps<0, 3, true>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); else trunk_issue_taps<0, 3, false>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); }
+                            __syncwarp();
+                            for (int t = 3; t < 6; ++t) mbar_wait_cluster(&w_full[t], wl & 1);
+                            if (elect_one()) { if (last) trunk_issue_taps<3, 6, true>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); else trunk_issue_taps<3, 6, false>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); }
+                            __syncwarp();
+                            for (int t = 6; t < 9; ++t) mbar_wait_cluster(&w_full[t], wl & 1);
+                            if (elect_one()) {
+                                if (last) trunk_issue_taps<6, 9, true>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty); else trunk_issue_taps<6, 9, false>(acc, a_tap0, a_off, b_desc0, IDESC, w_empty);
+                                umma2_commit_both(&a_empty[as]); umma2_commit_both(&acc_full[as]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        } else {
+            // ===================== epilogue (warps 0-3) =====================
+            const size_t p_total = (size_t)p.p_total;
+            uint32_t ait = 0;
+            int pending = -1;
+            // "item j of the current layer is in memory", to both CTAs' producers: the warp's stores are ordered before lane 0's cluster-scope
+            // release (the generic → async proxy fence sits on the consumer side, one thread, right before the TMA loads)
+            auto publish = [&](int j) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (!(p.dbg & 1)) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    mbar_arrive(&out_ready[j]);
+                    mbar_arrive_cluster(&out_ready[j], rank ^ 1);
+                }
+            };
+            for (int g = 0; g < n_groups; ++g) {
+                const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                for (int l = 0; l < L; ++l) {
+                    const bool has_res = (l & 1) != 0;                                   // second conv of a block: + the block's input (in place on X)
+                    __nv_bfloat16* out = (l & 1) ? p.X : p.Y;
+                    // this layer's bias → shared memory (the epilogue reads all 128 per row); the barrier also keeps the four warps within one
+                    // layer of each other, which is what makes the two-deep buffer safe
+                    float* bias = sBias2 + (l & 1) * CONV_COUT;
+                    bias[threadIdx.x] = p.bias[l][threadIdx.x];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int j = 0; j < nj; ++j, ++ait) {
+                        const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
+                        const int item = first_item + (g * TRUNK_GROUP + j) * item_step;
+                        const int row = item * 256 + (int)rank * 128 + warp * 32 + lane;
+                        const size_t grow = (size_t)CONV_GUARD + row;
+                        const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
+                        uint4 res[16];
+                        if (has_res) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.X + ((size_t)q * p_total + grow) * 8);
+                        }
+                        mbar_wait(&acc_full[as], ph);
+                        tc_fence_after();
+                        // deferred publication of the PREVIOUS item: its stores were issued a whole MMA phase ago, so the cluster-scope release fence
+                        // (which waits for this thread's outstanding stores) finds them drained
+                        if (pending >= 0) { publish(pending); pending = -1; }
+                        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128;
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32(taddr, ra);
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + 32, rb);
+                        pair_epi_chunk(ra, res, has_res, bias, 0, true, valid, out, p_total, grow);
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + 64, ra);
+                        pair_epi_chunk(rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow);
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + 96, rb);
+                        pair_epi_chunk(ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+                        pair_epi_chunk(rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow);
+                        // short groups (the tail of the board list) publish at once: with fewer than 3 items per layer the next layer's first load
+                        // would otherwise wait for a publication that only happens behind its own MMAs
+                        if (nj < 3 || (p.dbg & 4)) publish(j); else pending = j;
+                    }
+                }
+            }
+            if (pending >= 0) publish(pending);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 5) tmem_dealloc2(tmem_base, 256);
+}
+
 }  // namespace
 
 size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : (cin == 32 ? Cfg<32>::SMEM : Cfg<128>::SMEM); }
@@ -645,6 +889,22 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
         if (!attr_done[1]) { err = cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM); if (err) return (int)err; attr_done[1] = true; }
         k_conv3x3<128><<<grid, CONV1_THREADS, Cfg<128>::SMEM, stream>>>(p);
     } else return (int)cudaErrorInvalidValue;
+    return (int)cudaGetLastError();
+}
+
+bool trunk_fused_supported(int channels, int board_pitch, int n_layers) { return channels == CONV_COUT && board_pitch == 256 && n_layers >= 2 && n_layers % 2 == 0 && n_layers <= TRUNK_MAX_LAYERS; }
+
+int trunk_launch(const TrunkParams& p, int grid, cudaStream_t stream) {
+    static bool done = false;
+    cudaError_t err;
+    if (!done) { err = cudaFuncSetAttribute(k_trunk_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err; done = true; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TrunkCfg::SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, k_trunk_pair, p);
+    if (err) return (int)err;
     return (int)cudaGetLastError();
 }
 

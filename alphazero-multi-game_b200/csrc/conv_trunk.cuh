@@ -54,6 +54,21 @@ struct ConvParams {
                                     // weight half — runs while the previous kernel of the stream drains; activations are touched after griddepcontrol.wait)
 };
 
+// the whole residual trunk in one persistent launch (k_trunk_pair, conv_trunk.cu): layer l (0-based) reads X (l even) or Y (l odd) and writes
+// the other; odd layers add the block's input (in place on X); ReLU everywhere
+constexpr int TRUNK_MAX_LAYERS = 40;
+struct TrunkParams {
+    __nv_bfloat16* X; __nv_bfloat16* Y;          // [16][p_total][8] each
+    const __nv_bfloat16* w[TRUNK_MAX_LAYERS];    // pair-kernel weight images, one per layer
+    const float* bias[TRUNK_MAX_LAYERS];         // [128] folded BatchNorm shifts, one per layer
+    const uint8_t* rowvalid;
+    const int* n_boards_dev; int n_rows;
+    int n_layers, p_total, row_pitch;
+    int dbg;                                     // profiling experiments only (AZ_TRUNK_DBG): 1 = no cluster-scope release fence, 2 = no proxy fence; 0 in production
+};
+bool trunk_fused_supported(int channels, int board_pitch, int n_layers);
+int trunk_launch(const TrunkParams& p, int grid, cudaStream_t stream);
+
 size_t conv_smem_bytes(int cin);
 // launches on `stream`; cin in {16, 128}; returns cudaError_t as int
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream);

@@ -343,6 +343,15 @@ struct Net {
         const bool sample = !fe_on && n_dev != nullptr && blocks > 0 && (fwd_count++ % 64) == 63;
         if (conv_stream && blocks > 0) { AZ_CUDA_CHECK(cudaEventRecord(ev_in, s)); AZ_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_in, 0)); }
         if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], cs); }
+        static const bool trunk_fused = getenv("AZ_TRUNK_LAYERED") == nullptr;    // default: the whole trunk as one persistent launch (k_trunk_pair) where it applies
+        if (trunk_fused && NS == 1 && nn::trunk_fused_supported(C, board_pitch, 2 * blocks)) {
+            nn::TrunkParams tp{};
+            tp.X = X; tp.Y = Y; tp.rowvalid = rowvalid; tp.n_boards_dev = n_dev; tp.n_rows = n_fixed * board_pitch;
+            tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch;
+            if (const char* d = getenv("AZ_TRUNK_DBG")) tp.dbg = atoi(d);
+            for (int l = 0; l < 2 * blocks; ++l) { tp.w[l] = w.conv_w[wi(1 + l, 0, 0)]; tp.bias[l] = w.conv_b[bi(1 + l, 0)]; }
+            AZ_CHECK(nn::trunk_launch(tp, cs_sms, cs) == 0, "fused trunk launch failed"); ++launches;
+        } else
         for (int b = 0; b < blocks; ++b) {
             if (layer(X, Y, nullptr, 1 + 2 * b, alt_order ? 1 : 0)) return -1;
             if (layer(Y, X, X, 2 + 2 * b, 0)) return -1;
