@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
         const uint32_t full_count = rank == 0 ? 2 : 1;
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         for (int i = 0; i < 9; ++i) { mbar_init(&w_full[i], full_count); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], 8);
+        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], (p.dbg & 8) ? 2 : 8);
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc2(tslot, 256);
@@ -785,6 +785,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             // "item j of the current layer is in memory", to both CTAs' producers: the warp's stores are ordered before lane 0's cluster-scope
             // release (the generic → async proxy fence sits on the consumer side, one thread, right before the TMA loads)
             auto publish = [&](int j) {
+                if (p.dbg & 8) {          // experiment: one publication per CTA (a named barrier orders the four warps' stores before thread 0's fence)
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                        mbar_arrive(&out_ready[j]);
+                        mbar_arrive_cluster(&out_ready[j], rank ^ 1);
+                    }
+                    return;
+                }
                 __syncwarp();
                 if (lane == 0) {
                     if (!(p.dbg & 1)) asm volatile("fence.acq_rel.cluster;" ::: "memory");

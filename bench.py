@@ -307,6 +307,7 @@ def main():
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     nn_ms = eng.nn_bench(args.slots, 5)
     roofline = {"bound": "tensor", "kernel": (f"k_conv3x3_pair_wide (one 128->128 slice launch over {boards_per_launch} boards; weight-stationary CTA pair with K-split activation stages for the 21-row halo)" if args.game == "go19" else
+                           f"k_trunk_pair (the trunk's 20 128->128 3x3 conv layers over the {boards_per_launch} boards of one stream group as ONE persistent launch of the weight-stationary CTA-pair kernel, cta_group::2; figures are per layer = launch / 20)" if (args.game == "gomoku15" and not os.environ.get("AZ_TRUNK_LAYERED")) else
                            f"k_conv3x3_pair (one 128->128 3x3 conv layer over the {boards_per_launch} boards of one stream group; weight-stationary CTA pair, cta_group::2)"), "achieved": achieved,
                 # kernel timed inside a long step -> the SUSTAINED measured cuBLAS bf16 rate is the denominator; timed alone -> the burst one
                 "peak": pk["bf16_sustained"] if live_n else pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -317,7 +318,7 @@ def main():
                 # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
                 # layer without residual): dram__bytes_read.sum 269.9 MB + dram__bytes_write.sum 224.3 MB; algorithmic 268 + 268 MB
                 "traffic": 494.2e6 if (args.game == "gomoku15" and boards_per_launch == 4096) else None,
-                "launch_ms": conv_ms, "launch_ms_source": f"live: {live_n} launches bracketed by CUDA events inside the timed steps" if live_n else "timed alone (no sampled wave in the timed region)",
+                "launch_ms": conv_ms, "launch_ms_source": f"live: {live_n} layers bracketed by CUDA events inside the timed steps" if live_n else "timed alone (no sampled wave in the timed region)",
                 "launch_ms_timed_alone": conv_ms_alone, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": NET_FLOP_PER_EVAL * args.slots / (nn_ms / 1e3) / 1e12,
                 "step_share_note": f"{20 * args.streams} of these launches per wave (20 per stream group); see profiles/ for the ncu launch list"}
