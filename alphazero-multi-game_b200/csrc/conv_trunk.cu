@@ -619,8 +619,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
 //     (per-layer launches: 670 MB per layer, the residual layers run 10 % slower because of it);
 //   * weights: a ROLLING per-tap reload — the issuer commits w_empty[tap] behind the last item of a layer, the producer refills
 //     that tap with the next layer's weights while the remaining taps of the old layer are still being multiplied;
-//   * the epilogue publishes "item j of this layer is in memory" on out_ready[j] in both CTAs (proxy fence + cluster-scope
-//     release: the next layer's TMA loads of either CTA read rows written by both), the producer waits for it before loading.
+//   * the epilogue publishes "item j of this layer is in memory" on out_ready[j] in both CTAs (cluster-scope release; the next
+//     layer's TMA loads of either CTA read rows written by both), the producer waits for it (+ proxy fence) before loading.
 constexpr int TRUNK_GROUP = 7;
 // taps [T0, T1) of one item: 8 MMAs per tap, straight-line; COMMIT_W: a tcgen05.commit on w_empty[tap] behind each tap
 template <int T0, int T1, bool COMMIT_W>
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
     uint64_t* acc_empty = bars + 6;     // [2] leader only
     uint64_t* w_full = bars + 8;        // [9] tap landed (leader: + the peer's relay)
     uint64_t* w_empty = bars + 17;      // [9] the layer's last MMAs on this tap have completed (multicast commit): the tap may be refilled
-    uint64_t* out_ready = bars + 26;    // [TRUNK_GROUP] item j of the current layer is in memory: 4 local + 4 remote epilogue warps
+    uint64_t* out_ready = bars + 26;    // [TRUNK_GROUP] item j of the current layer is in memory: one arrival per CTA of the pair
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
         const uint32_t full_count = rank == 0 ? 2 : 1;
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         for (int i = 0; i < 9; ++i) { mbar_init(&w_full[i], full_count); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], (p.dbg & 8) ? 2 : 8);
+        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], 2);
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc2(tslot, 256);
@@ -782,20 +782,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
             int pending = -1;
-            // "item j of the current layer is in memory", to both CTAs' producers: the warp's stores are ordered before lane 0's cluster-scope
-            // release (the generic → async proxy fence sits on the consumer side, one thread, right before the TMA loads)
+            // "item j of the current layer is in memory", to both CTAs' producers, ONE publication per CTA: a named barrier orders the four
+            // epilogue warps' stores before thread 0's cluster-scope release fence (one fence per CTA and item instead of one per warp: -3 %);
+            // the generic → async proxy fence sits on the consumer side, one thread, right before the TMA loads
             auto publish = [&](int j) {
-                if (p.dbg & 8) {          // experiment: one publication per CTA (a named barrier orders the four warps' stores before thread 0's fence)
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (threadIdx.x == 0) {
-                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                        mbar_arrive(&out_ready[j]);
-                        mbar_arrive_cluster(&out_ready[j], rank ^ 1);
-                    }
-                    return;
-                }
-                __syncwarp();
-                if (lane == 0) {
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (threadIdx.x == 0) {
                     if (!(p.dbg & 1)) asm volatile("fence.acq_rel.cluster;" ::: "memory");
                     mbar_arrive(&out_ready[j]);
                     mbar_arrive_cluster(&out_ready[j], rank ^ 1);
