@@ -130,3 +130,34 @@ def test_two_kernel_heads_path_still_matches_fp32():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_nn_gpu.py") + "::test_trunk_matches_fp32_calibrated_heads", "-x", "-q",
                         "-m", "gpu"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _forward_dump(n, blocks, path):
+    """nn_forward over n random Gomoku 15x15 positions → npz (policy, value, logits); run in-process or as a child with other switches."""
+    from _eng import E, N
+    m = N.make_random_model(seed=3, randomize_bn=True, blocks=blocks)
+    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=n, evaluator=E.EVAL_RESNET, net_blocks=blocks, num_simulations=8,
+                   max_nodes_per_tree=2048, deterministic=1)
+    eng.load_weights(N.export_weights(m))
+    rng = np.random.default_rng(5)
+    x = (rng.random((n, 11, 15, 15)) < 0.15).astype(np.float32)
+    pol, val, logits = eng.nn_forward(x, want_logits=True)
+    np.savez(path, pol=pol, val=val, logits=logits)
+    eng.close()
+
+
+@pytest.mark.parametrize("n,blocks", [(100, 2), (600, 2), (1100, 10)])
+def test_fused_trunk_bit_identical_to_layered(n, blocks, tmp_path):
+    """k_trunk_pair (all layers in one persistent launch, per-pair groups of 7 boards) against the per-layer launches (AZ_TRUNK_LAYERED=1 in a
+    child process: the switch is read once): same MMAs and epilogue arithmetic → bit-identical outputs.  The board counts put 2 (n = 100),
+    7 + 2 (n = 600: 8 or 9 items per pair) and 7 + 7 + 1 (n = 1100) items on a CTA pair, i.e. full groups and both short-tail publication paths."""
+    import os, subprocess, sys
+    a, b = str(tmp_path / "fused.npz"), str(tmp_path / "layered.npz")
+    _forward_dump(n, blocks, a)
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = f"import sys; sys.path.insert(0, {here!r}); import test_nn_gpu as t; t._forward_dump({n}, {blocks}, {b!r})"
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, AZ_TRUNK_LAYERED="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    fa, fb = np.load(a), np.load(b)
+    for k in ("pol", "val", "logits"):
+        assert np.array_equal(fa[k].view(np.uint32), fb[k].view(np.uint32)), k
