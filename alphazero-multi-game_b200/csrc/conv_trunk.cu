@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
 //   * the epilogue publishes "item j of this layer is in memory" on out_ready[j] in both CTAs (cluster-scope release; the next
 //     layer's TMA loads of either CTA read rows written by both), the producer waits for it (+ proxy fence) before loading.
 constexpr int TRUNK_GROUP = 7;
+constexpr int TRUNK_BATCHED_MIN = 5;        // groups of at least this many items publish their outputs twice per layer (see the epilogue), shorter ones once
 // taps [T0, T1) of one item: 8 MMAs per tap, straight-line; COMMIT_W: a tcgen05.commit on w_empty[tap] behind each tap
 template <int T0, int T1, bool COMMIT_W>
 __device__ __forceinline__ void trunk_issue_taps(uint32_t acc, const uint64_t* a_tap0, uint64_t a_off, uint64_t b_desc0, uint32_t idesc, uint64_t* w_empty) {
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
     uint64_t* acc_empty = bars + 6;     // [2] leader only
     uint64_t* w_full = bars + 8;        // [9] tap landed (leader: + the peer's relay)
     uint64_t* w_empty = bars + 17;      // [9] the layer's last MMAs on this tap have completed (multicast commit): the tap may be refilled
-    uint64_t* out_ready = bars + 26;    // [TRUNK_GROUP] item j of the current layer is in memory: one arrival per CTA of the pair
+    uint64_t* out_ready = bars + 26;    // [2] the current layer's first nj-2 items / last 2 items are in memory: one arrival per CTA of the pair
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
         const uint32_t full_count = rank == 0 ? 2 : 1;
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         for (int i = 0; i < 9; ++i) { mbar_init(&w_full[i], full_count); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < TRUNK_GROUP; ++i) mbar_init(&out_ready[i], 2);
+        for (int i = 0; i < 2; ++i) mbar_init(&out_ready[i], 2);
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc2(tslot, 256);
@@ -699,8 +700,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         for (int j = 0; j < nj; ++j, ++ait) {
                             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
                             const int item = first_item + (g * TRUNK_GROUP + j) * item_step;
-                            if (l > 0) {
-                                mbar_wait_cluster(&out_ready[j], (uint32_t)((l - 1) & 1));      // both CTAs have written layer l-1 of this board
+                            if (l > 0 && (j == 0 || (nj >= TRUNK_BATCHED_MIN && j == nj - 2))) {
+                                // both CTAs have written layer l-1 of the boards loaded from here on: out_ready[0] covers the items before the
+                                // last two (all items in a short group), out_ready[1] the last two
+                                mbar_wait_cluster(&out_ready[j == 0 ? 0 : 1], (uint32_t)((l - 1) & 1));
                                 if (!(p.dbg & 2)) asm volatile("fence.proxy.async.global;" ::: "memory");   // their generic-proxy stores → this thread's TMA loads
                             }
                             mbar_wait(&a_empty[as], aph ^ 1);
@@ -781,16 +784,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             // ===================== epilogue (warps 0-3) =====================
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
-            int pending = -1;
-            // "item j of the current layer is in memory", to both CTAs' producers, ONE publication per CTA: a named barrier orders the four
-            // epilogue warps' stores before thread 0's cluster-scope release fence (one fence per CTA and item instead of one per warp: -3 %);
-            // the generic → async proxy fence sits on the consumer side, one thread, right before the TMA loads
-            auto publish = [&](int j) {
+            bool pending_b = false;
+            // "these items of the current layer are in memory", to both CTAs' producers.  One publication per CTA: a named barrier orders the
+            // four epilogue warps' stores before thread 0's cluster-scope release fence; the generic → async proxy fence sits on the consumer
+            // side, one thread, right before the TMA loads.  The fence costs an L2 round trip, so a layer publishes only twice: its first
+            // nj-2 items when the epilogue reaches item nj-2 (out_ready[0]: the next layer's first load needs them about then), its last two
+            // at item 1 of the NEXT layer (out_ready[1]: needed by that layer's load of item nj-2).  Both points are a full MMA phase behind
+            // the stores they cover, so the fence finds them drained.  Groups shorter than TRUNK_BATCHED_MIN items (the tail of the board
+            // list) publish everything on out_ready[0] right behind their last item.
+            auto publish = [&](int which) {
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (threadIdx.x == 0) {
                     if (!(p.dbg & 1)) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                    mbar_arrive(&out_ready[j]);
-                    mbar_arrive_cluster(&out_ready[j], rank ^ 1);
+                    mbar_arrive(&out_ready[which]);
+                    mbar_arrive_cluster(&out_ready[which], rank ^ 1);
                 }
             };
             for (int g = 0; g < n_groups; ++g) {
@@ -818,7 +825,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         tc_fence_after();
                         // deferred publication of the PREVIOUS item: its stores were issued a whole MMA phase ago, so the cluster-scope release fence
                         // (which waits for this thread's outstanding stores) finds them drained
-                        if (pending >= 0) { publish(pending); pending = -1; }
+                        if (pending_b && (j == 1 || nj < TRUNK_BATCHED_MIN)) { publish(1); pending_b = false; }
+                        if (nj >= TRUNK_BATCHED_MIN && j == nj - 2) publish(0);
                         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128;
                         uint32_t ra[32], rb[32];
                         tmem_ld32(taddr, ra);
@@ -836,13 +844,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
                         pair_epi_chunk(rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow);
-                        // short groups (the tail of the board list) publish at once: with fewer than 3 items per layer the next layer's first load
-                        // would otherwise wait for a publication that only happens behind its own MMAs
-                        if (nj < 3 || (p.dbg & 4)) publish(j); else pending = j;
+                        if (j == nj - 1) { if (nj >= TRUNK_BATCHED_MIN) pending_b = true; else publish(0); }
                     }
                 }
             }
-            if (pending >= 0) publish(pending);
+            if (pending_b) publish(1);
         }
     }
     tc_fence_before();

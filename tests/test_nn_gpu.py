@@ -146,11 +146,12 @@ def _forward_dump(n, blocks, path):
     eng.close()
 
 
-@pytest.mark.parametrize("n,blocks", [(100, 2), (600, 2), (1100, 10)])
+@pytest.mark.parametrize("n,blocks", [(100, 2), (600, 2), (898, 2), (1100, 10)])
 def test_fused_trunk_bit_identical_to_layered(n, blocks, tmp_path):
     """k_trunk_pair (all layers in one persistent launch, per-pair groups of 7 boards) against the per-layer launches (AZ_TRUNK_LAYERED=1 in a
     child process: the switch is read once): same MMAs and epilogue arithmetic → bit-identical outputs.  The board counts put 2 (n = 100),
-    7 + 2 (n = 600: 8 or 9 items per pair) and 7 + 7 + 1 (n = 1100) items on a CTA pair, i.e. full groups and both short-tail publication paths."""
+    7 + 1 / 2 (n = 600), 7 + 5 / 6 (n = 898) and 7 + 7 + 0 / 1 (n = 1100) items on a CTA pair, i.e. full groups (two publications per layer), shorter
+    batched groups and the short-tail path (one publication per layer)."""
     import os, subprocess, sys
     a, b = str(tmp_path / "fused.npz"), str(tmp_path / "layered.npz")
     _forward_dump(n, blocks, a)
