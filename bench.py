@@ -313,6 +313,7 @@ def main():
                 "peak": pk["bf16_sustained"] if live_n else pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / (pk["bf16_sustained"] if live_n else pk["bf16_tflops"]),
                 "peak_source": pk["source"] + (" sustained bf16 (kernel timed inside the step)" if live_n else " burst bf16 (kernel timed alone)"),
+                "frac_note": "the sustained peak is a power-capped cuBLAS bf16 GEMM (MEASURED_PEAKS.json), not a hardware limit: frac can exceed 1; nominal dense bf16 is 2250 TFLOP/s and the tensor pipe also multiplies the 12 % padding rows of the position stream, which `achieved` does not count",
                 "timed_alone": {"achieved": conv_flop / (conv_ms_alone / 1e3) / 1e12, "peak": pk["bf16_tflops"],
                                 "frac": conv_flop / (conv_ms_alone / 1e3) / 1e12 / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16"},
                 # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
