@@ -619,8 +619,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
 //     (per-layer launches: 670 MB per layer, the residual layers run 10 % slower because of it);
 //   * weights: a ROLLING per-tap reload — the issuer commits w_empty[tap] behind the last item of a layer, the producer refills
 //     that tap with the next layer's weights while the remaining taps of the old layer are still being multiplied;
-//   * the epilogue publishes "item j of this layer is in memory" on out_ready[j] in both CTAs (cluster-scope release; the next
-//     layer's TMA loads of either CTA read rows written by both), the producer waits for it (+ proxy fence) before loading.
+//   * the epilogue publishes "these items of this layer are in memory" on two out_ready barriers in both CTAs (cluster-scope
+//     release, twice per layer; the next layer's TMA loads of either CTA read rows written by both), the producer waits for
+//     them (+ proxy fence) before loading;
+//   * the per-layer bias lives in shared memory, double-buffered by layer parity (read from global in the epilogue it cost 45 %).
+// Group size: the largest number of boards per pair whose X + Y stay L2-resident over all pairs; TRUNK_GROUP = 7 also divides the
+// 55-56 boards a pair owns at 4096 boards into full groups.
 constexpr int TRUNK_GROUP = 7;
 constexpr int TRUNK_BATCHED_MIN = 5;        // groups of at least this many items publish their outputs twice per layer (see the epilogue), shorter ones once
 // taps [T0, T1) of one item: 8 MMAs per tap, straight-line; COMMIT_W: a tcgen05.commit on w_empty[tap] behind each tap
@@ -665,7 +669,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
     const int n_items = (n_rows + 255) / 256;
     const int first_item = (int)cluster_id_x(), item_step = (int)n_clusters_x();
     const int my_items = first_item < n_items ? (n_items - first_item + item_step - 1) / item_step : 0;
-    const int n_groups = (my_items + TRUNK_GROUP - 1) / TRUNK_GROUP;
+    const int GROUP = p.group > 0 ? p.group : TRUNK_GROUP;      // boards a pair takes through all layers at a time
+    const int n_groups = (my_items + GROUP - 1) / GROUP;
     const int L = p.n_layers;                                    // even: 2 per residual block
 
     if (threadIdx.x == 0) {
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             if (lane == 0) {
                 uint32_t ait = 0, wl = 0;                                 // activation stage counter, layer-instance counter
                 for (int g = 0; g < n_groups; ++g) {
-                    const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                    const int nj = min(GROUP, my_items - g * GROUP);
                     for (int l = 0; l < L; ++l, ++wl) {
                         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w[l]) + (size_t)rank * C::W_BYTES;
                         const __nv_bfloat16* in = (l & 1) ? p.Y : p.X;
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         load_tap(0);
                         for (int j = 0; j < nj; ++j, ++ait) {
                             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
-                            const int item = first_item + (g * TRUNK_GROUP + j) * item_step;
+                            const int item = first_item + (g * GROUP + j) * item_step;
                             if (l > 0 && (j == 0 || (nj >= TRUNK_BATCHED_MIN && j == nj - 2))) {
                                 // both CTAs have written layer l-1 of the boards loaded from here on: out_ready[0] covers the items before the
                                 // last two (all items in a short group), out_ready[1] the last two
@@ -722,7 +727,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             if (lane == 0) {
                 uint32_t ait = 0, wl = 0;
                 for (int g = 0; g < n_groups; ++g) {
-                    const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                    const int nj = min(GROUP, my_items - g * GROUP);
                     for (int l = 0; l < L; ++l, ++wl) {
                         mbar_wait(&w_full[0], wl & 1);
                         mbar_arrive_cluster(&w_full[0], 0);
@@ -746,7 +751,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             for (int tap = 0; tap < 9; ++tap) a_tap0[tap] = a_desc0 + (uint64_t)(int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));
             uint32_t ait = 0, wl = 0;
             for (int g = 0; g < n_groups; ++g) {
-                const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                const int nj = min(GROUP, my_items - g * GROUP);
                 for (int l = 0; l < L; ++l, ++wl) {
                     for (int j = 0; j < nj; ++j, ++ait) {
                         const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
@@ -796,12 +801,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (threadIdx.x == 0) {
                     if (!(p.dbg & 1)) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    // default-semantics arrives behind the explicit cluster-scope fence (as CUTLASS' ClusterBarrier does for its cross-CTA
+                    // consumer release); arrive.release.cluster on both would cost two more memory barriers: measured 3.26 -> 3.53 ms per forward
                     mbar_arrive(&out_ready[which]);
                     mbar_arrive_cluster(&out_ready[which], rank ^ 1);
                 }
             };
             for (int g = 0; g < n_groups; ++g) {
-                const int nj = min(TRUNK_GROUP, my_items - g * TRUNK_GROUP);
+                const int nj = min(GROUP, my_items - g * GROUP);
                 for (int l = 0; l < L; ++l) {
                     const bool has_res = (l & 1) != 0;                                   // second conv of a block: + the block's input (in place on X)
                     __nv_bfloat16* out = (l & 1) ? p.X : p.Y;
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     for (int j = 0; j < nj; ++j, ++ait) {
                         const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-                        const int item = first_item + (g * TRUNK_GROUP + j) * item_step;
+                        const int item = first_item + (g * GROUP + j) * item_step;
                         const int row = item * 256 + (int)rank * 128 + warp * 32 + lane;
                         const size_t grow = (size_t)CONV_GUARD + row;
                         const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);

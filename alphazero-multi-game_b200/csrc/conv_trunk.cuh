@@ -64,6 +64,7 @@ struct TrunkParams {
     const uint8_t* rowvalid;
     const int* n_boards_dev; int n_rows;
     int n_layers, p_total, row_pitch;
+    int group;                                   // boards per CTA pair and pass through all layers (0 = default 7): 74 pairs x group x 128 KB must stay in L2
     int dbg;                                     // profiling experiments only (AZ_TRUNK_DBG): 1 = no cluster-scope release fence, 2 = no proxy fence, 4 = publish every item at once instead of one item later; 0 in production
 };
 bool trunk_fused_supported(int channels, int board_pitch, int n_layers);

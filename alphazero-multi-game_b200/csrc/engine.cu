@@ -349,6 +349,7 @@ struct Net {
             tp.X = X; tp.Y = Y; tp.rowvalid = rowvalid; tp.n_boards_dev = n_dev; tp.n_rows = n_fixed * board_pitch;
             tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch;
             if (const char* d = getenv("AZ_TRUNK_DBG")) tp.dbg = atoi(d);
+            if (const char* d = getenv("AZ_TRUNK_GROUP")) tp.group = atoi(d);           // profiling switch
             for (int l = 0; l < 2 * blocks; ++l) { tp.w[l] = w.conv_w[wi(1 + l, 0, 0)]; tp.bias[l] = w.conv_b[bi(1 + l, 0)]; }
             AZ_CHECK(nn::trunk_launch(tp, cs_sms, cs) == 0, "fused trunk launch failed"); ++launches;
         } else
