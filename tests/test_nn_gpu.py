@@ -162,3 +162,26 @@ def test_fused_trunk_bit_identical_to_layered(n, blocks, tmp_path):
     fa, fb = np.load(a), np.load(b)
     for k in ("pol", "val", "logits"):
         assert np.array_equal(fa[k].view(np.uint32), fb[k].view(np.uint32)), k
+
+
+def test_fused_trunk_repeatable_at_full_batch():
+    """4096 boards x 20 layers in one persistent launch, ten times on the same inputs: every repetition bit-identical (the kernel synchronises
+    its two CTAs per layer through global memory + barriers; a missed ordering would show up as run-to-run differences)."""
+    from _eng import E, N
+    n = 4096
+    m = N.make_random_model(seed=4, randomize_bn=True, blocks=10)
+    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=n, evaluator=E.EVAL_RESNET, net_blocks=10, num_simulations=8,
+                   max_nodes_per_tree=2048, deterministic=1)
+    eng.load_weights(N.export_weights(m))
+    rng = np.random.default_rng(6)
+    x = (rng.random((n, 11, 15, 15)) < 0.2).astype(np.float32)
+    p0, v0, l0 = eng.nn_forward(x, want_logits=True)
+    assert np.all(np.isfinite(l0))
+    for _ in range(9):
+        p, v, l = eng.nn_forward(x, want_logits=True)
+        assert np.array_equal(l.view(np.uint32), l0.view(np.uint32)) and np.array_equal(v.view(np.uint32), v0.view(np.uint32))
+    # a permutation of the boards permutes the outputs (batch-position independence across the pairs' board groups)
+    perm = rng.permutation(n)
+    p, v, l = eng.nn_forward(x[perm], want_logits=True)
+    assert np.array_equal(l.view(np.uint32), l0[perm].view(np.uint32)) and np.array_equal(v.view(np.uint32), v0[perm].view(np.uint32))
+    eng.close()
