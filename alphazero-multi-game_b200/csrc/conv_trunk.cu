@@ -31,7 +31,7 @@ struct Cfg {
 
 // one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 → four 16-byte stores
 __device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
-                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false) {
+                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float v[8];
@@ -54,6 +54,7 @@ __device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* r
             ob[e] = __floats2bfloat162_rn(x, y);
         }
         if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
+        if (skip_store) continue;                           // k_trunk_pair: a row past the end of this pair's board group belongs to another pair
         *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
     }
 }
@@ -647,6 +648,7 @@ struct TrunkCfg : PairCfg {
     static constexpr int SMEM = OFF_TTSLOT + 16;
 };
 
+template <bool CONTIG>      // CONTIG: groups of consecutive boards of any size (rows past a group's end are not stored); else 256-row boards, strided groups
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParams p) {
     using C = TrunkCfg;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -665,13 +667,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int n_rows = p.n_boards_dev ? (*p.n_boards_dev) * 256 : p.n_rows;
-    const int n_items = (n_rows + 255) / 256;
-    const int first_item = (int)cluster_id_x(), item_step = (int)n_clusters_x();
-    const int my_items = first_item < n_items ? (n_items - first_item + item_step - 1) / item_step : 0;
-    const int GROUP = p.group > 0 ? p.group : TRUNK_GROUP;      // boards a pair takes through all layers at a time
-    const int n_groups = (my_items + GROUP - 1) / GROUP;
+    // Work: groups of `group_boards` consecutive boards; group gi belongs to pair gi % #pairs.  Inside a group the 256-row work items start
+    // at the group's first row (a pair-local item grid: boards of any padded size), the last one may reach past the group's end — those
+    // rows belong to another pair and are computed but never stored.
+    const int n_boards = p.n_boards_dev ? *p.n_boards_dev : p.n_rows / p.board_pitch;
+    const int GB = p.group_boards;
+    const int first_group = (int)cluster_id_x(), group_step = (int)n_clusters_x();
     const int L = p.n_layers;                                    // even: 2 per residual block
+    // Two ways to form a group.  Boards that are exactly one work item (256 rows, Gomoku 15x15): the group's GB boards are STRIDED by the
+    // number of pairs, so at any time the pairs stream through consecutive boards together (3 % faster than contiguous groups: the
+    // write-backs stay page-local).  Any other board size: GB consecutive boards on the pair-local item grid.
+    constexpr bool strided = !CONTIG;
+    const int n_groups_total = strided ? group_step * (((n_boards + group_step - 1) / group_step + GB - 1) / GB) : (n_boards + GB - 1) / GB;
+    auto group_rows = [&](int gi) { return min(GB, n_boards - gi * GB) * p.board_pitch; };                                   // contiguous mode
+    auto group_items = [&](int gi) {
+        if (!strided) return (group_rows(gi) + 255) / 256;
+        const int left = n_boards - gi % group_step - group_step * GB * (gi / group_step);                               // boards from this group's first one on
+        return left <= 0 ? 0 : min(GB, (left + group_step - 1) / group_step);
+    };
+    auto item_base = [&](int gi, int j) {                                                                                // first row of item j
+        return strided ? (gi % group_step + group_step * (GB * (gi / group_step) + j)) * 256 : gi * GB * p.board_pitch + j * 256;
+    };
+    const int item_stride = strided ? group_step * 256 : 256;                                                            // rows between two items of a group
 
     if (threadIdx.x == 0) {
         const uint32_t full_count = rank == 0 ? 2 : 1;
@@ -686,13 +703,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
     tc_fence_after();
     const uint32_t tmem_base = *tslot;
 
-    if (my_items > 0) {
+    if (first_group < n_groups_total) {
         if (warp == 4) {
             // ===================== TMA producer =====================
             if (lane == 0) {
                 uint32_t ait = 0, wl = 0;                                 // activation stage counter, layer-instance counter
-                for (int g = 0; g < n_groups; ++g) {
-                    const int nj = min(GROUP, my_items - g * GROUP);
+                for (int g = first_group; g < n_groups_total; g += group_step) {
+                    const int nj = group_items(g);
+                    if (nj == 0) continue;
+                    const int gbase = item_base(g, 0);
                     for (int l = 0; l < L; ++l, ++wl) {
                         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w[l]) + (size_t)rank * C::W_BYTES;
                         const __nv_bfloat16* in = (l & 1) ? p.Y : p.X;
@@ -704,7 +723,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         load_tap(0);
                         for (int j = 0; j < nj; ++j, ++ait) {
                             const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
-                            const int item = first_item + (g * GROUP + j) * item_step;
                             if (l > 0 && (j == 0 || (nj >= TRUNK_BATCHED_MIN && j == nj - 2))) {
                                 // both CTAs have written layer l-1 of the boards loaded from here on: out_ready[0] covers the items before the
                                 // last two (all items in a short group), out_ready[1] the last two
@@ -713,7 +731,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                             }
                             mbar_wait(&a_empty[as], aph ^ 1);
                             mbar_arrive_expect_tx(&a_full[as], C::A_STAGE);
-                            const size_t row0 = (size_t)CONV_GUARD + (size_t)item * 256 + rank * 128 - PAIR_HALO;
+                            const size_t row0 = (size_t)CONV_GUARD + (size_t)(gbase + j * item_stride) + rank * 128 - PAIR_HALO;
                             for (int kc = 0; kc < 16; ++kc)
                                 bulk_g2s(sA + as * C::A_STAGE + kc * C::PLANE, in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &a_full[as]);
                             if (j == 0) for (int tap = 1; tap < 9; ++tap) load_tap(tap);
@@ -726,8 +744,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             // ===================== relay (peer CTA) =====================
             if (lane == 0) {
                 uint32_t ait = 0, wl = 0;
-                for (int g = 0; g < n_groups; ++g) {
-                    const int nj = min(GROUP, my_items - g * GROUP);
+                for (int g = first_group; g < n_groups_total; g += group_step) {
+                    const int nj = group_items(g);
+                    if (nj == 0) continue;
                     for (int l = 0; l < L; ++l, ++wl) {
                         mbar_wait(&w_full[0], wl & 1);
                         mbar_arrive_cluster(&w_full[0], 0);
@@ -750,8 +769,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) a_tap0[tap] = a_desc0 + (uint64_t)(int64_t)((tap / 3 - 1) * p.row_pitch + (tap % 3 - 1));
             uint32_t ait = 0, wl = 0;
-            for (int g = 0; g < n_groups; ++g) {
-                const int nj = min(GROUP, my_items - g * GROUP);
+            for (int g = first_group; g < n_groups_total; g += group_step) {
+                const int nj = group_items(g);
+                    if (nj == 0) continue;
                 for (int l = 0; l < L; ++l, ++wl) {
                     for (int j = 0; j < nj; ++j, ++ait) {
                         const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
@@ -807,8 +827,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                     mbar_arrive_cluster(&out_ready[which], rank ^ 1);
                 }
             };
-            for (int g = 0; g < n_groups; ++g) {
-                const int nj = min(GROUP, my_items - g * GROUP);
+            for (int g = first_group; g < n_groups_total; g += group_step) {
+                const int nj = group_items(g);
+                    if (nj == 0) continue;
+                    const int gbase = item_base(g, 0);
+                const int lim = strided ? 0x7fffffff : g * GB * p.board_pitch + group_rows(g);      // strided boards are whole items: every row is ours
                 for (int l = 0; l < L; ++l) {
                     const bool has_res = (l & 1) != 0;                                   // second conv of a block: + the block's input (in place on X)
                     __nv_bfloat16* out = (l & 1) ? p.X : p.Y;
@@ -819,12 +842,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     for (int j = 0; j < nj; ++j, ++ait) {
                         const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
-                        const int item = first_item + (g * GROUP + j) * item_step;
-                        const int row = item * 256 + (int)rank * 128 + warp * 32 + lane;
+                        const int row = gbase + j * item_stride + (int)rank * 128 + warp * 32 + lane;
                         const size_t grow = (size_t)CONV_GUARD + row;
-                        const bool valid = (row < n_rows) && (p.rowvalid[grow] != 0);
+                        const bool mine = CONTIG ? row < lim : true;                     // rows past the group's end: computed, never stored
+                        const bool valid = mine && (p.rowvalid[grow] != 0);
                         uint4 res[16];
-                        if (has_res) {
+                        if (has_res) {                                                   // (uniform per layer; rows that are not ours are readable, just not ours to write)
 #pragma unroll
                             for (int q = 0; q < 16; ++q) res[q] = *reinterpret_cast<const uint4*>(p.X + ((size_t)q * p_total + grow) * 8);
                         }
@@ -839,18 +862,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         tmem_ld32(taddr, ra);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 32, rb);
-                        pair_epi_chunk(ra, res, has_res, bias, 0, true, valid, out, p_total, grow);
+                        pair_epi_chunk(ra, res, has_res, bias, 0, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 64, ra);
-                        pair_epi_chunk(rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow);
+                        pair_epi_chunk(rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 96, rb);
-                        pair_epi_chunk(ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow);
+                        pair_epi_chunk(ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                        pair_epi_chunk(rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow);
+                        pair_epi_chunk(rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         if (j == nj - 1) { if (nj >= TRUNK_BATCHED_MIN) pending_b = true; else publish(0); }
                     }
                 }
@@ -906,18 +929,26 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
     return (int)cudaGetLastError();
 }
 
-bool trunk_fused_supported(int channels, int board_pitch, int n_layers) { return channels == CONV_COUT && board_pitch == 256 && n_layers >= 2 && n_layers % 2 == 0 && n_layers <= TRUNK_MAX_LAYERS; }
+bool trunk_fused_supported(int channels, int board_pitch, int row_pitch, int n_layers) {
+    return channels == CONV_COUT && row_pitch + 1 <= PAIR_HALO && board_pitch <= TRUNK_GROUP * 256 / TRUNK_BATCHED_MIN && n_layers >= 2 && n_layers % 2 == 0 && n_layers <= TRUNK_MAX_LAYERS;
+}
+// boards per group: as many whole boards as fit in TRUNK_GROUP work items (Gomoku 15x15: 7 boards = 7 items; Go 9x9: 17 boards = 6.6 items)
+int trunk_group_boards(int board_pitch) { return TRUNK_GROUP * 256 / board_pitch; }
 
 int trunk_launch(const TrunkParams& p, int grid, cudaStream_t stream) {
     static bool done = false;
     cudaError_t err;
-    if (!done) { err = cudaFuncSetAttribute(k_trunk_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err; done = true; }
+    if (!done) {
+        err = cudaFuncSetAttribute(k_trunk_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err;
+        err = cudaFuncSetAttribute(k_trunk_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err;
+        done = true;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TrunkCfg::SMEM; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, k_trunk_pair, p);
+    err = p.board_pitch == 256 ? cudaLaunchKernelEx(&cfg, k_trunk_pair<false>, p) : cudaLaunchKernelEx(&cfg, k_trunk_pair<true>, p);
     if (err) return (int)err;
     return (int)cudaGetLastError();
 }

@@ -64,10 +64,13 @@ struct TrunkParams {
     const uint8_t* rowvalid;
     const int* n_boards_dev; int n_rows;
     int n_layers, p_total, row_pitch;
-    int group;                                   // boards per CTA pair and pass through all layers (0 = default 7): 74 pairs x group x 128 KB must stay in L2
+    int board_pitch;                             // rows per board (H+1)*(W+1)
+    int group_boards;                            // boards a CTA pair takes through all layers at a time (trunk_group_boards): 74 pairs x 7 items x 128 KB stay in L2
     int dbg;                                     // profiling experiments only (AZ_TRUNK_DBG): 1 = no cluster-scope release fence, 2 = no proxy fence, 4 = publish every item at once instead of one item later; 0 in production
 };
-bool trunk_fused_supported(int channels, int board_pitch, int n_layers);
+bool trunk_fused_supported(int channels, int board_pitch, int row_pitch, int n_layers);
+int trunk_group_boards(int board_pitch);
+constexpr int TRUNK_TAIL_ROWS = 512;          // extra zero rows the activation planes need after the last board: a pair-local item grid may overhang the stream's end
 int trunk_launch(const TrunkParams& p, int grid, cudaStream_t stream);
 
 size_t conv_smem_bytes(int cin);

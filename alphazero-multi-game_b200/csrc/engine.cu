@@ -203,7 +203,7 @@ struct Net {
         AZ_CHECK(channels == 128 || channels == 256, "conv trunk is built for 128 or 256 channels");
         NS = channels / nn::CONV_COUT;
         const size_t rows = (size_t)max_boards * board_pitch;
-        p_total = (int)(nn::CONV_GUARD + (rows + nn::CONV_BM - 1) / nn::CONV_BM * nn::CONV_BM + nn::CONV_GUARD);
+        p_total = (int)(nn::CONV_GUARD + (rows + nn::CONV_BM - 1) / nn::CONV_BM * nn::CONV_BM + nn::CONV_GUARD + (board_pitch % nn::CONV_BM == 0 ? 0 : nn::TRUNK_TAIL_ROWS));      // (boards of whole work items never overhang)
         PH = std::min(8, H); PW = std::min(8, W); feat = 32 * PH * PW;
         if (dev_alloc(&in16, (size_t)(cin_pad / 8) * p_total * 8)) return -1;
         if (dev_alloc(&X, (size_t)(C / 8) * p_total * 8)) return -1;
@@ -344,12 +344,15 @@ struct Net {
         if (conv_stream && blocks > 0) { AZ_CUDA_CHECK(cudaEventRecord(ev_in, s)); AZ_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_in, 0)); }
         if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], cs); }
         static const bool trunk_fused = getenv("AZ_TRUNK_LAYERED") == nullptr;    // default: the whole trunk as one persistent launch (k_trunk_pair) where it applies
-        if (trunk_fused && NS == 1 && nn::trunk_fused_supported(C, board_pitch, 2 * blocks)) {
+        if (trunk_fused && NS == 1 && nn::trunk_fused_supported(C, board_pitch, row_pitch, 2 * blocks)) {
             nn::TrunkParams tp{};
             tp.X = X; tp.Y = Y; tp.rowvalid = rowvalid; tp.n_boards_dev = n_dev; tp.n_rows = n_fixed * board_pitch;
-            tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch;
+            tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch; tp.board_pitch = board_pitch; tp.group_boards = nn::trunk_group_boards(board_pitch);
+            // small batches (Go 9x9 at 2048 boards, chess at 1024): X + Y fit in L2 as a whole, so one group per CTA pair balances the pairs better
+            // than groups of 7 work items (2048 Go boards = 120 such groups on 74 pairs)
+            if (board_pitch != 256 && (size_t)2 * max_boards * board_pitch * 256 <= ((size_t)110 << 20)) tp.group_boards = std::max(1, (max_boards + cs_sms / 2 - 1) / (cs_sms / 2));
             if (const char* d = getenv("AZ_TRUNK_DBG")) tp.dbg = atoi(d);
-            if (const char* d = getenv("AZ_TRUNK_GROUP")) tp.group = atoi(d);           // profiling switch
+            if (const char* d = getenv("AZ_TRUNK_GROUP")) tp.group_boards = std::max(1, atoi(d));           // profiling switch: boards per group
             for (int l = 0; l < 2 * blocks; ++l) { tp.w[l] = w.conv_w[wi(1 + l, 0, 0)]; tp.bias[l] = w.conv_b[bi(1 + l, 0)]; }
             AZ_CHECK(nn::trunk_launch(tp, cs_sms, cs) == 0, "fused trunk launch failed"); ++launches;
         } else

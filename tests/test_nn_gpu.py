@@ -132,31 +132,33 @@ def test_two_kernel_heads_path_still_matches_fp32():
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def _forward_dump(n, blocks, path):
-    """nn_forward over n random Gomoku 15x15 positions → npz (policy, value, logits); run in-process or as a child with other switches."""
+def _forward_dump(n, blocks, path, game=0, board=15, planes=11, actions=225):
+    """nn_forward over n random positions (default Gomoku 15x15) → npz (policy, value, logits); run in-process or as a child with other switches."""
     from _eng import E, N
-    m = N.make_random_model(seed=3, randomize_bn=True, blocks=blocks)
-    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=n, evaluator=E.EVAL_RESNET, net_blocks=blocks, num_simulations=8,
+    m = N.make_random_model(seed=3, randomize_bn=True, blocks=blocks, in_planes=planes, board=board, actions=actions)
+    eng = E.Engine(game=game, board_size=board, n_slots=n, evaluator=E.EVAL_RESNET, net_blocks=blocks, num_simulations=8,
                    max_nodes_per_tree=2048, deterministic=1)
     eng.load_weights(N.export_weights(m))
     rng = np.random.default_rng(5)
-    x = (rng.random((n, 11, 15, 15)) < 0.15).astype(np.float32)
+    x = (rng.random((n, planes, board, board)) < 0.15).astype(np.float32)
     pol, val, logits = eng.nn_forward(x, want_logits=True)
     np.savez(path, pol=pol, val=val, logits=logits)
     eng.close()
 
 
-@pytest.mark.parametrize("n,blocks", [(100, 2), (600, 2), (898, 2), (1100, 10)])
-def test_fused_trunk_bit_identical_to_layered(n, blocks, tmp_path):
+@pytest.mark.parametrize("n,blocks,game,board,planes,actions", [(100, 2, 0, 15, 11, 225), (600, 2, 0, 15, 11, 225), (898, 2, 0, 15, 11, 225), (1100, 10, 0, 15, 11, 225),
+                                                               (1500, 2, 2, 9, 8, 82), (700, 2, 2, 13, 8, 170), (2000, 2, 1, 8, 18, 20480), (333, 2, 0, 9, 11, 81)])
+def test_fused_trunk_bit_identical_to_layered(n, blocks, game, board, planes, actions, tmp_path):
     """k_trunk_pair (all layers in one persistent launch, per-pair groups of 7 boards) against the per-layer launches (AZ_TRUNK_LAYERED=1 in a
     child process: the switch is read once): same MMAs and epilogue arithmetic → bit-identical outputs.  The board counts put 2 (n = 100),
     7 + 1 / 2 (n = 600), 7 + 5 / 6 (n = 898) and 7 + 7 + 0 / 1 (n = 1100) items on a CTA pair, i.e. full groups (two publications per layer), shorter
-    batched groups and the short-tail path (one publication per layer)."""
+    batched groups and the short-tail path (one publication per layer).  Go 9x9 / 13x13, chess and Gomoku 9x9: boards that are not one
+    256-row work item each (board-aligned groups on a pair-local item grid, rows past a group's end computed but not stored)."""
     import os, subprocess, sys
     a, b = str(tmp_path / "fused.npz"), str(tmp_path / "layered.npz")
-    _forward_dump(n, blocks, a)
+    _forward_dump(n, blocks, a, game, board, planes, actions)
     here = os.path.dirname(os.path.abspath(__file__))
-    code = f"import sys; sys.path.insert(0, {here!r}); import test_nn_gpu as t; t._forward_dump({n}, {blocks}, {b!r})"
+    code = f"import sys; sys.path.insert(0, {here!r}); import test_nn_gpu as t; t._forward_dump({n}, {blocks}, {b!r}, {game}, {board}, {planes}, {actions})"
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, AZ_TRUNK_LAYERED="1"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     fa, fb = np.load(a), np.load(b)
