@@ -318,9 +318,9 @@ def main():
                                 "frac": conv_flop / (conv_ms_alone / 1e3) / 1e12 / pk["bf16_tflops"], "peak_source": pk["source"] + " burst bf16"},
                 # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1_summary.md (4096 Gomoku boards,
                 # layer without residual): dram__bytes_read.sum 269.9 MB + dram__bytes_write.sum 224.3 MB; algorithmic 268 + 268 MB
-                # fused trunk (k_trunk_pair, profiles/r1e_trunk_pair_ncu_raw.csv): dram__bytes_read.sum 821 MB + dram__bytes_write.sum 3107 MB per launch
-                # of 20 layers = 196.4 MB per layer — below the algorithmic 536-805 MB because a group's activations stay in L2
-                "traffic": (196.4e6 if not os.environ.get("AZ_TRUNK_LAYERED") else 494.2e6) if (args.game == "gomoku15" and boards_per_launch == 4096) else None,
+                # fused trunk (k_trunk_pair, profiles/r1f_trunk_pair_ncu_raw.csv): dram__bytes_read.sum 814 MB + dram__bytes_write.sum 3062 MB per launch
+                # of 20 layers = 193.8 MB per layer — below the algorithmic 536-805 MB because a group's activations stay in L2
+                "traffic": (193.8e6 if not os.environ.get("AZ_TRUNK_LAYERED") else 494.2e6) if (args.game == "gomoku15" and boards_per_launch == 4096) else None,
                 "launch_ms": conv_ms, "launch_ms_source": f"live: {live_n} layers bracketed by CUDA events inside the timed steps" if live_n else "timed alone (no sampled wave in the timed region)",
                 "launch_ms_timed_alone": conv_ms_alone, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": NET_FLOP_PER_EVAL * args.slots / (nn_ms / 1e3) / 1e12,
