@@ -43,42 +43,64 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
 // sum / write passes (one read of the partial sums, one write of logits and policy).
 constexpr int PV_WIDE_THREADS = 1024, PV_WIDE_MAX_PER_THREAD = 24;     // covers A <= 24576; many threads with few elements each: the passes are latency-bound
 __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams p) {
-    __shared__ float red[PV_WIDE_THREADS / 32];
-    __shared__ float bcast;
+    __shared__ float red_m[PV_WIDE_THREADS / 32], red_s[PV_WIDE_THREADS / 32];
+    __shared__ float bcast[2];
     const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (b >= nb) return;
+    // Online softmax: one pass gives every thread (max, sum of exp(x - max)) over its own logits, ONE block reduction combines the pairs
+    // ((m1, s1) + (m2, s2) = (M, s1 e^(m1 - M) + s2 e^(m2 - M))), one expf per logit.  The kernel is latency-bound (one 1024-thread
+    // block per SM, its phases do not overlap), so a reduction and an exp pass less is time saved.
     float v[PV_WIDE_MAX_PER_THREAD];
+    // all loads first (a thread's ~20 partial sums and biases in flight together), the max afterwards
+    const float* part0 = p.logits_part + (size_t)b * p.ld_part;
+#pragma unroll
+    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
+        const int i = tid + k * PV_WIDE_THREADS;
+        v[k] = i < p.A ? __ldg(p.bias_p + i) + __ldg(part0 + i) : 0.0f;
+    }
+    for (int sidx = 1; sidx < p.n_split_p; ++sidx) {
+#pragma unroll
+        for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
+            const int i = tid + k * PV_WIDE_THREADS;
+            if (i < p.A) v[k] += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.ld_part + i];
+        }
+    }
     float mx = -3.4e38f;
 #pragma unroll
     for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
         const int i = tid + k * PV_WIDE_THREADS;
         if (i < p.A) {
-            float x = p.bias_p[i];
-            for (int sidx = 0; sidx < p.n_split_p; ++sidx) x += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.ld_part + i];
-            v[k] = x; mx = fmaxf(mx, x);
+            mx = fmaxf(mx, v[k]);
+            if (p.want_logits) p.logits[(size_t)b * p.A + i] = v[k];   // API path only (az_engine_nn_forward)
         }
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) { float m = red[0]; for (int w = 1; w < PV_WIDE_THREADS / 32; ++w) m = fmaxf(m, red[w]); bcast = m; }
-    __syncthreads();
-    mx = bcast;
     float sum = 0.0f;
 #pragma unroll
-    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) { const int i = tid + k * PV_WIDE_THREADS; if (i < p.A) sum += expf(v[k] - mx); }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) { const int i = tid + k * PV_WIDE_THREADS; if (i < p.A) { v[k] = expf(v[k] - mx); sum += v[k]; } }
+    float M = mx, S = sum;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, M, o), s2 = __shfl_xor_sync(0xffffffffu, S, o);
+        const float mm = fmaxf(M, m2);
+        S = S * expf(M - mm) + s2 * expf(m2 - mm); M = mm;
+    }
+    if (lane == 0) { red_m[warp] = M; red_s[warp] = S; }
     __syncthreads();
-    if (lane == 0) red[warp] = sum;
+    if (warp == 0) {
+        M = red_m[lane]; S = red_s[lane];                              // PV_WIDE_THREADS / 32 == 32 partial pairs
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, M, o), s2 = __shfl_xor_sync(0xffffffffu, S, o);
+            const float mm = fmaxf(M, m2);
+            S = S * expf(M - mm) + s2 * expf(m2 - mm); M = mm;
+        }
+        if (lane == 0) { bcast[0] = M; bcast[1] = S; }
+    }
     __syncthreads();
-    if (tid == 0) { float t = 0.0f; for (int w = 0; w < PV_WIDE_THREADS / 32; ++w) t += red[w]; bcast = t; }
-    __syncthreads();
-    const float inv = 1.0f / bcast;
+    const float scale = expf(mx - bcast[0]) / bcast[1];              // this thread's exp(x - mx) values → exp(x - M) / S
 #pragma unroll
     for (int k = 0; k < PV_WIDE_MAX_PER_THREAD; ++k) {
         const int i = tid + k * PV_WIDE_THREADS;
-        if (i < p.A) { if (p.want_logits) p.logits[(size_t)b * p.A + i] = v[k]; p.policy[(size_t)b * p.A + i] = expf(v[k] - mx) * inv; }      // logits: API path only (az_engine_nn_forward)
+        if (i < p.A) p.policy[(size_t)b * p.A + i] = v[k] * scale;
     }
     if (warp == 0) {      // value head: tanh(relu(hidden) . w2 + b2)
         float d = 0.0f;
