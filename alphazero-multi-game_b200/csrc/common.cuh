@@ -18,6 +18,10 @@ namespace az {
 
 void set_error(const std::string& s);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair: engines may live on several GPUs of one
+// process (az_config.device), so the opt-in is made once per kernel AND device, under a lock (engine.cu).
+cudaError_t smem_opt_in(const void* kernel, int bytes);
+
 // Exactly-rounded fp32 ops with no FMA contraction: the search arithmetic must reproduce the
 // reference's x86 single-op sequence bit for bit (SURVEY.md §7 "Hard parts").
 AZ_HD float fadd(float a, float b) {

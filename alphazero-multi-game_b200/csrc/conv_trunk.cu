@@ -893,17 +893,15 @@ size_t conv_smem_bytes(int cin) { return cin == 16 ? Cfg<16>::SMEM : (cin == 32 
 bool conv_uses_pair(int cin, int row_pitch) { return cin == CONV_COUT && row_pitch + 1 <= WIDE_HALO; }     // same weight image for both pair kernels
 
 int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) {
-    static bool attr_done[4] = {false, false, false, false};
     cudaError_t err;
     if (cin == 32) {     // chess stem: 18 planes padded to 32 channels
-        if (!attr_done[3]) { err = cudaFuncSetAttribute(k_conv3x3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::SMEM); if (err) return (int)err; attr_done[3] = true; }
+        err = smem_opt_in((const void*)k_conv3x3<32>, (int)Cfg<32>::SMEM); if (err) return (int)err;
         k_conv3x3<32><<<grid, CONV1_THREADS, Cfg<32>::SMEM, stream>>>(p);
     } else if (cin == 16) {
-        if (!attr_done[0]) { err = cudaFuncSetAttribute(k_conv3x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::SMEM); if (err) return (int)err; attr_done[0] = true; }
+        err = smem_opt_in((const void*)k_conv3x3<16>, (int)Cfg<16>::SMEM); if (err) return (int)err;
         k_conv3x3<16><<<grid, CONV1_THREADS, Cfg<16>::SMEM, stream>>>(p);
     } else if (conv_uses_pair(cin, p.row_pitch) && p.row_pitch + 1 > PAIR_HALO) {          // boards 16..19 wide: K-split stages
-        static bool wide_done = false;
-        if (!wide_done) { err = cudaFuncSetAttribute(k_conv3x3_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg::SMEM); if (err) return (int)err; wide_done = true; }
+        err = smem_opt_in((const void*)k_conv3x3_pair_wide, (int)WideCfg::SMEM); if (err) return (int)err;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = WideCfg::SMEM; cfg.stream = stream;
         cudaLaunchAttribute at[2];
@@ -913,7 +911,7 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
         err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair_wide, p);
         if (err) return (int)err;
     } else if (conv_uses_pair(cin, p.row_pitch)) {
-        if (!attr_done[2]) { err = cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM); if (err) return (int)err; attr_done[2] = true; }
+        err = smem_opt_in((const void*)k_conv3x3_pair, (int)PairCfg::SMEM); if (err) return (int)err;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = stream;
         cudaLaunchAttribute at[2];
@@ -923,7 +921,7 @@ int conv3x3_launch(const ConvParams& p, int cin, int grid, cudaStream_t stream) 
         err = cudaLaunchKernelEx(&cfg, k_conv3x3_pair, p);
         if (err) return (int)err;
     } else if (cin == 128) {
-        if (!attr_done[1]) { err = cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM); if (err) return (int)err; attr_done[1] = true; }
+        err = smem_opt_in((const void*)k_conv3x3<128>, (int)Cfg<128>::SMEM); if (err) return (int)err;
         k_conv3x3<128><<<grid, CONV1_THREADS, Cfg<128>::SMEM, stream>>>(p);
     } else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
@@ -936,13 +934,9 @@ bool trunk_fused_supported(int channels, int board_pitch, int row_pitch, int n_l
 int trunk_group_boards(int board_pitch) { return TRUNK_GROUP * 256 / board_pitch; }
 
 int trunk_launch(const TrunkParams& p, int grid, cudaStream_t stream) {
-    static bool done = false;
     cudaError_t err;
-    if (!done) {
-        err = cudaFuncSetAttribute(k_trunk_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err;
-        err = cudaFuncSetAttribute(k_trunk_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrunkCfg::SMEM); if (err) return (int)err;
-        done = true;
-    }
+    err = smem_opt_in((const void*)k_trunk_pair<false>, (int)TrunkCfg::SMEM); if (err) return (int)err;
+    err = smem_opt_in((const void*)k_trunk_pair<true>, (int)TrunkCfg::SMEM); if (err) return (int)err;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(grid & ~1)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TrunkCfg::SMEM; cfg.stream = stream;
     cudaLaunchAttribute at[1];

@@ -12,6 +12,8 @@
 #include <cmath>
 #include <algorithm>
 #include <unordered_set>
+#include <set>
+#include <mutex>
 #include <cuda.h>
 
 #include "../../include/az_b200.h"
@@ -20,6 +22,18 @@
 namespace az {
 static thread_local std::string g_error;
 void set_error(const std::string& s) { g_error = s; }
+
+cudaError_t smem_opt_in(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;      // (kernel, device)
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return cudaSuccess;
+    if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) return e;
+    done.insert({kernel, dev});
+    return cudaSuccess;
+}
 }  // namespace az
 
 #include "gomoku.cuh"
@@ -409,14 +423,14 @@ struct Net {
 template <class G>
 __global__ void __launch_bounds__(128) k_rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_moves, int32_t* legal,
                                                      int32_t* n_legal, int32_t* terminal, int32_t* result, int32_t* player, float* planes,
-                                                     uint64_t* hist_scratch /*[n_games][max_moves]*/) {
+                                                     uint64_t* hist_scratch /*[n_games][max_moves + 1]*/) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= n_games) return;
     typename G::Warp& w = warp_ws<G>(smem);
     G::w_init(w, lane);
-    G::w_attach_history(w, hist_scratch + (size_t)g * max_moves, lane);
+    G::w_attach_history(w, hist_scratch + (size_t)g * (max_moves + 1), lane);     // initial position + one key per move
     int bad = 0;
     for (int i = 0; i < n_moves[g]; ++i) {
         if (!G::w_apply(w, moves[(size_t)g * max_moves + i], lane, true)) { bad = 1; break; }   // makeMove throws
@@ -572,6 +586,7 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
         const int per = (T + NG - 1) / NG;
+        NG = (T + per - 1) / per;                       // groups of `per` slots; a count that does not divide T leaves no empty trailing group
         groups.resize(NG);
         // SM partitions: AZ_SM_SPLIT=<SMs of the conv partition> (0 / unset: off); only useful with >= 2 stream groups and the network evaluator
         if (const char* sp = getenv("AZ_SM_SPLIT")) {
@@ -676,7 +691,21 @@ struct EngineT : EngineBase {
         for (int i = 0; i < n; ++i) AZ_CHECK(G::host_apply(s, moves[i]), "illegal move in az_engine_set_root");   // IllegalMove (igamestate.h:36-52)
         AZ_CHECK(!order || G::FIRST_FILL, "a root child order can only be given for Gomoku (QUIRK G2)");
         std::vector<int16_t> ord;
-        if (order) { ord.resize(n_order); for (int i = 0; i < n_order; ++i) ord[i] = (int16_t)order[i]; }
+        if (order) {
+            // the caller's first-fill order must be exactly the root's legal moves, each once (k_expand_backup trusts it)
+            AZ_CHECK(n_order >= 0 && n_order <= MC, "az_engine_set_root: first_fill_order longer than the action space");
+            std::vector<char> seen(G::CELLS, 0);
+            int n_empty = 0;
+            for (int a = 0; a < G::CELLS; ++a) { State t = s; if (G::host_apply(t, a)) ++n_empty; }
+            for (int i = 0; i < n_order; ++i) {
+                const int a = order[i];
+                AZ_CHECK(a >= 0 && a < G::CELLS && !seen[a], "az_engine_set_root: first_fill_order entry out of range or repeated");
+                State t = s; AZ_CHECK(G::host_apply(t, a), "az_engine_set_root: first_fill_order names an occupied cell");
+                seen[a] = 1;
+            }
+            AZ_CHECK(n_order == n_empty, "az_engine_set_root: first_fill_order must list every legal move of the root once");
+            ord.resize(n_order); for (int i = 0; i < n_order; ++i) ord[i] = (int16_t)order[i];
+        }
         return write_fresh(slot, s, order ? ord.data() : nullptr, order ? n_order : 0, order != nullptr);
     }
 
@@ -833,9 +862,17 @@ struct EngineT : EngineBase {
     int drain(void* buf, size_t cap, size_t* n, bool device) override {
         if (sync_all()) return -1;
         int32_t cnt = 0; AZ_CUDA_CHECK(cudaMemcpy(&cnt, ring_count, 4, cudaMemcpyDeviceToHost));
-        size_t take = std::min<size_t>(std::min<size_t>(cnt, ring_cap), cap);
+        const size_t have = std::min<size_t>(cnt, ring_cap), take = std::min(have, cap);
         if (take) AZ_CUDA_CHECK(cudaMemcpy(buf, ring, take * sizeof(SampleT), device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
-        AZ_CUDA_CHECK(cudaMemset(ring_count, 0, 4));
+        // a caller buffer smaller than the ring content keeps the rest for the next call (records move to the front of the ring)
+        const int32_t left = (int32_t)(have - take);
+        if (left) {
+            SampleT* tmp; if (dev_alloc(&tmp, (size_t)left)) return -1;
+            AZ_CUDA_CHECK(cudaMemcpy(tmp, ring + take, (size_t)left * sizeof(SampleT), cudaMemcpyDeviceToDevice));
+            AZ_CUDA_CHECK(cudaMemcpy(ring, tmp, (size_t)left * sizeof(SampleT), cudaMemcpyDeviceToDevice));
+            cudaFree(tmp);
+        }
+        AZ_CUDA_CHECK(cudaMemcpy(ring_count, &left, 4, cudaMemcpyHostToDevice));
         *n = take;
         return 0;
     }
@@ -1023,8 +1060,10 @@ struct EngineT : EngineBase {
 
     int rules_replay(const int32_t* moves, const int32_t* n_moves, int n_games, int max_mv, int32_t* legal, int32_t* n_legal,
                      int32_t* terminal, int32_t* result, int32_t* player, float* planes) override {
+        AZ_CHECK(n_games >= 1 && max_mv >= 1 && moves && n_moves, "az_rules_replay: bad sizes / null buffer");
+        for (int g = 0; g < n_games; ++g) AZ_CHECK(n_moves[g] >= 0 && n_moves[g] <= max_mv, "az_rules_replay: n_moves out of range");
         int32_t *dm, *dn, *dl, *dnl, *dt, *dr, *dp; float* dpl = nullptr; uint64_t* dh;
-        if (dev_alloc(&dh, (size_t)n_games * max_mv)) return -1;
+        if (dev_alloc(&dh, (size_t)n_games * (max_mv + 1))) return -1;
         if (dev_alloc(&dm, (size_t)n_games * max_mv) || dev_alloc(&dn, n_games) || dev_alloc(&dl, (size_t)n_games * MC) || dev_alloc(&dnl, n_games) ||
             dev_alloc(&dt, n_games) || dev_alloc(&dr, n_games) || dev_alloc(&dp, n_games)) return -1;
         if (planes && dev_alloc(&dpl, (size_t)n_games * G::PLANES * G::CELLS)) return -1;

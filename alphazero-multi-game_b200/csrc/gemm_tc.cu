@@ -262,8 +262,7 @@ __global__ void __launch_bounds__(256) k_pool(PoolParams p) {
 }  // namespace
 
 template <int NSUB> static int gemm_tc_launch_n(const GemmParams& p, int grid, cudaStream_t s) {
-    static bool done = false;
-    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GCfg<NSUB>::SMEM); if (e) return (int)e; done = true; }
+    if (cudaError_t e = smem_opt_in((const void*)k_gemm_tc<NSUB>, (int)GCfg<NSUB>::SMEM)) return (int)e;
     k_gemm_tc<NSUB><<<grid, G_THREADS, GCfg<NSUB>::SMEM, s>>>(p);
     return (int)cudaGetLastError();
 }
@@ -277,8 +276,7 @@ int gemm_tc_launch(const GemmParams& p, int grid, cudaStream_t s) {
 }
 int pool_launch(const PoolParams& p, int grid, cudaStream_t s) {
     const size_t smem = (size_t)POOL_NB * (p.board_pitch + 1) * 16;
-    static bool done = false;
-    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); if (e) return (int)e; done = true; }
+    if (cudaError_t e = smem_opt_in((const void*)k_pool, 96 * 1024)) return (int)e;
     if (smem > 96 * 1024) return (int)cudaErrorInvalidValue;
     k_pool<<<grid, 256, smem, s>>>(p);
     return (int)cudaGetLastError();

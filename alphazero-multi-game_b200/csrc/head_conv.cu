@@ -193,8 +193,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_head_conv_pool(const HeadConv
 bool head_conv_supported(int channels, int board_pitch, int H, int W) { return channels == 128 && board_pitch <= HC_ROWS && H >= 8 && W >= 8; }
 
 int head_conv_launch(const HeadConvParams& p, int grid, cudaStream_t s) {
-    static bool done = false;
-    if (!done) { cudaError_t e = cudaFuncSetAttribute(k_head_conv_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SMEM); if (e) return (int)e; done = true; }
+    if (cudaError_t e = smem_opt_in((const void*)k_head_conv_pool, (int)HC_SMEM)) return (int)e;
     k_head_conv_pool<<<grid, HC_THREADS, HC_SMEM, s>>>(p);
     return (int)cudaGetLastError();
 }

@@ -5,6 +5,11 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
+namespace az {
+// once per (kernel, device) opt-in to > 48 KB of dynamic shared memory (defined in engine.cu; see common.cuh)
+cudaError_t smem_opt_in(const void* kernel, int bytes);
+}
+
 namespace az { namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -5,7 +5,7 @@
 // One warp owns one tree and runs ONE simulation per wave, so inside a tree the arithmetic is exactly the
 // reference's serial ParallelMCTS (numThreads = 1): every float operation below is a single correctly
 // rounded fp32 op in the reference's order (no FMA contraction) and every tie-break follows the reference
-// scan order — visit counts are bit-exact, see tests/test_engine_parity.py.
+// scan order — visit counts are bit-exact, see tests/test_engine_gpu.py.
 #pragma once
 #include <cuda_bf16.h>
 #include <cfloat>

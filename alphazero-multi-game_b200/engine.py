@@ -240,7 +240,7 @@ class Engine:
         """Copy finished-game samples to HOST memory (pinned `out` if given) and empty the device ring."""
         dt = self.sample_dtype()
         if out is None:
-            cap = cap or max(32 * self.n_slots, 4096)
+            cap = cap or max(32 * self.n_slots, 4096, int(self.cfg.sample_ring_capacity))      # the whole ring (engine default: max(32 * slots, 4096))
             out = np.zeros(cap, dt)
         n = C.c_size_t()
         self._check(self.lib.az_engine_drain_samples(self.h, out.ctypes.data, len(out), C.byref(n)))

@@ -6,7 +6,7 @@ stem conv3x3(no bias)+BN+ReLU → `blocks` x [conv3x3+BN+ReLU, conv3x3+BN, +skip
 min(8,H) → policy: conv1x1(→32, no bias)+BN+ReLU → FC(32*8*8 → A) raw logits; value: conv1x1(→32)+BN+ReLU →
 FC(→256)+ReLU → FC(256→1) → tanh.  Random init per _initialize_weights (ddw_randwire.py:189-201).
 
-This module is the fp32 parity reference for the bf16 tcgen05 trunk (tests/test_nn_parity.py) and the
+This module is the fp32 parity reference for the bf16 tcgen05 trunk (tests/test_nn_gpu.py) and the
 source of the AZW1 weight blob; it is never on the engine's compute path.
 """
 import struct

@@ -19,6 +19,7 @@
 #include <vector>
 #include <queue>
 #include <unordered_set>
+#include <unordered_map>
 #include <algorithm>
 #include <memory>
 #include <cstdlib>
@@ -45,6 +46,10 @@ struct State {
     virtual int action_space() const = 0;
     virtual int board_size() const = 0;
     virtual uint64_t key() const = 0;           // HashEvaluator key (Appendix C)
+    // Granularity of the reference's getHash(), the TranspositionTable key (parallel_mcts.cpp:320-336, 851): Gomoku = stones + player
+    // (gomoku_state.cpp:620-656), Go = stones + player + ko point (go_state.cpp:773-811) — what key() covers — but chess = the piece
+    // PLACEMENT only (QUIRK C8, see Chess::tt_key).
+    virtual uint64_t tt_key() const { return key(); }
     virtual int planes() const = 0;
     virtual void tensor(float* out) const = 0;  // [planes][N][N]
     virtual int game_type() const = 0;
@@ -509,6 +514,11 @@ struct Chess : State {
         return ONGOING;
     }
     bool terminal() const override { return result() != ONGOING; }
+    // QUIRK C8: ChessState::getHash() is recomputed in full only while hash_dirty_ (ctor / setFromFEN); afterwards setPiece updates it
+    // incrementally (chess_state.cpp:230-241) and makeMove never marks it dirty, so side to move, castling rights and the e.p. square
+    // of the CURRENT position never enter it.  The reference's TranspositionTable therefore returns the cached policy / value of
+    // whichever position with the same piece placement was evaluated first in the game — also one with the other side to move.
+    uint64_t tt_key() const override { return h; }
     uint64_t key() const override {               // HashEvaluator key for chess (this repo's definition; the survey probe had none)
         uint64_t k = 1469598103934665603ULL;
         for (int s = 0; s < 64; ++s) k = mix64(k ^ (uint64_t)(b[s].t + 8 * b[s].c));
@@ -553,6 +563,18 @@ struct Search {
     std::unique_ptr<State> root_state; std::vector<Node> pool; int root = 0;
     int sims = 800; float cpuct = 1.5f; int vl = 3; int max_depth = 1000;
     eval_cb_t cb = nullptr; void* user = nullptr; long evals = 0;
+    // TranspositionTable (transposition_table.cpp:44-84, 128-176) as the serial search sees it: lookup by full 64-bit hash, first store
+    // wins ("existing-key store keeps the old policy").  Slot collisions (hash & (size - 1)) and the age-based replacement are not
+    // modelled: with 1 M slots and a few thousand entries per game they do not occur in the pinned runs.  One table per game, kept
+    // across moves (self_play_manager.cpp:159,175).  use_tt = false gives the TT-free search the device engine implements.
+    bool use_tt = true; long tt_hits = 0;
+    std::unordered_map<uint64_t, std::pair<std::vector<float>, float>> tt;
+    bool tt_lookup(const State& s, std::vector<float>& pol, float& v) {
+        if (!use_tt) return false;
+        auto it = tt.find(s.tt_key()); if (it == tt.end()) return false;
+        pol = it->second.first; v = it->second.second; ++tt_hits; return true;
+    }
+    void tt_store(const State& s, const std::vector<float>& pol, float v) { if (use_tt) tt.emplace(s.tt_key(), std::make_pair(pol, v)); }
 
     Search(const State& s, int sims_, float c, int vl_) : root_state(s.clone()), sims(sims_), cpuct(c), vl(vl_) {
         // root MCTSNode ctor evaluates state->isTerminal()/getGameResult() (mcts_node.cpp:24-25);
@@ -606,12 +628,20 @@ struct Search {
         if (pool[ni].term || st->terminal()) {              // :300-313 (M10)
             if (pool[ni].term) value = to_value(pool[ni].result, st->player());
             else { value = to_value(st->result(), st->player()); pool[ni].term = true; pool[ni].result = st->result(); }
-        } else { std::vector<float> pol; evaluate(*st, pol, value); expand(ni, *st, pol); }
+        } else {                                            // :316-358: TT first, else evaluate + store
+            std::vector<float> pol;
+            if (!tt_lookup(*st, pol, value)) { evaluate(*st, pol, value); tt_store(*st, pol, value); }
+            expand(ni, *st, pol);
+        }
         float cv = value;                                   // backpropagate :782-833 (M7)
         for (auto it = path.rbegin(); it != path.rend(); ++it) { Node& n = pool[*it]; rem_vl(n); n.N += 1; n.W = n.W + cv; cv = -cv; }
     }
     void search() {                                         // search :142-274 (M1), serial
-        if (!pool[root].expanded && !root_state->terminal()) { std::vector<float> pol; float v; evaluate(*root_state, pol, v); expand(root, *root_state, pol); }
+        if (!pool[root].expanded && !root_state->terminal()) {      // :153-163: evaluateState (TT lookup inside, :848-856), store, expand
+            std::vector<float> pol; float v;
+            if (!tt_lookup(*root_state, pol, v)) { evaluate(*root_state, pol, v); tt_store(*root_state, pol, v); }
+            expand(root, *root_state, pol);
+        }
         for (int i = 0; i < sims; ++i) simulate();
     }
     std::vector<float> probs(float T) const {               // getVisitCountDistribution mcts_node.cpp:289-322 (M12)
@@ -681,6 +711,9 @@ void orc_mcts_free(void* h) { delete (Search*)h; }
 void orc_mcts_search(void* h) { ((Search*)h)->search(); }
 void orc_mcts_set_sims(void* h, int sims) { ((Search*)h)->sims = sims; }
 long orc_mcts_eval_calls(void* h) { return ((Search*)h)->evals; }
+// 1 (default) = with the reference's TranspositionTable semantics; 0 = TT-free (every leaf evaluated on its own input: what the device engine does)
+void orc_mcts_set_tt(void* h, int on) { ((Search*)h)->use_tt = on != 0; }
+long orc_mcts_tt_hits(void* h) { return ((Search*)h)->tt_hits; }
 int orc_mcts_root_stats(void* h, int* actions, int* N, float* W, float* P, int cap, int* rootN, float* rootW) {
     Search* s = (Search*)h; const Node& r = s->pool[s->root];
     for (int i = 0; i < r.nchild && i < cap; ++i) { const Node& c = s->pool[r.first + i]; actions[i] = c.action; N[i] = c.N; W[i] = c.W; P[i] = c.P; }

@@ -21,10 +21,17 @@
 #include <vector>
 #include <string>
 #include <future>
+#include <algorithm>
 
 #include "alphazero/core/igamestate.h"
 #include "alphazero/games/gomoku/gomoku_state.h"
 #include "alphazero/games/go/go_state.h"
+#include "alphazero/games/chess/chess_state.h"
+#include "alphazero/selfplay/game_record.h"
+#include "alphazero/core/registry.h"
+#define private public      /* Dataset::augmentExample is private: the harness pins its image ORDER, which extractExamples' final shuffle hides */
+#include "alphazero/selfplay/dataset.h"
+#undef private
 #include "alphazero/mcts/parallel_mcts.h"
 #include "alphazero/mcts/mcts_node.h"
 #include "alphazero/mcts/transposition_table.h"
@@ -55,6 +62,14 @@ uint64_t state_key(const IGameState& s) {
         for (int pos = 0; pos < n * n; ++pos) h = mix64(h ^ (uint64_t)g.getStone(pos));
         h = mix64(h ^ (uint64_t)g.getCurrentPlayer());
         h = mix64(h ^ (uint64_t)(int64_t)(g.getKoPoint() + 1));
+    } else if (s.getGameType() == GameType::CHESS) {
+        // this repo's chess key (oracle/az_oracle.cpp Chess::key): pieces, side, castling rights, e.p. square
+        const auto& c = dynamic_cast<const alphazero::chess::ChessState&>(s);
+        for (int sq = 0; sq < 64; ++sq) { const auto pc = c.getPiece(sq); h = mix64(h ^ (uint64_t)((int)pc.type + 8 * (int)pc.color)); }
+        h = mix64(h ^ (uint64_t)c.getCurrentPlayer());
+        const auto cr = c.getCastlingRights();
+        h = mix64(h ^ (uint64_t)((cr.white_kingside ? 1 : 0) | (cr.white_queenside ? 2 : 0) | (cr.black_kingside ? 4 : 0) | (cr.black_queenside ? 8 : 0)));
+        h = mix64(h ^ (uint64_t)(int64_t)(c.getEnPassantSquare() + 1));
     }
     return h;
 }
@@ -142,6 +157,7 @@ void* ref_state_new(int game_type, int board_size) {
     try {
         if (game_type == 0) return new alphazero::gomoku::GomokuState(board_size, false, false, 1, false);
         if (game_type == 2) return new alphazero::go::GoState(board_size, 7.5f, true, true);
+        if (game_type == 1) return new alphazero::chess::ChessState();
     } catch (...) {}
     return nullptr;
 }
@@ -177,12 +193,94 @@ int ref_go_stone(void* h, int pos) { return ((alphazero::go::GoState*)h)->getSto
 int ref_go_ko(void* h) { return ((alphazero::go::GoState*)h)->getKoPoint(); }
 int ref_go_captured(void* h, int player) { return ((alphazero::go::GoState*)h)->getCapturedStones(player); }
 
+// chess extras (tests/games/chess/chess_state_test.cpp drives states through setFromFEN)
+int ref_chess_set_fen(void* h, const char* fen) { try { return ((alphazero::chess::ChessState*)h)->setFromFEN(fen) ? 0 : -1; } catch (...) { return -1; } }
+int ref_chess_piece(void* h, int sq) { const auto pc = ((alphazero::chess::ChessState*)h)->getPiece(sq); return (int)pc.type + 8 * (int)pc.color; }
+int ref_chess_in_check(void* h) { return ((alphazero::chess::ChessState*)h)->isInCheck() ? 1 : 0; }
+void ref_chess_set_fide(int) {}    // the reference IS the literal pawn-attack rule (QUIRK C5); kept so both checkers export the same names
+long ref_chess_perft(void* h, int depth) {
+    if (depth == 0) return 1;
+    IGameState* s = (IGameState*)h;
+    auto mv = s->getLegalMoves();
+    if (depth == 1) return (long)mv.size();
+    long n = 0;
+    for (int a : mv) { auto c = s->clone(); c->makeMove(a); n += ref_chess_perft(c.get(), depth - 1); }
+    return n;
+}
+
+// ---------------------------------------------------------------- Dataset / GameRecord (src/selfplay/dataset.cpp, game_record.cpp)
+// Dataset::extractExamples builds its replay state with core::createGameState (game_factory.cpp:92-120), which asks the
+// GameRegistry — and the reference registers nothing in it (its one REGISTER_GAME file, src/core/gomoku_state_plugin.cpp, is not part
+// of any build target; chess and Go have none).  The harness, as the application, registers the three games with the argument
+// names game_factory.cpp passes.
+static void register_games_once() {
+    static bool done = false; if (done) return; done = true;
+    auto& reg = alphazero::core::GameRegistry::instance();
+    using alphazero::core::VariantArgs;
+    reg.registerGame("gomoku", [](const VariantArgs& a) -> std::unique_ptr<IGameState> {
+        return std::make_unique<alphazero::gomoku::GomokuState>(a.get<int>("boardSize", 15), a.get<bool>("useRenju", false), a.get<bool>("useOmok", false),
+                                                                a.get<int>("seed", 0), a.get<bool>("useProLongOpening", false)); });
+    reg.registerGame("go", [](const VariantArgs& a) -> std::unique_ptr<IGameState> {
+        return std::make_unique<alphazero::go::GoState>(a.get<int>("boardSize", 19), a.get<float>("komi", 7.5f), a.get<bool>("chineseRules", true), true); });
+    reg.registerGame("chess", [](const VariantArgs& a) -> std::unique_ptr<IGameState> {
+        return std::make_unique<alphazero::chess::ChessState>(a.get<bool>("chess960", false)); });
+}
+// Dataset::augmentExample on one example: planes [C][N][N], policy [P] -> the 7 extra images in the reference's order
+void ref_augment_example(const float* planes, int C, int N, const float* policy, int P, int game_type, float* out_planes, float* out_policy) {
+    alphazero::selfplay::TrainingExample ex;
+    ex.state.assign(C, std::vector<std::vector<float>>(N, std::vector<float>(N)));
+    for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) ex.state[c][i][j] = planes[((size_t)c * N + i) * N + j];
+    ex.policy.assign(policy, policy + P); ex.value = 0.0f;
+    alphazero::selfplay::Dataset ds;
+    auto aug = ds.augmentExample(ex, (GameType)game_type);
+    for (size_t k = 0; k < aug.size(); ++k) {
+        for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) out_planes[(((size_t)k * C + c) * N + i) * N + j] = aug[k].state[c][i][j];
+        for (int a = 0; a < P; ++a) out_policy[(size_t)k * P + a] = aug[k].policy[a];
+    }
+}
+// Dataset::addGameRecord + extractExamples(includeAugmentations) for ONE game: moves[n], policies [n][P], result code.
+// extractExamples ends with a shuffle (random_device seed), so the examples come back in shuffled order: callers compare as multisets.
+// Returns the number of examples (call with out_planes == nullptr to query); -1 on an exception (illegal recorded move).
+int ref_dataset_extract(int game_type, int board_size, const int* moves, int n, const float* policies, int P, int result, int augment,
+                        float* out_planes, float* out_policy, float* out_value) {
+    try {
+        register_games_once();
+        alphazero::selfplay::GameRecord rec((GameType)game_type, board_size, false);
+        for (int i = 0; i < n; ++i) rec.addMove(moves[i], std::vector<float>(policies + (size_t)i * P, policies + (size_t)(i + 1) * P), 0.0f, 0);
+        rec.setResult((alphazero::core::GameResult)result);
+        alphazero::selfplay::Dataset ds;
+        ds.addGameRecord(rec);
+        ds.extractExamples(augment != 0);
+        const auto& ex = ds.examples_;
+        if (out_planes) {
+            size_t kp = 0, kq = 0;
+            for (size_t e = 0; e < ex.size(); ++e) {
+                for (auto& pl : ex[e].state) for (auto& row : pl) for (float x : row) out_planes[kp++] = x;
+                for (float x : ex[e].policy) out_policy[kq++] = x;
+                out_value[e] = ex[e].value;
+            }
+        }
+        return (int)ex.size();
+    } catch (...) { return -1; }
+}
+// GameRecord::toJson for a record built through addMove / setResult (timestamp = now); writes at most cap-1 bytes + NUL, returns the length
+int ref_game_record_json(int game_type, int board_size, int variant, const int* moves, int n, const float* policies, const int* policy_len, const float* values,
+                         const long long* think_ms, int result, char* out, int cap) {
+    alphazero::selfplay::GameRecord rec((GameType)game_type, board_size, variant != 0);
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) { rec.addMove(moves[i], std::vector<float>(policies + off, policies + off + policy_len[i]), values[i], think_ms[i]); off += policy_len[i]; }
+    rec.setResult((alphazero::core::GameResult)result);
+    const std::string j = rec.toJson();
+    if (out && cap > 0) { const size_t k = std::min<size_t>(j.size(), (size_t)cap - 1); std::memcpy(out, j.data(), k); out[k] = 0; }
+    return (int)j.size();
+}
+
 // ---------------------------------------------------------------- search API
 // evaluator: 0 = HashEvaluator, 1 = CallbackEvaluator(cb,user)
 void* ref_mcts_new(void* state, int sims, float cpuct, int virtual_loss, int evaluator, eval_cb_t cb, void* user) {
     auto* r = new RefMcts();
     if (evaluator == 0) r->nn.reset(new HashEvaluator()); else r->nn.reset(new CallbackEvaluator(cb, user));
-    r->tt.reset(new alphazero::mcts::TranspositionTable(1 << 16, 16));
+    r->tt.reset(new alphazero::mcts::TranspositionTable(1 << 20, 1 << 10));
     alphazero::mcts::MCTSConfig cfg;
     cfg.numThreads = 1; cfg.numSimulations = sims; cfg.cPuct = cpuct; cfg.fpuReduction = 0.0f;
     cfg.virtualLoss = virtual_loss; cfg.useDirichletNoise = false;

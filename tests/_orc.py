@@ -37,12 +37,16 @@ class Checker:
         f("state_tensor", C.c_int, [C.c_void_p, C.c_void_p])
         f("state_key", C.c_uint64, [C.c_void_p])
         f("hash_eval", None, [C.c_void_p, C.c_void_p, C.c_void_p])
-        if prefix == "orc_":     # chess exists only in the restatement (the reference's chess is not runnable)
-            f("chess_set_fen", C.c_int, [C.c_void_p, C.c_char_p])
-            f("chess_set_fide", None, [C.c_int])
-            f("chess_perft", C.c_long, [C.c_void_p, C.c_int])
-            f("chess_piece", C.c_int, [C.c_void_p, C.c_int])
-            f("chess_in_check", C.c_int, [C.c_void_p])
+        # chess: the restatement, and the reference itself with its legality recursion cut (oracle/build_ref.sh shim 6)
+        f("chess_set_fen", C.c_int, [C.c_void_p, C.c_char_p])
+        f("chess_set_fide", None, [C.c_int])
+        f("chess_perft", C.c_long, [C.c_void_p, C.c_int])
+        f("chess_piece", C.c_int, [C.c_void_p, C.c_int])
+        f("chess_in_check", C.c_int, [C.c_void_p])
+        if prefix == "ref_":     # the reference's Dataset / GameRecord (src/selfplay/dataset.cpp, game_record.cpp)
+            f("augment_example", None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+            f("dataset_extract", C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+            f("game_record_json", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int])
         f("go_stone", C.c_int, [C.c_void_p, C.c_int])
         f("go_ko", C.c_int, [C.c_void_p])
         f("go_captured", C.c_int, [C.c_void_p, C.c_int])
@@ -56,6 +60,9 @@ class Checker:
         f("mcts_action_probs", C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int])
         f("mcts_root_value", C.c_float, [C.c_void_p])
         f("mcts_update_with_move", None, [C.c_void_p, C.c_int])
+        if prefix == "orc_":
+            f("mcts_set_tt", None, [C.c_void_p, C.c_int])
+            f("mcts_tt_hits", C.c_long, [C.c_void_p])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.lib, self.prefix + name)

@@ -68,9 +68,77 @@ def playout_golden(R, game, n, seed, max_ply, pass_prob=0.03):
                 final_terminal=int(R.state_is_terminal(s)), final_result=int(R.state_result(s)))
 
 
+def chess_golden(R):
+    """Reference chess (recursion cut, oracle/build_ref.sh shim 6): digests of (legal order, terminal, result, player, isInCheck,
+    18 planes) on every position of seeded random games and on the C5 / C7 FEN cases; hash-evaluator searches."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_ref_chess_dataset as T
+    plays = []
+    for seed in range(8):
+        rng = np.random.default_rng(1000 + seed)
+        s = R.new_state(_orc.CHESS, 8)
+        moves, dig = [], []
+        for ply in range(450):
+            dig.append(T._digest(R, s))
+            if R.state_is_terminal(s):
+                break
+            lg = R.legal(s)
+            caps = [a for a in lg if R.chess_piece(s, int(a) & 63) != 0]
+            a = int(rng.choice(caps)) if (caps and rng.random() < 0.35) else int(rng.choice(lg))
+            assert R.state_make_move(s, a) == 0
+            moves.append(a)
+        plays.append(dict(seed=1000 + seed, moves=moves, ply_digest=dig, final_result=int(R.state_result(s))))
+    fens = {fen: T._digest(R, R.chess_from_fen(fen)) for fen in T.C5_FENS + [f for f, _ in T.C7_FENS]}
+    searches = []
+    for sims, n_moves, opening in [(150, 3, []), (100, 3, plays[0]["moves"][:16])]:
+        s = R.new_state(_orc.CHESS, 8)
+        for a in opening:
+            assert R.state_make_move(s, a) == 0
+        m = R.mcts_new(s, sims, 1.5, 3, 0, None, None)
+        out = []
+        for mv in range(n_moves):
+            R.mcts_search(m)
+            st = R.root_stats(m)
+            act = R.mcts_select_action(m, 1, 1.0)
+            out.append(dict(actions=st["actions"].tolist(), N=st["N"].tolist(), W=bits(st["W"]), P=bits(st["P"]), rootN=int(st["rootN"]), action=int(act)))
+            R.mcts_update_with_move(m, act)
+        searches.append(dict(sims=sims, opening=[int(a) for a in opening], moves=out))
+    return dict(playouts=plays, fens=fens, search=searches)
+
+
+def dataset_golden(R):
+    """Reference Dataset::augmentExample / extractExamples: digests per image / per example list."""
+    import test_ref_chess_dataset as T
+    O = _orc.oracle()
+    aug = []
+    for seed, (c, n, p, game) in enumerate([(11, 15, 225, 0), (8, 9, 82, 2), (8, 19, 362, 2), (11, 15, 97, 0), (8, 9, 30, 2)]):
+        pl, po = T._random_example(np.random.default_rng(seed), c, n, p)
+        r_pl, r_po = T._ref_augment(R, pl, po, game)
+        aug.append(dict(seed=seed, c=c, n=n, p=p, images=[hashlib.sha256(r_pl[k].tobytes() + r_po[k].tobytes()).hexdigest()[:16] for k in range(7)]))
+    ext = []
+    for i, (game, board, plen) in enumerate([(0, 9, 81), (2, 9, 82), (0, 15, 40), (1, 8, 37)]):
+        rng = np.random.default_rng(50 + i)
+        mv, res = T._random_game(O, rng, game, board, 12)
+        res = res if res != 0 else 3
+        pols = np.random.default_rng(70 + i).random((len(mv), plen)).astype(np.float32)
+        for augm in (1, 0):
+            k = 8 if (augm and game != 1) else 1
+            c = O.state_tensor(O.new_state(game, board), None)
+            n_ex = len(mv) * k
+            r_pl = np.zeros((n_ex, c, board, board), np.float32); r_po = np.zeros((n_ex, plen), np.float32); r_va = np.zeros(n_ex, np.float32)
+            assert R.dataset_extract(game, board, np.asarray(mv, np.int32).ctypes.data, len(mv), pols.ctypes.data, plen, res, augm, r_pl.ctypes.data, r_po.ctypes.data, r_va.ctypes.data) == n_ex
+            ext.append(dict(game=game, board=board, plen=plen, seed=70 + i, moves=[int(a) for a in mv], result=int(res), augment=augm,
+                            digest=hashlib.sha256("".join(T._canon(r_pl, r_po, r_va)).encode()).hexdigest()[:16]))
+    return dict(augment=aug, extract=ext)
+
+
 def main():
     R = _orc.reference()
     assert R is not None, "build oracle/_ref first (make -C oracle ref)"
+    json.dump(chess_golden(R), open(os.path.join(HERE, "chess_reference.json"), "w"))
+    json.dump(dataset_golden(R), open(os.path.join(HERE, "dataset_reference.json"), "w"))
+    if "--chess-dataset-only" in sys.argv:
+        return
     searches = [search_golden(R, _orc.GOMOKU, 15, 800, 6), search_golden(R, _orc.GO, 9, 400, 4),
                 search_golden(R, _orc.GOMOKU, 9, 200, 30)]
     json.dump(searches, open(os.path.join(HERE, "search_hash_eval.json"), "w"))

@@ -1,8 +1,8 @@
 """GPU parity tests for chess (BASELINE.json configs[4]): device move generation in the reference's
 order, legality (incl. the literal isSquareAttacked quirk C5), castling / en passant / promotion, terminal rules (mate,
 stalemate, material, fifty-move, placement-only threefold), the 18 feature planes, and the batched search with the hash
-evaluator — against the oracle's chess restatement (pinned in tests/test_chess_oracle.py; the reference's own chess cannot
-run).  Bar: bit-exact."""
+evaluator — against the oracle's chess restatement, which is pinned to the reference's own chess (oracle/_ref, recursion cut by
+shim 6) position by position and search by search in tests/test_ref_chess_dataset.py.  Bar: bit-exact."""
 import numpy as np
 import pytest
 
@@ -94,7 +94,7 @@ def test_chess_search_matches_oracle():
     sims = 120
     roots = [[], SCRIPTED[1][:6], SCRIPTED[2][:4], _random_games(O, 1, 40, seed=9)[0]]
     eng = chess_engine(len(roots), sims=sims)
-    searches = []
+    searches, tt_free = [], []
     for t, mv in enumerate(roots):
         s = O.new_state(CHESS, 8)
         for a in mv:
@@ -103,12 +103,18 @@ def test_chess_search_matches_oracle():
             s = O.new_state(CHESS, 8); mv = []
         eng.set_root(t, mv)
         searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+        # the engine evaluates every leaf on its own input (no TranspositionTable); the oracle's default models the reference's table,
+        # whose chess key is the piece placement only (QUIRK C8, tests/test_ref_chess_dataset.py).  Compare with the TT-free oracle and
+        # check beside it that the reference-faithful search gives the same trees on these roots (no C8 event in them).
+        tt_free.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None)); O.mcts_set_tt(tt_free[-1], 0)
     for move in range(3):
         eng.search()
         acts = []
         for t in range(len(roots)):
-            O.mcts_search(searches[t])
-            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            O.mcts_search(searches[t]); O.mcts_search(tt_free[t])
+            a, b, c = eng.root_stats(t), O.root_stats(tt_free[t]), O.root_stats(searches[t])
+            assert np.array_equal(b["N"], c["N"]) and np.array_equal(bits(b["W"]), bits(c["W"])), ("C8 event in a parity root", move, t)
+            O.mcts_update_with_move(tt_free[t], O.mcts_select_action(tt_free[t], 1, 1.0))
             assert np.array_equal(a["actions"], b["actions"]), (move, t)
             assert np.array_equal(a["N"], b["N"]), (move, t)
             assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, t)
