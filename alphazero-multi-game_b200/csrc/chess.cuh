@@ -25,6 +25,7 @@ struct Chess {
     static constexpr int SAMPLE_VISITS = 2 * MAX_CHILDREN;   // (action, count) pairs in child order: 20480 counts would be 40 KB
     static constexpr int PLANES = 18;
     static constexpr bool FIRST_FILL = false;
+    static constexpr bool TT_COARSE = true;            // QUIRK C8: the reference's TT key is the piece placement only (tree.cuh EvalTT)
     static constexpr int MAX_GAME_MOVES = 512;         // engine cap: the game is drawn at this ply
     static constexpr int MAXH = MAX_GAME_MOVES + 2;
     static constexpr int EXTRA = 62;
@@ -282,7 +283,7 @@ struct Chess {
 #if defined(__CUDACC__)
     // ---------------------------------------------------------------------------------------------- warp API (tree_kernels.cuh)
     struct Warp { Leaf s; const uint64_t* hist; uint64_t* hist_rw; int16_t pseudo[MAX_CHILDREN]; int16_t legal[MAX_CHILDREN]; int n_legal; };
-    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch; };
+    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch, f16; };
 
     __device__ static void copy_words(void* dst, const void* src, int bytes, int lane) {
         const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
@@ -387,7 +388,7 @@ struct Chess {
             for (int q = 0; q < 4; ++q) {
                 __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { const int pl = q * 8 + e; v[e] = __float2bfloat16_rn(pl < PLANES ? feature(w.s.c, pl, sq, reps) : 0.0f); }
+                for (int e = 0; e < 8; ++e) { const int pl = q * 8 + e; v[e] = net16(pl < PLANES ? feature(w.s.c, pl, sq, reps) : 0.0f, enc.f16 != 0); }
                 *reinterpret_cast<uint4*>(enc.ptr + ((size_t)q * enc.p_total + row) * 8) = *reinterpret_cast<const uint4*>(v);
             }
         }
@@ -397,6 +398,7 @@ struct Chess {
         for (int i = lane; i < PLANES * 64; i += 32) out[i] = feature(w.s.c, i / 64, i % 64, reps);
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
+    __device__ static uint64_t w_tt_key(Warp& w) { return w.s.c.key; }           // ChessState::getHash() granularity: the placement
     // training examples (az_engine_make_examples); the repetition count travels in the snapshot (w.n_legal doubles as its holder)
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {
         for (int i = lane; i < 16; i += 32) reinterpret_cast<uint32_t*>(w.s.c.b)[i] = reinterpret_cast<const uint32_t*>(g->b)[i];

@@ -66,6 +66,18 @@ AZ_HD uint64_t mix64(uint64_t x) {
     x ^= x >> 33; return x;
 }
 
+#if defined(__CUDACC__)
+}  // namespace az
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+namespace az {
+// a network input value in the engine's 16-bit storage type: fp16 or bf16 bits in the same container (az_config.net_precision)
+AZ_D __nv_bfloat16 net16(float x, bool f16) {
+    if (f16) { const __half h = __float2half_rn(x); return *reinterpret_cast<const __nv_bfloat16*>(&h); }
+    return __float2bfloat16_rn(x);
+}
+#endif
+
 // core::GameResult (reference include/alphazero/core/igamestate.h:25-30)
 enum : int { RES_ONGOING = 0, RES_DRAW = 1, RES_WIN_P1 = 2, RES_WIN_P2 = 3 };
 

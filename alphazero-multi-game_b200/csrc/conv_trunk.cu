@@ -29,9 +29,10 @@ struct Cfg {
     static constexpr int SMEM = OFF_TSLOT + 16;
 };
 
-// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 → four 16-byte stores
-__device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
-                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false) {
+// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 / fp16 → four 16-byte stores
+template <bool F16>
+__device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
+                                            __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store, bool skip_store) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float v[8];
@@ -40,23 +41,28 @@ __device__ __forceinline__ void pair_epi_chunk(const uint32_t* r, const uint4* r
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bb[e];
         if (has_res) {
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[q]);
+            const uint32_t* rb = reinterpret_cast<const uint32_t*>(&res[q]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+            for (int e = 0; e < 4; ++e) { const float2 f = unpack2_16<F16>(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
         }
         uint4 o;
-        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+        uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float x = v[2 * e], y = v[2 * e + 1];
             if (relu) { x = fmaxf(x, 0.0f); y = fmaxf(y, 0.0f); }
             if (!valid) { x = 0.0f; y = 0.0f; }
-            ob[e] = __floats2bfloat162_rn(x, y);
+            ob[e] = pack2_16<F16>(x, y);
         }
         if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
         if (skip_store) continue;                           // k_trunk_pair: a row past the end of this pair's board group belongs to another pair
         *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
     }
+}
+__device__ __forceinline__ void pair_epi_chunk(bool f16, const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
+                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false) {
+    if (f16) epi_chunk_t<true>(r, res, has_res, sBias, c0, relu, valid, out, p_total, grow, no_store, skip_store);
+    else epi_chunk_t<false>(r, res, has_res, sBias, c0, relu, valid, out, p_total, grow, no_store, skip_store);
 }
 
 // 8 epilogue warps (warps 0-3: rows 0-127 of the item, warps 4-7: rows 128-255; a warp reads TMEM lanes 32 (w % 4) ...), warp 8 = TMA
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
         // MMA occupies the tensor pipe for 64 cycles and the loop must spend fewer instructions than that per MMA.
         // Descriptors are therefore built once; inside the loop a descriptor is `base + constant` (the start-address
         // field is the low 14 bits in 16-byte units and never carries into the LBO field for addresses < 256 KB).
-        constexpr uint32_t IDESC = idesc_bf16(128, C::COUT);
+        const uint32_t IDESC = idesc_16(128, C::COUT, p.f16 != 0);
         {
             const bool skip_a = (p.dbg & 8) != 0, skip_w = (p.dbg & 4) != 0;
             const uint64_t a_desc0 = smem_desc(smem_u32(sA) + CONV_HALO * 16, C::PLANE, 128);
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
         __syncwarp();
     } else {
         // ===================== epilogue (warps 0-7) =====================
-        const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+        const bool has_res = p.resid != nullptr, relu = p.relu != 0, f16 = p.f16 != 0;
         const size_t p_total = (size_t)p.p_total;
         const int mt = warp >> 2, wq = warp & 3;             // M tile of the item, TMEM lane quarter
         uint32_t ait = 0;
@@ -195,16 +201,16 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, rb);
-                if (!(p.dbg & 2)) pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, ra);
-                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, rb);
-                if (!(p.dbg & 2)) pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tc_fence_before(); mbar_arrive(&acc_empty[as]);                        // this thread's part of the stage's two accumulators is drained (256 arrivals)
-                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
             }
         }
     }
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
             // issue), so this thread runs in lock-step with the pipe: every instruction between two MMAs beyond a handful, and
             // every barrier wait at an item boundary, is pipe idle time.  Hence: all 72 MMAs of an item unrolled with
             // descriptors that are `register + constant`, per-tap bases computed once per launch, one fused wait per item.
-            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            const uint32_t IDESC = idesc_16(256, CONV_COUT, p.f16 != 0);
             {
                 // the whole warp runs the loop converged; the tcgen05 instructions sit under elect_one()
                 const bool skip_a = (p.dbg & 8) != 0;
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
             }
         } else {
             // ===================== epilogue (warps 0-3): TMEM lanes 32w..32w+31 = rows of this CTA's tile =====================
-            const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+            const bool has_res = p.resid != nullptr, relu = p.relu != 0, f16 = p.f16 != 0;
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
             grid_dep_wait();                // PDL: the residual is read, and the output written, only after the previous layer has completed
@@ -401,18 +407,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair(const ConvPara
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, rb);
-                if (!(p.dbg & 2)) pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, ra);
-                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, rb);
-                if (!(p.dbg & 2)) pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);      // accumulator drained: the leader's barrier (also from the leader itself)
-                if (!(p.dbg & 2)) pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
+                if (!(p.dbg & 2)) pair_epi_chunk(f16, rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow, (p.dbg & 32) != 0);
                 if (tr) p.trace[ait * 8 + 6 + rank * 512] = clock64();
             }
         }
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
             __syncwarp();
         } else if (warp == 5) {
             // ===================== MMA issuer (leader CTA) =====================
-            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            const uint32_t IDESC = idesc_16(256, CONV_COUT, p.f16 != 0);
             const uint64_t p0_desc0 = smem_desc(smem_u32(sP0) + WIDE_HALO * 16, C::PLANE, 128);
             const uint64_t p1_desc0 = smem_desc(smem_u32(sP1) + WIDE_HALO * 16, C::PLANE, 128);
             const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
             }
         } else {
             // ===================== epilogue (warps 0-3) =====================
-            const bool has_res = p.resid != nullptr, relu = p.relu != 0;
+            const bool has_res = p.resid != nullptr, relu = p.relu != 0, f16 = p.f16 != 0;
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
             grid_dep_wait();                // PDL: the residual is read, and the output written, only after the previous layer has completed
@@ -586,18 +592,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, rb);
-                pair_epi_chunk(ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, ra);
-                pair_epi_chunk(rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, rb);
-                pair_epi_chunk(ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                pair_epi_chunk(rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
             }
         }
     }
@@ -762,7 +768,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             __syncwarp();
         } else if (warp == 5) {
             // ===================== MMA issuer (leader CTA; converged warp, tcgen05 under elect.sync) =====================
-            constexpr uint32_t IDESC = idesc_bf16(256, CONV_COUT);
+            const uint32_t IDESC = idesc_16(256, CONV_COUT, p.f16 != 0);
             const uint64_t a_desc0 = smem_desc(smem_u32(sA) + PAIR_HALO * 16, C::PLANE, 128);
             const uint64_t b_desc0 = smem_desc(smem_u32(sW), C::WPLANE, 128);
             uint64_t a_tap0[9];
@@ -808,6 +814,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
         } else {
             // ===================== epilogue (warps 0-3) =====================
             const size_t p_total = (size_t)p.p_total;
+            const bool f16 = p.f16 != 0;
             uint32_t ait = 0;
             bool pending_b = false;
             // "these items of the current layer are in memory", to both CTAs' producers.  One publication per CTA: a named barrier orders the
@@ -862,18 +869,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         tmem_ld32(taddr, ra);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 32, rb);
-                        pair_epi_chunk(ra, res, has_res, bias, 0, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, ra, res, has_res, bias, 0, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 64, ra);
-                        pair_epi_chunk(rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 96, rb);
-                        pair_epi_chunk(ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                        pair_epi_chunk(rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow, false, CONTIG && !mine);
                         if (j == nj - 1) { if (nj >= TRUNK_BATCHED_MIN) pending_b = true; else publish(0); }
                     }
                 }

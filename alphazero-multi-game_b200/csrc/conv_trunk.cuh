@@ -50,6 +50,7 @@ struct ConvParams {
                                     // rows its predecessor wrote last, which are still in L2)
     long long* trace;               // profiling only: per-item clock64 stamps of cluster 0 (conv_bench, AZ_CONV_TRACE), else nullptr
     int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
+    int f16;                        // 1: activations, residual and weights are fp16 (else bf16) in the same 16-bit containers
     int pdl;                        // pair kernels: launch with programmatic stream serialization (the prologue — barriers, TMEM, the resident
                                     // weight half — runs while the previous kernel of the stream drains; activations are touched after griddepcontrol.wait)
 };
@@ -65,6 +66,7 @@ struct TrunkParams {
     const int* n_boards_dev; int n_rows;
     int n_layers, p_total, row_pitch;
     int board_pitch;                             // rows per board (H+1)*(W+1)
+    int f16;                                     // 1: fp16 activations / weights (else bf16)
     int group_boards;                            // boards a CTA pair takes through all layers at a time (trunk_group_boards): 74 pairs x 7 items x 128 KB stay in L2
     int dbg;                                     // profiling experiments only (AZ_TRUNK_DBG): 1 = no cluster-scope release fence, 2 = no proxy fence, 4 = publish every item at once instead of one item later; 0 in production
 };

@@ -61,15 +61,16 @@ AZ_D float bn_scale(const float* bn, int n, int i) { return bn[i] / sqrtf(bn[3 *
 
 // One 128-output-channel x `cin`-input-channel sub-block (co0.., ci0..) of a layer whose full weight tensor is
 // w[C][cin_total][9]: the conv kernels are built for 128 output channels, wider trunks run as channel slices (Net::forward).
+AZ_D __nv_bfloat16 w16(float v, int f16) { return net16(v, f16 != 0); }      // a conv weight in the network's 16-bit type (fp16 subnormals below 6e-5: absolute error <= 3e-8)
 __global__ void k_prep_conv(const float* __restrict__ w, const float* __restrict__ bn, __nv_bfloat16* img, float* bias,
-                            int C, int cin_total, int co0, int ci0, int cin_real, int cin, int pair) {
+                            int C, int cin_total, int co0, int ci0, int cin_real, int cin, int pair, int f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int CO = nn::CONV_COUT;
     if (idx < CO && bias) bias[idx] = bn[C + co0 + idx] - bn[2 * C + co0 + idx] * bn_scale(bn, C, co0 + idx);
     if (idx >= CO * cin * 9) return;
     const int t = idx % 9, ci = (idx / 9) % cin, co = idx / (9 * cin);
     const float v = ci < cin_real ? w[((size_t)(co0 + co) * cin_total + ci0 + ci) * 9 + t] * bn_scale(bn, C, co0 + co) : 0.0f;
-    img[nn::conv_weight_index(cin, pair != 0, t, ci, co)] = __float2bfloat16(v);
+    img[nn::conv_weight_index(cin, pair != 0, t, ci, co)] = w16(v, f16);
 }
 // Head GEMM weight images: three-term bf16 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (K' = 3K), image = [W_hi | W_hi | W_lo]
 AZ_D void put3(__nv_bfloat16* img, int K, int n, int k, float v) {
@@ -78,7 +79,7 @@ AZ_D void put3(__nv_bfloat16* img, int K, int n, int k, float v) {
 }
 // both 1x1 convs as one [64 x C] matrix (rows 0-31 policy, 32-63 value), BatchNorm scale folded in; b1 = BN shifts
 __global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restrict__ pbn, const float* __restrict__ vcw, const float* __restrict__ vbn,
-                           __nv_bfloat16* g1, float* b1, int C, __nv_bfloat16* h1) {
+                           __nv_bfloat16* g1, float* b1, int C, __nv_bfloat16* h1, int f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 64) { const float* bn = idx < 32 ? pbn : vbn; const int o = idx & 31; b1[idx] = bn[32 + o] - bn[64 + o] * bn_scale(bn, 32, o); }
     if (idx >= 64 * C) return;
@@ -87,9 +88,11 @@ __global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restric
     const float wf = cw[(size_t)o * C + c] * bn_scale(bn, 32, o);
     put3(g1, C, n, c, wf);
     if (h1 && C == 128) {       // the fused heads kernel's image (head_conv.cuh): bf16 hi / lo pair of the same folded weight
-        const __nv_bfloat16 hi = __float2bfloat16_rn(wf);
+        // (fp16 mode: an fp16 hi / lo pair — the MMA's two operands share the type of the trunk output it multiplies)
+        const __nv_bfloat16 hi = w16(wf, f16);
+        const float hif = f16 ? __half2float(*reinterpret_cast<const __half*>(&hi)) : __bfloat162float(hi);
         h1[nn::head_conv_weight_index(0, n, c)] = hi;
-        h1[nn::head_conv_weight_index(1, n, c)] = __float2bfloat16_rn(wf - __bfloat162float(hi));
+        h1[nn::head_conv_weight_index(1, n, c)] = w16(wf - hif, f16);
     }
 }
 // FC weights with K re-ordered from torch's flatten order (ch*64 + cell) to the feature order the 1x1-conv GEMM writes
@@ -174,6 +177,7 @@ struct Net {
     int cin_pad = 16;          // stem input channels after zero padding: 16, or 32 for chess' 18 planes
     int p_tiles = 4;           // policy FC N tiles of 64: ceil(A / 64)
     int p_split = 1;           // policy FC as the three-term hi/lo bf16 split (1) or plain bf16 (0: heads wider than 1024 actions)
+    int f16 = 1;               // 16-bit storage type of activations and conv weights: 1 = fp16 (default), 0 = bf16 (az_config.net_precision)
     int NS = 1;                // channel slices of 128: a C-channel layer runs as NS x NS launches of the 128 -> 128 kernel
     int wi(int l, int co, int ci) const { return l == 0 ? co : NS + (l - 1) * NS * NS + co * NS + ci; }   // weight image index
     int bi(int l, int co) const { return l * NS + co; }
@@ -288,9 +292,9 @@ struct Net {
             for (int co = 0; co < NS; ++co)
                 for (int ci = 0; ci < (l == 0 ? 1 : NS); ++ci)
                     k_prep_conv<<<(n + 255) / 256, 256, 0, st>>>(d + cw[l], d + cbn[l], w.conv_w[wi(l, co, ci)], ci == 0 ? w.conv_b[bi(l, co)] : nullptr, C, cin_total,
-                                                                 co * nn::CONV_COUT, ci * nn::CONV_COUT, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0);
+                                                                 co * nn::CONV_COUT, ci * nn::CONV_COUT, cin_real, cin, nn::conv_uses_pair(cin, row_pitch) ? 1 : 0, f16);
         }
-        k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C, w.h1_w);
+        k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C, w.h1_w, f16);
         k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat, p_split);
         k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat, 1);
         AZ_CUDA_CHECK(cudaGetLastError());
@@ -304,7 +308,7 @@ struct Net {
         loaded = true;
         return 0;
     }
-    void share(const Net& o) { w = o.w; blocks = o.blocks; in_planes = o.in_planes; loaded = o.loaded; owns_weights = false; }
+    void share(const Net& o) { f16 = o.f16; w = o.w; blocks = o.blocks; in_planes = o.in_planes; loaded = o.loaded; owns_weights = false; }
     void free_weights() {
         if (!owns_weights) { w = NetWeights(); loaded = false; return; }
         for (auto p : w.conv_w) cudaFree(p);
@@ -333,7 +337,7 @@ struct Net {
         const int cs_sms = conv_stream ? n_sms_conv : n_sms;
         nn::ConvParams cp{};
         cp.rowvalid = rowvalid; cp.n_boards_dev = n_dev; cp.n_rows = n_fixed * board_pitch; cp.board_pitch = board_pitch;
-        cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1; cp.dbg = conv_dbg;
+        cp.p_total = p_total; cp.row_pitch = row_pitch; cp.relu = 1; cp.dbg = conv_dbg; cp.f16 = f16;
         const size_t slice = (size_t)(nn::CONV_COUT / 8) * p_total * 8;          // elements per 128-channel slice of an activation buffer
         for (int co = 0; co < NS; ++co) {                                         // stem: one launch per 128 output channels
             cp.in = in16; cp.out = X + co * slice; cp.resid = nullptr; cp.w = w.conv_w[wi(0, co, 0)]; cp.bias = w.conv_b[bi(0, co)];
@@ -361,7 +365,7 @@ struct Net {
         if (trunk_fused && NS == 1 && nn::trunk_fused_supported(C, board_pitch, row_pitch, 2 * blocks)) {
             nn::TrunkParams tp{};
             tp.X = X; tp.Y = Y; tp.rowvalid = rowvalid; tp.n_boards_dev = n_dev; tp.n_rows = n_fixed * board_pitch;
-            tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch; tp.board_pitch = board_pitch; tp.group_boards = nn::trunk_group_boards(board_pitch);
+            tp.f16 = f16; tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch; tp.board_pitch = board_pitch; tp.group_boards = nn::trunk_group_boards(board_pitch);
             // small batches (Go 9x9 at 2048 boards, chess at 1024): X + Y fit in L2 as a whole, so one group per CTA pair balances the pairs better
             // than groups of 7 work items (2048 Go boards = 120 such groups on 74 pairs)
             if (board_pitch != 256 && (size_t)2 * max_boards * board_pitch * 256 <= ((size_t)110 << 20)) tp.group_boards = std::max(1, (max_boards + cs_sms / 2 - 1) / (cs_sms / 2));
@@ -386,11 +390,11 @@ struct Net {
         static const bool fuse_heads = getenv("AZ_NO_HEAD_FUSION") == nullptr;      // profiling / parity switch: the two-kernel path
         if (fuse_heads && nn::head_conv_supported(C, board_pitch, H, W)) {
             // 1x1 convs on the full-resolution trunk output, pooling in the epilogue (head_conv.cu): one pass over X, no pooled intermediate
-            nn::HeadConvParams hp{X, w.h1_w, w.b1x1, n_dev, n_fixed, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, featP, featV, boards_cap, 256, alt_order ? 1 : 0};
+            nn::HeadConvParams hp{X, w.h1_w, w.b1x1, n_dev, n_fixed, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, featP, featV, boards_cap, 256, f16, alt_order ? 1 : 0};
             AZ_CHECK(nn::head_conv_launch(hp, n_sms, s) == 0, "fused heads launch failed"); ++launches;
             fe_rec(2, s); fe_rec(3, s);
         } else {
-            nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap};
+            nn::PoolParams pp{X, pooled, n_dev, n_fixed, C, H, W, row_pitch, board_pitch, p_total, nn::CONV_GUARD, boards_cap, 64 * boards_cap, f16};
             AZ_CHECK(nn::pool_launch(pp, n_sms * 8, s) == 0, "pool launch failed"); ++launches;
             fe_rec(2, s);
             nn::GemmParams g1{}; g1.A = pooled; g1.B = w.g1_w; g1.bias = w.b1x1; g1.a_rows = 64 * boards_cap; g1.a_plane_mod = 2 * (C / 8); g1.K = 3 * C; g1.n_tiles = 1; g1.n_valid = 64;
@@ -442,24 +446,29 @@ __global__ void __launch_bounds__(128) k_rules_replay(const int32_t* moves, cons
 }
 
 // createGameState + fresh ParallelMCTS for every slot (self_play_manager.cpp:157-175)
+__global__ void k_fill_i32(int32_t* p, int32_t v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
 template <class G>
 __global__ void __launch_bounds__(128) k_reset_all(TreePools tp, typename G::State* root_state, const int16_t* default_order, int n_order, int16_t* root_order,
-                                                  int32_t* root_order_n, int noise, int T) {
+                                                  int32_t* root_order_n, int noise, int T, EvalTT tt, long long pool_nodes) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
     typename G::Warp& w = warp_ws<G>(smem);
-    const size_t base = (size_t)t * tp.cap;
+    const long long per = pool_nodes / T;               // fresh trees: equal regions
+    const size_t base = (size_t)((long long)t * per);
     G::w_init(w, lane);
     G::w_store_root(w, root_state + t, lane);
     if (lane == 0) {
-        tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
+        tp.base[t] = (long long)t * per; tp.limit[t] = (int32_t)per;
+        tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.sub[base] = 0; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
         tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] = 0;
         tp.tflags[t] = (uint8_t)(TF_ACTIVE | (G::FIRST_FILL ? TF_FIRST_FILL : 0) | (noise ? TF_NEED_NOISE : 0));
         root_order_n[t] = n_order;
     }
     for (int i = lane; i < n_order; i += 32) root_order[(size_t)t * G::MAX_CHILDREN + i] = default_order[i];
+    if (tt.keys) { for (int i = lane; i < tt.cap; i += 32) tt.keys[(size_t)t * tt.cap + i] = 0; if (lane == 0) tt.count[t] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------ engine
@@ -502,16 +511,21 @@ struct EngineT : EngineBase {
     // Slots are split into `NG` stream groups; each group runs its own wave sequence (select → network → expand) on
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
-    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; Net net; };
+    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; Net net; };
+    EvalTT tt{};                                  // model of the reference's TranspositionTable (chess + hash evaluators, tree.cuh)
+    bool hash_eval() const { return cfg.evaluator == AZ_EVAL_HASH || cfg.evaluator == AZ_EVAL_HASH_PEAKED; }
     az_config cfg;
     int T = 0, NG = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_main = nullptr;
     std::vector<Group> groups;
     SmPartitions parts; bool partitioned = false;
-    TreePools tp{};
-    ScratchPools sc{};
-    int scratch_trees = 0;
+    TreePools tp{};                               // current pool buffer + per-tree arrays
+    TreePools alt{};                              // the other pool buffer (node arrays, base, limit); per-tree arrays shared with tp
+    long long pool_nodes = 0;                     // nodes per pool buffer
+    int32_t* kept = nullptr; RegionPlan* plan = nullptr;
+    int budget_sims = 0, sims_since_plan = 0;     // simulations every region is provisioned for / run since the regions were cut
+    unsigned long long overflows_seen = 0;
     State* root_state = nullptr; Leaf* leaf_state = nullptr;
     int16_t *root_order = nullptr, *default_order = nullptr; int32_t* root_order_n = nullptr;
     int32_t *chosen_child = nullptr, *chosen_action = nullptr, *forced = nullptr;
@@ -532,7 +546,7 @@ struct EngineT : EngineBase {
         }
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
-                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval}) cudaFree(p);
+                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key}) cudaFree(p);
             g.net.destroy();
             if (g.ev) cudaEventDestroy(g.ev);
             if (g.stream) cudaStreamDestroy(g.stream);
@@ -540,11 +554,13 @@ struct EngineT : EngineBase {
         groups.clear();
         parts.destroy(); partitioned = false;
         if (ev_main) { cudaEventDestroy(ev_main); ev_main = nullptr; }
-        for (void* p : {(void*)tp.N, (void*)tp.W, (void*)tp.P, (void*)tp.first, (void*)tp.act, (void*)tp.nchild, (void*)tp.flags, (void*)tp.root,
-                        (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id,
-                        (void*)sc.N, (void*)sc.W, (void*)sc.P, (void*)sc.first, (void*)sc.act, (void*)sc.nchild, (void*)sc.flags, (void*)sc.old_id,
+        for (void* p : {(void*)tp.N, (void*)tp.W, (void*)tp.P, (void*)tp.first, (void*)tp.sub, (void*)tp.act, (void*)tp.nchild, (void*)tp.flags, (void*)tp.base, (void*)tp.limit,
+                        (void*)tp.root, (void*)tp.alloc, (void*)tp.root_vl, (void*)tp.tflags, (void*)tp.move_num, (void*)tp.game_id,
+                        (void*)alt.N, (void*)alt.W, (void*)alt.P, (void*)alt.first, (void*)alt.sub, (void*)alt.act, (void*)alt.nchild, (void*)alt.flags, (void*)alt.base, (void*)alt.limit,
+                        (void*)kept, (void*)plan,
                         (void*)root_state, (void*)leaf_state, (void*)root_order, (void*)default_order, (void*)root_order_n, (void*)chosen_child,
-                        (void*)chosen_action, (void*)forced, (void*)game_buf, (void*)ring, (void*)ring_count, (void*)noise_scratch, (void*)dstats})
+                        (void*)chosen_action, (void*)forced, (void*)game_buf, (void*)ring, (void*)ring_count, (void*)noise_scratch, (void*)dstats,
+                        (void*)tt.keys, (void*)tt.vals, (void*)tt.count})
             cudaFree(p);
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
@@ -555,18 +571,25 @@ struct EngineT : EngineBase {
         cudaDeviceProp prop; AZ_CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
         AZ_CHECK(prop.major >= 10, "az_b200 needs an sm_100-class GPU (no fallback path exists)");
         AZ_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        int cap = c.max_nodes_per_tree;
-        if (cap <= 0) cap = 2 * (std::max(c.num_simulations, 1) + 1) * MC + 1;
-        tp.cap = cap;
-        const size_t tn = (size_t)T * cap;
-        if (dev_alloc(&tp.N, tn) || dev_alloc(&tp.W, tn) || dev_alloc(&tp.P, tn) || dev_alloc(&tp.first, tn) || dev_alloc(&tp.act, tn) ||
-            dev_alloc(&tp.nchild, tn) || dev_alloc(&tp.flags, tn) || dev_alloc(&tp.root, T) || dev_alloc(&tp.alloc, T) || dev_alloc(&tp.root_vl, T) ||
-            dev_alloc(&tp.tflags, T) || dev_alloc(&tp.move_num, T) || dev_alloc(&tp.game_id, T)) return -1;
-        // scratch for re-rooting: as many trees at a time as fit in ~1/8 of the pool memory (at least 1)
-        scratch_trees = std::max(1, std::min(T, (int)(((size_t)4 << 30) / ((size_t)cap * 25))));
-        const size_t sn = (size_t)scratch_trees * cap;
-        if (dev_alloc(&sc.N, sn) || dev_alloc(&sc.W, sn) || dev_alloc(&sc.P, sn) || dev_alloc(&sc.first, sn) || dev_alloc(&sc.act, sn) ||
-            dev_alloc(&sc.nchild, sn) || dev_alloc(&sc.flags, sn) || dev_alloc(&sc.old_id, sn)) return -1;
+        // Node pool (tree.cuh): two buffers of pool_nodes nodes (25 bytes each) shared by all trees.  max_nodes_per_tree is the AVERAGE per
+        // tree; default: what fits in ~55 % of the free device memory, between 1.25 x and 4 x one search's worst-case growth.
+        budget_sims = std::max(c.num_simulations, 1);
+        const long long growth = (long long)(budget_sims + 1) * MC + 1;
+        long long per_tree = c.max_nodes_per_tree;
+        if (per_tree <= 0) {
+            size_t free_b = 0, total_b = 0; AZ_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            per_tree = (long long)(0.55 * (double)free_b / (50.0 * T));
+            per_tree = std::max(growth * 5 / 4, std::min(growth * 4, per_tree));
+        }
+        AZ_CHECK(per_tree >= MC + 1, "max_nodes_per_tree must hold at least one expansion");
+        pool_nodes = per_tree * T;
+        const size_t tn = (size_t)pool_nodes;
+        for (TreePools* b : {&tp, &alt})
+            if (dev_alloc(&b->N, tn) || dev_alloc(&b->W, tn) || dev_alloc(&b->P, tn) || dev_alloc(&b->first, tn) || dev_alloc(&b->sub, tn) || dev_alloc(&b->act, tn) ||
+                dev_alloc(&b->nchild, tn) || dev_alloc(&b->flags, tn) || dev_alloc(&b->base, T) || dev_alloc(&b->limit, T)) return -1;
+        if (dev_alloc(&tp.root, T) || dev_alloc(&tp.alloc, T) || dev_alloc(&tp.root_vl, T) ||
+            dev_alloc(&tp.tflags, T) || dev_alloc(&tp.move_num, T) || dev_alloc(&tp.game_id, T) || dev_alloc(&kept, T) || dev_alloc(&plan, 1)) return -1;
+        alt.root = tp.root; alt.alloc = tp.alloc; alt.root_vl = tp.root_vl; alt.tflags = tp.tflags; alt.move_num = tp.move_num; alt.game_id = tp.game_id;
         if (dev_alloc(&root_state, T) || dev_alloc(&leaf_state, T) || dev_alloc(&root_order, (size_t)T * MC) || dev_alloc(&default_order, MC) ||
             dev_alloc(&root_order_n, T) || dev_alloc(&chosen_child, T) || dev_alloc(&chosen_action, T) || dev_alloc(&forced, T)) return -1;
         max_moves = G::MAX_GAME_MOVES;
@@ -582,6 +605,13 @@ struct EngineT : EngineBase {
             std::unordered_set<int> us; for (int a = 0; a < G::CELLS; ++a) us.insert(a);
             h_default_order.assign(us.begin(), us.end());
             AZ_CUDA_CHECK(cudaMemcpy(default_order, h_default_order.data(), h_default_order.size() * 2, cudaMemcpyHostToDevice));
+        }
+        if (G::TT_COARSE && hash_eval() && c.tt_entries >= 0) {
+            // per game: one entry per evaluation; sized for 64 moves' worth of simulations unless the caller says otherwise (inserts stop at half load)
+            long want = c.tt_entries > 0 ? (long)c.tt_entries : 2L * 64 * (std::max(c.num_simulations, 1) + 1);
+            int capn = 1024; while (capn < want && capn < (1 << 22)) capn <<= 1;
+            tt.cap = capn;
+            if (dev_alloc(&tt.keys, (size_t)T * capn) || dev_alloc(&tt.vals, (size_t)T * capn) || dev_alloc(&tt.count, T)) return -1;
         }
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
@@ -603,12 +633,13 @@ struct EngineT : EngineBase {
             if (dev_alloc(&g.wb.path, (size_t)n * MAX_DEPTH) || dev_alloc(&g.wb.path_len, n) || dev_alloc(&g.wb.leaf_node, n) || dev_alloc(&g.wb.leaf_kind, n) ||
                 dev_alloc(&g.wb.leaf_value, n) || dev_alloc(&g.wb.policy, (size_t)n * A) || dev_alloc(&g.wb.value, n) || dev_alloc(&g.wb.eval_slot, n) ||
                 dev_alloc(&g.wb.n_eval, 1)) return -1;
-            // view of the pools for this group's slots
-            g.tp = tp;
-            const size_t off = (size_t)g.t0 * cap;
-            g.tp.N += off; g.tp.W += off; g.tp.P += off; g.tp.first += off; g.tp.act += off; g.tp.nchild += off; g.tp.flags += off;
-            g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
+            if (tt.keys) {
+                if (dev_alloc(&g.wb.eval_key, n)) return -1;
+                g.tt = tt; g.tt.keys += (size_t)g.t0 * tt.cap; g.tt.vals += (size_t)g.t0 * tt.cap; g.tt.count += g.t0;
+            }
+            refresh_group_view(g);
             if (c.evaluator == AZ_EVAL_RESNET) {
+                g.net.f16 = c.net_precision == AZ_NET_BF16 ? 0 : 1;
                 if (g.net.init(G::N, G::N, A, per, c.net_channels, G::PLANES)) return -1;
                 if (partitioned) {
                     if (parts.stream(true, &g.net.conv_stream)) return -1;
@@ -621,6 +652,12 @@ struct EngineT : EngineBase {
         return reset_games();
     }
 
+    // view of the pools for a group's slots: per-tree arrays start at the group's first slot (node arrays are addressed through base[])
+    void refresh_group_view(Group& g) {
+        g.tp = tp;
+        g.tp.base += g.t0; g.tp.limit += g.t0;
+        g.tp.root += g.t0; g.tp.alloc += g.t0; g.tp.root_vl += g.t0; g.tp.tflags += g.t0; g.tp.move_num += g.t0; g.tp.game_id += g.t0;
+    }
     SearchParams sparams() const { return SearchParams{cfg.c_puct, cfg.virtual_loss, MAX_DEPTH}; }
     int blocks_for_warps(int n) const { return (n * 32 + 127) / 128; }
 
@@ -650,7 +687,9 @@ struct EngineT : EngineBase {
     }
 
     int write_fresh(int slot, const State& s, const int16_t* order, int n_order, bool first_fill) {
-        const size_t base = (size_t)slot * tp.cap;
+        if (sync_all()) return -1;
+        long long base_ll = 0; AZ_CUDA_CHECK(cudaMemcpy(&base_ll, tp.base + slot, 8, cudaMemcpyDeviceToHost));
+        const size_t base = (size_t)base_ll;
         const int res = G::host_root_result(s);
         int32_t zero = 0, one = 1, m1 = -1; float fz = 0.0f; int16_t a16 = -1, z16 = 0;
         uint8_t nf = res != RES_ONGOING ? (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)) : 0;
@@ -660,6 +699,7 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.W + base, &fz, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.P + base, &fz, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.first + base, &m1, 4, cudaMemcpyHostToDevice, stream));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(tp.sub + base, &zero, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.act + base, &a16, 2, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.nchild + base, &z16, 2, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.flags + base, &nf, 1, cudaMemcpyHostToDevice, stream));
@@ -670,6 +710,10 @@ struct EngineT : EngineBase {
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.move_num + slot, &zero, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(tp.game_id + slot, &gid, 4, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_state + slot, &s, sizeof(State), cudaMemcpyHostToDevice, stream));
+        if (tt.keys) {      // ParallelMCTS ctor: a table of its own
+            AZ_CUDA_CHECK(cudaMemsetAsync(tt.keys + (size_t)slot * tt.cap, 0, (size_t)tt.cap * 8, stream));
+            AZ_CUDA_CHECK(cudaMemsetAsync(tt.count + slot, 0, 4, stream));
+        }
         if (order && n_order > 0) AZ_CUDA_CHECK(cudaMemcpyAsync(root_order + (size_t)slot * MC, order, (size_t)n_order * 2, cudaMemcpyHostToDevice, stream));
         AZ_CUDA_CHECK(cudaMemcpyAsync(root_order_n + slot, &n_order, 4, cudaMemcpyHostToDevice, stream));
         if (sync_all()) return -1;   // host temporaries above go out of scope
@@ -678,8 +722,9 @@ struct EngineT : EngineBase {
 
     int reset_games() override {
         k_reset_all<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, default_order, G::FIRST_FILL ? G::CELLS : 0, root_order, root_order_n,
-                                                                                 cfg.deterministic ? 0 : 1, T);
+                                                                                 cfg.deterministic ? 0 : 1, T, tt, pool_nodes);
         AZ_LAUNCH_CHECK(); ++launches;
+        sims_since_plan = 0; budget_sims = (int)std::min<long long>(std::max(cfg.num_simulations, 1), (pool_nodes / T - 1) / MC - 1);
         AZ_CUDA_CHECK(cudaMemsetAsync(ring_count, 0, 4, stream));
         if (sync_all()) return -1;
         return 0;
@@ -718,13 +763,14 @@ struct EngineT : EngineBase {
         const bool timed = wave_timing && (wt_seen++ % 64) == 63;
         if (timed) { for (auto& e : wt_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(wt_ev[0], st); }
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
-        typename G::EncTarget enc{nullptr, 0, 0, 0};
-        if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch};
-        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.n, mode);
+        typename G::EncTarget enc{nullptr, 0, 0, 0, 0};
+        if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch, g.net.f16};
+        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) cudaEventRecord(wt_ev[1], st);
-        if (cfg.evaluator == AZ_EVAL_HASH) {
-            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n);
+        if (hash_eval()) {
+            k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n,
+                                                                                                                              cfg.evaluator == AZ_EVAL_HASH_PEAKED ? 1 : 0);
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             g.net.fe_on = timed;
@@ -749,6 +795,9 @@ struct EngineT : EngineBase {
 
     int search(int sims) override {
         if (sims <= 0) sims = cfg.num_simulations;
+        // every region is provisioned for budget_sims more simulations since it was last cut: re-cut (in place, no move) before running past that
+        if (sims_since_plan + sims > budget_sims && recut_regions(nullptr, std::max(sims, cfg.num_simulations))) return -1;
+        sims_since_plan += sims;
         if (fork_groups()) return -1;
         for (auto& g : groups) {
             if (wave(g, 1)) return -1;                  // search() preamble: expand unexpanded roots
@@ -761,20 +810,52 @@ struct EngineT : EngineBase {
         for (int i = 0; i < sims; ++i)
             for (auto& g : groups) if (wave(g, 0)) return -1;
         waves += sims + 1;
-        return join_groups();
+        if (join_groups()) return -1;
+        if (cfg.deterministic) return check_overflow();          // parity mode: a failed expansion is an error, not a statistic
+        return 0;
+    }
+    // a failed expansion (node pool exhausted) changes the search: report it as an error
+    int check_overflow() {
+        if (sync_all()) return -1;
+        Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
+        if (s.pool_overflows > overflows_seen) {
+            const unsigned long long n = s.pool_overflows - overflows_seen; overflows_seen = s.pool_overflows;
+            set_error("node pool exhausted: " + std::to_string(n) + " expansion(s) failed — raise az_config.max_nodes_per_tree (average nodes per tree; now " +
+                      std::to_string(pool_nodes / T) + ")");
+            return -4;
+        }
+        return 0;
+    }
+    // k_region_need / k_region_plan / k_reroot_copy (tree_kernels.cuh) with the per-slot chosen children in `cc_dev` (nullptr: no slot moves), then swap the buffers
+    int recut_regions(const int32_t* cc_dev, int sims_budget) {
+        if (!cc_dev) {
+            k_fill_i32<<<(T + 255) / 256, 256, 0, stream>>>(chosen_child, -2, T);
+            AZ_LAUNCH_CHECK(); ++launches;
+            cc_dev = chosen_child;
+        }
+        const int budget = (sims_budget + 1) * MC;
+        k_region_need<<<(T + 255) / 256, 256, 0, stream>>>(tp, cc_dev, kept, T);
+        AZ_LAUNCH_CHECK(); ++launches;
+        k_region_plan<<<1, 1024, 0, stream>>>(kept, alt.base, alt.limit, T, budget, pool_nodes, plan);
+        AZ_LAUNCH_CHECK(); ++launches;
+        k_reroot_copy<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, alt, root_state, cc_dev, T, dstats);
+        AZ_LAUNCH_CHECK(); ++launches;
+        for (auto f : {&TreePools::N, &TreePools::first, &TreePools::sub}) std::swap(tp.*f, alt.*f);
+        std::swap(tp.W, alt.W); std::swap(tp.P, alt.P); std::swap(tp.act, alt.act); std::swap(tp.nchild, alt.nchild); std::swap(tp.flags, alt.flags);
+        std::swap(tp.base, alt.base); std::swap(tp.limit, alt.limit);
+        for (auto& g : groups) refresh_group_view(g);
+        // the plan guarantees min(budget, slack share) growth per tree; budget_sims = what that covers
+        budget_sims = sims_budget; sims_since_plan = 0;
+        return 0;
     }
 
     int commit_moves(const int32_t* forced_dev) {
         MoveParams mp{cfg.deterministic, cfg.init_temperature, cfg.final_temperature, cfg.temperature_drop_move, cfg.seed};
         k_choose_move<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, mp, game_buf, max_moves, forced_dev, chosen_child, chosen_action, T, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
-        for (int t0 = 0; t0 < T; t0 += scratch_trees) {
-            const int cnt = std::min(scratch_trees, T - t0);
-            k_reroot<G><<<blocks_for_warps(cnt), 128, warp_ws_bytes<G>(), stream>>>(tp, sc, root_state, chosen_child, t0, cnt, T);
-            AZ_LAUNCH_CHECK(); ++launches;
-        }
+        if (recut_regions(chosen_child, cfg.num_simulations)) return -1;
         k_finish_games<G><<<blocks_for_warps(T), 128, warp_ws_bytes<G>(), stream>>>(tp, root_state, game_buf, max_moves, ring, ring_cap, ring_count, default_order, G::FIRST_FILL ? G::CELLS : 0,
-                                                                   root_order, root_order_n, cfg.auto_restart, cfg.deterministic ? 0 : 1, T, dstats);
+                                                                   root_order, root_order_n, cfg.auto_restart, cfg.deterministic ? 0 : 1, T, dstats, tt);
         AZ_LAUNCH_CHECK(); ++launches;
         return 0;
     }
@@ -827,7 +908,8 @@ struct EngineT : EngineBase {
     int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
         if (sync_all()) return -1;
-        const size_t base = (size_t)slot * tp.cap;
+        long long base_ll = 0; AZ_CUDA_CHECK(cudaMemcpy(&base_ll, tp.base + slot, 8, cudaMemcpyDeviceToHost));
+        const size_t base = (size_t)base_ll;
         int32_t root; AZ_CUDA_CHECK(cudaMemcpy(&root, tp.root + slot, 4, cudaMemcpyDeviceToHost));
         int32_t f; int16_t nc;
         AZ_CUDA_CHECK(cudaMemcpy(&f, tp.first + base + root, 4, cudaMemcpyDeviceToHost));
@@ -963,7 +1045,7 @@ struct EngineT : EngineBase {
         for (int o = 0; o < n; o += cap) {               // group 0's buffers, `cap` boards at a time
             const int c = std::min(cap, n - o);
             AZ_CUDA_CHECK(cudaMemcpyAsync(dpl, planes + (size_t)o * net.in_planes * G::CELLS, (size_t)c * net.in_planes * G::CELLS * 4, cudaMemcpyHostToDevice, g.stream));
-            AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, net.cin_pad, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, g.stream) == 0, "pack launch failed");
+            AZ_CHECK(nn::pack_planes_launch(dpl, net.in16, c, net.in_planes, net.cin_pad, G::N, G::N, net.row_pitch, net.board_pitch, net.p_total, nn::CONV_GUARD, net.f16, g.stream) == 0, "pack launch failed");
             ++launches;
             if (net.forward(nullptr, c, g.wb.policy, g.wb.value, g.stream)) { cudaFree(dpl); return -1; }
             AZ_CUDA_CHECK(cudaMemcpyAsync(policy + (size_t)o * A, g.wb.policy, (size_t)c * A * 4, cudaMemcpyDeviceToHost, g.stream));
@@ -1006,7 +1088,7 @@ struct EngineT : EngineBase {
         AZ_CHECK(n_boards >= 1 && n_boards <= net.max_boards, "n_boards must be in [1, slots per stream group]");
         nn::ConvParams cp{};
         cp.rowvalid = net.rowvalid; cp.n_boards_dev = nullptr; cp.n_rows = n_boards * net.board_pitch; cp.board_pitch = net.board_pitch;
-        cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1;
+        cp.p_total = net.p_total; cp.row_pitch = net.row_pitch; cp.relu = 1; cp.f16 = net.f16;
         cp.in = net.X; cp.out = net.Y; cp.resid = nullptr; cp.w = net.w.conv_w[net.wi(1, 0, 0)]; cp.bias = net.w.conv_b[net.bi(1, 0)];
         if (const char* d = getenv("AZ_CONV_DBG")) cp.dbg = atoi(d);      // profiling experiments (conv_trunk.cu)
         if (getenv("AZ_CONV_RESID")) cp.resid = net.X;                    // time the residual variant (second conv of a block)
@@ -1095,7 +1177,7 @@ AZ_API void az_config_default(az_config* c) {
     c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
     c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
     c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
-    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1; c->net_precision = AZ_NET_FP16; c->tt_entries = 0;
 }
 
 AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }

@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(256) k_pool(PoolParams p) {
             for (int y = y0; y < y1; ++y)
                 for (int x = x0; x < x1; ++x) {
                     const uint4 u = brow[y * p.row_pitch + x];
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    const uint32_t* h = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
+                    for (int e = 0; e < 4; ++e) { const float2 f = p.f16 ? unpack2_16<true>(h[e]) : unpack2_16<false>(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
                 }
             const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
             uint4 ov, ol;

@@ -37,6 +37,7 @@ struct PoolParams {
     __nv_bfloat16* pooled;      // [2*C/8][pooled_rows][8] (hi planes then lo planes), row = cell*boards_cap + board
     const int* n_boards_dev; int n_boards;
     int channels, H, W, row_pitch, board_pitch, p_total, guard, boards_cap, pooled_rows;
+    int f16;                    // 1: the trunk output is fp16 (else bf16); the pooled hi / lo planes are bf16 either way
 };
 
 inline size_t gemm_weight_elems(int n_total, int k_total) { return (size_t)((n_total + 63) / 64) * 64 * k_total; }

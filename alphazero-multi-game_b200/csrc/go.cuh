@@ -29,6 +29,7 @@ struct Go {
     static constexpr int MAX_CHILDREN = CELLS + 1;     // pass + every cell
     static constexpr int SAMPLE_VISITS = CELLS + 1;    // visit counts by action, pass last
     static constexpr int PLANES = 8;
+    static constexpr bool TT_COARSE = false;          // the reference's TT key (stones + player + ko) covers the hash evaluator's input
     static constexpr bool FIRST_FILL = false;          // legal-move order is the same for every enumeration (QUIRK Go2)
     static constexpr int MAX_GAME_MOVES = 2 * CELLS;   // engine cap (the reference has none): the game is scored at this ply
     static constexpr int MAXH = MAX_GAME_MOVES + 2;    // superko keys of the root lineage
@@ -305,7 +306,7 @@ struct Go {
 #if defined(__CUDACC__)
     // ---------------------------------------------------------------------------------------------- warp API (tree_kernels.cuh)
     struct Warp { Leaf s; const uint64_t* hist; uint64_t* hist_rw; uint8_t libs[(CELLS + 15) / 16 * 16]; };
-    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch; };
+    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch, f16; };
 
     __device__ static void copy_words(void* dst, const void* src, int bytes, int lane) {
         const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
@@ -416,7 +417,7 @@ struct Go {
             const int libs = w.libs[y * N + x];
             __align__(16) __nv_bfloat16 v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(c < PLANES ? feature(w.s.c, c, x, y, libs) : 0.0f);
+            for (int c = 0; c < 16; ++c) v[c] = net16(c < PLANES ? feature(w.s.c, c, x, y, libs) : 0.0f, enc.f16 != 0);
             *reinterpret_cast<uint4*>(enc.ptr + ((size_t)0 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[0]);
             *reinterpret_cast<uint4*>(enc.ptr + ((size_t)1 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[8]);
         }

@@ -26,6 +26,7 @@ struct Gomoku {
     static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
     static constexpr int MAX_CHILDREN = CELLS;
     static constexpr int SAMPLE_VISITS = CELLS;
+    static constexpr bool TT_COARSE = false;          // the reference's TT key (stones + player) covers the hash evaluator's input
     static constexpr bool FIRST_FILL = true;       // QUIRK G2: the first enumeration of a lineage has its own order
     static constexpr int MAX_GAME_MOVES = CELLS;
 
@@ -189,7 +190,7 @@ struct Gomoku {
     // Warp API used by the tree kernels (tree_kernels.cuh): the game state of the tree a warp owns lives in that
     // warp's shared-memory workspace; mutating calls are made by the whole warp (lane 0 writes, __syncwarp after).
     struct Warp { State s; };
-    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch; };
+    struct EncTarget { __nv_bfloat16* ptr; int p_total, guard, board_pitch, f16; };
 
     __device__ static void w_load(Warp& w, const State* g, int lane) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
@@ -265,7 +266,7 @@ struct Gomoku {
             if (y >= N) continue;                             // hole column stays zero
             __align__(16) __nv_bfloat16 v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(c < PLANES ? feature(w.s, c, x, y) : 0.0f);
+            for (int c = 0; c < 16; ++c) v[c] = net16(c < PLANES ? feature(w.s, c, x, y) : 0.0f, enc.f16 != 0);
             *reinterpret_cast<uint4*>(enc.ptr + ((size_t)0 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[0]);
             *reinterpret_cast<uint4*>(enc.ptr + ((size_t)1 * enc.p_total + row0 + p) * 8) = *reinterpret_cast<const uint4*>(&v[8]);
         }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_head_conv_pool(const HeadConv
         __syncwarp();
     } else if (warp == 9) {
         // ===================== MMA issuer (converged warp, tcgen05 under elect.sync) =====================
-        constexpr uint32_t IDESC = idesc_bf16(128, 64);
+        const uint32_t IDESC = idesc_16(128, 64, p.f16 != 0);
         const uint64_t a_desc0 = smem_desc(smem_u32(sA), HC_PLANE, 128);
         const uint64_t b_desc0 = smem_desc(smem_u32(sW), HC_WPLANE, 128);
         mbar_wait(w_full, 0);

@@ -15,6 +15,7 @@ struct HeadConvParams {
     int H, W, row_pitch, board_pitch, p_total, guard;
     // features in the FC layers' A layout (gemm_tc.cuh GEMM_OUT_FEAT): plane = cell*4 + ch/8, row = board; lo half at plane feat_lo_plane + ...
     __nv_bfloat16* featP; __nv_bfloat16* featV; int feat_rows; int feat_lo_plane;
+    int f16;                    // 1: the trunk output and the hi / lo weight image are fp16 (else bf16); the pooled features stay bf16 hi / lo
     int reverse;                // walk the boards from the last to the first: the trunk's last layer wrote them first to last, so the last ones are still in L2
 };
 

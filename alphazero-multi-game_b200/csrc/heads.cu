@@ -4,6 +4,7 @@
 // src/nn/torch_neural_network.cpp:298-316), value = tanh(FC 256→1), plus the fp32-planes → bf16 input packer used by
 // az_engine_nn_forward.
 #include "heads.cuh"
+#include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
 namespace az { namespace nn {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams
 }
 
 // fp32 NCHW planes (host-supplied, az_engine_nn_forward) → the trunk's bf16 input layout
-__global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard) {
+__global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard, int f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int cells = H * W;
     if (idx >= n * cells) return;
@@ -123,7 +124,9 @@ __global__ void k_pack_planes(const float* planes, __nv_bfloat16* in, int n, int
     const size_t row = (size_t)guard + (size_t)b * board_pitch + y * row_pitch + x;
     for (int c = 0; c < cin_pad; ++c) {
         const float v = c < Cp ? planes[((size_t)b * Cp + c) * cells + cell] : 0.0f;
-        in[((size_t)(c >> 3) * p_total + row) * 8 + (c & 7)] = __float2bfloat16_rn(v);
+        __nv_bfloat16 o = __float2bfloat16_rn(v);
+        if (f16) { const __half h = __float2half_rn(v); o = *reinterpret_cast<const __nv_bfloat16*>(&h); }
+        in[((size_t)(c >> 3) * p_total + row) * 8 + (c & 7)] = o;
     }
 }
 
@@ -138,9 +141,9 @@ int policy_value_launch(const OutParams& p, int max_boards, cudaStream_t s) {
     k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
-int pack_planes_launch(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard, cudaStream_t s) {
+int pack_planes_launch(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch, int board_pitch, int p_total, int guard, int f16, cudaStream_t s) {
     const int total = n * H * W;
-    k_pack_planes<<<(total + 255) / 256, 256, 0, s>>>(planes, in, n, Cp, cin_pad, H, W, row_pitch, board_pitch, p_total, guard);
+    k_pack_planes<<<(total + 255) / 256, 256, 0, s>>>(planes, in, n, Cp, cin_pad, H, W, row_pitch, board_pitch, p_total, guard, f16);
     return (int)cudaGetLastError();
 }
 

@@ -21,6 +21,6 @@ struct OutParams {
 
 int policy_value_launch(const OutParams& p, int max_boards, cudaStream_t s);
 int pack_planes_launch(const float* planes, __nv_bfloat16* in, int n, int Cp, int cin_pad, int H, int W, int row_pitch,
-                       int board_pitch, int p_total, int guard, cudaStream_t s);
+                       int board_pitch, int p_total, int guard, int f16, cudaStream_t s);
 
 }}  // namespace az::nn

@@ -12,6 +12,28 @@ cudaError_t smem_opt_in(const void* kernel, int bytes);
 
 namespace az { namespace ptx {
 
+// ---- the network's 16-bit storage type: bf16 or fp16 in the same 16-bit container (az_config.net_precision).  Activations and conv
+// weights share the type (the tcgen05 kind::f16 descriptor names one format per operand; both operands are kept the same).
+#if defined(__CUDACC__)
+}}
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+namespace az { namespace ptx {
+constexpr float F16_MAX = 65504.0f;
+template <bool F16> __device__ __forceinline__ uint32_t pack2_16(float x, float y) {
+    if (F16) { const __half2 h = __floats2half2_rn(fminf(fmaxf(x, -F16_MAX), F16_MAX), fminf(fmaxf(y, -F16_MAX), F16_MAX)); return *reinterpret_cast<const uint32_t*>(&h); }   // saturate, never inf
+    const __nv_bfloat162 b = __floats2bfloat162_rn(x, y); return *reinterpret_cast<const uint32_t*>(&b);
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2_16(uint32_t u) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ uint16_t cvt1_16(float x, bool f16) {
+    if (f16) { const __half h = __float2half_rn(fminf(fmaxf(x, -F16_MAX), F16_MAX)); return *reinterpret_cast<const uint16_t*>(&h); }
+    const __nv_bfloat16 b = __float2bfloat16_rn(x); return *reinterpret_cast<const uint16_t*>(&b);
+}
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -188,5 +210,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A = B = fp16 (a_format / b_format fields = 0): same instruction, same rate, 11 significand bits instead of 8
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_16(int M, int N, bool f16) { return f16 ? idesc_f16(M, N) : idesc_bf16(M, N); }
 
 }}  // namespace az::ptx

@@ -33,13 +33,13 @@ constexpr size_t warp_ws_bytes(int extra_bytes_per_warp = 0) { return 4 * ((size
 template <class G>
 __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
                                                typename G::Leaf* __restrict__ leaf_state, WaveBuffers wb,
-                                               SearchParams sp, typename G::EncTarget enc, int T, int mode) {
+                                               SearchParams sp, typename G::EncTarget enc, EvalTT tt, int T, int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
     typename G::Warp& w = warp_ws<G>(smem);
-    const size_t base = (size_t)t * tp.cap;
+    const size_t base = (size_t)tp.base[t];
     const uint8_t tf = tp.tflags[t];
     int8_t kind = LEAF_NONE;
     int node = tp.root[t];
@@ -113,6 +113,27 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
     if (kind == LEAF_EVAL) {
         if (lane == 0) slot = atomicAdd(wb.n_eval, 1);
         slot = warp_bcast(slot, 0);
+        if constexpr (G::TT_COARSE) {
+            // TranspositionTable lookup / store of the reference (parallel_mcts.cpp:153-163 for the root, :316-358 for a leaf): the table
+            // key is the placement; a hit evaluates under the first-seen position's key.  One simulation per tree per wave keeps the
+            // reference's serial lookup-then-store order.
+            if (tt.keys != nullptr && wb.eval_key != nullptr) {
+                const uint64_t own = G::w_key(w, lane);
+                if (lane == 0) {
+                    uint64_t ek = own, pk = G::w_tt_key(w);
+                    if (pk == 0) pk = 1;
+                    const size_t tb = (size_t)t * tt.cap;
+                    const uint32_t mask = (uint32_t)tt.cap - 1;
+                    uint32_t i = (uint32_t)mix64(pk) & mask;
+                    for (int probe = 0; probe < tt.cap; ++probe, i = (i + 1) & mask) {
+                        const uint64_t k = tt.keys[tb + i];
+                        if (k == pk) { ek = tt.vals[tb + i]; break; }
+                        if (k == 0) { if (tt.count[t] < tt.cap / 2) { tt.keys[tb + i] = pk; tt.vals[tb + i] = own; tt.count[t] += 1; } break; }
+                    }
+                    wb.eval_key[t] = ek;
+                }
+            }
+        }
     }
     if (lane == 0) {
         wb.leaf_kind[t] = kind; wb.leaf_node[t] = node; wb.path_len[t] = (mode == 1 || kind == LEAF_NONE) ? 0 : depth;
@@ -130,7 +151,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
 // action order by one lane so it is the reference's fp32 sum bit for bit.
 template <class G>
 __global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __restrict__ leaf_state, const typename G::State* __restrict__ root_state,
-                                                  WaveBuffers wb, int T) {
+                                                  WaveBuffers wb, int T, int peaked) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -142,13 +163,16 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __res
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     const int slot = wb.eval_slot[t];
     G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
-    const uint64_t h = G::w_key(w, lane);
+    const uint64_t h = (G::TT_COARSE && wb.eval_key != nullptr) ? wb.eval_key[t] : G::w_key(w, lane);
+    // AZ_EVAL_HASH_PEAKED: the raw prior of action mix(h ^ 0x5EED) % A is multiplied by 4096 (exact) before the normalisation
+    const int peak = peaked ? (int)(mix64(h ^ 0x5EEDULL) % (uint64_t)A) : -1;
     float sum = 0.0f;
     for (int c0 = 0; c0 < A; c0 += CH) {
         __syncwarp();
         for (int i = lane; i < CH && c0 + i < A; i += 32) {
             const uint64_t r = mix64(h + (uint64_t)(c0 + i) * 0x9E3779B97F4A7C15ULL) >> 40;
             raw[i] = fdiv((float)(r + 1), 16777216.0f);
+            if (c0 + i == peak) raw[i] = fmul(raw[i], 4096.0f);
         }
         __syncwarp();
         if (lane == 0) for (int i = 0; i < CH && c0 + i < A; ++i) sum = fadd(sum, raw[i]);      // ascending action order, one lane
@@ -156,7 +180,9 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __res
     sum = __shfl_sync(0xffffffffu, sum, 0);
     for (int i = lane; i < A; i += 32) {
         const uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
-        wb.policy[(size_t)slot * A + i] = fdiv(fdiv((float)(r + 1), 16777216.0f), sum);
+        float rw = fdiv((float)(r + 1), 16777216.0f);
+        if (i == peak) rw = fmul(rw, 4096.0f);
+        wb.policy[(size_t)slot * A + i] = fdiv(rw, sum);
     }
     if (lane == 0) {
         float v = fdiv((float)(mix64(h ^ 0xABCDEFULL) >> 40), 16777216.0f);
@@ -183,9 +209,10 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     typename G::Warp& w = warp_ws<G>(smem, EXTRA);
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     int16_t* acts = reinterpret_cast<int16_t*>(raw + MC);
-    const size_t base = (size_t)t * tp.cap;
+    const size_t base = (size_t)tp.base[t];
     float v = wb.leaf_value[t];
     const int leaf = wb.leaf_node[t];
+    int n_new = 0;                                      // children created by this simulation: added to every path node's descendant count
 
     if (kind == LEAF_EVAL) {
         const int slot = wb.eval_slot[t];
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         // children = the legal moves in the reference's order, priors = policy[action] (0 for out-of-range actions, i.e.
         // Go's pass at -1), expandNodeWithPolicy parallel_mcts.cpp:690-711
         const int n = G::w_enumerate(w, lane, first_fill ? root_order + (size_t)t * MC : nullptr, first_fill ? root_order_n[t] : 0, acts, raw, pol);
-        if (alloc + n > tp.cap) {
+        if (alloc + n > tp.limit[t]) {
             if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         } else if (n > 0) {
             // policySum accumulated in child order (parallel_mcts.cpp:705-711) — serial on purpose
@@ -208,9 +235,10 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
             const float uniform = fdiv(1.0f, (float)n);
             for (int i = lane; i < n; i += 32) {
                 const size_t c = base + alloc + i;
-                tp.N[c] = 0; tp.W[c] = 0.0f; tp.first[c] = -1; tp.nchild[c] = 0; tp.flags[c] = 0; tp.act[c] = acts[i];
+                tp.N[c] = 0; tp.W[c] = 0.0f; tp.first[c] = -1; tp.sub[c] = 0; tp.nchild[c] = 0; tp.flags[c] = 0; tp.act[c] = acts[i];
                 tp.P[c] = sum > 0.0f ? fdiv(raw[i], sum) : uniform;     // :714-724
             }
+            n_new = n;
             if (lane == 0) {
                 tp.first[base + leaf] = alloc; tp.nchild[base + leaf] = (int16_t)n; tp.alloc[t] = alloc + n;
                 if (first_fill) tp.tflags[t] = tf & ~TF_FIRST_FILL;
@@ -226,6 +254,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     // W += 3, N += 1, W += v.  The root received one extra virtual loss at selection start that is never
     // removed (QUIRK M7): N_root += 4, VL_root += 3, W_root goes through -3,-3,+3,+v.
     const int plen = wb.path_len[t];
+    if (plen == 0 && n_new > 0 && lane == 0) tp.sub[base + leaf] += n_new;      // root-expansion wave: no path, the leaf is the root
     if (plen > 0 && lane == 0) {
         const int* path = wb.path + (size_t)t * MAX_DEPTH;
         const float vl = (float)sp.virtual_loss;
@@ -237,6 +266,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
                           tp.N[c] += sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
             else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] += 1; }
             tp.W[c] = wv;
+            if (n_new) tp.sub[c] += n_new;
             cv = -cv;
         }
         atomicAdd(&stats->simulations, 1ULL);
@@ -285,7 +315,7 @@ __global__ void __launch_bounds__(128) k_dirichlet(TreePools tp, int T, int slot
     if (t >= T) return;
     const uint8_t tf = tp.tflags[t];
     if (!(tf & TF_ACTIVE) || (tf & TF_GAME_OVER) || !(tf & TF_NEED_NOISE)) return;
-    const size_t base = (size_t)t * tp.cap;
+    const size_t base = (size_t)tp.base[t];
     const int root = tp.root[t];
     const int f = tp.first[base + root];
     if (f < 0) return;                                   // terminal root: nothing to perturb
@@ -349,7 +379,7 @@ __global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::S
     const uint8_t tf = tp.tflags[t];
     if (!(tf & TF_ACTIVE) || (tf & TF_GAME_OVER)) return;
     if (forced_action && forced_action[t] == -2) return;
-    const size_t base = (size_t)t * tp.cap;
+    const size_t base = (size_t)tp.base[t];
     const int root = tp.root[t];
     const int f = tp.first[base + root];
     const int nc = f >= 0 ? tp.nchild[base + root] : 0;
@@ -422,70 +452,111 @@ __global__ void __launch_bounds__(128) k_choose_move(TreePools tp, typename G::S
     }
 }
 
-// Re-root with compaction (M14): the chosen child's subtree is copied breadth-first into a scratch pool
-// (children stay contiguous and in order), then copied back to the front of the tree's pool.  The
-// reference frees the siblings recursively; here they are simply not copied.
-struct ScratchPools { int32_t* N; float* W; float* P; int32_t* first; int16_t* act; int16_t* nchild; uint8_t* flags; int32_t* old_id; };
-
-template <class G>
-__global__ void __launch_bounds__(128) k_reroot(TreePools tp, ScratchPools sc, const typename G::State* __restrict__ root_state,
-                                               const int32_t* __restrict__ chosen_child, int t0, int tcount, int T) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wi >= tcount) return;
-    const int t = t0 + wi;
+// Re-root (M14, updateWithMove parallel_mcts.cpp:1065-1108) + region re-cut.  Three steps per move commit:
+//   k_region_need  — per tree: nodes kept = 1 + descendants of the chosen child (the whole tree if the slot did not move, 1 for a fresh root)
+//   k_region_plan  — one block: prefix sum of kept + growth budget over the trees → new base / limit in the OTHER pool buffer; when the
+//                    pool cannot hold every tree's worst-case growth the budgets shrink evenly and `short_nodes` reports by how much
+//   k_reroot_copy  — one warp per tree: breadth-first copy of the kept subtree old buffer → new region (children stay contiguous and in
+//                    order); the reference frees the siblings recursively, here they are simply not copied.
+__global__ void k_region_need(TreePools tp, const int32_t* __restrict__ chosen_child, int32_t* kept, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int cc = chosen_child[t];
-    if (cc == -2) return;                                // slot did not move
+    const size_t base = (size_t)tp.base[t];
+    kept[t] = cc == -2 ? tp.alloc[t] : (cc < 0 ? 1 : tp.sub[base + cc] + 1);
+}
+struct RegionPlan { unsigned long long need_total, kept_total, short_nodes; };
+__global__ void __launch_bounds__(1024) k_region_plan(const int32_t* __restrict__ kept, int64_t* new_base, int32_t* new_limit, int T, int budget,
+                                                     long long pool_nodes, RegionPlan* plan) {
+    __shared__ long long s_part[1024];
+    __shared__ long long s_kept_total;
+    const int tid = threadIdx.x, per = (T + 1023) / 1024;
+    const int t0 = min(tid * per, T), t1 = min(t0 + per, T);
+    long long k = 0;
+    for (int t = t0; t < t1; ++t) k += kept[t];
+    s_part[tid] = k;
+    __syncthreads();
+    if (tid == 0) { long long acc = 0; for (int i = 0; i < 1024; ++i) { const long long v = s_part[i]; s_part[i] = acc; acc += v; } s_kept_total = acc; }
+    __syncthreads();
+    const long long kept_total = s_kept_total;
+    // growth per tree: the full budget plus an equal share of the slack, or — pool too small — an equal share of what is left
+    const long long room = pool_nodes - kept_total;
+    long long grow = room > 0 ? room / T : 0;
+    if (tid == 0) { plan->need_total = (unsigned long long)(kept_total + (long long)T * budget); plan->kept_total = (unsigned long long)kept_total;
+                    plan->short_nodes = grow < budget ? (unsigned long long)((long long)T * (budget - grow)) : 0ULL; }
+    grow = min(grow, (long long)0x7fffffff - 0x1000000);
+    long long b = s_part[tid] + (long long)t0 * grow;
+    for (int t = t0; t < t1; ++t) {
+        new_base[t] = b;
+        const long long lim = min((long long)kept[t] + grow, pool_nodes - b);       // (kept_total > pool_nodes: truncated, flagged by the copy)
+        new_limit[t] = (int32_t)max(lim, 0LL);
+        b += kept[t] + grow;
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(128) k_reroot_copy(TreePools tp, TreePools np, const typename G::State* __restrict__ root_state,
+                                                    const int32_t* __restrict__ chosen_child, int T, Stats* stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int cc = chosen_child[t];
     typename G::Warp& w = warp_ws<G>(smem);
-    const size_t base = (size_t)t * tp.cap;
-    const size_t sb = (size_t)wi * tp.cap;
+    const size_t ob = (size_t)tp.base[t], nb = (size_t)np.base[t];
+    const int lim = np.limit[t];
     int count = 1;
-    if (cc < 0) {
+    bool truncated = lim < 1;
+    if (cc == -1) {
         // child did not exist: fresh root (parallel_mcts.cpp:1097-1101)
-        if (lane == 0) { tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0; }
-    } else {
+        if (lane == 0 && !truncated) { np.N[nb] = 0; np.W[nb] = 0.0f; np.P[nb] = 0.0f; np.first[nb] = -1; np.sub[nb] = 0; np.act[nb] = -1; np.nchild[nb] = 0; np.flags[nb] = 0; }
+    } else if (!truncated) {
+        const int r = cc == -2 ? tp.root[t] : cc;               // slot did not move: the whole tree goes over as it is
+        // new node j: all fields copied; np.first[j] temporarily holds the OLD index of j's first child until j is processed
         if (lane == 0) {
-            sc.N[sb] = tp.N[base + cc]; sc.W[sb] = tp.W[base + cc]; sc.P[sb] = tp.P[base + cc]; sc.act[sb] = tp.act[base + cc];
-            sc.flags[sb] = tp.flags[base + cc]; sc.first[sb] = -1; sc.nchild[sb] = 0; sc.old_id[sb] = cc;
+            np.N[nb] = tp.N[ob + r]; np.W[nb] = tp.W[ob + r]; np.P[nb] = tp.P[ob + r]; np.act[nb] = tp.act[ob + r]; np.flags[nb] = tp.flags[ob + r];
+            np.sub[nb] = tp.sub[ob + r]; np.nchild[nb] = tp.nchild[ob + r]; np.first[nb] = tp.first[ob + r];
         }
         __syncwarp();
-        for (int j0 = 0; j0 < count;) {
+        for (int j0 = 0; j0 < count && !truncated;) {
             // only nodes that exist at the start of the chunk; nodes appended meanwhile wait for a later chunk
             const int end = min(j0 + 32, count);
             const int j = j0 + lane;
             int fo = -1, no = 0;
-            if (j < end) { const int o = sc.old_id[sb + j]; fo = tp.first[base + o]; no = tp.nchild[base + o]; }
+            if (j < end) { fo = np.first[nb + j]; no = np.nchild[nb + j]; }
             unsigned m = __ballot_sync(0xffffffffu, fo >= 0);
             while (m) {
                 const int src = __ffs(m) - 1; m &= m - 1;
                 const int f = __shfl_sync(0xffffffffu, fo, src), n = __shfl_sync(0xffffffffu, no, src);
+                if (count + n > lim) { truncated = true; break; }
                 for (int i = lane; i < n; i += 32) {
-                    const size_t o = base + f + i, d = sb + count + i;
-                    sc.N[d] = tp.N[o]; sc.W[d] = tp.W[o]; sc.P[d] = tp.P[o]; sc.act[d] = tp.act[o]; sc.flags[d] = tp.flags[o];
-                    sc.first[d] = -1; sc.nchild[d] = 0; sc.old_id[d] = f + i;
+                    const size_t o = ob + f + i, d = nb + count + i;
+                    np.N[d] = tp.N[o]; np.W[d] = tp.W[o]; np.P[d] = tp.P[o]; np.act[d] = tp.act[o]; np.flags[d] = tp.flags[o];
+                    np.sub[d] = tp.sub[o]; np.nchild[d] = tp.nchild[o]; np.first[d] = tp.first[o];
                 }
-                if (lane == 0) { sc.first[sb + j0 + src] = count; sc.nchild[sb + j0 + src] = (int16_t)n; }
+                if (lane == 0) np.first[nb + j0 + src] = count;
                 count += n;
             }
             __syncwarp();
             j0 = end;
         }
-        for (int i = lane; i < count; i += 32) {
-            tp.N[base + i] = sc.N[sb + i]; tp.W[base + i] = sc.W[sb + i]; tp.P[base + i] = sc.P[sb + i]; tp.first[base + i] = sc.first[sb + i];
-            tp.act[base + i] = sc.act[sb + i]; tp.nchild[base + i] = sc.nchild[sb + i]; tp.flags[base + i] = sc.flags[sb + i];
-        }
+        // pool exhausted: the slot continues from an unexpanded root (flagged TF_OVERFLOW and counted — an error, see az_engine_search)
+        if (truncated && lane == 0) { np.first[nb] = -1; np.nchild[nb] = 0; np.sub[nb] = 0; }
     }
     // the new root's terminal status comes from the state, as in the root MCTSNode ctor (mcts_node.cpp:24-25)
     G::w_load_root(w, root_state + t, lane);
-    const int res = G::w_root_result(w, lane);
+    const int res = cc == -2 ? RES_ONGOING : G::w_root_result(w, lane);
     if (lane == 0) {
         uint8_t tf = tp.tflags[t];
-        if (res != RES_ONGOING) { tp.flags[base] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)); tf |= TF_GAME_OVER; }
-        tf &= ~TF_FIRST_FILL;
+        if (cc != -2) {
+            if (res != RES_ONGOING && !truncated) { np.flags[nb] = (uint8_t)(NF_TERMINAL | (res << NF_RESULT_SHIFT)); }
+            if (res != RES_ONGOING) tf |= TF_GAME_OVER;
+            tf &= ~TF_FIRST_FILL;
+            tp.root_vl[t] = 0;
+        }
+        if (truncated) { tf |= TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         tp.tflags[t] = tf;
-        tp.root[t] = 0; tp.alloc[t] = count; tp.root_vl[t] = 0;
+        tp.root[t] = 0; tp.alloc[t] = truncated ? 1 : count;
     }
 }
 
@@ -495,7 +566,7 @@ template <class G>
 __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::State* root_state, Sample<G>* game_buf, int max_moves,
                                                      Sample<G>* out, int out_cap, int* out_count, const int16_t* __restrict__ default_order,
                                                      int default_order_n, int16_t* root_order, int32_t* root_order_n,
-                                                     int auto_restart, int noise_every_even_move, int T, Stats* stats) {
+                                                     int auto_restart, int noise_every_even_move, int T, Stats* stats, EvalTT tt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -508,7 +579,7 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
         if (noise_every_even_move && lane == 0 && tp.move_num[t] > 0 && ((tp.move_num[t] - 1) % 2 == 0)) tp.tflags[t] = tf | TF_NEED_NOISE;
         return;
     }
-    const size_t base = (size_t)t * tp.cap;
+    const size_t base = (size_t)tp.base[t];
     G::w_load_root(w, root_state + t, lane);
     const int res = G::w_root_result(w, lane);
     const int n = min(tp.move_num[t], max_moves);
@@ -538,13 +609,14 @@ __global__ void __launch_bounds__(128) k_finish_games(TreePools tp, typename G::
     if (lane == 0) {
         atomicAdd(&stats->games, 1ULL);
         if (auto_restart) {
-            tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
+            tp.N[base] = 0; tp.W[base] = 0.0f; tp.P[base] = 0.0f; tp.first[base] = -1; tp.sub[base] = 0; tp.act[base] = -1; tp.nchild[base] = 0; tp.flags[base] = 0;
             tp.root[t] = 0; tp.alloc[t] = 1; tp.root_vl[t] = 0; tp.move_num[t] = 0; tp.game_id[t] += 1;
             tp.tflags[t] = TF_ACTIVE | (G::FIRST_FILL ? TF_FIRST_FILL : 0) | (noise_every_even_move ? TF_NEED_NOISE : 0);
             root_order_n[t] = default_order_n;
         } else tp.tflags[t] = tf & ~TF_ACTIVE;   // keeps TF_GAME_OVER for the host to see
     }
     if (auto_restart) for (int i = lane; i < default_order_n; i += 32) root_order[(size_t)t * G::MAX_CHILDREN + i] = default_order[i];
+    if (auto_restart && tt.keys) { for (int i = lane; i < tt.cap; i += 32) tt.keys[(size_t)t * tt.cap + i] = 0; if (lane == 0) tt.count[t] = 0; }     // a new game gets a new table
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 GOMOKU, CHESS, GO = 0, 1, 2
 ONGOING, DRAW, WIN_PLAYER1, WIN_PLAYER2 = 0, 1, 2, 3
-EVAL_HASH, EVAL_RESNET = 0, 1
+EVAL_HASH, EVAL_RESNET, EVAL_HASH_PEAKED = 0, 1, 2
+NET_FP16, NET_BF16 = 0, 1
 
 
 class LibraryMissing(RuntimeError):
@@ -30,7 +31,7 @@ class EngineConfig(C.Structure):
                 ("init_temperature", C.c_float), ("final_temperature", C.c_float),
                 ("temperature_drop_move", C.c_int32), ("auto_restart", C.c_int32),
                 ("sample_ring_capacity", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
-                ("n_streams", C.c_int32), ("reserved_", C.c_int32)]
+                ("n_streams", C.c_int32), ("net_precision", C.c_int32), ("tt_entries", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -31,7 +31,14 @@ enum { AZ_GAME_GOMOKU = 0, AZ_GAME_CHESS = 1, AZ_GAME_GO = 2 };
 enum { AZ_ONGOING = 0, AZ_DRAW = 1, AZ_WIN_PLAYER1 = 2, AZ_WIN_PLAYER2 = 3 };
 /* evaluator behind nn::NeuralNetwork::predict (include/alphazero/nn/neural_network.h:29) */
 enum { AZ_EVAL_HASH = 0,   /* stateless integer-mix evaluator (parity runs) */
-       AZ_EVAL_RESNET = 1  /* policy/value ResNet, bf16 on tcgen05 tensor cores */ };
+       AZ_EVAL_RESNET = 1, /* policy/value ResNet, 16-bit operands on tcgen05 tensor cores (kind::f16), fp32 accumulation */
+       AZ_EVAL_HASH_PEAKED = 2 /* AZ_EVAL_HASH with one action's raw prior x 4096 (a peaked policy: deep, narrow trees; node-pool stress / parity) */ };
+/* 16-bit storage type of the network's activations and conv weights.  nn::TorchNeuralNetworkConfig::useFp16
+ * (include/alphazero/nn/torch_neural_network.h:29: the reference's own reduced-precision mode is fp16, model_.to(torch::kHalf),
+ * src/nn/torch_neural_network.cpp:183,267,409).  fp16 and bf16 run the same tcgen05.mma.kind::f16 instruction at the same rate; fp16
+ * carries 11 significand bits instead of 8, which is what the policy KL <= 1e-3 tolerance needs on the BASELINE network
+ * (profiles/r2_kl_rounding_experiment.md).  Stores saturate at +-65504 instead of overflowing. */
+enum { AZ_NET_FP16 = 0, AZ_NET_BF16 = 1 };
 
 /* mcts::MCTSConfig (include/alphazero/mcts/parallel_mcts.h:41-74) + SelfPlayManager exploration params
  * (src/selfplay/self_play_manager.cpp:16-37) + engine sizing. */
@@ -59,6 +66,11 @@ typedef struct az_config {
     uint64_t seed;              /* Philox key for noise / temperature sampling */
     int32_t n_streams;          /* stream groups the slots are split into (tree kernels of one group overlap the
                                    network pass of another); 0 = default (1: measured no gain under the 1 kW power cap) */
+    int32_t net_precision;      /* AZ_NET_FP16 (default) | AZ_NET_BF16 */
+    int32_t tt_entries;         /* chess + hash evaluators only: per-tree capacity of the model of the reference's TranspositionTable
+                                   (keyed by the piece placement, QUIRK C8: a leaf whose placement was evaluated before in the game gets that
+                                   position's evaluation, src/mcts/parallel_mcts.cpp:320-336).  0 = default (on, sized from num_simulations),
+                                   -1 = off (every leaf evaluated on its own input) */
     int32_t reserved_;
 } az_config;
 

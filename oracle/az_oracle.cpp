@@ -538,11 +538,15 @@ struct Chess : State {
 };
 
 // ------------------------------------------------------------------------------------ HashEvaluator
-static void hash_eval(uint64_t h, int A, float* policy, float* value) {
+// peaked (evaluator 2): the raw prior of action mix(h ^ 0x5EED) % A is multiplied by 4096 before the normalisation — a deterministic
+// evaluator with a sharply peaked policy (deep, narrow trees: what a trained network produces), same exactly-rounded fp32 ops
+static void hash_eval(uint64_t h, int A, float* policy, float* value, bool peaked = false) {
     float sum = 0.0f;
+    const int peak = peaked ? (int)(mix64(h ^ 0x5EEDULL) % (uint64_t)A) : -1;
     for (int i = 0; i < A; ++i) {
         uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
         policy[i] = (float)(r + 1) / (float)(1 << 24);
+        if (i == peak) policy[i] = policy[i] * 4096.0f;
         sum += policy[i];
     }
     for (int i = 0; i < A; ++i) policy[i] = policy[i] / sum;
@@ -562,7 +566,7 @@ struct Node {                          // MCTSNode, include/alphazero/mcts/mcts_
 struct Search {
     std::unique_ptr<State> root_state; std::vector<Node> pool; int root = 0;
     int sims = 800; float cpuct = 1.5f; int vl = 3; int max_depth = 1000;
-    eval_cb_t cb = nullptr; void* user = nullptr; long evals = 0;
+    eval_cb_t cb = nullptr; void* user = nullptr; long evals = 0; bool peaked = false;
     // TranspositionTable (transposition_table.cpp:44-84, 128-176) as the serial search sees it: lookup by full 64-bit hash, first store
     // wins ("existing-key store keeps the old policy").  Slot collisions (hash & (size - 1)) and the age-based replacement are not
     // modelled: with 1 M slots and a few thousand entries per game they do not occur in the pinned runs.  One table per game, kept
@@ -589,7 +593,7 @@ struct Search {
     void evaluate(const State& s, std::vector<float>& pol, float& v) {
         ++evals; int A = s.action_space(); pol.assign(A, 0.0f);
         if (cb) { int C = s.planes(), n = s.board_size(); std::vector<float> t((size_t)C * n * n); s.tensor(t.data()); cb(t.data(), C, n, n, A, pol.data(), &v, user); }
-        else hash_eval(s.key(), A, pol.data(), &v);
+        else hash_eval(s.key(), A, pol.data(), &v, peaked);
     }
     void expand(int ni, const State& s, const std::vector<float>& pol) {   // expandNodeWithPolicy :681-745 (M5)
         if (pool[ni].expanded || pool[ni].term) return;
@@ -705,6 +709,7 @@ int orc_go_captured(void* h, int pl) { return ((Go*)h)->captured[pl]; }
 void* orc_mcts_new(void* state, int sims, float cpuct, int vl, int evaluator, eval_cb_t cb, void* user) {
     Search* s = new Search(*(State*)state, sims, cpuct, vl);
     if (evaluator == 1) { s->cb = cb; s->user = user; }
+    if (evaluator == 2) s->peaked = true;
     return s;
 }
 void orc_mcts_free(void* h) { delete (Search*)h; }

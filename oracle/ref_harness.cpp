@@ -74,11 +74,13 @@ uint64_t state_key(const IGameState& s) {
     return h;
 }
 
-void hash_eval(uint64_t h, int A, float* policy, float* value) {
+void hash_eval(uint64_t h, int A, float* policy, float* value, bool peaked = false) {
     float sum = 0.0f;
+    const int peak = peaked ? (int)(mix64(h ^ 0x5EEDULL) % (uint64_t)A) : -1;     // evaluator 2: one action's raw prior x 4096
     for (int i = 0; i < A; ++i) {
         uint64_t r = mix64(h + (uint64_t)i * 0x9E3779B97F4A7C15ULL) >> 40;
         float raw = (float)(r + 1) / (float)(1 << 24);
+        if (i == peak) raw = raw * 4096.0f;
         policy[i] = raw;
         sum += raw;
     }
@@ -111,11 +113,12 @@ public:
 
 class HashEvaluator : public EvaluatorBase {
 public:
+    bool peaked = false;
     std::pair<std::vector<float>, float> predict(const IGameState& s) override {
         ++calls;
         int A = s.getActionSpaceSize();
         std::vector<float> pol(A); float v;
-        hash_eval(state_key(s), A, pol.data(), &v);
+        hash_eval(state_key(s), A, pol.data(), &v, peaked);
         return {pol, v};
     }
 };
@@ -276,10 +279,11 @@ int ref_game_record_json(int game_type, int board_size, int variant, const int* 
 }
 
 // ---------------------------------------------------------------- search API
-// evaluator: 0 = HashEvaluator, 1 = CallbackEvaluator(cb,user)
+// evaluator: 0 = HashEvaluator, 1 = CallbackEvaluator(cb,user), 2 = HashEvaluator with a peaked policy
 void* ref_mcts_new(void* state, int sims, float cpuct, int virtual_loss, int evaluator, eval_cb_t cb, void* user) {
     auto* r = new RefMcts();
-    if (evaluator == 0) r->nn.reset(new HashEvaluator()); else r->nn.reset(new CallbackEvaluator(cb, user));
+    if (evaluator == 0 || evaluator == 2) { auto* he = new HashEvaluator(); he->peaked = evaluator == 2; r->nn.reset(he); }
+    else r->nn.reset(new CallbackEvaluator(cb, user));
     r->tt.reset(new alphazero::mcts::TranspositionTable(1 << 20, 1 << 10));
     alphazero::mcts::MCTSConfig cfg;
     cfg.numThreads = 1; cfg.numSimulations = sims; cfg.cPuct = cpuct; cfg.fpuReduction = 0.0f;

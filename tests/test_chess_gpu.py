@@ -92,9 +92,12 @@ def test_chess_search_matches_oracle():
     valueSum / prior bits, then play on for a few moves (subtree reuse)."""
     O = _orc.oracle()
     sims = 120
-    roots = [[], SCRIPTED[1][:6], SCRIPTED[2][:4], _random_games(O, 1, 40, seed=9)[0]]
+    # SCRIPTED[1][:6], SCRIPTED[4][:6] and the seed-11 game contain QUIRK C8 events within these searches (a leaf whose piece placement was
+    # evaluated before with other castling rights / side to move gets that position's cached evaluation from the reference's
+    # TranspositionTable, tests/test_ref_chess_dataset.py): the engine's table model (tree.cuh EvalTT) must reproduce them
+    roots = [[], SCRIPTED[1][:6], SCRIPTED[2][:4], SCRIPTED[4][:6], _random_games(O, 1, 40, seed=9)[0], _random_games(O, 1, 40, seed=11)[0]]
     eng = chess_engine(len(roots), sims=sims)
-    searches, tt_free = [], []
+    searches = []
     for t, mv in enumerate(roots):
         s = O.new_state(CHESS, 8)
         for a in mv:
@@ -103,18 +106,12 @@ def test_chess_search_matches_oracle():
             s = O.new_state(CHESS, 8); mv = []
         eng.set_root(t, mv)
         searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
-        # the engine evaluates every leaf on its own input (no TranspositionTable); the oracle's default models the reference's table,
-        # whose chess key is the piece placement only (QUIRK C8, tests/test_ref_chess_dataset.py).  Compare with the TT-free oracle and
-        # check beside it that the reference-faithful search gives the same trees on these roots (no C8 event in them).
-        tt_free.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None)); O.mcts_set_tt(tt_free[-1], 0)
     for move in range(3):
         eng.search()
         acts = []
         for t in range(len(roots)):
-            O.mcts_search(searches[t]); O.mcts_search(tt_free[t])
-            a, b, c = eng.root_stats(t), O.root_stats(tt_free[t]), O.root_stats(searches[t])
-            assert np.array_equal(b["N"], c["N"]) and np.array_equal(bits(b["W"]), bits(c["W"])), ("C8 event in a parity root", move, t)
-            O.mcts_update_with_move(tt_free[t], O.mcts_select_action(tt_free[t], 1, 1.0))
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
             assert np.array_equal(a["actions"], b["actions"]), (move, t)
             assert np.array_equal(a["N"], b["N"]), (move, t)
             assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, t)
@@ -171,4 +168,31 @@ def test_chess_selfplay_with_resnet_evaluator():
     eng.play(2)
     s = eng.stats()
     assert s["moves"] == 2 * T and s["simulations"] == 3 * sims * T and s["pool_overflows"] == 0
+    eng.close()
+
+
+def test_chess_search_without_table_model_matches_tt_free_oracle():
+    """tt_entries = -1 switches the TranspositionTable model off: every leaf is evaluated on its own input.  On a root with a QUIRK C8
+    event the engine then equals the oracle's TT-free search and differs from the reference-faithful one exactly where the oracle says."""
+    O = _orc.oracle()
+    sims, mv = 120, SCRIPTED[4][:6]
+    eng = chess_engine(1, sims=sims, tt_entries=-1)
+    s = O.new_state(CHESS, 8)
+    for a in mv:
+        assert O.state_make_move(s, a) == 0
+    eng.set_root(0, mv)
+    on, off = O.mcts_new(s, sims, 1.5, 3, 0, None, None), O.mcts_new(s, sims, 1.5, 3, 0, None, None)
+    O.mcts_set_tt(off, 0)
+    differed = False
+    for move in range(3):
+        eng.search(); O.mcts_search(on); O.mcts_search(off)
+        a, b, c = eng.root_stats(0), O.root_stats(off), O.root_stats(on)
+        assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]) and np.array_equal(bits(a["W"]), bits(b["W"])), move
+        differed |= not (np.array_equal(b["N"], c["N"]) and np.array_equal(bits(b["W"]), bits(c["W"])))
+        act = O.mcts_select_action(off, 1, 1.0)
+        if O.mcts_select_action(on, 1, 1.0) != act:
+            differed = True
+            break
+        O.mcts_update_with_move(off, act); O.mcts_update_with_move(on, act); eng.advance([act])
+    assert differed
     eng.close()

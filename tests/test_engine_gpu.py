@@ -278,3 +278,66 @@ def test_c_abi_error_behaviour():
     net.play(1)
     assert net.stats()["moves"] == 4
     net.close()
+
+
+def test_dirichlet_noise_schedule_matches_playSingleGame():
+    """SelfPlayManager::playSingleGame (self_play_manager.cpp:184, 209-211): addDirichletNoise once before the first search and again after
+    every EVEN move number — so the searches at plies 0, 1, 3, 5, ... see noisy root priors and those at plies 2, 4, 6, ... the pristine
+    ones (normalised network policy, also when the root is a reused subtree).  The noise values themselves are unpinned (libstdc++
+    gamma_distribution vs Philox); the schedule is deterministic and checked here: pristine priors are compared bit for bit with the
+    oracle's expansion arithmetic."""
+    from _eng import hash_engine
+    O = _orc.oracle()
+    board, sims, T = 9, 60, 3
+    eng = hash_engine(T, board=board, sims=sims, deterministic=0, auto_restart=0, init_temperature=0.0, final_temperature=0.0, seed=3, n_streams=1)
+    states = [O.new_state(GOMOKU, board) for _ in range(T)]
+    for ply in range(8):
+        eng.search()
+        acts = []
+        for t in range(T):
+            st = eng.root_stats(t)
+            pol, _ = O.hash_policy_value(states[t])
+            raw = pol[st["actions"]]
+            tot = np.float32(0.0)
+            for x in raw:
+                tot = np.float32(tot + x)
+            pristine = np.array_equal((raw / tot).astype(np.float32).view(np.uint32), st["P"].view(np.uint32))
+            noisy_ply = ply == 0 or (ply - 1) % 2 == 0
+            assert pristine == (not noisy_ply), (ply, t)
+            assert abs(float(st["P"].sum()) - 1.0) < 1e-4
+            a = int(st["actions"][int(np.argmax(st["N"]))])
+            assert O.state_make_move(states[t], a) == 0
+            acts.append(a)
+        eng.advance(acts)
+    eng.close()
+
+
+def test_advisor_regressions_groups_order_drain():
+    """(1) stream-group counts that do not divide the slots (9 / 4 left an empty group: invalid launch; 5 / 4 a negative one); (2) a caller's
+    first-fill order is validated; (3) a drain buffer smaller than the ring keeps the rest for the next call."""
+    from _eng import E, hash_engine
+    for n_slots, n_streams in [(9, 4), (5, 4), (7, 3)]:
+        eng = hash_engine(n_slots, board=9, sims=12, n_streams=n_streams)
+        eng.search()
+        assert all(int(eng.root_stats(t)["N"].sum()) == 12 for t in range(n_slots))
+        eng.close()
+    eng = hash_engine(2, board=9, sims=8)
+    with pytest.raises(E.EngineError, match="first_fill_order"):
+        eng.set_root(0, [40], first_fill_order=list(range(81)))             # 40 is occupied
+    with pytest.raises(E.EngineError, match="first_fill_order"):
+        eng.set_root(0, [40], first_fill_order=[0] * 80)                    # repeated
+    with pytest.raises(E.EngineError, match="first_fill_order"):
+        eng.set_root(0, [40], first_fill_order=list(range(40)))             # incomplete
+    eng.set_root(0, [40], first_fill_order=[a for a in range(81) if a != 40])
+    eng.close()
+    eng = hash_engine(16, board=9, sims=8, deterministic=0, auto_restart=1, seed=11)
+    got = 0
+    for _ in range(60):
+        eng.play(2)
+    st = eng.stats()
+    first = eng.drain_samples(cap=5)
+    rest = eng.drain_samples()
+    assert len(first) == 5 and st["samples_dropped"] == 0
+    assert len(first) + len(rest) >= st["games"] and len(rest) > 0         # nothing was thrown away by the short drain
+    assert not set(zip(first["game_id"].tolist(), first["slot"].tolist(), first["ply"].tolist())) & set(zip(rest["game_id"].tolist(), rest["slot"].tolist(), rest["ply"].tolist()))
+    eng.close()

@@ -243,3 +243,54 @@ def test_go_full_size_2048_slots_identical_and_golden():
     st = eng.stats()
     assert st["simulations"] == 3 * 400 * T and st["pool_overflows"] == 0
     eng.close()
+
+
+def test_go_peaked_policy_deep_trees_no_overflow():
+    """Node-pool behaviour under a PEAKED policy (what a trained network produces; AZ_EVAL_HASH_PEAKED = the hash evaluator with one
+    action's raw prior x 4096): after the first sweep over the children most simulations go below one child, that child is played, and
+    its subtree — 450-520 visits on top of which the next 400 land — is kept move after move, so a tree holds more than two searches'
+    worth of expansions: more than the fixed 2 x (sims + 1) x A nodes per tree of round 1, which overflowed here.  Go 9x9 @400, 20
+    consecutive moves on 4 roots; regions are re-cut at every move commit from the kept-subtree sizes (tree.cuh).  Asserts 0 failed
+    expansions and bit-equality with the oracle (== the reference, tests/test_oracle.py) on every move."""
+    O = _orc.oracle()
+    board, sims = 9, 400
+    from _eng import E
+    openings = [[], [40], [30, 50], [20, 60, 41]]
+    eng = go_engine(len(openings), board=board, sims=sims, evaluator=E.EVAL_HASH_PEAKED, max_nodes_per_tree=int(2.6 * (sims + 1) * 82))
+    searches = []
+    for t, mv in enumerate(openings):
+        s = O.new_state(GO, board)
+        for a in mv:
+            assert O.state_make_move(s, a) == 0
+        eng.set_root(t, mv)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 2, None, None))
+    shares, deepest = [], 0
+    for move in range(20):
+        eng.search()
+        acts = []
+        for t in range(len(openings)):
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, t)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, t)
+            assert a["rootN"] == b["rootN"]
+            shares.append(a["N"].max() / max(1, a["N"].sum())); deepest = max(deepest, int(a["N"].sum()))
+            act = O.mcts_select_action(searches[t], 1, 1.0)
+            acts.append(act)
+            O.mcts_update_with_move(searches[t], act)
+        eng.advance(acts)
+    assert eng.stats()["pool_overflows"] == 0
+    # the trees really are deeper than one search: the root's children hold more than 2 x sims visits, the played child about half of them
+    assert deepest > 2 * sims and np.mean(shares) > 0.45
+    eng.close()
+
+
+def test_pool_exhaustion_is_an_error_not_silent():
+    """A pool that cannot hold the search: az_engine_search fails (deterministic / parity mode) instead of leaving leaves unexpanded."""
+    from _eng import E
+    eng = go_engine(2, board=9, sims=200, evaluator=E.EVAL_HASH_PEAKED, max_nodes_per_tree=60 * 82)
+    with pytest.raises(E.EngineError, match="node pool exhausted"):
+        for _ in range(6):
+            eng.search()
+            eng.advance([int(eng.root_stats(t)["actions"][int(np.argmax(eng.root_stats(t)["N"]))]) for t in range(2)])
+    eng.close()
