@@ -29,9 +29,11 @@ struct Cfg {
     static constexpr int SMEM = OFF_TSLOT + 16;
 };
 
-// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 / fp16 → four 16-byte stores
-template <bool F16>
-__device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
+// one 32-channel chunk of the epilogue: + bias (+ residual) → ReLU → pad-row mask → bf16 / fp16 → four 16-byte stores.  The epilogue warps
+// share the SM's issue slots with the MMA issuer, so the per-pair work is kept to: 2 FADD (bias), 1-2 unpack + 2 FADD (residual), ONE
+// F2FP conversion that also does the ReLU and the fp16 saturation, one select for the pad-row mask.
+template <bool F16, bool RELU>
+__device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool valid,
                                             __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store, bool skip_store) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -48,12 +50,7 @@ __device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res,
         uint4 o;
         uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float x = v[2 * e], y = v[2 * e + 1];
-            if (relu) { x = fmaxf(x, 0.0f); y = fmaxf(y, 0.0f); }
-            if (!valid) { x = 0.0f; y = 0.0f; }
-            ob[e] = pack2_16<F16>(x, y);
-        }
+        for (int e = 0; e < 4; ++e) { const uint32_t pk = pack2_16<F16, RELU>(v[2 * e], v[2 * e + 1]); ob[e] = valid ? pk : 0u; }
         if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
         if (skip_store) continue;                           // k_trunk_pair: a row past the end of this pair's board group belongs to another pair
         *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
@@ -61,8 +58,10 @@ __device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res,
 }
 __device__ __forceinline__ void pair_epi_chunk(bool f16, const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
                                                __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false) {
-    if (f16) epi_chunk_t<true>(r, res, has_res, sBias, c0, relu, valid, out, p_total, grow, no_store, skip_store);
-    else epi_chunk_t<false>(r, res, has_res, sBias, c0, relu, valid, out, p_total, grow, no_store, skip_store);
+    if (f16) { if (relu) epi_chunk_t<true, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store);
+               else epi_chunk_t<true, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store); }
+    else { if (relu) epi_chunk_t<false, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store);
+           else epi_chunk_t<false, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store); }
 }
 
 // 8 epilogue warps (warps 0-3: rows 0-127 of the item, warps 4-7: rows 128-255; a warp reads TMEM lanes 32 (w % 4) ...), warp 8 = TMA

@@ -20,9 +20,18 @@ namespace az { namespace ptx {
 #include <cuda_fp16.h>
 namespace az { namespace ptx {
 constexpr float F16_MAX = 65504.0f;
-template <bool F16> __device__ __forceinline__ uint32_t pack2_16(float x, float y) {
-    if (F16) { const __half2 h = __floats2half2_rn(fminf(fmaxf(x, -F16_MAX), F16_MAX), fminf(fmaxf(y, -F16_MAX), F16_MAX)); return *reinterpret_cast<const uint32_t*>(&h); }   // saturate, never inf
-    const __nv_bfloat162 b = __floats2bfloat162_rn(x, y); return *reinterpret_cast<const uint32_t*>(&b);
+// (x, y) -> one 32-bit word of two 16-bit values (x in the low half) in ONE conversion instruction: F2FP[.RELU][.SATFINITE].  fp16 stores
+// saturate at +-65504 instead of overflowing to inf; RELU folds max(., 0) into the conversion.
+template <bool F16, bool RELU> __device__ __forceinline__ uint32_t pack2_16(float x, float y) {
+    uint32_t r;
+    if (F16) {
+        if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+        else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    } else {
+        if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+        else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    }
+    return r;
 }
 template <bool F16> __device__ __forceinline__ float2 unpack2_16(uint32_t u) {
     if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
