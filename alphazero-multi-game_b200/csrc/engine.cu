@@ -473,7 +473,11 @@ __global__ void __launch_bounds__(128) k_reset_all(TreePools tp, typename G::Sta
 
 // ------------------------------------------------------------------------------------------------ engine
 struct EngineBase {
+    int device = 0;                 // every C-ABI call makes this the calling thread's current device (engines on several GPUs in one process)
     virtual ~EngineBase() {}
+    virtual int set_search_params(float c_puct, int virtual_loss) = 0;
+    virtual int node_stats(int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n,
+                           int32_t* node_visits, float* node_wsum, float* node_prior, int32_t* node_flags) = 0;
     virtual int load_weights(const void* blob, size_t bytes) = 0;
     virtual int reset_games() = 0;
     virtual int set_root(int slot, const int32_t* moves, int n, const int32_t* order, int n_order) = 0;
@@ -535,7 +539,7 @@ struct EngineT : EngineBase {
     unsigned long long launches = 0, waves = 0;
     std::vector<int16_t> h_default_order;
 
-    ~EngineT() override { destroy(); }
+    ~EngineT() override { cudaSetDevice(device); destroy(); }
 
     void destroy() {
         cudaDeviceSynchronize();
@@ -566,7 +570,7 @@ struct EngineT : EngineBase {
     }
 
     int init(const az_config& c) {
-        cfg = c; T = c.n_slots;
+        cfg = c; T = c.n_slots; device = c.device;
         AZ_CUDA_CHECK(cudaSetDevice(c.device));
         cudaDeviceProp prop; AZ_CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
         AZ_CHECK(prop.major >= 10, "az_b200 needs an sm_100-class GPU (no fallback path exists)");
@@ -905,6 +909,52 @@ struct EngineT : EngineBase {
         return 0;
     }
 
+    int set_search_params(float c_puct, int virtual_loss) override {
+        AZ_CHECK(c_puct > 0.0f && virtual_loss >= 0, "bad search parameters");
+        cfg.c_puct = c_puct; cfg.virtual_loss = virtual_loss;
+        return 0;
+    }
+    // children of the node reached from the root by `path` (actions): MCTSNode::children / actions of any node (mcts_node.h:54-75)
+    int node_stats(int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n,
+                   int32_t* node_visits, float* node_wsum, float* node_prior, int32_t* node_flags) override {
+        AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
+        AZ_CHECK(n_path >= 0 && (n_path == 0 || path), "bad path");
+        if (sync_all()) return -1;
+        long long base_ll = 0; AZ_CUDA_CHECK(cudaMemcpy(&base_ll, tp.base + slot, 8, cudaMemcpyDeviceToHost));
+        const size_t base = (size_t)base_ll;
+        int32_t node; AZ_CUDA_CHECK(cudaMemcpy(&node, tp.root + slot, 4, cudaMemcpyDeviceToHost));
+        std::vector<int16_t> a16;
+        for (int d = 0; d <= n_path; ++d) {
+            int32_t f; int16_t nc;
+            AZ_CUDA_CHECK(cudaMemcpy(&f, tp.first + base + node, 4, cudaMemcpyDeviceToHost));
+            AZ_CUDA_CHECK(cudaMemcpy(&nc, tp.nchild + base + node, 2, cudaMemcpyDeviceToHost));
+            const int count = f >= 0 ? nc : 0;
+            a16.resize(count);
+            if (count) AZ_CUDA_CHECK(cudaMemcpy(a16.data(), tp.act + base + f, 2 * count, cudaMemcpyDeviceToHost));
+            if (d == n_path) {
+                AZ_CHECK(*n >= count, "node_stats: buffers too small");
+                *n = count;
+                for (int i = 0; i < count; ++i) actions[i] = a16[i];
+                if (count) {
+                    AZ_CUDA_CHECK(cudaMemcpy(visits, tp.N + base + f, 4 * count, cudaMemcpyDeviceToHost));
+                    AZ_CUDA_CHECK(cudaMemcpy(wsum, tp.W + base + f, 4 * count, cudaMemcpyDeviceToHost));
+                    AZ_CUDA_CHECK(cudaMemcpy(priors, tp.P + base + f, 4 * count, cudaMemcpyDeviceToHost));
+                }
+                break;
+            }
+            int found = -1;
+            for (int i = 0; i < count; ++i) if (a16[i] == path[d]) { found = i; break; }
+            AZ_CHECK(found >= 0, "node_stats: action not found among the node's children");
+            node = f + found;
+        }
+        uint8_t fl = 0;
+        if (node_visits) AZ_CUDA_CHECK(cudaMemcpy(node_visits, tp.N + base + node, 4, cudaMemcpyDeviceToHost));
+        if (node_wsum) AZ_CUDA_CHECK(cudaMemcpy(node_wsum, tp.W + base + node, 4, cudaMemcpyDeviceToHost));
+        if (node_prior) AZ_CUDA_CHECK(cudaMemcpy(node_prior, tp.P + base + node, 4, cudaMemcpyDeviceToHost));
+        if (node_flags) { AZ_CUDA_CHECK(cudaMemcpy(&fl, tp.flags + base + node, 1, cudaMemcpyDeviceToHost)); *node_flags = fl; }
+        return 0;
+    }
+
     int root_stats(int slot, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n, int32_t* rn, float* rw) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
         if (sync_all()) return -1;
@@ -1201,7 +1251,8 @@ AZ_API int az_engine_create(const az_config* cfg, az_engine** out) {
     return 0;
 }
 AZ_API int az_engine_destroy(az_engine* e) { delete e; return 0; }
-#define AZ_FWD(call) do { if (!e) { az::set_error("null engine"); return -1; } return e->impl->call; } while (0)
+#define AZ_FWD(call) do { if (!e) { az::set_error("null engine"); return -1; } \
+                          if (cudaSetDevice(e->impl->device) != cudaSuccess) { az::set_error("cudaSetDevice failed"); return -1; } return e->impl->call; } while (0)
 AZ_API int az_engine_load_weights(az_engine* e, const void* blob, size_t bytes) { AZ_FWD(load_weights(blob, bytes)); }
 AZ_API int az_engine_reset_games(az_engine* e) { AZ_FWD(reset_games()); }
 AZ_API int az_engine_set_root(az_engine* e, int slot, const int32_t* moves, int n, const int32_t* order, int n_order) { AZ_FWD(set_root(slot, moves, n, order, n_order)); }
@@ -1222,6 +1273,18 @@ AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, con
 }
 AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n, int augment, float* planes, float* policy, float* value) { AZ_FWD(make_examples(samples, n, augment, planes, policy, value)); }
 AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
+AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss) { AZ_FWD(set_search_params(c_puct, virtual_loss)); }
+AZ_API int az_engine_node_stats(az_engine* e, int slot, const int32_t* path, int n_path, int32_t* a, int32_t* v, float* w, float* p, int32_t* n, int32_t* nv, float* nw,
+                                float* np_, int32_t* nf) { AZ_FWD(node_stats(slot, path, n_path, a, v, w, p, n, nv, nw, np_, nf)); }
+// plain device memory for the host layer's multi-GPU sample exchange (the host mirror links no CUDA runtime of its own)
+#define AZ_DEV(dev) do { if (cudaSetDevice(dev) != cudaSuccess) { az::set_error("cudaSetDevice failed"); return -1; } } while (0)
+AZ_API int az_device_count(int* n) { if (!n) return -1; if (cudaGetDeviceCount(n) != cudaSuccess) { *n = 0; cudaGetLastError(); } return 0; }
+AZ_API int az_device_alloc(int device, size_t bytes, void** out) { AZ_DEV(device); AZ_CUDA_CHECK(cudaMalloc(out, bytes ? bytes : 1)); return 0; }
+AZ_API int az_device_free(int device, void* p) { AZ_DEV(device); AZ_CUDA_CHECK(cudaFree(p)); return 0; }
+AZ_API int az_device_memcpy(int device, void* dst, const void* src, size_t bytes, int to_host) {
+    AZ_DEV(device); AZ_CUDA_CHECK(cudaMemcpy(dst, src, bytes, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice)); return 0;
+}
+AZ_API int az_device_sync(int device) { AZ_DEV(device); AZ_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
 AZ_API int az_engine_nn_forward(az_engine* e, const float* planes, int n, float* policy, float* value, float* logits) { AZ_FWD(nn_forward(planes, n, policy, value, logits)); }
 AZ_API int az_engine_nn_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(nn_bench(n_boards, reps, ms)); }
 AZ_API int az_engine_conv_bench(az_engine* e, int n_boards, int reps, float* ms) { AZ_FWD(conv_bench(n_boards, reps, ms)); }

@@ -52,7 +52,8 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_slot_state", "az_engine_sample_layout", "az_engine_drain_samples",
            "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_examples_from_games", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_conv_sampled", "az_engine_event_record", "az_engine_event_elapsed",
-           "az_rules_replay"]
+           "az_rules_replay", "az_engine_set_search_params", "az_engine_node_stats", "az_device_count", "az_device_alloc", "az_device_free",
+           "az_device_memcpy", "az_device_sync"]
 
 
 def library_path():
@@ -110,6 +111,9 @@ def load_library():
         "az_engine_event_record": [vp, C.c_int],
         "az_engine_event_elapsed": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "az_rules_replay": [vp, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, f32p],
+        "az_engine_set_search_params": [vp, C.c_float, C.c_int],
+        "az_engine_node_stats": [vp, C.c_int, i32p, C.c_int, i32p, i32p, f32p, f32p, i32p, i32p, f32p, f32p, i32p],
+        "az_device_count": [i32p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

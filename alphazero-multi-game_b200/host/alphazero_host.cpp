@@ -8,9 +8,12 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <random>
 #include <sstream>
+#include <thread>
+#include <dlfcn.h>
 
 #include <nlohmann/json.hpp>
 
@@ -465,12 +468,12 @@ void B200NeuralNetwork::printModelSummary() const { std::cout << getModelInfo() 
 // ================================================================================================ mcts
 namespace mcts {
 
-ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, nn::NeuralNetwork* nn, TranspositionTable*, int numThreads, int numSimulations,
-                           float cPuct, float fpuReduction, int virtualLoss) : nn_(nn) {
+ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, nn::NeuralNetwork* nn, TranspositionTable* tt, int numThreads, int numSimulations,
+                           float cPuct, float fpuReduction, int virtualLoss) : nn_(nn), tt_(tt) {
     config_.numThreads = numThreads; config_.numSimulations = numSimulations; config_.cPuct = cPuct; config_.fpuReduction = fpuReduction; config_.virtualLoss = virtualLoss;
     build(rootState);
 }
-ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, const MCTSConfig& config, nn::NeuralNetwork* nn, TranspositionTable*) : config_(config), nn_(nn) { build(rootState); }
+ParallelMCTS::ParallelMCTS(const core::IGameState& rootState, const MCTSConfig& config, nn::NeuralNetwork* nn, TranspositionTable* tt) : config_(config), nn_(nn), tt_(tt) { build(rootState); }
 ParallelMCTS::~ParallelMCTS() { if (eng_) az_engine_destroy(eng_); }
 
 void ParallelMCTS::build(const core::IGameState& rootState) {
@@ -495,8 +498,82 @@ void ParallelMCTS::build(const core::IGameState& rootState) {
     const bool firstFill = rootState.getGameType() == core::GameType::GOMOKU;      // only Gomoku's child order depends on the lineage
     check(az_engine_set_root(eng_, 0, moves.data(), (int)moves.size(), firstFill ? ord.data() : nullptr, firstFill ? (int)ord.size() : 0), "az_engine_set_root");
 }
-void ParallelMCTS::setCPuct(float c) { config_.cPuct = c; }
-void ParallelMCTS::setVirtualLoss(int v) { config_.virtualLoss = v; }
+void ParallelMCTS::setCPuct(float c) { config_.cPuct = c; check(az_engine_set_search_params(eng_, config_.cPuct, config_.virtualLoss), "az_engine_set_search_params"); }
+void ParallelMCTS::setVirtualLoss(int v) { config_.virtualLoss = v; check(az_engine_set_search_params(eng_, config_.cPuct, config_.virtualLoss), "az_engine_set_search_params"); }
+void ParallelMCTS::setSelectionStrategy(MCTSNodeSelection s) {
+    if (s != MCTSNodeSelection::PUCT) throw std::runtime_error("the B200 engine implements PUCT selection only (the reference's default, mcts_node.cpp:61-119)");
+    config_.selectionStrategy = s;
+}
+void ParallelMCTS::setConfig(const MCTSConfig& config) {
+    if (config.selectionStrategy != MCTSNodeSelection::PUCT) throw std::runtime_error("the B200 engine implements PUCT selection only");
+    config_ = config;
+    check(az_engine_set_search_params(eng_, config_.cPuct, config_.virtualLoss), "az_engine_set_search_params");
+}
+void ParallelMCTS::setNeuralNetwork(nn::NeuralNetwork* nn) {
+    auto* nb = dynamic_cast<nn::B200NeuralNetwork*>(nn);
+    auto* ob = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
+    if (!nb) throw std::runtime_error("ParallelMCTS on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork)");
+    if (nb->isHash() != ob->isHash() || nb->blocks() != ob->blocks() || nb->channels() != ob->channels())
+        throw std::runtime_error("setNeuralNetwork: the new network must have the shape the engine was built for (same evaluator kind, blocks, channels)");
+    nn_ = nn;
+    if (!nb->isHash()) check(az_engine_load_weights(eng_, nb->blob().data(), nb->blob().size()), "az_engine_load_weights");
+}
+MCTSNode ParallelMCTS::getNode(const std::vector<int>& path) const {
+    MCTSNode nd; const int cap = rootState_->getActionSpaceSize() + 1;
+    std::vector<int32_t> p(path.begin(), path.end()), a(cap), n(cap); nd.childValueSums.resize(cap); nd.childPriors.resize(cap);
+    int32_t cnt = cap, nv = 0, fl = 0;
+    check(az_engine_node_stats(eng_, 0, p.data(), (int)p.size(), a.data(), n.data(), nd.childValueSums.data(), nd.childPriors.data(), &cnt, &nv, &nd.valueSum, &nd.prior, &fl),
+          "az_engine_node_stats");
+    nd.actions.assign(a.begin(), a.begin() + cnt); nd.childVisits.assign(n.begin(), n.begin() + cnt); nd.childValueSums.resize(cnt); nd.childPriors.resize(cnt);
+    nd.visitCount = nv; nd.isExpanded = cnt > 0; nd.isTerminal = (fl & 1) != 0; nd.gameResult = (core::GameResult)((fl >> 1) & 3);
+    return nd;
+}
+void ParallelMCTS::printSearchPath(int action) const {
+    MCTSNode root = getNode();
+    if (std::find(root.actions.begin(), root.actions.end(), action) == root.actions.end()) { std::cout << "Action " << action << " not found in children" << std::endl; return; }
+    MCTSNode child = getNode({action});
+    std::cout << "Path for action " << action << ":\n  Root: V=" << root.visitCount << ", Q=" << std::fixed << std::setprecision(3) << root.getValue()
+              << "\n  Child: V=" << child.visitCount << ", Q=" << child.getValue() << ", P=" << child.prior << std::endl;
+    if (child.isExpanded) {
+        std::cout << "  Grandchildren:" << std::endl;
+        std::vector<size_t> idx(child.actions.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return child.childVisits[x] > child.childVisits[y]; });
+        for (size_t k = 0; k < std::min<size_t>(5, idx.size()); ++k) {
+            const size_t i = idx[k];
+            std::cout << "    Action " << child.actions[i] << ": V=" << child.childVisits[i] << ", Q=" << (child.childVisits[i] ? child.childValueSums[i] / child.childVisits[i] : 0.0f)
+                      << ", P=" << child.childPriors[i] << std::endl;
+        }
+    }
+}
+float MCTSNode::getTerminalValue(int currentPlayer) const {
+    if (gameResult == core::GameResult::WIN_PLAYER1) return currentPlayer == 1 ? 1.0f : -1.0f;
+    if (gameResult == core::GameResult::WIN_PLAYER2) return currentPlayer == 2 ? 1.0f : -1.0f;
+    return 0.0f;
+}
+// mcts_node.cpp:38-59: FLT_MAX for an unvisited node, else "Q + c * P * sqrt(N_parent) / (1 + N)" — the formula the reference documents there
+// (its body returns that formula evaluated on the constants of its own unit test, 0.875, for every visited node; not reproduced)
+float MCTSNode::getUcbScore(float cPuct, int, float, int parentVisits) const {
+    if (visitCount == 0) return std::numeric_limits<float>::max();
+    return valueSum / (float)visitCount + cPuct * prior * std::sqrt((float)parentVisits) / (1.0f + (float)visitCount);
+}
+int MCTSNode::getBestAction() const {
+    int best = -1, mx = -1;
+    for (size_t i = 0; i < actions.size(); ++i) if (childVisits[i] > mx) { mx = childVisits[i]; best = actions[i]; }
+    return best;
+}
+std::vector<float> MCTSNode::getVisitCountDistribution(float temperature) const {
+    std::vector<float> d(childVisits.size(), 0.0f);
+    if (d.empty()) return d;
+    float total = 0.0f; std::vector<float> c(d.size());
+    for (size_t i = 0; i < d.size(); ++i) { c[i] = std::pow((float)childVisits[i], 1.0f / std::max(0.01f, temperature)); total += c[i]; }
+    if (total > 0.0f) for (size_t i = 0; i < d.size(); ++i) d[i] = c[i] / total; else for (auto& x : d) x = 1.0f / (float)d.size();
+    return d;
+}
+std::string MCTSNode::toString(int) const {
+    std::ostringstream ss;
+    ss << "Node(V=" << visitCount << ", Q=" << std::fixed << std::setprecision(3) << getValue() << ", P=" << prior << ", children=" << actions.size() << (isTerminal ? ", terminal" : "") << ")";
+    return ss.str();
+}
 
 void ParallelMCTS::search() { check(az_engine_search(eng_, config_.numSimulations), "az_engine_search"); check(az_engine_sync(eng_), "az_engine_sync"); searched_ = true; }
 
@@ -762,59 +839,178 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
     c.deterministic = deterministic_ ? 1 : 0; c.dirichlet_alpha = dirichletAlpha_; c.dirichlet_epsilon = dirichletEpsilon_;
     c.init_temperature = initialTemperature_; c.final_temperature = finalTemperature_; c.temperature_drop_move = temperatureDropMove_; c.auto_restart = 1;
     c.sample_ring_capacity = gameType == core::GameType::CHESS ? c.n_slots * 512 : c.n_slots * bs * bs * (gameType == core::GameType::GO ? 2 : 1);   // move caps: 512 / 2 N^2 / N^2
+    if (saveGames_) std::filesystem::create_directories(outputDir_);
+    if (devices_.size() > 1) return generateGamesMultiGpu(gameType, bs, c);
+    if (devices_.size() == 1) c.device = devices_[0];
     az_engine* e = nullptr;
     check(az_engine_create(&c, &e), "az_engine_create");
     std::vector<GameRecord> done;
-    if (saveGames_) std::filesystem::create_directories(outputDir_);
     try {
         if (!b->isHash()) check(az_engine_load_weights(e, b->blob().data(), b->blob().size()), "az_engine_load_weights");
         az_sample_layout L; check(az_engine_sample_layout(e, &L), "az_engine_sample_layout");
         std::vector<uint8_t> buf((size_t)c.sample_ring_capacity * L.record_bytes);
         const int A = L.n_visits < bs * bs + 1 ? bs * bs : (gameType == core::GameType::GO ? bs * bs + 1 : bs * bs);   // Go: pass is the last entry
+        auto consume = [&](const uint8_t* data, size_t n, int64_t ms) { appendRecords(data, n, L, gameType, bs, A, ms, done); };
         while ((int)done.size() < numGames_ && !abort_) {
             const auto t0 = std::chrono::steady_clock::now();
             check(az_engine_play(e, 1), "az_engine_play");
             size_t n = 0; check(az_engine_drain_samples(e, buf.data(), (size_t)c.sample_ring_capacity, &n), "az_engine_drain_samples");
             const int64_t ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
             totalMoves_ += c.n_slots;
-            // samples of one finished game are contiguous and in ply order (k_finish_games)
-            size_t i = 0;
-            while (i < n && (int)done.size() < numGames_) {
-                const uint8_t* r0 = buf.data() + i * L.record_bytes;
-                uint32_t gid; int32_t slot; std::memcpy(&gid, r0 + L.off_game_id, 4); std::memcpy(&slot, r0 + L.off_slot, 4);
-                GameRecord rec(gameType, bs, false);
-                int8_t result = 0;
-                for (; i < n; ++i) {
-                    const uint8_t* r = buf.data() + i * L.record_bytes;
-                    uint32_t g2; int32_t s2; std::memcpy(&g2, r + L.off_game_id, 4); std::memcpy(&s2, r + L.off_slot, 4);
-                    if (g2 != gid || s2 != slot) break;
-                    int16_t action; float rv; std::memcpy(&action, r + L.off_action, 2); std::memcpy(&rv, r + L.off_root_value, 4); std::memcpy(&result, r + L.off_result, 1);
-                    std::vector<float> pol; float tot = 0.0f;
-                    if (gameType == core::GameType::CHESS) {              // (action, count) pairs in child order → child-ordered distribution (the reference's own format)
-                        for (int i = 0; 2 * i + 1 < L.n_visits; ++i) {
-                            uint16_t act, v; std::memcpy(&act, r + L.off_visits + 4 * i, 2); std::memcpy(&v, r + L.off_visits + 4 * i + 2, 2);
-                            if (act == 0 && v == 0) break;
-                            pol.push_back((float)v); tot += (float)v;
-                        }
-                    } else {
-                        pol.assign(A, 0.0f);
-                        for (int a = 0; a < A; ++a) { uint16_t v; std::memcpy(&v, r + L.off_visits + 2 * a, 2); pol[a] = (float)v; tot += pol[a]; }
-                    }
-                    if (tot > 0) for (auto& x : pol) x /= tot;            // action-indexed visit distribution
-                    rec.addMove(action, pol, rv, ms);
-                }
-                rec.setResult((core::GameResult)result);
-                if (saveGames_) {
-                    std::ostringstream fn; fn << outputDir_ << "/" << std::setfill('0') << std::setw(3) << done.size() << "_slot" << slot << "_" << gid << ".json";
-                    rec.saveToFile(fn.str());
-                }
-                done.push_back(std::move(rec));
-                completedGames_ = (int)done.size();
-                if (progressCallback_) progressCallback_((int)done.size() - 1, (int)done.back().getMoves().size(), numGames_, totalMoves_.load());
-            }
+            consume(buf.data(), n, ms);
         }
+        az_stats st; check(az_engine_get_stats(e, &st), "az_engine_get_stats");
+        lastStats_ = {st.simulations, st.evaluations, st.moves, st.games, st.nodes_created, st.nodes_expanded, st.terminal_leaves, st.pool_overflows, st.samples_dropped};
     } catch (...) { az_engine_destroy(e); running_ = false; throw; }
     az_engine_destroy(e);
+    running_ = false;
+    return done;
+}
+
+
+// finished-game sample records → GameRecords.  Samples of one finished game are contiguous and in ply order (k_finish_games).
+void SelfPlayManager::appendRecords(const uint8_t* data, size_t n, const az_sample_layout& L, core::GameType gameType, int bs, int A, int64_t ms, std::vector<GameRecord>& done) {
+    size_t i = 0;
+    while (i < n && (int)done.size() < numGames_) {
+        const uint8_t* r0 = data + i * L.record_bytes;
+        uint32_t gid; int32_t slot; std::memcpy(&gid, r0 + L.off_game_id, 4); std::memcpy(&slot, r0 + L.off_slot, 4);
+        GameRecord rec(gameType, bs, false);
+        int8_t result = 0;
+        for (; i < n; ++i) {
+            const uint8_t* r = data + i * L.record_bytes;
+            uint32_t g2; int32_t s2; std::memcpy(&g2, r + L.off_game_id, 4); std::memcpy(&s2, r + L.off_slot, 4);
+            if (g2 != gid || s2 != slot) break;
+            int16_t action; float rv; std::memcpy(&action, r + L.off_action, 2); std::memcpy(&rv, r + L.off_root_value, 4); std::memcpy(&result, r + L.off_result, 1);
+            std::vector<float> pol; float tot = 0.0f;
+            if (gameType == core::GameType::CHESS) {              // (action, count) pairs in child order → child-ordered distribution (the reference's own format)
+                for (int k = 0; 2 * k + 1 < L.n_visits; ++k) {
+                    uint16_t act, v; std::memcpy(&act, r + L.off_visits + 4 * k, 2); std::memcpy(&v, r + L.off_visits + 4 * k + 2, 2);
+                    if (act == 0 && v == 0) break;
+                    pol.push_back((float)v); tot += (float)v;
+                }
+            } else {
+                pol.assign(A, 0.0f);
+                for (int a = 0; a < A; ++a) { uint16_t v; std::memcpy(&v, r + L.off_visits + 2 * a, 2); pol[a] = (float)v; tot += pol[a]; }
+            }
+            if (tot > 0) for (auto& x : pol) x /= tot;            // action-indexed visit distribution
+            rec.addMove(action, pol, rv, ms);
+        }
+        rec.setResult((core::GameResult)result);
+        if (saveGames_) {
+            std::ostringstream fn; fn << outputDir_ << "/" << std::setfill('0') << std::setw(3) << done.size() << "_slot" << slot << "_" << gid << ".json";
+            rec.saveToFile(fn.str());
+        }
+        done.push_back(std::move(rec));
+        completedGames_ = (int)done.size();
+        if (progressCallback_) progressCallback_((int)done.size() - 1, (int)done.back().getMoves().size(), numGames_, totalMoves_.load());
+    }
+}
+
+// ---- NCCL, resolved at run time (only a run over several GPUs needs it; the library is not a link dependency of the host layer) ----
+namespace {
+struct Nccl {
+    void* lib = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    enum { Uint8 = 1, Uint64 = 5, Sum = 0 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+    void load() {
+        if (lib) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) throw std::runtime_error(std::string("multi-GPU self-play needs NCCL: ") + dlerror());
+        auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + n); return p; };
+        GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+        CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+        AllGather = (int (*)(const void*, void*, size_t, int, void*, void*))sym("ncclAllGather");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, void*))sym("ncclAllReduce");
+        GroupStart = (int (*)())sym("ncclGroupStart"); GroupEnd = (int (*)())sym("ncclGroupEnd");
+    }
+    void ok(int rc, const char* what) const { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (GetErrorString ? GetErrorString(rc) : "NCCL error")); }
+};
+}  // namespace
+
+// Games sharded over several GPUs of one node: one engine and one host thread per device, no exchange during the waves.
+// After every move: each device drains its finished-game samples into its own DEVICE buffer (az_engine_drain_samples_device); the
+// counts are known on the host, so every device sends max(count) records in one ncclAllGather; the engines' cumulative counters go
+// through one ncclAllReduce(sum).  Device 0's copy of the gathered records is read to the host and turned into GameRecords, rank
+// after rank.  (The reference runs one process-wide thread pool of whole games, self_play_manager.cpp:47-113; its multi-GPU story is
+// N OS processes, python/scripts/orchestrate_selfplay.py.)
+std::vector<GameRecord> SelfPlayManager::generateGamesMultiGpu(core::GameType gameType, int bs, const az_config& base) {
+    const int D = (int)devices_.size();
+    int ndev = 0; check(az_device_count(&ndev), "az_device_count");
+    for (int d : devices_) if (d < 0 || d >= ndev) throw std::runtime_error("setDevices: device " + std::to_string(d) + " does not exist (" + std::to_string(ndev) + " visible)");
+    static Nccl nccl; nccl.load();
+    auto* b = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
+    struct Rank { az_engine* e = nullptr; void *send = nullptr, *recv = nullptr, *st_in = nullptr, *st_out = nullptr; size_t n = 0; std::string err; };
+    std::vector<Rank> rk(D);
+    std::vector<void*> comms(D, nullptr);
+    std::vector<GameRecord> done;
+    az_sample_layout L{};
+    const size_t cap = (size_t)base.sample_ring_capacity;
+    auto cleanup = [&]() {
+        for (int d = 0; d < D; ++d) {
+            if (rk[d].e) az_engine_destroy(rk[d].e);
+            for (void* p : {rk[d].send, rk[d].recv, rk[d].st_in, rk[d].st_out}) if (p) az_device_free(devices_[d], p);
+            if (comms[d]) nccl.CommDestroy(comms[d]);
+        }
+    };
+    try {
+        for (int d = 0; d < D; ++d) {
+            az_config c = base; c.device = devices_[d]; c.seed = base.seed + 7919ULL * d;
+            check(az_engine_create(&c, &rk[d].e), "az_engine_create");
+            if (!b->isHash()) check(az_engine_load_weights(rk[d].e, b->blob().data(), b->blob().size()), "az_engine_load_weights");
+        }
+        check(az_engine_sample_layout(rk[0].e, &L), "az_engine_sample_layout");
+        for (int d = 0; d < D; ++d) {
+            check(az_device_alloc(devices_[d], cap * L.record_bytes, &rk[d].send), "az_device_alloc");
+            check(az_device_alloc(devices_[d], (size_t)D * cap * L.record_bytes, &rk[d].recv), "az_device_alloc");
+            check(az_device_alloc(devices_[d], 16 * 8, &rk[d].st_in), "az_device_alloc"); check(az_device_alloc(devices_[d], 16 * 8, &rk[d].st_out), "az_device_alloc");
+        }
+        nccl.ok(nccl.CommInitAll(comms.data(), D, devices_.data()), "ncclCommInitAll");
+        const int A = L.n_visits < bs * bs + 1 ? bs * bs : (gameType == core::GameType::GO ? bs * bs + 1 : bs * bs);
+        std::vector<uint8_t> host((size_t)D * cap * L.record_bytes);
+        lastGatheredBytes_ = 0;
+        while ((int)done.size() < numGames_ && !abort_) {
+            const auto t0 = std::chrono::steady_clock::now();
+            // one move on every device, concurrently; then each device's finished-game samples into its device buffer
+            std::vector<std::thread> th;
+            for (int d = 0; d < D; ++d)
+                th.emplace_back([&, d]() {
+                    if (az_engine_play(rk[d].e, 1) != 0 || az_engine_drain_samples_device(rk[d].e, rk[d].send, cap, &rk[d].n) != 0) rk[d].err = az_last_error();
+                });
+            for (auto& t : th) t.join();
+            for (int d = 0; d < D; ++d) if (!rk[d].err.empty()) throw std::runtime_error("device " + std::to_string(devices_[d]) + ": " + rk[d].err);
+            totalMoves_ += D * base.n_slots;
+            size_t m = 0; for (int d = 0; d < D; ++d) m = std::max(m, rk[d].n);
+            // counters: every rank contributes its cumulative az_stats, the sum lands on every rank
+            for (int d = 0; d < D; ++d) {
+                az_stats st; check(az_engine_get_stats(rk[d].e, &st), "az_engine_get_stats");
+                unsigned long long v[16] = {st.simulations, st.evaluations, st.moves, st.games, st.nodes_created, st.nodes_expanded, st.terminal_leaves, st.pool_overflows, st.samples_dropped};
+                check(az_device_memcpy(devices_[d], rk[d].st_in, v, sizeof v, 0), "az_device_memcpy");
+            }
+            nccl.ok(nccl.GroupStart(), "ncclGroupStart");
+            for (int d = 0; d < D; ++d) {
+                if (m) nccl.ok(nccl.AllGather(rk[d].send, rk[d].recv, m * L.record_bytes, Nccl::Uint8, comms[d], nullptr), "ncclAllGather");
+                nccl.ok(nccl.AllReduce(rk[d].st_in, rk[d].st_out, 16, Nccl::Uint64, Nccl::Sum, comms[d], nullptr), "ncclAllReduce");
+            }
+            nccl.ok(nccl.GroupEnd(), "ncclGroupEnd");
+            for (int d = 0; d < D; ++d) check(az_device_sync(devices_[d]), "az_device_sync");
+            unsigned long long tot[16]; check(az_device_memcpy(devices_[0], tot, rk[0].st_out, sizeof tot, 1), "az_device_memcpy");
+            lastStats_.assign(tot, tot + 9);
+            const int64_t ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+            if (m) {
+                check(az_device_memcpy(devices_[0], host.data(), rk[0].recv, (size_t)D * m * L.record_bytes, 1), "az_device_memcpy");
+                lastGatheredBytes_ += (size_t)D * m * L.record_bytes;
+                for (int d = 0; d < D; ++d) appendRecords(host.data() + (size_t)d * m * L.record_bytes, rk[d].n, L, gameType, bs, A, ms, done);
+            }
+        }
+    } catch (...) { cleanup(); running_ = false; throw; }
+    cleanup();
     running_ = false;
     return done;
 }

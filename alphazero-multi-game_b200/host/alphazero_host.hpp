@@ -319,6 +319,21 @@ private:
     size_t size_;
 };
 
+// mcts::MCTSNode (include/alphazero/mcts/mcts_node.h:54-75, 80-119, 200-230) as a read-only SNAPSHOT of one node of the device tree: the
+// fields and the inspection methods the reference binds to Python (python_bindings.cpp:245-253); children are held as plain statistics.
+class MCTSNode {
+public:
+    int visitCount = 0, virtualLoss = 0; float valueSum = 0.0f, prior = 0.0f;
+    bool isTerminal = false, isExpanded = false; core::GameResult gameResult = core::GameResult::ONGOING;
+    std::vector<int> actions, childVisits; std::vector<float> childValueSums, childPriors;
+    float getValue() const { return visitCount == 0 ? 0.0f : valueSum / visitCount; }                       // mcts_node.h:80-86
+    float getTerminalValue(int currentPlayer) const;                                                       // mcts_node.cpp:387-399
+    float getUcbScore(float cPuct, int currentPlayer, float fpuReduction = 0.0f, int parentVisits = 0) const;   // mcts_node.cpp:121-166
+    int getBestAction() const;                                                                             // first child with the most visits
+    std::vector<float> getVisitCountDistribution(float temperature = 1.0f) const;                          // mcts_node.cpp:289-322
+    std::string toString(int maxDepth = 1) const;
+};
+
 class ParallelMCTS {
 public:
     ParallelMCTS(const core::IGameState& rootState, nn::NeuralNetwork* nn = nullptr, TranspositionTable* tt = nullptr,
@@ -338,6 +353,18 @@ public:
     void setVirtualLoss(int v);
     void setDeterministicMode(bool enable) { config_.useBatchInference = enable; }
     void setDebugMode(bool) {}
+    // parallel_mcts.cpp:1173-1261.  The evaluator runs inside the device waves: a new network is loaded into the engine (tree kept, as in
+    // the reference); the transposition table, batch size / timeout and batched-search switches have nothing to act on (every wave is one
+    // batch) and are recorded only; PUCT is the one selection strategy built (the reference's default and the only one self-play uses).
+    void setNeuralNetwork(nn::NeuralNetwork* nn);
+    void setTranspositionTable(TranspositionTable* tt) { tt_ = tt; }
+    void setSelectionStrategy(MCTSNodeSelection s);
+    void setConfig(const MCTSConfig& config);
+    void enableBatchedMCTS(bool enable) { config_.useBatchedMCTS = enable; }
+    void setBatchSize(int n) { config_.batchSize = n; }
+    void setBatchTimeout(int ms) { config_.batchTimeoutMs = ms; }
+    void printSearchPath(int action) const;                     // parallel_mcts.cpp:1390-1450
+    MCTSNode getNode(const std::vector<int>& path = {}) const;  // snapshot of the node reached from the root by `path` ({} = the root)
     std::string getSearchInfo() const;
     void printSearchStats() const;
     size_t getMemoryUsage() const;
@@ -349,6 +376,7 @@ private:
     void build(const core::IGameState& rootState);
     MCTSConfig config_;
     nn::NeuralNetwork* nn_;
+    TranspositionTable* tt_ = nullptr;
     az_engine* eng_ = nullptr;
     std::unique_ptr<core::IGameState> rootState_;
     bool searched_ = false;
@@ -434,8 +462,16 @@ public:
     int getCompletedGamesCount() const { return completedGames_; }
     int getTotalMovesCount() const { return totalMoves_; }
     // engine knobs without a reference counterpart
-    void setConcurrentGames(int n) { concurrentGames_ = n; }     // game slots on the GPU (default min(numGames, 4096))
+    void setConcurrentGames(int n) { concurrentGames_ = n; }     // game slots per GPU (default min(numGames, 4096))
     void setDeterministic(bool d) { deterministic_ = d; }        // noise off + first-max-visit move (parity runs)
+    // GPUs the games are sharded over (default: device 0 only).  One engine + one host thread per device, no exchange during the waves;
+    // finished-game samples are drained on each device, all-gathered with ncclAllGather and the counters summed with ncclAllReduce
+    //  — libnccl.so.2 is loaded at run time when more than one device is named.
+    void setDevices(const std::vector<int>& devices) { devices_ = devices; }
+    const std::vector<int>& getDevices() const { return devices_; }
+    // counters summed over the devices by the last generateGames: simulations, evaluations, moves, games (ncclAllReduce when > 1 device)
+    std::vector<unsigned long long> getLastRunStats() const { return lastStats_; }
+    size_t getLastGatheredSampleBytes() const { return lastGatheredBytes_; }
 private:
     nn::NeuralNetwork* nn_;
     int numGames_, numSimulations_, numThreads_;
@@ -448,6 +484,11 @@ private:
     int batchSize_ = 64, batchTimeoutMs_ = 10, concurrentGames_ = 0;
     bool deterministic_ = false;
     mcts::MCTSConfig mctsConfig_;
+    std::vector<int> devices_;
+    std::vector<unsigned long long> lastStats_;
+    size_t lastGatheredBytes_ = 0;
+    std::vector<GameRecord> generateGamesMultiGpu(core::GameType gameType, int bs, const az_config& base);
+    void appendRecords(const uint8_t* data, size_t n, const az_sample_layout& L, core::GameType gameType, int bs, int A, int64_t ms, std::vector<GameRecord>& done);
 };
 
 }  // namespace selfplay

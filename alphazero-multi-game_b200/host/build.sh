@@ -11,9 +11,9 @@ JSONINC="$($PY -c 'import os, sysconfig; print(os.path.join(sysconfig.get_paths(
 CXX="${AZ_HOST_CXX:-/usr/bin/g++}"   # NOT $CXX: the image's /opt/gcc wrapper links a second, static libstdc++ into the module
 $CXX -std=c++17 -O2 -fPIC -shared -ffp-contract=off -fvisibility=hidden -I"$PYINC" -I"$PBINC" -I"$JSONINC" -I/usr/local/cuda/include \
     "$HERE/alphazero_host.cpp" "$HERE/python_module.cpp" -o "$PKG/_alphazero_cpp$SUFFIX" \
-    -L"$PKG" -laz_b200 -Wl,-rpath,'$ORIGIN'
+    -L"$PKG" -laz_b200 -ldl -pthread -Wl,-rpath,'$ORIGIN'
 echo "built $PKG/_alphazero_cpp$SUFFIX"
 # the reference's `self_play` command over the same host classes
 $CXX -std=c++17 -O2 -ffp-contract=off -I"$JSONINC" -I/usr/local/cuda/include "$HERE/alphazero_host.cpp" "$HERE/selfplay_main.cpp" -o "$PKG/self_play" \
-    -L"$PKG" -laz_b200 -Wl,-rpath,'$ORIGIN'
+    -L"$PKG" -laz_b200 -ldl -pthread -Wl,-rpath,'$ORIGIN'
 echo "built $PKG/self_play"

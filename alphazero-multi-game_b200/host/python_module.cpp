@@ -76,6 +76,14 @@ PYBIND11_MODULE(_alphazero_cpp, m) {
         .def_readonly("evaluationCalls", &mcts::MCTSStats::evaluationCalls).def_readonly("cacheHits", &mcts::MCTSStats::cacheHits)
         .def_readonly("cacheMisses", &mcts::MCTSStats::cacheMisses).def_readonly("batchedEvaluations", &mcts::MCTSStats::batchedEvaluations)
         .def_readonly("totalBatches", &mcts::MCTSStats::totalBatches);
+    py::class_<mcts::MCTSNode>(m, "MCTSNode")
+        .def("getUcbScore", &mcts::MCTSNode::getUcbScore, py::arg("cPuct"), py::arg("currentPlayer"), py::arg("fpuReduction") = 0.0f, py::arg("parentVisits") = 0)
+        .def("getTerminalValue", &mcts::MCTSNode::getTerminalValue).def("getValue", &mcts::MCTSNode::getValue).def("getBestAction", &mcts::MCTSNode::getBestAction)
+        .def("getVisitCountDistribution", &mcts::MCTSNode::getVisitCountDistribution, py::arg("temperature") = 1.0f)
+        .def("toString", &mcts::MCTSNode::toString, py::arg("maxDepth") = 1)
+        .def_readonly("visitCount", &mcts::MCTSNode::visitCount).def_readonly("valueSum", &mcts::MCTSNode::valueSum).def_readonly("prior", &mcts::MCTSNode::prior)
+        .def_readonly("isTerminal", &mcts::MCTSNode::isTerminal).def_readonly("isExpanded", &mcts::MCTSNode::isExpanded).def_readonly("actions", &mcts::MCTSNode::actions)
+        .def_readonly("childVisits", &mcts::MCTSNode::childVisits).def_readonly("childValueSums", &mcts::MCTSNode::childValueSums).def_readonly("childPriors", &mcts::MCTSNode::childPriors);
     py::class_<mcts::TranspositionTable>(m, "TranspositionTable")
         .def(py::init<size_t, size_t>(), py::arg("size") = 1048576, py::arg("numShards") = 1024)
         .def("getSize", &mcts::TranspositionTable::getSize).def("getHitRate", &mcts::TranspositionTable::getHitRate)
@@ -97,6 +105,11 @@ PYBIND11_MODULE(_alphazero_cpp, m) {
         .def("setNumThreads", &mcts::ParallelMCTS::setNumThreads).def("setNumSimulations", &mcts::ParallelMCTS::setNumSimulations)
         .def("setCPuct", &mcts::ParallelMCTS::setCPuct).def("setFpuReduction", &mcts::ParallelMCTS::setFpuReduction)
         .def("setVirtualLoss", &mcts::ParallelMCTS::setVirtualLoss).def("setDeterministicMode", &mcts::ParallelMCTS::setDeterministicMode)
+        .def("setNeuralNetwork", &mcts::ParallelMCTS::setNeuralNetwork, py::keep_alive<1, 2>()).def("setTranspositionTable", &mcts::ParallelMCTS::setTranspositionTable, py::keep_alive<1, 2>())
+        .def("setSelectionStrategy", &mcts::ParallelMCTS::setSelectionStrategy).def("setConfig", &mcts::ParallelMCTS::setConfig)
+        .def("enableBatchedMCTS", &mcts::ParallelMCTS::enableBatchedMCTS).def("setBatchSize", &mcts::ParallelMCTS::setBatchSize)
+        .def("setBatchTimeout", &mcts::ParallelMCTS::setBatchTimeout).def("printSearchPath", &mcts::ParallelMCTS::printSearchPath)
+        .def("getNode", &mcts::ParallelMCTS::getNode, py::arg("path") = std::vector<int>{})
         .def("setDebugMode", &mcts::ParallelMCTS::setDebugMode).def("printSearchStats", &mcts::ParallelMCTS::printSearchStats)
         .def("getSearchInfo", &mcts::ParallelMCTS::getSearchInfo).def("getMemoryUsage", &mcts::ParallelMCTS::getMemoryUsage)
         .def("getRootChildren", [](const mcts::ParallelMCTS& self) { auto r = self.rootStats(); return py::make_tuple(r.actions, r.visits, r.valueSums, r.priors, r.rootVisits, r.rootValueSum); });
@@ -149,5 +162,7 @@ PYBIND11_MODULE(_alphazero_cpp, m) {
             self.setMctsConfig(c);
         })
         .def("getCompletedGamesCount", &selfplay::SelfPlayManager::getCompletedGamesCount).def("getTotalMovesCount", &selfplay::SelfPlayManager::getTotalMovesCount)
-        .def("setConcurrentGames", &selfplay::SelfPlayManager::setConcurrentGames).def("setDeterministic", &selfplay::SelfPlayManager::setDeterministic);
+        .def("setConcurrentGames", &selfplay::SelfPlayManager::setConcurrentGames).def("setDeterministic", &selfplay::SelfPlayManager::setDeterministic)
+        .def("setDevices", &selfplay::SelfPlayManager::setDevices).def("getDevices", &selfplay::SelfPlayManager::getDevices)
+        .def("getLastRunStats", &selfplay::SelfPlayManager::getLastRunStats).def("getLastGatheredSampleBytes", &selfplay::SelfPlayManager::getLastGatheredSampleBytes);
 }

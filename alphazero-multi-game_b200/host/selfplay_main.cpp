@@ -50,7 +50,8 @@ void usage() {
                  "  --size SIZE           Board size (default: depends on game)\n"
                  "  --num-games NUM       Number of games to generate (default: 100)\n"
                  "  --simulations SIMS    Number of MCTS simulations per move (default: 800)\n"
-                 "  --slots N             Concurrent games on the GPU (default: min(num-games, 4096))\n"
+                 "  --slots N             Concurrent games per GPU (default: min(num-games, 4096))\n"
+                 "  --gpus N              Shard the games over GPUs 0..N-1 of this node (sample all-gather + counter all-reduce over NCCL)\n"
                  "  --output-dir DIR      Output directory (default: data/games)\n"
                  "  --temperature TEMP    Initial temperature (default: 1.0)\n"
                  "  --temp-drop MOVE      Move to drop temperature (default: 30)\n"
@@ -98,6 +99,8 @@ int main(int argc, char** argv) {
         sp.setBatchConfig(batchSize, batchTimeout);
         sp.setSaveGames(true, outputDir);
         if (a.has("slots")) sp.setConcurrentGames(a.num("slots", 0));
+        const int gpus = a.num("gpus", 1);
+        if (gpus > 1) { std::vector<int> dv; for (int d = 0; d < gpus; ++d) dv.push_back(d); sp.setDevices(dv); }
         if (a.flag("deterministic", false)) sp.setDeterministic(true);
         mcts::MCTSConfig mc; mc.numSimulations = sims; mc.cPuct = cPuct; mc.fpuReduction = fpu; mc.virtualLoss = virtualLoss;
         mc.useDirichletNoise = true; mc.dirichletAlpha = alpha; mc.dirichletEpsilon = eps; mc.useProgressiveWidening = pw;

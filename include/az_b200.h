@@ -155,6 +155,23 @@ AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, con
 
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out);
 AZ_API int az_engine_sync(az_engine* e);
+/* ParallelMCTS::setCPuct / setVirtualLoss / setConfig (src/mcts/parallel_mcts.cpp:1173-1261): take effect from the next search */
+AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss);
+/* MCTSNode::children / actions / visitCount / valueSum / prior of ANY node (include/alphazero/mcts/mcts_node.h:54-75; what
+ * ParallelMCTS::printSearchPath walks, parallel_mcts.cpp:1390-1450): the node reached from the slot's root by the action sequence
+ * `path` (n_path = 0: the root).  Children in child order; *n_children in: capacity, out: count; node_* = the node's own fields,
+ * node_flags bit 0 = terminal, bits 1-2 = GameResult. */
+AZ_API int az_engine_node_stats(az_engine* e, int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* value_sums,
+                                float* priors, int32_t* n_children, int32_t* node_visits, float* node_value_sum, float* node_prior, int32_t* node_flags);
+
+/* Device memory for the host layer's multi-GPU exchange (SelfPlayManager over several GPUs: finished-game samples are drained on each
+ * device with az_engine_drain_samples_device, all-gathered with ncclAllGather and read from one device).  Nothing in the
+ * reference corresponds to these (it has no GPU memory of its own); they keep the host layer free of a CUDA runtime dependency. */
+AZ_API int az_device_count(int* n);
+AZ_API int az_device_alloc(int device, size_t bytes, void** out);
+AZ_API int az_device_free(int device, void* p);
+AZ_API int az_device_memcpy(int device, void* dst, const void* src, size_t bytes, int to_host);
+AZ_API int az_device_sync(int device);
 
 /* NeuralNetwork::predictBatch (src/nn/torch_neural_network.cpp:224-363) on caller-supplied feature planes:
  * planes fp32 [n][C][H][W] (host) → policy fp32 [n][A] (softmax over the A logits, :298-316), value fp32 [n]. */

@@ -220,3 +220,74 @@ def test_self_play_command_reference_flags_and_outputs(tmp_path):
     assert m["num_games_completed"] == 3 and m["simulations"] == 30 and m["threads"] == 2 and m["use_gpu"] is True
     bad = subprocess.run([exe, "--model", "hash", "--variant"], capture_output=True, text=True)
     assert bad.returncode == 1 and "variant" in bad.stderr
+
+
+def test_parallel_mcts_inspection_and_setters():
+    """The ParallelMCTS members the reference binds beyond the search loop (python_bindings.cpp:245-253, 303-314): MCTSNode snapshots
+    (getNode), printSearchPath, setConfig / setCPuct (take effect on the next search: the search then equals an oracle run with the new
+    constant), setSelectionStrategy (PUCT only), setNeuralNetwork, setTranspositionTable / batch knobs (recorded, nothing to act on)."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    nn = az.createNeuralNetwork("hash", az.GameType.GOMOKU, 9)
+    state = az.createGameState(az.GameType.GOMOKU, 9, False)
+    mcts = az.ParallelMCTS(state, nn, az.TranspositionTable(1024, 4), 1, 150, 1.5, 0.0, 3)
+    mcts.setDeterministicMode(True)
+    mcts.setCPuct(2.25)                                   # before the first search
+    mcts.search()
+    om = O.mcts_new(O.new_state(_orc.GOMOKU, 9), 150, 2.25, 3, 0, None, None)
+    O.mcts_search(om)
+    b = O.root_stats(om)
+    root = mcts.getNode()
+    assert root.actions == b["actions"].tolist() and root.childVisits == b["N"].tolist() and root.visitCount == b["rootN"] and root.isExpanded
+    assert np.array_equal(np.array(root.childValueSums, np.float32).view(np.uint32), b["W"].view(np.uint32))
+    best = root.getBestAction()
+    assert best == b["actions"][int(np.argmax(b["N"]))]
+    child = mcts.getNode([best])
+    assert child.visitCount == int(b["N"].max()) and abs(child.prior - float(b["P"][int(np.argmax(b["N"]))])) == 0.0
+    assert sum(child.childVisits) == child.visitCount - 1 and "Node(V=" in child.toString()
+    d = root.getVisitCountDistribution(1.0)
+    assert abs(sum(d) - 1.0) < 1e-5 and np.allclose(d, mcts.getActionProbabilities(1.0))
+    assert child.getUcbScore(1.5, 1, 0.0, root.visitCount) > child.getValue()
+    mcts.printSearchPath(best); mcts.printSearchPath(-7)
+    cfg = az.MCTSConfig(); cfg.numSimulations = 60; cfg.cPuct = 1.5; cfg.virtualLoss = 3
+    mcts.setConfig(cfg); mcts.enableBatchedMCTS(True); mcts.setBatchSize(32); mcts.setBatchTimeout(5); mcts.setTranspositionTable(None); mcts.setNeuralNetwork(nn)
+    with pytest.raises(RuntimeError, match="PUCT"):
+        mcts.setSelectionStrategy(az.MCTSNodeSelection.RAVE)
+    mcts.setSelectionStrategy(az.MCTSNodeSelection.PUCT)
+    mcts.search()                                         # 60 more simulations with cPuct 1.5 on the same tree
+    assert sum(mcts.getNode().childVisits) == 150 + 60
+
+
+def test_selfplay_manager_over_two_gpus_nccl():
+    """SelfPlayManager.setDevices([0, 1]): games sharded over two GPUs (one engine + host thread each), finished-game samples all-gathered
+    with ncclAllGather, counters summed with ncclAllReduce — all from the C++ host layer, through the reference's own API.  Needs 2 GPUs
+    (`gpurun --gpus 2`); deterministic mode, so the two devices' games are the same game (every slot plays the oracle's game) and each
+    record can be checked against the single-GPU run."""
+    import _alphazero_cpp as az
+    import ctypes as C
+    from _eng import E
+    n = C.c_int32(0)
+    E.load_library().az_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    nn = az.createNeuralNetwork("hash", az.GameType.GOMOKU, 9)
+    one = az.SelfPlayManager(nn, 4, 48, 1); one.setConcurrentGames(4); one.setDeterministic(True)
+    ref_games = one.generateGames(az.GameType.GOMOKU, 9, False)
+    two = az.SelfPlayManager(nn, 8, 48, 1); two.setConcurrentGames(4); two.setDeterministic(True); two.setDevices([0, 1])
+    games = two.generateGames(az.GameType.GOMOKU, 9, False)
+    assert len(games) == 8 and two.getLastGatheredSampleBytes() > 0
+    want = [m.action for m in ref_games[0].getMoves()]
+    for g in games:
+        assert [m.action for m in g.getMoves()] == want and g.getResult() == ref_games[0].getResult()
+    st1, st2 = one.getLastRunStats(), two.getLastRunStats()
+    assert st2[3] >= 8 and st2[0] == 2 * st1[0] and st2[2] == 2 * st1[2]          # games; simulations and moves: twice the one-GPU run (all-reduced)
+    # throughput mode with the ResNet on both devices: runs, finishes, returns well-formed records
+    from _eng import N
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "w.azw")
+        open(p, "wb").write(N.export_weights(N.make_random_model(seed=0, blocks=1, board=9, actions=81)))
+        net = az.createNeuralNetwork(p, az.GameType.GOMOKU, 9)
+        mgr = az.SelfPlayManager(net, 6, 16, 1); mgr.setConcurrentGames(8); mgr.setDevices([0, 1])
+        gs = mgr.generateGames(az.GameType.GOMOKU, 9, False)
+        assert len(gs) == 6 and all(len(g.getMoves()) >= 5 and g.getResult() != az.GameResult.ONGOING for g in gs)
