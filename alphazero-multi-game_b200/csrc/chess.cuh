@@ -25,6 +25,7 @@ struct Chess {
     static constexpr int SAMPLE_VISITS = 2 * MAX_CHILDREN;   // (action, count) pairs in child order: 20480 counts would be 40 KB
     static constexpr int PLANES = 18;
     static constexpr bool FIRST_FILL = false;
+    static constexpr bool LEGAL_POLICY = true;         // 20480-wide policy head: inside the waves only the legal moves' logits are computed
     static constexpr bool TT_COARSE = true;            // QUIRK C8: the reference's TT key is the piece placement only (tree.cuh EvalTT)
     static constexpr int MAX_GAME_MOVES = 512;         // engine cap: the game is drawn at this ply
     static constexpr int MAXH = MAX_GAME_MOVES + 2;
@@ -373,6 +374,17 @@ struct Chess {
         __syncwarp();
         return n;
     }
+    // the legal list for the policy head; regen = false: w.legal is current (w_result / w_gen_legal ran on this state)
+    __device__ static int w_store_legal(Warp& w, int lane, int16_t* out, bool regen) {
+        const int n = regen ? w_gen_legal(w, lane) : w.n_legal;
+        for (int i = lane; i < n; i += 32) out[i] = w.legal[i];
+        return n;
+    }
+    __device__ static int w_enumerate_pre(int lane, const int16_t* pre, int n, int16_t* acts, float* raw, const float* pol) {
+        for (int i = lane; i < n; i += 32) { const int a = pre[i]; acts[i] = (int16_t)a; raw[i] = pol[a]; }
+        __syncwarp();
+        return n;
+    }
     __device__ static int w_legal(Warp& w, int lane, int32_t* out) {
         const int n = w_gen_legal(w, lane);
         for (int i = lane; i < n; i += 32) out[i] = w.legal[i];
@@ -399,6 +411,9 @@ struct Chess {
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
     __device__ static uint64_t w_tt_key(Warp& w) { return w.s.c.key; }           // ChessState::getHash() granularity: the placement
+    // profiling (AZ_EVAL_DUP_STATS): the 18 planes = pieces, side, castling, e.p., min(1, halfmove / 100), repetitions / 3
+    __device__ static uint64_t w_input_key(Warp& w) { uint64_t h = key_core(w.s.c); h = mix64(h ^ (uint64_t)min((int)w.s.c.half, 100)); return mix64(h ^ (uint64_t)w_reps(w)); }
+    __device__ static uint64_t w_ref_tt_key(Warp& w) { return w.s.c.key; }
     // training examples (az_engine_make_examples); the repetition count travels in the snapshot (w.n_legal doubles as its holder)
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {
         for (int i = lane; i < 16; i += 32) reinterpret_cast<uint32_t*>(w.s.c.b)[i] = reinterpret_cast<const uint32_t*>(g->b)[i];

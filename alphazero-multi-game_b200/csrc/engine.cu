@@ -99,6 +99,13 @@ __global__ void k_prep_1x1(const float* __restrict__ pcw, const float* __restric
 // (cell*32 + ch); rows >= n_rows stay zero (N padded to 256)
 // split = 0: plain bf16 image (K' = K) for very wide heads (chess' 20480 actions: the three-term image would be 252 MB and its
 // GEMM 3x the L2 traffic; the A operand then uses only the hi planes)
+// policy FC weights row-major [n_rows][feat] bf16 with K in feature order (cell * 32 + channel): the legal-moves-only policy kernel reads one row per legal action
+__global__ void k_prep_fc_rows(const float* __restrict__ w /*[n_rows][feat]*/, __nv_bfloat16* rows, int n_rows, int feat) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_rows * feat) return;
+    const int kt = (int)(idx % feat), n = (int)(idx / feat);
+    rows[(size_t)n * feat + (kt % 64) * 32 + kt / 64] = __float2bfloat16(w[idx]);
+}
 __global__ void k_prep_fc(const float* __restrict__ w /*[n_rows][feat]*/, __nv_bfloat16* img, int n_rows, int feat, int split) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n_rows * feat) return;
@@ -166,6 +173,7 @@ struct NetWeights {            // device images
     float *b1x1 = nullptr, *pfc_b = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *vfc2_b = nullptr;   // fp32 biases / tiny last layer
     float* zero_bias = nullptr;                                                                          // [128] for the accumulating channel-slice launches
     __nv_bfloat16 *g1_w = nullptr, *pfc_img = nullptr, *vfc1_img = nullptr;                              // tcgen05 GEMM weight images
+    __nv_bfloat16* pfc_rows = nullptr;                                                                    // wide heads: policy FC weights row-major [A][feat] (legal-moves-only policy, heads.cu)
     __nv_bfloat16* h1_w = nullptr;                                                                        // fused heads kernel: hi / lo image of the folded 1x1 weights (head_conv.cuh)
     float* blob = nullptr; size_t blob_bytes = 0;                                                        // device copy of the last AZW1 blob
     int blocks = -1, in_planes = -1;                                                                     // shape the images above were allocated for
@@ -279,6 +287,7 @@ struct Net {
             if (dev_alloc(&w.b1x1, 64) || dev_alloc(&w.pfc_b, (size_t)p_tiles * 64) || dev_alloc(&w.vfc1_b, 256) || dev_alloc(&w.vfc2_w, 256) || dev_alloc(&w.vfc2_b, 1) ||
                 dev_alloc(&w.g1_w, nn::gemm_weight_elems(64, 3 * C)) || dev_alloc(&w.pfc_img, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat)) ||
                 dev_alloc(&w.vfc1_img, nn::gemm_weight_elems(256, 3 * feat)) || dev_alloc(&w.h1_w, nn::head_conv_weight_elems())) return -1;
+            if (!p_split && dev_alloc(&w.pfc_rows, (size_t)A * feat)) return -1;
             AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_img, 0, nn::gemm_weight_elems(p_tiles * 64, (p_split ? 3 : 1) * feat) * 2, st));      // rows >= A stay zero
             AZ_CUDA_CHECK(cudaMemsetAsync(w.pfc_b, 0, (size_t)p_tiles * 64 * 4, st));
             w.blocks = nb; w.in_planes = ip;
@@ -297,6 +306,7 @@ struct Net {
         k_prep_1x1<<<(64 * C + 255) / 256, 256, 0, st>>>(d + pcw, d + pbn, d + vcw, d + vbn, w.g1_w, w.b1x1, C, w.h1_w, f16);
         k_prep_fc<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_img, A, feat, p_split);
         k_prep_fc<<<(unsigned)(((size_t)256 * feat + 255) / 256), 256, 0, st>>>(d + v1w, w.vfc1_img, 256, feat, 1);
+        if (w.pfc_rows) k_prep_fc_rows<<<(unsigned)(((size_t)A * feat + 255) / 256), 256, 0, st>>>(d + pfw, w.pfc_rows, A, feat);
         AZ_CUDA_CHECK(cudaGetLastError());
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.pfc_b, d + pfb, (size_t)A * 4, cudaMemcpyDeviceToDevice, st));
         AZ_CUDA_CHECK(cudaMemcpyAsync(w.vfc1_b, d + v1b, 256 * 4, cudaMemcpyDeviceToDevice, st));
@@ -316,7 +326,7 @@ struct Net {
         w.conv_w.clear(); w.conv_b.clear();
         for (float** p : {&w.b1x1, &w.pfc_b, &w.vfc1_b, &w.vfc2_w, &w.vfc2_b, &w.blob, &w.zero_bias}) { cudaFree(*p); *p = nullptr; }
         w.blob_bytes = 0; w.blocks = -1; w.in_planes = -1;
-        for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img, &w.h1_w}) { cudaFree(*p); *p = nullptr; }
+        for (__nv_bfloat16** p : {&w.g1_w, &w.pfc_img, &w.vfc1_img, &w.h1_w, &w.pfc_rows}) { cudaFree(*p); *p = nullptr; }
         loaded = false;
     }
     void destroy() {
@@ -328,7 +338,9 @@ struct Net {
         for (void* p : {(void*)in16, (void*)X, (void*)Y, (void*)rowvalid, (void*)pooled, (void*)featP, (void*)featV, (void*)logits, (void*)hidden, (void*)logits_part, (void*)hidden_part}) cudaFree(p);
     }
     // in16 (already filled) → policy[n][A], value[n].  n from n_dev (device) or n_fixed.
-    int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s) {
+    // legal / n_legal (device, per evaluation slot) != nullptr on a wide head: logits of the legal moves only (k_policy_legal_value)
+    int forward(const int* n_dev, int n_fixed, float* policy, float* value, cudaStream_t s, const int16_t* legal = nullptr, const int32_t* n_legal = nullptr, int legal_pitch = 0,
+                const int32_t* slot_tree = nullptr) {
         static const bool alt_order = getenv("AZ_CONV_NO_ALT") == nullptr;      // profiling switch for the alternating item order
         static const bool pdl = getenv("AZ_CONV_NO_PDL") == nullptr;            // profiling switch for programmatic dependent launch of the trunk layers
         static const int conv_dbg = getenv("AZ_CONV_WEIGHTS_FIRST") ? 64 : 0;   // profiling switch: all nine weight taps ahead of the first activation stage
@@ -408,12 +420,20 @@ struct Net {
         nn::GemmParams g2{}; g2.A = featP; g2.B = w.pfc_img; g2.bias = w.pfc_b; g2.a_rows = boards_cap; g2.a_plane_mod = 512; g2.K = (p_split ? 3 : 1) * feat; g2.n_tiles = p_tiles; g2.n_valid = A;
         g2.units = 1; g2.unit_rows = 0; g2.m_valid_dev = n_dev; g2.m_valid = n_fixed; g2.relu = 0; g2.mode = nn::GEMM_OUT_ROWS; g2.out_rows = logits_part; g2.ldo = ld_part;
         g2.k_splits = p_splits; g2.split_stride = (size_t)max_boards * ld_part;
-        AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches;
+        const bool legal_only = legal != nullptr && w.pfc_rows != nullptr && feat == 2048;
+        if (!legal_only) { AZ_CHECK(nn::gemm_tc_launch(g2, n_sms, s) == 0, "policy fc gemm launch failed"); ++launches; }
         fe_rec(4, s);
         nn::GemmParams g3 = g2; g3.A = featV; g3.B = w.vfc1_img; g3.bias = w.vfc1_b; g3.K = 3 * feat; g3.n_tiles = 4; g3.n_valid = 256; g3.relu = 1; g3.out_rows = hidden_part; g3.ldo = 256;
         g3.k_splits = fc_splits; g3.split_stride = (size_t)max_boards * 256;
         AZ_CHECK(nn::gemm_tc_launch(g3, n_sms, s) == 0, "value fc gemm launch failed"); ++launches;
         fe_rec(5, s);
+        if (legal_only) {
+            nn::LegalPolicyParams lp{featP, boards_cap, 256, w.pfc_rows, w.pfc_b, legal, n_legal, legal_pitch, slot_tree, hidden_part, (size_t)max_boards * 256, fc_splits, w.vfc1_b, w.vfc2_w, w.vfc2_b, 256,
+                                     policy, value, n_dev, n_fixed, A};
+            AZ_CHECK(nn::policy_legal_value_launch(lp, max_boards, s) == 0, "legal policy launch failed"); ++launches;
+            fe_rec(6, s);
+            return 0;
+        }
         nn::OutParams op{logits_part, hidden_part, (size_t)max_boards * ld_part, (size_t)max_boards * 256, p_splits, fc_splits, w.pfc_b, w.vfc1_b, w.vfc2_w, w.vfc2_b, logits, policy, value, n_dev, n_fixed, A, 256, n_dev == nullptr ? 1 : 0, ld_part};
         AZ_CHECK(nn::policy_value_launch(op, max_boards, s) == 0, "output launch failed"); ++launches;
         fe_rec(6, s);
@@ -516,6 +536,7 @@ struct EngineT : EngineBase {
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
     struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; Net net; };
+    DupStats dup{};                               // AZ_EVAL_DUP_STATS (profiling): see tree.cuh
     EvalTT tt{};                                  // model of the reference's TranspositionTable (chess + hash evaluators, tree.cuh)
     bool hash_eval() const { return cfg.evaluator == AZ_EVAL_HASH || cfg.evaluator == AZ_EVAL_HASH_PEAKED; }
     az_config cfg;
@@ -543,6 +564,14 @@ struct EngineT : EngineBase {
 
     void destroy() {
         cudaDeviceSynchronize();
+        if (dup.counters) {
+            unsigned long long c[8] = {}; cudaMemcpy(c, dup.counters, 64, cudaMemcpyDeviceToHost);
+            const double ev = c[0] ? (double)c[0] : 1.0;
+            fprintf(stderr, "az eval-duplicate stats: %llu leaf evaluations; exact network input: %.3f %% duplicate inside their wave, %.3f %% seen before in the run; "
+                            "reference TT key: %.3f %% / %.3f %%; run-table inserts refused: %llu\n", c[0], 100.0 * c[1] / ev, 100.0 * c[2] / ev, 100.0 * c[3] / ev, 100.0 * c[4] / ev, c[5]);
+            for (void* p : {(void*)dup.wave_keys, (void*)dup.run_keys, (void*)dup.wave_keys_ref, (void*)dup.run_keys_ref, (void*)dup.counters}) cudaFree(p);
+            dup = DupStats{};
+        }
         if (wave_timing && wt_n) {
             fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
             fprintf(stderr, "  evaluator: stem %.3f, trunk %.3f, pool (or fused 1x1 conv + pool) %.3f, 1x1 gemm %.3f, policy fc %.3f, value fc %.3f, softmax/tanh %.3f ms\n", wt_fwd[0] / wt_n, wt_fwd[1] / wt_n,
@@ -550,7 +579,7 @@ struct EngineT : EngineBase {
         }
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
-                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key}) cudaFree(p);
+                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key, (void*)g.wb.legal, (void*)g.wb.n_legal, (void*)g.wb.slot_tree, (void*)g.wb.dd_keys, (void*)g.wb.dd_owner, (void*)g.wb.dd_idx}) cudaFree(p);
             g.net.destroy();
             if (g.ev) cudaEventDestroy(g.ev);
             if (g.stream) cudaStreamDestroy(g.stream);
@@ -617,6 +646,13 @@ struct EngineT : EngineBase {
             tt.cap = capn;
             if (dev_alloc(&tt.keys, (size_t)T * capn) || dev_alloc(&tt.vals, (size_t)T * capn) || dev_alloc(&tt.count, T)) return -1;
         }
+        if (getenv("AZ_EVAL_DUP_STATS")) {
+            dup.wave_mask = (1u << 20) - 1; dup.run_mask = (1u << 28) - 1;                 // 8 MB per wave set, 2 GB per run set
+            if (dev_alloc(&dup.wave_keys, (size_t)dup.wave_mask + 1) || dev_alloc(&dup.wave_keys_ref, (size_t)dup.wave_mask + 1) ||
+                dev_alloc(&dup.run_keys, (size_t)dup.run_mask + 1) || dev_alloc(&dup.run_keys_ref, (size_t)dup.run_mask + 1) || dev_alloc(&dup.counters, 8)) return -1;
+            AZ_CUDA_CHECK(cudaMemset(dup.run_keys, 0, ((size_t)dup.run_mask + 1) * 8)); AZ_CUDA_CHECK(cudaMemset(dup.run_keys_ref, 0, ((size_t)dup.run_mask + 1) * 8));
+            AZ_CUDA_CHECK(cudaMemset(dup.counters, 0, 64));
+        }
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
         const int per = (T + NG - 1) / NG;
@@ -637,6 +673,17 @@ struct EngineT : EngineBase {
             if (dev_alloc(&g.wb.path, (size_t)n * MAX_DEPTH) || dev_alloc(&g.wb.path_len, n) || dev_alloc(&g.wb.leaf_node, n) || dev_alloc(&g.wb.leaf_kind, n) ||
                 dev_alloc(&g.wb.leaf_value, n) || dev_alloc(&g.wb.policy, (size_t)n * A) || dev_alloc(&g.wb.value, n) || dev_alloc(&g.wb.eval_slot, n) ||
                 dev_alloc(&g.wb.n_eval, 1)) return -1;
+            if (G::LEGAL_POLICY && c.evaluator == AZ_EVAL_RESNET && !c.dense_policy) {
+                if (dev_alloc(&g.wb.legal, (size_t)n * MC) || dev_alloc(&g.wb.n_legal, n)) return -1;
+            }
+            if (c.evaluator == AZ_EVAL_RESNET) {
+                if (dev_alloc(&g.wb.slot_tree, n)) return -1;
+                if (c.eval_dedup >= 0) {
+                    unsigned int cap_dd = 1024; while (cap_dd < 4u * (unsigned)n) cap_dd <<= 1;
+                    g.wb.dd_mask = cap_dd - 1;
+                    if (dev_alloc(&g.wb.dd_keys, cap_dd) || dev_alloc(&g.wb.dd_owner, cap_dd) || dev_alloc(&g.wb.dd_idx, n)) return -1;
+                }
+            }
             if (tt.keys) {
                 if (dev_alloc(&g.wb.eval_key, n)) return -1;
                 g.tt = tt; g.tt.keys += (size_t)g.t0 * tt.cap; g.tt.vals += (size_t)g.t0 * tt.cap; g.tt.count += g.t0;
@@ -767,9 +814,17 @@ struct EngineT : EngineBase {
         const bool timed = wave_timing && (wt_seen++ % 64) == 63;
         if (timed) { for (auto& e : wt_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(wt_ev[0], st); }
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
+        if (g.wb.dd_keys) {
+            AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_keys, 0, ((size_t)g.wb.dd_mask + 1) * 8, st));
+            AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_owner, 0x7f, ((size_t)g.wb.dd_mask + 1) * 4, st));      // 0x7f7f7f7f > any tree index
+        }
+        if (dup.counters) {
+            AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys, 0, ((size_t)dup.wave_mask + 1) * 8, st));
+            AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys_ref, 0, ((size_t)dup.wave_mask + 1) * 8, st));
+        }
         typename G::EncTarget enc{nullptr, 0, 0, 0, 0};
         if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch, g.net.f16};
-        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode);
+        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode, dup);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) cudaEventRecord(wt_ev[1], st);
         if (hash_eval()) {
@@ -778,7 +833,11 @@ struct EngineT : EngineBase {
             AZ_LAUNCH_CHECK(); ++launches;
         } else {
             g.net.fe_on = timed;
-            if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st)) return -1;
+            if (g.wb.dd_keys) {
+                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats);
+                AZ_LAUNCH_CHECK(); ++launches;
+            }
+            if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st, g.wb.legal, g.wb.n_legal, MC, g.wb.slot_tree)) return -1;
             g.net.fe_on = false;
         }
         if (timed) cudaEventRecord(wt_ev[2], st);
@@ -1077,7 +1136,7 @@ struct EngineT : EngineBase {
         if (sync_all()) return -1;
         Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
         o->simulations = s.simulations; o->evaluations = s.evaluations; o->terminal_leaves = s.terminal_leaves; o->nodes_created = s.nodes_created;
-        o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped;
+        o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped; o->eval_shared = s.eval_shared;
         o->kernel_launches = launches + net_launches(); o->waves = waves;
         return 0;
     }
@@ -1227,7 +1286,7 @@ AZ_API void az_config_default(az_config* c) {
     c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
     c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
     c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
-    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1; c->net_precision = AZ_NET_FP16; c->tt_entries = 0;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1; c->net_precision = AZ_NET_FP16; c->tt_entries = 0; c->dense_policy = 0; c->eval_dedup = 0; c->reserved_ = 0;
 }
 
 AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }

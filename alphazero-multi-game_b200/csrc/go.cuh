@@ -29,6 +29,7 @@ struct Go {
     static constexpr int MAX_CHILDREN = CELLS + 1;     // pass + every cell
     static constexpr int SAMPLE_VISITS = CELLS + 1;    // visit counts by action, pass last
     static constexpr int PLANES = 8;
+    static constexpr bool LEGAL_POLICY = false;
     static constexpr bool TT_COARSE = false;          // the reference's TT key (stones + player + ko) covers the hash evaluator's input
     static constexpr bool FIRST_FILL = false;          // legal-move order is the same for every enumeration (QUIRK Go2)
     static constexpr int MAX_GAME_MOVES = 2 * CELLS;   // engine cap (the reference has none): the game is scored at this ply
@@ -427,6 +428,9 @@ struct Go {
         for (int i = lane; i < PLANES * CELLS; i += 32) { const int c = i / CELLS, a = i % CELLS; out[i] = feature(w.s.c, c, a % N, a / N, w.libs[a]); }
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
+    // profiling (AZ_EVAL_DUP_STATS): the 8 planes are functions of stones, side and ko point — the same key as the reference's TT (go_state.cpp:773-811)
+    __device__ static uint64_t w_input_key(Warp& w) { return key_core(w.s.c); }
+    __device__ static uint64_t w_ref_tt_key(Warp& w) { return key_core(w.s.c); }
     // training examples (az_engine_make_examples)
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {
         if (lane == 0) {

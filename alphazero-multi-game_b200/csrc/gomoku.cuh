@@ -26,6 +26,7 @@ struct Gomoku {
     static constexpr int ACTIONS = CELLS;          // length of the policy vector / visit-count vector
     static constexpr int MAX_CHILDREN = CELLS;
     static constexpr int SAMPLE_VISITS = CELLS;
+    static constexpr bool LEGAL_POLICY = false;       // narrow policy head: all A logits are computed
     static constexpr bool TT_COARSE = false;          // the reference's TT key (stones + player) covers the hash evaluator's input
     static constexpr bool FIRST_FILL = true;       // QUIRK G2: the first enumeration of a lineage has its own order
     static constexpr int MAX_GAME_MOVES = CELLS;
@@ -275,6 +276,10 @@ struct Gomoku {
         for (int i = lane; i < PLANES * CELLS; i += 32) { const int c = i / CELLS, a = i % CELLS; out[i] = feature(w.s, c, a / N, a % N); }
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key(w.s); }
+    // profiling (AZ_EVAL_DUP_STATS): key over the whole network input (stones, side, the six history moves of planes 3-8) and over what the
+    // reference's TranspositionTable distinguishes (stones + side, gomoku_state.cpp:620-656)
+    __device__ static uint64_t w_input_key(Warp& w) { uint64_t h = key(w.s); for (int i = 0; i < 6; ++i) h = mix64(h ^ (uint64_t)(uint16_t)w.s.last[i]); return h; }
+    __device__ static uint64_t w_ref_tt_key(Warp& w) { return key(w.s); }
     // training examples (az_engine_make_examples): state from a sample's snapshot, plane value at tensor index [c][i][j], dense policy
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) { w_load(w, g, lane); }
     __device__ static float tensor_value(Warp& w, int c, int i, int j) { return feature(w.s, c, i, j); }

@@ -54,6 +54,13 @@ struct WaveBuffers {
     float* value;        // [T]
     int32_t* eval_slot;  // [T] compacted NN batch index of this tree's leaf, -1 = none
     int32_t* n_eval;     // [1] number of leaves that need an evaluation this wave
+    int16_t* legal;      // [T][MAX_CHILDREN] wide policy heads (chess): the leaf's legal actions in child order, by TREE; else nullptr
+    int32_t* n_legal;    // [T]
+    int32_t* slot_tree;  // [T] evaluation slot → the tree whose leaf it holds
+    // in-wave evaluation dedup (M16, the TranspositionTable's role inside one wave): leaves of different trees with the SAME network input
+    // share one evaluation.  dd_keys / dd_owner: open-addressing set of the wave's input keys [dd_mask + 1] (cleared every wave), owner =
+    // the smallest tree index with that key; dd_idx[t] = the tree's entry.  nullptr = off.
+    unsigned long long* dd_keys; int32_t* dd_owner; int32_t* dd_idx; unsigned int dd_mask;
     uint64_t* eval_key;  // [T] hash evaluators + EvalTT: the key the leaf is evaluated under (its own, or the first-seen position's); else nullptr
 };
 
@@ -66,6 +73,26 @@ struct WaveBuffers {
 // input: their tables are result-transparent and not materialised.
 struct EvalTT { uint64_t* keys; uint64_t* vals; int32_t* count; int32_t cap; };
 
+// AZ_EVAL_DUP_STATS (profiling only): how many leaf evaluations an evaluation cache could have skipped.  Two open-addressing key sets per
+// key flavour — one cleared every wave ("another tree evaluates the same input in this wave"), one kept for the whole run ("this input was
+// evaluated before, in any tree, any game") — for (a) the exact network input and (b) the reference TranspositionTable's key.
+struct DupStats {
+    unsigned long long* wave_keys; unsigned long long* run_keys; unsigned long long* wave_keys_ref; unsigned long long* run_keys_ref;
+    unsigned int wave_mask, run_mask;
+    unsigned long long* counters;      // [0] evaluations, [1] duplicate of the wave (input), [2] seen before in the run (input), [3] / [4] the same for the reference key, [5] run-table inserts refused (full)
+};
+__device__ __forceinline__ bool dup_probe_insert(unsigned long long* keys, unsigned int mask, unsigned long long k, bool* full) {
+    if (k == 0) k = 1;
+    unsigned int i = (unsigned int)mix64(k) & mask;
+    for (int probe = 0; probe < 64; ++probe, i = (i + 1) & mask) {
+        const unsigned long long old = atomicCAS(&keys[i], 0ULL, k);
+        if (old == 0ULL) return false;          // inserted: not seen before
+        if (old == k) return true;
+    }
+    if (full) *full = true;
+    return false;
+}
+
 struct SearchParams {
     float c_puct;        // MCTSConfig::cPuct (1.5)
     int virtual_loss;    // MCTSConfig::virtualLoss (3)
@@ -74,7 +101,7 @@ struct SearchParams {
 
 struct Stats {           // mirrors mcts::MCTSStats (parallel_mcts.h:77-99) + engine counters
     unsigned long long simulations, evaluations, terminal_leaves, nodes_created, nodes_expanded,
-        pool_overflows, moves, games, samples_dropped;
+        pool_overflows, moves, games, samples_dropped, eval_shared;   // eval_shared: leaf evaluations served by another tree's evaluation of the same input in the same wave
 };
 
 }  // namespace az

@@ -33,7 +33,7 @@ constexpr size_t warp_ws_bytes(int extra_bytes_per_warp = 0) { return 4 * ((size
 template <class G>
 __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
                                                typename G::Leaf* __restrict__ leaf_state, WaveBuffers wb,
-                                               SearchParams sp, typename G::EncTarget enc, EvalTT tt, int T, int mode) {
+                                               SearchParams sp, typename G::EncTarget enc, EvalTT tt, int T, int mode, DupStats ds) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,9 +110,26 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
         }
     }
     int slot = -1;
+    const bool dedup = wb.dd_keys != nullptr;
     if (kind == LEAF_EVAL) {
-        if (lane == 0) slot = atomicAdd(wb.n_eval, 1);
-        slot = warp_bcast(slot, 0);
+        if (dedup) {
+            // register the leaf's network input in the wave's key set; slots are handed out, and the planes written, by k_dedup_encode
+            const uint64_t ki = G::w_input_key(w);
+            if (lane == 0) {
+                unsigned long long k = ki ? ki : 1ULL;
+                unsigned int i = (unsigned int)mix64(k) & wb.dd_mask;
+                while (true) {
+                    const unsigned long long old = atomicCAS(&wb.dd_keys[i], 0ULL, k);
+                    if (old == 0ULL || old == k) break;
+                    i = (i + 1) & wb.dd_mask;                       // the set has 4 x T entries: always terminates
+                }
+                atomicMin(&wb.dd_owner[i], t);
+                wb.dd_idx[t] = (int32_t)i;
+            }
+        } else {
+            if (lane == 0) { slot = atomicAdd(wb.n_eval, 1); if (wb.slot_tree) wb.slot_tree[slot] = t; }
+            slot = warp_bcast(slot, 0);
+        }
         if constexpr (G::TT_COARSE) {
             // TranspositionTable lookup / store of the reference (parallel_mcts.cpp:153-163 for the root, :316-358 for a leaf): the table
             // key is the placement; a hit evaluates under the first-seen position's key.  One simulation per tree per wave keeps the
@@ -141,8 +158,53 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
     }
     if (kind == LEAF_EVAL) {
         G::w_store_leaf(w, leaf_state + t, lane);
-        if (enc.ptr != nullptr) G::w_encode(w, lane, enc, slot);
+        if (enc.ptr != nullptr && !dedup) G::w_encode(w, lane, enc, slot);
+        if (ds.counters != nullptr) {
+            const uint64_t ki = G::w_input_key(w), kr = G::w_ref_tt_key(w);
+            if (lane == 0) {
+                bool full = false;
+                atomicAdd(&ds.counters[0], 1ULL);
+                if (dup_probe_insert(ds.wave_keys, ds.wave_mask, ki, nullptr)) atomicAdd(&ds.counters[1], 1ULL);
+                if (dup_probe_insert(ds.run_keys, ds.run_mask, ki, &full)) atomicAdd(&ds.counters[2], 1ULL);
+                if (dup_probe_insert(ds.wave_keys_ref, ds.wave_mask, kr, nullptr)) atomicAdd(&ds.counters[3], 1ULL);
+                if (dup_probe_insert(ds.run_keys_ref, ds.run_mask, kr, &full)) atomicAdd(&ds.counters[4], 1ULL);
+                if (full) atomicAdd(&ds.counters[5], 1ULL);
+            }
+        }
+        if constexpr (G::LEGAL_POLICY) {
+            // wide policy head: the network computes the logits of the leaf's legal moves only (heads.cu k_policy_legal_value).  The leaf's
+            // terminal test (w_result) has just enumerated them; the root-expansion wave does it here
+            if (wb.legal != nullptr) {
+                const int n = G::w_store_legal(w, lane, wb.legal + (size_t)t * G::MAX_CHILDREN, mode == 1);
+                if (lane == 0) wb.n_legal[t] = n;
+            }
+        }
     }
+}
+
+// In-wave evaluation dedup, second half: the owner of every distinct network input (the smallest tree index that registered it) takes an
+// evaluation slot and writes its feature planes; every other tree with that input points at the owner.  Result-transparent: the
+// network output of a board does not depend on its position in the batch (tests/test_nn_gpu.py), so sharing the owner's policy / value
+// is bit-identical to evaluating the duplicate.
+template <class G>
+__global__ void __launch_bounds__(128) k_dedup_encode(const typename G::Leaf* __restrict__ leaf_state, const typename G::State* __restrict__ root_state,
+                                                     WaveBuffers wb, typename G::EncTarget enc, int T, Stats* stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    if (wb.leaf_kind[t] != LEAF_EVAL) return;
+    const int owner = wb.dd_owner[wb.dd_idx[t]];
+    if (owner != t) {
+        if (lane == 0) { wb.eval_slot[t] = -2 - owner; atomicAdd(&stats->eval_shared, 1ULL); }
+        return;
+    }
+    typename G::Warp& w = warp_ws<G>(smem);
+    int slot = 0;
+    if (lane == 0) { slot = atomicAdd(wb.n_eval, 1); wb.eval_slot[t] = slot; if (wb.slot_tree) wb.slot_tree[slot] = t; }
+    slot = warp_bcast(slot, 0);
+    G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
+    G::w_encode(w, lane, enc, slot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,7 +277,8 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     int n_new = 0;                                      // children created by this simulation: added to every path node's descendant count
 
     if (kind == LEAF_EVAL) {
-        const int slot = wb.eval_slot[t];
+        int slot = wb.eval_slot[t];
+        if (slot <= -2) slot = wb.eval_slot[-2 - slot];      // in-wave dedup: the owner's evaluation of the same network input
         const float* pol = wb.policy + (size_t)slot * A;
         v = wb.value[slot];
         G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
@@ -224,7 +287,12 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         const int alloc = tp.alloc[t];
         // children = the legal moves in the reference's order, priors = policy[action] (0 for out-of-range actions, i.e.
         // Go's pass at -1), expandNodeWithPolicy parallel_mcts.cpp:690-711
-        const int n = G::w_enumerate(w, lane, first_fill ? root_order + (size_t)t * MC : nullptr, first_fill ? root_order_n[t] : 0, acts, raw, pol);
+        int n;
+        if constexpr (G::LEGAL_POLICY) {
+            // the selection kernel already enumerated this leaf's legal moves for the policy head: no second move generation
+            if (wb.legal != nullptr) n = G::w_enumerate_pre(lane, wb.legal + (size_t)t * MC, wb.n_legal[t], acts, raw, pol);
+            else n = G::w_enumerate(w, lane, nullptr, 0, acts, raw, pol);
+        } else n = G::w_enumerate(w, lane, first_fill ? root_order + (size_t)t * MC : nullptr, first_fill ? root_order_n[t] : 0, acts, raw, pol);
         if (alloc + n > tp.limit[t]) {
             if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         } else if (n > 0) {

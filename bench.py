@@ -42,8 +42,10 @@ def flops(c):
     cells = c["board"] * c["board"]
     conv = cells * 9 * 128 * 128 * 2
     ns = c["channels"] // 128
+    # policy FC: all A logits, except on the wide chess head, where the waves compute the legal moves' logits only (~35 per position)
+    policy_fc = 2048 * (c["actions"] if c["actions"] <= 1024 else 35) * 2
     net = (cells * 9 * c["planes"] * c["channels"] * 2 + 2 * c["blocks"] * ns * ns * conv + 2 * (64 * c["channels"] * 32 * 2)
-           + 2048 * c["actions"] * 2 + 2048 * 256 * 2 + 512)
+           + policy_fc + 2048 * 256 * 2 + 512)
     return conv, net
 
 
@@ -236,7 +238,9 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     ms_max = allreduce(ms, dist.ReduceOp.MAX) if dist else ms
     n_sims = allreduce(float(s1["simulations"] - s0["simulations"]), dist.ReduceOp.SUM) if dist else float(s1["simulations"] - s0["simulations"])
     moves = allreduce(float(s1["moves"] - s0["moves"]), dist.ReduceOp.SUM) if dist else float(s1["moves"] - s0["moves"])
-    evals = float(s1["evaluations"] - s0["evaluations"])
+    leaf_evals = float(s1["evaluations"] - s0["evaluations"])
+    shared = float(s1["eval_shared"] - s0["eval_shared"])             # leaves served by another tree's evaluation of the same input in the same wave
+    evals = leaf_evals - shared                                        # network evaluations actually run (what the FLOP accounting uses)
     launches = int(s1["kernel_launches"] - s0["kernel_launches"])
     value = n_sims / (ms_max / 1e3)
 
@@ -337,6 +341,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     out = {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
            "config": workload_config(c, args, world, slots, sims),
            "moves_per_sec": moves / (ms_max / 1e3), "nn_evals_per_sec_rank0": evals / (ms / 1e3),
+           "eval_shared_frac_rank0": shared / max(leaf_evals, 1.0),
            "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * net_flop / 1e12 / pk["bf16_sustained"],
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
            "games_finished": int(e1["games"]), "samples_dropped": int(e1["samples_dropped"]), "pool_overflows": int(e1["pool_overflows"])}
@@ -384,7 +389,7 @@ def main():
     if args.game == "gomoku15" and args.slots is None and args.sims is None:
         for k in [x for x in args.others.split(",") if x]:
             o = measure(k, args, max(args.other_steps, 5), 3 if k != "go19" else 2, max(args.other_steps, 5) if k != "go19" else 3, rank, world, local, dist)
-            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "tensor_roofline_frac_in_step", "e2e",
+            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "e2e",
                                               "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")}
             others[k]["roofline"] = {kk: o["roofline"][kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launch_ms", "launch_ms_source", "whole_net_ms", "whole_net_tflops")}
     overflow = head["pool_overflows"] + sum(o["pool_overflows"] for o in others.values())
@@ -394,7 +399,7 @@ def main():
                 "dtype": args.precision, "dtype_note": "16-bit tensor-core operands (tcgen05 kind::f16), fp32 accumulation; fp16 is the reference's own half-precision mode "
                                                        "(TorchNeuralNetworkConfig::useFp16) and meets the KL <= 1e-3 tolerance on the BASELINE network; --precision bf16 runs the bf16 storage at the same rate",
                 "data": "synthetic"}
-        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "tensor_roofline_frac_in_step", "roofline", "cpu_baseline", "e2e",
+        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "roofline", "cpu_baseline", "e2e",
                                           "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")})
         line["other_configs"] = others
         if overflow:

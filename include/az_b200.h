@@ -71,7 +71,13 @@ typedef struct az_config {
                                    (keyed by the piece placement, QUIRK C8: a leaf whose placement was evaluated before in the game gets that
                                    position's evaluation, src/mcts/parallel_mcts.cpp:320-336).  0 = default (on, sized from num_simulations),
                                    -1 = off (every leaf evaluated on its own input) */
+    int32_t eval_dedup;         /* ResNet evaluator: 0 = default (on): leaves of different trees that present the SAME network input in the same wave
+                                   share one evaluation (the role of the reference's TranspositionTable — an evaluation cache, M16 — inside one wave;
+                                   result-transparent: bit-identical searches with it on or off); -1 = off */
     int32_t reserved_;
+    int32_t dense_policy;       /* wide policy heads (chess, 20480 actions): 0 = inside the waves the network computes the logits of the leaf's
+                                   legal moves only (their softmax equals the full softmax renormalised over the legal moves, which is what the
+                                   expansion computes, parallel_mcts.cpp:705-724); 1 = all A logits + the full softmax, as az_engine_nn_forward does */
 } az_config;
 
 /* mcts::MCTSStats (include/alphazero/mcts/parallel_mcts.h:77-99) + engine counters, cumulative */
@@ -80,6 +86,8 @@ typedef struct az_stats {
              moves, games, samples_dropped;
     uint64_t kernel_launches;   /* CUDA kernels this engine has launched */
     uint64_t waves;
+    uint64_t eval_shared;       /* leaf evaluations served by another tree's evaluation of the same network input in the same wave (MCTSStats::cacheHits);
+                                   network evaluations actually run = evaluations - eval_shared */
 } az_stats;
 
 typedef struct az_engine az_engine;

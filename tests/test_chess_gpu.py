@@ -196,3 +196,44 @@ def test_chess_search_without_table_model_matches_tt_free_oracle():
         O.mcts_update_with_move(off, act); O.mcts_update_with_move(on, act); eng.advance([act])
     assert differed
     eng.close()
+
+
+def test_chess_legal_only_policy_equals_dense_softmax():
+    """Inside the waves the chess network computes the logits of the leaf's LEGAL moves only (one 2048-long dot product per legal move
+    instead of the 20480 x 2048 policy FC + a 20480-wide softmax): softmax over all A followed by the expansion's renormalisation over
+    the legal moves is the softmax over the legal logits.  Root priors of the legal-only engine vs (a) the dense engine
+    (dense_policy = 1: all logits, full softmax, renormalised at expansion) and (b) the fp32 PyTorch network: KL <= 1e-3 (north-star
+    tolerance), in practice ~1e-6."""
+    import torch
+    from _eng import E, N
+    O = _orc.oracle()
+    m = N.make_random_model(seed=2, randomize_bn=True, blocks=3, in_planes=18, board=8, actions=20480)
+    gen = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        m.p_fc.weight *= 0.2; m.v_fc1.weight *= 0.05; m.v_fc2.weight *= 0.2
+        m.p_fc.bias.copy_(torch.rand(m.p_fc.bias.shape, generator=gen) - 0.5)
+    blob = N.export_weights(m)
+    games = _random_games(O, 6, 60, seed=21)
+    roots = [[]] + [g[:k] for g, k in zip(games, (5, 12, 20, 33, 41, 58))]
+    stats = []
+    for dense in (0, 1):
+        eng = E.Engine(game=E.CHESS, board_size=8, n_slots=len(roots), evaluator=E.EVAL_RESNET, net_blocks=3, num_simulations=4, deterministic=1,
+                       auto_restart=0, max_nodes_per_tree=4096, dense_policy=dense)
+        eng.load_weights(blob)
+        for t, mv in enumerate(roots):
+            eng.set_root(t, mv)
+        eng.search(4)
+        stats.append([eng.root_stats(t) for t in range(len(roots))])
+        eng.close()
+    for t, mv in enumerate(roots):
+        a, b = stats[0][t], stats[1][t]
+        assert np.array_equal(a["actions"], b["actions"]) and len(a["actions"]) > 0
+        assert np.allclose(a["P"], b["P"], rtol=2e-3, atol=1e-6), (t, np.abs(a["P"] - b["P"]).max())
+        s = O.new_state(CHESS, 8)
+        for x in mv:
+            assert O.state_make_move(s, x) == 0
+        with torch.no_grad():
+            lg, _ = m(torch.tensor(O.tensor(s)[None]))
+        ref = torch.softmax(lg[0, torch.tensor(a["actions"].astype(np.int64))], 0).numpy()
+        kl = float((ref * (np.log(ref + 1e-30) - np.log(a["P"] + 1e-30))).sum())
+        assert kl <= 1e-3, (t, kl)

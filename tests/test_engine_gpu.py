@@ -341,3 +341,48 @@ def test_advisor_regressions_groups_order_drain():
     assert len(first) + len(rest) >= st["games"] and len(rest) > 0         # nothing was thrown away by the short drain
     assert not set(zip(first["game_id"].tolist(), first["slot"].tolist(), first["ply"].tolist())) & set(zip(rest["game_id"].tolist(), rest["slot"].tolist(), rest["ply"].tolist()))
     eng.close()
+
+
+@pytest.mark.parametrize("game,board", [(GOMOKU, 15), (_orc.GO, 9), (_orc.CHESS, 8)])
+def test_in_wave_eval_dedup_is_result_transparent(game, board):
+    """In-wave evaluation dedup (the TranspositionTable's role, M16, inside one wave): trees whose leaves present the same network input in
+    the same wave share ONE ResNet evaluation.  The network output of a board does not depend on its batch position, so the searches are
+    bit-identical with the dedup on and off — same child order, visit counts, valueSum and prior bits on every slot over several moves
+    (slots 0-5 play the same game, so most of their leaves are shared; the others start from different openings)."""
+    from _eng import E, N
+    O = _orc.oracle()
+    planes, actions = {GOMOKU: (11, board * board), _orc.GO: (8, board * board + 1), _orc.CHESS: (18, 20480)}[game]
+    m = N.make_random_model(seed=4, randomize_bn=True, blocks=2, in_planes=planes, board=board, actions=actions)
+    blob = N.export_weights(m)
+    rng = np.random.default_rng(3)
+    openings = [[] for _ in range(6)]
+    for _ in range(6):
+        s = O.new_state(game, board); mv = []
+        for _ in range(int(rng.integers(1, 12))):
+            lg = O.legal(s)
+            a = int(rng.choice(lg[lg >= 0] if game == _orc.GO else lg))
+            O.state_make_move(s, a); mv.append(a)
+        openings.append(mv)
+    out = []
+    for dedup in (0, -1):
+        eng = E.Engine(game=game, board_size=board, n_slots=len(openings), evaluator=E.EVAL_RESNET, net_blocks=2, num_simulations=48, deterministic=1,
+                       auto_restart=0, eval_dedup=dedup)
+        eng.load_weights(blob)
+        for t, mv in enumerate(openings):
+            eng.set_root(t, mv)
+        res = []
+        for move in range(3):
+            eng.search()
+            res.append([eng.root_stats(t) for t in range(len(openings))])
+            eng.advance([int(r["actions"][int(np.argmax(r["N"]))]) if len(r["N"]) else -2 for r in res[-1]])      # (-2: the game in this slot is over — Go: two passes)
+        st = eng.stats()
+        out.append((res, st))
+        eng.close()
+    (on, st_on), (off, st_off) = out
+    assert st_on["eval_shared"] > 0 and st_off["eval_shared"] == 0 and st_on["evaluations"] == st_off["evaluations"]
+    assert st_on["eval_shared"] >= st_on["evaluations"] // 3                    # six identical games: at least 5/12 of the leaves are shared
+    for move in range(3):
+        for t in range(len(openings)):
+            a, b = on[move][t], off[move][t]
+            assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, t)
+            assert np.array_equal(a["W"].view(np.uint32), b["W"].view(np.uint32)) and np.array_equal(a["P"].view(np.uint32), b["P"].view(np.uint32)), (move, t)
