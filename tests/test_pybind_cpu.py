@@ -221,3 +221,24 @@ def test_self_play_command_help_and_loud_failure_without_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--model", "hash", "--num-games", "1", "--output-dir", "/tmp/az_sp_none"], capture_output=True, text=True)
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_python_caller_clis_accept_the_reference_arguments():
+    """scripts/self_play.py and scripts/orchestrate_selfplay.py take every option of the reference's drivers
+    (python/scripts/self_play.py:76-136, python/scripts/orchestrate_selfplay.py:92-160), with the reference's defaults."""
+    sys.path.insert(0, os.path.join(PKG, "scripts"))
+    import self_play as sp
+    import orchestrate_selfplay as orch
+    a = sp.parse_args(["--model", "m.azw", "--game", "go", "--size", "9", "--num-games", "7", "--simulations", "50", "--threads", "3", "--output-dir", "o",
+                       "--temperature", "0.8", "--temp-drop", "12", "--final-temp", "0.1", "--dirichlet-alpha", "0.3", "--dirichlet-epsilon", "0.2", "--seed", "5",
+                       "--batch-size", "32", "--batch-timeout", "7", "--no-batched-search", "--fp16", "--create-random-model", "--fpu-reduction", "0.2",
+                       "--c-puct", "2.0", "--virtual-loss", "2", "--use-transposition-table", "--progressive-widening", "--profile"])
+    assert (a.game, a.size, a.num_games, a.simulations, a.temp_drop, a.c_puct, a.virtual_loss) == ("go", 9, 7, 50, 12, 2.0, 2)
+    d = sp.parse_args([])
+    assert (d.game, d.num_games, d.simulations, d.output_dir, d.temperature, d.temp_drop, d.final_temp, d.dirichlet_alpha, d.dirichlet_epsilon, d.fpu_reduction,
+            d.c_puct, d.virtual_loss) == ("gomoku", 100, 800, "data/games", 1.0, 30, 0.0, 0.03, 0.25, 0.1, 1.5, 3)
+    o = orch.parse_args(["--processes", "4", "--model", "x", "--monitor-interval", "2", "--use-cpp-binary", "--no-tt", "--optimize-batch", "--cache-size", "1024",
+                         "--optimize-threads", "--compact-size", "3", "--pin-threads", "--batch-size", "8", "--batch-timeout", "5"])
+    assert o.processes == 4 and o.use_cpp_binary and o.batch_size == 8
+    od = orch.parse_args([])
+    assert (od.processes, od.batch_size, od.batch_timeout, od.monitor_interval, od.cache_size) == (1, 16, 10, 5, 2097152)

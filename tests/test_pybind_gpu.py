@@ -291,3 +291,31 @@ def test_selfplay_manager_over_two_gpus_nccl():
         mgr = az.SelfPlayManager(net, 6, 16, 1); mgr.setConcurrentGames(8); mgr.setDevices([0, 1])
         gs = mgr.generateGames(az.GameType.GOMOKU, 9, False)
         assert len(gs) == 6 and all(len(g.getMoves()) >= 5 and g.getResult() != az.GameResult.ONGOING for g in gs)
+
+
+def test_python_self_play_driver_and_orchestrator(tmp_path):
+    """scripts/self_play.py (the reference's python/scripts/self_play.py flow: createNeuralNetwork → SelfPlayManager → setMctsConfig(dict) → progress
+    callback → GameRecord files + metadata JSON with the reference's keys) and scripts/orchestrate_selfplay.py (per-process output layout, summary)."""
+    import json, subprocess, sys
+    scripts = os.path.join(ROOT, "alphazero-multi-game_b200", "scripts")
+    out = tmp_path / "py"
+    r = subprocess.run([sys.executable, os.path.join(scripts, "self_play.py"), "--model", "hash", "--game", "gomoku", "--size", "9", "--num-games", "3", "--simulations", "24",
+                        "--slots", "3", "--output-dir", str(out), "--threads", "2", "--batch-size", "16", "--seed", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Self-play finished." in r.stdout and "Progress:" in r.stdout
+    files = sorted(os.listdir(out))
+    meta = [f for f in files if f.startswith("metadata_")]
+    assert len([f for f in files if not f.startswith("metadata_")]) == 3 and len(meta) == 1
+    m = json.loads((out / meta[0]).read_text())
+    ref_keys = ["timestamp", "game", "board_size", "num_games_requested", "num_games_completed", "simulations", "threads", "temperature", "temp_drop", "final_temp",
+                "dirichlet_alpha", "dirichlet_epsilon", "variant", "model_path_arg", "total_moves", "avg_moves_per_game", "total_time_seconds", "avg_time_per_game_seconds",
+                "avg_moves_per_second", "use_gpu", "fp16_used", "batch_size_used", "batch_timeout_used", "seed", "nn_loaded", "nn_avg_inference_ms", "nn_device_info",
+                "nn_batch_size", "nn_batch_timeout", "nn_fp16_enabled", "fpu_reduction", "c_puct", "virtual_loss", "use_transposition_table", "progressive_widening"]
+    assert list(m)[:len(ref_keys)] == ref_keys and m["num_games_completed"] == 3
+    out2 = tmp_path / "orch"
+    r = subprocess.run([sys.executable, os.path.join(scripts, "orchestrate_selfplay.py"), "--model", "hash", "--game", "gomoku", "--size", "9", "--num-games", "2",
+                        "--simulations", "16", "--processes", "1", "--output-dir", str(out2), "--monitor-interval", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert os.path.isdir(out2 / "proc_0") and any(f.startswith("orchestration_summary_") for f in os.listdir(out2))
+    s = json.loads(r.stdout.strip().splitlines()[-1])
+    assert s["total_games"] == 2 and s["return_code"] == 0
