@@ -370,7 +370,7 @@ struct Net {
             return 0;
         };
         fe_rec(0, s);
-        const bool sample = !fe_on && n_dev != nullptr && blocks > 0 && (fwd_count++ % 64) == 63;
+        const bool sample = false;      // (live trunk timing now comes from the wave-timing events of EngineT::wave)
         if (conv_stream && blocks > 0) { AZ_CUDA_CHECK(cudaEventRecord(ev_in, s)); AZ_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_in, 0)); }
         if (sample) { for (auto& e : tev) if (!e) cudaEventCreate(&e); cudaEventRecord(tev[0], cs); }
         static const bool trunk_fused = getenv("AZ_TRUNK_LAYERED") == nullptr;    // default: the whole trunk as one persistent launch (k_trunk_pair) where it applies
@@ -496,6 +496,8 @@ struct EngineBase {
     int device = 0;                 // every C-ABI call makes this the calling thread's current device (engines on several GPUs in one process)
     virtual ~EngineBase() {}
     virtual int set_search_params(float c_puct, int virtual_loss) = 0;
+    virtual int get_timing(az_timing* out) = 0;
+    virtual int set_external(az_eval_fn fn, void* user) = 0;
     virtual int node_stats(int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n,
                            int32_t* node_visits, float* node_wsum, float* node_prior, int32_t* node_flags) = 0;
     virtual int load_weights(const void* blob, size_t bytes) = 0;
@@ -536,6 +538,10 @@ struct EngineT : EngineBase {
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
     struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; Net net; };
+    // AZ_EVAL_EXTERNAL: the caller's evaluator + staging (device: leaf paths by evaluation slot; host: the same + its answers)
+    az_eval_fn ext_fn = nullptr; void* ext_user = nullptr;
+    int32_t *ext_paths = nullptr, *ext_plen = nullptr, *ext_slot_tree = nullptr;
+    std::vector<int32_t> h_paths, h_plen, h_slot; std::vector<float> h_policy, h_value;
     DupStats dup{};                               // AZ_EVAL_DUP_STATS (profiling): see tree.cuh
     EvalTT tt{};                                  // model of the reference's TranspositionTable (chess + hash evaluators, tree.cuh)
     bool hash_eval() const { return cfg.evaluator == AZ_EVAL_HASH || cfg.evaluator == AZ_EVAL_HASH_PEAKED; }
@@ -573,7 +579,8 @@ struct EngineT : EngineBase {
             dup = DupStats{};
         }
         if (wave_timing && wt_n) {
-            fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, evaluator %.3f ms, expand/backup %.3f ms\n", wt_n, wt_ms[0] / wt_n, wt_ms[1] / wt_n, wt_ms[2] / wt_n);
+            fprintf(stderr, "az wave timing over %ld sampled waves: select %.3f ms, dedup + encode %.3f ms, evaluator %.3f ms, expand/backup %.3f ms; move commit %.3f ms over %ld moves\n", wt_n, wt_ms[0] / wt_n,
+                    wt_ms[1] / wt_n, wt_ms[2] / wt_n, wt_ms[3] / wt_n, cm_n ? cm_ms / cm_n : 0.0, cm_n);
             fprintf(stderr, "  evaluator: stem %.3f, trunk %.3f, pool (or fused 1x1 conv + pool) %.3f, 1x1 gemm %.3f, policy fc %.3f, value fc %.3f, softmax/tanh %.3f ms\n", wt_fwd[0] / wt_n, wt_fwd[1] / wt_n,
                     wt_fwd[2] / wt_n, wt_fwd[3] / wt_n, wt_fwd[4] / wt_n, wt_fwd[5] / wt_n, wt_fwd[6] / wt_n);
         }
@@ -593,7 +600,7 @@ struct EngineT : EngineBase {
                         (void*)kept, (void*)plan,
                         (void*)root_state, (void*)leaf_state, (void*)root_order, (void*)default_order, (void*)root_order_n, (void*)chosen_child,
                         (void*)chosen_action, (void*)forced, (void*)game_buf, (void*)ring, (void*)ring_count, (void*)noise_scratch, (void*)dstats,
-                        (void*)tt.keys, (void*)tt.vals, (void*)tt.count})
+                        (void*)tt.keys, (void*)tt.vals, (void*)tt.count, (void*)ext_paths, (void*)ext_plen, (void*)ext_slot_tree})
             cudaFree(p);
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
@@ -646,6 +653,10 @@ struct EngineT : EngineBase {
             tt.cap = capn;
             if (dev_alloc(&tt.keys, (size_t)T * capn) || dev_alloc(&tt.vals, (size_t)T * capn) || dev_alloc(&tt.count, T)) return -1;
         }
+        if (c.evaluator == AZ_EVAL_EXTERNAL) {
+            if (dev_alloc(&ext_paths, (size_t)T * MAX_DEPTH) || dev_alloc(&ext_plen, T) || dev_alloc(&ext_slot_tree, T)) return -1;
+            h_paths.resize((size_t)T * MAX_DEPTH); h_plen.resize(T); h_slot.resize(T); h_policy.resize((size_t)T * A); h_value.resize(T);
+        }
         if (getenv("AZ_EVAL_DUP_STATS")) {
             dup.wave_mask = (1u << 20) - 1; dup.run_mask = (1u << 28) - 1;                 // 8 MB per wave set, 2 GB per run set
             if (dev_alloc(&dup.wave_keys, (size_t)dup.wave_mask + 1) || dev_alloc(&dup.wave_keys_ref, (size_t)dup.wave_mask + 1) ||
@@ -655,6 +666,7 @@ struct EngineT : EngineBase {
         }
         AZ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         NG = std::max(1, std::min(c.n_streams > 0 ? c.n_streams : 1, T));
+        if (c.evaluator == AZ_EVAL_EXTERNAL) NG = 1;
         const int per = (T + NG - 1) / NG;
         NG = (T + per - 1) / per;                       // groups of `per` slots; a count that does not divide T leaves no empty trailing group
         groups.resize(NG);
@@ -807,11 +819,19 @@ struct EngineT : EngineBase {
 
     // one wave of one group: select → evaluator → expand/backup, on the group's stream
     // AZ_WAVE_TIMING=1 (profiling): CUDA events around select / evaluator / expand of every 64th wave, printed at destroy
+    // Every 64th wave of a ResNet engine is bracketed kernel by kernel with CUDA events on its stream (one host sync per 64 waves): the
+    // per-step budget bench.py reports (az_engine_get_timing) and the live trunk time of its roofline.  AZ_WAVE_TIMING=1 also prints it.
     bool wave_timing = getenv("AZ_WAVE_TIMING") != nullptr;
-    cudaEvent_t wt_ev[4] = {}; double wt_ms[3] = {0, 0, 0}, wt_fwd[7] = {0, 0, 0, 0, 0, 0, 0}; long wt_n = 0, wt_seen = 0;
+    cudaEvent_t wt_ev[5] = {}; double wt_ms[4] = {0, 0, 0, 0}, wt_fwd[7] = {0, 0, 0, 0, 0, 0, 0}; long wt_n = 0, wt_seen = 0;
+    cudaEvent_t cm_ev[2] = {}; bool cm_pending = false; double cm_ms = 0; long cm_n = 0;
+    void resolve_commit_timing() {
+        if (!cm_pending || cudaEventQuery(cm_ev[1]) != cudaSuccess) return;
+        float ms = 0; if (cudaEventElapsedTime(&ms, cm_ev[0], cm_ev[1]) == cudaSuccess) { cm_ms += ms; ++cm_n; }
+        cm_pending = false;
+    }
     int wave(Group& g, int mode) {
         cudaStream_t st = g.stream;
-        const bool timed = wave_timing && (wt_seen++ % 64) == 63;
+        const bool timed = (wave_timing || cfg.evaluator == AZ_EVAL_RESNET) && (wt_seen++ % 64) == 63;
         if (timed) { for (auto& e : wt_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(wt_ev[0], st); }
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
         if (g.wb.dd_keys) {
@@ -827,7 +847,9 @@ struct EngineT : EngineBase {
         k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode, dup);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) cudaEventRecord(wt_ev[1], st);
-        if (hash_eval()) {
+        if (cfg.evaluator == AZ_EVAL_EXTERNAL) {
+            if (external_eval(g)) return -1;
+        } else if (hash_eval()) {
             k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n,
                                                                                                                               cfg.evaluator == AZ_EVAL_HASH_PEAKED ? 1 : 0);
             AZ_LAUNCH_CHECK(); ++launches;
@@ -837,21 +859,25 @@ struct EngineT : EngineBase {
                 k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats);
                 AZ_LAUNCH_CHECK(); ++launches;
             }
+            if (timed) cudaEventRecord(wt_ev[2], st);
             if (g.net.forward(g.wb.n_eval, 0, g.wb.policy, g.wb.value, st, g.wb.legal, g.wb.n_legal, MC, g.wb.slot_tree)) return -1;
             g.net.fe_on = false;
         }
-        if (timed) cudaEventRecord(wt_ev[2], st);
+        if (timed) { if (hash_eval()) cudaEventRecord(wt_ev[2], st); cudaEventRecord(wt_ev[3], st); }
         k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, root_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
                                                                                     root_order_n + g.t0, sparams(), g.n, dstats);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) {
-            cudaEventRecord(wt_ev[3], st); cudaEventSynchronize(wt_ev[3]);
-            for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, wt_ev[i], wt_ev[i + 1]); wt_ms[i] += ms; }
-            if (cfg.evaluator == AZ_EVAL_RESNET && g.net.fe[6]) {       // select end → stem → trunk → pool → 1x1 → policy FC → value FC → softmax
-                cudaEvent_t seq[8] = {wt_ev[1], g.net.fe[0], g.net.fe[1], g.net.fe[2], g.net.fe[3], g.net.fe[4], g.net.fe[5], g.net.fe[6]};
+            cudaEventRecord(wt_ev[4], st); cudaEventSynchronize(wt_ev[4]);
+            for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, wt_ev[i], wt_ev[i + 1]); wt_ms[i] += ms; }     // select, dedup + encode, evaluator, expand
+            if (cfg.evaluator == AZ_EVAL_RESNET && g.net.fe[6]) {       // dedup end → stem → trunk → pool → 1x1 → policy FC → value FC → softmax
+                cudaEvent_t seq[8] = {wt_ev[2], g.net.fe[0], g.net.fe[1], g.net.fe[2], g.net.fe[3], g.net.fe[4], g.net.fe[5], g.net.fe[6]};
                 for (int i = 0; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, seq[i], seq[i + 1]); wt_fwd[i] += ms; }
+                float tr = 0; cudaEventElapsedTime(&tr, g.net.fe[0], g.net.fe[1]);                 // the trunk of this wave: the live roofline sample
+                if (g.net.blocks > 0 && mode == 0) { g.net.conv_ms += tr; g.net.conv_sampled += (unsigned long long)(2 * g.net.blocks * g.net.NS * g.net.NS); }
             }
             ++wt_n;
+            resolve_commit_timing();
         }
         return 0;
     }
@@ -946,7 +972,14 @@ struct EngineT : EngineBase {
     unsigned long long noise_calls = 0;
 
     int play(int n_moves) override {
-        for (int m = 0; m < n_moves; ++m) { if (search(cfg.num_simulations)) return -1; if (commit_moves(nullptr)) return -1; }
+        for (int m = 0; m < n_moves; ++m) {
+            if (search(cfg.num_simulations)) return -1;
+            resolve_commit_timing();
+            const bool tm = !cm_pending;
+            if (tm) { for (auto& e : cm_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(cm_ev[0], stream); }
+            if (commit_moves(nullptr)) return -1;
+            if (tm) { cudaEventRecord(cm_ev[1], stream); cm_pending = true; }
+        }
         return 0;
     }
 
@@ -968,6 +1001,43 @@ struct EngineT : EngineBase {
         return 0;
     }
 
+    int set_external(az_eval_fn fn, void* user) override {
+        AZ_CHECK(cfg.evaluator == AZ_EVAL_EXTERNAL, "engine was not created with AZ_EVAL_EXTERNAL");
+        ext_fn = fn; ext_user = user;
+        return 0;
+    }
+    // one wave's leaves → the caller's evaluator → policy / value on the device (the group's stream is drained: one host round trip per wave)
+    int external_eval(Group& g) {
+        AZ_CHECK(ext_fn != nullptr, "no external evaluator set (az_engine_set_external_evaluator)");
+        AZ_CHECK(NG == 1, "AZ_EVAL_EXTERNAL runs with one stream group");
+        cudaStream_t st = g.stream;
+        int32_t n = 0;
+        AZ_CUDA_CHECK(cudaMemcpyAsync(&n, g.wb.n_eval, 4, cudaMemcpyDeviceToHost, st));
+        k_leaf_paths<<<(g.n + 127) / 128, 128, 0, st>>>(g.tp, g.wb, ext_slot_tree, ext_paths, ext_plen, g.n);
+        AZ_LAUNCH_CHECK(); ++launches;
+        AZ_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (n <= 0) return 0;
+        AZ_CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), ext_paths, (size_t)n * MAX_DEPTH * 4, cudaMemcpyDeviceToHost, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(h_plen.data(), ext_plen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(h_slot.data(), ext_slot_tree, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; ++i) h_slot[i] += g.t0;
+        std::fill(h_policy.begin(), h_policy.begin() + (size_t)n * A, 0.0f);
+        AZ_CHECK(ext_fn(n, h_slot.data(), h_paths.data(), h_plen.data(), MAX_DEPTH, A, h_policy.data(), h_value.data(), ext_user) == 0, "the external evaluator reported an error");
+        AZ_CUDA_CHECK(cudaMemcpyAsync(g.wb.policy, h_policy.data(), (size_t)n * A * 4, cudaMemcpyHostToDevice, st));
+        AZ_CUDA_CHECK(cudaMemcpyAsync(g.wb.value, h_value.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        AZ_CUDA_CHECK(cudaStreamSynchronize(st));              // (pageable host vectors: the copies above are staged; keep it simple and ordered)
+        return 0;
+    }
+    int get_timing(az_timing* o) override {
+        if (sync_all()) return -1;
+        resolve_commit_timing();
+        std::memset(o, 0, sizeof(*o));
+        o->waves_sampled = (uint64_t)wt_n; o->moves_sampled = (uint64_t)cm_n;
+        o->select_ms = wt_ms[0]; o->dedup_encode_ms = wt_ms[1]; o->evaluator_ms = wt_ms[2]; o->expand_backup_ms = wt_ms[3]; o->commit_ms = cm_ms;
+        o->stem_ms = wt_fwd[0]; o->trunk_ms = wt_fwd[1]; o->head_conv_ms = wt_fwd[2]; o->conv1x1_gemm_ms = wt_fwd[3]; o->policy_fc_ms = wt_fwd[4]; o->value_fc_ms = wt_fwd[5]; o->policy_value_ms = wt_fwd[6];
+        return 0;
+    }
     int set_search_params(float c_puct, int virtual_loss) override {
         AZ_CHECK(c_puct > 0.0f && virtual_loss >= 0, "bad search parameters");
         cfg.c_puct = c_puct; cfg.virtual_loss = virtual_loss;
@@ -1333,6 +1403,8 @@ AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, con
 AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n, int augment, float* planes, float* policy, float* value) { AZ_FWD(make_examples(samples, n, augment, planes, policy, value)); }
 AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
 AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss) { AZ_FWD(set_search_params(c_puct, virtual_loss)); }
+AZ_API int az_engine_set_external_evaluator(az_engine* e, az_eval_fn fn, void* user) { AZ_FWD(set_external(fn, user)); }
+AZ_API int az_engine_get_timing(az_engine* e, az_timing* out) { if (!out) { az::set_error("null argument"); return -1; } AZ_FWD(get_timing(out)); }
 AZ_API int az_engine_node_stats(az_engine* e, int slot, const int32_t* path, int n_path, int32_t* a, int32_t* v, float* w, float* p, int32_t* n, int32_t* nv, float* nw,
                                 float* np_, int32_t* nf) { AZ_FWD(node_stats(slot, path, n_path, a, v, w, p, n, nv, nw, np_, nf)); }
 // plain device memory for the host layer's multi-GPU sample exchange (the host mirror links no CUDA runtime of its own)

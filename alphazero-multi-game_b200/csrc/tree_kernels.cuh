@@ -207,6 +207,18 @@ __global__ void __launch_bounds__(128) k_dedup_encode(const typename G::Leaf* __
     G::w_encode(w, lane, enc, slot);
 }
 
+// AZ_EVAL_EXTERNAL: the leaves of the wave as move sequences from their roots, by evaluation slot (the host replays them on its own states)
+__global__ void k_leaf_paths(TreePools tp, WaveBuffers wb, int32_t* slot_tree, int32_t* path_actions /*[T][MAX_DEPTH]*/, int32_t* path_len, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || wb.leaf_kind[t] != LEAF_EVAL) return;
+    const int slot = wb.eval_slot[t];
+    const size_t base = (size_t)tp.base[t];
+    const int n = max(wb.path_len[t] - 1, 0);               // path[0] is the root; the root-expansion wave has no path
+    const int* path = wb.path + (size_t)t * MAX_DEPTH;
+    for (int i = 0; i < n; ++i) path_actions[(size_t)slot * MAX_DEPTH + i] = (int32_t)tp.act[base + path[i + 1]];
+    path_len[slot] = n; slot_tree[slot] = t;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stateless HashEvaluator — the deterministic evaluator used for bit-exact parity
 // against the reference's serial search.  One warp per leaf; the policy sum is accumulated in ascending

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 GOMOKU, CHESS, GO = 0, 1, 2
 ONGOING, DRAW, WIN_PLAYER1, WIN_PLAYER2 = 0, 1, 2, 3
-EVAL_HASH, EVAL_RESNET, EVAL_HASH_PEAKED = 0, 1, 2
+EVAL_HASH, EVAL_RESNET, EVAL_HASH_PEAKED, EVAL_EXTERNAL = 0, 1, 2, 3
 NET_FP16, NET_BF16 = 0, 1
 
 
@@ -40,6 +40,12 @@ class Stats(C.Structure):
                                           "samples_dropped", "kernel_launches", "waves", "eval_shared")]
 
 
+class Timing(C.Structure):
+    _fields_ = [("waves_sampled", C.c_uint64), ("moves_sampled", C.c_uint64)] + [(n, C.c_double) for n in (
+        "select_ms", "dedup_encode_ms", "evaluator_ms", "expand_backup_ms", "commit_ms", "stem_ms", "trunk_ms", "head_conv_ms", "conv1x1_gemm_ms",
+        "policy_fc_ms", "value_fc_ms", "policy_value_ms")]
+
+
 class SampleLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("record_bytes", "off_game_id", "off_slot", "off_ply", "off_action",
                                          "off_player", "off_z", "off_result", "off_root_value",
@@ -53,7 +59,7 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_examples_from_games", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_conv_sampled", "az_engine_event_record", "az_engine_event_elapsed",
            "az_rules_replay", "az_engine_set_search_params", "az_engine_node_stats", "az_device_count", "az_device_alloc", "az_device_free",
-           "az_device_memcpy", "az_device_sync"]
+           "az_device_memcpy", "az_device_sync", "az_engine_get_timing", "az_engine_set_external_evaluator"]
 
 
 def library_path():
@@ -114,6 +120,7 @@ def load_library():
         "az_engine_set_search_params": [vp, C.c_float, C.c_int],
         "az_engine_node_stats": [vp, C.c_int, i32p, C.c_int, i32p, i32p, f32p, f32p, i32p, i32p, f32p, f32p, i32p],
         "az_device_count": [i32p],
+        "az_engine_get_timing": [vp, C.POINTER(Timing)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -240,6 +247,12 @@ class Engine:
                          "offsets": [L.off_game_id, L.off_slot, L.off_ply, L.off_action, L.off_player, L.off_z,
                                      L.off_result, L.off_root_value, L.off_root_visits, L.off_state, L.off_visits],
                          "itemsize": L.record_bytes})
+
+    def timing(self):
+        """az_engine_get_timing: sums (ms) over the sampled waves / moves, as a dict."""
+        t = Timing()
+        self._check(self.lib.az_engine_get_timing(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timing._fields_}
 
     def drain_samples(self, cap=None, out=None):
         """Copy finished-game samples to HOST memory (pinned `out` if given) and empty the device ring."""

@@ -375,7 +375,30 @@ bool ChessState::equals(const core::IGameState& o) const {
 // ================================================================================================ nn
 namespace nn {
 
+// "hash-host": the hash evaluator as a PLAIN nn::NeuralNetwork that computes on the host (it forwards to B200NeuralNetwork("hash")'s host
+// arithmetic but is not a B200NeuralNetwork): what an arbitrary user-supplied evaluator looks like to ParallelMCTS, which then runs it
+// through the external-evaluator path.  Same numbers as the device hash evaluator, so the two paths can be compared bit for bit.
+class HostHashNetwork : public NeuralNetwork {
+public:
+    HostHashNetwork(core::GameType gt, int bs) : inner_("hash", gt, bs) {}
+    std::pair<std::vector<float>, float> predict(const core::IGameState& s) override { ++calls_; return inner_.predict(s); }
+    void predictBatch(const std::vector<std::reference_wrapper<const core::IGameState>>& st, std::vector<std::vector<float>>& p, std::vector<float>& v) override {
+        calls_ += (long)st.size(); inner_.predictBatch(st, p, v);
+    }
+    bool isGpuAvailable() const override { return false; }
+    std::string getDeviceInfo() const override { return "host hash evaluator (external-evaluator path), " + std::to_string(calls_) + " evaluations"; }
+    float getInferenceTimeMs() const override { return 0.0f; }
+    int getBatchSize() const override { return 1; }
+    std::string getModelInfo() const override { return "HostHashNetwork"; }
+    size_t getModelSizeBytes() const override { return 0; }
+    void benchmark(int, int) override {}
+    void enableDebugMode(bool) override {}
+    void printModelSummary() const override {}
+private:
+    B200NeuralNetwork inner_; long calls_ = 0;
+};
 std::unique_ptr<NeuralNetwork> NeuralNetwork::create(const std::string& modelPath, core::GameType gameType, int boardSize, bool) {
+    if (modelPath == "hash-host") return std::make_unique<HostHashNetwork>(gameType, boardSize);
     return std::make_unique<B200NeuralNetwork>(modelPath, gameType, boardSize);
 }
 
@@ -478,16 +501,21 @@ ParallelMCTS::~ParallelMCTS() { if (eng_) az_engine_destroy(eng_); }
 
 void ParallelMCTS::build(const core::IGameState& rootState) {
     auto* b = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
-    if (!b) throw std::runtime_error("ParallelMCTS on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork); arbitrary host evaluators cannot run inside the device waves");
+    if (!nn_) throw std::runtime_error("ParallelMCTS on the B200 engine needs a neural network (createNeuralNetwork)");
+    // Any other nn::NeuralNetwork implementation (neural_network.h:19-131) evaluates the leaves on the host: the engine hands over each wave's
+    // leaves as move sequences, the states are rebuilt from the root clone and go through nn_->predictBatch (one round trip per wave).
+    external_ = b == nullptr;
     rootState_ = rootState.clone();                                   // parallel_mcts.cpp:65
     az_config c; az_config_default(&c);
     c.game = (int)rootState.getGameType(); c.board_size = rootState.getBoardSize(); c.n_slots = 1;
     c.num_simulations = config_.numSimulations; c.c_puct = config_.cPuct; c.virtual_loss = config_.virtualLoss;
-    c.evaluator = b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET; c.net_blocks = b->blocks(); c.net_channels = b->channels();
+    c.evaluator = external_ ? AZ_EVAL_EXTERNAL : (b->isHash() ? AZ_EVAL_HASH : AZ_EVAL_RESNET);
+    if (b) { c.net_blocks = b->blocks(); c.net_channels = b->channels(); }
     c.deterministic = config_.useDirichletNoise ? 0 : 1; c.dirichlet_alpha = config_.dirichletAlpha; c.dirichlet_epsilon = config_.dirichletEpsilon;
     c.auto_restart = 0; c.n_streams = 1;
     check(az_engine_create(&c, &eng_), "az_engine_create");
-    if (!b->isHash()) check(az_engine_load_weights(eng_, b->blob().data(), b->blob().size()), "az_engine_load_weights");
+    if (external_) check(az_engine_set_external_evaluator(eng_, &ParallelMCTS::evalTrampoline, this), "az_engine_set_external_evaluator");
+    else if (!b->isHash()) check(az_engine_load_weights(eng_, b->blob().data(), b->blob().size()), "az_engine_load_weights");
     // The root MCTSNode ctor calls state->isTerminal() (mcts_node.cpp:24), which is what first enumerates the legal moves
     // of a fresh lineage; the order that enumeration produces is the root's child order (QUIRK G2).
     rootState_->isTerminal();
@@ -500,6 +528,27 @@ void ParallelMCTS::build(const core::IGameState& rootState) {
 }
 void ParallelMCTS::setCPuct(float c) { config_.cPuct = c; check(az_engine_set_search_params(eng_, config_.cPuct, config_.virtualLoss), "az_engine_set_search_params"); }
 void ParallelMCTS::setVirtualLoss(int v) { config_.virtualLoss = v; check(az_engine_set_search_params(eng_, config_.cPuct, config_.virtualLoss), "az_engine_set_search_params"); }
+int ParallelMCTS::evalTrampoline(int n, const int32_t*, const int32_t* paths, const int32_t* lens, int maxLen, int actions, float* policy, float* value, void* user) {
+    auto* self = static_cast<ParallelMCTS*>(user);
+    try {
+        std::vector<std::unique_ptr<core::IGameState>> states; states.reserve(n);
+        std::vector<std::reference_wrapper<const core::IGameState>> refs;
+        for (int i = 0; i < n; ++i) {
+            auto s = self->rootState_->clone();
+            for (int k = 0; k < lens[i]; ++k) s->makeMove(paths[(size_t)i * maxLen + k]);
+            refs.push_back(std::cref(*s)); states.push_back(std::move(s));
+        }
+        std::vector<std::vector<float>> pol; std::vector<float> val;
+        self->nn_->predictBatch(refs, pol, val);
+        if ((int)pol.size() != n || (int)val.size() != n) throw std::runtime_error("predictBatch returned the wrong number of results");
+        for (int i = 0; i < n; ++i) {
+            const int m = std::min<int>((int)pol[i].size(), actions);
+            for (int a = 0; a < m; ++a) policy[(size_t)i * actions + a] = pol[i][a];
+            value[i] = val[i];
+        }
+        return 0;
+    } catch (const std::exception& e) { self->evalError_ = e.what(); return 1; }
+}
 void ParallelMCTS::setSelectionStrategy(MCTSNodeSelection s) {
     if (s != MCTSNodeSelection::PUCT) throw std::runtime_error("the B200 engine implements PUCT selection only (the reference's default, mcts_node.cpp:61-119)");
     config_.selectionStrategy = s;
@@ -512,7 +561,9 @@ void ParallelMCTS::setConfig(const MCTSConfig& config) {
 void ParallelMCTS::setNeuralNetwork(nn::NeuralNetwork* nn) {
     auto* nb = dynamic_cast<nn::B200NeuralNetwork*>(nn);
     auto* ob = dynamic_cast<nn::B200NeuralNetwork*>(nn_);
-    if (!nb) throw std::runtime_error("ParallelMCTS on the B200 engine needs a B200NeuralNetwork (createNeuralNetwork)");
+    if (!nn) throw std::runtime_error("setNeuralNetwork: null network");
+    if (external_ && !nb) { nn_ = nn; return; }                          // host evaluator swapped for another host evaluator
+    if (!nb || !ob) throw std::runtime_error("setNeuralNetwork: a device evaluator can only be replaced by a device evaluator of the same shape (and a host one by a host one)");
     if (nb->isHash() != ob->isHash() || nb->blocks() != ob->blocks() || nb->channels() != ob->channels())
         throw std::runtime_error("setNeuralNetwork: the new network must have the shape the engine was built for (same evaluator kind, blocks, channels)");
     nn_ = nn;
@@ -575,7 +626,12 @@ std::string MCTSNode::toString(int) const {
     return ss.str();
 }
 
-void ParallelMCTS::search() { check(az_engine_search(eng_, config_.numSimulations), "az_engine_search"); check(az_engine_sync(eng_), "az_engine_sync"); searched_ = true; }
+void ParallelMCTS::search() {
+    evalError_.clear();
+    if (az_engine_search(eng_, config_.numSimulations) != 0)
+        throw std::runtime_error(std::string("az_engine_search: ") + az_last_error() + (evalError_.empty() ? "" : " (" + evalError_ + ")"));
+    check(az_engine_sync(eng_), "az_engine_sync"); searched_ = true;
+}
 
 ParallelMCTS::RootStats ParallelMCTS::rootStats() const {
     RootStats r; const int cap = rootState_->getActionSpaceSize() + 1;

@@ -378,6 +378,9 @@ private:
     nn::NeuralNetwork* nn_;
     TranspositionTable* tt_ = nullptr;
     az_engine* eng_ = nullptr;
+    bool external_ = false;      // nn_ is not a B200NeuralNetwork: the leaves are evaluated on the host through nn_->predictBatch (AZ_EVAL_EXTERNAL)
+    std::string evalError_;
+    static int evalTrampoline(int n, const int32_t* slot, const int32_t* paths, const int32_t* lens, int maxLen, int actions, float* policy, float* value, void* user);
     std::unique_ptr<core::IGameState> rootState_;
     bool searched_ = false;
 };

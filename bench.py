@@ -226,6 +226,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     barrier()
     s0 = eng.stats()
     live0 = eng.conv_sampled()
+    tm0 = eng.timing()
     eng.event_record(0)
     for _ in range(steps):
         eng.play(1)
@@ -234,7 +235,14 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     barrier()
     s1 = eng.stats()
     live1 = eng.conv_sampled()
+    tm1 = eng.timing()
     clk = clocks.stop()
+    # per-step budget from the engine's own sampled CUDA events (every 64th wave kernel by kernel, every move commit): (sims + 1) waves + one commit
+    nw = max(tm1["waves_sampled"] - tm0["waves_sampled"], 1); nm = max(tm1["moves_sampled"] - tm0["moves_sampled"], 1)
+    budget = {k[:-3]: (tm1[k] - tm0[k]) / nw * (sims + 1) for k in ("select_ms", "dedup_encode_ms", "stem_ms", "trunk_ms", "head_conv_ms", "conv1x1_gemm_ms",
+                                                                     "policy_fc_ms", "value_fc_ms", "policy_value_ms", "expand_backup_ms")}
+    budget["move_commit"] = (tm1["commit_ms"] - tm0["commit_ms"]) / nm
+    budget_sum = sum(budget.values())
     ms_max = allreduce(ms, dist.ReduceOp.MAX) if dist else ms
     n_sims = allreduce(float(s1["simulations"] - s0["simulations"]), dist.ReduceOp.SUM) if dist else float(s1["simulations"] - s0["simulations"])
     moves = allreduce(float(s1["moves"] - s0["moves"]), dist.ReduceOp.SUM) if dist else float(s1["moves"] - s0["moves"])
@@ -343,6 +351,8 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
            "moves_per_sec": moves / (ms_max / 1e3), "nn_evals_per_sec_rank0": evals / (ms / 1e3),
            "eval_shared_frac_rank0": shared / max(leaf_evals, 1.0),
            "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * net_flop / 1e12 / pk["bf16_sustained"],
+           "step_budget_ms": {**{k: round(v, 3) for k, v in budget.items()}, "sum": round(budget_sum, 2), "sum_over_ms_per_step": round(budget_sum / (ms / steps), 4),
+                              "source": f"az_engine_get_timing: {int(nw)} sampled waves and {int(nm)} move commits of rank 0 inside the timed steps, scaled to {sims} + 1 waves and one commit"},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
            "games_finished": int(e1["games"]), "samples_dropped": int(e1["samples_dropped"]), "pool_overflows": int(e1["pool_overflows"])}
     eng.close()
@@ -389,7 +399,7 @@ def main():
     if args.game == "gomoku15" and args.slots is None and args.sims is None:
         for k in [x for x in args.others.split(",") if x]:
             o = measure(k, args, max(args.other_steps, 5), 3 if k != "go19" else 2, max(args.other_steps, 5) if k != "go19" else 3, rank, world, local, dist)
-            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "e2e",
+            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "e2e",
                                               "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")}
             others[k]["roofline"] = {kk: o["roofline"][kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launch_ms", "launch_ms_source", "whole_net_ms", "whole_net_tflops")}
     overflow = head["pool_overflows"] + sum(o["pool_overflows"] for o in others.values())
@@ -399,7 +409,7 @@ def main():
                 "dtype": args.precision, "dtype_note": "16-bit tensor-core operands (tcgen05 kind::f16), fp32 accumulation; fp16 is the reference's own half-precision mode "
                                                        "(TorchNeuralNetworkConfig::useFp16) and meets the KL <= 1e-3 tolerance on the BASELINE network; --precision bf16 runs the bf16 storage at the same rate",
                 "data": "synthetic"}
-        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "roofline", "cpu_baseline", "e2e",
+        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "roofline", "cpu_baseline", "e2e",
                                           "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")})
         line["other_configs"] = others
         if overflow:

@@ -32,7 +32,9 @@ enum { AZ_ONGOING = 0, AZ_DRAW = 1, AZ_WIN_PLAYER1 = 2, AZ_WIN_PLAYER2 = 3 };
 /* evaluator behind nn::NeuralNetwork::predict (include/alphazero/nn/neural_network.h:29) */
 enum { AZ_EVAL_HASH = 0,   /* stateless integer-mix evaluator (parity runs) */
        AZ_EVAL_RESNET = 1, /* policy/value ResNet, 16-bit operands on tcgen05 tensor cores (kind::f16), fp32 accumulation */
-       AZ_EVAL_HASH_PEAKED = 2 /* AZ_EVAL_HASH with one action's raw prior x 4096 (a peaked policy: deep, narrow trees; node-pool stress / parity) */ };
+       AZ_EVAL_HASH_PEAKED = 2, /* AZ_EVAL_HASH with one action's raw prior x 4096 (a peaked policy: deep, narrow trees; node-pool stress / parity) */
+       AZ_EVAL_EXTERNAL = 3 /* the caller evaluates the leaves on the host (az_engine_set_external_evaluator): any nn::NeuralNetwork implementation
+                               behind ParallelMCTS; one host round trip per wave — the compatibility path, not the fast one */ };
 /* 16-bit storage type of the network's activations and conv weights.  nn::TorchNeuralNetworkConfig::useFp16
  * (include/alphazero/nn/torch_neural_network.h:29: the reference's own reduced-precision mode is fp16, model_.to(torch::kHalf),
  * src/nn/torch_neural_network.cpp:183,267,409).  fp16 and bf16 run the same tcgen05.mma.kind::f16 instruction at the same rate; fp16
@@ -161,8 +163,26 @@ AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n_r
 AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, const int32_t* n_moves, const int8_t* results, int n_games, int max_moves,
                                          const float* policy_in, int policy_len, int augment, float* planes, float* policy, float* value);
 
+/* nn::NeuralNetwork::predictBatch (include/alphazero/nn/neural_network.h:38-42) supplied by the CALLER, for engines created with
+ * AZ_EVAL_EXTERNAL: once per wave the engine hands over the n leaves that need an evaluation as move sequences from their slots' current
+ * roots — slot[i], path_len[i] actions at path_actions + i * max_len (reference action codes; 0 actions = the root itself) — and expects
+ * policy[i * actions .. ] (probabilities over the action space, what predict returns) and value[i].  Called on the thread that calls
+ * az_engine_search / az_engine_play; a non-zero return aborts the search with an error. */
+typedef int (*az_eval_fn)(int n, const int32_t* slot, const int32_t* path_actions, const int32_t* path_len, int max_len, int actions,
+                          float* policy, float* value, void* user);
+AZ_API int az_engine_set_external_evaluator(az_engine* e, az_eval_fn fn, void* user);
 AZ_API int az_engine_get_stats(az_engine* e, az_stats* out);
 AZ_API int az_engine_sync(az_engine* e);
+/* Where the time of a step goes (no reference counterpart; MCTSStats has only counters): every 64th wave of a ResNet engine is bracketed
+ * kernel by kernel with CUDA events on its stream, every move commit of az_engine_play as a whole.  Sums in ms over the sampled waves /
+ * moves: a step of S simulations costs about (S + 1) x (select + dedup_encode + evaluator + expand_backup) / waves_sampled + commit / moves_sampled.
+ * evaluator = stem + trunk + head_conv + conv1x1_gemm + policy_fc + value_fc + policy_value. */
+typedef struct az_timing {
+    uint64_t waves_sampled, moves_sampled;
+    double select_ms, dedup_encode_ms, evaluator_ms, expand_backup_ms, commit_ms;
+    double stem_ms, trunk_ms, head_conv_ms, conv1x1_gemm_ms, policy_fc_ms, value_fc_ms, policy_value_ms;
+} az_timing;
+AZ_API int az_engine_get_timing(az_engine* e, az_timing* out);
 /* ParallelMCTS::setCPuct / setVirtualLoss / setConfig (src/mcts/parallel_mcts.cpp:1173-1261): take effect from the next search */
 AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss);
 /* MCTSNode::children / actions / visitCount / valueSum / prior of ANY node (include/alphazero/mcts/mcts_node.h:54-75; what

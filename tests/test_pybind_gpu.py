@@ -319,3 +319,34 @@ def test_python_self_play_driver_and_orchestrator(tmp_path):
     assert os.path.isdir(out2 / "proc_0") and any(f.startswith("orchestration_summary_") for f in os.listdir(out2))
     s = json.loads(r.stdout.strip().splitlines()[-1])
     assert s["total_games"] == 2 and s["return_code"] == 0
+
+
+@pytest.mark.parametrize("game,board,moves", [(_orc.GOMOKU, 9, 4), (_orc.GO, 9, 3)])
+def test_parallel_mcts_with_an_arbitrary_host_evaluator(game, board, moves):
+    """ParallelMCTS accepts ANY nn::NeuralNetwork (neural_network.h:19-131), not only the device evaluators: a network that is not a
+    B200NeuralNetwork runs through AZ_EVAL_EXTERNAL — every wave's leaves go to the host as move sequences, the states are rebuilt from the
+    root clone and evaluated with predictBatch, policies / values go back.  "hash-host" is the hash evaluator computed by a plain host
+    NeuralNetwork: the search must equal the oracle (== the device hash evaluator) bit for bit, incl. subtree reuse across moves."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    gt = az.GameType.GOMOKU if game == _orc.GOMOKU else az.GameType.GO
+    nn = az.createNeuralNetwork("hash-host", gt, board)
+    assert "host hash evaluator" in nn.getDeviceInfo() and not nn.isGpuAvailable()
+    state = az.createGameState(gt, board, False)
+    o_state = O.new_state(game, board)
+    for a in ([40, 41] if game == _orc.GOMOKU else [30]):
+        state.makeMove(a); assert O.state_make_move(o_state, a) == 0
+    mcts = az.ParallelMCTS(state, nn, None, 1, 90, 1.5, 0.0, 3)
+    mcts.setDeterministicMode(True)
+    om = O.mcts_new(o_state, 90, 1.5, 3, 0, None, None)
+    for mv in range(moves):
+        mcts.search(); O.mcts_search(om)
+        actions, visits, wsum, priors, root_n, root_w = mcts.getRootChildren()
+        b = O.root_stats(om)
+        assert actions == b["actions"].tolist() and visits == b["N"].tolist() and root_n == b["rootN"], mv
+        assert np.array_equal(np.array(wsum, np.float32).view(np.uint32), b["W"].view(np.uint32)), mv
+        assert np.array_equal(np.array(priors, np.float32).view(np.uint32), b["P"].view(np.uint32)), mv
+        a = mcts.selectAction(True, 1.0)
+        assert a == O.mcts_select_action(om, 1, 1.0)
+        mcts.updateWithMove(a); O.mcts_update_with_move(om, a)
+    assert "evaluations" in nn.getDeviceInfo()
