@@ -96,7 +96,17 @@ struct Chess {
         }
         return false;
     }
-    AZ_HD static int king_sq(const Core& c, int col) { for (int s = 0; s < 64; ++s) if (c.b[s] == (uint8_t)(KING | (col << 3))) return s; return -1; }
+    AZ_HD static int king_sq(const Core& c, int col) {         // getKingSquare chess_state.cpp:1139-1147: the first square holding that king
+#if defined(__CUDA_ARCH__)
+        const uint32_t pat = 0x01010101u * (uint32_t)(KING | (col << 3));
+        const uint32_t* wd = reinterpret_cast<const uint32_t*>(c.b);           // four squares per word, byte-wise compare
+        for (int i = 0; i < 16; ++i) { const uint32_t m = __vcmpeq4(wd[i], pat); if (m) return i * 4 + ((__ffs(m) - 1) >> 3); }
+        return -1;
+#else
+        for (int s = 0; s < 64; ++s) if (c.b[s] == (uint8_t)(KING | (col << 3))) return s;
+        return -1;
+#endif
+    }
     AZ_HD static bool in_check(const Core& c, int col) { const int k = king_sq(c, col); return k >= 0 && attacked(c, k, 3 - col); }
     // isValidCastle (chess_rules.cpp:675-727), standard chess: rook files 7 / 0
     AZ_HD static bool castle_ok(const Core& c, int from, int to) {
@@ -112,56 +122,59 @@ struct Chess {
         }
         return true;
     }
-    // generatePseudoLegalMoves (chess_rules.cpp:57-98, :470-673) as action codes, in the reference's order
-    AZ_HD static int gen_pseudo(const Core& c, int16_t* out) {
+    // generatePseudoLegalMoves (chess_rules.cpp:57-98, :470-673) as action codes, in the reference's order: squares ascending (gen_square: the
+    // moves of the piece on one square, at most 27), castling last (gen_castling)
+    AZ_HD static int gen_square(const Core& c, int sq, int16_t* out) {
         int n = 0; const int cur = c.player;
-        for (int sq = 0; sq < 64; ++sq) {
-            const uint8_t p = c.b[sq];
-            if (!p || Cc(p) != cur) continue;
-            const int r = sq >> 3, f = sq & 7;
-            switch (T(p)) {
-                case PAWN: {
-                    const int d = cur == WHITE ? -1 : 1, nr = r + d;
-                    if (nr >= 0 && nr < 8 && !c.b[nr * 8 + f]) {
-                        if (nr == 0 || nr == 7) { out[n++] = (int16_t)code(sq, nr * 8 + f, QUEEN); out[n++] = (int16_t)code(sq, nr * 8 + f, ROOK); out[n++] = (int16_t)code(sq, nr * 8 + f, BISHOP); out[n++] = (int16_t)code(sq, nr * 8 + f, KNIGHT); }
-                        else out[n++] = (int16_t)code(sq, nr * 8 + f, 0);
-                        if ((cur == WHITE && r == 6) || (cur == BLACK && r == 1)) { const int t2 = (nr + d) * 8 + f; if (!c.b[t2]) out[n++] = (int16_t)code(sq, t2, 0); }
-                    }
-                    for (int df = -1; df <= 1; df += 2) {
-                        const int nf = f + df;
-                        if (!on(nr, nf)) continue;
-                        const int t = nr * 8 + nf;
-                        if (c.b[t] && Cc(c.b[t]) != cur) {
-                            if (nr == 0 || nr == 7) { out[n++] = (int16_t)code(sq, t, QUEEN); out[n++] = (int16_t)code(sq, t, ROOK); out[n++] = (int16_t)code(sq, t, BISHOP); out[n++] = (int16_t)code(sq, t, KNIGHT); }
-                            else out[n++] = (int16_t)code(sq, t, 0);
-                        }
-                        if (c.ep == t) out[n++] = (int16_t)code(sq, t, 0);
-                    }
-                    break;
+        const uint8_t p = c.b[sq];
+        if (!p || Cc(p) != cur) return 0;
+        const int r = sq >> 3, f = sq & 7;
+        switch (T(p)) {
+            case PAWN: {
+                const int d = cur == WHITE ? -1 : 1, nr = r + d;
+                if (nr >= 0 && nr < 8 && !c.b[nr * 8 + f]) {
+                    if (nr == 0 || nr == 7) { out[n++] = (int16_t)code(sq, nr * 8 + f, QUEEN); out[n++] = (int16_t)code(sq, nr * 8 + f, ROOK); out[n++] = (int16_t)code(sq, nr * 8 + f, BISHOP); out[n++] = (int16_t)code(sq, nr * 8 + f, KNIGHT); }
+                    else out[n++] = (int16_t)code(sq, nr * 8 + f, 0);
+                    if ((cur == WHITE && r == 6) || (cur == BLACK && r == 1)) { const int t2 = (nr + d) * 8 + f; if (!c.b[t2]) out[n++] = (int16_t)code(sq, t2, 0); }
                 }
-                case KNIGHT:
-                case KING:
-                    for (int i = 0; i < 8; ++i) {
-                        int dr, df; if (T(p) == KNIGHT) knight(i, dr, df); else dir8(i, dr, df);
-                        if (!on(r + dr, f + df)) continue;
-                        const int t = (r + dr) * 8 + f + df;
-                        if (!c.b[t] || Cc(c.b[t]) != cur) out[n++] = (int16_t)code(sq, t, 0);
+                for (int df = -1; df <= 1; df += 2) {
+                    const int nf = f + df;
+                    if (!on(nr, nf)) continue;
+                    const int t = nr * 8 + nf;
+                    if (c.b[t] && Cc(c.b[t]) != cur) {
+                        if (nr == 0 || nr == 7) { out[n++] = (int16_t)code(sq, t, QUEEN); out[n++] = (int16_t)code(sq, t, ROOK); out[n++] = (int16_t)code(sq, t, BISHOP); out[n++] = (int16_t)code(sq, t, KNIGHT); }
+                        else out[n++] = (int16_t)code(sq, t, 0);
                     }
-                    break;
-                default: {                                   // sliders (addSlidingMoves :559-590)
-                    const int nd = T(p) == QUEEN ? 8 : 4;
-                    for (int i = 0; i < nd; ++i) {
-                        int dr, df; if (T(p) == QUEEN) dir8(i, dr, df); else if (T(p) == BISHOP) bishop(i, dr, df); else rook(i, dr, df);
-                        for (int k = 1; on(r + dr * k, f + df * k); ++k) {
-                            const int t = (r + dr * k) * 8 + f + df * k;
-                            if (!c.b[t]) out[n++] = (int16_t)code(sq, t, 0);
-                            else { if (Cc(c.b[t]) != cur) out[n++] = (int16_t)code(sq, t, 0); break; }
-                        }
+                    if (c.ep == t) out[n++] = (int16_t)code(sq, t, 0);
+                }
+                break;
+            }
+            case KNIGHT:
+            case KING:
+                for (int i = 0; i < 8; ++i) {
+                    int dr, df; if (T(p) == KNIGHT) knight(i, dr, df); else dir8(i, dr, df);
+                    if (!on(r + dr, f + df)) continue;
+                    const int t = (r + dr) * 8 + f + df;
+                    if (!c.b[t] || Cc(c.b[t]) != cur) out[n++] = (int16_t)code(sq, t, 0);
+                }
+                break;
+            default: {                                   // sliders (addSlidingMoves :559-590)
+                const int nd = T(p) == QUEEN ? 8 : 4;
+                for (int i = 0; i < nd; ++i) {
+                    int dr, df; if (T(p) == QUEEN) dir8(i, dr, df); else if (T(p) == BISHOP) bishop(i, dr, df); else rook(i, dr, df);
+                    for (int k = 1; on(r + dr * k, f + df * k); ++k) {
+                        const int t = (r + dr * k) * 8 + f + df * k;
+                        if (!c.b[t]) out[n++] = (int16_t)code(sq, t, 0);
+                        else { if (Cc(c.b[t]) != cur) out[n++] = (int16_t)code(sq, t, 0); break; }
                     }
                 }
             }
         }
-        if (!in_check(c, cur)) {                              // addCastlingMoves :613-673
+        return n;
+    }
+    AZ_HD static int gen_castling(const Core& c, int16_t* out) {   // addCastlingMoves :613-673
+        int n = 0; const int cur = c.player;
+        if (!in_check(c, cur)) {
             const bool ck = c.rights & (cur == WHITE ? R_WK : R_BK), cq = c.rights & (cur == WHITE ? R_WQ : R_BQ);
             const int ks = king_sq(c, cur);
             if ((ck || cq) && ks >= 0) {
@@ -171,6 +184,11 @@ struct Chess {
             }
         }
         return n;
+    }
+    AZ_HD static int gen_pseudo(const Core& c, int16_t* out) {
+        int n = 0;
+        for (int sq = 0; sq < 64; ++sq) n += gen_square(c, sq, out + n);
+        return n + gen_castling(c, out + n);
     }
     // makeMove(ChessMove) without the legality check (chess_state.cpp:976-1095); returns the key recordPosition() stores
     AZ_HD static uint64_t apply_core(Core& c, int a) {
@@ -329,9 +347,24 @@ struct Chess {
     // legal moves of the warp's state into w.legal (reference order); pseudo-legal by lane 0, legality one move per lane
     __device__ static int w_gen_legal(Warp& w, int lane) {
         __syncwarp();
+        // pseudo-legal moves: one square per lane (two rounds: squares 0-31, 32-63), each lane's moves placed behind those of the lower squares
+        // (exclusive prefix sum of the per-square counts) — the reference's square-ascending order; castling last, by lane 0
         int np = 0;
-        if (lane == 0) np = gen_pseudo(w.s.c, w.pseudo);
-        np = __shfl_sync(0xffffffffu, np, 0);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            int16_t mv[28];
+            const int n = gen_square(w.s.c, half * 32 + lane, mv);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int off = np + incl - n;
+            for (int i = 0; i < n; ++i) w.pseudo[off + i] = mv[i];
+            np += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        int nc = 0;
+        if (lane == 0) nc = gen_castling(w.s.c, w.pseudo + np);
+        np += __shfl_sync(0xffffffffu, nc, 0);
         __syncwarp();
         int cnt = 0;
         for (int k = 0; k < np; k += 32) {
@@ -361,8 +394,26 @@ struct Chess {
         __syncwarp();
         return ok;
     }
-    __device__ static int w_reps(Warp& w) { return repetitions(w.s.c, w.hist, w.s.extra); }
-    __device__ static int w_result(Warp& w, int lane) { const int n = w_gen_legal(w, lane); return result_core(w.s.c, n, w_reps(w)); }
+    // position count of the current placement key (isThreefoldRepetition / plane 17), the history scanned by the whole (converged) warp
+    __device__ static int w_reps(Warp& w, int lane) {
+        int n = 0; const uint64_t k = w.s.c.key;
+        for (int i = lane; i < w.s.c.hist_n; i += 32) n += w.hist[i] == k;
+        for (int i = lane; i < w.s.c.n_extra; i += 32) n += w.s.extra[i] == k;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        return n;
+    }
+    // hasInsufficientMaterial: every drawn pattern has at most four pieces on the board — count them with two ballots first
+    __device__ static bool w_insufficient(Warp& w, int lane) {
+        const int n = __popc(__ballot_sync(0xffffffffu, w.s.c.b[lane] != 0)) + __popc(__ballot_sync(0xffffffffu, w.s.c.b[lane + 32] != 0));
+        return n <= 4 && insufficient(w.s.c);
+    }
+    __device__ static int w_result(Warp& w, int lane) {          // isTerminal / getGameResult chess_state.cpp:599-652, same order of tests as result_core
+        const int n = w_gen_legal(w, lane);
+        if (n == 0) return in_check(w.s.c, w.s.c.player) ? (w.s.c.player == WHITE ? RES_WIN_P2 : RES_WIN_P1) : RES_DRAW;
+        if (w_insufficient(w, lane) || w.s.c.half >= 100 || w_reps(w, lane) >= 3) return RES_DRAW;
+        return RES_ONGOING;
+    }
     __device__ static int w_root_result(Warp& w, int lane) { const int r = w_result(w, lane); return (r == RES_ONGOING && w.s.c.ply >= MAX_GAME_MOVES) ? RES_DRAW : r; }
     __device__ static int w_player(const Warp& w) { return w.s.c.player; }
     __device__ static int w_ply(const Warp& w) { return w.s.c.ply; }
@@ -392,7 +443,7 @@ struct Chess {
     }
     // feature planes straight into the conv trunk's input layout (bf16, 32 channels = 18 + 14 zero); row = rank * 9 + file
     __device__ static void w_encode(Warp& w, int lane, const EncTarget& enc, int slot) {
-        const int reps = w_reps(w);
+        const int reps = w_reps(w, lane);
         const size_t row0 = (size_t)enc.guard + (size_t)slot * enc.board_pitch;
         for (int sq = lane; sq < 64; sq += 32) {
             const size_t row = row0 + (size_t)(sq >> 3) * (N + 1) + (sq & 7);
@@ -406,13 +457,18 @@ struct Chess {
         }
     }
     __device__ static void w_planes(Warp& w, int lane, float* out) {           // fp32 [18][rank][file]
-        const int reps = w_reps(w);
+        const int reps = w_reps(w, lane);
         for (int i = lane; i < PLANES * 64; i += 32) out[i] = feature(w.s.c, i / 64, i % 64, reps);
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
     __device__ static uint64_t w_tt_key(Warp& w) { return w.s.c.key; }           // ChessState::getHash() granularity: the placement
     // profiling (AZ_EVAL_DUP_STATS): the 18 planes = pieces, side, castling, e.p., min(1, halfmove / 100), repetitions / 3
-    __device__ static uint64_t w_input_key(Warp& w) { uint64_t h = key_core(w.s.c); h = mix64(h ^ (uint64_t)min((int)w.s.c.half, 100)); return mix64(h ^ (uint64_t)w_reps(w)); }
+    // (the placement part is the incrementally maintained Zobrist-style key: O(1) instead of key_core's 64-step chain)
+    __device__ static uint64_t w_input_key(Warp& w, int lane) {
+        const Core& c = w.s.c;
+        const uint64_t rest = (uint64_t)c.player | ((uint64_t)(c.rights & 15) << 2) | ((uint64_t)(c.ep + 1) << 6) | ((uint64_t)min((int)c.half, 100) << 13) | ((uint64_t)w_reps(w, lane) << 20);
+        return mix64(c.key ^ mix64(rest + 0x9E3779B97F4A7C15ULL));
+    }
     __device__ static uint64_t w_ref_tt_key(Warp& w) { return w.s.c.key; }
     // training examples (az_engine_make_examples); the repetition count travels in the snapshot (w.n_legal doubles as its holder)
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {

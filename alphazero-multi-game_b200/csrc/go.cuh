@@ -429,7 +429,7 @@ struct Go {
     }
     __device__ static uint64_t w_key(Warp& w, int) { return key_core(w.s.c); }
     // profiling (AZ_EVAL_DUP_STATS): the 8 planes are functions of stones, side and ko point — the same key as the reference's TT (go_state.cpp:773-811)
-    __device__ static uint64_t w_input_key(Warp& w) { return key_core(w.s.c); }
+    __device__ static uint64_t w_input_key(Warp& w, int) { return key_core(w.s.c); }
     __device__ static uint64_t w_ref_tt_key(Warp& w) { return key_core(w.s.c); }
     // training examples (az_engine_make_examples)
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) {

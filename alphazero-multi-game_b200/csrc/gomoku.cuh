@@ -278,7 +278,7 @@ struct Gomoku {
     __device__ static uint64_t w_key(Warp& w, int) { return key(w.s); }
     // profiling (AZ_EVAL_DUP_STATS): key over the whole network input (stones, side, the six history moves of planes 3-8) and over what the
     // reference's TranspositionTable distinguishes (stones + side, gomoku_state.cpp:620-656)
-    __device__ static uint64_t w_input_key(Warp& w) { uint64_t h = key(w.s); for (int i = 0; i < 6; ++i) h = mix64(h ^ (uint64_t)(uint16_t)w.s.last[i]); return h; }
+    __device__ static uint64_t w_input_key(Warp& w, int) { uint64_t h = key(w.s); for (int i = 0; i < 6; ++i) h = mix64(h ^ (uint64_t)(uint16_t)w.s.last[i]); return h; }
     __device__ static uint64_t w_ref_tt_key(Warp& w) { return key(w.s); }
     // training examples (az_engine_make_examples): state from a sample's snapshot, plane value at tensor index [c][i][j], dense policy
     __device__ static void w_from_snapshot(Warp& w, const Snapshot* g, int lane) { w_load(w, g, lane); }

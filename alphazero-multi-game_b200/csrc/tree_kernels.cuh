@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
     if (kind == LEAF_EVAL) {
         if (dedup) {
             // register the leaf's network input in the wave's key set; slots are handed out, and the planes written, by k_dedup_encode
-            const uint64_t ki = G::w_input_key(w);
+            const uint64_t ki = G::w_input_key(w, lane);
             if (lane == 0) {
                 unsigned long long k = ki ? ki : 1ULL;
                 unsigned int i = (unsigned int)mix64(k) & wb.dd_mask;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
         G::w_store_leaf(w, leaf_state + t, lane);
         if (enc.ptr != nullptr && !dedup) G::w_encode(w, lane, enc, slot);
         if (ds.counters != nullptr) {
-            const uint64_t ki = G::w_input_key(w), kr = G::w_ref_tt_key(w);
+            const uint64_t ki = G::w_input_key(w, lane), kr = G::w_ref_tt_key(w);
             if (lane == 0) {
                 bool full = false;
                 atomicAdd(&ds.counters[0], 1ULL);
