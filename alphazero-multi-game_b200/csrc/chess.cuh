@@ -421,7 +421,7 @@ struct Chess {
     __device__ static void record_visit(uint16_t* visits, int child, int action, int n) { visits[2 * child] = (uint16_t)action; visits[2 * child + 1] = (uint16_t)min(n, 65535); }
     __device__ static int w_enumerate(Warp& w, int lane, const int16_t*, int, int16_t* acts, float* raw, const float* pol) {
         const int n = w_gen_legal(w, lane);
-        for (int i = lane; i < n; i += 32) { const int a = w.legal[i]; acts[i] = (int16_t)a; raw[i] = pol[a]; }
+        for (int i = lane; i < n; i += 32) { const int a = w.legal[i]; acts[i] = (int16_t)a; raw[i] = pol ? pol[a] : 0.0f; }   // pol == nullptr: priors come from the evaluation cache
         __syncwarp();
         return n;
     }
@@ -432,7 +432,7 @@ struct Chess {
         return n;
     }
     __device__ static int w_enumerate_pre(int lane, const int16_t* pre, int n, int16_t* acts, float* raw, const float* pol) {
-        for (int i = lane; i < n; i += 32) { const int a = pre[i]; acts[i] = (int16_t)a; raw[i] = pol[a]; }
+        for (int i = lane; i < n; i += 32) { const int a = pre[i]; acts[i] = (int16_t)a; raw[i] = pol ? pol[a] : 0.0f; }
         __syncwarp();
         return n;
     }

@@ -537,7 +537,7 @@ struct EngineT : EngineBase {
     // Slots are split into `NG` stream groups; each group runs its own wave sequence (select → network → expand) on
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
-    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; Net net; };
+    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; EvalCache ec{}; Net net; };
     // AZ_EVAL_EXTERNAL: the caller's evaluator + staging (device: leaf paths by evaluation slot; host: the same + its answers)
     az_eval_fn ext_fn = nullptr; void* ext_user = nullptr;
     int32_t *ext_paths = nullptr, *ext_plen = nullptr, *ext_slot_tree = nullptr;
@@ -586,7 +586,8 @@ struct EngineT : EngineBase {
         }
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
-                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key, (void*)g.wb.legal, (void*)g.wb.n_legal, (void*)g.wb.slot_tree, (void*)g.wb.dd_keys, (void*)g.wb.dd_owner, (void*)g.wb.dd_idx}) cudaFree(p);
+                            (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key, (void*)g.wb.legal, (void*)g.wb.n_legal, (void*)g.wb.slot_tree, (void*)g.wb.dd_keys, (void*)g.wb.dd_owner, (void*)g.wb.dd_idx, (void*)g.wb.cache_entry,
+                            (void*)g.ec.keys, (void*)g.ec.stamp, (void*)g.ec.value, (void*)g.ec.policy}) cudaFree(p);
             g.net.destroy();
             if (g.ev) cudaEventDestroy(g.ev);
             if (g.stream) cudaStreamDestroy(g.stream);
@@ -688,13 +689,28 @@ struct EngineT : EngineBase {
             if (G::LEGAL_POLICY && c.evaluator == AZ_EVAL_RESNET && !c.dense_policy) {
                 if (dev_alloc(&g.wb.legal, (size_t)n * MC) || dev_alloc(&g.wb.n_legal, n)) return -1;
             }
-            if (c.evaluator == AZ_EVAL_RESNET) {
-                if (dev_alloc(&g.wb.slot_tree, n)) return -1;
-                if (c.eval_dedup >= 0) {
-                    unsigned int cap_dd = 1024; while (cap_dd < 4u * (unsigned)n) cap_dd <<= 1;
-                    g.wb.dd_mask = cap_dd - 1;
-                    if (dev_alloc(&g.wb.dd_keys, cap_dd) || dev_alloc(&g.wb.dd_owner, cap_dd) || dev_alloc(&g.wb.dd_idx, n)) return -1;
-                }
+            // evaluation cache across waves (EvalCache, tree.cuh): on by default behind the ResNet evaluator; behind a hash evaluator only when asked
+            // for (parity runs: the search must equal the reference's with the cache on) and not next to the chess table model, whose
+            // evaluations are not a function of the leaf's own input
+            const bool hash_cache = hash_eval() && c.eval_cache_entries > 0 && !tt.keys;
+            const bool want_cache = c.eval_dedup >= 0 && c.eval_cache_entries >= 0 && (c.evaluator == AZ_EVAL_RESNET || hash_cache);
+            if (c.evaluator == AZ_EVAL_RESNET && dev_alloc(&g.wb.slot_tree, n)) return -1;
+            if ((c.evaluator == AZ_EVAL_RESNET && c.eval_dedup >= 0) || want_cache) {
+                unsigned int cap_dd = 1024; while (cap_dd < 4u * (unsigned)n) cap_dd <<= 1;
+                g.wb.dd_mask = cap_dd - 1;
+                if (dev_alloc(&g.wb.dd_keys, cap_dd) || dev_alloc(&g.wb.dd_owner, cap_dd) || dev_alloc(&g.wb.dd_idx, n)) return -1;
+            }
+            if (want_cache) {
+                // default: 4 M entries over the groups (Gomoku 15x15: 916 B per entry = 3.8 GB), never more than ~1/16 of the device memory
+                const int pw = G::LEGAL_POLICY ? MC : A;
+                size_t free_b = 0, total_b = 0; AZ_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+                long long want = c.eval_cache_entries > 0 ? (long long)c.eval_cache_entries : (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw));
+                want = std::max<long long>(want / NG, 64);
+                unsigned int capn = 64; while ((long long)capn * 2 <= want && capn < (1u << 30)) capn <<= 1;
+                g.ec.mask = capn - 1; g.ec.pw = pw; g.ec.wave = 0;
+                if (dev_alloc(&g.ec.keys, capn) || dev_alloc(&g.ec.stamp, capn) || dev_alloc(&g.ec.value, capn) || dev_alloc(&g.ec.policy, (size_t)capn * pw) ||
+                    dev_alloc(&g.wb.cache_entry, n)) return -1;
+                AZ_CUDA_CHECK(cudaMemset(g.ec.keys, 0, (size_t)capn * 8)); AZ_CUDA_CHECK(cudaMemset(g.ec.stamp, 0, (size_t)capn * 4));
             }
             if (tt.keys) {
                 if (dev_alloc(&g.wb.eval_key, n)) return -1;
@@ -746,6 +762,8 @@ struct EngineT : EngineBase {
         if (sync_all()) return -1;
         if (groups[0].net.load(blob, bytes, stream)) return -1;
         for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.share(groups[0].net);
+        for (auto& g : groups)      // a new network: cached evaluations of the old one are void
+            if (g.ec.keys) { AZ_CUDA_CHECK(cudaMemsetAsync(g.ec.keys, 0, ((size_t)g.ec.mask + 1) * 8, stream)); AZ_CUDA_CHECK(cudaStreamSynchronize(stream)); }
         return 0;
     }
 
@@ -838,18 +856,23 @@ struct EngineT : EngineBase {
             AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_keys, 0, ((size_t)g.wb.dd_mask + 1) * 8, st));
             AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_owner, 0x7f, ((size_t)g.wb.dd_mask + 1) * 4, st));      // 0x7f7f7f7f > any tree index
         }
+        if (g.ec.keys) ++g.ec.wave;
         if (dup.counters) {
             AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys, 0, ((size_t)dup.wave_mask + 1) * 8, st));
             AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys_ref, 0, ((size_t)dup.wave_mask + 1) * 8, st));
         }
         typename G::EncTarget enc{nullptr, 0, 0, 0, 0};
         if (cfg.evaluator == AZ_EVAL_RESNET) enc = typename G::EncTarget{g.net.in16, g.net.p_total, nn::CONV_GUARD, g.net.board_pitch, g.net.f16};
-        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode, dup);
+        k_select<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(g.tp, root_state + g.t0, leaf_state + g.t0, g.wb, sparams(), enc, g.tt, g.n, mode, dup, g.ec);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) cudaEventRecord(wt_ev[1], st);
         if (cfg.evaluator == AZ_EVAL_EXTERNAL) {
             if (external_eval(g)) return -1;
         } else if (hash_eval()) {
+            if (g.wb.dd_keys) {
+                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats);
+                AZ_LAUNCH_CHECK(); ++launches;
+            }
             k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n,
                                                                                                                               cfg.evaluator == AZ_EVAL_HASH_PEAKED ? 1 : 0);
             AZ_LAUNCH_CHECK(); ++launches;
@@ -865,7 +888,7 @@ struct EngineT : EngineBase {
         }
         if (timed) { if (hash_eval()) cudaEventRecord(wt_ev[2], st); cudaEventRecord(wt_ev[3], st); }
         k_expand_backup<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(MC * 4 + (MC * 2 + 15) / 16 * 16), st>>>(g.tp, leaf_state + g.t0, root_state + g.t0, g.wb, root_order + (size_t)g.t0 * MC,
-                                                                                    root_order_n + g.t0, sparams(), g.n, dstats);
+                                                                                    root_order_n + g.t0, sparams(), g.n, dstats, g.ec);
         AZ_LAUNCH_CHECK(); ++launches;
         if (timed) {
             cudaEventRecord(wt_ev[4], st); cudaEventSynchronize(wt_ev[4]);
@@ -1206,7 +1229,7 @@ struct EngineT : EngineBase {
         if (sync_all()) return -1;
         Stats s; AZ_CUDA_CHECK(cudaMemcpy(&s, dstats, sizeof(Stats), cudaMemcpyDeviceToHost));
         o->simulations = s.simulations; o->evaluations = s.evaluations; o->terminal_leaves = s.terminal_leaves; o->nodes_created = s.nodes_created;
-        o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped; o->eval_shared = s.eval_shared;
+        o->nodes_expanded = s.nodes_expanded; o->pool_overflows = s.pool_overflows; o->moves = s.moves; o->games = s.games; o->samples_dropped = s.samples_dropped; o->eval_shared = s.eval_shared; o->eval_cached = s.eval_cached;
         o->kernel_launches = launches + net_launches(); o->waves = waves;
         return 0;
     }
@@ -1356,7 +1379,7 @@ AZ_API void az_config_default(az_config* c) {
     c->game = AZ_GAME_GOMOKU; c->board_size = 15; c->n_slots = 4096; c->num_simulations = 800; c->c_puct = 1.5f; c->virtual_loss = 3;
     c->evaluator = AZ_EVAL_RESNET; c->net_blocks = 10; c->net_channels = 128; c->max_nodes_per_tree = 0; c->deterministic = 0;
     c->dirichlet_alpha = 0.03f; c->dirichlet_epsilon = 0.25f; c->init_temperature = 1.0f; c->final_temperature = 0.0f; c->temperature_drop_move = 30;
-    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1; c->net_precision = AZ_NET_FP16; c->tt_entries = 0; c->dense_policy = 0; c->eval_dedup = 0; c->reserved_ = 0;
+    c->auto_restart = 1; c->sample_ring_capacity = 0; c->device = 0; c->seed = 1234; c->n_streams = 1; c->net_precision = AZ_NET_FP16; c->tt_entries = 0; c->dense_policy = 0; c->eval_dedup = 0; c->eval_cache_entries = 0;
 }
 
 AZ_API const char* az_last_error(void) { return az::g_error.c_str(); }

@@ -62,7 +62,27 @@ struct WaveBuffers {
     // the smallest tree index with that key; dd_idx[t] = the tree's entry.  nullptr = off.
     unsigned long long* dd_keys; int32_t* dd_owner; int32_t* dd_idx; unsigned int dd_mask;
     uint64_t* eval_key;  // [T] hash evaluators + EvalTT: the key the leaf is evaluated under (its own, or the first-seen position's); else nullptr
+    int32_t* cache_entry; // [T] EvalCache entry that serves this tree's leaf (-1: none); nullptr = no cache
 };
+
+// Evaluation cache across waves (M16: what the reference's TranspositionTable is — 64-bit key -> (policy, value), transposition_table.cpp:44-84,
+// 128-176; lookups parallel_mcts.cpp:320-336, 851).  Key = G::w_input_key, the WHOLE network input, so a hit returns exactly what the
+// network would compute: the search is bit-identical with the cache on or off (policies are kept in fp32).  CACHE_WAYS-way buckets;
+// `stamp` = wave number of the entry's last store or hit.  Probes happen in k_select, stores in k_expand_backup of the same wave: a
+// store claims a way with atomicCAS(stamp, seen, wave) and only ways whose stamp is not the current wave can be claimed — so an entry
+// that was hit (read by k_expand_backup) or stored in this wave is never overwritten in it; oldest stamp is the victim.  Which
+// evaluations get stored depends on warp timing; what a hit returns does not.
+constexpr int CACHE_WAYS = 4;
+struct EvalCache {
+    unsigned long long* keys;   // [cap], 0 = empty
+    uint32_t* stamp;            // [cap]
+    float* value;               // [cap]
+    float* policy;              // [cap][pw]: action-indexed (pw = ACTIONS), or the children's raw priors in child order for LEGAL_POLICY games (pw = MAX_CHILDREN)
+    unsigned int mask;          // cap - 1
+    int pw;
+    uint32_t wave;              // number of the running wave, >= 1
+};
+__device__ __forceinline__ unsigned int cache_bucket(const EvalCache& ec, unsigned long long k) { return ((unsigned int)(mix64(k) >> 24) & ec.mask) & ~(unsigned int)(CACHE_WAYS - 1); }
 
 // Model of the reference's per-game TranspositionTable (src/mcts/transposition_table.cpp:44-84, 128-176; lookups at
 // parallel_mcts.cpp:320-336, 851) for games whose table key is coarser than the evaluator's input.  Chess: ChessState::getHash() covers
@@ -101,7 +121,8 @@ struct SearchParams {
 
 struct Stats {           // mirrors mcts::MCTSStats (parallel_mcts.h:77-99) + engine counters
     unsigned long long simulations, evaluations, terminal_leaves, nodes_created, nodes_expanded,
-        pool_overflows, moves, games, samples_dropped, eval_shared;   // eval_shared: leaf evaluations served by another tree's evaluation of the same input in the same wave
+        pool_overflows, moves, games, samples_dropped, eval_shared,   // eval_shared: leaf evaluations served by another tree's evaluation of the same input in the same wave
+        eval_cached;                                                  // ... served by the evaluation cache (an earlier wave's evaluation of the same input)
 };
 
 }  // namespace az

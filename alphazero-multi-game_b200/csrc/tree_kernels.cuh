@@ -33,7 +33,7 @@ constexpr size_t warp_ws_bytes(int extra_bytes_per_warp = 0) { return 4 * ((size
 template <class G>
 __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::State* __restrict__ root_state,
                                                typename G::Leaf* __restrict__ leaf_state, WaveBuffers wb,
-                                               SearchParams sp, typename G::EncTarget enc, EvalTT tt, int T, int mode, DupStats ds) {
+                                               SearchParams sp, typename G::EncTarget enc, EvalTT tt, int T, int mode, DupStats ds, EvalCache ec) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -117,14 +117,25 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
             const uint64_t ki = G::w_input_key(w, lane);
             if (lane == 0) {
                 unsigned long long k = ki ? ki : 1ULL;
-                unsigned int i = (unsigned int)mix64(k) & wb.dd_mask;
-                while (true) {
-                    const unsigned long long old = atomicCAS(&wb.dd_keys[i], 0ULL, k);
-                    if (old == 0ULL || old == k) break;
-                    i = (i + 1) & wb.dd_mask;                       // the set has 4 x T entries: always terminates
+                // evaluation cache first (EvalCache, tree.cuh): an input evaluated in an earlier wave needs neither a slot nor an owner
+                int ce = -1;
+                if (ec.keys != nullptr) {
+                    const unsigned int b = cache_bucket(ec, k);
+#pragma unroll
+                    for (int wy = 0; wy < CACHE_WAYS; ++wy) if (ce < 0 && ec.keys[b + wy] == k) ce = (int)(b + wy);
+                    if (ce >= 0) ec.stamp[ce] = ec.wave;            // hit: refreshed, and protected from this wave's stores
+                    wb.cache_entry[t] = ce;
                 }
-                atomicMin(&wb.dd_owner[i], t);
-                wb.dd_idx[t] = (int32_t)i;
+                if (ce < 0) {
+                    unsigned int i = (unsigned int)mix64(k) & wb.dd_mask;
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&wb.dd_keys[i], 0ULL, k);
+                        if (old == 0ULL || old == k) break;
+                        i = (i + 1) & wb.dd_mask;                   // the set has 4 x T entries: always terminates
+                    }
+                    atomicMin(&wb.dd_owner[i], t);
+                    wb.dd_idx[t] = (int32_t)i;
+                }
             }
         } else {
             if (lane == 0) { slot = atomicAdd(wb.n_eval, 1); if (wb.slot_tree) wb.slot_tree[slot] = t; }
@@ -194,6 +205,10 @@ __global__ void __launch_bounds__(128) k_dedup_encode(const typename G::Leaf* __
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
     if (wb.leaf_kind[t] != LEAF_EVAL) return;
+    if (wb.cache_entry != nullptr && wb.cache_entry[t] >= 0) {          // served by the evaluation cache
+        if (lane == 0) atomicAdd(&stats->eval_cached, 1ULL);
+        return;
+    }
     const int owner = wb.dd_owner[wb.dd_idx[t]];
     if (owner != t) {
         if (lane == 0) { wb.eval_slot[t] = -2 - owner; atomicAdd(&stats->eval_shared, 1ULL); }
@@ -203,6 +218,7 @@ __global__ void __launch_bounds__(128) k_dedup_encode(const typename G::Leaf* __
     int slot = 0;
     if (lane == 0) { slot = atomicAdd(wb.n_eval, 1); wb.eval_slot[t] = slot; if (wb.slot_tree) wb.slot_tree[slot] = t; }
     slot = warp_bcast(slot, 0);
+    if (enc.ptr == nullptr) return;                                       // hash evaluators read the leaf state themselves
     G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
     G::w_encode(w, lane, enc, slot);
 }
@@ -236,6 +252,7 @@ __global__ void __launch_bounds__(128) k_hash_eval(const typename G::Leaf* __res
     typename G::Warp& w = warp_ws<G>(smem, CH * 4);
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     const int slot = wb.eval_slot[t];
+    if (slot < 0) return;                                                 // shared with another tree of the wave, or served by the evaluation cache
     G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
     const uint64_t h = (G::TT_COARSE && wb.eval_key != nullptr) ? wb.eval_key[t] : G::w_key(w, lane);
     // AZ_EVAL_HASH_PEAKED: the raw prior of action mix(h ^ 0x5EED) % A is multiplied by 4096 (exact) before the normalisation
@@ -271,7 +288,7 @@ template <class G>
 __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typename G::Leaf* __restrict__ leaf_state,
                                                       const typename G::State* __restrict__ root_state, WaveBuffers wb, const int16_t* __restrict__ root_order,
                                                       const int32_t* __restrict__ root_order_n, SearchParams sp,
-                                                      int T, Stats* stats) {
+                                                      int T, Stats* stats, EvalCache ec) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -290,9 +307,18 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
 
     if (kind == LEAF_EVAL) {
         int slot = wb.eval_slot[t];
-        if (slot <= -2) slot = wb.eval_slot[-2 - slot];      // in-wave dedup: the owner's evaluation of the same network input
-        const float* pol = wb.policy + (size_t)slot * A;
-        v = wb.value[slot];
+        const bool own_eval = slot >= 0;                     // this tree's leaf went through the evaluator itself
+        const int ce = ec.keys != nullptr ? wb.cache_entry[t] : -1;
+        const float* pol; const float* cpol = nullptr;
+        if (ce >= 0) {                                       // evaluation cache: an earlier wave's evaluation of the same network input
+            cpol = ec.policy + (size_t)ce * ec.pw;
+            pol = G::LEGAL_POLICY ? nullptr : cpol;
+            v = ec.value[ce];
+        } else {
+            if (slot <= -2) slot = wb.eval_slot[-2 - slot];  // in-wave dedup: the owner's evaluation of the same network input
+            pol = wb.policy + (size_t)slot * A;
+            v = wb.value[slot];
+        }
         G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
         const uint8_t tf = tp.tflags[t];
         const bool first_fill = (tf & TF_FIRST_FILL) && leaf == tp.root[t];
@@ -305,6 +331,35 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
             if (wb.legal != nullptr) n = G::w_enumerate_pre(lane, wb.legal + (size_t)t * MC, wb.n_legal[t], acts, raw, pol);
             else n = G::w_enumerate(w, lane, nullptr, 0, acts, raw, pol);
         } else n = G::w_enumerate(w, lane, first_fill ? root_order + (size_t)t * MC : nullptr, first_fill ? root_order_n[t] : 0, acts, raw, pol);
+        if constexpr (G::LEGAL_POLICY) {
+            if (cpol != nullptr) { for (int i = lane; i < n; i += 32) raw[i] = cpol[i]; __syncwarp(); }      // cached: the children's raw priors in child order
+        }
+        if (ec.keys != nullptr && own_eval) {
+            // store this evaluation: claim the oldest way of the bucket that was neither hit nor stored in this wave (tree.cuh)
+            int claimed = -1;
+            if (lane == 0) {
+                const unsigned long long k = wb.dd_keys[wb.dd_idx[t]];
+                const unsigned int b = cache_bucket(ec, k);
+                for (int attempt = 0; attempt < CACHE_WAYS && claimed < 0; ++attempt) {
+                    int best = -1; uint32_t best_age = 0, best_s = 0;
+                    for (int wy = 0; wy < CACHE_WAYS; ++wy) {
+                        const uint32_t s = *(volatile uint32_t*)&ec.stamp[b + wy];
+                        if (s == ec.wave) continue;
+                        const uint32_t age = *(volatile unsigned long long*)&ec.keys[b + wy] == 0ULL ? 0xffffffffu : ec.wave - s;
+                        if (best < 0 || age > best_age) { best = wy; best_age = age; best_s = s; }
+                    }
+                    if (best < 0) break;
+                    if (atomicCAS(&ec.stamp[b + best], best_s, ec.wave) == best_s) claimed = (int)(b + best);
+                }
+                if (claimed >= 0) { ec.keys[claimed] = k; ec.value[claimed] = v; }
+            }
+            claimed = warp_bcast(claimed, 0);
+            if (claimed >= 0) {
+                float* dst = ec.policy + (size_t)claimed * ec.pw;
+                if constexpr (G::LEGAL_POLICY) { for (int i = lane; i < n; i += 32) dst[i] = raw[i]; }
+                else { for (int i = lane; i < A; i += 32) dst[i] = pol[i]; }
+            }
+        }
         if (alloc + n > tp.limit[t]) {
             if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         } else if (n > 0) {

@@ -31,13 +31,13 @@ class EngineConfig(C.Structure):
                 ("init_temperature", C.c_float), ("final_temperature", C.c_float),
                 ("temperature_drop_move", C.c_int32), ("auto_restart", C.c_int32),
                 ("sample_ring_capacity", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
-                ("n_streams", C.c_int32), ("net_precision", C.c_int32), ("tt_entries", C.c_int32), ("eval_dedup", C.c_int32), ("reserved_", C.c_int32), ("dense_policy", C.c_int32)]
+                ("n_streams", C.c_int32), ("net_precision", C.c_int32), ("tt_entries", C.c_int32), ("eval_dedup", C.c_int32), ("eval_cache_entries", C.c_int32), ("dense_policy", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("simulations", "evaluations", "terminal_leaves", "nodes_created",
                                           "nodes_expanded", "pool_overflows", "moves", "games",
-                                          "samples_dropped", "kernel_launches", "waves", "eval_shared")]
+                                          "samples_dropped", "kernel_launches", "waves", "eval_shared", "eval_cached")]
 
 
 class Timing(C.Structure):

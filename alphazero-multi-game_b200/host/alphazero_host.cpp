@@ -679,7 +679,7 @@ void ParallelMCTS::updateWithMove(int action) {                        // parall
 void ParallelMCTS::addDirichletNoise(float alpha, float epsilon) { check(az_engine_add_dirichlet_noise(eng_, alpha, epsilon), "az_engine_add_dirichlet_noise"); }
 MCTSStats ParallelMCTS::getStats() const {
     az_stats s; check(az_engine_get_stats(eng_, &s), "az_engine_get_stats");
-    MCTSStats m; m.nodesCreated = s.nodes_created; m.nodesExpanded = s.nodes_expanded; m.simulationCount = s.simulations; m.evaluationCalls = s.evaluations - s.eval_shared; m.cacheHits = s.eval_shared; m.cacheMisses = s.evaluations - s.eval_shared;
+    MCTSStats m; m.nodesCreated = s.nodes_created; m.nodesExpanded = s.nodes_expanded; m.simulationCount = s.simulations; m.evaluationCalls = s.evaluations - s.eval_shared - s.eval_cached; m.cacheHits = s.eval_shared + s.eval_cached; m.cacheMisses = m.evaluationCalls;
     return m;
 }
 std::string ParallelMCTS::getSearchInfo() const {                       // parallel_mcts.cpp:1319-1388 (same fields)

@@ -196,7 +196,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     conv_flop_board, net_flop = flops(c)
     eng = E.Engine(game=getattr(E, c["game"]), board_size=c["board"], n_slots=slots, num_simulations=sims, evaluator=E.EVAL_RESNET,
                    net_blocks=c["blocks"], net_channels=c["channels"], deterministic=0, auto_restart=1, device=local, seed=1234 + rank,
-                   n_streams=args.streams, net_precision=E.NET_BF16 if args.precision == "bf16" else E.NET_FP16)
+                   n_streams=args.streams, net_precision=E.NET_BF16 if args.precision == "bf16" else E.NET_FP16, eval_cache_entries=args.cache)
     model = N.make_random_model(seed=0, in_planes=c["planes"], board=c["board"], actions=c["actions"], blocks=c["blocks"], channels=c["channels"])
     blob = N.export_weights(model)
     eng.load_weights(blob)
@@ -248,7 +248,8 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     moves = allreduce(float(s1["moves"] - s0["moves"]), dist.ReduceOp.SUM) if dist else float(s1["moves"] - s0["moves"])
     leaf_evals = float(s1["evaluations"] - s0["evaluations"])
     shared = float(s1["eval_shared"] - s0["eval_shared"])             # leaves served by another tree's evaluation of the same input in the same wave
-    evals = leaf_evals - shared                                        # network evaluations actually run (what the FLOP accounting uses)
+    cached = float(s1["eval_cached"] - s0["eval_cached"])             # ... by the evaluation cache (an earlier wave's evaluation of the same input)
+    evals = leaf_evals - shared - cached                               # network evaluations actually run (what the FLOP accounting uses)
     launches = int(s1["kernel_launches"] - s0["kernel_launches"])
     value = n_sims / (ms_max / 1e3)
 
@@ -349,7 +350,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
     out = {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
            "config": workload_config(c, args, world, slots, sims),
            "moves_per_sec": moves / (ms_max / 1e3), "nn_evals_per_sec_rank0": evals / (ms / 1e3),
-           "eval_shared_frac_rank0": shared / max(leaf_evals, 1.0),
+           "eval_shared_frac_rank0": shared / max(leaf_evals, 1.0), "eval_cached_frac_rank0": cached / max(leaf_evals, 1.0),
            "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * net_flop / 1e12 / pk["bf16_sustained"],
            "step_budget_ms": {**{k: round(v, 3) for k, v in budget.items()}, "sum": round(budget_sum, 2), "sum_over_ms_per_step": round(budget_sum / (ms / steps), 4),
                               "source": f"az_engine_get_timing: {int(nw)} sampled waves and {int(nm)} move commits of rank 0 inside the timed steps, scaled to {sims} + 1 waves and one commit"},
@@ -371,6 +372,7 @@ def main():
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"], help="16-bit storage of activations / conv weights (az_config.net_precision)")
+    ap.add_argument("--cache", type=int, default=0, help="evaluation cache entries (az_config.eval_cache_entries): 0 = default (4 M), -1 = off")
     ap.add_argument("--others", default="go9,chess,go19", help="comma-separated BASELINE configs measured into `other_configs` ('' = none)")
     ap.add_argument("--other-steps", type=int, default=5)
     ap.add_argument("--ref-sims-per-step", type=int, default=200)
@@ -399,7 +401,7 @@ def main():
     if args.game == "gomoku15" and args.slots is None and args.sims is None:
         for k in [x for x in args.others.split(",") if x]:
             o = measure(k, args, max(args.other_steps, 5), 3 if k != "go19" else 2, max(args.other_steps, 5) if k != "go19" else 3, rank, world, local, dist)
-            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "e2e",
+            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "e2e",
                                               "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")}
             others[k]["roofline"] = {kk: o["roofline"][kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launch_ms", "launch_ms_source", "whole_net_ms", "whole_net_tflops")}
     overflow = head["pool_overflows"] + sum(o["pool_overflows"] for o in others.values())
@@ -409,7 +411,7 @@ def main():
                 "dtype": args.precision, "dtype_note": "16-bit tensor-core operands (tcgen05 kind::f16), fp32 accumulation; fp16 is the reference's own half-precision mode "
                                                        "(TorchNeuralNetworkConfig::useFp16) and meets the KL <= 1e-3 tolerance on the BASELINE network; --precision bf16 runs the bf16 storage at the same rate",
                 "data": "synthetic"}
-        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "roofline", "cpu_baseline", "e2e",
+        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "roofline", "cpu_baseline", "e2e",
                                           "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")})
         line["other_configs"] = others
         if overflow:

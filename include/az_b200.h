@@ -76,7 +76,11 @@ typedef struct az_config {
     int32_t eval_dedup;         /* ResNet evaluator: 0 = default (on): leaves of different trees that present the SAME network input in the same wave
                                    share one evaluation (the role of the reference's TranspositionTable — an evaluation cache, M16 — inside one wave;
                                    result-transparent: bit-identical searches with it on or off); -1 = off */
-    int32_t reserved_;
+    int32_t eval_cache_entries; /* evaluation cache ACROSS waves (the reference's TranspositionTable, src/mcts/transposition_table.cpp:44-84, 128-176: 64-bit
+                                   key -> (policy, value)): key = the whole network input, fp32 policies, 4-way buckets, oldest entry replaced — a hit
+                                   returns exactly what the network would compute, so searches are bit-identical with it on or off.  0 = default (ResNet
+                                   evaluator: 4 M entries; hash evaluators: off), > 0 = entries (rounded down to a power of two), -1 = off.  Needs
+                                   eval_dedup >= 0.  Cleared by az_engine_load_weights */
     int32_t dense_policy;       /* wide policy heads (chess, 20480 actions): 0 = inside the waves the network computes the logits of the leaf's
                                    legal moves only (their softmax equals the full softmax renormalised over the legal moves, which is what the
                                    expansion computes, parallel_mcts.cpp:705-724); 1 = all A logits + the full softmax, as az_engine_nn_forward does */
@@ -89,7 +93,8 @@ typedef struct az_stats {
     uint64_t kernel_launches;   /* CUDA kernels this engine has launched */
     uint64_t waves;
     uint64_t eval_shared;       /* leaf evaluations served by another tree's evaluation of the same network input in the same wave (MCTSStats::cacheHits);
-                                   network evaluations actually run = evaluations - eval_shared */
+                                   network evaluations actually run = evaluations - eval_shared - eval_cached */
+    uint64_t eval_cached;       /* leaf evaluations served by the evaluation cache (an earlier wave's evaluation of the same network input) */
 } az_stats;
 
 typedef struct az_engine az_engine;

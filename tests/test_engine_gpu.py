@@ -49,14 +49,15 @@ def test_rules_kernels_match_golden_and_oracle():
         eng.close()
 
 
-@pytest.mark.parametrize("idx", [0, 2])
-def test_search_matches_reference_golden(idx):
+@pytest.mark.parametrize("idx,cache", [(0, 0), (2, 0), (2, 1 << 12)])
+def test_search_matches_reference_golden(idx, cache):
     """Serial-search parity on the golden cases generated from the patched reference (Gomoku 15x15 @800 sims,
-    9x9 @200 sims): child order, visit counts, valueSum and prior bits, root leak, chosen move."""
+    9x9 @200 sims): child order, visit counts, valueSum and prior bits, root leak, chosen move.  cache > 0: with the evaluation cache
+    (M16) on behind the hash evaluator, deliberately small (4096 entries per engine: evictions happen) — still bit-equal."""
     from _eng import hash_engine
     case = json.load(open(os.path.join(GOLD, "search_hash_eval.json")))[idx]
     assert case["game"] == GOMOKU
-    eng = hash_engine(3, board=case["board"], sims=case["sims"])
+    eng = hash_engine(3, board=case["board"], sims=case["sims"], eval_cache_entries=cache)
     for mv, g in enumerate(case["moves"]):
         eng.search()
         for slot in range(3):                      # identical games in every slot
@@ -366,7 +367,7 @@ def test_in_wave_eval_dedup_is_result_transparent(game, board):
     out = []
     for dedup in (0, -1):
         eng = E.Engine(game=game, board_size=board, n_slots=len(openings), evaluator=E.EVAL_RESNET, net_blocks=2, num_simulations=48, deterministic=1,
-                       auto_restart=0, eval_dedup=dedup)
+                       auto_restart=0, eval_dedup=dedup, eval_cache_entries=-1)
         eng.load_weights(blob)
         for t, mv in enumerate(openings):
             eng.set_root(t, mv)
@@ -386,3 +387,51 @@ def test_in_wave_eval_dedup_is_result_transparent(game, board):
             a, b = on[move][t], off[move][t]
             assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, t)
             assert np.array_equal(a["W"].view(np.uint32), b["W"].view(np.uint32)) and np.array_equal(a["P"].view(np.uint32), b["P"].view(np.uint32)), (move, t)
+
+
+@pytest.mark.parametrize("game,board", [(GOMOKU, 15), (_orc.GO, 9), (_orc.CHESS, 8)])
+def test_eval_cache_across_waves_is_result_transparent(game, board):
+    """Evaluation cache across waves (M16 / SURVEY 8f.3: the reference's TranspositionTable, 64-bit key -> (policy, value)) behind the ResNet
+    evaluator.  Key = the whole network input, policies kept in fp32: a hit returns exactly what the network would compute, so searches are
+    bit-identical with the cache on and off.  Each engine searches the same roots TWICE (fresh trees the second time): with the cache on
+    the second pass is served almost entirely from the cache; all four runs must agree bit for bit on every slot and move."""
+    from _eng import E, N
+    O = _orc.oracle()
+    planes, actions = {GOMOKU: (11, board * board), _orc.GO: (8, board * board + 1), _orc.CHESS: (18, 20480)}[game]
+    m = N.make_random_model(seed=5, randomize_bn=True, blocks=2, in_planes=planes, board=board, actions=actions)
+    blob = N.export_weights(m)
+    rng = np.random.default_rng(11)
+    openings = []
+    for _ in range(8):
+        s = O.new_state(game, board); mv = []
+        for _ in range(int(rng.integers(0, 10))):
+            lg = O.legal(s)
+            a = int(rng.choice(lg[lg >= 0] if game == _orc.GO else lg))
+            O.state_make_move(s, a); mv.append(a)
+        openings.append(mv)
+    runs = {}
+    for cache in (1 << 16, -1):
+        eng = E.Engine(game=game, board_size=board, n_slots=len(openings), evaluator=E.EVAL_RESNET, net_blocks=2, num_simulations=64, deterministic=1,
+                       auto_restart=0, eval_cache_entries=cache)
+        eng.load_weights(blob)
+        for rep in range(2):
+            for t, mv in enumerate(openings):
+                eng.set_root(t, mv)
+            res = []
+            for move in range(2):
+                eng.search()
+                res.append([eng.root_stats(t) for t in range(len(openings))])
+                eng.advance([int(r["actions"][int(np.argmax(r["N"]))]) if len(r["N"]) else -2 for r in res[-1]])
+            runs[(cache, rep)] = (res, eng.stats())
+        eng.close()
+    ref = runs[(-1, 0)][0]
+    for key, (res, _) in runs.items():
+        for move in range(2):
+            for t in range(len(openings)):
+                a, b = res[move][t], ref[move][t]
+                assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (key, move, t)
+                assert np.array_equal(a["W"].view(np.uint32), b["W"].view(np.uint32)) and np.array_equal(a["P"].view(np.uint32), b["P"].view(np.uint32)), (key, move, t)
+    on0, on1, off1 = runs[(1 << 16, 0)][1], runs[(1 << 16, 1)][1], runs[(-1, 1)][1]
+    assert off1["eval_cached"] == 0 and on1["evaluations"] == off1["evaluations"]
+    second_pass = on1["evaluations"] - on0["evaluations"]
+    assert on1["eval_cached"] - on0["eval_cached"] >= 0.9 * second_pass, (on0, on1)      # the second pass re-evaluates (almost) nothing

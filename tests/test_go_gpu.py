@@ -91,24 +91,32 @@ def test_go_rules_edge_cases():
     eng.close()
 
 
-def test_go_search_matches_reference_golden():
+@pytest.mark.parametrize("cache", [0, 1 << 14])
+def test_go_search_matches_reference_golden(cache):
     """Serial-search parity on the golden case generated from the patched reference (Go 9x9 @400 sims):
-    child order (pass first), visit counts, valueSum and prior bits, root leak, chosen move."""
+    child order (pass first), visit counts, valueSum and prior bits, root leak, chosen move.  cache > 0: the same with the evaluation
+    cache (M16, the reference's TranspositionTable) switched on behind the hash evaluator — transpositions inside the trees are served
+    from the cache and the search still equals the reference's bit for bit (the reference ran with ITS table on)."""
     cases = [c for c in json.load(open(os.path.join(GOLD, "search_hash_eval.json"))) if c["game"] == GO]
     assert cases
     case = cases[0]
-    eng = go_engine(3, board=case["board"], sims=case["sims"])
-    for mv, g in enumerate(case["moves"]):
-        eng.search()
+    eng = go_engine(3, board=case["board"], sims=case["sims"], eval_cache_entries=cache)
+    for rep in range(2 if cache else 1):           # second pass (fresh trees, same roots): every evaluation comes out of the cache
         for slot in range(3):
-            st = eng.root_stats(slot)
-            assert st["actions"].tolist() == g["actions"], (mv, slot)
-            assert st["N"].tolist() == g["N"], (mv, slot)
-            assert bits(st["W"]).tolist() == g["W"], (mv, slot)
-            assert bits(st["P"]).tolist() == g["P"], (mv, slot)
-            assert st["rootN"] == g["rootN"] and int(bits([st["rootW"]])[0]) == g["rootW"]
-        eng.advance([g["action"]] * 3)
-    assert eng.stats()["pool_overflows"] == 0
+            eng.set_root(slot, [])
+        for mv, g in enumerate(case["moves"]):
+            eng.search()
+            for slot in range(3):
+                st = eng.root_stats(slot)
+                assert st["actions"].tolist() == g["actions"], (rep, mv, slot)
+                assert st["N"].tolist() == g["N"], (rep, mv, slot)
+                assert bits(st["W"]).tolist() == g["W"], (rep, mv, slot)
+                assert bits(st["P"]).tolist() == g["P"], (rep, mv, slot)
+                assert st["rootN"] == g["rootN"] and int(bits([st["rootW"]])[0]) == g["rootW"]
+            eng.advance([g["action"]] * 3)
+    st = eng.stats()
+    assert st["pool_overflows"] == 0
+    assert (st["eval_cached"] > 0) == (cache > 0), st
     eng.close()
 
 
