@@ -676,8 +676,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
     // at the group's first row (a pair-local item grid: boards of any padded size), the last one may reach past the group's end — those
     // rows belong to another pair and are computed but never stored.
     const int n_boards = p.n_boards_dev ? *p.n_boards_dev : p.n_rows / p.board_pitch;
-    const int GB = p.group_boards;
     const int first_group = (int)cluster_id_x(), group_step = (int)n_clusters_x();
+    const int GB = (CONTIG && p.balance) ? max(1, min(p.group_boards, (n_boards + group_step - 1) / group_step)) : p.group_boards;
     const int L = p.n_layers;                                    // even: 2 per residual block
     // Two ways to form a group.  Boards that are exactly one work item (256 rows, Gomoku 15x15): the group's GB boards are STRIDED by the
     // number of pairs, so at any time the pairs stream through consecutive boards together (3 % faster than contiguous groups: the

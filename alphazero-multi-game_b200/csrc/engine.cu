@@ -380,7 +380,7 @@ struct Net {
             tp.f16 = f16; tp.n_layers = 2 * blocks; tp.p_total = p_total; tp.row_pitch = row_pitch; tp.board_pitch = board_pitch; tp.group_boards = nn::trunk_group_boards(board_pitch);
             // small batches (Go 9x9 at 2048 boards, chess at 1024): X + Y fit in L2 as a whole, so one group per CTA pair balances the pairs better
             // than groups of 7 work items (2048 Go boards = 120 such groups on 74 pairs)
-            if (board_pitch != 256 && (size_t)2 * max_boards * board_pitch * 256 <= ((size_t)110 << 20)) tp.group_boards = std::max(1, (max_boards + cs_sms / 2 - 1) / (cs_sms / 2));
+            if (board_pitch != 256 && (size_t)2 * max_boards * board_pitch * 256 <= ((size_t)110 << 20)) { tp.group_boards = std::max(1, (max_boards + cs_sms / 2 - 1) / (cs_sms / 2)); tp.balance = 1; }
             if (const char* d = getenv("AZ_TRUNK_DBG")) tp.dbg = atoi(d);
             if (const char* d = getenv("AZ_TRUNK_GROUP")) tp.group_boards = std::max(1, atoi(d));           // profiling switch: boards per group
             for (int l = 0; l < 2 * blocks; ++l) { tp.w[l] = w.conv_w[wi(1 + l, 0, 0)]; tp.bias[l] = w.conv_b[bi(1 + l, 0)]; }
@@ -537,7 +537,9 @@ struct EngineT : EngineBase {
     // Slots are split into `NG` stream groups; each group runs its own wave sequence (select → network → expand) on
     // its own stream with its own wave / activation buffers, so the tree kernels of one group overlap the tensor-core
     // pass of the other.  Move-commit kernels run once for all slots on the main stream.
-    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; EvalCache ec{}; Net net; };
+    struct Group { int t0 = 0, n = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; WaveBuffers wb{}; TreePools tp{}; EvalTT tt{}; EvalCache ec{}; Net net;
+                   // the simulation wave as a CUDA graph, one instance per pool-buffer parity (the node arrays swap at every move commit); replays add `n` launches
+                   struct WaveGraph { cudaGraphExec_t exec = nullptr; const void* key = nullptr; unsigned long long n = 0, n_net = 0; } wg[2]; };
     // AZ_EVAL_EXTERNAL: the caller's evaluator + staging (device: leaf paths by evaluation slot; host: the same + its answers)
     az_eval_fn ext_fn = nullptr; void* ext_user = nullptr;
     int32_t *ext_paths = nullptr, *ext_plen = nullptr, *ext_slot_tree = nullptr;
@@ -587,7 +589,8 @@ struct EngineT : EngineBase {
         for (auto& g : groups) {
             for (void* p : {(void*)g.wb.path, (void*)g.wb.path_len, (void*)g.wb.leaf_node, (void*)g.wb.leaf_kind, (void*)g.wb.leaf_value, (void*)g.wb.policy,
                             (void*)g.wb.value, (void*)g.wb.eval_slot, (void*)g.wb.n_eval, (void*)g.wb.eval_key, (void*)g.wb.legal, (void*)g.wb.n_legal, (void*)g.wb.slot_tree, (void*)g.wb.dd_keys, (void*)g.wb.dd_owner, (void*)g.wb.dd_idx, (void*)g.wb.cache_entry,
-                            (void*)g.ec.keys, (void*)g.ec.stamp, (void*)g.ec.value, (void*)g.ec.policy}) cudaFree(p);
+                            (void*)g.ec.keys, (void*)g.ec.stamp, (void*)g.ec.value, (void*)g.ec.policy, (void*)g.ec.wave}) cudaFree(p);
+            drop_graphs(g);
             g.net.destroy();
             if (g.ev) cudaEventDestroy(g.ev);
             if (g.stream) cudaStreamDestroy(g.stream);
@@ -707,7 +710,9 @@ struct EngineT : EngineBase {
                 long long want = c.eval_cache_entries > 0 ? (long long)c.eval_cache_entries : (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw));
                 want = std::max<long long>(want / NG, 64);
                 unsigned int capn = 64; while ((long long)capn * 2 <= want && capn < (1u << 30)) capn <<= 1;
-                g.ec.mask = capn - 1; g.ec.pw = pw; g.ec.wave = 0;
+                g.ec.mask = capn - 1; g.ec.pw = pw;
+                if (dev_alloc(&g.ec.wave, 2)) return -1;
+                { const uint32_t w0[2] = {1u, 1u}; AZ_CUDA_CHECK(cudaMemcpy(g.ec.wave, w0, 8, cudaMemcpyHostToDevice)); }
                 if (dev_alloc(&g.ec.keys, capn) || dev_alloc(&g.ec.stamp, capn) || dev_alloc(&g.ec.value, capn) || dev_alloc(&g.ec.policy, (size_t)capn * pw) ||
                     dev_alloc(&g.wb.cache_entry, n)) return -1;
                 AZ_CUDA_CHECK(cudaMemset(g.ec.keys, 0, (size_t)capn * 8)); AZ_CUDA_CHECK(cudaMemset(g.ec.stamp, 0, (size_t)capn * 4));
@@ -762,6 +767,7 @@ struct EngineT : EngineBase {
         if (sync_all()) return -1;
         if (groups[0].net.load(blob, bytes, stream)) return -1;
         for (size_t gi = 1; gi < groups.size(); ++gi) groups[gi].net.share(groups[0].net);
+        for (auto& g : groups) drop_graphs(g);                       // weight images may have moved
         for (auto& g : groups)      // a new network: cached evaluations of the old one are void
             if (g.ec.keys) { AZ_CUDA_CHECK(cudaMemsetAsync(g.ec.keys, 0, ((size_t)g.ec.mask + 1) * 8, stream)); AZ_CUDA_CHECK(cudaStreamSynchronize(stream)); }
         return 0;
@@ -847,16 +853,43 @@ struct EngineT : EngineBase {
         float ms = 0; if (cudaEventElapsedTime(&ms, cm_ev[0], cm_ev[1]) == cudaSuccess) { cm_ms += ms; ++cm_n; }
         cm_pending = false;
     }
+    // The simulation wave (mode 0) is the same launch sequence 800 times per move — its sizes travel in device counters — so it is captured
+    // once per pool-buffer parity into a CUDA graph and replayed (AZ_NO_WAVE_GRAPH=1: plain launches).  Root-expansion waves, the sampled
+    // (event-bracketed) waves, the external evaluator and the profiling modes launch directly.
+    bool use_graphs = getenv("AZ_NO_WAVE_GRAPH") == nullptr;
+    void drop_graphs(Group& g) { for (auto& w : g.wg) { if (w.exec) cudaGraphExecDestroy(w.exec); w = typename Group::WaveGraph{}; } }
     int wave(Group& g, int mode) {
-        cudaStream_t st = g.stream;
         const bool timed = (wave_timing || cfg.evaluator == AZ_EVAL_RESNET) && (wt_seen++ % 64) == 63;
+        if (!use_graphs || mode != 0 || timed || cfg.evaluator == AZ_EVAL_EXTERNAL || dup.counters != nullptr) return enqueue_wave(g, mode, timed);
+        typename Group::WaveGraph* w = nullptr;
+        for (auto& c : g.wg) if (c.exec && c.key == (const void*)g.tp.N) w = &c;
+        if (!w) {
+            w = g.wg[0].exec ? &g.wg[1] : &g.wg[0];
+            if (w->exec) { cudaGraphExecDestroy(w->exec); *w = typename Group::WaveGraph{}; }
+            const unsigned long long l0 = launches, n0 = g.net.launches;
+            cudaGraph_t graph = nullptr;
+            AZ_CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+            const int rc = enqueue_wave(g, 0, false);
+            const cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+            if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error(std::string("wave graph capture failed: ") + cudaGetErrorString(ce)); return -1; }
+            const cudaError_t ie = cudaGraphInstantiate(&w->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            AZ_CUDA_CHECK(ie);
+            w->key = (const void*)g.tp.N; w->n = launches - l0; w->n_net = g.net.launches - n0;
+            launches = l0; g.net.launches = n0;                      // the capture launched nothing
+        }
+        AZ_CUDA_CHECK(cudaGraphLaunch(w->exec, g.stream));
+        launches += w->n; g.net.launches += w->n_net;
+        return 0;
+    }
+    int enqueue_wave(Group& g, int mode, bool timed) {
+        cudaStream_t st = g.stream;
         if (timed) { for (auto& e : wt_ev) if (!e) cudaEventCreate(&e); cudaEventRecord(wt_ev[0], st); }
         AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.n_eval, 0, 4, st));
         if (g.wb.dd_keys) {
             AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_keys, 0, ((size_t)g.wb.dd_mask + 1) * 8, st));
             AZ_CUDA_CHECK(cudaMemsetAsync(g.wb.dd_owner, 0x7f, ((size_t)g.wb.dd_mask + 1) * 4, st));      // 0x7f7f7f7f > any tree index
         }
-        if (g.ec.keys) ++g.ec.wave;
         if (dup.counters) {
             AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys, 0, ((size_t)dup.wave_mask + 1) * 8, st));
             AZ_CUDA_CHECK(cudaMemsetAsync(dup.wave_keys_ref, 0, ((size_t)dup.wave_mask + 1) * 8, st));
@@ -870,7 +903,7 @@ struct EngineT : EngineBase {
             if (external_eval(g)) return -1;
         } else if (hash_eval()) {
             if (g.wb.dd_keys) {
-                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats);
+                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats, g.ec.wave);
                 AZ_LAUNCH_CHECK(); ++launches;
             }
             k_hash_eval<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>((A < HASH_EVAL_CHUNK ? A : HASH_EVAL_CHUNK) * 4), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, g.n,
@@ -879,7 +912,7 @@ struct EngineT : EngineBase {
         } else {
             g.net.fe_on = timed;
             if (g.wb.dd_keys) {
-                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats);
+                k_dedup_encode<G><<<blocks_for_warps(g.n), 128, warp_ws_bytes<G>(), st>>>(leaf_state + g.t0, root_state + g.t0, g.wb, enc, g.n, dstats, g.ec.wave);
                 AZ_LAUNCH_CHECK(); ++launches;
             }
             if (timed) cudaEventRecord(wt_ev[2], st);
@@ -1064,6 +1097,7 @@ struct EngineT : EngineBase {
     int set_search_params(float c_puct, int virtual_loss) override {
         AZ_CHECK(c_puct > 0.0f && virtual_loss >= 0, "bad search parameters");
         cfg.c_puct = c_puct; cfg.virtual_loss = virtual_loss;
+        for (auto& g : groups) drop_graphs(g);                       // the search parameters are kernel arguments of the captured waves
         return 0;
     }
     // children of the node reached from the root by `path` (actions): MCTSNode::children / actions of any node (mcts_node.h:54-75)

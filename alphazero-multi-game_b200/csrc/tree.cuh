@@ -80,7 +80,9 @@ struct EvalCache {
     float* policy;              // [cap][pw]: action-indexed (pw = ACTIONS), or the children's raw priors in child order for LEGAL_POLICY games (pw = MAX_CHILDREN)
     unsigned int mask;          // cap - 1
     int pw;
-    uint32_t wave;              // number of the running wave, >= 1
+    uint32_t* wave;             // device counters (the wave sequence is replayed as a CUDA graph: nothing per wave may be a kernel argument): [0] = number of the wave
+                                // k_select is running (>= 1), [1] = number of the wave k_expand_backup is running; k_dedup_encode, between the two, copies [0] to [1] and
+                                // advances [0]
 };
 __device__ __forceinline__ unsigned int cache_bucket(const EvalCache& ec, unsigned long long k) { return ((unsigned int)(mix64(k) >> 24) & ec.mask) & ~(unsigned int)(CACHE_WAYS - 1); }
 

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                     const unsigned int b = cache_bucket(ec, k);
 #pragma unroll
                     for (int wy = 0; wy < CACHE_WAYS; ++wy) if (ce < 0 && ec.keys[b + wy] == k) ce = (int)(b + wy);
-                    if (ce >= 0) ec.stamp[ce] = ec.wave;            // hit: refreshed, and protected from this wave's stores
+                    if (ce >= 0) ec.stamp[ce] = ec.wave[0];         // hit: refreshed, and protected from this wave's stores
                     wb.cache_entry[t] = ce;
                 }
                 if (ce < 0) {
@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
 // is bit-identical to evaluating the duplicate.
 template <class G>
 __global__ void __launch_bounds__(128) k_dedup_encode(const typename G::Leaf* __restrict__ leaf_state, const typename G::State* __restrict__ root_state,
-                                                     WaveBuffers wb, typename G::EncTarget enc, int T, Stats* stats) {
+                                                     WaveBuffers wb, typename G::EncTarget enc, int T, Stats* stats, uint32_t* cache_wave) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    if (cache_wave != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { const uint32_t wv = cache_wave[0]; cache_wave[1] = wv; cache_wave[0] = wv + 1; }   // EvalCache::wave (tree.cuh)
     if (t >= T) return;
     if (wb.leaf_kind[t] != LEAF_EVAL) return;
     if (wb.cache_entry != nullptr && wb.cache_entry[t] >= 0) {          // served by the evaluation cache
@@ -340,16 +341,17 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
             if (lane == 0) {
                 const unsigned long long k = wb.dd_keys[wb.dd_idx[t]];
                 const unsigned int b = cache_bucket(ec, k);
+                const uint32_t wave = ec.wave[1];
                 for (int attempt = 0; attempt < CACHE_WAYS && claimed < 0; ++attempt) {
                     int best = -1; uint32_t best_age = 0, best_s = 0;
                     for (int wy = 0; wy < CACHE_WAYS; ++wy) {
                         const uint32_t s = *(volatile uint32_t*)&ec.stamp[b + wy];
-                        if (s == ec.wave) continue;
-                        const uint32_t age = *(volatile unsigned long long*)&ec.keys[b + wy] == 0ULL ? 0xffffffffu : ec.wave - s;
+                        if (s == wave) continue;
+                        const uint32_t age = *(volatile unsigned long long*)&ec.keys[b + wy] == 0ULL ? 0xffffffffu : wave - s;
                         if (best < 0 || age > best_age) { best = wy; best_age = age; best_s = s; }
                     }
                     if (best < 0) break;
-                    if (atomicCAS(&ec.stamp[b + best], best_s, ec.wave) == best_s) claimed = (int)(b + best);
+                    if (atomicCAS(&ec.stamp[b + best], best_s, wave) == best_s) claimed = (int)(b + best);
                 }
                 if (claimed >= 0) { ec.keys[claimed] = k; ec.value[claimed] = v; }
             }
