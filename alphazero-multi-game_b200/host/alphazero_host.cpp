@@ -32,17 +32,22 @@ static void check(int rc, const char* what) {
 // ================================================================================================ core
 namespace core {
 std::unique_ptr<IGameState> createGameState(GameType type, int boardSize, bool variantRules) {
-    // reference: src/core/igamestate.cpp:10-69 (registry based); only what the engine can search is constructible
+    // reference: src/core/igamestate.cpp:10-69 / src/core/game_factory.cpp:90-112.  variantRules = true does not yield a usable state
+    // in the reference either, so it is an error here, raised where the reference would die (tests/test_ref_variants.py probes the compiled
+    // reference): Gomoku -> Renju, whose first getLegalMoves() / isLegalMove() for Black recurses without end (renju_double_four_or_more swaps
+    // the board accessor for a lambda that calls the accessor, gomoku_rules.cpp:198-220; Omok: omok_check_double_three_strict, :360-397) and
+    // overflows the stack; chess -> ChessState(chess960 = true), whose default position number 518 gets both knights on one square from
+    // Chess960::getPermutation (chess960.cpp:466-480) and fails its assert / throws "Invalid piece index in Chess960 generation" (:25-76).
+    // Go ignores the flag (Chinese rules, komi 7.5 either way).
     if (type == GameType::GOMOKU) {
-        if (variantRules) throw GameStateException("Failed to create game state: Renju rules are out of scope of the B200 engine");
+        if (variantRules) throw GameStateException("Failed to create game state: Renju rules never terminate in the reference (gomoku_rules.cpp:198-220); not provided");
         return std::make_unique<gomoku::GomokuState>(boardSize > 0 ? boardSize : 15, false, false, 0, false);
     }
     if (type == GameType::GO) {
-        if (variantRules) throw GameStateException("Failed to create game state: Japanese rules are out of scope of the B200 engine");
         return std::make_unique<go::GoState>(boardSize > 0 ? boardSize : 19);       // igamestate.cpp:50-55 default 19
     }
     if (type == GameType::CHESS) {
-        if (variantRules) throw GameStateException("Failed to create game state: Chess960 is out of scope of the B200 engine");
+        if (variantRules) throw GameStateException("Failed to create game state: Invalid piece index in Chess960 generation");      // the reference's own message (release build)
         return std::make_unique<chess::ChessState>();
     }
     throw GameStateException("Failed to create game state: unknown game type");
@@ -54,7 +59,9 @@ namespace gomoku {
 
 GomokuState::GomokuState(int bs, bool use_renju, bool use_omok, int, bool use_pro_long)
     : IGameState(core::GameType::GOMOKU), board_size(bs), current_player(BLACK), cells_((size_t)bs * bs, 0) {
-    if (use_renju || use_omok || use_pro_long) throw core::GameStateException("Renju / Omok / pro-long variants are out of scope of the B200 engine");
+    // Renju / Omok: see core::createGameState — the reference's forbidden-move tests do not return.  Pro-long opening is a constraint on Black's
+    // first moves only (gomoku_state.cpp:552-556); not provided.
+    if (use_renju || use_omok || use_pro_long) throw core::GameStateException("Renju / Omok forbidden-move rules never terminate in the reference (gomoku_rules.cpp:198-220, 360-397); variants are not provided");
     if (bs < 5 || bs > 19) throw core::GameStateException("unsupported board size");
 }
 bool GomokuState::is_occupied(int a) const { return a < 0 || a >= (int)cells_.size() || cells_[a] != 0; }

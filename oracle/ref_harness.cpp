@@ -164,6 +164,18 @@ void* ref_state_new(int game_type, int board_size) {
     } catch (...) {}
     return nullptr;
 }
+// the variant rules behind createGameState(type, boardSize, variantRules = true) (src/core/game_factory.cpp:90-112): Gomoku -> Renju
+// (variant 1; 2 = Omok, the GomokuState ctor's third flag), chess -> ChessState(chess960 = true).  The probe test runs these in a child
+// process: at the reference's HEAD they do not survive their first use (tests/test_ref_variants.py).
+void* ref_state_new_variant(int game_type, int board_size, int variant) {
+    if (game_type == 0) return new alphazero::gomoku::GomokuState(board_size, variant == 1, variant == 2, 1, false);
+    if (game_type == 1) return new alphazero::chess::ChessState(variant != 0);
+    return nullptr;
+}
+// ChessState(chess960 = true, fen = "", position_number): 1 = constructed, 0 = threw
+int ref_chess960_constructible(int position_number) {
+    try { alphazero::chess::ChessState s(true, "", position_number); return 1; } catch (...) { return 0; }
+}
 void ref_state_free(void* h) { delete (IGameState*)h; }
 void* ref_state_clone(void* h) { return ((IGameState*)h)->clone().release(); }
 int ref_state_make_move(void* h, int action) {
