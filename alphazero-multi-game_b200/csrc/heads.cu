@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
     float mx = -3.4e38f;
     for (int i = lane; i < p.A; i += 32) {
         float v = p.bias_p[i];
+#pragma unroll 4
         for (int sidx = 0; sidx < p.n_split_p; ++sidx) v += p.logits_part[(size_t)sidx * p.logits_stride + (size_t)b * p.ld_part + i];
         lg[i] = v; mx = fmaxf(mx, v);
     }
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
     float d = 0.0f;
     for (int i = lane; i < p.hidden_n; i += 32) {
         float h = p.bias_h[i];
+#pragma unroll 4
         for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
         d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
     }
@@ -46,9 +48,15 @@ constexpr int PV_WIDE_THREADS = 1024, PV_WIDE_MAX_PER_THREAD = 24;     // covers
 __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams p) {
     __shared__ float red_m[PV_WIDE_THREADS / 32], red_s[PV_WIDE_THREADS / 32];
     __shared__ float bcast[2];
+    __shared__ float hid[1024];
     const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (b >= nb) return;
+    if (tid < p.hidden_n) {      // value head, first half: one hidden unit per thread, ahead of the softmax passes
+        float h = p.bias_h[tid];
+        for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += __ldg(p.hidden_part + (size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + tid);
+        hid[tid] = fmaxf(h, 0.0f);
+    }
     // Online softmax: one pass gives every thread (max, sum of exp(x - max)) over its own logits, ONE block reduction combines the pairs
     // ((m1, s1) + (m2, s2) = (M, s1 e^(m1 - M) + s2 e^(m2 - M))), one expf per logit.  The kernel is latency-bound (one 1024-thread
     // block per SM, its phases do not overlap), so a reduction and an exp pass less is time saved.
@@ -103,13 +111,9 @@ __global__ void __launch_bounds__(PV_WIDE_THREADS) k_policy_value_wide(OutParams
         const int i = tid + k * PV_WIDE_THREADS;
         if (i < p.A) p.policy[(size_t)b * p.A + i] = v[k] * scale;
     }
-    if (warp == 0) {      // value head: tanh(relu(hidden) . w2 + b2)
+    if (warp == 0) {      // value head, second half: tanh(relu(hidden) . w2 + b2)
         float d = 0.0f;
-        for (int i = lane; i < p.hidden_n; i += 32) {
-            float h = p.bias_h[i];
-            for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
-            d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
-        }
+        for (int i = lane; i < p.hidden_n; i += 32) d = fmaf(hid[i], p.w2[i], d);
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
     }
@@ -128,9 +132,17 @@ __global__ void __launch_bounds__(PL_THREADS) k_policy_legal_value(LegalPolicyPa
     __shared__ __align__(16) float feat[PL_FEAT];
     __shared__ float logit[PL_MAX_LEGAL];
     __shared__ float red[PL_THREADS / 32];
+    __shared__ float hid[1024];
     const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (b >= nb) return;
+    // value head, first half: hidden unit per thread (split-K slabs added in slab order), issued ahead of the policy work so that its loads
+    // are in flight behind it.  (One warp walking 8 units x n_split slabs serially was 65 % of this kernel: profiles/r2l_chess_tree_kernels.md)
+    for (int i = tid; i < p.hidden_n; i += PL_THREADS) {
+        float h = p.bias_h[i];
+        for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += __ldg(p.hidden_part + (size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i);
+        hid[i] = fmaxf(h, 0.0f);
+    }
     {   // feature plane `tid` (8 features): hi + lo
         const uint4 hi = *reinterpret_cast<const uint4*>(p.featP + ((size_t)tid * p.feat_rows + b) * 8);
         const uint4 lo = *reinterpret_cast<const uint4*>(p.featP + ((size_t)(p.feat_lo_plane + tid) * p.feat_rows + b) * 8);
@@ -178,13 +190,9 @@ __global__ void __launch_bounds__(PL_THREADS) k_policy_legal_value(LegalPolicyPa
 #pragma unroll
     for (int k = 0; k < PL_THREADS / 32; ++k) sm += red[k];
     if (tid < n) p.policy[(size_t)b * p.A + (int)(uint16_t)lg[tid]] = e / sm;
-    if (warp == 0) {      // value head: tanh(relu(hidden) . w2 + b2)
+    if (warp == 0) {      // value head, second half: tanh(relu(hidden) . w2 + b2) (hid[] was published by the barriers above)
         float d = 0.0f;
-        for (int i = lane; i < p.hidden_n; i += 32) {
-            float h = p.bias_h[i];
-            for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
-            d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
-        }
+        for (int i = lane; i < p.hidden_n; i += 32) d = fmaf(hid[i], p.w2[i], d);
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
     }

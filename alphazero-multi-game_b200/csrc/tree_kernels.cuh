@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
             if (lane == 0) path[0] = node;
             int parentN = tp.N[base + node] + sp.virtual_loss;
             int f = rf;
+            int nc = tp.nchild[base + node];
             while (true) {
-                const int nc = tp.nchild[base + node];
                 // QUIRK M4: Q is negated only for children of depth-1 nodes (mcts_node.cpp:88-93)
                 const bool negate = (depth == 1);
                 const float sq = fsqrt((float)parentN);
@@ -92,9 +92,12 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                 ++depth;
                 if (lane == 0) path[depth] = child;
                 node = child;
+                // the child's header in one round trip (first / flags / nchild / N are independent loads), not one field per dependent step
                 f = tp.first[base + node];
-                if (f < 0 || (tp.flags[base + node] & NF_TERMINAL) || depth >= sp.max_depth - 1) break;
+                const uint8_t cfl = tp.flags[base + node];
+                nc = tp.nchild[base + node];
                 parentN = tp.N[base + node];
+                if (f < 0 || (cfl & NF_TERMINAL) || depth >= sp.max_depth - 1) break;
             }
             // --- leaf classification (parallel_mcts.cpp:300-313)
             const uint8_t fl = tp.flags[base + node];
@@ -392,21 +395,22 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     // removed (QUIRK M7): N_root += 4, VL_root += 3, W_root goes through -3,-3,+3,+v.
     const int plen = wb.path_len[t];
     if (plen == 0 && n_new > 0 && lane == 0) tp.sub[base + leaf] += n_new;      // root-expansion wave: no path, the leaf is the root
-    if (plen > 0 && lane == 0) {
+    if (plen > 0) {
+        // every path node's update depends only on its own W / N and on the sign the value has at its depth (v at the leaf, negated once per
+        // level up): one node per lane instead of a serial walk — the same fp32 operations per node, in the same order
         const int* path = wb.path + (size_t)t * MAX_DEPTH;
         const float vl = (float)sp.virtual_loss;
-        float cv = v;
-        for (int j = plen - 1; j >= 0; --j) {
+        for (int j = lane; j < plen; j += 32) {
             const size_t c = base + path[j];
+            const float cv = ((plen - 1 - j) & 1) ? -v : v;
             float wv = tp.W[c];
             if (j == 0) { wv = fsub(wv, vl); wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv);
                           tp.N[c] += sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
             else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] += 1; }
             tp.W[c] = wv;
             if (n_new) tp.sub[c] += n_new;
-            cv = -cv;
         }
-        atomicAdd(&stats->simulations, 1ULL);
+        if (lane == 0) atomicAdd(&stats->simulations, 1ULL);
     }
 }
 
