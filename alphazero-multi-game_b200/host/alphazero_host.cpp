@@ -520,6 +520,10 @@ void ParallelMCTS::build(const core::IGameState& rootState) {
     if (b) { c.net_blocks = b->blocks(); c.net_channels = b->channels(); }
     c.deterministic = config_.useDirichletNoise ? 0 : 1; c.dirichlet_alpha = config_.dirichletAlpha; c.dirichlet_epsilon = config_.dirichletEpsilon;
     c.auto_restart = 0; c.n_streams = 1;
+    // the TranspositionTable of the reference (own table of config.transpositionTableSize when none is passed, parallel_mcts.cpp:86-91) = the
+    // device evaluation cache; one tree adds numSimulations entries per move, so the request is capped at 64 K entries per ParallelMCTS
+    if (!external_ && config_.transpositionTableSize > 0) c.eval_cache_entries = (int)std::max<size_t>(64, std::min<size_t>(tt_ ? tt_->getSize() : (size_t)config_.transpositionTableSize, 65536));
+    else c.eval_cache_entries = -1;
     check(az_engine_create(&c, &eng_), "az_engine_create");
     if (external_) check(az_engine_set_external_evaluator(eng_, &ParallelMCTS::evalTrampoline, this), "az_engine_set_external_evaluator");
     else if (!b->isHash()) check(az_engine_load_weights(eng_, b->blob().data(), b->blob().size()), "az_engine_load_weights");
@@ -638,6 +642,11 @@ void ParallelMCTS::search() {
     if (az_engine_search(eng_, config_.numSimulations) != 0)
         throw std::runtime_error(std::string("az_engine_search: ") + az_last_error() + (evalError_.empty() ? "" : " (" + evalError_ + ")"));
     check(az_engine_sync(eng_), "az_engine_sync"); searched_ = true;
+    if (tt_) {      // TranspositionTable::getLookups / getHits (transposition_table.cpp:44-84): one lookup per evaluated leaf
+        az_stats s; check(az_engine_get_stats(eng_, &s), "az_engine_get_stats");
+        const size_t lk = (size_t)s.evaluations, ht = (size_t)(s.eval_shared + s.eval_cached);
+        tt_->addStats(lk - ttLookups_, ht - ttHits_); ttLookups_ = lk; ttHits_ = ht;
+    }
 }
 
 ParallelMCTS::RootStats ParallelMCTS::rootStats() const {

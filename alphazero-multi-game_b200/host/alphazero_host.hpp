@@ -304,19 +304,24 @@ struct MCTSStats {
 
 // The reference's TT is an evaluation cache that is result-transparent with a deterministic evaluator;
 // the engine has no use for it.  Kept so existing call sites construct and pass one.
+// mcts::TranspositionTable (include/alphazero/mcts/transposition_table.h, src/mcts/transposition_table.cpp:44-84, 128-176): the evaluation cache.
+// On the B200 engine the table itself lives on the device (az_config.eval_cache_entries, csrc/tree.cuh EvalCache: 64-bit network-input key ->
+// fp32 policy + value, 4-way buckets, filled and probed inside the waves); this object carries the size the caller asks for into the engines
+// built with it and collects their lookup / hit counters.  Searches are bit-identical with it present or absent.
 class TranspositionTable {
 public:
     explicit TranspositionTable(size_t size = 1048576, size_t numShards = 1024) : size_(size) { (void)numShards; }
     size_t getSize() const { return size_; }
-    float getHitRate() const { return 0.0f; }
-    size_t getLookups() const { return 0; }
-    size_t getHits() const { return 0; }
-    size_t getEntryCount() const { return 0; }
-    size_t getMemoryUsageBytes() const { return 0; }
-    void clear() {}
+    float getHitRate() const { return lookups_ ? (float)hits_ / (float)lookups_ : 0.0f; }
+    size_t getLookups() const { return lookups_; }
+    size_t getHits() const { return hits_; }
+    size_t getEntryCount() const { return std::min<size_t>(lookups_ - hits_, size_); }      // one store per miss
+    size_t getMemoryUsageBytes() const { return size_ * 16; }                                // key / stamp / value; the policies are per game type
+    void clear() { lookups_ = hits_ = 0; }                                                   // (device tables are cleared when an engine loads weights)
     void resize(size_t s) { size_ = s; }
+    void addStats(size_t lookups, size_t hits) { lookups_ += lookups; hits_ += hits; }       // called by ParallelMCTS::search
 private:
-    size_t size_;
+    size_t size_, lookups_ = 0, hits_ = 0;
 };
 
 // mcts::MCTSNode (include/alphazero/mcts/mcts_node.h:54-75, 80-119, 200-230) as a read-only SNAPSHOT of one node of the device tree: the
@@ -377,6 +382,7 @@ private:
     MCTSConfig config_;
     nn::NeuralNetwork* nn_;
     TranspositionTable* tt_ = nullptr;
+    size_t ttLookups_ = 0, ttHits_ = 0;      // engine counters already credited to tt_
     az_engine* eng_ = nullptr;
     bool external_ = false;      // nn_ is not a B200NeuralNetwork: the leaves are evaluated on the host through nn_->predictBatch (AZ_EVAL_EXTERNAL)
     std::string evalError_;
