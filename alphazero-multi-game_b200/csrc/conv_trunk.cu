@@ -21,11 +21,14 @@ struct Cfg {
     static constexpr int NAS = 2;                              // A stages
     static constexpr int WPLANE = COUT * 16;                   // bytes per 8-channel K chunk of the weights
     static constexpr int W_STAGE = (WK / 8) * WPLANE;
-    static constexpr int NWS = 4;                              // weight stages in the ring
+    // weights: a ring of 4 stages streamed per item — or, when all nine taps fit (the stems: 36 KB at 16 input channels, 72 KB at 32), loaded
+    // once and kept: re-streaming 9 stages through a 4-deep ring for every item (18 MMAs) made the stem wait on TMA round trips, not on stores
+    static constexpr bool RESIDENT = CIN < 64;
+    static constexpr int NWS = RESIDENT ? 9 * STAGES_PER_TAP : 4;
     static constexpr int OFF_W = NAS * A_STAGE;
     static constexpr int OFF_BIAS = OFF_W + NWS * W_STAGE;
     static constexpr int OFF_BARS = OFF_BIAS + COUT * 4;
-    static constexpr int OFF_TSLOT = OFF_BARS + 16 * 8;
+    static constexpr int OFF_TSLOT = OFF_BARS + (8 + 2 * NWS) * 8;
     static constexpr int SMEM = OFF_TSLOT + 16;
 };
 
@@ -79,10 +82,10 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::OFF_TSLOT);
     uint64_t* a_full = bars;          // [2] TMA → MMA
     uint64_t* a_empty = bars + 2;     // [2] MMA → TMA
-    uint64_t* w_full = bars + 4;      // [4]
-    uint64_t* w_empty = bars + 8;     // [4]
-    uint64_t* acc_full = bars + 12;   // [2] MMA → epilogue
-    uint64_t* acc_empty = bars + 14;  // [2] epilogue → MMA
+    uint64_t* acc_full = bars + 4;    // [2] MMA → epilogue
+    uint64_t* acc_empty = bars + 6;   // [2] epilogue → MMA
+    uint64_t* w_full = bars + 8;      // [NWS]
+    uint64_t* w_empty = bars + 8 + C::NWS;   // [NWS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_rows = p.n_boards_dev ? (*p.n_boards_dev) * p.board_pitch : p.n_rows;
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
         weights:
             for (int st = 0; st < 9 * C::STAGES_PER_TAP; ++st, ++wit) {
                 const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
+                if (C::RESIDENT && wit >= C::NWS) continue;             // resident weights: loaded with the first item only
                 if ((p.dbg & 4) && wit >= C::NWS) continue;
                 mbar_wait(&w_empty[ws], wph ^ 1);
                 if (lane == 0) {
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
 #pragma unroll
                     for (int h = 0; h < C::STAGES_PER_TAP; ++h, ++wit) {
                         const uint32_t ws = wit % C::NWS, wph = (wit / C::NWS) & 1;
-                        if (!(skip_w && wit >= C::NWS)) mbar_wait(&w_full[ws], wph);
+                        if (!((skip_w || C::RESIDENT) && wit >= C::NWS)) mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
                         const uint64_t b_st = b_desc0 + (uint64_t)(ws * (C::W_STAGE >> 4));
                         const uint64_t a_h = a_tap + (uint64_t)(h * (C::WK / 8) * (C::PLANE >> 4));
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(CONV1_THREADS, 1) k_conv3x3(const ConvParams p
                                               b_st + (uint64_t)(2 * kk * (C::WPLANE >> 4)), IDESC, kk == 0 ? accumulate : 1u);
                                 }
                             }
-                            if (!skip_w) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
+                            if (!skip_w && !C::RESIDENT) umma_commit(&w_empty[ws]);     // weight stage reusable once these MMAs retire
                             if (tap == 8 && h == C::STAGES_PER_TAP - 1) { if (!skip_a) umma_commit(&a_empty[as]); umma_commit(&acc_full[as]); }
                         }
                         __syncwarp();

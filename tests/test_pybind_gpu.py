@@ -350,3 +350,32 @@ def test_parallel_mcts_with_an_arbitrary_host_evaluator(game, board, moves):
         assert a == O.mcts_select_action(om, 1, 1.0)
         mcts.updateWithMove(a); O.mcts_update_with_move(om, a)
     assert "evaluations" in nn.getDeviceInfo()
+
+
+def test_transposition_table_object_is_the_device_evaluation_cache():
+    """mcts::TranspositionTable (python_bindings.cpp:255-266) on the B200 engine: the table lives on the device (az_config.eval_cache_entries),
+    the Python object carries the requested size into the engine and collects lookups / hits.  Searching a Go position twice from fresh
+    ParallelMCTS objects is NOT served across engines (one device table per engine, as the reference keeps one table per ParallelMCTS,
+    self_play_manager.cpp:159,175), but inside one engine a second search of the same root after set-up hits; results equal the oracle's."""
+    import _alphazero_cpp as az
+    O = _orc.oracle()
+    nn = az.createNeuralNetwork("hash", az.GameType.GO, 9)
+    tt = az.TranspositionTable(4096, 4)
+    state = az.createGameState(az.GameType.GO, 9, False)
+    mcts = az.ParallelMCTS(state, nn, tt, 1, 200, 1.5, 0.0, 3)
+    mcts.setDeterministicMode(True)
+    om = O.mcts_new(O.new_state(_orc.GO, 9), 200, 1.5, 3, 0, None, None)
+    for mv in range(3):
+        mcts.search(); O.mcts_search(om)
+        actions, visits, wsum, priors, root_n, root_w = mcts.getRootChildren()
+        b = O.root_stats(om)
+        assert actions == b["actions"].tolist() and visits == b["N"].tolist()
+        assert np.array_equal(np.array(wsum, np.float32).view(np.uint32), b["W"].view(np.uint32))
+        a = mcts.selectAction(True, 1.0)
+        assert a == O.mcts_select_action(om, 1, 1.0)
+        state.makeMove(a); mcts.updateWithMove(a); O.mcts_update_with_move(om, a)
+    assert tt.getSize() == 4096 and 3 * 150 <= tt.getLookups() <= 3 * 201      # one lookup per evaluated leaf (terminal leaves need none)
+    assert 0 <= tt.getHits() <= tt.getLookups() and 0.0 <= tt.getHitRate() <= 1.0
+    assert tt.getEntryCount() == min(tt.getLookups() - tt.getHits(), 4096)
+    tt.clear()
+    assert tt.getLookups() == 0
