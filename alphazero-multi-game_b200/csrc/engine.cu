@@ -358,13 +358,17 @@ struct Net {
         // A C -> C layer = NS x NS launches of the 128 -> 128 kernel: output slice co accumulates over the input slices, the first
         // launch adds bias (+ the block's skip connection), the following ones add the partial sum through the residual path (in
         // place: a thread re-reads only the rows it writes), ReLU on the last.  NS = 1 is the plain single launch.
+        int slice_launch = 0;
         auto layer = [&](const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* skip, int l, int reverse) -> int {
             for (int co = 0; co < NS; ++co)
                 for (int ci = 0; ci < NS; ++ci) {
                     cp.in = in + ci * slice; cp.out = out + co * slice;
                     cp.w = w.conv_w[wi(l, co, ci)]; cp.bias = ci == 0 ? w.conv_b[bi(l, co)] : w.zero_bias;
                     cp.resid = ci == 0 ? (skip ? skip + co * slice : nullptr) : cp.out;
-                    cp.relu = ci == NS - 1 ? 1 : 0; cp.reverse = NS == 1 ? reverse : 0; cp.pdl = pdl ? 1 : 0;
+                    cp.relu = ci == NS - 1 ? 1 : 0; cp.pdl = pdl ? 1 : 0;
+                    // item order: every launch starts on the rows its predecessor touched last (still in L2).  Slice launches: the partial sum a launch
+                    // wrote is the next one's residual, so consecutive launches alternate direction (AZ_CONV_NO_ALT: all forward)
+                    cp.reverse = NS == 1 ? reverse : (alt_order ? ((slice_launch++) & 1) : 0);
                     AZ_CHECK(nn::conv3x3_launch(cp, 128, cs_sms, cs) == 0, "conv launch failed"); ++launches;
                 }
             return 0;
