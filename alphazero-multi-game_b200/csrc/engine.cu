@@ -500,6 +500,7 @@ struct EngineBase {
     int device = 0;                 // every C-ABI call makes this the calling thread's current device (engines on several GPUs in one process)
     virtual ~EngineBase() {}
     virtual int set_search_params(float c_puct, int virtual_loss) = 0;
+    virtual int set_num_simulations(int sims) = 0;
     virtual int get_timing(az_timing* out) = 0;
     virtual int set_external(az_eval_fn fn, void* user) = 0;
     virtual int node_stats(int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n,
@@ -708,10 +709,14 @@ struct EngineT : EngineBase {
                 if (dev_alloc(&g.wb.dd_keys, cap_dd) || dev_alloc(&g.wb.dd_owner, cap_dd) || dev_alloc(&g.wb.dd_idx, n)) return -1;
             }
             if (want_cache) {
-                // default: 4 M entries over the groups (Gomoku 15x15: 916 B per entry = 3.8 GB), never more than ~1/16 of the device memory
+                // entries are split over the groups (Gomoku 15x15: 916 B per entry, 4 M = 3.8 GB); never more than ~1/16 of the device memory
                 const int pw = G::LEGAL_POLICY ? MC : A;
                 size_t free_b = 0, total_b = 0; AZ_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-                long long want = c.eval_cache_entries > 0 ? (long long)c.eval_cache_entries : (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw));
+                // default: room for four moves' worth of evaluations of every slot, between 64 K and 4 M entries (chess: 8.8 / 11.5 / 13.0 / 13.1 % hits at
+                // 256 K / 1 M / 4 M / 16 M entries in moves 6-11 of the bench)
+                const long long two_moves = 4LL * T * (std::max(c.num_simulations, 1) + 1);
+                long long want = c.eval_cache_entries > 0 ? (long long)c.eval_cache_entries
+                                                          : std::max<long long>(1 << 16, std::min<long long>(two_moves, (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw))));
                 want = std::max<long long>(want / NG, 64);
                 unsigned int capn = 64; while ((long long)capn * 2 <= want && capn < (1u << 30)) capn <<= 1;
                 g.ec.mask = capn - 1; g.ec.pw = pw;
@@ -1101,10 +1106,18 @@ struct EngineT : EngineBase {
     int set_search_params(float c_puct, int virtual_loss) override {
         AZ_CHECK(c_puct > 0.0f && virtual_loss >= 0, "bad search parameters");
         cfg.c_puct = c_puct; cfg.virtual_loss = virtual_loss;
+        if (sync_all()) return -1;
         for (auto& g : groups) drop_graphs(g);                       // the search parameters are kernel arguments of the captured waves
         return 0;
     }
     // children of the node reached from the root by `path` (actions): MCTSNode::children / actions of any node (mcts_node.h:54-75)
+    int set_num_simulations(int sims) override {
+        AZ_CHECK(sims >= 1, "num_simulations must be at least 1");
+        // the node pool was sized at creation (az_config.num_simulations / max_nodes_per_tree): a search must fit its worst-case growth
+        AZ_CHECK(((long long)sims + 1) * MC + 1 <= pool_nodes / T, "num_simulations exceeds what the node pool was sized for (create the engine with the largest count, or a larger max_nodes_per_tree)");
+        cfg.num_simulations = sims;                                // az_engine_play / the default of az_engine_search; regions are re-cut on demand (search())
+        return 0;
+    }
     int node_stats(int slot, const int32_t* path, int n_path, int32_t* actions, int32_t* visits, float* wsum, float* priors, int32_t* n,
                    int32_t* node_visits, float* node_wsum, float* node_prior, int32_t* node_flags) override {
         AZ_CHECK(slot >= 0 && slot < T, "slot out of range");
@@ -1464,6 +1477,7 @@ AZ_API int az_engine_examples_from_games(az_engine* e, const int32_t* moves, con
 AZ_API int az_engine_make_examples(az_engine* e, const void* samples, size_t n, int augment, float* planes, float* policy, float* value) { AZ_FWD(make_examples(samples, n, augment, planes, policy, value)); }
 AZ_API int az_engine_sync(az_engine* e) { AZ_FWD(sync()); }
 AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss) { AZ_FWD(set_search_params(c_puct, virtual_loss)); }
+AZ_API int az_engine_set_num_simulations(az_engine* e, int sims) { AZ_FWD(set_num_simulations(sims)); }
 AZ_API int az_engine_set_external_evaluator(az_engine* e, az_eval_fn fn, void* user) { AZ_FWD(set_external(fn, user)); }
 AZ_API int az_engine_get_timing(az_engine* e, az_timing* out) { if (!out) { az::set_error("null argument"); return -1; } AZ_FWD(get_timing(out)); }
 AZ_API int az_engine_node_stats(az_engine* e, int slot, const int32_t* path, int n_path, int32_t* a, int32_t* v, float* w, float* p, int32_t* n, int32_t* nv, float* nw,

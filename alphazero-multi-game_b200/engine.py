@@ -59,7 +59,7 @@ EXPORTS = ["az_config_default", "az_last_error", "az_engine_create", "az_engine_
            "az_engine_drain_samples_device", "az_engine_make_examples", "az_engine_examples_from_games", "az_engine_get_stats", "az_engine_sync", "az_engine_nn_forward",
            "az_engine_nn_bench", "az_engine_conv_bench", "az_engine_conv_sampled", "az_engine_event_record", "az_engine_event_elapsed",
            "az_rules_replay", "az_engine_set_search_params", "az_engine_node_stats", "az_device_count", "az_device_alloc", "az_device_free",
-           "az_device_memcpy", "az_device_sync", "az_engine_get_timing", "az_engine_set_external_evaluator"]
+           "az_device_memcpy", "az_device_sync", "az_engine_get_timing", "az_engine_set_external_evaluator", "az_engine_set_num_simulations"]
 
 
 def library_path():
@@ -118,6 +118,7 @@ def load_library():
         "az_engine_event_elapsed": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "az_rules_replay": [vp, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, f32p],
         "az_engine_set_search_params": [vp, C.c_float, C.c_int],
+        "az_engine_set_num_simulations": [vp, C.c_int],
         "az_engine_node_stats": [vp, C.c_int, i32p, C.c_int, i32p, i32p, f32p, f32p, i32p, i32p, f32p, f32p, i32p],
         "az_device_count": [i32p],
         "az_engine_get_timing": [vp, C.POINTER(Timing)],
@@ -219,6 +220,9 @@ class Engine:
 
     def play(self, n_moves=1):
         self._check(self.lib.az_engine_play(self.h, n_moves))
+
+    def set_num_simulations(self, sims):
+        self._check(self.lib.az_engine_set_num_simulations(self.h, int(sims)))
 
     def add_dirichlet_noise(self, alpha=0.03, epsilon=0.25):
         self._check(self.lib.az_engine_add_dirichlet_noise(self.h, alpha, epsilon))

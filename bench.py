@@ -181,6 +181,7 @@ def workload_config(c, args, world, slots, sims):
                         f"{c['blocks']}-block {c['channels']}-ch random-init ResNet (BASELINE.json configs[{c['idx']}])",
             "slots_per_gpu": slots, "sims_per_move": sims, "parallelism": f"games sharded over {world} GPU(s)",
             "step": "one self-play move on every slot (root expansion + sims waves + move commit)", "stream_groups": args.streams,
+            "preroll_moves": args.preroll,
             "net_precision": args.precision,
             "l2": "working set (node pools, activations) >> 126 MB L2; no explicit flush"}
 
@@ -217,6 +218,14 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
         dist.all_reduce(t, op=op)
         return float(t.item())
 
+    # Pre-roll (untimed, not part of the W warm-up steps): every slot starts from the initial position, so in the first moves thousands of games
+    # walk through the same openings and the evaluation cache / in-wave sharing serve a share of the leaves that a long self-play run (games at
+    # every phase) never sees (chess: 44 % at moves 3-8, 13 % at moves 6-11, 9 % at moves 40-60).  A few cheap moves (noise + temperature on, 48
+    # simulations each) take the games apart first; the timed steps then run the full configuration on mid-game positions.
+    if args.preroll > 0:
+        eng.set_num_simulations(min(48, sims))
+        eng.play(args.preroll)
+        eng.set_num_simulations(sims)
     for _ in range(warmup):
         eng.play(1)
     eng.drain_samples(out=samples_np)
@@ -372,6 +381,7 @@ def main():
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--streams", type=int, default=1, help="stream groups the slots are split into (tree kernels of one overlap the network pass of the other)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"], help="16-bit storage of activations / conv weights (az_config.net_precision)")
+    ap.add_argument("--preroll", type=int, default=8, help="untimed 48-simulation moves played before the warm-up so that the games are at different positions (0 = start every game at move 0)")
     ap.add_argument("--cache", type=int, default=0, help="evaluation cache entries (az_config.eval_cache_entries): 0 = default (4 M), -1 = off")
     ap.add_argument("--others", default="go9,chess,go19", help="comma-separated BASELINE configs measured into `other_configs` ('' = none)")
     ap.add_argument("--other-steps", type=int, default=5)

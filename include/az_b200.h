@@ -79,7 +79,7 @@ typedef struct az_config {
     int32_t eval_cache_entries; /* evaluation cache ACROSS waves (the reference's TranspositionTable, src/mcts/transposition_table.cpp:44-84, 128-176: 64-bit
                                    key -> (policy, value)): key = the whole network input, fp32 policies, 4-way buckets, oldest entry replaced — a hit
                                    returns exactly what the network would compute, so searches are bit-identical with it on or off.  0 = default (ResNet
-                                   evaluator: 4 M entries; hash evaluators: off), > 0 = entries (rounded down to a power of two), -1 = off.  Needs
+                                   evaluator: four moves' worth of evaluations of all slots, 64 K ... 4 M entries; hash evaluators: off), > 0 = entries (rounded down to a power of two), -1 = off.  Needs
                                    eval_dedup >= 0.  Cleared by az_engine_load_weights */
     int32_t dense_policy;       /* wide policy heads (chess, 20480 actions): 0 = inside the waves the network computes the logits of the leaf's
                                    legal moves only (their softmax equals the full softmax renormalised over the legal moves, which is what the
@@ -190,6 +190,10 @@ typedef struct az_timing {
 AZ_API int az_engine_get_timing(az_engine* e, az_timing* out);
 /* ParallelMCTS::setCPuct / setVirtualLoss / setConfig (src/mcts/parallel_mcts.cpp:1173-1261): take effect from the next search */
 AZ_API int az_engine_set_search_params(az_engine* e, float c_puct, int virtual_loss);
+/* ParallelMCTS::setNumSimulations (src/mcts/parallel_mcts.cpp:1183-1185) / SelfPlayManager's numSimulations: simulations per move of az_engine_play and the
+ * default of az_engine_search, from the next search on.  The node pool is sized at creation: counts above az_config.num_simulations need a
+ * max_nodes_per_tree that holds (num_simulations + 1) x max-children nodes per tree, else the call fails */
+AZ_API int az_engine_set_num_simulations(az_engine* e, int num_simulations);
 /* MCTSNode::children / actions / visitCount / valueSum / prior of ANY node (include/alphazero/mcts/mcts_node.h:54-75; what
  * ParallelMCTS::printSearchPath walks, parallel_mcts.cpp:1390-1450): the node reached from the slot's root by the action sequence
  * `path` (n_path = 0: the root).  Children in child order; *n_children in: capacity, out: count; node_* = the node's own fields,

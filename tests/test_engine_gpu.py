@@ -435,3 +435,22 @@ def test_eval_cache_across_waves_is_result_transparent(game, board):
     assert off1["eval_cached"] == 0 and on1["evaluations"] == off1["evaluations"]
     second_pass = on1["evaluations"] - on0["evaluations"]
     assert on1["eval_cached"] - on0["eval_cached"] >= 0.9 * second_pass, (on0, on1)      # the second pass re-evaluates (almost) nothing
+
+
+def test_set_num_simulations_between_moves():
+    """az_engine_set_num_simulations (ParallelMCTS::setNumSimulations, parallel_mcts.cpp:1183-1185): az_engine_play uses the new count from the
+    next move on; growing it back re-cuts the node regions before the search; a count the node pool cannot hold is refused."""
+    from _eng import hash_engine
+    eng = hash_engine(8, board=9, sims=300, deterministic=0, auto_restart=1, max_nodes_per_tree=0)
+    eng.set_num_simulations(40); eng.play(1)
+    assert eng.stats()["simulations"] == 8 * 40
+    eng.set_num_simulations(12); eng.play(2)
+    assert eng.stats()["simulations"] == 8 * (40 + 2 * 12)
+    eng.set_num_simulations(300); eng.play(1)
+    st = eng.stats()
+    assert st["simulations"] == 8 * (40 + 24 + 300) and st["pool_overflows"] == 0
+    with pytest.raises(RuntimeError):
+        eng.set_num_simulations(0)
+    with pytest.raises(RuntimeError, match="node pool"):
+        eng.set_num_simulations(100000)           # beyond what the pool was sized for at creation
+    eng.close()
