@@ -66,19 +66,32 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                 const bool negate = (depth == 1);
                 const float sq = fsqrt((float)parentN);
                 float best = -FLT_MAX; int bi = 0x7fffffff;
-                for (int i = lane; i < nc; i += 32) {
-                    const size_t c = base + f + i;
-                    const int n = tp.N[c];
-                    float sc;
-                    if (n == 0) sc = FLT_MAX;                   // mcts_node.cpp:63-66
-                    else {
-                        float q = fdiv(tp.W[c], (float)n);      // children carry no virtual loss when scored
-                        if (negate) q = -q;
-                        const float u = fdiv(fmul(fmul(sp.c_puct, tp.P[c]), sq), fadd(1.0f, (float)n));
-                        const float d = n < 5 ? fmul(0.05f, (float)(5 - n)) : 0.0f;   // :113-116
-                        sc = fadd(fadd(q, u), d);
+                // children in batches of 4 x 32: all N / W / P loads of a batch are issued before the first is used (with W and P loaded only
+                // behind the test of N, every 32 children cost two dependent memory round trips: 14 per level on a full Gomoku node)
+                for (int i0 = lane; i0 < nc; i0 += 128) {
+                    int cn[4]; float cw[4], cp[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        const size_t c = base + f + (i < nc ? i : 0);
+                        cn[u] = tp.N[c]; cw[u] = tp.W[c]; cp[u] = tp.P[c];
                     }
-                    if (sc > best) { best = sc; bi = i; }       // strict >: first child wins ties (:556)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        if (i >= nc) break;
+                        const int n = cn[u];
+                        float sc;
+                        if (n == 0) sc = FLT_MAX;                   // mcts_node.cpp:63-66
+                        else {
+                            float q = fdiv(cw[u], (float)n);        // children carry no virtual loss when scored
+                            if (negate) q = -q;
+                            const float uu = fdiv(fmul(fmul(sp.c_puct, cp[u]), sq), fadd(1.0f, (float)n));
+                            const float d = n < 5 ? fmul(0.05f, (float)(5 - n)) : 0.0f;   // :113-116
+                            sc = fadd(fadd(q, uu), d);
+                        }
+                        if (sc > best) { best = sc; bi = i; }       // strict >: first child wins ties (:556)
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -403,12 +416,12 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
         for (int j = lane; j < plen; j += 32) {
             const size_t c = base + path[j];
             const float cv = ((plen - 1 - j) & 1) ? -v : v;
-            float wv = tp.W[c];
+            float wv = tp.W[c]; const int nv = tp.N[c]; const int sv = tp.sub[c];       // the three loads together, then the stores
             if (j == 0) { wv = fsub(wv, vl); wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv);
-                          tp.N[c] += sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
-            else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] += 1; }
+                          tp.N[c] = nv + sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
+            else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] = nv + 1; }
             tp.W[c] = wv;
-            if (n_new) tp.sub[c] += n_new;
+            if (n_new) tp.sub[c] = sv + n_new;
         }
         if (lane == 0) atomicAdd(&stats->simulations, 1ULL);
     }
