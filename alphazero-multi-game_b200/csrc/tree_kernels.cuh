@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                 int ce = -1;
                 if (ec.keys != nullptr) {
                     const unsigned int b = cache_bucket(ec, k);
-#pragma unroll
-                    for (int wy = 0; wy < CACHE_WAYS; ++wy) if (ce < 0 && ec.keys[b + wy] == k) ce = (int)(b + wy);
+                    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(ec.keys + b), k23 = *reinterpret_cast<const ulonglong2*>(ec.keys + b + 2);   // the bucket: one 32-byte sector
+                    static_assert(CACHE_WAYS == 4, "the probe reads four ways");
+                    ce = k01.x == k ? (int)b : k01.y == k ? (int)b + 1 : k23.x == k ? (int)b + 2 : k23.y == k ? (int)b + 3 : -1;
                     if (ce >= 0) ec.stamp[ce] = ec.wave[0];         // hit: refreshed, and protected from this wave's stores
                     wb.cache_entry[t] = ce;
                 }
