@@ -157,12 +157,25 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_head_conv_pool(const HeadConv
             for (int oy = oyq; oy < 8; oy += 4) {
                 const int y0 = (oy * p.H) / 8, y1 = ((oy + 1) * p.H + 7) / 8;
                 float s[8] = {};
-                for (int y = y0; y < y1; ++y)
-                    for (int x = x0; x < x1; ++x) {
-                        const int row = y * p.row_pitch + x;
-                        const float4 u0 = *reinterpret_cast<const float4*>(sT + tile_off(row, 2 * cg));
-                        const float4 u1 = *reinterpret_cast<const float4*>(sT + tile_off(row, 2 * cg + 1));
-                        s[0] += u0.x; s[1] += u0.y; s[2] += u0.z; s[3] += u0.w; s[4] += u1.x; s[5] += u1.y; s[6] += u1.z; s[7] += u1.w;
+                // adaptive windows of boards 8..16 wide are at most 3 x 3 cells (launch check): a fixed, fully unrolled 3 x 3 walk with the cells
+                // outside the window predicated off — all shared-memory loads of a window in flight together, same summation order (y, then x)
+                float4 u[9][2];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {         // loads first, unconditionally (cells outside the window: clamped to the board, discarded below)
+                        const int row = min(y0 + dy, p.H - 1) * p.row_pitch + min(x0 + dx, p.W - 1);
+                        u[dy * 3 + dx][0] = *reinterpret_cast<const float4*>(sT + tile_off(row, 2 * cg));
+                        u[dy * 3 + dx][1] = *reinterpret_cast<const float4*>(sT + tile_off(row, 2 * cg + 1));
+                    }
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (y0 + dy < y1 && x0 + dx < x1) {
+                            const float4 u0 = u[dy * 3 + dx][0], u1 = u[dy * 3 + dx][1];
+                            s[0] += u0.x; s[1] += u0.y; s[2] += u0.z; s[3] += u0.w; s[4] += u1.x; s[5] += u1.y; s[6] += u1.z; s[7] += u1.w;
+                        }
                     }
                 const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
                 uint4 ov, ol;
@@ -190,7 +203,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_head_conv_pool(const HeadConv
 
 }  // namespace
 
-bool head_conv_supported(int channels, int board_pitch, int H, int W) { return channels == 128 && board_pitch <= HC_ROWS && H >= 8 && W >= 8; }
+// (H, W <= 16: every adaptive pooling window [floor(i H / 8), ceil((i + 1) H / 8)) is at most 3 cells wide — the epilogue's fixed 3 x 3 walk)
+bool head_conv_supported(int channels, int board_pitch, int H, int W) { return channels == 128 && board_pitch <= HC_ROWS && H >= 8 && W >= 8 && H <= 16 && W <= 16; }
 
 int head_conv_launch(const HeadConvParams& p, int grid, cudaStream_t s) {
     if (cudaError_t e = smem_opt_in((const void*)k_head_conv_pool, (int)HC_SMEM)) return (int)e;
