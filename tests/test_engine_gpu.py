@@ -454,3 +454,36 @@ def test_set_num_simulations_between_moves():
     with pytest.raises(RuntimeError, match="node pool"):
         eng.set_num_simulations(100000)           # beyond what the pool was sized for at creation
     eng.close()
+
+
+def test_eval_cache_tiny_capacity_with_stream_groups_is_result_transparent():
+    """The evaluation cache under pressure: 128 entries per stream group (32 buckets of 4 ways: almost every store evicts), two stream
+    groups (one table each), ResNet evaluator, Go 9x9 — bit-identical to the same engine with the cache off, and the cache does serve leaves:
+    odd slots start one pass into the game, i.e. on the position every even slot's tree evaluates in its first simulation (pass is child 0
+    and unvisited children are taken in order), one wave after the odd slots' root expansion stored it.  What gets stored depends on warp
+    timing; what a hit returns must not."""
+    from _eng import E, N
+    m = N.make_random_model(seed=9, randomize_bn=True, blocks=2, in_planes=8, board=9, actions=82)
+    blob = N.export_weights(m)
+    runs = []
+    for cache in (256, -1):
+        eng = E.Engine(game=E.GO, board_size=9, n_slots=12, evaluator=E.EVAL_RESNET, net_blocks=2, num_simulations=160, deterministic=1,
+                       auto_restart=0, n_streams=2, eval_cache_entries=cache)
+        eng.load_weights(blob)
+        for t in range(12):
+            eng.set_root(t, [-1] if t % 2 else [])
+        res = []
+        for move in range(4):
+            eng.search()
+            r = [eng.root_stats(t) for t in range(12)]
+            res.append(r)
+            eng.advance([int(x["actions"][int(np.argmax(x["N"]))]) if len(x["N"]) else -2 for x in r])
+        runs.append((res, eng.stats()))
+        eng.close()
+    (on, st_on), (off, st_off) = runs
+    assert st_on["eval_cached"] > 0 and st_off["eval_cached"] == 0 and st_on["evaluations"] == st_off["evaluations"] and st_on["pool_overflows"] == 0
+    for move in range(4):
+        for t in range(12):
+            a, b = on[move][t], off[move][t]
+            assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, t)
+            assert np.array_equal(a["W"].view(np.uint32), b["W"].view(np.uint32)) and np.array_equal(a["P"].view(np.uint32), b["P"].view(np.uint32)), (move, t)
