@@ -362,7 +362,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
            "eval_shared_frac_rank0": shared / max(leaf_evals, 1.0), "eval_cached_frac_rank0": cached / max(leaf_evals, 1.0),
            "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * net_flop / 1e12 / pk["bf16_sustained"],
            "step_budget_ms": {**{k: round(v, 3) for k, v in budget.items()}, "sum": round(budget_sum, 2), "sum_over_ms_per_step": round(budget_sum / (ms / steps), 4),
-                              "source": f"az_engine_get_timing: {int(nw)} sampled waves and {int(nm)} move commits of rank 0 inside the timed steps, scaled to {sims} + 1 waves and one commit"},
+                              "source": f"az_engine_get_timing: {int(nw)} sampled waves and {int(nm)} move commits of rank 0 inside the timed steps, scaled to {sims} + 1 waves and one commit; the sampled waves are launched kernel by kernel with events in between, the others are CUDA-graph replays, so on short waves (chess, Go 9x9) the sum overstates the step by the launch gaps the replay removes"},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
            "games_finished": int(e1["games"]), "samples_dropped": int(e1["samples_dropped"]), "pool_overflows": int(e1["pool_overflows"])}
     eng.close()
