@@ -217,22 +217,37 @@ def test_full_size_resnet_batch_position_independence():
     model = N.make_random_model(seed=3, blocks=10)
     with torch.no_grad():
         model.p_fc.weight *= 0.03; model.v_fc1.weight *= 0.02
-    eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=T, evaluator=E.EVAL_RESNET, net_blocks=10, num_simulations=sims,
-                   deterministic=1, auto_restart=0, max_nodes_per_tree=2 * (sims + 2) * 225 + 1)
-    eng.load_weights(N.export_weights(model))
-    for mv in range(2):
-        eng.search()
-        ref = eng.root_stats(0)
-        assert int(ref["N"].sum()) == sims * (mv + 1) or int(ref["N"].sum()) >= sims
-        for slot in (1, 255, 256, 1000, 2049, 4094, 4095):
-            st = eng.root_stats(slot)
-            assert np.array_equal(st["actions"], ref["actions"]) and np.array_equal(st["N"], ref["N"]), (mv, slot)
-            assert np.array_equal(bits(st["W"]), bits(ref["W"])) and np.array_equal(bits(st["P"]), bits(ref["P"])), (mv, slot)
-        eng.play(0)
-        a = int(ref["actions"][int(np.argmax(ref["N"]))])
-        eng.advance([a] * T)
-    assert eng.stats()["pool_overflows"] == 0
-    eng.close()
+    blob = N.export_weights(model)
+    first = None
+    # eval_dedup = -1: all 4096 boards really go through the network (with the sharing on, 4095 of them would ride on slot 0's evaluation);
+    # then the default engine (in-wave sharing + evaluation cache): one evaluation per wave, the same bits in every slot
+    for dedup in (-1, 0):
+        eng = E.Engine(game=E.GOMOKU, board_size=15, n_slots=T, evaluator=E.EVAL_RESNET, net_blocks=10, num_simulations=sims,
+                       deterministic=1, auto_restart=0, max_nodes_per_tree=2 * (sims + 2) * 225 + 1, eval_dedup=dedup)
+        eng.load_weights(blob)
+        seen = []
+        for mv in range(2):
+            eng.search()
+            ref = eng.root_stats(0)
+            assert int(ref["N"].sum()) == sims * (mv + 1) or int(ref["N"].sum()) >= sims
+            for slot in (1, 255, 256, 1000, 2049, 4094, 4095):
+                st = eng.root_stats(slot)
+                assert np.array_equal(st["actions"], ref["actions"]) and np.array_equal(st["N"], ref["N"]), (dedup, mv, slot)
+                assert np.array_equal(bits(st["W"]), bits(ref["W"])) and np.array_equal(bits(st["P"]), bits(ref["P"])), (dedup, mv, slot)
+            seen.append(ref)
+            eng.play(0)
+            a = int(ref["actions"][int(np.argmax(ref["N"]))])
+            eng.advance([a] * T)
+        st = eng.stats()
+        assert st["pool_overflows"] == 0
+        assert (st["eval_shared"] == 0) if dedup < 0 else (st["eval_shared"] + st["eval_cached"] >= st["evaluations"] * 4090 // 4096)
+        eng.close()
+        if first is None:
+            first = seen
+        else:
+            for a, b in zip(first, seen):
+                assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"])
+                assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"]))
 
 
 def test_c_abi_error_behaviour():
