@@ -341,6 +341,20 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
                 "launch_ms_timed_alone": conv_ms_alone, "flop_per_launch": conv_flop,
                 "whole_net_ms": nn_ms, "whole_net_tflops": net_flop * slots / (nn_ms / 1e3) / 1e12}
 
+    # ---- the synchronised opening phase beside it (rank 0; skipped for configs whose step takes seconds) -------
+    # every slot restarted at move 0 with an empty evaluation cache, 3 untimed + 3 timed moves: what a fresh batch of games sees while all
+    # of them still walk through the same openings (the cache / in-wave sharing serve a large share of the leaves).  Reported, not the value.
+    opening = None
+    if rank == 0 and args.preroll > 0 and (ms / steps < 1500.0 or key == args.game):
+        eng.load_weights(blob); eng.reset_games()
+        eng.play(3); eng.drain_samples(out=samples_np)
+        eng.sync(); o0 = eng.stats(); eng.event_record(2)
+        eng.play(3)
+        eng.event_record(3); oms = eng.event_elapsed(2, 3); o1 = eng.stats()
+        ol = float(o1["evaluations"] - o0["evaluations"])
+        opening = {"value_rank0": float(o1["simulations"] - o0["simulations"]) / (oms / 1e3), "unit": UNIT, "moves": "3-5 of games that all start together at move 0",
+                   "eval_cached_frac": float(o1["eval_cached"] - o0["eval_cached"]) / max(ol, 1.0), "eval_shared_frac": float(o1["eval_shared"] - o0["eval_shared"]) / max(ol, 1.0)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own serial search on the host cores --
     cpu = None
     if want_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -363,7 +377,7 @@ def measure(key, args, steps, warmup, e2e_steps, rank, world, local, dist, slots
            "tensor_roofline_frac_in_step": (evals / (ms / 1e3)) * net_flop / 1e12 / pk["bf16_sustained"],
            "step_budget_ms": {**{k: round(v, 3) for k, v in budget.items()}, "sum": round(budget_sum, 2), "sum_over_ms_per_step": round(budget_sum / (ms / steps), 4),
                               "source": f"az_engine_get_timing: {int(nw)} sampled waves and {int(nm)} move commits of rank 0 inside the timed steps, scaled to {sims} + 1 waves and one commit; the sampled waves are launched kernel by kernel with events in between, the others are CUDA-graph replays, so on short waves (chess, Go 9x9) the sum overstates the step by the launch gaps the replay removes"},
-           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "opening_phase": opening, "gpu_launches": launches, "clocks": clk,
            "games_finished": int(e1["games"]), "samples_dropped": int(e1["samples_dropped"]), "pool_overflows": int(e1["pool_overflows"])}
     eng.close()
     return out
@@ -411,7 +425,7 @@ def main():
     if args.game == "gomoku15" and args.slots is None and args.sims is None:
         for k in [x for x in args.others.split(",") if x]:
             o = measure(k, args, max(args.other_steps, 5), 3 if k != "go19" else 2, max(args.other_steps, 5) if k != "go19" else 3, rank, world, local, dist)
-            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "e2e",
+            others[k] = {kk: o[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "moves_per_sec", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "e2e", "opening_phase",
                                               "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")}
             others[k]["roofline"] = {kk: o["roofline"][kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launch_ms", "launch_ms_source", "whole_net_ms", "whole_net_tflops")}
     overflow = head["pool_overflows"] + sum(o["pool_overflows"] for o in others.values())
@@ -421,7 +435,7 @@ def main():
                 "dtype": args.precision, "dtype_note": "16-bit tensor-core operands (tcgen05 kind::f16), fp32 accumulation; fp16 is the reference's own half-precision mode "
                                                        "(TorchNeuralNetworkConfig::useFp16) and meets the KL <= 1e-3 tolerance on the BASELINE network; --precision bf16 runs the bf16 storage at the same rate",
                 "data": "synthetic"}
-        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "roofline", "cpu_baseline", "e2e",
+        line.update({k: head[k] for k in ("config", "moves_per_sec", "nn_evals_per_sec_rank0", "eval_shared_frac_rank0", "eval_cached_frac_rank0", "tensor_roofline_frac_in_step", "step_budget_ms", "roofline", "cpu_baseline", "e2e", "opening_phase",
                                           "gpu_launches", "clocks", "games_finished", "samples_dropped", "pool_overflows")})
         line["other_configs"] = others
         if overflow:
