@@ -863,6 +863,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         }
                         mbar_wait(&acc_full[as], ph);
                         tc_fence_after();
+                        if constexpr (!CONTIG) {
+                            // The MMAs of this item are complete, so its input rows are consumed.  On odd layers the input is Y, which nobody reads again
+                            // before the next even layer overwrites it: drop those lines from L2 (discard.global.L2) instead of letting them be written
+                            // back — ncu: 3.12 -> 1.76 GB written, 776 -> 531 MB read per 20-layer launch (profiles/r2_summary.md 17).  Rows 232-255 of a
+                            // board stay (the next board's halo reads them as zeros); X is never dead (skip connection, overwritten in place).
+                            if (p.discard && has_res) {
+                                const int r = (int)rank * 128 + warp * 32 + lane;               // row inside the 256-row board
+                                if ((r & 7) == 0 && r < 232) {
+                                    const char* y0 = reinterpret_cast<const char*>(p.Y) + ((size_t)CONV_GUARD + row) * 16;
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q) asm volatile("discard.global.L2 [%0], 128;" :: "l"(y0 + (size_t)q * p_total * 16) : "memory");
+                                }
+                            }
+                        } else {
+                            // Board-aligned groups: items are consecutive 256-row windows of the group, so the last 17 rows of item j are still the top
+                            // halo of item j + 1 — every item drops the window shifted back by 24 rows.  Never the group's last 17 rows (the next group's
+                            // halo reads them as zeros) and nothing outside [gbase, lim) (another pair's rows).
+                            if (p.discard && has_res) {
+                                const int rp = row - 24;
+                                if ((rp & 7) == 0 && rp >= gbase && rp + 8 <= lim - 17) {
+                                    const char* y0 = reinterpret_cast<const char*>(p.Y) + ((size_t)CONV_GUARD + rp) * 16;
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q) asm volatile("discard.global.L2 [%0], 128;" :: "l"(y0 + (size_t)q * p_total * 16) : "memory");
+                                }
+                            }
+                        }
                         // deferred publication of the PREVIOUS item: its stores were issued a whole MMA phase ago, so the cluster-scope release fence
                         // (which waits for this thread's outstanding stores) finds them drained
                         if (pending_b && (j == 1 || nj < TRUNK_BATCHED_MIN)) { publish(1); pending_b = false; }

@@ -386,6 +386,8 @@ struct Net {
             // than groups of 7 work items (2048 Go boards = 120 such groups on 74 pairs)
             if (board_pitch != 256 && (size_t)2 * max_boards * board_pitch * 256 <= ((size_t)110 << 20)) { tp.group_boards = std::max(1, (max_boards + cs_sms / 2 - 1) / (cs_sms / 2)); tp.balance = 1; }
             if (const char* d = getenv("AZ_TRUNK_DBG")) tp.dbg = atoi(d);
+            static const bool no_discard = getenv("AZ_TRUNK_NO_DISCARD") != nullptr;
+            tp.discard = no_discard ? 0 : 1;
             if (const char* d = getenv("AZ_TRUNK_GROUP")) tp.group_boards = std::max(1, atoi(d));           // profiling switch: boards per group
             for (int l = 0; l < 2 * blocks; ++l) { tp.w[l] = w.conv_w[wi(1 + l, 0, 0)]; tp.bias[l] = w.conv_b[bi(1 + l, 0)]; }
             AZ_CHECK(nn::trunk_launch(tp, cs_sms, cs) == 0, "fused trunk launch failed"); ++launches;
