@@ -37,7 +37,7 @@ struct Cfg {
 // F2FP conversion that also does the ReLU and the fp16 saturation, one select for the pad-row mask.
 template <bool F16, bool RELU>
 __device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool valid,
-                                            __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store, bool skip_store) {
+                                            __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store, bool skip_store, uint64_t pol = 0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float v[8];
@@ -56,15 +56,17 @@ __device__ __forceinline__ void epi_chunk_t(const uint32_t* r, const uint4* res,
         for (int e = 0; e < 4; ++e) { const uint32_t pk = pack2_16<F16, RELU>(v[2 * e], v[2 * e + 1]); ob[e] = valid ? pk : 0u; }
         if (no_store && o.x != 0x7fc17fc1u) continue;       // profiling experiment (dbg & 32): keep the math, drop the store
         if (skip_store) continue;                           // k_trunk_pair: a row past the end of this pair's board group belongs to another pair
-        *reinterpret_cast<uint4*>(out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8) = o;
+        __nv_bfloat16* dst = out + ((size_t)(c0 / 8 + q) * p_total + grow) * 8;
+        if (pol) asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w), "l"(pol) : "memory");
+        else *reinterpret_cast<uint4*>(dst) = o;
     }
 }
 __device__ __forceinline__ void pair_epi_chunk(bool f16, const uint32_t* r, const uint4* res, bool has_res, const float* sBias, int c0, bool relu, bool valid,
-                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false) {
-    if (f16) { if (relu) epi_chunk_t<true, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store);
-               else epi_chunk_t<true, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store); }
-    else { if (relu) epi_chunk_t<false, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store);
-           else epi_chunk_t<false, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store); }
+                                               __nv_bfloat16* out, size_t p_total, size_t grow, bool no_store = false, bool skip_store = false, uint64_t pol = 0) {
+    if (f16) { if (relu) epi_chunk_t<true, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store, pol);
+               else epi_chunk_t<true, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store, pol); }
+    else { if (relu) epi_chunk_t<false, true>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store, pol);
+           else epi_chunk_t<false, false>(r, res, has_res, sBias, c0, valid, out, p_total, grow, no_store, skip_store, pol); }
 }
 
 // 8 epilogue warps (warps 0-3: rows 0-127 of the item, warps 4-7: rows 128-255; a warp reads TMEM lanes 32 (w % 4) ...), warp 8 = TMA
@@ -820,6 +822,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
             const bool f16 = p.f16 != 0;
             uint32_t ait = 0;
             bool pending_b = false;
+            // X — the skip connection, live across two layers (input of the next layer, residual of the one after) — is stored with an L2 evict_last
+            // policy: with the dead Y rows discarded this brings the launch to 1.12 GB written (ncu), profiles/r2_summary.md 17
+            uint64_t pol_last = 0;
+            if (p.discard) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
             // "these items of the current layer are in memory", to both CTAs' producers.  One publication per CTA: a named barrier orders the
             // four epilogue warps' stores before thread 0's cluster-scope release fence; the generic → async proxy fence sits on the consumer
             // side, one thread, right before the TMA loads.  The fence costs an L2 round trip, so a layer publishes only twice: its first
@@ -898,18 +904,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_trunk_pair(const TrunkParam
                         tmem_ld32(taddr, ra);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 32, rb);
-                        pair_epi_chunk(f16, ra, res, has_res, bias, 0, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, ra, res, has_res, bias, 0, true, valid, out, p_total, grow, false, CONTIG && !mine, has_res ? pol_last : 0);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 64, ra);
-                        pair_epi_chunk(f16, rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, rb, res + 4, has_res, bias, 32, true, valid, out, p_total, grow, false, CONTIG && !mine, has_res ? pol_last : 0);
                         tmem_ld_wait();
                         tmem_ld32(taddr + 96, rb);
-                        pair_epi_chunk(f16, ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, ra, res + 8, has_res, bias, 64, true, valid, out, p_total, grow, false, CONTIG && !mine, has_res ? pol_last : 0);
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                        pair_epi_chunk(f16, rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow, false, CONTIG && !mine);
+                        pair_epi_chunk(f16, rb, res + 12, has_res, bias, 96, true, valid, out, p_total, grow, false, CONTIG && !mine, has_res ? pol_last : 0);
                         if (j == nj - 1) { if (nj >= TRUNK_BATCHED_MIN) pending_b = true; else publish(0); }
                     }
                 }

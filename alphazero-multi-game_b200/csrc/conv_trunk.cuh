@@ -70,7 +70,7 @@ struct TrunkParams {
     int group_boards;                            // boards a CTA pair takes through all layers at a time (trunk_group_boards): 74 pairs x 7 items x 128 KB stay in L2
     int balance;                                 // 1 (boards of any size, one group per pair): the group size follows the number of boards of THIS launch (device counter), so that
                                                  // every pair gets a group when in-wave sharing / the evaluation cache leave fewer boards than the engine has slots
-    int discard;                                 // 1: consumed Y rows are dropped from L2 instead of written back (256-row boards; AZ_TRUNK_NO_DISCARD=1 switches it off)
+    int discard;                                 // 1: L2 management — consumed Y rows are dropped from L2 instead of written back, X is stored evict_last (AZ_TRUNK_NO_DISCARD=1: off)
     int dbg;                                     // profiling experiments only (AZ_TRUNK_DBG): 1 = no cluster-scope release fence, 2 = no proxy fence, 4 = publish every item at once instead of one item later; 0 in production
 };
 bool trunk_fused_supported(int channels, int board_pitch, int row_pitch, int n_layers);
