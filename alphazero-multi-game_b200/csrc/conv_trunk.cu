@@ -500,6 +500,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
                 for (int tap = 0; tap < 9; ++tap) bulk_g2s(sW + tap * C::WTAP, wsrc + (size_t)tap * C::WTAP, C::WTAP, w_full);
                 grid_dep_wait();            // PDL: everything above ran under the previous layer's tail; its activations are needed from here on
                 grid_dep_launch();          // (after the wait, so a dependent grid can only start once this grid's own prerequisites are complete)
+                uint64_t pol_stream = 0;
+                if (p.l2_hints & 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
                 uint32_t ait = 0;
                 for (int item = first_item; item < n_items; item += item_step, ++ait) {
                     const uint32_t as = ait & 1, aph = (ait >> 1) & 1;
@@ -507,10 +509,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
                     const size_t row0 = (size_t)CONV_GUARD + (size_t)item_eff * 256 + rank * 128 - WIDE_HALO;
                     mbar_wait(&p0_empty[as], aph ^ 1);
                     mbar_arrive_expect_tx(&p0_full[as], C::HALF);
-                    for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP0 + as * C::HALF + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &p0_full[as]);
+                    if (pol_stream) { for (int kc = 0; kc < 8; ++kc) bulk_g2s_hint(sP0 + as * C::HALF + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &p0_full[as], pol_stream); }
+                    else for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP0 + as * C::HALF + kc * C::PLANE, p.in + ((size_t)kc * p.p_total + row0) * 8, C::PLANE, &p0_full[as]);
                     mbar_wait(p1_empty, (ait & 1) ^ 1);
                     mbar_arrive_expect_tx(p1_full, C::HALF);
-                    for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP1 + kc * C::PLANE, p.in + ((size_t)(8 + kc) * p.p_total + row0) * 8, C::PLANE, p1_full);
+                    if (pol_stream) { for (int kc = 0; kc < 8; ++kc) bulk_g2s_hint(sP1 + kc * C::PLANE, p.in + ((size_t)(8 + kc) * p.p_total + row0) * 8, C::PLANE, p1_full, pol_stream); }
+                    else for (int kc = 0; kc < 8; ++kc) bulk_g2s(sP1 + kc * C::PLANE, p.in + ((size_t)(8 + kc) * p.p_total + row0) * 8, C::PLANE, p1_full);
                 }
             }
             __syncwarp();
@@ -579,6 +583,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
             const bool has_res = p.resid != nullptr, relu = p.relu != 0, f16 = p.f16 != 0;
             const size_t p_total = (size_t)p.p_total;
             uint32_t ait = 0;
+            uint64_t pol = 0;
+            if (p.l2_hints & 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
             grid_dep_wait();                // PDL: the residual is read, and the output written, only after the previous layer has completed
             for (int item = first_item; item < n_items; item += item_step, ++ait) {
                 const uint32_t as = ait & 1, ph = (ait >> 1) & 1;
@@ -597,18 +603,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv3x3_pair_wide(const Con
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, rb);
-                pair_epi_chunk(f16, ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, ra, res, has_res, sBias, 0, relu, valid, p.out, p_total, grow, false, false, pol);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, ra);
-                pair_epi_chunk(f16, rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, rb, res + 4, has_res, sBias, 32, relu, valid, p.out, p_total, grow, false, false, pol);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, rb);
-                pair_epi_chunk(f16, ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, ra, res + 8, has_res, sBias, 64, relu, valid, p.out, p_total, grow, false, false, pol);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                pair_epi_chunk(f16, rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow);
+                pair_epi_chunk(f16, rb, res + 12, has_res, sBias, 96, relu, valid, p.out, p_total, grow, false, false, pol);
             }
         }
     }

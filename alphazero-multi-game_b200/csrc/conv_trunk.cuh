@@ -51,6 +51,8 @@ struct ConvParams {
     long long* trace;               // profiling only: per-item clock64 stamps of cluster 0 (conv_bench, AZ_CONV_TRACE), else nullptr
     int dbg;                        // profiling experiments only (conv_bench): see conv_trunk.cu; 0 in production
     int f16;                        // 1: activations, residual and weights are fp16 (else bf16) in the same 16-bit containers
+    int l2_hints;                   // wide pair kernel (slice launches of 256-channel trunks): bit 0 = stores evict_last (a partial sum the next launch reads back),
+                                    // bit 1 = activation loads evict_first (streamed once per launch)
     int pdl;                        // pair kernels: launch with programmatic stream serialization (the prologue — barriers, TMEM, the resident
                                     // weight half — runs while the previous kernel of the stream drains; activations are touched after griddepcontrol.wait)
 };

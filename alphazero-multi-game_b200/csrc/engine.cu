@@ -369,6 +369,9 @@ struct Net {
                     // item order: every launch starts on the rows its predecessor touched last (still in L2).  Slice launches: the partial sum a launch
                     // wrote is the next one's residual, so consecutive launches alternate direction (AZ_CONV_NO_ALT: all forward)
                     cp.reverse = NS == 1 ? reverse : (alt_order ? ((slice_launch++) & 1) : 0);
+                    // slice launches: a partial sum (ci < NS - 1) is read back by the next launch — keep it in L2; the activations stream through once
+                    static const int hint_bits = getenv("AZ_SLICE_HINTS") ? atoi(getenv("AZ_SLICE_HINTS")) : 3;      // profiling switch: 0 = no hints
+                    cp.l2_hints = NS > 1 ? ((ci < NS - 1 ? (hint_bits & 1) : 0) | (hint_bits & 2)) : 0;
                     AZ_CHECK(nn::conv3x3_launch(cp, 128, cs_sms, cs) == 0, "conv launch failed"); ++launches;
                 }
             return 0;
