@@ -719,17 +719,21 @@ struct EngineT : EngineBase {
                 size_t free_b = 0, total_b = 0; AZ_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
                 // default: room for four moves' worth of evaluations of every slot, between 64 K and 4 M entries (chess: 8.8 / 11.5 / 13.0 / 13.1 % hits at
                 // 256 K / 1 M / 4 M / 16 M entries in moves 6-11 of the bench)
-                const long long two_moves = 4LL * T * (std::max(c.num_simulations, 1) + 1);
+                const long long four_moves = 4LL * T * (std::max(c.num_simulations, 1) + 1);
                 long long want = c.eval_cache_entries > 0 ? (long long)c.eval_cache_entries
-                                                          : std::max<long long>(1 << 16, std::min<long long>(two_moves, (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw))));
+                                                          : std::max<long long>(1 << 16, std::min<long long>(four_moves, (long long)std::min<size_t>((size_t)1 << 22, total_b / 16 / (size_t)(16 + 4 * pw))));
                 want = std::max<long long>(want / NG, 64);
                 unsigned int capn = 64; while ((long long)capn * 2 <= want && capn < (1u << 30)) capn <<= 1;
-                g.ec.mask = capn - 1; g.ec.pw = pw;
-                if (dev_alloc(&g.ec.wave, 2)) return -1;
-                { const uint32_t w0[2] = {1u, 1u}; AZ_CUDA_CHECK(cudaMemcpy(g.ec.wave, w0, 8, cudaMemcpyHostToDevice)); }
-                if (dev_alloc(&g.ec.keys, capn) || dev_alloc(&g.ec.stamp, capn) || dev_alloc(&g.ec.value, capn) || dev_alloc(&g.ec.policy, (size_t)capn * pw) ||
-                    dev_alloc(&g.wb.cache_entry, n)) return -1;
-                AZ_CUDA_CHECK(cudaMemset(g.ec.keys, 0, (size_t)capn * 8)); AZ_CUDA_CHECK(cudaMemset(g.ec.stamp, 0, (size_t)capn * 4));
+                // the cache is an optimisation: on a device that is nearly full (a caller-sized node pool) it shrinks, down to nothing, instead of failing the engine
+                while (capn > 64 && (size_t)capn * (16 + 4 * (size_t)pw) + ((size_t)1 << 30) > free_b) capn >>= 1;
+                if ((size_t)capn * (16 + 4 * (size_t)pw) + ((size_t)1 << 30) <= free_b) {
+                    g.ec.mask = capn - 1; g.ec.pw = pw;
+                    if (dev_alloc(&g.ec.wave, 2)) return -1;
+                    { const uint32_t w0[2] = {1u, 1u}; AZ_CUDA_CHECK(cudaMemcpy(g.ec.wave, w0, 8, cudaMemcpyHostToDevice)); }
+                    if (dev_alloc(&g.ec.keys, capn) || dev_alloc(&g.ec.stamp, capn) || dev_alloc(&g.ec.value, capn) || dev_alloc(&g.ec.policy, (size_t)capn * pw) ||
+                        dev_alloc(&g.wb.cache_entry, n)) return -1;
+                    AZ_CUDA_CHECK(cudaMemset(g.ec.keys, 0, (size_t)capn * 8)); AZ_CUDA_CHECK(cudaMemset(g.ec.stamp, 0, (size_t)capn * 4));
+                }
             }
             if (tt.keys) {
                 if (dev_alloc(&g.wb.eval_key, n)) return -1;
