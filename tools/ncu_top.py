@@ -10,7 +10,11 @@ for r in rows:
         cur["hdr"] = r
     elif cur is not None and len(r) == len(cur["hdr"]):
         cur["data"].append(r)
+seen = set()
 for b in blocks:
+    if (b["name"], len(b["data"])) in seen or not b["data"]:      # ncu repeats the kernel header line
+        continue
+    seen.add((b["name"], len(b["data"])))
     hdr = b["hdr"]; ci = {h: i for i, h in enumerate(hdr)}; data = b["data"]; s = ci["# Samples"]
     tot = sum(float(r[s] or 0) for r in data)
     print("==", b["name"][:100], "| samples", tot, "| instructions", len(data))
