@@ -684,10 +684,28 @@ __global__ void __launch_bounds__(128) k_reroot_copy(TreePools tp, TreePools np,
                 const int src = __ffs(m) - 1; m &= m - 1;
                 const int f = __shfl_sync(0xffffffffu, fo, src), n = __shfl_sync(0xffffffffu, no, src);
                 if (count + n > lim) { truncated = true; break; }
-                for (int i = lane; i < n; i += 32) {
-                    const size_t o = ob + f + i, d = nb + count + i;
-                    np.N[d] = tp.N[o]; np.W[d] = tp.W[o]; np.P[d] = tp.P[o]; np.act[d] = tp.act[o]; np.flags[d] = tp.flags[o];
-                    np.sub[d] = tp.sub[o]; np.nchild[d] = tp.nchild[o]; np.first[d] = tp.first[o];
+                // 4 x 32 children per pass, all eight fields of all four loaded before the first store: the copy moves ~10 GB per Gomoku move
+                // (profiles/r2_commit_kernels_ncu.csv) and with one child per lane in flight it ran at 8 % of the HBM roof
+                for (int i0 = lane; i0 < n; i0 += 128) {
+                    int32_t vN[4], vF[4], vS[4]; float vW[4], vP[4]; int16_t vA[4], vC[4]; uint8_t vL[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        if (i < n) {
+                            const size_t o = ob + f + i;
+                            vN[u] = tp.N[o]; vW[u] = tp.W[o]; vP[u] = tp.P[o]; vA[u] = tp.act[o]; vL[u] = tp.flags[o];
+                            vS[u] = tp.sub[o]; vC[u] = tp.nchild[o]; vF[u] = tp.first[o];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        if (i < n) {
+                            const size_t d = nb + count + i;
+                            np.N[d] = vN[u]; np.W[d] = vW[u]; np.P[d] = vP[u]; np.act[d] = vA[u]; np.flags[d] = vL[u];
+                            np.sub[d] = vS[u]; np.nchild[d] = vC[u]; np.first[d] = vF[u];
+                        }
+                    }
                 }
                 if (lane == 0) np.first[nb + j0 + src] = count;
                 count += n;
