@@ -237,3 +237,45 @@ def test_chess_legal_only_policy_equals_dense_softmax():
         ref = torch.softmax(lg[0, torch.tensor(a["actions"].astype(np.int64))], 0).numpy()
         kl = float((ref * (np.log(ref + 1e-30) - np.log(a["P"] + 1e-30))).sum())
         assert kl <= 1e-3, (t, kl)
+
+
+def test_chess_full_size_1024_slots_identical_and_oracle():
+    """BASELINE.json configs[4] at full size (chess, 1024 slots, 800 simulations), hash evaluator + the reference-table model, deterministic mode:
+    the slots cycle through four roots (start position, castling rights on both sides, an e.p. square, a random middlegame); every slot of a root
+    must hold the same tree — wherever it sits in the 1024-wide waves — and that tree must equal the oracle's serial 800-simulation search
+    bit for bit (child order, visit counts, valueSum / prior bits), over two moves with subtree reuse."""
+    O = _orc.oracle()
+    sims, T = 800, 1024
+    roots = [[], SCRIPTED[1][:8], SCRIPTED[2][:4], _random_games(O, 1, 40, seed=9)[0]]
+    R = len(roots)
+    eng = chess_engine(T, sims=sims)
+    searches = []
+    for r, mv in enumerate(roots):
+        s = O.new_state(CHESS, 8)
+        for a in mv:
+            assert O.state_make_move(s, a) == 0
+        assert not O.state_is_terminal(s)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+    for t in range(T):
+        eng.set_root(t, roots[t % R])
+    for move in range(2):
+        eng.search()
+        acts = []
+        for r in range(R):
+            O.mcts_search(searches[r])
+            b = O.root_stats(searches[r])
+            for slot in (r, r + R * 1, r + R * 127, r + R * 128, r + R * 255):
+                a = eng.root_stats(slot)
+                assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, r, slot)
+                assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, r, slot)
+                assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0], (move, r, slot)
+            acts.append(O.mcts_select_action(searches[r], 1, 1.0))
+            O.mcts_update_with_move(searches[r], acts[-1])
+        first = [eng.root_stats(r) for r in range(R)]
+        for t in range(R, T):                      # every slot, not only the sampled ones: same visit counts and valueSum bits as its root's first slot
+            a = eng.root_stats(t)
+            assert np.array_equal(a["N"], first[t % R]["N"]) and np.array_equal(bits(a["W"]), bits(first[t % R]["W"])), (move, t)
+        eng.advance([acts[t % R] for t in range(T)])
+    st = eng.stats()
+    assert st["simulations"] == 2 * sims * T and st["pool_overflows"] == 0, st
+    eng.close()

@@ -161,6 +161,45 @@ def test_go_search_matches_oracle_random_positions():
     eng.close()
 
 
+@pytest.mark.parametrize("board,sims", [(13, 400), (19, 500)])
+def test_go_search_matches_oracle_13_and_19(board, sims):
+    """The larger boards of BASELINE.json configs[3] (19x19: 6-word bitboards, 362 children per node) and 13x13: mid-game positions with
+    captures from random legal playouts, searched together and compared with the oracle's serial search bit for bit over two moves."""
+    O = _orc.oracle()
+    rng = np.random.default_rng(board)
+    T = 4
+    eng = go_engine(T, board=board, sims=sims)
+    searches = []
+    for t in range(T):
+        s = O.new_state(GO, board)
+        moves = []
+        for _ in range([0, 60, 150, 260][t] * board * board // 361):
+            lg = O.legal(s)
+            cand = lg[lg >= 0] if len(lg) > 1 else lg
+            a = int(rng.choice(cand))
+            assert O.state_make_move(s, a) == 0
+            moves.append(a)
+        assert not O.state_is_terminal(s)
+        eng.set_root(t, moves)
+        searches.append(O.mcts_new(s, sims, 1.5, 3, 0, None, None))
+    for mv in range(2):
+        eng.search()
+        acts = []
+        for t in range(T):
+            O.mcts_search(searches[t])
+            a, b = eng.root_stats(t), O.root_stats(searches[t])
+            assert np.array_equal(a["actions"], b["actions"]), (board, mv, t)
+            assert np.array_equal(a["N"], b["N"]), (board, mv, t)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (board, mv, t)
+            assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0]
+            act = O.mcts_select_action(searches[t], 1, 1.0)
+            acts.append(act)
+            O.mcts_update_with_move(searches[t], act)
+        eng.advance(acts)
+    assert eng.stats()["pool_overflows"] == 0
+    eng.close()
+
+
 def test_go_selfplay_loop_matches_oracle():
     """az_engine_play in deterministic mode against the oracle's playSingleGame restatement for the first 30 moves of a
     9x9 game: same moves, same recorded visit counts (pass = last entry of the visit vector)."""
@@ -250,6 +289,49 @@ def test_go_full_size_2048_slots_identical_and_golden():
         eng.advance([g["action"]] * T)
     st = eng.stats()
     assert st["simulations"] == 3 * 400 * T and st["pool_overflows"] == 0
+    eng.close()
+
+
+def test_go19_full_size_1024_slots_identical_and_oracle():
+    """BASELINE.json configs[3] at its per-GPU size (Go 19x19, 1024 slots, 400 simulations), hash evaluator, deterministic mode: the slots
+    alternate between the empty board and a 150-move middle game with captures; every slot of a root must hold the same tree, equal to the
+    oracle's serial search bit for bit, over two moves (subtree reuse, region re-cut at 362 children per node)."""
+    O = _orc.oracle()
+    board, sims, T = 19, 400, 1024
+    rng = np.random.default_rng(19)
+    s1 = O.new_state(GO, board)
+    mid = []
+    for _ in range(150):
+        lg = O.legal(s1)
+        a = int(rng.choice(lg[lg >= 0]))
+        assert O.state_make_move(s1, a) == 0
+        mid.append(a)
+    assert not O.state_is_terminal(s1)
+    roots, states = [[], mid], [O.new_state(GO, board), s1]
+    R = len(roots)
+    searches = [O.mcts_new(st, sims, 1.5, 3, 0, None, None) for st in states]
+    eng = go_engine(T, board=board, sims=sims, n_streams=1)
+    for t in range(T):
+        eng.set_root(t, roots[t % R])
+    for move in range(2):
+        eng.search()
+        acts = []
+        for r in range(R):
+            O.mcts_search(searches[r])
+            b = O.root_stats(searches[r])
+            a = eng.root_stats(r)
+            assert np.array_equal(a["actions"], b["actions"]) and np.array_equal(a["N"], b["N"]), (move, r)
+            assert np.array_equal(bits(a["W"]), bits(b["W"])) and np.array_equal(bits(a["P"]), bits(b["P"])), (move, r)
+            assert a["rootN"] == b["rootN"] and bits([a["rootW"]])[0] == bits([b["rootW"]])[0], (move, r)
+            acts.append(O.mcts_select_action(searches[r], 1, 1.0))
+            O.mcts_update_with_move(searches[r], acts[-1])
+        first = [eng.root_stats(r) for r in range(R)]
+        for t in range(R, T):
+            a = eng.root_stats(t)
+            assert np.array_equal(a["N"], first[t % R]["N"]) and np.array_equal(bits(a["W"]), bits(first[t % R]["W"])), (move, t)
+        eng.advance([acts[t % R] for t in range(T)])
+    st = eng.stats()
+    assert st["simulations"] == 2 * sims * T and st["pool_overflows"] == 0, st
     eng.close()
 
 
