@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
     const bool live = (tf & TF_ACTIVE) && !(tf & TF_GAME_OVER);
     if (live) {
         const int rf = tp.first[base + node];
-        const bool rterm = tp.flags[base + node] & NF_TERMINAL;
+        const uint8_t rflags = tp.flags[base + node];
+        const int rootN = tp.N[base + node], rootNc = tp.nchild[base + node];      // with first / flags: the root's header in one round trip
+        const bool rterm = rflags & NF_TERMINAL;
         if (mode == 1) {
             if (rf < 0 && !rterm) { kind = LEAF_EVAL; G::w_load_root(w, root_state + t, lane); }   // root needs its first evaluation
         } else if (rf >= 0 && !rterm) {
@@ -58,9 +60,10 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
             // loss while its children are scored (:461), so parentVisits = N_root + virtualLoss (:539).
             int* path = wb.path + (size_t)t * MAX_DEPTH;
             if (lane == 0) path[0] = node;
-            int parentN = tp.N[base + node] + sp.virtual_loss;
+            int parentN = rootN + sp.virtual_loss;
             int f = rf;
-            int nc = tp.nchild[base + node];
+            int nc = rootNc;
+            uint8_t lfl = rflags;          // flags of the node the descent stands on
             while (true) {
                 // QUIRK M4: Q is negated only for children of depth-1 nodes (mcts_node.cpp:88-93)
                 const bool negate = (depth == 1);
@@ -101,19 +104,22 @@ __global__ void __launch_bounds__(128) k_select(TreePools tp, const typename G::
                 }
                 if (bi == 0x7fffffff) break;                    // no selectable child (bestChild == nullptr)
                 const int child = f + bi;
-                G::w_apply(w, (int)tp.act[base + child], lane);
+                // the child's action and header in ONE round trip, issued before the move is applied (act / first / flags / nchild / N are
+                // independent loads; behind w_apply's shared-memory stores they would be a second dependent round trip per level)
+                const int cact = (int)tp.act[base + child];
+                const int cfirst = tp.first[base + child];
+                const uint8_t cfl = tp.flags[base + child];
+                const int cnc = tp.nchild[base + child];
+                const int cN = tp.N[base + child];
+                G::w_apply(w, cact, lane);
                 ++depth;
                 if (lane == 0) path[depth] = child;
                 node = child;
-                // the child's header in one round trip (first / flags / nchild / N are independent loads), not one field per dependent step
-                f = tp.first[base + node];
-                const uint8_t cfl = tp.flags[base + node];
-                nc = tp.nchild[base + node];
-                parentN = tp.N[base + node];
+                f = cfirst; nc = cnc; parentN = cN; lfl = cfl;
                 if (f < 0 || (cfl & NF_TERMINAL) || depth >= sp.max_depth - 1) break;
             }
             // --- leaf classification (parallel_mcts.cpp:300-313)
-            const uint8_t fl = tp.flags[base + node];
+            const uint8_t fl = lfl;
             if (fl & NF_TERMINAL) { kind = LEAF_TERMINAL; tvalue = result_to_value((fl >> NF_RESULT_SHIFT) & 3, G::w_player(w)); }
             else {
                 const int res = G::w_result(w, lane);
