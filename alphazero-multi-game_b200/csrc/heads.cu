@@ -4,6 +4,7 @@
 // src/nn/torch_neural_network.cpp:298-316), value = tanh(FC 256→1), plus the fp32-planes → bf16 input packer used by
 // az_engine_nn_forward.
 #include "heads.cuh"
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -37,6 +38,63 @@ __global__ void __launch_bounds__(128) k_policy_value(OutParams p) {
 #pragma unroll 4
         for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += p.hidden_part[(size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i];
         d = fmaf(fmaxf(h, 0.0f), p.w2[i], d);
+    }
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
+}
+
+// The same for A <= 32 * PER (Gomoku 225, Go 82 / 170 / 362) with a board's logits in registers: the kernel is a chain of memory round
+// trips (one warp per board), so all PER loads of a split-K slab are issued together, four slabs deep, instead of one element's slabs at
+// a time, and the logits are not written to memory and read back between the max / sum / store passes.  The arithmetic per element and
+// the order of every sum are those of k_policy_value: bit-identical output.
+template <int PER>
+__global__ void __launch_bounds__(128) k_policy_value_reg(OutParams p) {
+    const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nb) return;
+    constexpr int HP = 8;                                   // hidden units per lane and pass (hidden_n = 256: one pass)
+    float v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = lane + 32 * k; v[k] = i < p.A ? __ldg(p.bias_p + i) : 0.0f; }
+    const float* part = p.logits_part + (size_t)b * p.ld_part;
+#pragma unroll 4
+    for (int sidx = 0; sidx < p.n_split_p; ++sidx) {
+        float tk[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { const int i = lane + 32 * k; tk[k] = i < p.A ? part[(size_t)sidx * p.logits_stride + i] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) if (lane + 32 * k < p.A) v[k] += tk[k];
+    }
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = lane + 32 * k;
+        if (i < p.A) { mx = fmaxf(mx, v[k]); if (p.want_logits) p.logits[(size_t)b * p.A + i] = v[k]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) if (lane + 32 * k < p.A) { v[k] = expf(v[k] - mx); s += v[k]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = lane + 32 * k; if (i < p.A) p.policy[(size_t)b * p.A + i] = v[k] * inv; }
+    float d = 0.0f;
+    for (int i0 = 0; i0 < p.hidden_n; i0 += 32 * HP) {
+        float h[HP];
+#pragma unroll
+        for (int k = 0; k < HP; ++k) { const int i = i0 + lane + 32 * k; h[k] = i < p.hidden_n ? __ldg(p.bias_h + i) : 0.0f; }
+        const float* hpart = p.hidden_part + (size_t)b * p.hidden_n + i0;
+#pragma unroll 4
+        for (int sidx = 0; sidx < p.n_split_h; ++sidx) {
+            float tk[HP];
+#pragma unroll
+            for (int k = 0; k < HP; ++k) { const int i = lane + 32 * k; tk[k] = i0 + i < p.hidden_n ? hpart[(size_t)sidx * p.hidden_stride + i] : 0.0f; }
+#pragma unroll
+            for (int k = 0; k < HP; ++k) if (i0 + lane + 32 * k < p.hidden_n) h[k] += tk[k];
+        }
+#pragma unroll
+        for (int k = 0; k < HP; ++k) { const int i = i0 + lane + 32 * k; if (i < p.hidden_n) d = fmaf(fmaxf(h[k], 0.0f), __ldg(p.w2 + i), d); }
     }
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     if (lane == 0) p.value[b] = tanhf(d + p.b2[0]);
@@ -133,30 +191,42 @@ __global__ void __launch_bounds__(PL_THREADS) k_policy_legal_value(LegalPolicyPa
     __shared__ float logit[PL_MAX_LEGAL];
     __shared__ float red[PL_THREADS / 32];
     __shared__ float hid[1024];
+    __shared__ int acts_s[PL_MAX_LEGAL];
     const int nb = p.n_boards_dev ? *p.n_boards_dev : p.n_boards;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (b >= nb) return;
-    // value head, first half: hidden unit per thread (split-K slabs added in slab order), issued ahead of the policy work so that its loads
-    // are in flight behind it.  (One warp walking 8 units x n_split slabs serially was 65 % of this kernel: profiles/r2l_chess_tree_kernels.md)
-    for (int i = tid; i < p.hidden_n; i += PL_THREADS) {
+    // The kernel is a chain of dependent memory round trips (one block per board, ~7 blocks per SM): every load that does not depend on
+    // another one is issued before the first value is used — slot -> tree, the feature planes, and ALL split-K slabs of the value head's
+    // hidden units (chess at 1024 boards runs the FC split 16 ways: added one behind the other they were 16 round trips).
+    const int tree = p.slot_tree[b];
+    const uint4 fhi = *reinterpret_cast<const uint4*>(p.featP + ((size_t)tid * p.feat_rows + b) * 8);                       // feature plane `tid` (8 features): hi + lo
+    const uint4 flo = *reinterpret_cast<const uint4*>(p.featP + ((size_t)(p.feat_lo_plane + tid) * p.feat_rows + b) * 8);
+    constexpr int MAX_SPLIT = 16;
+    for (int i = tid; i < p.hidden_n; i += PL_THREADS) {      // value head, first half: hidden unit per thread (split-K slabs added in slab order)
+        float hp[MAX_SPLIT];
+#pragma unroll
+        for (int sidx = 0; sidx < MAX_SPLIT; ++sidx) hp[sidx] = sidx < p.n_split_h ? __ldg(p.hidden_part + (size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i) : 0.0f;
         float h = p.bias_h[i];
-        for (int sidx = 0; sidx < p.n_split_h; ++sidx) h += __ldg(p.hidden_part + (size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i);
+#pragma unroll
+        for (int sidx = 0; sidx < MAX_SPLIT; ++sidx) if (sidx < p.n_split_h) h += hp[sidx];
+        for (int sidx = MAX_SPLIT; sidx < p.n_split_h; ++sidx) h += __ldg(p.hidden_part + (size_t)sidx * p.hidden_stride + (size_t)b * p.hidden_n + i);
         hid[i] = fmaxf(h, 0.0f);
     }
-    {   // feature plane `tid` (8 features): hi + lo
-        const uint4 hi = *reinterpret_cast<const uint4*>(p.featP + ((size_t)tid * p.feat_rows + b) * 8);
-        const uint4 lo = *reinterpret_cast<const uint4*>(p.featP + ((size_t)(p.feat_lo_plane + tid) * p.feat_rows + b) * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&hi); const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(&lo);
+    const int n = min(p.n_legal[tree], PL_MAX_LEGAL);
+    const int16_t* lg = p.legal + (size_t)tree * p.legal_pitch;
+    if (tid < p.legal_pitch) acts_s[tid] = (int)(uint16_t)lg[tid];      // the leaf's legal actions (entries beyond n are not used), next to the load of n
+    {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&fhi); const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(&flo);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const float2 a = __bfloat1622float2(h[e]), c = __bfloat1622float2(l[e]); feat[tid * 8 + 2 * e] = a.x + c.x; feat[tid * 8 + 2 * e + 1] = a.y + c.y; }
     }
     __syncthreads();
-    const int tree = p.slot_tree[b];
-    const int n = min(p.n_legal[tree], PL_MAX_LEGAL);
-    const int16_t* lg = p.legal + (size_t)tree * p.legal_pitch;
+    // one legal move per warp at a time, two moves' weight rows in flight
+#pragma unroll 2
     for (int i = warp; i < n; i += PL_THREADS / 32) {
-        const int a = (int)(uint16_t)lg[i];
+        const int a = acts_s[i];
         const uint4* wr = reinterpret_cast<const uint4*>(p.w_rows + (size_t)a * PL_FEAT);
+        const float bp = __ldg(p.bias_p + a);                    // with the weight row, not behind the reduction
         float acc = 0.0f;
 #pragma unroll
         for (int j = 0; j < PL_FEAT / 256; ++j) {
@@ -168,7 +238,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_policy_legal_value(LegalPolicyPa
             acc = fmaf(w2.x, f1.x, acc); acc = fmaf(w2.y, f1.y, acc); acc = fmaf(w3.x, f1.z, acc); acc = fmaf(w3.y, f1.w, acc);
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) logit[i] = acc + p.bias_p[a];
+        if (lane == 0) logit[i] = acc + bp;
     }
     __syncthreads();
     // softmax over the n legal logits (thread i owns logit i)
@@ -189,7 +259,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_policy_legal_value(LegalPolicyPa
     sm = 0.0f;
 #pragma unroll
     for (int k = 0; k < PL_THREADS / 32; ++k) sm += red[k];
-    if (tid < n) p.policy[(size_t)b * p.A + (int)(uint16_t)lg[tid]] = e / sm;
+    if (tid < n) p.policy[(size_t)b * p.A + acts_s[tid]] = e / sm;
     if (warp == 0) {      // value head, second half: tanh(relu(hidden) . w2 + b2) (hid[] was published by the barriers above)
         float d = 0.0f;
         for (int i = lane; i < p.hidden_n; i += 32) d = fmaf(hid[i], p.w2[i], d);
@@ -221,7 +291,11 @@ int policy_value_launch(const OutParams& p, int max_boards, cudaStream_t s) {
         k_policy_value_wide<<<max_boards, PV_WIDE_THREADS, 0, s>>>(p);
         return (int)cudaGetLastError();
     }
-    k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
+    static const bool old_kernel = getenv("AZ_PV_OLD") != nullptr;      // parity switch: the memory-resident variant (tools/pv_bits.py compares the two bit for bit)
+    if (old_kernel) k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
+    else if (p.A <= 256) k_policy_value_reg<8><<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
+    else if (p.A <= 384) k_policy_value_reg<12><<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
+    else k_policy_value<<<(max_boards * 32 + 127) / 128, 128, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
 int policy_legal_value_launch(const LegalPolicyParams& p, int max_boards, cudaStream_t s) {
