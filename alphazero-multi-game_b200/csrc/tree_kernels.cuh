@@ -317,22 +317,43 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    // The kernel is a chain of dependent memory round trips (one warp per tree): every per-tree scalar it will need is loaded here, in ONE
+    // round trip, before the first of them is used (they were four: kind -> base / leaf -> slot / cache entry -> tree flags / alloc, and
+    // further down limit, the dedup entry and the path length one at a time).
     const int8_t kind = wb.leaf_kind[t];
+    const long long base_ = tp.base[t];
+    float v = wb.leaf_value[t];
+    const int leaf = wb.leaf_node[t];
+    const int slot_ = wb.eval_slot[t];
+    const int ce_ = ec.keys != nullptr ? wb.cache_entry[t] : -1;
+    const int ddi_ = (ec.keys != nullptr && wb.dd_idx != nullptr) ? wb.dd_idx[t] : -1;
+    const uint32_t cwave = ec.keys != nullptr ? ec.wave[1] : 0u;
+    const uint8_t tf = tp.tflags[t];
+    const int troot = tp.root[t];
+    const int alloc = tp.alloc[t];
+    const int tlimit = tp.limit[t];
+    const int plen = wb.path_len[t];
     if (kind == LEAF_NONE) return;
     constexpr int A = G::ACTIONS, MC = G::MAX_CHILDREN;
     constexpr int EXTRA = MC * 4 + (MC * 2 + 15) / 16 * 16;
     typename G::Warp& w = warp_ws<G>(smem, EXTRA);
     float* raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&w) + (sizeof(typename G::Warp) + 15) / 16 * 16);
     int16_t* acts = reinterpret_cast<int16_t*>(raw + MC);
-    const size_t base = (size_t)tp.base[t];
-    float v = wb.leaf_value[t];
-    const int leaf = wb.leaf_node[t];
+    const size_t base = (size_t)base_;
     int n_new = 0;                                      // children created by this simulation: added to every path node's descendant count
+    // the path nodes' statistics (one node per lane, backup below): nothing in the expansion writes W / N / sub of a path node, so they are
+    // fetched now and are in flight behind the expansion
+    const int* path = wb.path + (size_t)t * MAX_DEPTH;
+    const int pj = lane < plen ? path[lane] : 0;
+    float pW = 0.0f; int pN = 0, pS = 0;
+    if (lane < plen) { pW = tp.W[base + pj]; pN = tp.N[base + pj]; pS = tp.sub[base + pj]; }
 
     if (kind == LEAF_EVAL) {
-        int slot = wb.eval_slot[t];
+        int slot = slot_;
         const bool own_eval = slot >= 0;                     // this tree's leaf went through the evaluator itself
-        const int ce = ec.keys != nullptr ? wb.cache_entry[t] : -1;
+        const int ce = ce_;
+        // the key this evaluation is stored under (the wave's key set entry of this tree), fetched ahead of the store
+        const unsigned long long store_key = (ec.keys != nullptr && own_eval && ddi_ >= 0) ? wb.dd_keys[ddi_] : 0ULL;
         const float* pol; const float* cpol = nullptr;
         if (ce >= 0) {                                       // evaluation cache: an earlier wave's evaluation of the same network input
             cpol = ec.policy + (size_t)ce * ec.pw;
@@ -344,9 +365,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
             v = wb.value[slot];
         }
         G::w_load_leaf(w, leaf_state + t, root_state + t, lane);
-        const uint8_t tf = tp.tflags[t];
-        const bool first_fill = (tf & TF_FIRST_FILL) && leaf == tp.root[t];
-        const int alloc = tp.alloc[t];
+        const bool first_fill = (tf & TF_FIRST_FILL) && leaf == troot;
         // children = the legal moves in the reference's order, priors = policy[action] (0 for out-of-range actions, i.e.
         // Go's pass at -1), expandNodeWithPolicy parallel_mcts.cpp:690-711
         int n;
@@ -362,15 +381,20 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
             // store this evaluation: claim the oldest way of the bucket that was neither hit nor stored in this wave (tree.cuh)
             int claimed = -1;
             if (lane == 0) {
-                const unsigned long long k = wb.dd_keys[wb.dd_idx[t]];
+                const unsigned long long k = store_key;
                 const unsigned int b = cache_bucket(ec, k);
-                const uint32_t wave = ec.wave[1];
+                const uint32_t wave = cwave;
                 for (int attempt = 0; attempt < CACHE_WAYS && claimed < 0; ++attempt) {
                     int best = -1; uint32_t best_age = 0, best_s = 0;
+                    // the bucket's four stamps and four keys as eight independent loads (one round trip), then the choice
+                    uint32_t st[CACHE_WAYS]; unsigned long long ky[CACHE_WAYS];
+#pragma unroll
+                    for (int wy = 0; wy < CACHE_WAYS; ++wy) { st[wy] = *(volatile uint32_t*)&ec.stamp[b + wy]; ky[wy] = *(volatile unsigned long long*)&ec.keys[b + wy]; }
+#pragma unroll
                     for (int wy = 0; wy < CACHE_WAYS; ++wy) {
-                        const uint32_t s = *(volatile uint32_t*)&ec.stamp[b + wy];
+                        const uint32_t s = st[wy];
                         if (s == wave) continue;
-                        const uint32_t age = *(volatile unsigned long long*)&ec.keys[b + wy] == 0ULL ? 0xffffffffu : wave - s;
+                        const uint32_t age = ky[wy] == 0ULL ? 0xffffffffu : wave - s;
                         if (best < 0 || age > best_age) { best = wy; best_age = age; best_s = s; }
                     }
                     if (best < 0) break;
@@ -385,7 +409,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
                 else { for (int i = lane; i < A; i += 32) dst[i] = pol[i]; }
             }
         }
-        if (alloc + n > tp.limit[t]) {
+        if (alloc + n > tlimit) {
             if (lane == 0) { tp.tflags[t] = tf | TF_OVERFLOW; atomicAdd(&stats->pool_overflows, 1ULL); }
         } else if (n > 0) {
             // policySum accumulated in child order (parallel_mcts.cpp:705-711) — serial on purpose
@@ -413,17 +437,17 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreePools tp, const typen
     // Per path node the reference does W -= 3 (added after selection), then in reverse path order
     // W += 3, N += 1, W += v.  The root received one extra virtual loss at selection start that is never
     // removed (QUIRK M7): N_root += 4, VL_root += 3, W_root goes through -3,-3,+3,+v.
-    const int plen = wb.path_len[t];
     if (plen == 0 && n_new > 0 && lane == 0) tp.sub[base + leaf] += n_new;      // root-expansion wave: no path, the leaf is the root
     if (plen > 0) {
         // every path node's update depends only on its own W / N and on the sign the value has at its depth (v at the leaf, negated once per
         // level up): one node per lane instead of a serial walk — the same fp32 operations per node, in the same order
-        const int* path = wb.path + (size_t)t * MAX_DEPTH;
         const float vl = (float)sp.virtual_loss;
         for (int j = lane; j < plen; j += 32) {
-            const size_t c = base + path[j];
+            const size_t c = base + (j == lane ? pj : path[j]);
             const float cv = ((plen - 1 - j) & 1) ? -v : v;
-            float wv = tp.W[c]; const int nv = tp.N[c]; const int sv = tp.sub[c];       // the three loads together, then the stores
+            float wv; int nv, sv;
+            if (j == lane) { wv = pW; nv = pN; sv = pS; }                                // fetched ahead of the expansion
+            else { wv = tp.W[c]; nv = tp.N[c]; sv = tp.sub[c]; }                         // paths deeper than 32 nodes: the three loads together, then the stores
             if (j == 0) { wv = fsub(wv, vl); wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv);
                           tp.N[c] = nv + sp.virtual_loss + 1; tp.root_vl[t] += sp.virtual_loss; }
             else { wv = fsub(wv, vl); wv = fadd(wv, vl); wv = fadd(wv, cv); tp.N[c] = nv + 1; }
