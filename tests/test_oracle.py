@@ -129,6 +129,49 @@ def test_oracle_matches_reference_live():
             O.mcts_update_with_move(mo, x); R.mcts_update_with_move(mr, y)
 
 
+@pytest.mark.skipif(not _orc.have_ref(), reason="oracle/_ref not built")
+def test_oracle_matches_reference_live_other_boards():
+    """The board sizes the GPU tests compare with the restatement only (Go 13x13 and 19x19 — BASELINE configs[3] —, Gomoku 9x9): lock-step
+    random playouts (legal order, terminal flag, result, planes, key on every position) and serial searches from mid-game positions,
+    oracle vs the patched reference, bit for bit."""
+    O, R = _orc.oracle(), _orc.reference()
+    rng = np.random.default_rng(23)
+    for game, n, ngames, plies in [(GO, 13, 2, 260), (GO, 19, 1, 420), (GOMOKU, 9, 6, 81)]:
+        for _ in range(ngames):
+            so, sr = O.new_state(game, n), R.new_state(game, n)
+            for ply in range(plies):
+                lo, lr = O.legal(so), R.legal(sr)
+                assert np.array_equal(lo, lr), (game, n, ply)
+                assert O.state_is_terminal(so) == R.state_is_terminal(sr)
+                assert O.state_result(so) == R.state_result(sr)
+                if ply % 7 == 0:
+                    assert np.array_equal(O.tensor(so), R.tensor(sr)), (game, n, ply)
+                assert O.state_key(so) == R.state_key(sr)
+                if O.state_is_terminal(so):
+                    break
+                cand = lo[1:] if (game == GO and len(lo) > 1 and rng.random() > 0.02) else lo
+                a = int(rng.choice(cand))
+                assert O.state_make_move(so, a) == 0 and R.state_make_move(sr, a) == 0
+    for game, n, sims, opening in [(GO, 13, 400, 60), (GO, 19, 300, 150), (GOMOKU, 9, 200, 8)]:
+        so, sr = O.new_state(game, n), R.new_state(game, n)
+        for _ in range(opening):
+            l = O.legal(so); R.legal(sr)
+            a = int(rng.choice(l[1:] if game == GO else l))
+            assert O.state_make_move(so, a) == 0 and R.state_make_move(sr, a) == 0
+        assert not O.state_is_terminal(so)
+        mo, mr = O.mcts_new(so, sims, 1.5, 3, 0, None, None), R.mcts_new(sr, sims, 1.5, 3, 0, None, None)
+        for mv in range(2):
+            O.mcts_search(mo); R.mcts_search(mr)
+            a, b = O.root_stats(mo), R.root_stats(mr)
+            for k in ("actions", "N"):
+                assert np.array_equal(a[k], b[k]), (game, n, k, mv)
+            assert bits(a["W"]) == bits(b["W"]) and bits(a["P"]) == bits(b["P"]), (game, n, mv)
+            assert a["rootN"] == b["rootN"]
+            x, y = O.mcts_select_action(mo, 1, 1.0), R.mcts_select_action(mr, 1, 1.0)
+            assert x == y
+            O.mcts_update_with_move(mo, x); R.mcts_update_with_move(mr, y)
+
+
 # ------------------------------------------------------------------ reference gtest known answers
 def _checkers():
     ks = [_orc.oracle()]
