@@ -161,9 +161,20 @@ std::optional<int> GomokuState::stringToAction(const std::string& s) const {
     if (x < 0 || x >= board_size || y < 0 || y >= board_size) return std::nullopt;
     return x * board_size + y;
 }
-std::string GomokuState::toString() const {
+// Column letters of the board printouts: A, B, ... with 'I' left out (gomoku_state.cpp:319-325, go_state.cpp:523-530)
+char boardColumnLetter(int i) { const char c = (char)('A' + i); return c >= 'I' ? (char)(c + 1) : c; }
+std::string GomokuState::toString() const {                   // layout of gomoku_state.cpp:316-358, character for character
     std::ostringstream ss;
-    for (int x = 0; x < board_size; ++x) { for (int y = 0; y < board_size; ++y) ss << ".XO"[cells_[x * board_size + y]] << ' '; ss << '\n'; }
+    auto header = [&]() { ss << "  "; for (int y = 0; y < board_size; ++y) ss << ' ' << boardColumnLetter(y); ss << '\n'; };
+    header();
+    for (int x = 0; x < board_size; ++x) {
+        const int row = board_size - x;
+        ss << (row < 10 ? " " : "") << row << ' ';
+        for (int y = 0; y < board_size; ++y) ss << ".XO"[cells_[x * board_size + y]] << ' ';
+        ss << row << '\n';
+    }
+    header();
+    ss << "Current player: " << (current_player == 1 ? "Black (X)" : "White (O)") << '\n';
     return ss.str();
 }
 bool GomokuState::equals(const core::IGameState& o) const {
@@ -195,6 +206,7 @@ struct GoState::Impl {
     virtual uint64_t key() const = 0;
     virtual uint64_t posHash() const = 0;
     virtual void planes(std::vector<std::vector<std::vector<float>>>& t) const = 0;
+    virtual void scores(float& black, float& white) const = 0;      // area scores, komi included (GoRules::calculateScores, go_rules.cpp:313-359)
 };
 
 template <int N>
@@ -224,6 +236,21 @@ struct GoImpl : GoState::Impl {
     int ko() const override { return c.ko; }
     uint64_t key() const override { return G::key_core(c); }
     uint64_t posHash() const override { return G::pos_key(c.key, c.player, c.ko); }
+    void scores(float& black, float& white) const override {      // the two sums G::score compares (stones + empty regions bordered by one colour only)
+        const auto valid = G::valid_bb();
+        typename G::BB empty;
+        for (int i = 0; i < G::NW; ++i) empty.w[i] = valid.w[i] & ~(c.bb[0].w[i] | c.bb[1].w[i]);
+        int bs = G::popc(c.bb[0]), ws = G::popc(c.bb[1]);
+        while (G::any(empty)) {
+            typename G::BB seed = G::zero(); G::setb(seed, G::lowest(empty));
+            const auto reg = G::flood(seed, empty, valid);
+            const auto edge = G::nb(reg, valid);
+            uint64_t tb = 0, tw = 0;
+            for (int i = 0; i < G::NW; ++i) { tb |= edge.w[i] & c.bb[0].w[i]; tw |= edge.w[i] & c.bb[1].w[i]; empty.w[i] &= ~reg.w[i]; }
+            if (tb && !tw) bs += G::popc(reg); else if (tw && !tb) ws += G::popc(reg);
+        }
+        black = (float)bs; white = (float)ws + G::KOMI;
+    }
     void planes(std::vector<std::vector<std::vector<float>>>& t) const override {      // go_state.cpp:349-445, index [plane][y][x]
         t.assign(8, std::vector<std::vector<float>>(N, std::vector<float>(N, 0.0f)));
         const auto valid = G::valid_bb();
@@ -248,18 +275,22 @@ GoState::GoState(int bs, float komi, bool chinese_rules, bool enforce_superko) :
     if (komi != 7.5f || !chinese_rules || !enforce_superko) throw core::GameStateException("only komi 7.5 / Chinese rules / superko are built into the B200 engine");
     impl_ = makeGoImpl(bs);
 }
-GoState::GoState(const GoState& o) : IGameState(core::GameType::GO), board_size_(o.board_size_), impl_(o.impl_->clone()), move_history_(o.move_history_) {}
+GoState::GoState(const GoState& o) : IGameState(core::GameType::GO), board_size_(o.board_size_), impl_(o.impl_->clone()), move_history_(o.move_history_) { captured_[1] = o.captured_[1]; captured_[2] = o.captured_[2]; }
 GoState::~GoState() = default;
 std::vector<int> GoState::getLegalMoves() const { return impl_->legal(); }
 bool GoState::isLegalMove(int a) const { return impl_->isLegal(a); }
 void GoState::makeMove(int a) {                               // go_state.cpp:190-261
+    const int mover = impl_->player();
+    auto opponentStones = [&]() { int n = 0; for (int p = 0; p < board_size_ * board_size_; ++p) n += impl_->stone(p) == 3 - mover; return n; };
+    const int before = a >= 0 ? opponentStones() : 0;
     if (!impl_->apply(a)) throw core::IllegalMoveException("Illegal move attempted", a);
+    if (a >= 0) captured_[mover] += before - opponentStones();          // captured_stones_[current_player_] += capturedStones (:245)
     move_history_.push_back(a);
 }
 bool GoState::undoMove() {                                    // replay (the bitboard state keeps no undo stack)
     if (move_history_.empty()) return false;
     std::vector<int> h(move_history_.begin(), move_history_.end() - 1);
-    impl_ = makeGoImpl(board_size_); move_history_.clear();
+    impl_ = makeGoImpl(board_size_); move_history_.clear(); captured_[1] = captured_[2] = 0;
     for (int a : h) makeMove(a);
     return true;
 }
@@ -289,10 +320,42 @@ std::optional<int> GoState::stringToAction(const std::string& s) const {
     if (x < 0 || x >= board_size_ || y < 0 || y >= board_size_) return std::nullopt;
     return y * board_size_ + x;
 }
-std::string GoState::toString() const {
-    std::ostringstream o;
-    for (int y = 0; y < board_size_; ++y) { for (int x = 0; x < board_size_; ++x) o << ".XO"[getStone(y * board_size_ + x)]; o << "\n"; }
-    return o.str();
+std::string GoState::toString() const {                       // layout of go_state.cpp:519-603 (no dead-stone marks: nothing in the self-play path sets them)
+    std::ostringstream ss;
+    auto header = [&]() { ss << "   "; for (int x = 0; x < board_size_; ++x) ss << gomoku::boardColumnLetter(x) << ' '; ss << '\n'; };
+    header();
+    const int ko = getKoPoint();
+    for (int y = 0; y < board_size_; ++y) {
+        ss << std::setw(2) << (board_size_ - y) << ' ';
+        for (int x = 0; x < board_size_; ++x) {
+            const int pos = y * board_size_ + x, st = getStone(pos);
+            ss << (st == 1 ? "X " : st == 2 ? "O " : pos == ko ? "k " : ". ");
+        }
+        ss << (board_size_ - y) << '\n';
+    }
+    header();
+    ss << "Current player: " << (getCurrentPlayer() == 1 ? "Black" : "White") << '\n';
+    ss << "Captures - Black: " << captured_[1] << ", White: " << captured_[2] << '\n';
+    ss << "Komi: " << 7.5f << '\n' << "Rules: Chinese" << '\n' << "Superko enforcement: Yes" << '\n';
+    if (isTerminal()) {
+        float b = 0.0f, w = 0.0f; impl_->scores(b, w);
+        ss << "Game over!" << '\n' << "Final score - Black: " << b << ", White: " << w << " (with komi " << 7.5f << ")" << '\n';
+        if (b > w) ss << "Black wins by " << (b - w) << " points" << '\n';
+        else if (w > b) ss << "White wins by " << (w - b) << " points" << '\n';
+        else ss << "Game ended in a draw" << '\n';
+    }
+    return ss.str();
+}
+std::vector<std::vector<std::vector<float>>> GoState::getTensorRepresentation() const {      // go_state.cpp:349-378: black, white, side to move
+    std::vector<std::vector<std::vector<float>>> t(3, std::vector<std::vector<float>>(board_size_, std::vector<float>(board_size_, 0.0f)));
+    const float turn = getCurrentPlayer() == 1 ? 1.0f : 0.0f;
+    for (int y = 0; y < board_size_; ++y)
+        for (int x = 0; x < board_size_; ++x) {
+            const int st = getStone(y * board_size_ + x);
+            if (st == 1) t[0][y][x] = 1.0f; else if (st == 2) t[1][y][x] = 1.0f;
+            t[2][y][x] = turn;
+        }
+    return t;
 }
 bool GoState::equals(const core::IGameState& o) const {
     auto* g = dynamic_cast<const GoState*>(&o);
@@ -365,10 +428,50 @@ std::optional<int> ChessState::stringToAction(const std::string& s) const {
     if (s.size() >= 5) { const char c = (char)std::tolower((unsigned char)s[4]); pc = c == 'q' ? 1 : c == 'r' ? 2 : c == 'b' ? 3 : c == 'n' ? 4 : 0; }
     return (pc << 12) | (from << 6) | to;
 }
-std::string ChessState::toString() const {
-    std::ostringstream o; const char* names = ".pnbrqk";
-    for (int r = 0; r < 8; ++r) { for (int f = 0; f < 8; ++f) { const int p = impl_->s.c.b[r * 8 + f]; char c = names[p & 7]; if ((p >> 3) == 1) c = (char)std::toupper((unsigned char)c); o << c; } o << "\n"; }
-    return o.str();
+std::string ChessState::toFEN() const {                       // chess_state.cpp:270-378 (standard castling letters)
+    std::ostringstream ss; const char* names = ".pnbrqk";
+    const auto& c = impl_->s.c;
+    for (int r = 0; r < 8; ++r) {
+        int run = 0;
+        for (int f = 0; f < 8; ++f) {
+            const int p = c.b[r * 8 + f];
+            if (!p) { ++run; continue; }
+            if (run) { ss << run; run = 0; }
+            char ch = names[p & 7]; if ((p >> 3) == 1) ch = (char)std::toupper((unsigned char)ch);
+            ss << ch;
+        }
+        if (run) ss << run;
+        if (r < 7) ss << '/';
+    }
+    ss << ' ' << (c.player == 1 ? 'w' : 'b') << ' ';
+    if (c.rights & az::Chess::R_WK) ss << 'K';
+    if (c.rights & az::Chess::R_WQ) ss << 'Q';
+    if (c.rights & az::Chess::R_BK) ss << 'k';
+    if (c.rights & az::Chess::R_BQ) ss << 'q';
+    if (!(c.rights & 15)) ss << '-';
+    ss << ' ' << ((c.ep >= 0 && c.ep < 64) ? sqName(c.ep) : std::string("-")) << ' ' << c.half << ' ' << (1 + c.ply / 2);
+    return ss.str();
+}
+std::string ChessState::toString() const {                    // layout of chess_state.cpp:795-867
+    std::ostringstream ss; const char* names = ".pnbrqk";
+    const auto& c = impl_->s.c;
+    ss << "  a b c d e f g h" << '\n';
+    for (int r = 0; r < 8; ++r) {
+        ss << (8 - r) << ' ';
+        for (int f = 0; f < 8; ++f) { const int p = c.b[r * 8 + f]; char ch = names[p & 7]; if ((p >> 3) == 1) ch = (char)std::toupper((unsigned char)ch); ss << ch << ' '; }
+        ss << (8 - r) << '\n';
+    }
+    ss << "  a b c d e f g h" << '\n';
+    ss << "Current player: " << (c.player == 1 ? "White" : "Black") << '\n' << "Castling rights: ";
+    if (c.rights & az::Chess::R_WK) ss << 'K';
+    if (c.rights & az::Chess::R_WQ) ss << 'Q';
+    if (c.rights & az::Chess::R_BK) ss << 'k';
+    if (c.rights & az::Chess::R_BQ) ss << 'q';
+    if (!(c.rights & 15)) ss << '-';
+    ss << '\n' << "En passant square: " << ((c.ep >= 0 && c.ep < 64) ? sqName(c.ep) : std::string("-")) << '\n';
+    ss << "Halfmove clock: " << c.half << '\n' << "Fullmove number: " << (1 + c.ply / 2) << '\n';
+    ss << "FEN: " << toFEN() << '\n';
+    return ss.str();
 }
 bool ChessState::equals(const core::IGameState& o) const {
     auto* c = dynamic_cast<const ChessState*>(&o);

@@ -143,7 +143,7 @@ public:
     int getCurrentPlayer() const override;
     int getBoardSize() const override { return board_size_; }
     int getActionSpaceSize() const override { return board_size_ * board_size_ + 1; }      // go_state.cpp:345-347
-    std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const override { return getEnhancedTensorRepresentation(); }
+    std::vector<std::vector<std::vector<float>>> getTensorRepresentation() const override;       // 3 planes: black, white, side to move (go_state.cpp:349-378)
     std::vector<std::vector<std::vector<float>>> getEnhancedTensorRepresentation() const override;
     uint64_t getHash() const override;
     std::unique_ptr<core::IGameState> clone() const override { return std::make_unique<GoState>(*this); }
@@ -161,6 +161,7 @@ private:
     int board_size_;
     std::unique_ptr<Impl> impl_;
     std::vector<int> move_history_;
+    int captured_[3] = {0, 0, 0};                // stones captured BY player 1 / 2 (captured_stones_, go_state.cpp:245)
 };
 
 }  // namespace go
@@ -191,6 +192,7 @@ public:
     std::string actionToString(int action) const override;                             // "e2e4", "e7e8q"
     std::optional<int> stringToAction(const std::string& s) const override;
     std::string toString() const override;
+    std::string toFEN() const;                                                         // chess_state.cpp:270-378
     bool equals(const core::IGameState& other) const override;
     std::vector<int> getMoveHistory() const override { return move_history_; }
     bool validate() const override { return true; }

@@ -200,6 +200,36 @@ int ref_state_tensor(void* h, float* out) {
     return (int)t.size();
 }
 uint64_t ref_state_key(void* h) { return state_key(*(IGameState*)h); }
+// the rest of the IGameState surface (include/alphazero/core/igamestate.h:60-223), for the host mirror's state classes (tests/test_pybind_cpu.py):
+// strings are copied into `out` (cap bytes, NUL-terminated), return value = the full length, -1 = the call threw
+static int copy_str(const std::string& v, char* out, int cap) {
+    if (out && cap > 0) { const int n = (int)std::min<size_t>(v.size(), (size_t)cap - 1); std::memcpy(out, v.data(), n); out[n] = 0; }
+    return (int)v.size();
+}
+int ref_state_action_to_string(void* h, int action, char* out, int cap) {
+    try { return copy_str(((IGameState*)h)->actionToString(action), out, cap); } catch (...) { return -1; }
+}
+// returns 0 and the action in *action when the string parses (std::optional has a value), 1 when it does not, -1 when the call threw
+int ref_state_string_to_action(void* h, const char* text, int* action) {
+    try { auto a = ((IGameState*)h)->stringToAction(text); if (!a) return 1; *action = *a; return 0; } catch (...) { return -1; }
+}
+int ref_state_to_string(void* h, char* out, int cap) {
+    try { return copy_str(((IGameState*)h)->toString(), out, cap); } catch (...) { return -1; }
+}
+int ref_state_undo(void* h) { try { return ((IGameState*)h)->undoMove() ? 1 : 0; } catch (...) { return -1; } }
+int ref_state_validate(void* h) { try { return ((IGameState*)h)->validate() ? 1 : 0; } catch (...) { return -1; } }
+int ref_state_equals(void* a, void* b) { try { return ((IGameState*)a)->equals(*(IGameState*)b) ? 1 : 0; } catch (...) { return -1; } }
+int ref_state_history(void* h, int* out, int cap) {
+    auto m = ((IGameState*)h)->getMoveHistory();
+    for (int i = 0; i < (int)m.size() && i < cap; ++i) out[i] = m[i];
+    return (int)m.size();
+}
+// getTensorRepresentation (the basic planes): writes C*H*W floats; returns C (out == nullptr queries C)
+int ref_state_basic_tensor(void* h, float* out) {
+    auto t = ((IGameState*)h)->getTensorRepresentation();
+    if (out) { size_t k = 0; for (auto& pl : t) for (auto& row : pl) for (float x : row) out[k++] = x; }
+    return (int)t.size();
+}
 void ref_hash_eval(void* h, float* policy, float* value) {
     IGameState* s = (IGameState*)h; hash_eval(state_key(*s), s->getActionSpaceSize(), policy, value);
 }

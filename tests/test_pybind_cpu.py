@@ -242,3 +242,60 @@ def test_python_caller_clis_accept_the_reference_arguments():
     assert o.processes == 4 and o.use_cpp_binary and o.batch_size == 8
     od = orch.parse_args([])
     assert (od.processes, od.batch_size, od.batch_timeout, od.monitor_interval, od.cache_size) == (1, 16, 10, 5, 2097152)
+
+
+@pytest.mark.skipif(not _orc.have_ref(), reason="oracle/_ref not built")
+def test_state_string_api_matches_reference_live():
+    """The rest of the IGameState surface the pybind module binds (python_bindings.cpp:57-73) — actionToString, stringToAction (incl. the
+    strings the reference accepts by accident: lower case, 'H 8', a Go prefix of 'e2e4'), toString (board printouts character for
+    character, Go's finished-game block with scores, chess castling / e.p. / clocks / FEN), getTensorRepresentation (3 / 3 / 12 planes),
+    getMoveHistory, undoMove — host mirror vs the reference's own GomokuState / GoState / ChessState on seeded random games.
+    The reference runs in a child process (tests/_ref_state_api_child.py: its static libstdc++ must not meet numpy's in one process).
+    Not reproduced, on purpose: the reference's chess undoMove does not restore the position (the undone move is refused afterwards,
+    asserted below on the reference's own output), and ChessState::actionToString prints squares for out-of-range actions."""
+    import hashlib
+    import subprocess
+    az = _mod()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ref_state_api_child.py"), _orc.ref_path()], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    recs = json.loads(out.stdout)
+    assert len(recs) == 10
+
+    def mk(game, board):
+        if game == 0:
+            return az.GomokuState(board)
+        return az.createGameState(az.GameType.GO if game == 2 else az.GameType.CHESS, board if game == 2 else 0, False)
+
+    n_strings = n_undo = 0
+    for rec in recs:
+        g, b = rec["game"], rec["board"]
+        s = mk(g, b)
+        for text, want in rec["bad"].items():
+            assert s.stringToAction(text) == want, (g, b, text)
+        for a, want in rec["bad_a2s"].items():
+            if g != 1:
+                assert s.actionToString(int(a)) == want, (g, b, a)
+        assert bool(s.undoMove()) == bool(rec["undo_on_fresh"])
+        for i, st in enumerate(rec["steps"]):
+            s.getLegalMoves()                              # the child enumerates at every ply (Gomoku's legal order depends on it, QUIRK G2)
+            for a, x, y in zip(st["pick"], st["a2s"], st["s2a"]):
+                assert s.actionToString(a) == x and s.stringToAction(x) == y == a, (g, b, i, a)
+                n_strings += 1
+            assert s.toString() == st["to_string"], (g, b, i)
+            t = np.array(s.getTensorRepresentation(), np.float32)
+            assert t.shape == (st["basic_c"], b, b) and hashlib.sha256(t.tobytes()).hexdigest()[:16] == st["basic_sha"], (g, b, i)
+            s.makeMove(st["move"])
+            h = s.getMoveHistory()
+            assert len(h) == st["history_len"] and h[-3:] == st["history_tail"], (g, b, i)
+            if "undo" in st:
+                assert st["equals_clone"] == 1 and st["equals_after_undo"] == 0 and st["remake"] == 0
+                assert bool(s.undoMove()) == bool(st["undo"])
+                assert s.getLegalMoves() == st["legal_after_undo"] and s.getCurrentPlayer() == st["player_after_undo"], (g, b, i)
+                s.makeMove(st["move"])
+                n_undo += 1
+            if "chess_undo" in st:
+                assert st["chess_undo"] == 1 and st["chess_remake"] == -1          # the reference defect, pinned as such
+        if "final_to_string" in rec:
+            s.makeMove(-1); s.makeMove(-1)
+            assert s.isTerminal() and s.toString() == rec["final_to_string"], (g, b)
+    assert n_strings > 1500 and n_undo > 30
