@@ -320,6 +320,25 @@ int ref_game_record_json(int game_type, int board_size, int variant, const int* 
     return (int)j.size();
 }
 
+// File formats: the reference's own readers / writers over files the host mirror wrote (tests/test_pybind_cpu.py; child process).
+// GameRecord::loadFromFile(in).saveToFile(out) (game_record.cpp:119-150): returns the number of moves read, -1 = threw / could not write
+int ref_game_record_file_roundtrip(const char* in, const char* out) {
+    try {
+        alphazero::selfplay::GameRecord rec = alphazero::selfplay::GameRecord::loadFromFile(in);
+        if (!rec.saveToFile(out)) return -1;
+        return (int)rec.getMoves().size();
+    } catch (...) { return -1; }
+}
+// Dataset::loadFromFile(in) + saveToFile(out) (dataset.cpp:151-216): returns the number of examples read, -1 = load or save failed
+int ref_dataset_file_roundtrip(const char* in, const char* out) {
+    try {
+        alphazero::selfplay::Dataset d;
+        if (!d.loadFromFile(in)) return -1;
+        if (!d.saveToFile(out)) return -1;
+        return (int)d.size();
+    } catch (...) { return -1; }
+}
+
 // ---------------------------------------------------------------- search API
 // evaluator: 0 = HashEvaluator, 1 = CallbackEvaluator(cb,user), 2 = HashEvaluator with a peaked policy
 void* ref_mcts_new(void* state, int sims, float cpuct, int virtual_loss, int evaluator, eval_cb_t cb, void* user) {

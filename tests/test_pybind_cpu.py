@@ -299,3 +299,45 @@ def test_state_string_api_matches_reference_live():
             s.makeMove(-1); s.makeMove(-1)
             assert s.isTerminal() and s.toString() == rec["final_to_string"], (g, b)
     assert n_strings > 1500 and n_undo > 30
+
+
+@pytest.mark.skipif(not _orc.have_ref(), reason="oracle/_ref not built")
+def test_game_record_and_dataset_files_roundtrip_through_the_reference(tmp_path):
+    """Files written by the host mirror (GameRecord::saveToFile, game_record.cpp:119-131; Dataset::saveToFile, dataset.cpp:151-188) are read
+    by the reference's own loaders and written back by its own writers BYTE-identically, and the mirror reads the reference's files back to the
+    same records — existing data directories stay readable in both directions.  (Reference in a child process, standard library only.)"""
+    import random
+    import subprocess
+    az = _mod()
+    rng = random.Random(1)
+
+    def ref_roundtrip(fn, src, dst):
+        code = "import ctypes as C, sys; lib = C.CDLL(sys.argv[1]); print(getattr(lib, sys.argv[2])(sys.argv[3].encode(), sys.argv[4].encode()))"
+        out = subprocess.run([sys.executable, "-c", code, _orc.ref_path(), fn, str(src), str(dst)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-1000:]
+        return int(out.stdout.strip())
+
+    for gt, board, acts in ((az.GameType.GOMOKU, 15, 225), (az.GameType.GO, 9, 82), (az.GameType.CHESS, 8, 20480)):
+        rec = az.GameRecord(gt, board, False)
+        n = rng.randrange(3, 12)
+        for _ in range(n):
+            rec.addMove(rng.randrange(-1 if gt == az.GameType.GO else 0, acts - 1), [rng.random() for _ in range(rng.randrange(1, 9))], rng.random() * 2 - 1, rng.randrange(5000))
+        rec.setResult(az.GameResult.WIN_PLAYER2)
+        a, b = tmp_path / f"rec_{board}_a.json", tmp_path / f"rec_{board}_b.json"
+        assert rec.saveToFile(str(a))
+        assert ref_roundtrip("ref_game_record_file_roundtrip", a, b) == n
+        assert a.read_bytes() == b.read_bytes()
+        back = az.GameRecord.loadFromFile(str(b))
+        assert [m.action for m in back.getMoves()] == [m.action for m in rec.getMoves()] and back.getResult() == rec.getResult()
+        assert [m.policy for m in back.getMoves()] == [m.policy for m in rec.getMoves()]
+    ex = [{"state": [[[float(rng.random() < 0.5) for _ in range(3)] for _ in range(3)] for _ in range(4)], "policy": [rng.random() for _ in range(10)], "value": v}
+          for v in (-1.0, 0.0, 1.0, 0.5)]
+    c, e, f = tmp_path / "c.json", tmp_path / "e.json", tmp_path / "f.json"
+    c.write_text(json.dumps({"examples": ex}))
+    ds = az.Dataset()
+    assert ds.loadFromFile(str(c)) and ds.size() == 4 and ds.saveToFile(str(e))
+    assert ref_roundtrip("ref_dataset_file_roundtrip", e, f) == 4
+    assert e.read_bytes() == f.read_bytes()
+    ds2 = az.Dataset()
+    assert ds2.loadFromFile(str(f)) and ds2.size() == 4 and sorted(ds2.getBatch(4)[2]) == sorted(ds.getBatch(4)[2]) == [-1.0, 0.0, 0.5, 1.0]      # getBatch draws at random
+    assert ref_roundtrip("ref_dataset_file_roundtrip", tmp_path / "missing.json", f) == -1
