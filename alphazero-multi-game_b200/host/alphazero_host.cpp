@@ -1014,6 +1014,7 @@ std::vector<GameRecord> SelfPlayManager::generateGames(core::GameType gameType, 
     c.deterministic = deterministic_ ? 1 : 0; c.dirichlet_alpha = dirichletAlpha_; c.dirichlet_epsilon = dirichletEpsilon_;
     c.init_temperature = initialTemperature_; c.final_temperature = finalTemperature_; c.temperature_drop_move = temperatureDropMove_; c.auto_restart = 1;
     c.sample_ring_capacity = gameType == core::GameType::CHESS ? c.n_slots * 512 : c.n_slots * bs * bs * (gameType == core::GameType::GO ? 2 : 1);   // move caps: 512 / 2 N^2 / N^2
+    if (mctsConfig_.transpositionTableSize <= 0) c.eval_cache_entries = -1;      // no TranspositionTable (self_play --no-tt): no device evaluation cache
     if (saveGames_) std::filesystem::create_directories(outputDir_);
     if (devices_.size() > 1) return generateGamesMultiGpu(gameType, bs, c);
     if (devices_.size() == 1) c.device = devices_[0];

@@ -62,7 +62,8 @@ void usage() {
                  "  --virtual-loss VALUE  Virtual loss amount (default: 3)\n"
                  "  --deterministic       Noise off, first max-visit move (parity runs)\n"
                  "  accepted for compatibility, no effect: --threads --batch-size --batch-timeout --no-batched-search --fp16\n"
-                 "                                         --fpu-reduction --use-tt --progressive-widening\n"
+                 "                                         --fpu-reduction --progressive-widening\n"
+                 "  --no-tt               No transposition table = no device evaluation cache (results are identical either way)\n"
                  "  not supported (error): --no-gpu, --variant\n"
                  "  --help                Display this help message\n";
 }
@@ -87,7 +88,7 @@ int main(int argc, char** argv) {
         const int batchSize = a.num("batch-size", 8), batchTimeout = a.num("batch-timeout", 10);
         const float cPuct = a.flt("c-puct", 1.5f), fpu = a.flt("fpu-reduction", 0.1f);
         const int virtualLoss = a.num("virtual-loss", 3);
-        const bool useTT = a.flag("use-tt", true), pw = a.flag("progressive-widening", false), fp16 = a.flag("fp16", false);
+        const bool useTT = !a.has("no-tt") && a.flag("use-tt", true), pw = a.flag("progressive-widening", false), fp16 = a.flag("fp16", false);
 
         std::filesystem::create_directories(outputDir);
         std::cout << "Loading model from " << modelPath << std::endl;
@@ -104,6 +105,7 @@ int main(int argc, char** argv) {
         if (a.flag("deterministic", false)) sp.setDeterministic(true);
         mcts::MCTSConfig mc; mc.numSimulations = sims; mc.cPuct = cPuct; mc.fpuReduction = fpu; mc.virtualLoss = virtualLoss;
         mc.useDirichletNoise = true; mc.dirichletAlpha = alpha; mc.dirichletEpsilon = eps; mc.useProgressiveWidening = pw;
+        if (!useTT) mc.transpositionTableSize = 0;      // --no-tt (what the reference's main tests, selfplay_main.cpp:188): no evaluation cache
         sp.setMctsConfig(mc);
         sp.setProgressCallback([](int gameId, int moves, int totalGames, int totalMoves) {
             std::cout << "Game " << (gameId + 1) << "/" << totalGames << " finished after " << moves << " moves (total moves played: " << totalMoves << ")" << std::endl;
