@@ -159,6 +159,12 @@ PYBIND11_MODULE(_alphazero_cpp, m) {
             geti("virtualLoss", c.virtualLoss); getb("useDirichletNoise", c.useDirichletNoise); getf("dirichletAlpha", c.dirichletAlpha);
             getf("dirichletEpsilon", c.dirichletEpsilon); getb("useBatchInference", c.useBatchInference); getb("useBatchedMCTS", c.useBatchedMCTS);
             geti("batchSize", c.batchSize); geti("batchTimeoutMs", c.batchTimeoutMs);
+            getb("useTemporalDifference", c.useTemporalDifference); getb("useProgressiveWidening", c.useProgressiveWidening); getb("useFmapCache", c.useFmapCache);
+            if (d.contains("searchMode") && py::isinstance<py::str>(d["searchMode"])) {      // python_bindings.cpp:436-444 (every mode runs the wave engine)
+                const std::string m = d["searchMode"].cast<std::string>();
+                if (m == "SERIAL") c.searchMode = mcts::MCTSSearchMode::SERIAL; else if (m == "PARALLEL") c.searchMode = mcts::MCTSSearchMode::PARALLEL;
+                else if (m == "BATCHED") c.searchMode = mcts::MCTSSearchMode::BATCHED;
+            }
             self.setMctsConfig(c);
         })
         .def("getCompletedGamesCount", &selfplay::SelfPlayManager::getCompletedGamesCount).def("getTotalMovesCount", &selfplay::SelfPlayManager::getTotalMovesCount)
