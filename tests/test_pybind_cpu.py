@@ -344,3 +344,17 @@ def test_game_record_and_dataset_files_roundtrip_through_the_reference(tmp_path)
     ds2 = az.Dataset()
     assert ds2.loadFromFile(str(f)) and ds2.size() == 4 and sorted(ds2.getBatch(4)[2]) == sorted(ds.getBatch(4)[2]) == [-1.0, 0.0, 0.5, 1.0]      # getBatch draws at random
     assert ref_roundtrip("ref_dataset_file_roundtrip", tmp_path / "missing.json", f) == -1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python/alphazero"), reason="reference tree not present")
+def test_reference_python_package_imports_against_this_module():
+    """python/alphazero/__init__.py:12-28 of the reference does `from _alphazero_cpp import (GameType, ..., SelfPlayManager)` and then imports its
+    own Python sub-packages: with this repo's module first on the path the reference's package imports unchanged (child process: it must
+    not pick up a module imported earlier in this one)."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, sys.argv[1]); sys.path.insert(0, '/root/reference/python'); import alphazero, _alphazero_cpp; "
+            "assert alphazero.SelfPlayManager is _alphazero_cpp.SelfPlayManager and alphazero.ParallelMCTS is _alphazero_cpp.ParallelMCTS; "
+            "assert _alphazero_cpp.__file__.startswith(sys.argv[1]); print(alphazero.__version__)")
+    _mod()
+    out = subprocess.run([sys.executable, "-c", code, PKG], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "1.0.0", out.stderr[-1500:]
