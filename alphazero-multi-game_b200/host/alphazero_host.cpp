@@ -52,6 +52,20 @@ std::unique_ptr<IGameState> createGameState(GameType type, int boardSize, bool v
     }
     throw GameStateException("Failed to create game state: unknown game type");
 }
+std::unique_ptr<IGameState> GameFactory::createGomokuState(int boardSize, bool useRenju, bool useOmok, int seed, bool useProLongOpening) {
+    return std::make_unique<gomoku::GomokuState>(boardSize, useRenju, useOmok, seed, useProLongOpening);
+}
+std::unique_ptr<IGameState> GameFactory::createChessState(bool chess960, const std::string& fen) { return std::make_unique<chess::ChessState>(chess960, fen); }
+std::unique_ptr<IGameState> GameFactory::createGoState(int boardSize, float komi, bool chineseRules) { return std::make_unique<go::GoState>(boardSize, komi, chineseRules); }
+bool GameFactory::isGameSupported(GameType type) { return type == GameType::GOMOKU || type == GameType::CHESS || type == GameType::GO; }
+int GameFactory::getDefaultBoardSize(GameType type) {            // game_factory.cpp:80-87
+    switch (type) {
+        case GameType::GOMOKU: return 15;
+        case GameType::CHESS: return 8;
+        case GameType::GO: return 19;
+        default: throw std::invalid_argument("Unsupported game type");
+    }
+}
 }  // namespace core
 
 // ================================================================================================ gomoku
@@ -65,6 +79,9 @@ GomokuState::GomokuState(int bs, bool use_renju, bool use_omok, int, bool use_pr
     if (bs < 5 || bs > 19) throw core::GameStateException("unsupported board size");
 }
 bool GomokuState::is_occupied(int a) const { return a < 0 || a >= (int)cells_.size() || cells_[a] != 0; }
+bool GomokuState::is_bit_set(int player_index, int a) const noexcept { return a >= 0 && a < (int)cells_.size() && cells_[a] == player_index + 1; }
+int GomokuState::count_total_stones() const noexcept { int n = 0; for (int8_t c : cells_) n += c != 0; return n; }
+bool GomokuState::board_equal(const GomokuState& o) const { return o.board_size == board_size && o.current_player == current_player && o.cells_ == cells_; }
 
 std::vector<int> GomokuState::getLegalMoves() const {       // gomoku_state.cpp:518-566 (QUIRK G2: set iteration order)
     if (valid_moves_dirty_) {
@@ -206,7 +223,7 @@ struct GoState::Impl {
     virtual uint64_t key() const = 0;
     virtual uint64_t posHash() const = 0;
     virtual void planes(std::vector<std::vector<std::vector<float>>>& t) const = 0;
-    virtual void scores(float& black, float& white) const = 0;      // area scores, komi included (GoRules::calculateScores, go_rules.cpp:313-359)
+    virtual void scores(float& black, float& white) const = 0;      // area scores before komi (GoRules::calculateScores, go_rules.cpp:313-359)
 };
 
 template <int N>
@@ -249,7 +266,7 @@ struct GoImpl : GoState::Impl {
             for (int i = 0; i < G::NW; ++i) { tb |= edge.w[i] & c.bb[0].w[i]; tw |= edge.w[i] & c.bb[1].w[i]; empty.w[i] &= ~reg.w[i]; }
             if (tb && !tw) bs += G::popc(reg); else if (tw && !tb) ws += G::popc(reg);
         }
-        black = (float)bs; white = (float)ws + G::KOMI;
+        black = (float)bs; white = (float)ws;
     }
     void planes(std::vector<std::vector<std::vector<float>>>& t) const override {      // go_state.cpp:349-445, index [plane][y][x]
         t.assign(8, std::vector<std::vector<float>>(N, std::vector<float>(N, 0.0f)));
@@ -272,10 +289,12 @@ static std::unique_ptr<GoState::Impl> makeGoImpl(int n) {
 }
 
 GoState::GoState(int bs, float komi, bool chinese_rules, bool enforce_superko) : IGameState(core::GameType::GO), board_size_(bs) {
-    if (komi != 7.5f || !chinese_rules || !enforce_superko) throw core::GameStateException("only komi 7.5 / Chinese rules / superko are built into the B200 engine");
+    // the state class scores with any komi (host arithmetic); the engine itself is built for komi 7.5 (ParallelMCTS / SelfPlayManager check it)
+    if (!chinese_rules || !enforce_superko) throw core::GameStateException("only Chinese rules with positional superko are provided");
+    komi_ = komi;
     impl_ = makeGoImpl(bs);
 }
-GoState::GoState(const GoState& o) : IGameState(core::GameType::GO), board_size_(o.board_size_), impl_(o.impl_->clone()), move_history_(o.move_history_) { captured_[1] = o.captured_[1]; captured_[2] = o.captured_[2]; }
+GoState::GoState(const GoState& o) : IGameState(core::GameType::GO), board_size_(o.board_size_), impl_(o.impl_->clone()), move_history_(o.move_history_), komi_(o.komi_) { captured_[1] = o.captured_[1]; captured_[2] = o.captured_[2]; }
 GoState::~GoState() = default;
 std::vector<int> GoState::getLegalMoves() const { return impl_->legal(); }
 bool GoState::isLegalMove(int a) const { return impl_->isLegal(a); }
@@ -295,7 +314,11 @@ bool GoState::undoMove() {                                    // replay (the bit
     return true;
 }
 bool GoState::isTerminal() const { return impl_->terminal(); }
-core::GameResult GoState::getGameResult() const { return static_cast<core::GameResult>(impl_->result()); }
+core::GameResult GoState::getGameResult() const {            // go_state.cpp:315-335: area scores once two passes ended the game
+    if (!impl_->terminal()) return core::GameResult::ONGOING;
+    float b = 0.0f, w = 0.0f; impl_->scores(b, w); w += komi_;
+    return b > w ? core::GameResult::WIN_PLAYER1 : (w > b ? core::GameResult::WIN_PLAYER2 : core::GameResult::DRAW);
+}
 int GoState::getCurrentPlayer() const { return impl_->player(); }
 std::vector<std::vector<std::vector<float>>> GoState::getEnhancedTensorRepresentation() const { std::vector<std::vector<std::vector<float>>> t; impl_->planes(t); return t; }
 uint64_t GoState::getHash() const { return impl_->posHash(); }
@@ -336,10 +359,10 @@ std::string GoState::toString() const {                       // layout of go_st
     header();
     ss << "Current player: " << (getCurrentPlayer() == 1 ? "Black" : "White") << '\n';
     ss << "Captures - Black: " << captured_[1] << ", White: " << captured_[2] << '\n';
-    ss << "Komi: " << 7.5f << '\n' << "Rules: Chinese" << '\n' << "Superko enforcement: Yes" << '\n';
+    ss << "Komi: " << komi_ << '\n' << "Rules: Chinese" << '\n' << "Superko enforcement: Yes" << '\n';
     if (isTerminal()) {
-        float b = 0.0f, w = 0.0f; impl_->scores(b, w);
-        ss << "Game over!" << '\n' << "Final score - Black: " << b << ", White: " << w << " (with komi " << 7.5f << ")" << '\n';
+        float b = 0.0f, w = 0.0f; impl_->scores(b, w); w += komi_;
+        ss << "Game over!" << '\n' << "Final score - Black: " << b << ", White: " << w << " (with komi " << komi_ << ")" << '\n';
         if (b > w) ss << "Black wins by " << (b - w) << " points" << '\n';
         else if (w > b) ss << "White wins by " << (w - b) << " points" << '\n';
         else ss << "Game ended in a draw" << '\n';
@@ -372,10 +395,59 @@ namespace chess {
 struct ChessState::Impl { az::Chess::State s; };
 
 ChessState::ChessState(bool chess960, const std::string& fen, int) : IGameState(core::GameType::CHESS), impl_(new Impl()) {
-    if (chess960 || !fen.empty()) throw core::GameStateException("Chess960 / FEN set-up are out of scope of the B200 engine (standard initial position only)");
+    if (chess960) throw core::GameStateException("Chess960 set-up is not provided (the reference's own fails for its default position, DESIGN.md 9)");
     az::Chess::init(impl_->s);
+    if (!fen.empty() && !setFromFEN(fen)) throw core::GameStateException("Invalid FEN string");       // chess_state.cpp:118-122
 }
-ChessState::ChessState(const ChessState& o) : IGameState(core::GameType::CHESS), impl_(new Impl(*o.impl_)), move_history_(o.move_history_) {}
+Piece ChessState::getPiece(int sq) const {
+    Piece p; const int c = getPieceCode(sq);
+    if (c) { p.type = static_cast<PieceType>(c & 7); p.color = static_cast<PieceColor>(c >> 3); }
+    return p;
+}
+CastlingRights ChessState::getCastlingRights() const {
+    const int r = impl_->s.c.rights; CastlingRights cr;
+    cr.white_kingside = r & az::Chess::R_WK; cr.white_queenside = r & az::Chess::R_WQ; cr.black_kingside = r & az::Chess::R_BK; cr.black_queenside = r & az::Chess::R_BQ;
+    return cr;
+}
+int ChessState::getEnPassantSquare() const { return impl_->s.c.ep; }
+int ChessState::getHalfmoveClock() const { return impl_->s.c.half; }
+int ChessState::getFullmoveNumber() const { return 1 + impl_->s.c.ply / 2; }
+// chess_state.cpp:382-495: six fields; a malformed string returns false (the reference leaves a half-filled board behind; this one keeps the old
+// position).  The position becomes the first entry of the repetition history (recordPosition()), the move history starts empty.
+bool ChessState::setFromFEN(const std::string& fen) {
+    std::istringstream ss(fen);
+    std::string board, active, castling, ep, half, full;
+    if (!(ss >> board >> active >> castling >> ep >> half >> full)) return false;
+    az::Chess::State st;
+    az::Chess::init(st);
+    for (int sq = 0; sq < 64; ++sq) az::Chess::put(st.c, sq, 0, 0);
+    int rank = 0, file = 0;
+    for (char ch : board) {
+        if (ch == '/') { ++rank; file = 0; continue; }
+        if (std::isdigit((unsigned char)ch)) { file += ch - '0'; continue; }
+        if (file >= 8 || rank >= 8) return false;
+        int t = 0;
+        switch (std::tolower((unsigned char)ch)) { case 'p': t = 1; break; case 'n': t = 2; break; case 'b': t = 3; break; case 'r': t = 4; break; case 'q': t = 5; break; case 'k': t = 6; break; default: return false; }
+        az::Chess::put(st.c, rank * 8 + file, t, std::isupper((unsigned char)ch) ? (int)az::Chess::WHITE : (int)az::Chess::BLACK);
+        ++file;
+    }
+    st.c.player = (int8_t)(active == "w" ? az::Chess::WHITE : az::Chess::BLACK);
+    int rights = 0;
+    for (char ch : castling) rights |= ch == 'K' ? az::Chess::R_WK : ch == 'Q' ? az::Chess::R_WQ : ch == 'k' ? az::Chess::R_BK : ch == 'q' ? az::Chess::R_BQ : 0;
+    st.c.rights = (int8_t)rights;
+    st.c.ep = -1;
+    if (ep != "-") { if (ep.size() < 2 || ep[0] < 'a' || ep[0] > 'h' || ep[1] < '1' || ep[1] > '8') st.c.ep = -1; else st.c.ep = (int16_t)(('8' - ep[1]) * 8 + (ep[0] - 'a')); }
+    int hm = 0, fm = 1;
+    try { hm = std::stoi(half); fm = std::stoi(full); } catch (...) { return false; }
+    st.c.half = (int16_t)hm;
+    st.c.ply = (int16_t)(2 * std::max(fm - 1, 0) + (st.c.player == az::Chess::BLACK ? 1 : 0));
+    st.hist[0] = st.c.key; st.c.hist_n = 1;
+    impl_->s = st;
+    move_history_.clear();
+    fen_start_ = fen;
+    return true;
+}
+ChessState::ChessState(const ChessState& o) : IGameState(core::GameType::CHESS), impl_(new Impl(*o.impl_)), move_history_(o.move_history_), fen_start_(o.fen_start_) {}
 ChessState::~ChessState() = default;
 std::vector<int> ChessState::getLegalMoves() const {           // chess_state.cpp:498-510 over generateLegalMoves
     int16_t lg[az::Chess::MAX_CHILDREN]; const int n = az::Chess::host_legal(impl_->s, lg);
@@ -389,7 +461,8 @@ void ChessState::makeMove(int a) {                              // chess_state.c
 bool ChessState::undoMove() {
     if (move_history_.empty()) return false;
     std::vector<int> h(move_history_.begin(), move_history_.end() - 1);
-    az::Chess::init(impl_->s); move_history_.clear();
+    if (fen_start_.empty()) { az::Chess::init(impl_->s); move_history_.clear(); }
+    else { const std::string f = fen_start_; setFromFEN(f); }
     for (int a : h) makeMove(a);
     return true;
 }
@@ -616,6 +689,9 @@ void ParallelMCTS::build(const core::IGameState& rootState) {
     // leaves as move sequences, the states are rebuilt from the root clone and go through nn_->predictBatch (one round trip per wave).
     external_ = b == nullptr;
     rootState_ = rootState.clone();                                   // parallel_mcts.cpp:65
+    // the engine's roots are move sequences from the game's initial position under the engine's rules
+    if (auto* g = dynamic_cast<const go::GoState*>(&rootState)) if (g->getKomi() != 7.5f) throw std::runtime_error("ParallelMCTS on the B200 engine: Go is built for komi 7.5");
+    if (auto* ch = dynamic_cast<const chess::ChessState*>(&rootState)) if (ch->isFromFEN()) throw std::runtime_error("ParallelMCTS on the B200 engine: chess roots set up from a FEN are not supported (roots are move sequences from the initial position)");
     az_config c; az_config_default(&c);
     c.game = (int)rootState.getGameType(); c.board_size = rootState.getBoardSize(); c.n_slots = 1;
     c.num_simulations = config_.numSimulations; c.c_puct = config_.cPuct; c.virtual_loss = config_.virtualLoss;

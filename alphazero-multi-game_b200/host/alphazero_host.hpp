@@ -75,6 +75,17 @@ protected:
 
 std::unique_ptr<IGameState> createGameState(GameType type, int boardSize = 0, bool variantRules = false);
 
+// include/alphazero/core/game_factory.h:16-75.  The reference's factory goes through its GameRegistry, in which no game is ever registered
+// (SURVEY.md Appendix B), so at HEAD every create* call throws and isGameSupported is false for every game; this one constructs the states.
+class GameFactory {
+public:
+    static std::unique_ptr<IGameState> createGomokuState(int boardSize = 15, bool useRenju = false, bool useOmok = false, int seed = 0, bool useProLongOpening = false);
+    static std::unique_ptr<IGameState> createChessState(bool chess960 = false, const std::string& fen = "");
+    static std::unique_ptr<IGameState> createGoState(int boardSize = 19, float komi = 7.5f, bool chineseRules = true);
+    static bool isGameSupported(GameType type);
+    static int getDefaultBoardSize(GameType type);
+};
+
 }  // namespace core
 
 namespace gomoku {
@@ -107,6 +118,12 @@ public:
     bool validate() const override;
     bool is_occupied(int action) const;
     std::vector<std::vector<int>> get_board() const;
+    // the rest of the reference's public helpers (gomoku_state.h:88-117), used by its unit tests
+    bool is_bit_set(int player_index, int action) const noexcept;      // player_index 0 = BLACK, 1 = WHITE
+    int count_total_stones() const noexcept;
+    bool board_equal(const GomokuState& other) const;
+    bool isUsingRenjuRules() const { return false; }                   // Renju / Omok states cannot be constructed
+    bool isUsingOmokRules() const { return false; }
     // true until the legal moves of this lineage were enumerated once (QUIRK G2: first-fill order)
     bool neverEnumerated() const { return never_filled_; }
 
@@ -155,6 +172,13 @@ public:
     bool validate() const override { return true; }
     int getStone(int pos) const;                 // 0 empty, 1 black, 2 white; pos = y*N + x
     int getKoPoint() const;
+    // go_state.h:112-150
+    int getCapturedStones(int player) const { return (player == 1 || player == 2) ? captured_[player] : 0; }
+    float getKomi() const { return komi_; }
+    bool isChineseRules() const { return true; }
+    bool isEnforcingSuperko() const { return true; }
+    std::pair<int, int> actionToCoord(int action) const { return (action < 0 || action >= board_size_ * board_size_) ? std::pair<int, int>{-1, -1} : std::pair<int, int>{action % board_size_, action / board_size_}; }
+    int coordToAction(int x, int y) const { return (x < 0 || y < 0 || x >= board_size_ || y >= board_size_) ? -1 : y * board_size_ + x; }
     uint64_t hashEvaluatorKey() const;           // SURVEY Appendix C key (B200NeuralNetwork("hash").predict)
     struct Impl;
 private:
@@ -162,11 +186,27 @@ private:
     std::unique_ptr<Impl> impl_;
     std::vector<int> move_history_;
     int captured_[3] = {0, 0, 0};                // stones captured BY player 1 / 2 (captured_stones_, go_state.cpp:245)
+    float komi_ = 7.5f;                          // any komi for the state's own scoring; the engine is built for 7.5
 };
 
 }  // namespace go
 
 namespace chess {
+
+// include/alphazero/games/chess/chess_state.h:21-82
+enum class PieceType { NONE = 0, PAWN = 1, KNIGHT = 2, BISHOP = 3, ROOK = 4, QUEEN = 5, KING = 6 };
+enum class PieceColor { NONE = 0, WHITE = 1, BLACK = 2 };
+struct CastlingRights {
+    bool white_kingside = true, white_queenside = true, black_kingside = true, black_queenside = true;
+    bool operator==(const CastlingRights& o) const { return white_kingside == o.white_kingside && white_queenside == o.white_queenside && black_kingside == o.black_kingside && black_queenside == o.black_queenside; }
+};
+struct Piece {
+    PieceType type = PieceType::NONE;
+    PieceColor color = PieceColor::NONE;
+    bool operator==(const Piece& o) const { return type == o.type && color == o.color; }
+    bool operator!=(const Piece& o) const { return !(*this == o); }
+    bool is_empty() const { return type == PieceType::NONE; }
+};
 
 // Host-side chess state (reference chess::ChessState, include/alphazero/games/chess/chess_state.h:84-406; standard chess
 // from the initial position).  Rules arithmetic is the SAME header the kernels compile (csrc/chess.cuh, host+device),
@@ -197,12 +237,21 @@ public:
     std::vector<int> getMoveHistory() const override { return move_history_; }
     bool validate() const override { return true; }
     int getPieceCode(int square) const;          // type | colour << 3 (0 = empty)
+    // chess_state.h:150-215: square = rank * 8 + file with rank 0 = the eighth rank (the reference's getSquare)
+    Piece getPiece(int square) const;
+    CastlingRights getCastlingRights() const;
+    int getEnPassantSquare() const;
+    int getHalfmoveClock() const;
+    int getFullmoveNumber() const;
+    bool isFromFEN() const { return !fen_start_.empty(); }
+    bool setFromFEN(const std::string& fen);     // chess_state.cpp:382-495 (standard castling letters; Chess960 rook-file letters are not read)
     bool isInCheck() const;
     uint64_t hashEvaluatorKey() const;
     struct Impl;
 private:
     std::unique_ptr<Impl> impl_;
     std::vector<int> move_history_;
+    std::string fen_start_;                      // FEN the game was set up from ("" = the initial position): undoMove replays from it
 };
 
 }  // namespace chess

@@ -106,3 +106,20 @@ $CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$TMP/ref_harness.o" &
 wait
 $CXX -shared -Wl,-z,defs -o "$OUT/libaz_ref.so" $OBJS "$TMP/ref_harness.o" -pthread
 echo "build_ref: wrote $OUT/libaz_ref.so"
+
+# The reference's own unit-test sources for the state classes (tests/{games,core}/*_test.cpp), read in place and compiled UNMODIFIED with the
+# stand-in gtest of oracle/mini_gtest against the objects above: oracle/_ref/ref_state_tests prints one PASS / FAIL / CRASH line per test.
+# tests/test_ref_unit_tests.py runs it next to the same sources compiled against the B200 host mirror.
+UT="games/gomoku/gomoku_state_test.cpp games/go/go_state_test.cpp games/chess/chess_state_test.cpp core/igamestate_test.cpp core/game_factory_test.cpp"
+UTOBJ=""
+for t in $UT; do
+  o="$TMP/ut_$(echo "$t" | sed 's|/|_|g').o"
+  extra=""; case "$t" in games/chess/*) extra="-include alphazero/games/chess/chess_state.h";;
+                         core/igamestate_test.cpp) extra="-include alphazero/core/game_factory.h";; esac   # the test calls createGameState, which igamestate.h does not declare
+  $CXX $FLAGS -I"$HERE/mini_gtest" $extra -c "$REF/tests/$t" -o "$o" &
+  UTOBJ="$UTOBJ $o"
+done
+$CXX $FLAGS -I"$HERE/mini_gtest" -c "$HERE/mini_gtest/main.cpp" -o "$TMP/ut_main.o" &
+wait
+$CXX -o "$OUT/ref_state_tests" $UTOBJ "$TMP/ut_main.o" $OBJS -pthread
+echo "build_ref: wrote $OUT/ref_state_tests"
